@@ -1,0 +1,295 @@
+"""CPU oracle for the attention-LSTM caption decoder hot path.
+
+TEST INFRASTRUCTURE ONLY.  Nothing in the product package may import this module; it is used by
+`tests/`, `__graft_entry__.smoke()` and `bench.py`'s cpu_baseline / `--impl reference` legs as the
+checker and as the timed CPU port of the reference, never as the thing shipped.
+
+What it is: a plain fp32 PyTorch-on-CPU restatement, written as pure functions over a
+`state_dict`, of the reference algorithm in /root/reference/pivot_based_eccv2018:
+    models/AttModel.py     (AttModel, Attention, Att2in2Core, TopDownCore)
+    models/CaptionModel.py (beam_search)
+    misc/criterion.py      (LanguageModelCriterion)
+The arithmetic itself lives in a third-party dependency of the reference (PyTorch, un-pinned by the
+reference; here torch 2.11): nn.Linear / nn.LSTMCell / nn.Embedding / log_softmax / softmax / bmm /
+sort / max.  Each function cites the reference lines it follows.
+
+Parity pin: the reference has NO tests or golden vectors for this path.  The
+oracle is pinned instead against outputs of the unmodified reference run in the build container
+(`tests/golden/make_golden.py` imports /root/reference and writes `tests/golden/*.npz`); the
+CPU test-suite checks this file against those fixtures (`tests/test_oracle_golden.py`), and against
+the live reference when /root/reference is present (`tests/test_oracle_vs_reference.py`).
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn.functional as F
+
+KINDS = ("att2in2", "topdown")
+
+
+def num_layers(kind):
+    # models/AttModel.py:62 (att2in2 -> opt.num_layers == 1) and :689 (topdown forces 2)
+    return 2 if kind == "topdown" else 1
+
+
+def _linear(sd, prefix, x):
+    return F.linear(x, sd[prefix + ".weight"], sd[prefix + ".bias"])
+
+
+# ------------------------------------------------------------------------------------------------
+# feature prologue -- models/AttModel.py:99-117 (clip_att, _prepare_feature), :30-53 (pack_wrapper)
+# ------------------------------------------------------------------------------------------------
+def prepare_features(sd, kind, fc_feats, att_feats, att_masks=None):
+    if att_masks is not None:  # clip_att (:99-105)
+        keep = int(att_masks.long().sum(1).max())
+        att_feats = att_feats[:, :keep].contiguous()
+        att_masks = att_masks[:, :keep].contiguous()
+    if kind == "topdown":  # fc_embed = Linear+ReLU (:76-78); identity for att2in2 (:674-675)
+        fc = torch.relu(_linear(sd, "fc_embed.0", fc_feats))
+    else:
+        fc = fc_feats
+    # att_embed = Linear+ReLU (:79-84, use_bn=0, dropout off).  With masks the reference packs the
+    # valid regions, embeds them and pads the rest with ZEROS (pad_packed_sequence, :50-51).
+    att = torch.relu(_linear(sd, "att_embed.0", att_feats))
+    if att_masks is not None:
+        n_valid = att_masks.long().sum(1)
+        valid = (torch.arange(att.size(1))[None, :] < n_valid[:, None]).to(att.dtype)
+        att = att * valid[:, :, None]
+    p_att = _linear(sd, "ctx2att", att)  # :115 (bias also lands on padded rows, like the reference)
+    return fc, att, p_att, att_masks
+
+
+# ------------------------------------------------------------------------------------------------
+# additive attention -- models/AttModel.py:538-558
+# ------------------------------------------------------------------------------------------------
+def attention(sd, h, att, p_att, att_masks=None, return_weights=False):
+    att_h = _linear(sd, "core.attention.h2att", h)                      # :543
+    hidden = torch.tanh(p_att + att_h[:, None, :])                      # :544-546
+    w = sd["core.attention.alpha_net.weight"].view(-1)
+    score = hidden @ w + sd["core.attention.alpha_net.bias"]            # :548-549
+    weight = torch.softmax(score, dim=1)                                # :551
+    if att_masks is not None:                                           # :552-554
+        weight = weight * att_masks.to(weight.dtype)
+        weight = weight / weight.sum(1, keepdim=True)
+    ctx = torch.bmm(weight[:, None, :], att).squeeze(1)                 # :555-556
+    return (ctx, weight) if return_weights else ctx
+
+
+# ------------------------------------------------------------------------------------------------
+# recurrent cores
+# ------------------------------------------------------------------------------------------------
+def _lstm_cell(sd, prefix, x, h, c):
+    """torch.nn.LSTMCell, gate order i, f, g, o (used at models/AttModel.py:426-427,434,441)."""
+    gates = (F.linear(x, sd[prefix + ".weight_ih"], sd[prefix + ".bias_ih"]) +
+             F.linear(h, sd[prefix + ".weight_hh"], sd[prefix + ".bias_hh"]))
+    i, f, g, o = gates.chunk(4, dim=1)
+    c_new = torch.sigmoid(f) * c + torch.sigmoid(i) * torch.tanh(g)
+    h_new = torch.sigmoid(o) * torch.tanh(c_new)
+    return h_new, c_new
+
+
+def core_att2in2(sd, xt, fc, att, p_att, state, att_masks=None):
+    """models/AttModel.py:581-601 -- maxout LSTM whose cell input is the attended context."""
+    h_prev, c_prev = state[0][-1], state[1][-1]
+    H = h_prev.size(1)
+    ctx = attention(sd, h_prev, att, p_att, att_masks)                  # :582
+    sums = _linear(sd, "core.i2h", xt) + _linear(sd, "core.h2h", h_prev)  # :584
+    sig = torch.sigmoid(sums[:, :3 * H])                                # :585-589
+    i_g, f_g, o_g = sig[:, :H], sig[:, H:2 * H], sig[:, 2 * H:]
+    pre = sums[:, 3 * H:] + _linear(sd, "core.a2c", ctx)                # :591-592
+    g = torch.maximum(pre[:, :H], pre[:, H:])                           # :593-595
+    c = f_g * c_prev + i_g * g                                          # :596
+    h = o_g * torch.tanh(c)                                             # :597
+    return h, (h[None], c[None])                                        # :599-601 (dropout p=0)
+
+
+def core_topdown(sd, xt, fc, att, p_att, state, att_masks=None):
+    """models/AttModel.py:430-446 -- attention LSTM + language LSTM."""
+    h_lang_prev = state[0][-1]
+    x1 = torch.cat([h_lang_prev, fc, xt], 1)                            # :431-432
+    h_att, c_att = _lstm_cell(sd, "core.att_lstm", x1, state[0][0], state[1][0])    # :434
+    ctx = attention(sd, h_att, att, p_att, att_masks)                   # :436
+    x2 = torch.cat([ctx, h_att], 1)                                     # :438
+    h_lang, c_lang = _lstm_cell(sd, "core.lang_lstm", x2, state[0][1], state[1][1])  # :441
+    return h_lang, (torch.stack([h_att, h_lang]), torch.stack([c_att, c_lang]))   # :443-446
+
+
+CORES = {"att2in2": core_att2in2, "topdown": core_topdown}
+
+
+def init_hidden(sd, kind, rows):
+    # models/AttModel.py:94-97
+    H = sd["logit.weight"].size(1)
+    z = sd["logit.weight"].new_zeros(num_layers(kind), rows, H)
+    return (z, z.clone())
+
+
+def logprobs_state(sd, kind, it, fc, att, p_att, att_masks, state):
+    """models/AttModel.py:158-165: embed -> core -> logit -> log_softmax."""
+    xt = torch.relu(sd["embed.0.weight"][it])                           # :73-75,160
+    out, state = CORES[kind](sd, xt, fc, att, p_att, state, att_masks)  # :162
+    return torch.log_softmax(_linear(sd, "logit", out), dim=1), state    # :163
+
+
+# ------------------------------------------------------------------------------------------------
+# teacher-forced forward -- models/AttModel.py:119-156 (ss_prob == 0)
+# ------------------------------------------------------------------------------------------------
+def teacher_forced(sd, kind, fc_feats, att_feats, seq, att_masks=None):
+    B, T = fc_feats.size(0), seq.size(1) - 1
+    V = sd["logit.weight"].size(0)
+    state = init_hidden(sd, kind, B)
+    fc, att, p_att, masks = prepare_features(sd, kind, fc_feats, att_feats, att_masks)
+    steps = []
+    for i in range(T):
+        if i >= 1 and int(seq[:, i].sum()) == 0:                        # :148-151
+            break
+        lp, state = logprobs_state(sd, kind, seq[:, i], fc, att, p_att, masks, state)
+        steps.append(lp)
+    out = torch.stack(steps, 1)
+    if out.size(1) < T:                                                 # untouched steps stay 0 (:123)
+        out = torch.cat([out, out.new_zeros(B, T - out.size(1), V)], 1)
+    return out
+
+
+def xe_loss(logprobs, target, mask):
+    """misc/criterion.py:143-150."""
+    target = target[:, :logprobs.size(1)]
+    mask = mask[:, :logprobs.size(1)]
+    picked = logprobs.gather(2, target.unsqueeze(2)).squeeze(2)
+    return -(picked * mask).sum() / mask.sum()
+
+
+def train_loss(sd, kind, fc_feats, att_feats, labels, masks, att_masks=None):
+    """The call pattern of trainer.py:164-165."""
+    out = teacher_forced(sd, kind, fc_feats, att_feats, labels, att_masks)
+    return xe_loss(out, labels[:, 1:], masks[:, 1:])
+
+
+def loss_and_grads(sd, kind, fc_feats, att_feats, labels, masks, att_masks=None):
+    leaf = {k: v.detach().clone().requires_grad_(True) for k, v in sd.items()}
+    loss = train_loss(leaf, kind, fc_feats, att_feats, labels, masks, att_masks)
+    loss.backward()
+    grads = {k: (v.grad if v.grad is not None else torch.zeros_like(v)) for k, v in leaf.items()}
+    return loss.detach(), grads
+
+
+# ------------------------------------------------------------------------------------------------
+# greedy sampling -- models/AttModel.py:198-253 with sample_max=1
+# ------------------------------------------------------------------------------------------------
+@torch.no_grad()
+def sample_greedy(sd, kind, fc_feats, att_feats, seq_length, att_masks=None,
+                  decoding_constraint=0, return_margins=False):
+    B = fc_feats.size(0)
+    state = init_hidden(sd, kind, B)
+    fc, att, p_att, masks = prepare_features(sd, kind, fc_feats, att_feats, att_masks)
+    seq = torch.zeros(B, seq_length, dtype=torch.int64)
+    seq_lp = torch.zeros(B, seq_length)
+    margins = torch.full((B, seq_length), float("inf"))
+    it = torch.zeros(B, dtype=torch.int64)
+    unfinished = None
+    for t in range(seq_length + 1):
+        lp, state = logprobs_state(sd, kind, it, fc, att, p_att, masks, state)
+        if decoding_constraint and t > 0:                               # :220-223
+            lp = lp.clone()
+            lp.scatter_(1, seq[:, t - 1:t], float("-inf"))
+        if t == seq_length:                                             # :226-227
+            break
+        best, it = lp.max(1)                                            # :229
+        top2 = lp.topk(2, dim=1).values
+        margins[:, t] = top2[:, 0] - top2[:, 1]
+        unfinished = (it > 0) if t == 0 else unfinished & (it > 0)      # :242-245
+        it = it * unfinished.to(it.dtype)                               # :246
+        seq[:, t] = it
+        seq_lp[:, t] = best                                             # :248 (not masked)
+        if int(unfinished.sum()) == 0:                                  # :250
+            break
+    return (seq, seq_lp, margins) if return_margins else (seq, seq_lp)
+
+
+# ------------------------------------------------------------------------------------------------
+# beam search -- models/AttModel.py:167-196 + models/CaptionModel.py:33-177 (group_size == 1)
+# One image at a time with Python-side candidate bookkeeping, like the reference: this is also the
+# cost structure the CPU baseline is meant to show.
+# ------------------------------------------------------------------------------------------------
+@torch.no_grad()
+def _beam_search_one(sd, kind, state, logprobs, fc, att, p_att, masks, seq_length, beam_size,
+                     decoding_constraint, max_ppl):
+    b, T = beam_size, seq_length
+    beam_seq = torch.zeros(T, b, dtype=torch.int64)                      # CaptionModel.py:109-111
+    beam_lp = torch.zeros(T, b)
+    beam_sum = torch.zeros(b)
+    done = []
+    for t in range(T):
+        lpf = logprobs.float().clone()
+        if decoding_constraint and t > 0:                               # :130-131
+            lpf.scatter_(1, beam_seq[t - 1].unsqueeze(1), float("-inf"))
+        lpf[:, -1] -= 1000.0                                            # UNK suppression :133
+        ys, ix = torch.sort(lpf, 1, True)                               # :61
+        cands = []
+        rows = 1 if t == 0 else b                                       # :64-66
+        for c in range(min(b, ys.size(1))):                             # c-major, q-minor :67-73
+            for q in range(rows):
+                cands.append((beam_sum[q] + ys[q, c].item(), int(ix[q, c]), q, lpf[q, ix[q, c]]))
+        cands.sort(key=lambda e: -e[0])                                 # stable :74
+        new_state = [s.clone() for s in state]
+        if t >= 1:
+            prev_seq, prev_lp = beam_seq[:t].clone(), beam_lp[:t].clone()
+        for vix in range(b):                                            # :82-95
+            p, tok, q, r = cands[vix]
+            if t >= 1:
+                beam_seq[:t, vix] = prev_seq[:, q]
+                beam_lp[:t, vix] = prev_lp[:, q]
+            for s_new, s_old in zip(new_state, state):
+                s_new[:, vix] = s_old[:, q]
+            beam_seq[t, vix] = tok
+            beam_lp[t, vix] = r
+            beam_sum[vix] = p
+        state = new_state
+        for vix in range(b):                                            # :155-167
+            if int(beam_seq[t, vix]) == 0 or t == T - 1:
+                p = beam_sum[vix].item()
+                done.append({"seq": beam_seq[:, vix].clone(), "logps": beam_lp[:, vix].clone(),
+                             "unaug_p": beam_lp[:, vix].sum().item(),
+                             "p": p / (t + 1) if max_ppl else p})
+                beam_sum[vix] = -1000
+        logprobs, state = logprobs_state(sd, kind, beam_seq[t], fc, att, p_att, masks, state)  # :171-172
+    done.sort(key=lambda d: -d["p"])                                    # :175
+    return done[:b]
+
+
+@torch.no_grad()
+def sample_beam(sd, kind, fc_feats, att_feats, seq_length, beam_size=10, att_masks=None,
+                decoding_constraint=0, max_ppl=0):
+    """Returns (seq (B,T) int64, seqLogprobs (B,T) fp32, done_beams list-of-lists)."""
+    B = fc_feats.size(0)
+    fc, att, p_att, masks = prepare_features(sd, kind, fc_feats, att_feats, att_masks)
+    V = sd["logit.weight"].size(0)
+    assert beam_size <= V                                               # AttModel.py:173
+    seq = torch.zeros(seq_length, B, dtype=torch.int64)
+    seq_lp = torch.zeros(seq_length, B)
+    done_beams = []
+    for k in range(B):                                                  # AttModel.py:179
+        state = init_hidden(sd, kind, beam_size)
+        fc_k = fc[k:k + 1].expand(beam_size, fc.size(1))
+        att_k = att[k:k + 1].expand(beam_size, *att.shape[1:]).contiguous()
+        p_att_k = p_att[k:k + 1].expand(beam_size, *p_att.shape[1:]).contiguous()
+        m_k = masks[k:k + 1].expand(beam_size, masks.size(1)).contiguous() if masks is not None else None
+        it = torch.zeros(beam_size, dtype=torch.int64)
+        lp, state = logprobs_state(sd, kind, it, fc_k, att_k, p_att_k, m_k, state)   # :186-190
+        done = _beam_search_one(sd, kind, state, lp, fc_k, att_k, p_att_k, m_k, seq_length,
+                                beam_size, decoding_constraint, max_ppl)
+        done_beams.append(done)
+        seq[:, k] = done[0]["seq"]                                      # :193-194
+        seq_lp[:, k] = done[0]["logps"]
+    return seq.t(), seq_lp.t(), done_beams
+
+
+def sample(sd, kind, fc_feats, att_feats, seq_length, att_masks=None, opt=None):
+    """Dispatch of AttModel._sample (models/AttModel.py:198-205)."""
+    opt = opt or {}
+    if opt.get("beam_size", 1) > 1:
+        s, lp, _ = sample_beam(sd, kind, fc_feats, att_feats, seq_length, opt["beam_size"], att_masks,
+                               opt.get("decoding_constraint", 0), opt.get("max_ppl", 0))
+        return s, lp
+    return sample_greedy(sd, kind, fc_feats, att_feats, seq_length, att_masks,
+                         opt.get("decoding_constraint", 0))

@@ -1,0 +1,43 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
+GOLDEN_CASES = ["att2in2_plain", "att2in2_peaked", "att2in2_masked",
+                "topdown_plain", "topdown_peaked", "topdown_masked"]
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+
+
+def pytest_collection_modifyitems(config, items):
+    if torch.cuda.is_available():
+        return
+    skip = pytest.mark.skip(reason="no CUDA device")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
+def load_golden(name):
+    """Returns dict with sub-dicts sd / in / out / grad / <sampling tags> of torch tensors."""
+    z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    tree = {}
+    for key in z.files:
+        group, leaf = key.split("/", 1)
+        tree.setdefault(group, {})[leaf] = torch.from_numpy(np.asarray(z[key]))
+    tree["kind"] = name.split("_")[0]
+    return tree
+
+
+@pytest.fixture(params=GOLDEN_CASES)
+def golden(request):
+    return load_golden(request.param)

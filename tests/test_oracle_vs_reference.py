@@ -1,0 +1,45 @@
+"""Oracle restatement vs the live, unmodified reference at larger shapes and more seeds.
+Runs only where /root/reference exists (the build container); skipped on the GPU box."""
+import pytest
+import torch
+
+from oracle import decoder_oracle as O
+from oracle import reference_shim
+from unpaired_image_captioning_b200 import synth
+
+pytestmark = pytest.mark.skipif(not reference_shim.available(), reason="reference tree not present")
+
+
+@pytest.fixture(scope="module")
+def ref():
+    return reference_shim.load()
+
+
+@pytest.mark.parametrize("kind", ["att2in2", "topdown"])
+@pytest.mark.parametrize("seed,use_masks", [(11, False), (12, True)])
+def test_midsize_forward_loss_sampling(ref, kind, seed, use_masks):
+    models, criterion = ref
+    opt = synth.make_opt(caption_model=kind, vocab_size=299, rnn_size=64, input_encoding_size=48,
+                         att_hid_size=40, seq_length=9, fc_feat_size=96, att_feat_size=96)
+    sd = synth.init_state_dict(opt, seed=seed, peaked=30.0, eos_bias=0.5)
+    model = models.setup(opt)
+    model.load_state_dict(sd)
+    model.eval()
+    B, L = 6, 11
+    fc, att = synth.make_features(B, L, 96, seed=seed)
+    labels, masks = synth.make_captions(B, 9, 299, seed=seed, min_len=3)
+    am = synth.make_att_masks(B, L, seed=seed) if use_masks else None
+
+    ref_out = model(fc, None, att, labels, am)
+    out = O.teacher_forced(sd, kind, fc, att, labels, am)
+    torch.testing.assert_close(out, ref_out.detach(), rtol=1e-5, atol=2e-6)
+    ref_loss = criterion.LanguageModelCriterion(opt)(ref_out, labels[:, 1:], masks[:, 1:])
+    torch.testing.assert_close(O.xe_loss(out, labels[:, 1:], masks[:, 1:]), ref_loss.detach(), rtol=1e-5, atol=1e-6)
+
+    with torch.no_grad():
+        for o in ({"beam_size": 1}, {"beam_size": 3}, {"beam_size": 4, "max_ppl": 1},
+                  {"beam_size": 3, "decoding_constraint": 1}):
+            rs, rlp = model(fc, None, att, am, opt=dict(o), mode="sample")
+            s, lp = O.sample(sd, kind, fc, att, 9, am, dict(o))
+            assert torch.equal(s, rs), o
+            torch.testing.assert_close(lp, rlp, rtol=1e-5, atol=2e-6)
