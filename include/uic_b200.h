@@ -1,0 +1,138 @@
+/*
+ * uic_b200.h -- C ABI of the B200-native attention-LSTM caption decoder kernels.
+ *
+ * The reference (gujiuxiang/unpaired_image_captioning, pivot_based_eccv2018/) has no FFI or operator
+ * registry on this path: every operation below is a chain of torch ops inside models/AttModel.py,
+ * models/CaptionModel.py and misc/criterion.py.  Each entry point names the reference lines it
+ * replaces.  INTEGRATION.md shows the ctypes binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless stated otherwise;
+ *   - the caller owns every buffer (inputs, outputs, workspaces); nothing is allocated or freed here;
+ *   - `stream` is a cudaStream_t passed as void*; all work is stream-ordered and asynchronous;
+ *   - return value 0 = ok, negative = UIC_ERR_*; uic_last_error() gives the message (thread-local);
+ *   - bf16 buffers are raw uint16 storage (torch.bfloat16); "ld*" are row pitches in ELEMENTS;
+ *   - token ids are int64 (torch.long), like the reference; token 0 = BOS = EOS = pad, the last
+ *     vocabulary index V-1 is UNK (scripts/prepro_labels.py:86-88).
+ */
+#ifndef UIC_B200_H_
+#define UIC_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define UIC_OK 0
+#define UIC_ERR_ARG (-1)     /* null / inconsistent arguments */
+#define UIC_ERR_SHAPE (-2)   /* unsupported or empty shape */
+#define UIC_ERR_ALIGN (-3)   /* pointer or pitch alignment */
+#define UIC_ERR_CUDA (-4)    /* CUDA runtime / driver error (message has the detail) */
+#define UIC_ERR_DEVICE (-5)  /* not an sm_100 device */
+
+/* uic_gemm_bf16 flags */
+#define UIC_GEMM_RELU 1
+#define UIC_GEMM_ACCUMULATE 2   /* c_f32 += result (used for gradient accumulation) */
+#define UIC_GEMM_A_MN_MAJOR 4   /* A is stored [K, M] row-major instead of [M, K] */
+#define UIC_GEMM_B_MN_MAJOR 8   /* B is stored [K, N] row-major instead of [N, K] */
+
+/* sampling flags (uic_greedy_step / uic_row_topk) */
+#define UIC_SAMPLE_DECODING_CONSTRAINT 1 /* -inf on the previous token (AttModel.py:220-223, CaptionModel.py:130-131) */
+#define UIC_BEAM_MAX_PPL 2               /* divide finished scores by length (CaptionModel.py:163-164) */
+
+/* ---- library ------------------------------------------------------------------------------- */
+const char* uic_last_error(void);
+int uic_version(void);
+/* Kernel launches issued through this library since process start (bench.py's gpu_launches). */
+int64_t uic_launch_count(void);
+/* 0 = tcgen05 tensor-core GEMM (default), 1 = CUDA-core verification GEMM (tests/debug only). */
+int uic_set_gemm_impl(int impl);
+/* Fails with UIC_ERR_DEVICE unless the current device is compute capability 10.x. */
+int uic_check_device(void);
+
+/* ---- dense contractions -------------------------------------------------------------------- */
+/* D[M,N] = act(A[M,K] * B[N,K]^T + bias[N] (+ D)), bf16 operands, fp32 accumulate on tcgen05.
+ * Replaces every nn.Linear / nn.LSTMCell matmul on the path: models/AttModel.py:76-92 (fc_embed,
+ * att_embed, logit, ctx2att), :426-427 (LSTMCell), :535 (h2att), :574-576 (a2c, i2h, h2h) and their
+ * autograd backward (dgrad: B MN-major, wgrad: A and B MN-major).
+ * Either output may be NULL (but not both): c_f32 (fp32, pitch ldc) and c_bf16 (bf16, pitch ldcb). */
+int uic_gemm_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, float* c_f32, int64_t ldc, void* c_bf16,
+                  int64_t ldcb, const float* bias, int M, int N, int K, int flags, void* stream);
+
+/* ---- elementwise / layout ------------------------------------------------------------------ */
+/* dst_bf16[r, c] = bf16(relu?(src[r, c])) for an (rows x cols) fp32 matrix. Used to stage fp32
+ * features and weights as tensor-core operands. */
+int uic_cast_f32_bf16(const float* src, int64_t ld_src, void* dst, int64_t ld_dst, int64_t rows, int64_t cols, int relu,
+                      void* stream);
+/* out[r, 0:E] = table[tok[r], 0:E] (bf16 rows; ReLU is pre-applied to the table copy).
+ * Replaces self.embed = Embedding+ReLU (models/AttModel.py:73-75,160). */
+int uic_embed_rows(const void* table_bf16, int64_t ld_table, const int64_t* tok, void* out_bf16, int64_t ld_out, int rows,
+                   int E, int V, void* stream);
+
+/* x[i, l, :] = 0 for l >= sum(att_masks[i, :]): the zero padding pad_packed_sequence leaves behind
+ * in pack_wrapper (models/AttModel.py:44-53). x is (n_img*L, H) bf16 contiguous. */
+int uic_zero_padded_rows(void* x_bf16, const float* att_masks, int n_img, int L, int H, void* stream);
+
+/* ---- fused additive attention step (models/AttModel.py:538-558) ------------------------------
+ * For image i (n_img of them) and beam j < beams (row r = i*beams + j):
+ *   e[l]  = sum_a w_alpha[a] * tanh(p_att[i,l,a] + att_h[r,a])        (alpha_net bias cancels in softmax)
+ *   alpha = softmax_l(e);  if att_masks: alpha = alpha*m / sum(alpha*m)
+ *   ctx[r,:] = sum_l alpha[l] * att[i,l,:]
+ * att_h is the h2att projection INCLUDING its bias (fp32, pitch ld_att_h).  p_att / att are bf16,
+ * read once per image and shared by the image's beams.  Outputs (each optional): ctx_bf16, ctx_f32,
+ * alpha (rows x L fp32, saved for backward). */
+int uic_att_step_fwd(const float* att_h, int64_t ld_att_h, const void* p_att_bf16, const void* att_bf16,
+                     const float* w_alpha, const float* att_masks, void* ctx_bf16, int64_t ld_ctx_bf16, float* ctx_f32,
+                     int64_t ld_ctx_f32, float* alpha, int n_img, int beams, int L, int A, int H, void* stream);
+
+/* ---- LSTM pointwise ------------------------------------------------------------------------- */
+/* Att2in2 maxout cell (models/AttModel.py:584-601): sums = i2h(xt)+h2h(h) (rows x 5H, pitch ld_sums),
+ * a2c = a2c(ctx) (rows x 2H, pitch ld_a2c); i,f,o = sigmoid(sums[:, :3H]);
+ * g = max(sums[:,3H:4H]+a2c[:, :H], sums[:,4H:]+a2c[:,H:]); c = f*c_prev + i*g; h = o*tanh(c).
+ * h is written as fp32 (optional) and as bf16 to up to two destinations (next step's GEMM operand
+ * slots).  c_prev == NULL means zero state. */
+int uic_lstm_maxout_fwd(const float* sums, int64_t ld_sums, const float* a2c, int64_t ld_a2c, const float* c_prev,
+                        float* c_out, float* h_f32, void* h_bf16_a, int64_t ld_ha, void* h_bf16_b, int64_t ld_hb, int rows,
+                        int H, void* stream);
+/* torch.nn.LSTMCell pointwise, gate order i,f,g,o (models/AttModel.py:434,441): gates (rows x 4H). */
+int uic_lstm_cell_fwd(const float* gates, int64_t ld_gates, const float* c_prev, float* c_out, float* h_f32,
+                      void* h_bf16_a, int64_t ld_ha, void* h_bf16_b, int64_t ld_hb, int rows, int H, void* stream);
+
+/* ---- vocabulary softmax family --------------------------------------------------------------- */
+/* out[r, :] = log_softmax(logits[r, :]) (F.log_softmax, models/AttModel.py:163). */
+int uic_log_softmax_rows(const float* logits, int64_t ld_logits, float* out, int64_t ld_out, int rows, int V, void* stream);
+/* Fused masked cross-entropy forward (misc/criterion.py:143-150 without materialising log-probs):
+ * lse[r] = logsumexp(logits[r,:]); nll[r] = -(logits[r,target[r]] - lse[r]) * mask[r]. */
+int uic_lse_xent_fwd(const float* logits, int64_t ld_logits, const int64_t* target, const float* mask, float* lse,
+                     float* nll, int rows, int V, void* stream);
+
+/* One greedy decoding step (models/AttModel.py:218-251, sample_max=1) for `rows` sequences:
+ * log-softmax normaliser + argmax over V fused; writes seq[r,t] / seq_logprobs[r,t], updates the
+ * unfinished flags, emits the next input token (0 for finished rows) and counts the rows still
+ * unfinished into n_unfinished[t] so that later steps reproduce the reference's early `break`. */
+int uic_greedy_step(const float* logits, int64_t ld_logits, int64_t* seq, float* seq_logprobs, uint8_t* unfinished,
+                    int64_t* next_tok, int32_t* n_unfinished, int t, int seq_length, int rows, int V, int flags, void* stream);
+
+/* Per-row top-k of the log-probabilities after the beam-search edits (models/CaptionModel.py:
+ * 128-133,61): optional -inf on the previous token, -1000 on the UNK column; ties -> smaller id. */
+int uic_row_topk(const float* logits, int64_t ld_logits, const int64_t* prev_tok, float* topk_val, int32_t* topk_idx,
+                 int rows, int V, int k, int flags, void* stream);
+
+/* One beam-search bookkeeping step for all images at once (models/CaptionModel.py:48-97,155-172):
+ * merges the beams x k candidates of each image (c-major, q-minor stable order), forks the
+ * sequence tables, records finished hypotheses (token 0 or last step) into the sorted done lists,
+ * and emits parent row + next token for every beam. */
+int uic_beam_step(const float* topk_val, const int32_t* topk_idx, int32_t* beam_seq, float* beam_lp, float* beam_sum,
+                  int32_t* done_seq, float* done_lp, double* done_p, float* done_unaug, int32_t* done_cnt,
+                  int32_t* parent_row, int64_t* next_tok, int t, int seq_length, int n_img, int beams, int flags,
+                  void* stream);
+/* Re-order recurrent state by parent beam (CaptionModel.py:89-91): for two column ranges of the
+ * bf16 activation matrix and `n_state` fp32 state matrices (rows x H each, contiguous). */
+int uic_beam_gather(const int32_t* parent_row, const void* x_src, void* x_dst, int64_t ld_x, int col0_a, int ncol_a,
+                    int col0_b, int ncol_b, const float* c_src, float* c_dst, int n_state, int rows, int H, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* UIC_B200_H_ */

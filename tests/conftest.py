@@ -35,6 +35,7 @@ def load_golden(name):
         group, leaf = key.split("/", 1)
         tree.setdefault(group, {})[leaf] = torch.from_numpy(np.asarray(z[key]))
     tree["kind"] = name.split("_")[0]
+    tree["name"] = name
     return tree
 
 

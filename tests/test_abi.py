@@ -1,0 +1,67 @@
+"""CPU-only checks of the drop-in boundary: the shared library builds/loads, exports every symbol
+include/uic_b200.h declares, and the ctypes table matches the header (no compute calls here)."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "uic_b200.h")
+
+
+def _declared():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(uic_[a-z0-9_]+)\s*\(", src)))
+
+
+@pytest.fixture(scope="module")
+def lib_path():
+    from unpaired_image_captioning_b200 import build
+    return build.build()
+
+
+def test_header_declares_the_path():
+    names = _declared()
+    for required in ("uic_gemm_bf16", "uic_att_step_fwd", "uic_lstm_maxout_fwd", "uic_lstm_cell_fwd", "uic_lse_xent_fwd",
+                     "uic_greedy_step", "uic_beam_step", "uic_last_error"):
+        assert required in names
+
+
+def test_library_exports_every_declared_symbol(lib_path):
+    lib = ctypes.CDLL(lib_path)
+    for name in _declared():
+        assert hasattr(lib, name), f"{name} declared in uic_b200.h but not exported"
+
+
+def test_ctypes_table_matches_header(lib_path):
+    from unpaired_image_captioning_b200 import _lib
+    assert sorted(_lib.SIGNATURES) == _declared()
+    # argument counts agree with the prototypes
+    src = re.sub(r"/\*.*?\*/", "", open(HEADER).read(), flags=re.S)
+    for name, (_, args) in _lib.SIGNATURES.items():
+        m = re.search(r"\b%s\s*\(([^;]*?)\)\s*;" % name, src, flags=re.S)
+        assert m, name
+        params = [p for p in m.group(1).split(",") if p.strip() and p.strip() != "void"]
+        assert len(params) == len(args), (name, len(params), len(args))
+
+
+def test_missing_device_fails_loudly():
+    import torch
+    from unpaired_image_captioning_b200 import _lib
+    if torch.cuda.is_available():
+        pytest.skip("has a device")
+    with pytest.raises(_lib.UicError):
+        _lib.require_device()
+
+
+def test_sass_uses_blackwell_tensor_and_tma_instructions(lib_path):
+    import shutil
+    import subprocess
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run(["cuobjdump", "-sass", lib_path], capture_output=True, text=True).stdout
+    assert "UTCHMMA" in sass      # tcgen05.mma
+    assert "UTMALDG" in sass      # TMA tile loads
+    assert "LDTM" in sass         # tcgen05.ld (TMEM -> registers)

@@ -1,0 +1,244 @@
+"""Per-kernel parity on the B200: each C-ABI entry point against a plain fp32 PyTorch evaluation of
+the same formula on the same (bf16-rounded) operands.  All calls go through libuic_b200.so."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from unpaired_image_captioning_b200 import _lib  # noqa: E402
+from unpaired_image_captioning_b200._lib import check, ptr, stream  # noqa: E402
+
+DEV = "cuda"
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _device():
+    _lib.require_device()
+    yield
+    _lib.load().uic_set_gemm_impl(0)
+
+
+def _rand_bf16(*shape, seed=0, scale=1.0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to(DEV).to(torch.bfloat16)
+
+
+# ---------------------------------------------------------------------------------------------------
+# GEMM (tcgen05) -- shapes cover full tiles, M/N/K tails, the per-step and prologue sizes
+# ---------------------------------------------------------------------------------------------------
+GEMM_SHAPES = [(128, 128, 64), (128, 128, 512), (256, 384, 192), (5, 52, 32), (35, 52, 64), (300, 200, 72),
+               (768, 3072, 1024), (256, 10000, 512), (16 * 17, 10000, 512), (6272, 512, 2048), (48, 2560, 1024)]
+
+
+@pytest.mark.parametrize("M,N,K", GEMM_SHAPES)
+def test_gemm_tn_matches_fp32(M, N, K):
+    a, b = _rand_bf16(M, K, seed=1), _rand_bf16(N, K, seed=2, scale=0.05)
+    bias = torch.randn(N, device=DEV)
+    out = torch.empty(M, N, device=DEV)
+    _lib.gemm(a, b, bias, out_f32=out)
+    ref = a.float() @ b.float().t() + bias
+    torch.testing.assert_close(out, ref, rtol=2e-4, atol=2e-4)
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (300, 200, 72), (768, 3072, 1024)])
+def test_gemm_tcgen05_equals_simt_kernel(M, N, K):
+    a, b = _rand_bf16(M, K, seed=3), _rand_bf16(N, K, seed=4, scale=0.05)
+    lib = _lib.load()
+    o_tc, o_simt = torch.empty(M, N, device=DEV), torch.empty(M, N, device=DEV)
+    _lib.gemm(a, b, out_f32=o_tc)
+    check(lib.uic_set_gemm_impl(1))
+    try:
+        _lib.gemm(a, b, out_f32=o_simt)
+    finally:
+        check(lib.uic_set_gemm_impl(0))
+    torch.testing.assert_close(o_tc, o_simt, rtol=1e-4, atol=1e-4)
+
+
+def test_gemm_epilogues_and_strided_operands():
+    M, N, K = 200, 328, 256
+    big_a = _rand_bf16(M, K + 128, seed=5)
+    a = big_a[:, 64:64 + K]                      # column slice of a wider activation matrix (pitch K+128)
+    b = _rand_bf16(N, K, seed=6, scale=0.05)
+    bias = torch.randn(N, device=DEV)
+    ref = a.float() @ b.float().t() + bias
+    out_f, out_b = torch.empty(M, N, device=DEV), torch.empty(M, N + 8, device=DEV, dtype=torch.bfloat16)[:, :N]
+    _lib.gemm(a, b, bias, out_f32=out_f, out_bf16=out_b, relu=True)
+    torch.testing.assert_close(out_f, ref.relu(), rtol=2e-4, atol=2e-4)
+    torch.testing.assert_close(out_b.float(), ref.relu(), rtol=1e-2, atol=1e-2)
+    acc = torch.full((M, N), 0.5, device=DEV)
+    _lib.gemm(a, b, None, out_f32=acc, accumulate=True)
+    torch.testing.assert_close(acc, ref - bias + 0.5, rtol=2e-4, atol=2e-4)
+
+
+@pytest.mark.parametrize("a_mn,b_mn", [(False, True), (True, False), (True, True)])
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (200, 328, 136), (512, 2560, 8704 // 8)])
+def test_gemm_mn_major_operands(a_mn, b_mn, M, N, K):
+    """dgrad (B stored [K,N]) and wgrad (A stored [K,M], B stored [K,N]) forms."""
+    a, b = _rand_bf16(M, K, seed=7), _rand_bf16(N, K, seed=8, scale=0.05)
+    ref = a.float() @ b.float().t()
+    a_arg = a.t().contiguous() if a_mn else a
+    b_arg = b.t().contiguous() if b_mn else b
+    out = torch.empty(M, N, device=DEV)
+    _lib.gemm(a_arg, b_arg, out_f32=out, a_mn=a_mn, b_mn=b_mn)
+    torch.testing.assert_close(out, ref, rtol=2e-4, atol=2e-4)
+
+
+def test_gemm_rejects_bad_arguments():
+    a, b = _rand_bf16(16, 24), _rand_bf16(8, 24)
+    with pytest.raises(ValueError):
+        _lib.gemm(a.float(), b, out_f32=torch.empty(16, 8, device=DEV))
+    with pytest.raises(_lib.UicError):  # pitch 20 elements = 40 bytes is not TMA-addressable
+        _lib.gemm(_rand_bf16(16, 20), _rand_bf16(8, 20), out_f32=torch.empty(16, 8, device=DEV))
+
+
+# ---------------------------------------------------------------------------------------------------
+# fused attention step
+# ---------------------------------------------------------------------------------------------------
+def _att_reference(att_h, p_att, att, w, masks, beams):
+    B, L, A = p_att.shape
+    p = p_att.float().repeat_interleave(beams, 0)
+    a = att.float().repeat_interleave(beams, 0)
+    e = torch.tanh(p + att_h[:, None, :]) @ w
+    alpha = torch.softmax(e, 1)
+    if masks is not None:
+        m = masks.repeat_interleave(beams, 0)
+        alpha = alpha * m
+        alpha = alpha / alpha.sum(1, keepdim=True)
+    return torch.bmm(alpha[:, None, :], a).squeeze(1), alpha
+
+
+@pytest.mark.parametrize("B,beams,L,A,H,use_masks", [
+    (5, 1, 7, 32, 32, False), (5, 3, 7, 32, 32, True), (4, 5, 36, 512, 512, False), (3, 2, 196, 512, 512, True),
+    (2, 3, 196, 512, 1024, False), (3, 10, 20, 64, 40, False), (16, 1, 196, 512, 512, False), (2, 1, 5, 264, 776, True)])
+def test_att_step_fwd(B, beams, L, A, H, use_masks):
+    lib = _lib.load()
+    R = B * beams
+    p_att, att = _rand_bf16(B, L, A, seed=11), _rand_bf16(B, L, H, seed=12).abs()
+    att_h_full = torch.randn(R, A + 24, device=DEV)   # pitch larger than A, like the fused gate GEMM output
+    att_h = att_h_full[:, 8:8 + A]
+    w = torch.randn(A, device=DEV) * 0.2
+    masks = None
+    if use_masks:
+        n = torch.randint(1, L + 1, (B,))
+        masks = (torch.arange(L)[None, :] < n[:, None]).float().to(DEV).contiguous()
+    ctx_b = torch.empty(R, H, device=DEV, dtype=torch.bfloat16)
+    ctx_f = torch.empty(R, H, device=DEV)
+    alpha = torch.empty(R, L, device=DEV)
+    check(lib.uic_att_step_fwd(ptr(att_h), att_h_full.stride(0), ptr(p_att), ptr(att), ptr(w), ptr(masks), ptr(ctx_b), H,
+                               ptr(ctx_f), H, ptr(alpha), B, beams, L, A, H, stream()))
+    ref_ctx, ref_alpha = _att_reference(att_h, p_att, att, w, masks, beams)
+    torch.testing.assert_close(alpha, ref_alpha, rtol=5e-3, atol=2e-5)     # tanh.approx.f32 inside the score
+    torch.testing.assert_close(ctx_f, ref_ctx, rtol=5e-3, atol=5e-4)
+    torch.testing.assert_close(ctx_b.float(), ref_ctx, rtol=1e-2, atol=1e-2)
+
+
+# ---------------------------------------------------------------------------------------------------
+# LSTM pointwise
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("R,H", [(5, 32), (48, 512), (7, 1024)])
+def test_lstm_maxout_and_cell_fwd(R, H):
+    lib = _lib.load()
+    sums, a2c, c_prev = torch.randn(R, 5 * H, device=DEV), torch.randn(R, 2 * H, device=DEV), torch.randn(R, H, device=DEV)
+    c_out, h_f = torch.empty(R, H, device=DEV), torch.empty(R, H, device=DEV)
+    X = torch.zeros(R, 3 * H, device=DEV, dtype=torch.bfloat16)
+    check(lib.uic_lstm_maxout_fwd(ptr(sums), 5 * H, ptr(a2c), 2 * H, ptr(c_prev), ptr(c_out), ptr(h_f), ptr(X[:, H:]), 3 * H,
+                                  ptr(X[:, 2 * H:]), 3 * H, R, H, stream()))
+    sig = torch.sigmoid(sums[:, :3 * H])
+    g = torch.maximum(sums[:, 3 * H:4 * H] + a2c[:, :H], sums[:, 4 * H:] + a2c[:, H:])
+    c_ref = sig[:, H:2 * H] * c_prev + sig[:, :H] * g
+    h_ref = sig[:, 2 * H:] * torch.tanh(c_ref)
+    torch.testing.assert_close(c_out, c_ref, rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(h_f, h_ref, rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(X[:, H:2 * H].float(), h_ref, rtol=1e-2, atol=1e-2)
+    assert torch.equal(X[:, H:2 * H], X[:, 2 * H:]) and float(X[:, :H].abs().max()) == 0.0
+
+    gates = torch.randn(R, 4 * H, device=DEV)
+    check(lib.uic_lstm_cell_fwd(ptr(gates), 4 * H, ptr(c_prev), ptr(c_out), ptr(h_f), None, 0, None, 0, R, H, stream()))
+    i, f, g, o = gates.chunk(4, 1)
+    c_ref = torch.sigmoid(f) * c_prev + torch.sigmoid(i) * torch.tanh(g)
+    torch.testing.assert_close(c_out, c_ref, rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(h_f, torch.sigmoid(o) * torch.tanh(c_ref), rtol=1e-5, atol=1e-5)
+    # zero initial state through the NULL c_prev form
+    check(lib.uic_lstm_cell_fwd(ptr(gates), 4 * H, None, ptr(c_out), ptr(h_f), None, 0, None, 0, R, H, stream()))
+    torch.testing.assert_close(c_out, torch.sigmoid(i) * torch.tanh(g), rtol=1e-5, atol=1e-5)
+
+
+def test_cast_embed_and_zero_padding():
+    lib = _lib.load()
+    src = torch.randn(37, 72, device=DEV)
+    assert torch.equal(_lib.cast_bf16(src), src.to(torch.bfloat16))
+    assert torch.equal(_lib.cast_bf16(src, relu=True), src.relu().to(torch.bfloat16))
+    odd = torch.randn(5, 13, device=DEV)      # non-vector path
+    assert torch.equal(_lib.cast_bf16(odd), odd.to(torch.bfloat16))
+    table = _rand_bf16(50, 40, seed=21)
+    tok = torch.tensor([0, 49, 7, 7, 3], device=DEV)
+    out = torch.zeros(5, 100, device=DEV, dtype=torch.bfloat16)
+    check(lib.uic_embed_rows(ptr(table), 40, ptr(tok), ptr(out[:, 16:]), 100, 5, 40, 50, stream()))
+    assert torch.equal(out[:, 16:56], table[tok]) and float(out[:, :16].abs().max()) == 0.0
+    x = _rand_bf16(3 * 4, 16, seed=22)
+    masks = torch.tensor([[1, 1, 1, 1], [1, 0, 0, 0], [1, 1, 0, 0]], device=DEV, dtype=torch.float32)
+    ref = x.clone().view(3, 4, 16) * masks[:, :, None].to(torch.bfloat16)
+    check(lib.uic_zero_padded_rows(ptr(x), ptr(masks), 3, 4, 16, stream()))
+    assert torch.equal(x.view(3, 4, 16), ref)
+
+
+# ---------------------------------------------------------------------------------------------------
+# vocabulary kernels
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("R,V", [(5, 52), (33, 10000), (7, 30001), (4, 1000)])
+def test_log_softmax_and_xent(R, V):
+    lib = _lib.load()
+    ld = V + 3
+    buf = torch.randn(R, ld, device=DEV) * 3
+    logits = buf[:, :V]
+    out = torch.empty(R, V, device=DEV)
+    check(lib.uic_log_softmax_rows(ptr(logits), ld, ptr(out), V, R, V, stream()))
+    ref = torch.log_softmax(logits, 1)
+    torch.testing.assert_close(out, ref, rtol=1e-5, atol=2e-5)
+    target = torch.randint(0, V, (R,), device=DEV)
+    mask = (torch.rand(R, device=DEV) > 0.3).float()
+    lse, nll = torch.empty(R, device=DEV), torch.empty(R, device=DEV)
+    check(lib.uic_lse_xent_fwd(ptr(logits), ld, ptr(target), ptr(mask), ptr(lse), ptr(nll), R, V, stream()))
+    torch.testing.assert_close(lse, torch.logsumexp(logits, 1), rtol=1e-5, atol=2e-5)
+    torch.testing.assert_close(nll, -ref.gather(1, target[:, None]).squeeze(1) * mask, rtol=1e-5, atol=2e-5)
+
+
+@pytest.mark.parametrize("R,V,k", [(6, 52, 3), (40, 10000, 3), (9, 10000, 5), (5, 30000, 10), (3, 20, 16)])
+def test_row_topk(R, V, k):
+    lib = _lib.load()
+    logits = torch.randn(R, V, device=DEV) * 2
+    logits[:, V - 1] += 20.0                      # UNK would win without the -1000 edit
+    prev = torch.randint(0, V - 1, (R,), device=DEV)
+    logits[torch.arange(R), prev] += 30.0         # the banned token would win without the constraint
+    val, idx = torch.empty(R, k, device=DEV), torch.empty(R, k, device=DEV, dtype=torch.int32)
+    for flags in (0, _lib.SAMPLE_DECODING_CONSTRAINT):
+        check(lib.uic_row_topk(ptr(logits), V, ptr(prev), ptr(val), ptr(idx), R, V, k, flags, stream()))
+        lp = torch.log_softmax(logits, 1)
+        if flags:
+            lp[torch.arange(R), prev] = float("-inf")
+        lp[:, V - 1] -= 1000.0
+        ref_val, ref_idx = torch.sort(lp, 1, descending=True, stable=True)
+        assert torch.equal(idx.long(), ref_idx[:, :k])
+        torch.testing.assert_close(val, ref_val[:, :k], rtol=1e-5, atol=3e-5)
+
+
+def test_greedy_step_sequence_semantics():
+    """Three steps on hand-made logits: finished rows emit 0, log-probs are not masked, and nothing is
+    written once every row has finished (models/AttModel.py:242-251)."""
+    lib = _lib.load()
+    R, V, T = 4, 50, 5
+    seq, lp = torch.zeros(R, T, dtype=torch.int64, device=DEV), torch.zeros(R, T, device=DEV)
+    unf, tok = torch.zeros(R, dtype=torch.uint8, device=DEV), torch.zeros(R, dtype=torch.int64, device=DEV)
+    nunf = torch.zeros(T, dtype=torch.int32, device=DEV)
+    want = [[3, 0, 7, 9], [5, 4, 0, 0], [0, 0, 0, 0], [8, 8, 8, 8]]   # argmax per step/row; step 3 must be skipped
+    refs = []
+    for t in range(4):
+        logits = torch.randn(R, V, device=DEV)
+        logits[torch.arange(R), torch.tensor(want[t], device=DEV)] += 10.0
+        refs.append(torch.log_softmax(logits, 1).max(1).values)
+        check(lib.uic_greedy_step(ptr(logits), V, ptr(seq), ptr(lp), ptr(unf), ptr(tok), ptr(nunf), t, T, R, V, 0, stream()))
+    assert seq[:, :3].t().tolist() == [[3, 0, 7, 9], [5, 0, 0, 0], [0, 0, 0, 0]]
+    assert nunf.tolist() == [3, 1, 0, 0, 0]
+    for t in range(3):
+        torch.testing.assert_close(lp[:, t], refs[t], rtol=1e-5, atol=2e-5)
+    assert float(lp[:, 3:].abs().max()) == 0.0 and int(seq[:, 3:].abs().max()) == 0

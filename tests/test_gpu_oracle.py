@@ -1,0 +1,63 @@
+"""CUDA path vs the CPU oracle on seeded synthetic inputs at the real layer sizes of configs 1-3
+(rnn 512, vocab 10k, 196 / 36 regions), sized so the oracle finishes in seconds."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+import unpaired_image_captioning_b200 as uic  # noqa: E402
+from oracle import decoder_oracle as O  # noqa: E402
+from unpaired_image_captioning_b200 import synth  # noqa: E402
+from parity import compare_greedy  # noqa: E402
+
+REL = 1e-3
+
+
+def _case(kind, B, L, seed, peaked=0.0, eos_bias=0.0, masks=False):
+    opt = synth.make_opt(caption_model=kind, vocab_size=9999, rnn_size=512, input_encoding_size=512, att_hid_size=512,
+                         seq_length=16)
+    sd = synth.init_state_dict(opt, seed=seed, peaked=peaked, eos_bias=eos_bias)
+    fc, att = synth.make_features(B, L, 2048, seed=seed)
+    labels, lmasks = synth.make_captions(B, 16, 9999, seed=seed)
+    am = synth.make_att_masks(B, L, seed=seed) if masks else None
+    model = uic.setup(opt)
+    model.load_state_dict(sd)
+    return opt, sd, model.cuda().eval(), fc, att, labels, lmasks, am
+
+
+@pytest.mark.parametrize("kind,L,masks", [("att2in2", 196, False), ("topdown", 36, False), ("topdown", 36, True)])
+def test_teacher_forced_and_loss(kind, L, masks):
+    opt, sd, model, fc, att, labels, lmasks, am = _case(kind, 8, L, seed=1234, masks=masks)
+    ref = O.teacher_forced(sd, kind, fc, att, labels, am)
+    ref_loss = O.xe_loss(ref, labels[:, 1:], lmasks[:, 1:])
+    cu = lambda t: None if t is None else t.cuda()
+    with torch.no_grad():
+        out = model(cu(fc), None, cu(att), cu(labels), cu(am))
+        loss = uic.LanguageModelCriterion(opt)(out, cu(labels)[:, 1:], cu(lmasks)[:, 1:])
+    sel = lmasks[:, 1:].bool()
+    rel = ((out.cpu() - ref).abs() / ref.abs().clamp_min(1.0))[sel]
+    assert float(rel.max()) < REL, float(rel.max())
+    assert abs(float(loss) - float(ref_loss)) < REL * float(ref_loss)
+
+
+@pytest.mark.parametrize("kind,L", [("att2in2", 196), ("topdown", 36)])
+def test_greedy_with_margin_exemption(kind, L):
+    opt, sd, model, fc, att, *_ = _case(kind, 16, L, seed=77)
+    ref_seq, ref_lp, margins = O.sample_greedy(sd, kind, fc, att, 16, return_margins=True)
+    seq, lp = model(fc.cuda(), None, att.cuda(), None, opt={"beam_size": 1}, mode="sample")
+    exact, exempt, failures = compare_greedy(seq.cpu(), ref_seq, margins, tol=2e-2)
+    assert not failures, failures
+    assert exact >= 1
+    first = (seq.cpu() == ref_seq).all(1)
+    torch.testing.assert_close(lp.cpu()[first], ref_lp[first], rtol=REL, atol=REL * 10)
+
+
+@pytest.mark.parametrize("kind,L,beam", [("att2in2", 196, 3), ("topdown", 36, 3), ("att2in2", 49, 5)])
+def test_beam_peaked_exact(kind, L, beam):
+    """Wide-margin variant (scaled logit weights, raised EOS bias): ids must be identical."""
+    opt, sd, model, fc, att, *_ = _case(kind, 6, L, seed=5, peaked=40.0, eos_bias=2.0)
+    ref_seq, ref_lp, ref_done = O.sample_beam(sd, kind, fc, att, 16, beam)
+    seq, lp = model(fc.cuda(), None, att.cuda(), None, opt={"beam_size": beam}, mode="sample")
+    rows = (seq == ref_seq).all(1)
+    assert float(rows.float().mean()) >= 0.8, (seq, ref_seq)
+    torch.testing.assert_close(lp[rows], ref_lp[rows], rtol=2e-2, atol=2e-2)

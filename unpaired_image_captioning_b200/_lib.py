@@ -1,0 +1,120 @@
+"""ctypes binding of libuic_b200.so (the C ABI declared in include/uic_b200.h).
+
+There is no CPU or PyTorch fallback: if the library is missing or a call fails, this raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+_PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG_DIR, "libuic_b200.so")
+
+_p, _i, _i64, _f = C.c_void_p, C.c_int, C.c_int64, C.c_float
+
+# name -> (restype, argtypes); must list every symbol of include/uic_b200.h (tests check this)
+SIGNATURES = {
+    "uic_last_error": (C.c_char_p, []),
+    "uic_version": (_i, []),
+    "uic_launch_count": (_i64, []),
+    "uic_set_gemm_impl": (_i, [_i]),
+    "uic_check_device": (_i, []),
+    "uic_gemm_bf16": (_i, [_p, _i64, _p, _i64, _p, _i64, _p, _i64, _p, _i, _i, _i, _i, _p]),
+    "uic_cast_f32_bf16": (_i, [_p, _i64, _p, _i64, _i64, _i64, _i, _p]),
+    "uic_embed_rows": (_i, [_p, _i64, _p, _p, _i64, _i, _i, _i, _p]),
+    "uic_zero_padded_rows": (_i, [_p, _p, _i, _i, _i, _p]),
+    "uic_att_step_fwd": (_i, [_p, _i64, _p, _p, _p, _p, _p, _i64, _p, _i64, _p, _i, _i, _i, _i, _i, _p]),
+    "uic_lstm_maxout_fwd": (_i, [_p, _i64, _p, _i64, _p, _p, _p, _p, _i64, _p, _i64, _i, _i, _p]),
+    "uic_lstm_cell_fwd": (_i, [_p, _i64, _p, _p, _p, _p, _i64, _p, _i64, _i, _i, _p]),
+    "uic_log_softmax_rows": (_i, [_p, _i64, _p, _i64, _i, _i, _p]),
+    "uic_lse_xent_fwd": (_i, [_p, _i64, _p, _p, _p, _p, _i, _i, _p]),
+    "uic_greedy_step": (_i, [_p, _i64, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p]),
+    "uic_row_topk": (_i, [_p, _i64, _p, _p, _p, _i, _i, _i, _i, _p]),
+    "uic_beam_step": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p]),
+    "uic_beam_gather": (_i, [_p, _p, _p, _i64, _i, _i, _i, _i, _p, _p, _i, _i, _i, _p]),
+}
+
+GEMM_RELU, GEMM_ACCUMULATE, GEMM_A_MN, GEMM_B_MN = 1, 2, 4, 8
+SAMPLE_DECODING_CONSTRAINT, BEAM_MAX_PPL = 1, 2
+
+_lib = None
+
+
+class UicError(RuntimeError):
+    pass
+
+
+def load():
+    """Load the shared library (once).  Raises if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise UicError(f"{LIB_PATH} not found: build it with `python -m unpaired_image_captioning_b200.build` "
+                       "(there is no CPU fallback for the decoder kernels)")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype, fn.argtypes = res, args
+    _lib = lib
+    return lib
+
+
+def check(rc):
+    if rc != 0:
+        raise UicError(f"uic error {rc}: {load().uic_last_error().decode(errors='replace')}")
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    return None if t is None else t.data_ptr()
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def require_device():
+    if not torch.cuda.is_available():
+        raise UicError("no CUDA device: the decoder kernels are sm_100a-only and have no CPU fallback")
+    check(load().uic_check_device())
+
+
+def launch_count():
+    return int(load().uic_launch_count())
+
+
+# ---- typed convenience wrappers (validate dtype/contiguity like torch would) -----------------------
+def _is_bf16(t):
+    return t.dtype == torch.bfloat16 and t.is_cuda and t.stride(-1) == 1
+
+
+def gemm(a, b, bias=None, out_f32=None, out_bf16=None, relu=False, accumulate=False, a_mn=False, b_mn=False):
+    """D[M,N] = act(A @ B^T + bias).  `a` is (M,K) [or (K,M) if a_mn], `b` is (N,K) [or (K,N) if b_mn];
+    both 2-D bf16 views whose last stride is 1 (row pitch arbitrary)."""
+    if not (_is_bf16(a) and _is_bf16(b) and a.dim() == 2 and b.dim() == 2):
+        raise ValueError("gemm: operands must be 2-D CUDA bfloat16 tensors with unit inner stride")
+    M, K = (a.shape[1], a.shape[0]) if a_mn else a.shape
+    N, Kb = (b.shape[1], b.shape[0]) if b_mn else b.shape
+    if K != Kb:
+        raise ValueError(f"gemm: K mismatch {K} vs {Kb}")
+    for o, dt in ((out_f32, torch.float32), (out_bf16, torch.bfloat16)):
+        if o is not None and (o.dtype != dt or o.shape != (M, N) or o.stride(1) != 1):
+            raise ValueError("gemm: bad output tensor")
+    if bias is not None and (bias.dtype != torch.float32 or bias.numel() != N or not bias.is_contiguous()):
+        raise ValueError("gemm: bias must be contiguous fp32 of length N")
+    flags = (GEMM_RELU if relu else 0) | (GEMM_ACCUMULATE if accumulate else 0) | (GEMM_A_MN if a_mn else 0) | (GEMM_B_MN if b_mn else 0)
+    check(load().uic_gemm_bf16(ptr(a), a.stride(0), ptr(b), b.stride(0), ptr(out_f32), out_f32.stride(0) if out_f32 is not None else 0,
+                               ptr(out_bf16), out_bf16.stride(0) if out_bf16 is not None else 0, ptr(bias), M, N, K, flags, stream()))
+
+
+def cast_bf16(src, dst=None, relu=False):
+    """fp32 (rows, cols) -> bf16, optional ReLU."""
+    if src.dtype != torch.float32 or src.dim() != 2 or src.stride(1) != 1:
+        raise ValueError("cast_bf16: src must be a 2-D fp32 tensor with unit inner stride")
+    if dst is None:
+        dst = torch.empty(src.shape, dtype=torch.bfloat16, device=src.device)
+    check(load().uic_cast_f32_bf16(ptr(src), src.stride(0), ptr(dst), dst.stride(0), src.shape[0], src.shape[1], int(relu), stream()))
+    return dst

@@ -1,0 +1,244 @@
+// C-ABI layer of libuic_b200.so: argument validation, error strings, launch accounting and the
+// TMA descriptor cache.  Signatures and contracts are documented in include/uic_b200.h.
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <unordered_map>
+
+#include "uic_internal.h"
+
+namespace uic {
+
+static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+static std::atomic<int> g_gemm_impl{-1};
+
+int set_error(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+int gemm_impl() {
+  int v = g_gemm_impl.load(std::memory_order_relaxed);
+  if (v < 0) {
+    const char* e = getenv("UIC_GEMM");
+    v = (e != nullptr && strcmp(e, "simt") == 0) ? GEMM_IMPL_SIMT : GEMM_IMPL_TCGEN05;
+    g_gemm_impl.store(v);
+  }
+  return v;
+}
+
+// ---- TMA descriptor cache ---------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+struct MapKey {
+  const void* base;
+  long long rows, cols, ld;
+  int box_rows, box_cols;
+  bool operator==(const MapKey& o) const {
+    return base == o.base && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows && box_cols == o.box_cols;
+  }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    size_t h = reinterpret_cast<size_t>(k.base);
+    auto mix = [&h](size_t v) { h ^= v + 0x9e3779b97f4a7c15ULL + (h << 6) + (h >> 2); };
+    mix(static_cast<size_t>(k.rows));
+    mix(static_cast<size_t>(k.cols));
+    mix(static_cast<size_t>(k.ld));
+    mix(static_cast<size_t>(k.box_rows) * 1315423911u + static_cast<size_t>(k.box_cols));
+    return h;
+  }
+};
+
+int get_tensor_map_bf16(CUtensorMap* out, const void* base, long long rows, long long cols, long long ld, int box_rows,
+                        int box_cols) {
+  static std::mutex mu;
+  static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
+  MapKey key{base, rows, cols, ld, box_rows, box_cols};
+  {
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) {
+      *out = it->second;
+      return 0;
+    }
+  }
+  EncodeTiledFn fn = encode_fn();
+  if (fn == nullptr) return set_error(UIC_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(cols), static_cast<cuuint64_t>(rows)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 2};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(box_cols), static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  CUtensorMap m;
+  CUresult r = fn(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return set_error(UIC_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for base=%p rows=%lld cols=%lld ld=%lld box=%dx%d",
+                     static_cast<int>(r), base, rows, cols, ld, box_rows, box_cols);
+  {
+    std::lock_guard<std::mutex> lock(mu);
+    if (cache.size() > 65536) cache.clear();
+    cache.emplace(key, m);
+  }
+  *out = m;
+  return 0;
+}
+
+}  // namespace uic
+
+// ---- extern "C" ---------------------------------------------------------------------------------
+using namespace uic;
+#define ST(s) static_cast<cudaStream_t>(s)
+#define REQUIRE(cond, code, ...) \
+  do {                           \
+    if (!(cond)) return set_error(code, __VA_ARGS__); \
+  } while (0)
+
+extern "C" {
+
+const char* uic_last_error(void) { return g_err; }
+int uic_version(void) { return 100; }
+int64_t uic_launch_count(void) { return g_launches.load(); }
+int uic_set_gemm_impl(int impl) {
+  REQUIRE(impl == 0 || impl == 1, UIC_ERR_ARG, "uic_set_gemm_impl: impl must be 0 or 1");
+  g_gemm_impl.store(impl);
+  return 0;
+}
+int uic_check_device(void) {
+  int dev = 0;
+  UIC_CUDA_OK(cudaGetDevice(&dev));
+  cudaDeviceProp p;
+  UIC_CUDA_OK(cudaGetDeviceProperties(&p, dev));
+  REQUIRE(p.major == 10, UIC_ERR_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", dev, p.major, p.minor);
+  return 0;
+}
+
+int uic_gemm_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, float* c_f32, int64_t ldc, void* c_bf16,
+                  int64_t ldcb, const float* bias, int M, int N, int K, int flags, void* stream) {
+  REQUIRE(A && B, UIC_ERR_ARG, "uic_gemm_bf16: null operand");
+  return gemm_bf16(A, lda, B, ldb, c_f32, ldc, c_bf16, ldcb, bias, M, N, K, flags, ST(stream));
+}
+
+int uic_cast_f32_bf16(const float* src, int64_t ld_src, void* dst, int64_t ld_dst, int64_t rows, int64_t cols, int relu,
+                      void* stream) {
+  REQUIRE(src && dst, UIC_ERR_ARG, "uic_cast_f32_bf16: null pointer");
+  if (rows == 0 || cols == 0) return 0;
+  return cast_f32_bf16(src, ld_src, dst, ld_dst, rows, cols, relu, ST(stream));
+}
+
+int uic_embed_rows(const void* table, int64_t ld_table, const int64_t* tok, void* out, int64_t ld_out, int rows, int E, int V,
+                   void* stream) {
+  REQUIRE(table && tok && out, UIC_ERR_ARG, "uic_embed_rows: null pointer");
+  if (rows == 0) return 0;
+  return embed_rows(table, ld_table, tok, out, ld_out, rows, E, V, ST(stream));
+}
+
+int uic_zero_padded_rows(void* x_bf16, const float* att_masks, int n_img, int L, int H, void* stream) {
+  REQUIRE(x_bf16 && att_masks, UIC_ERR_ARG, "uic_zero_padded_rows: null pointer");
+  if (n_img == 0 || L == 0) return 0;
+  return zero_padded_rows(x_bf16, att_masks, n_img, L, H, ST(stream));
+}
+
+int uic_att_step_fwd(const float* att_h, int64_t ld_att_h, const void* p_att, const void* att, const float* w_alpha,
+                     const float* masks, void* ctx_bf16, int64_t ld_ctx_bf16, float* ctx_f32, int64_t ld_ctx_f32, float* alpha,
+                     int n_img, int beams, int L, int A, int H, void* stream) {
+  REQUIRE(att_h && p_att && att && w_alpha, UIC_ERR_ARG, "uic_att_step_fwd: null input");
+  REQUIRE(ctx_bf16 || ctx_f32, UIC_ERR_ARG, "uic_att_step_fwd: no output buffer");
+  if (n_img == 0) return 0;
+  return att_step_fwd(att_h, ld_att_h, p_att, att, w_alpha, masks, ctx_bf16, ld_ctx_bf16, ctx_f32, ld_ctx_f32, alpha, n_img,
+                      beams, L, A, H, ST(stream));
+}
+
+int uic_lstm_maxout_fwd(const float* sums, int64_t ld_sums, const float* a2c, int64_t ld_a2c, const float* c_prev, float* c_out,
+                        float* h_f32, void* h_a, int64_t ld_ha, void* h_b, int64_t ld_hb, int rows, int H, void* stream) {
+  REQUIRE(sums && a2c && c_out, UIC_ERR_ARG, "uic_lstm_maxout_fwd: null pointer");
+  if (rows == 0) return 0;
+  return lstm_maxout_fwd(sums, ld_sums, a2c, ld_a2c, c_prev, c_out, h_f32, h_a, ld_ha, h_b, ld_hb, rows, H, ST(stream));
+}
+
+int uic_lstm_cell_fwd(const float* gates, int64_t ld_gates, const float* c_prev, float* c_out, float* h_f32, void* h_a,
+                      int64_t ld_ha, void* h_b, int64_t ld_hb, int rows, int H, void* stream) {
+  REQUIRE(gates && c_out, UIC_ERR_ARG, "uic_lstm_cell_fwd: null pointer");
+  if (rows == 0) return 0;
+  return lstm_cell_fwd(gates, ld_gates, c_prev, c_out, h_f32, h_a, ld_ha, h_b, ld_hb, rows, H, ST(stream));
+}
+
+int uic_log_softmax_rows(const float* logits, int64_t ld, float* out, int64_t ld_out, int rows, int V, void* stream) {
+  REQUIRE(logits && out, UIC_ERR_ARG, "uic_log_softmax_rows: null pointer");
+  if (rows == 0) return 0;
+  REQUIRE(V > 0, UIC_ERR_SHAPE, "uic_log_softmax_rows: V=%d", V);
+  return log_softmax_rows(logits, ld, out, ld_out, rows, V, ST(stream));
+}
+
+int uic_lse_xent_fwd(const float* logits, int64_t ld, const int64_t* target, const float* mask, float* lse, float* nll, int rows,
+                     int V, void* stream) {
+  REQUIRE(logits && target && mask && lse && nll, UIC_ERR_ARG, "uic_lse_xent_fwd: null pointer");
+  if (rows == 0) return 0;
+  REQUIRE(V > 0, UIC_ERR_SHAPE, "uic_lse_xent_fwd: V=%d", V);
+  return lse_xent_fwd(logits, ld, target, mask, lse, nll, rows, V, ST(stream));
+}
+
+int uic_greedy_step(const float* logits, int64_t ld, int64_t* seq, float* seq_lp, uint8_t* unfinished, int64_t* next_tok,
+                    int32_t* n_unfinished, int t, int seq_length, int rows, int V, int flags, void* stream) {
+  REQUIRE(logits && seq && seq_lp && unfinished && next_tok && n_unfinished, UIC_ERR_ARG, "uic_greedy_step: null pointer");
+  REQUIRE(t >= 0 && t < seq_length, UIC_ERR_ARG, "uic_greedy_step: t=%d outside [0,%d)", t, seq_length);
+  if (rows == 0) return 0;
+  return greedy_step(logits, ld, seq, seq_lp, unfinished, next_tok, n_unfinished, t, seq_length, rows, V, flags, ST(stream));
+}
+
+int uic_row_topk(const float* logits, int64_t ld, const int64_t* prev_tok, float* topk_val, int32_t* topk_idx, int rows, int V,
+                 int k, int flags, void* stream) {
+  REQUIRE(logits && topk_val && topk_idx, UIC_ERR_ARG, "uic_row_topk: null pointer");
+  REQUIRE(k >= 1 && k <= 16 && k <= V, UIC_ERR_SHAPE, "uic_row_topk: k=%d must be in [1,16] and <= V=%d", k, V);
+  REQUIRE(!(flags & UIC_SAMPLE_DECODING_CONSTRAINT) || prev_tok, UIC_ERR_ARG, "uic_row_topk: constraint needs prev_tok");
+  if (rows == 0) return 0;
+  return row_topk(logits, ld, prev_tok, topk_val, topk_idx, rows, V, k, flags, ST(stream));
+}
+
+int uic_beam_step(const float* topk_val, const int32_t* topk_idx, int32_t* beam_seq, float* beam_lp, float* beam_sum,
+                  int32_t* done_seq, float* done_lp, double* done_p, float* done_unaug, int32_t* done_cnt, int32_t* parent_row,
+                  int64_t* next_tok, int t, int seq_length, int n_img, int beams, int flags, void* stream) {
+  REQUIRE(topk_val && topk_idx && beam_seq && beam_lp && beam_sum && done_seq && done_lp && done_p && done_unaug && done_cnt &&
+              parent_row && next_tok,
+          UIC_ERR_ARG, "uic_beam_step: null pointer");
+  REQUIRE(beams >= 1 && beams <= 16, UIC_ERR_SHAPE, "uic_beam_step: beams=%d must be in [1,16]", beams);
+  REQUIRE(t >= 0 && t < seq_length && seq_length <= 64, UIC_ERR_SHAPE, "uic_beam_step: t=%d seq_length=%d (max 64)", t, seq_length);
+  if (n_img == 0) return 0;
+  return beam_step(topk_val, topk_idx, beam_seq, beam_lp, beam_sum, done_seq, done_lp, done_p, done_unaug, done_cnt, parent_row,
+                   next_tok, t, seq_length, n_img, beams, flags, ST(stream));
+}
+
+int uic_beam_gather(const int32_t* parent_row, const void* x_src, void* x_dst, int64_t ld_x, int col0_a, int ncol_a, int col0_b,
+                    int ncol_b, const float* c_src, float* c_dst, int n_state, int rows, int H, void* stream) {
+  REQUIRE(parent_row && x_src && x_dst, UIC_ERR_ARG, "uic_beam_gather: null pointer");
+  REQUIRE(x_src != x_dst && (c_src == nullptr || c_src != c_dst), UIC_ERR_ARG, "uic_beam_gather: must not run in place");
+  if (rows == 0) return 0;
+  return beam_gather(parent_row, x_src, x_dst, ld_x, col0_a, ncol_a, col0_b, ncol_b, c_src, c_dst, n_state, rows, H, ST(stream));
+}
+
+}  // extern "C"

@@ -1,0 +1,218 @@
+// Element-wise and row-movement kernels of the decoder step: fp32->bf16 operand staging, embedding
+// row gather, the two LSTM pointwise updates and the beam-state gather.  All are HBM/L2-bound
+// streaming kernels: 16-byte vector accesses where alignment allows, grid sized from the data.
+#include "uic_internal.h"
+#include "uic_ptx.cuh"
+
+namespace uic {
+
+static inline int blocks_for(long long work, int threads) {
+  long long b = (work + threads - 1) / threads;
+  const long long cap = 148LL * 16;  // a few waves of the 148 SMs; kernels are grid-stride
+  return static_cast<int>(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+// ---- fp32 -> bf16 (optionally ReLU) -------------------------------------------------------------
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ src, long long ld_src, __nv_bfloat16* __restrict__ dst,
+                                     long long ld_dst, long long rows, long long cols, int relu, int vec) {
+  if (vec) {  // cols % 8 == 0, pitches % 8 == 0, 16/32-byte aligned bases
+    const long long cg = cols / 8;
+    const long long total = rows * cg;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+      const long long r = i / cg, c = (i - r * cg) * 8;
+      const float4 a = *reinterpret_cast<const float4*>(src + r * ld_src + c);
+      const float4 b = *reinterpret_cast<const float4*>(src + r * ld_src + c + 4);
+      float f[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+      if (relu) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) f[k] = fmaxf(f[k], 0.0f);
+      }
+      uint4 q;
+      q.x = f2_to_bf16x2(f[0], f[1]);
+      q.y = f2_to_bf16x2(f[2], f[3]);
+      q.z = f2_to_bf16x2(f[4], f[5]);
+      q.w = f2_to_bf16x2(f[6], f[7]);
+      *reinterpret_cast<uint4*>(dst + r * ld_dst + c) = q;
+    }
+  } else {
+    const long long total = rows * cols;
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+      const long long r = i / cols, c = i - r * cols;
+      float v = src[r * ld_src + c];
+      if (relu) v = fmaxf(v, 0.0f);
+      dst[r * ld_dst + c] = __float2bfloat16_rn(v);
+    }
+  }
+}
+
+int cast_f32_bf16(const float* src, long long ld_src, void* dst, long long ld_dst, long long rows, long long cols, int relu,
+                  cudaStream_t stream) {
+  const int vec = (cols % 8 == 0) && (ld_src % 4 == 0) && (ld_dst % 8 == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0) &&
+                  ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
+  const long long work = vec ? rows * (cols / 8) : rows * cols;
+  cast_f32_bf16_kernel<<<blocks_for(work, 256), 256, 0, stream>>>(src, ld_src, static_cast<__nv_bfloat16*>(dst), ld_dst, rows,
+                                                                   cols, relu, vec);
+  UIC_CUDA_OK(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+// ---- embedding rows -------------------------------------------------------------------------------
+__global__ void embed_rows_kernel(const __nv_bfloat16* __restrict__ table, long long ld_table, const int64_t* __restrict__ tok,
+                                  __nv_bfloat16* __restrict__ out, long long ld_out, int rows, int E, int V, int vec) {
+  const int per_row = vec ? E / 8 : E;
+  const long long total = static_cast<long long>(rows) * per_row;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int r = static_cast<int>(i / per_row);
+    const int c = static_cast<int>(i - static_cast<long long>(r) * per_row);
+    long long t = tok[r];
+    t = t < 0 ? 0 : (t >= V ? V - 1 : t);
+    if (vec)
+      *reinterpret_cast<uint4*>(out + r * ld_out + c * 8) = *reinterpret_cast<const uint4*>(table + t * ld_table + c * 8);
+    else
+      out[r * ld_out + c] = table[t * ld_table + c];
+  }
+}
+
+int embed_rows(const void* table, long long ld_table, const int64_t* tok, void* out, long long ld_out, int rows, int E, int V,
+               cudaStream_t stream) {
+  const int vec = (E % 8 == 0) && (ld_table % 8 == 0) && (ld_out % 8 == 0) && ((reinterpret_cast<uintptr_t>(table) & 15) == 0) &&
+                  ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+  const long long work = static_cast<long long>(rows) * (vec ? E / 8 : E);
+  embed_rows_kernel<<<blocks_for(work, 256), 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(table), ld_table, tok,
+                                                                static_cast<__nv_bfloat16*>(out), ld_out, rows, E, V, vec);
+  UIC_CUDA_OK(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+// ---- LSTM pointwise ---------------------------------------------------------------------------------
+struct HOut {
+  float* h_f32;
+  __nv_bfloat16* h_a;
+  long long ld_ha;
+  __nv_bfloat16* h_b;
+  long long ld_hb;
+};
+
+__device__ __forceinline__ void store_h(const HOut& o, int r, int j, int H, float h) {
+  if (o.h_f32) o.h_f32[static_cast<long long>(r) * H + j] = h;
+  const __nv_bfloat16 hb = __float2bfloat16_rn(h);
+  if (o.h_a) o.h_a[static_cast<long long>(r) * o.ld_ha + j] = hb;
+  if (o.h_b) o.h_b[static_cast<long long>(r) * o.ld_hb + j] = hb;
+}
+
+// Att2in2Core.forward pointwise part, models/AttModel.py:585-597.
+__global__ void lstm_maxout_fwd_kernel(const float* __restrict__ sums, long long ld_sums, const float* __restrict__ a2c,
+                                       long long ld_a2c, const float* __restrict__ c_prev, float* __restrict__ c_out, HOut o,
+                                       int rows, int H) {
+  const long long total = static_cast<long long>(rows) * H;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int r = static_cast<int>(i / H), j = static_cast<int>(i - static_cast<long long>(r) * H);
+    const float* s = sums + r * ld_sums;
+    const float* a = a2c + r * ld_a2c;
+    const float ig = sigmoid_acc(s[j]);
+    const float fg = sigmoid_acc(s[H + j]);
+    const float og = sigmoid_acc(s[2 * H + j]);
+    const float g = fmaxf(s[3 * H + j] + a[j], s[4 * H + j] + a[H + j]);
+    const float cp = c_prev ? c_prev[i] : 0.0f;
+    const float c = fg * cp + ig * g;
+    c_out[i] = c;
+    store_h(o, r, j, H, og * tanhf(c));
+  }
+}
+
+// torch.nn.LSTMCell pointwise part (gate order i, f, g, o), used at models/AttModel.py:434,441.
+__global__ void lstm_cell_fwd_kernel(const float* __restrict__ gates, long long ld_gates, const float* __restrict__ c_prev,
+                                     float* __restrict__ c_out, HOut o, int rows, int H) {
+  const long long total = static_cast<long long>(rows) * H;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int r = static_cast<int>(i / H), j = static_cast<int>(i - static_cast<long long>(r) * H);
+    const float* g4 = gates + r * ld_gates;
+    const float ig = sigmoid_acc(g4[j]);
+    const float fg = sigmoid_acc(g4[H + j]);
+    const float gg = tanhf(g4[2 * H + j]);
+    const float og = sigmoid_acc(g4[3 * H + j]);
+    const float cp = c_prev ? c_prev[i] : 0.0f;
+    const float c = fg * cp + ig * gg;
+    c_out[i] = c;
+    store_h(o, r, j, H, og * tanhf(c));
+  }
+}
+
+int lstm_maxout_fwd(const float* sums, long long ld_sums, const float* a2c, long long ld_a2c, const float* c_prev, float* c_out,
+                    float* h_f32, void* h_a, long long ld_ha, void* h_b, long long ld_hb, int rows, int H, cudaStream_t stream) {
+  HOut o{h_f32, static_cast<__nv_bfloat16*>(h_a), ld_ha, static_cast<__nv_bfloat16*>(h_b), ld_hb};
+  lstm_maxout_fwd_kernel<<<blocks_for(static_cast<long long>(rows) * H, 256), 256, 0, stream>>>(sums, ld_sums, a2c, ld_a2c, c_prev,
+                                                                                                 c_out, o, rows, H);
+  UIC_CUDA_OK(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+int lstm_cell_fwd(const float* gates, long long ld_gates, const float* c_prev, float* c_out, float* h_f32, void* h_a,
+                  long long ld_ha, void* h_b, long long ld_hb, int rows, int H, cudaStream_t stream) {
+  HOut o{h_f32, static_cast<__nv_bfloat16*>(h_a), ld_ha, static_cast<__nv_bfloat16*>(h_b), ld_hb};
+  lstm_cell_fwd_kernel<<<blocks_for(static_cast<long long>(rows) * H, 256), 256, 0, stream>>>(gates, ld_gates, c_prev, c_out, o,
+                                                                                               rows, H);
+  UIC_CUDA_OK(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+// ---- beam state gather (CaptionModel.py:89-91) -------------------------------------------------------
+__global__ void beam_gather_kernel(const int32_t* __restrict__ parent, const __nv_bfloat16* __restrict__ x_src,
+                                   __nv_bfloat16* __restrict__ x_dst, long long ld_x, int col0_a, int ncol_a, int col0_b,
+                                   int ncol_b, const float* __restrict__ c_src, float* __restrict__ c_dst, int n_state, int rows,
+                                   int H) {
+  const int r = blockIdx.x;
+  const int q = parent[r];
+  for (int c = threadIdx.x; c < ncol_a; c += blockDim.x) x_dst[r * ld_x + col0_a + c] = x_src[q * ld_x + col0_a + c];
+  for (int c = threadIdx.x; c < ncol_b; c += blockDim.x) x_dst[r * ld_x + col0_b + c] = x_src[q * ld_x + col0_b + c];
+  if (c_src != nullptr) {
+    for (int s = 0; s < n_state; ++s) {
+      const float* src = c_src + (static_cast<long long>(s) * rows + q) * H;
+      float* dst = c_dst + (static_cast<long long>(s) * rows + r) * H;
+      for (int c = threadIdx.x; c < H; c += blockDim.x) dst[c] = src[c];
+    }
+  }
+}
+
+int beam_gather(const int32_t* parent_row, const void* x_src, void* x_dst, long long ld_x, int col0_a, int ncol_a, int col0_b,
+                int ncol_b, const float* c_src, float* c_dst, int n_state, int rows, int H, cudaStream_t stream) {
+  beam_gather_kernel<<<rows, 128, 0, stream>>>(parent_row, static_cast<const __nv_bfloat16*>(x_src),
+                                               static_cast<__nv_bfloat16*>(x_dst), ld_x, col0_a, ncol_a, col0_b, ncol_b, c_src,
+                                               c_dst, n_state, rows, H);
+  UIC_CUDA_OK(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+}  // namespace uic
+
+namespace uic {
+
+// ---- zero the padded regions of the embedded features (pad_packed_sequence, AttModel.py:50-51) -----
+__global__ void zero_padded_rows_kernel(__nv_bfloat16* __restrict__ x, const float* __restrict__ masks, int L, int H) {
+  const long long row = blockIdx.x;  // row = img * L + l
+  const int img = static_cast<int>(row / L), l = static_cast<int>(row - static_cast<long long>(img) * L);
+  // number of valid regions = sum of the mask row (masks are prefix-shaped in the reference's packed path)
+  float n = 0.0f;
+  for (int q = 0; q < L; ++q) n += masks[static_cast<long long>(img) * L + q];
+  if (l < static_cast<int>(n)) return;
+  for (int c = threadIdx.x; c < H; c += blockDim.x) x[row * H + c] = __float2bfloat16_rn(0.0f);
+}
+
+int zero_padded_rows(void* x, const float* masks, int n_img, int L, int H, cudaStream_t stream) {
+  zero_padded_rows_kernel<<<n_img * L, 128, 0, stream>>>(static_cast<__nv_bfloat16*>(x), masks, L, H);
+  UIC_CUDA_OK(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+}  // namespace uic

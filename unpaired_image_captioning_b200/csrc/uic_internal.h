@@ -1,0 +1,58 @@
+// Internal declarations shared by the kernel translation units and the C-ABI layer (api.cu).
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/uic_b200.h"
+
+namespace uic {
+
+enum { GEMM_IMPL_TCGEN05 = 0, GEMM_IMPL_SIMT = 1 };
+
+int set_error(int code, const char* fmt, ...);
+void count_launch();
+int gemm_impl();
+
+// Cached cuTensorMapEncodeTiled for a row-major bf16 matrix [rows, cols] with pitch ld (elements),
+// box = box_rows x box_cols, 128-byte swizzle, zero fill out of bounds.
+int get_tensor_map_bf16(CUtensorMap* out, const void* base, long long rows, long long cols, long long ld, int box_rows,
+                        int box_cols);
+
+#define UIC_CUDA_OK(expr)                                                                                   \
+  do {                                                                                                      \
+    cudaError_t _e = (expr);                                                                                \
+    if (_e != cudaSuccess)                                                                                  \
+      return ::uic::set_error(UIC_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+// kernels.  Each returns 0 or a negative UIC_ERR_* (after set_error).
+int gemm_bf16(const void* A, long long lda, const void* B, long long ldb, float* c_f32, long long ldc, void* c_bf16,
+              long long ldcb, const float* bias, int M, int N, int K, int flags, cudaStream_t stream);
+int cast_f32_bf16(const float* src, long long ld_src, void* dst, long long ld_dst, long long rows, long long cols, int relu,
+                  cudaStream_t stream);
+int zero_padded_rows(void* x, const float* masks, int n_img, int L, int H, cudaStream_t stream);
+int embed_rows(const void* table, long long ld_table, const int64_t* tok, void* out, long long ld_out, int rows, int E, int V,
+               cudaStream_t stream);
+int att_step_fwd(const float* att_h, long long ld_att_h, const void* p_att, const void* att, const float* w_alpha,
+                 const float* masks, void* ctx_bf16, long long ld_ctx_bf16, float* ctx_f32, long long ld_ctx_f32, float* alpha,
+                 int n_img, int beams, int L, int A, int H, cudaStream_t stream);
+int lstm_maxout_fwd(const float* sums, long long ld_sums, const float* a2c, long long ld_a2c, const float* c_prev, float* c_out,
+                    float* h_f32, void* h_a, long long ld_ha, void* h_b, long long ld_hb, int rows, int H, cudaStream_t stream);
+int lstm_cell_fwd(const float* gates, long long ld_gates, const float* c_prev, float* c_out, float* h_f32, void* h_a,
+                  long long ld_ha, void* h_b, long long ld_hb, int rows, int H, cudaStream_t stream);
+int log_softmax_rows(const float* logits, long long ld, float* out, long long ld_out, int rows, int V, cudaStream_t stream);
+int lse_xent_fwd(const float* logits, long long ld, const int64_t* target, const float* mask, float* lse, float* nll, int rows,
+                 int V, cudaStream_t stream);
+int greedy_step(const float* logits, long long ld, int64_t* seq, float* seq_lp, uint8_t* unfinished, int64_t* next_tok,
+                int32_t* n_unfinished, int t, int seq_length, int rows, int V, int flags, cudaStream_t stream);
+int row_topk(const float* logits, long long ld, const int64_t* prev_tok, float* topk_val, int32_t* topk_idx, int rows, int V,
+             int k, int flags, cudaStream_t stream);
+int beam_step(const float* topk_val, const int32_t* topk_idx, int32_t* beam_seq, float* beam_lp, float* beam_sum,
+              int32_t* done_seq, float* done_lp, double* done_p, float* done_unaug, int32_t* done_cnt, int32_t* parent_row,
+              int64_t* next_tok, int t, int seq_length, int n_img, int beams, int flags, cudaStream_t stream);
+int beam_gather(const int32_t* parent_row, const void* x_src, void* x_dst, long long ld_x, int col0_a, int ncol_a, int col0_b,
+                int ncol_b, const float* c_src, float* c_dst, int n_state, int rows, int H, cudaStream_t stream);
+
+}  // namespace uic

@@ -1,0 +1,284 @@
+// Row kernels over the vocabulary axis: log-softmax, fused masked cross-entropy, greedy argmax
+// step and per-row top-k for beam search.  One CTA per decoder row; every kernel makes a single
+// online (max, sum-exp) pass over the row with 16-byte loads, then a block reduction with warp
+// shuffles.  The logits were just written by the logit GEMM, so these reads are L2 hits.
+#include "uic_internal.h"
+#include "uic_ptx.cuh"
+
+namespace uic {
+
+constexpr int ROW_THREADS = 256;
+constexpr int ROW_WARPS = ROW_THREADS / 32;
+
+struct MaxSum {
+  float m, s;
+};
+__device__ __forceinline__ void ms_push(MaxSum& a, float x) {
+  if (x > a.m) {
+    a.s = a.s * __expf(a.m - x) + 1.0f;  // exp(-inf) = 0 for the first element
+    a.m = x;
+  } else {
+    a.s += __expf(x - a.m);
+  }
+}
+__device__ __forceinline__ MaxSum ms_merge(MaxSum a, MaxSum b) {
+  MaxSum r;
+  r.m = fmaxf(a.m, b.m);
+  if (r.m == -INFINITY) {
+    r.s = 0.0f;
+    return r;
+  }
+  r.s = a.s * __expf(a.m - r.m) + b.s * __expf(b.m - r.m);
+  return r;
+}
+__device__ __forceinline__ MaxSum ms_block_reduce(MaxSum v, MaxSum* s_part) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    MaxSum other;
+    other.m = __shfl_xor_sync(0xffffffffu, v.m, o);
+    other.s = __shfl_xor_sync(0xffffffffu, v.s, o);
+    v = ms_merge(v, other);
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (lane == 0) s_part[warp] = v;
+  __syncthreads();
+  MaxSum r = s_part[0];
+#pragma unroll
+  for (int q = 1; q < ROW_WARPS; ++q) r = ms_merge(r, s_part[q]);
+  return r;
+}
+
+// Visit every element of a row once; float4 loads when the row start is 16-byte aligned.
+template <typename F>
+__device__ __forceinline__ void for_each_in_row(const float* row, int V, F&& f) {
+  if ((reinterpret_cast<uintptr_t>(row) & 15) == 0) {
+    const int v4 = V >> 2;
+    for (int i = threadIdx.x; i < v4; i += ROW_THREADS) {
+      const float4 q = *reinterpret_cast<const float4*>(row + 4 * i);
+      f(4 * i, q.x);
+      f(4 * i + 1, q.y);
+      f(4 * i + 2, q.z);
+      f(4 * i + 3, q.w);
+    }
+    for (int i = (v4 << 2) + threadIdx.x; i < V; i += ROW_THREADS) f(i, row[i]);
+  } else {
+    for (int i = threadIdx.x; i < V; i += ROW_THREADS) f(i, row[i]);
+  }
+}
+
+// ---- log_softmax (models/AttModel.py:163) ---------------------------------------------------------
+__global__ void __launch_bounds__(ROW_THREADS) log_softmax_rows_kernel(const float* __restrict__ logits, long long ld,
+                                                                       float* __restrict__ out, long long ld_out, int V) {
+  __shared__ MaxSum s_part[ROW_WARPS];
+  const float* row = logits + static_cast<long long>(blockIdx.x) * ld;
+  float* orow = out + static_cast<long long>(blockIdx.x) * ld_out;
+  MaxSum a{-INFINITY, 0.0f};
+  for_each_in_row(row, V, [&](int, float x) { ms_push(a, x); });
+  const MaxSum r = ms_block_reduce(a, s_part);
+  const float log_s = logf(r.s);
+  for_each_in_row(row, V, [&](int i, float x) { orow[i] = (x - r.m) - log_s; });
+}
+
+int log_softmax_rows(const float* logits, long long ld, float* out, long long ld_out, int rows, int V, cudaStream_t stream) {
+  log_softmax_rows_kernel<<<rows, ROW_THREADS, 0, stream>>>(logits, ld, out, ld_out, V);
+  UIC_CUDA_OK(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+// ---- fused masked cross-entropy forward (misc/criterion.py:143-150) --------------------------------
+__global__ void __launch_bounds__(ROW_THREADS) lse_xent_fwd_kernel(const float* __restrict__ logits, long long ld,
+                                                                   const int64_t* __restrict__ target,
+                                                                   const float* __restrict__ mask, float* __restrict__ lse,
+                                                                   float* __restrict__ nll, int V) {
+  __shared__ MaxSum s_part[ROW_WARPS];
+  const int r = blockIdx.x;
+  const float* row = logits + static_cast<long long>(r) * ld;
+  MaxSum a{-INFINITY, 0.0f};
+  for_each_in_row(row, V, [&](int, float x) { ms_push(a, x); });
+  const MaxSum red = ms_block_reduce(a, s_part);
+  if (threadIdx.x == 0) {
+    const float log_s = logf(red.s);
+    lse[r] = red.m + log_s;
+    long long t = target[r];
+    t = t < 0 ? 0 : (t >= V ? V - 1 : t);
+    nll[r] = -((row[t] - red.m) - log_s) * mask[r];
+  }
+}
+
+int lse_xent_fwd(const float* logits, long long ld, const int64_t* target, const float* mask, float* lse, float* nll, int rows,
+                 int V, cudaStream_t stream) {
+  lse_xent_fwd_kernel<<<rows, ROW_THREADS, 0, stream>>>(logits, ld, target, mask, lse, nll, V);
+  UIC_CUDA_OK(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+// ---- greedy step (models/AttModel.py:218-251, sample_max=1) ------------------------------------------
+struct Best {
+  float v;
+  int i;
+};
+__device__ __forceinline__ bool better(float v, int i, const Best& b) { return v > b.v || (v == b.v && i < b.i); }
+
+__global__ void __launch_bounds__(ROW_THREADS) greedy_step_kernel(const float* __restrict__ logits, long long ld,
+                                                                  int64_t* __restrict__ seq, float* __restrict__ seq_lp,
+                                                                  uint8_t* __restrict__ unfinished,
+                                                                  int64_t* __restrict__ next_tok,
+                                                                  int32_t* __restrict__ n_unfinished, int t, int T, int V,
+                                                                  int flags) {
+  // The reference leaves the loop once every row has finished (AttModel.py:250-251): later
+  // columns of seq / seqLogprobs stay zero.
+  if (t > 0 && n_unfinished[t - 1] == 0) return;
+  __shared__ MaxSum s_part[ROW_WARPS];
+  __shared__ Best s_best[ROW_WARPS];
+  const int r = blockIdx.x;
+  const float* row = logits + static_cast<long long>(r) * ld;
+  const int banned = ((flags & UIC_SAMPLE_DECODING_CONSTRAINT) && t > 0) ? static_cast<int>(seq[static_cast<long long>(r) * T + t - 1]) : -1;
+  MaxSum a{-INFINITY, 0.0f};
+  Best b{-INFINITY, 0x7fffffff};
+  for_each_in_row(row, V, [&](int i, float x) {
+    ms_push(a, x);
+    const float xs = (i == banned) ? -INFINITY : x;
+    if (better(xs, i, b)) {
+      b.v = xs;
+      b.i = i;
+    }
+  });
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, b.v, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, b.i, o);
+    if (better(ov, oi, b)) {
+      b.v = ov;
+      b.i = oi;
+    }
+  }
+  if ((threadIdx.x & 31) == 0) s_best[threadIdx.x >> 5] = b;
+  const MaxSum red = ms_block_reduce(a, s_part);  // contains the __syncthreads that publishes s_best
+  if (threadIdx.x == 0) {
+    Best w = s_best[0];
+    for (int q = 1; q < ROW_WARPS; ++q)
+      if (better(s_best[q].v, s_best[q].i, w)) w = s_best[q];
+    const float lp = (w.v - red.m) - logf(red.s);
+    long long it = w.i;
+    const bool u = (t == 0 ? true : unfinished[r] != 0) && it > 0;  // :242-245
+    it = u ? it : 0;                                                 // :246
+    seq[static_cast<long long>(r) * T + t] = it;
+    seq_lp[static_cast<long long>(r) * T + t] = lp;                  // :248, not masked
+    unfinished[r] = u ? 1 : 0;
+    next_tok[r] = it;
+    if (u) atomicAdd(&n_unfinished[t], 1);
+  }
+}
+
+int greedy_step(const float* logits, long long ld, int64_t* seq, float* seq_lp, uint8_t* unfinished, int64_t* next_tok,
+                int32_t* n_unfinished, int t, int seq_length, int rows, int V, int flags, cudaStream_t stream) {
+  greedy_step_kernel<<<rows, ROW_THREADS, 0, stream>>>(logits, ld, seq, seq_lp, unfinished, next_tok, n_unfinished, t, seq_length,
+                                                       V, flags);
+  UIC_CUDA_OK(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+// ---- per-row top-k after the beam-search edits (models/CaptionModel.py:128-133,61) -------------------
+template <int KMAX>
+__global__ void __launch_bounds__(ROW_THREADS) row_topk_kernel(const float* __restrict__ logits, long long ld,
+                                                               const int64_t* __restrict__ prev_tok, float* __restrict__ topk_val,
+                                                               int32_t* __restrict__ topk_idx, int V, int k, int flags) {
+  __shared__ MaxSum s_part[ROW_WARPS];
+  __shared__ float s_val[ROW_THREADS * KMAX];
+  __shared__ int s_idx[ROW_THREADS * KMAX];
+  __shared__ Best s_best[ROW_WARPS];
+  __shared__ int s_winner;
+  const int r = blockIdx.x;
+  const float* row = logits + static_cast<long long>(r) * ld;
+  const int banned = ((flags & UIC_SAMPLE_DECODING_CONSTRAINT) && prev_tok) ? static_cast<int>(prev_tok[r]) : -1;
+
+  float val[KMAX];
+  int idx[KMAX];
+#pragma unroll
+  for (int q = 0; q < KMAX; ++q) {
+    val[q] = -INFINITY;
+    idx[q] = 0x7fffffff;
+  }
+  MaxSum a{-INFINITY, 0.0f};
+  for_each_in_row(row, V, [&](int i, float x) {
+    ms_push(a, x);
+    float xs = (i == V - 1) ? x - 1000.0f : x;  // UNK suppression (:133)
+    if (i == banned) xs = -INFINITY;            // decoding constraint (:130-131)
+    // indices arrive in increasing order per thread, so ">" keeps the smaller index on ties
+    if (xs > val[KMAX - 1] || (idx[KMAX - 1] == 0x7fffffff)) {
+      val[KMAX - 1] = xs;
+      idx[KMAX - 1] = i;
+#pragma unroll
+      for (int q = KMAX - 1; q > 0; --q) {
+        if (val[q] > val[q - 1] || idx[q - 1] == 0x7fffffff) {
+          const float tv = val[q];
+          val[q] = val[q - 1];
+          val[q - 1] = tv;
+          const int ti = idx[q];
+          idx[q] = idx[q - 1];
+          idx[q - 1] = ti;
+        }
+      }
+    }
+  });
+#pragma unroll
+  for (int q = 0; q < KMAX; ++q) {
+    s_val[threadIdx.x * KMAX + q] = val[q];
+    s_idx[threadIdx.x * KMAX + q] = idx[q];
+  }
+  const MaxSum red = ms_block_reduce(a, s_part);
+  const float log_s = logf(red.s);
+
+  int head = 0;
+  for (int round = 0; round < k; ++round) {
+    Best b{-INFINITY, 0x7fffffff};
+    if (head < KMAX && s_idx[threadIdx.x * KMAX + head] != 0x7fffffff) {
+      b.v = s_val[threadIdx.x * KMAX + head];
+      b.i = s_idx[threadIdx.x * KMAX + head];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, b.v, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, b.i, o);
+      if (oi != 0x7fffffff && (b.i == 0x7fffffff || better(ov, oi, b))) {
+        b.v = ov;
+        b.i = oi;
+      }
+    }
+    if ((threadIdx.x & 31) == 0) s_best[threadIdx.x >> 5] = b;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      Best w = s_best[0];
+      for (int q = 1; q < ROW_WARPS; ++q)
+        if (s_best[q].i != 0x7fffffff && (w.i == 0x7fffffff || better(s_best[q].v, s_best[q].i, w))) w = s_best[q];
+      s_winner = w.i;
+      // ys[q, c] of the reference: the edited log-probability (the UNK shift is applied to the
+      // log-prob in fp32, like `logprobsf[:, V-1] - 1000`)
+      float lp = ((row[w.i] - red.m) - log_s);
+      if (w.i == V - 1) lp -= 1000.0f;
+      if (w.i == banned) lp = -INFINITY;
+      topk_val[static_cast<long long>(r) * k + round] = lp;
+      topk_idx[static_cast<long long>(r) * k + round] = w.i;
+    }
+    __syncthreads();
+    if (head < KMAX && s_idx[threadIdx.x * KMAX + head] == s_winner) ++head;
+  }
+}
+
+int row_topk(const float* logits, long long ld, const int64_t* prev_tok, float* topk_val, int32_t* topk_idx, int rows, int V,
+             int k, int flags, cudaStream_t stream) {
+  if (k <= 4)
+    row_topk_kernel<4><<<rows, ROW_THREADS, 0, stream>>>(logits, ld, prev_tok, topk_val, topk_idx, V, k, flags);
+  else if (k <= 8)
+    row_topk_kernel<8><<<rows, ROW_THREADS, 0, stream>>>(logits, ld, prev_tok, topk_val, topk_idx, V, k, flags);
+  else
+    row_topk_kernel<16><<<rows, ROW_THREADS, 0, stream>>>(logits, ld, prev_tok, topk_val, topk_idx, V, k, flags);
+  UIC_CUDA_OK(cudaGetLastError());
+  count_launch();
+  return 0;
+}
+
+}  // namespace uic

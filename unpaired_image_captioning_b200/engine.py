@@ -1,0 +1,364 @@
+"""Device-side execution engine of the attention-LSTM decoder: packed bf16 weights, HBM workspaces,
+the per-step kernel plans for the two cores on the hot path (Att2in2Core, TopDownCore) and the
+fully on-device greedy / beam decode loops (captured into CUDA graphs).
+
+Data layout in HBM (R = decoder rows = images x beams, Kx = width of the activation matrix X):
+
+  att2in2  X = [ xt (E) | h (H) ]                                     models/AttModel.py:581-601
+           S = X @ [[W_i2h W_h2h],[0 W_h2att]]^T + b   (R, 5H + A)    one GEMM gives the gate sums AND att_h
+  topdown  X = [ h_att_prev | xt (E) | fc | h_lang_prev | h_att | ctx ]   models/AttModel.py:430-446
+           G1 = X[:, :E+3H] @ W1^T, att_h = X[:, h_att] @ W_h2att^T, G2 = X[:, h_lang_prev:] @ W2^T
+  The weight columns are permuted once at pack time so that every GEMM reads a CONTIGUOUS column
+  range of X; torch.cat copies of the reference (:432,:438) disappear.
+  att (B, L, H) and p_att (B, L, A) are bf16, produced once per batch by the prologue GEMMs and
+  shared by all beams of an image.  Recurrent c stays fp32; h is stored as bf16 GEMM operand.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from ._lib import check, gemm, ptr, stream
+
+BF16 = torch.bfloat16
+
+
+def _bf16(t):
+    """fp32 weight -> bf16 operand through the library's cast kernel."""
+    t2 = t.detach().reshape(t.shape[0], -1) if t.dim() > 1 else t.detach().reshape(1, -1)
+    return _lib.cast_bf16(t2.contiguous().float())
+
+
+class PackedWeights:
+    """bf16 operand copies of the module parameters in the layouts the step plans need.
+
+    Rebuilt when any parameter's version counter or storage changes (optimizer steps,
+    load_state_dict)."""
+
+    def __init__(self, model):
+        self.kind = model.kind
+        sd = {k: v.detach() for k, v in model.state_dict().items()}
+        self.signature = PackedWeights.signature_of(model)
+        H, E, A = model.rnn_size, model.input_encoding_size, model.att_hid_size
+        self.H, self.E, self.A, self.V = H, E, A, model.vocab_size + 1
+        f32 = lambda k: sd[k].float().contiguous()
+        # Embedding + ReLU folded into the table copy (models/AttModel.py:73-75)
+        self.emb_relu = _lib.cast_bf16(f32("embed.0.weight"), relu=True)
+        self.w_att_embed, self.b_att_embed = _bf16(sd["att_embed.0.weight"]), f32("att_embed.0.bias")
+        self.w_ctx2att, self.b_ctx2att = _bf16(sd["ctx2att.weight"]), f32("ctx2att.bias")
+        self.w_logit, self.b_logit = _bf16(sd["logit.weight"]), f32("logit.bias")
+        self.w_alpha = f32("core.attention.alpha_net.weight").reshape(-1).contiguous()
+        w_h2att, b_h2att = f32("core.attention.h2att.weight"), f32("core.attention.h2att.bias")
+        if self.kind == "att2in2":
+            self.Kx = E + H
+            w1 = torch.zeros(5 * H + A, E + H, device=w_h2att.device)
+            w1[:5 * H, :E] = f32("core.i2h.weight")
+            w1[:5 * H, E:] = f32("core.h2h.weight")
+            w1[5 * H:, E:] = w_h2att
+            self.w1 = _bf16(w1)
+            self.b1 = torch.cat([f32("core.i2h.bias") + f32("core.h2h.bias"), b_h2att]).contiguous()
+            self.w_a2c, self.b_a2c = _bf16(sd["core.a2c.weight"]), f32("core.a2c.bias")
+        elif self.kind == "topdown":
+            self.Kx = E + 5 * H
+            self.w_fc, self.b_fc = _bf16(sd["fc_embed.0.weight"]), f32("fc_embed.0.bias")
+            w_ih, w_hh = f32("core.att_lstm.weight_ih"), f32("core.att_lstm.weight_hh")
+            # reference input order is [h_lang_prev, fc, xt] (:432); X order is [h_att_prev, xt, fc, h_lang_prev]
+            self.w1 = _bf16(torch.cat([w_hh, w_ih[:, 2 * H:], w_ih[:, H:2 * H], w_ih[:, :H]], 1))
+            self.b1 = (f32("core.att_lstm.bias_ih") + f32("core.att_lstm.bias_hh")).contiguous()
+            w_ih2, w_hh2 = f32("core.lang_lstm.weight_ih"), f32("core.lang_lstm.weight_hh")
+            # reference input order is [ctx, h_att] (:438); X order is [h_lang_prev, h_att, ctx]
+            self.w2 = _bf16(torch.cat([w_hh2, w_ih2[:, H:], w_ih2[:, :H]], 1))
+            self.b2 = (f32("core.lang_lstm.bias_ih") + f32("core.lang_lstm.bias_hh")).contiguous()
+            self.w_h2att, self.b_h2att = _bf16(w_h2att), b_h2att
+        else:
+            raise ValueError(self.kind)
+
+    @staticmethod
+    def signature_of(model):
+        return tuple((p.data_ptr(), p._version) for p in model.parameters())
+
+
+class Slots:
+    """Column ranges of the activation matrix X."""
+
+    def __init__(self, kind, E, H):
+        if kind == "att2in2":
+            self.xt, self.h_out = (0, E), (E, E + H)
+            self.gather = [(E, H), (0, 0)]           # recurrent columns re-ordered by beam parent
+            self.n_state = 1
+        else:
+            self.h_att_prev, self.xt, self.fc = (0, H), (H, H + E), (H + E, 2 * H + E)
+            self.h_lang, self.h_att, self.ctx = (2 * H + E, 3 * H + E), (3 * H + E, 4 * H + E), (4 * H + E, 5 * H + E)
+            self.h_out = self.h_lang
+            self.gather = [(0, H), (2 * H + E, H)]
+            self.n_state = 2
+
+
+class Features:
+    """Output of the prologue (models/AttModel.py:107-117): bf16 att / p_att tiles (+ fc for topdown)."""
+
+    def __init__(self, att, p_att, fc, masks, B, L):
+        self.att, self.p_att, self.fc, self.masks, self.B, self.L = att, p_att, fc, masks, B, L
+
+
+class DecoderEngine:
+    def __init__(self, model):
+        _lib.require_device()
+        self.model = model
+        self.kind = model.kind
+        self._packed = None
+        self._graphs = {}
+        self.use_graphs = True
+        self.lib = _lib.load()
+
+    # ---- weights ---------------------------------------------------------------------------------
+    @property
+    def w(self):
+        if self._packed is None or self._packed.signature != PackedWeights.signature_of(self.model):
+            self._packed = PackedWeights(self.model)
+            self._graphs.clear()  # captured graphs hold pointers into the old operand copies
+        return self._packed
+
+    # ---- prologue ---------------------------------------------------------------------------------
+    def prepare(self, fc_feats, att_feats, att_masks=None):
+        """clip_att + fc_embed + att_embed + ctx2att (models/AttModel.py:99-117)."""
+        w = self.w
+        if att_masks is not None:  # clip to the longest valid length (:99-105)
+            keep = int(att_masks.long().sum(1).max())
+            att_feats, att_masks = att_feats[:, :keep], att_masks[:, :keep].contiguous().float()
+        B, L, D = att_feats.shape
+        H, A = w.H, w.A
+        x = _lib.cast_bf16(att_feats.reshape(B * L, D).float() if att_feats.dtype != torch.float32 else att_feats.reshape(B * L, D))
+        att = torch.empty(B * L, H, dtype=BF16, device=x.device)
+        gemm(x, w.w_att_embed, w.b_att_embed, out_bf16=att, relu=True)
+        if att_masks is not None:
+            check(self.lib.uic_zero_padded_rows(ptr(att), ptr(att_masks), B, L, H, stream()))
+        p_att = torch.empty(B * L, A, dtype=BF16, device=x.device)
+        gemm(att, w.w_ctx2att, w.b_ctx2att, out_bf16=p_att)
+        fc = None
+        if self.kind == "topdown":
+            fc = torch.empty(B, H, dtype=BF16, device=x.device)
+            gemm(_lib.cast_bf16(fc_feats.float().contiguous()), w.w_fc, w.b_fc, out_bf16=fc, relu=True)
+        return Features(att.view(B, L, H), p_att.view(B, L, A), fc, att_masks, B, L)
+
+    # ---- one decoder step: X, c -> logits -------------------------------------------------------------
+    def _workspace(self, R, dev):
+        w = self.w
+        ws = {}
+        if self.kind == "att2in2":
+            ws["S"] = torch.empty(R, 5 * w.H + w.A, dtype=torch.float32, device=dev)
+            ws["ctx"] = torch.empty(R, w.H, dtype=BF16, device=dev)
+            ws["a2c"] = torch.empty(R, 2 * w.H, dtype=torch.float32, device=dev)
+        else:
+            ws["G"] = torch.empty(R, 4 * w.H, dtype=torch.float32, device=dev)
+            ws["att_h"] = torch.empty(R, w.A, dtype=torch.float32, device=dev)
+        ws["logits"] = torch.empty(R, w.V, dtype=torch.float32, device=dev)
+        return ws
+
+    def core_step(self, X, c, feats, ws, beams=1, X_next=None, c_out=None, h_all=None, alpha=None):
+        """Runs the recurrent core for one step, in place on X / c unless X_next / c_out are given
+        (teacher-forced runs keep every step's operands for backward).  h_all: optional extra bf16
+        destination (rows, H) for the step output (time-batched logit operand)."""
+        w, lib, st = self.w, self.lib, stream()
+        H, E, A, R = w.H, w.E, w.A, X.shape[0]
+        sl = Slots(self.kind, E, H)
+        c_out = c if c_out is None else c_out
+        Xn = X if X_next is None else X_next
+        ldx = X.stride(0)
+
+        def cols(t, rng):
+            return t[:, rng[0]:rng[1]]
+
+        if self.kind == "att2in2":
+            S = ws["S"]
+            gemm(X, w.w1, w.b1, out_f32=S)
+            check(lib.uic_att_step_fwd(ptr(S[:, 5 * H:]), S.stride(0), ptr(feats.p_att), ptr(feats.att), ptr(w.w_alpha),
+                                       ptr(feats.masks), ptr(ws["ctx"]), H, None, 0, ptr(alpha), feats.B, beams, feats.L, A, H, st))
+            gemm(ws["ctx"], w.w_a2c, w.b_a2c, out_f32=ws["a2c"])
+            h_dst = cols(Xn, sl.h_out)
+            check(lib.uic_lstm_maxout_fwd(ptr(S), S.stride(0), ptr(ws["a2c"]), 2 * H, ptr(c[0]), ptr(c_out[0]), None,
+                                          ptr(h_dst), Xn.stride(0), ptr(h_all), h_all.stride(0) if h_all is not None else 0,
+                                          R, H, st))
+        else:
+            G = ws["G"]
+            gemm(X[:, :E + 3 * H], w.w1, w.b1, out_f32=G)
+            # h_att goes to this step's h_att slot (operand of h2att and of the language LSTM) and to
+            # the next step's h_att_prev slot
+            check(lib.uic_lstm_cell_fwd(ptr(G), 4 * H, ptr(c[0]), ptr(c_out[0]), None, ptr(cols(X, sl.h_att)), ldx,
+                                        ptr(cols(Xn, sl.h_att_prev)), Xn.stride(0), R, H, st))
+            gemm(cols(X, sl.h_att), w.w_h2att, w.b_h2att, out_f32=ws["att_h"])
+            ctx = cols(X, sl.ctx)
+            check(lib.uic_att_step_fwd(ptr(ws["att_h"]), A, ptr(feats.p_att), ptr(feats.att), ptr(w.w_alpha), ptr(feats.masks),
+                                       ptr(ctx), ldx, None, 0, ptr(alpha), feats.B, beams, feats.L, A, H, st))
+            gemm(X[:, E + 2 * H:], w.w2, w.b2, out_f32=G)
+            check(lib.uic_lstm_cell_fwd(ptr(G), 4 * H, ptr(c[1]), ptr(c_out[1]), None, ptr(cols(Xn, sl.h_lang)), Xn.stride(0),
+                                        ptr(h_all), h_all.stride(0) if h_all is not None else 0, R, H, st))
+        return cols(Xn, sl.h_out)
+
+    def logits_of(self, h, out):
+        gemm(h, self.w.w_logit, self.w.b_logit, out_f32=out)
+
+    def _new_state(self, R, dev, feats, beams):
+        w = self.w
+        sl = Slots(self.kind, w.E, w.H)
+        X = torch.zeros(R, w.Kx, dtype=BF16, device=dev)
+        c = torch.zeros(sl.n_state, R, w.H, dtype=torch.float32, device=dev)
+        if self.kind == "topdown":  # every beam row of image i carries fc[i]
+            idx = torch.arange(R, device=dev, dtype=torch.int64) // beams
+            check(self.lib.uic_embed_rows(ptr(feats.fc), w.H, ptr(idx), ptr(X[:, sl.fc[0]:]), X.stride(0), R, w.H, feats.B, stream()))
+        return X, c, sl
+
+    def _embed(self, tok, X, sl):
+        w = self.w
+        check(self.lib.uic_embed_rows(ptr(w.emb_relu), w.E, ptr(tok), ptr(X[:, sl.xt[0]:]), X.stride(0), X.shape[0], w.E, w.V, stream()))
+
+    # ---- greedy (models/AttModel.py:198-253, sample_max = 1) -------------------------------------------
+    def greedy(self, feats, seq_length, decoding_constraint=0):
+        w, lib = self.w, self.lib
+        B, dev, T = feats.B, feats.att.device, seq_length
+        flags = _lib.SAMPLE_DECODING_CONSTRAINT if decoding_constraint else 0
+        key = ("greedy", B, feats.L, T, flags, feats.masks is not None)
+
+        def alloc():
+            s = {"att": torch.empty_like(feats.att), "p_att": torch.empty_like(feats.p_att),
+                 "fc": None if feats.fc is None else torch.empty_like(feats.fc),
+                 "masks": None if feats.masks is None else torch.empty_like(feats.masks),
+                 "ws": self._workspace(B, dev),
+                 "seq": torch.zeros(B, T, dtype=torch.int64, device=dev), "lp": torch.zeros(B, T, device=dev),
+                 "unf": torch.zeros(B, dtype=torch.uint8, device=dev), "tok": torch.zeros(B, dtype=torch.int64, device=dev),
+                 "nunf": torch.zeros(T, dtype=torch.int32, device=dev)}
+            s["feats"] = Features(s["att"], s["p_att"], s["fc"], s["masks"], B, feats.L)
+            s["X"], s["c"], s["sl"] = self._new_state(B, dev, s["feats"], 1)
+            s["img_idx"] = torch.arange(B, device=dev, dtype=torch.int64)
+            return s
+
+        def run(s):
+            f = s["feats"]
+            X, c, sl, ws = s["X"], s["c"], s["sl"], s["ws"]
+            X.zero_(); c.zero_(); s["seq"].zero_(); s["lp"].zero_(); s["nunf"].zero_(); s["tok"].zero_()
+            if self.kind == "topdown":
+                check(lib.uic_embed_rows(ptr(f.fc), w.H, ptr(s["img_idx"]), ptr(X[:, sl.fc[0]:]), X.stride(0), B, w.H, B, stream()))
+            self._embed(s["tok"], X, sl)
+            for t in range(T):
+                h = self.core_step(X, c, f, ws)
+                self.logits_of(h, ws["logits"])
+                check(lib.uic_greedy_step(ptr(ws["logits"]), w.V, ptr(s["seq"]), ptr(s["lp"]), ptr(s["unf"]), ptr(s["tok"]),
+                                          ptr(s["nunf"]), t, T, B, w.V, flags, stream()))
+                if t + 1 < T:
+                    self._embed(s["tok"], X, sl)
+            return s["seq"], s["lp"]
+
+        return self._decode(key, alloc, run, feats)
+
+    # ---- beam search (models/AttModel.py:167-196 + models/CaptionModel.py:33-177) -------------------------
+    def beam(self, feats, seq_length, beam_size, decoding_constraint=0, max_ppl=0):
+        w, lib = self.w, self.lib
+        B, dev, T, b = feats.B, feats.att.device, seq_length, beam_size
+        R = B * b
+        tk_flags = _lib.SAMPLE_DECODING_CONSTRAINT if decoding_constraint else 0
+        bs_flags = _lib.BEAM_MAX_PPL if max_ppl else 0
+        key = ("beam", B, b, feats.L, T, tk_flags, bs_flags, feats.masks is not None)
+
+        def alloc():
+            s = {"att": torch.empty_like(feats.att), "p_att": torch.empty_like(feats.p_att),
+                 "fc": None if feats.fc is None else torch.empty_like(feats.fc),
+                 "masks": None if feats.masks is None else torch.empty_like(feats.masks),
+                 "ws": self._workspace(R, dev),
+                 "tk_val": torch.empty(R, b, device=dev), "tk_idx": torch.empty(R, b, dtype=torch.int32, device=dev),
+                 "beam_seq": torch.zeros(B, b, T, dtype=torch.int32, device=dev), "beam_lp": torch.zeros(B, b, T, device=dev),
+                 "beam_sum": torch.zeros(B, b, device=dev),
+                 "done_seq": torch.zeros(B, b, T, dtype=torch.int32, device=dev), "done_lp": torch.zeros(B, b, T, device=dev),
+                 "done_p": torch.zeros(B, b, dtype=torch.float64, device=dev), "done_unaug": torch.zeros(B, b, device=dev),
+                 "done_cnt": torch.zeros(B, dtype=torch.int32, device=dev),
+                 "parent": torch.zeros(R, dtype=torch.int32, device=dev), "tok": torch.zeros(R, dtype=torch.int64, device=dev)}
+            s["feats"] = Features(s["att"], s["p_att"], s["fc"], s["masks"], B, feats.L)
+            s["X"], s["c"], s["sl"] = self._new_state(R, dev, s["feats"], b)
+            s["X2"], s["c2"] = torch.zeros_like(s["X"]), torch.zeros_like(s["c"])
+            s["img_idx"] = torch.arange(R, device=dev, dtype=torch.int64) // b
+            return s
+
+        def run(s):
+            f, ws, sl = s["feats"], s["ws"], s["sl"]
+            for k in ("X", "X2", "c", "c2", "beam_seq", "beam_lp", "beam_sum", "done_seq", "done_lp", "done_p", "done_unaug",
+                      "done_cnt", "tok"):
+                s[k].zero_()
+            bufs = [(s["X"], s["c"]), (s["X2"], s["c2"])]
+            if self.kind == "topdown":
+                for X, _ in bufs:
+                    check(lib.uic_embed_rows(ptr(f.fc), w.H, ptr(s["img_idx"]), ptr(X[:, sl.fc[0]:]), X.stride(0), R, w.H, B, stream()))
+            self._embed(s["tok"], bufs[0][0], sl)  # BOS for every beam row (AttModel.py:186-190)
+            (ga, na), (gb, nb) = sl.gather
+            for t in range(T):
+                X, c = bufs[t % 2]
+                Xn, cn = bufs[(t + 1) % 2]
+                h = self.core_step(X, c, f, ws, beams=b)
+                self.logits_of(h, ws["logits"])
+                check(lib.uic_row_topk(ptr(ws["logits"]), w.V, ptr(s["tok"]) if (tk_flags and t > 0) else None, ptr(s["tk_val"]),
+                                       ptr(s["tk_idx"]), R, w.V, b, tk_flags if t > 0 else 0, stream()))
+                check(lib.uic_beam_step(ptr(s["tk_val"]), ptr(s["tk_idx"]), ptr(s["beam_seq"]), ptr(s["beam_lp"]), ptr(s["beam_sum"]),
+                                        ptr(s["done_seq"]), ptr(s["done_lp"]), ptr(s["done_p"]), ptr(s["done_unaug"]),
+                                        ptr(s["done_cnt"]), ptr(s["parent"]), ptr(s["tok"]), t, T, B, b, bs_flags, stream()))
+                if t + 1 < T:  # the reference's last get_logprobs_state (CaptionModel.py:171-172) has no observable effect
+                    check(lib.uic_beam_gather(ptr(s["parent"]), ptr(X), ptr(Xn), X.stride(0), ga, na, gb, nb, ptr(c), ptr(cn),
+                                              sl.n_state, R, w.H, stream()))
+                    self._embed(s["tok"], Xn, sl)
+            return s["done_seq"], s["done_lp"], s["done_p"], s["done_unaug"], s["done_cnt"]
+
+        return self._decode(key, alloc, run, feats)
+
+    def _decode(self, key, alloc, run, feats):
+        """First call per shape: allocate the static buffers, run the loop eagerly once (warms every
+        kernel), then capture it into a CUDA graph; later calls only refresh the feature tiles and
+        replay.  No host synchronisation happens inside the loop either way."""
+        if not self.use_graphs:
+            s = alloc()
+            self._load_feats(s, feats)
+            return run(s)
+        entry = self._graphs.get(key)
+        if entry is None:
+            s = alloc()
+            self._load_feats(s, feats)
+            run(s)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                out = run(s)
+            entry = (g, s, out)
+            self._graphs[key] = entry
+        g, s, out = entry
+        self._load_feats(s, feats)
+        g.replay()
+        return out
+
+    @staticmethod
+    def _load_feats(s, feats):
+        s["att"].copy_(feats.att)
+        s["p_att"].copy_(feats.p_att)
+        if feats.fc is not None:
+            s["fc"].copy_(feats.fc)
+        if feats.masks is not None:
+            s["masks"].copy_(feats.masks)
+
+    # ---- teacher-forced forward (models/AttModel.py:119-156), no autograd ---------------------------------
+    @torch.no_grad()
+    def teacher_forced_logits(self, feats, seq, n_steps):
+        """Runs `n_steps` teacher-forced steps and returns the fp32 logits (B, T_total, V) view of the
+        time-batched logit GEMM output (rows b*T_total + t); steps >= n_steps are left untouched."""
+        w, lib = self.w, self.lib
+        B, dev = feats.B, feats.att.device
+        T_total = seq.size(1) - 1
+        X, c, sl = self._new_state(B, dev, feats, 1)
+        ws = self._workspace_tf(B, dev)
+        h_all = torch.zeros(B, T_total, w.H, dtype=BF16, device=dev)
+        seq = seq.contiguous()
+        for t in range(n_steps):
+            self._embed(seq[:, t].contiguous(), X, sl)
+            self.core_step(X, c, feats, ws, h_all=h_all[:, t])
+        logits = torch.empty(B * T_total, w.V, dtype=torch.float32, device=dev)
+        gemm(h_all.view(B * T_total, w.H), w.w_logit, w.b_logit, out_f32=logits)
+        return logits.view(B, T_total, w.V)
+
+    def _workspace_tf(self, R, dev):
+        ws = self._workspace(R, dev)
+        del ws["logits"]
+        return ws

@@ -1,0 +1,351 @@
+"""Host-side mirror of the reference's decoder interface (same names, arguments and error behaviour)
+with the arithmetic running in the sm_100a kernels of libuic_b200.so.
+
+Reference surface reproduced here:
+  models/__init__.py:22-59      setup(opt)
+  models/CaptionModel.py:27-31  CaptionModel.forward(*args, mode=...)
+  models/AttModel.py:55-253     AttModel (_prepare_feature, _forward, get_logprobs_state, _sample, _sample_beam)
+  models/AttModel.py:529-601    Attention, Att2in2Core        :421-446  TopDownCore
+  models/AttModel.py:670-690    Att2in2Model, TopDownModel
+Parameter names and shapes are identical to the reference, so `state_dict()`s are interchangeable
+(`model_i2t-best.pth` loads, trainer.py:102).
+
+There is no PyTorch/CPU fallback: modules must live on a CUDA (sm_100) device to be called.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from . import _lib
+from ._lib import check, ptr, stream
+from .engine import BF16, DecoderEngine, Features, Slots
+
+HOT_PATH_MODELS = ("att2in2", "topdown")
+
+
+class CaptionModel(nn.Module):
+    """models/CaptionModel.py:19-31 -- `mode` keyword dispatch to `_forward` / `_sample`."""
+
+    def forward(self, *args, **kwargs):
+        mode = kwargs.pop("mode", "forward")
+        return getattr(self, "_" + mode)(*args, **kwargs)
+
+
+class Attention(nn.Module):
+    """models/AttModel.py:529-558."""
+
+    def __init__(self, opt):
+        super().__init__()
+        self.rnn_size = opt.rnn_size
+        self.att_hid_size = opt.att_hid_size
+        self.h2att = nn.Linear(self.rnn_size, self.att_hid_size)
+        self.alpha_net = nn.Linear(self.att_hid_size, 1)
+
+    def forward(self, h, att_feats, p_att_feats, att_masks=None):
+        _lib.require_device()
+        lib = _lib.load()
+        R, H, A = h.size(0), att_feats.size(-1), self.att_hid_size
+        att = att_feats.reshape(-1, att_feats.numel() // att_feats.size(0) // H, H)
+        n_img, L = att.size(0), att.size(1)
+        if R % n_img:
+            raise ValueError(f"Attention: {R} rows do not divide over {n_img} images")
+        att_b = att if att.dtype == BF16 else _lib.cast_bf16(att.reshape(-1, H).float())
+        p_att = p_att_feats.reshape(-1, A)
+        p_b = p_att if p_att.dtype == BF16 else _lib.cast_bf16(p_att.float())
+        att_h = torch.empty(R, A, device=h.device)
+        _lib.gemm(_lib.cast_bf16(h.float().contiguous()), _lib.cast_bf16(self.h2att.weight.detach()),
+                  self.h2att.bias.detach().float().contiguous(), out_f32=att_h)
+        ctx = torch.empty(R, H, device=h.device)
+        masks = None if att_masks is None else att_masks.reshape(n_img, L).float().contiguous()
+        w = self.alpha_net.weight.detach().float().reshape(-1).contiguous()
+        check(lib.uic_att_step_fwd(ptr(att_h), A, ptr(p_b), ptr(att_b), ptr(w), ptr(masks), None, 0, ptr(ctx), H, None,
+                                   n_img, R // n_img, L, A, H, stream()))
+        return ctx
+
+
+class _CoreBase(nn.Module):
+    """Shared plumbing: a core step through the engine from fp32 API tensors."""
+
+    def forward(self, xt, fc_feats, att_feats, p_att_feats, state, att_masks=None):
+        return self._owner()._core_api(xt, fc_feats, att_feats, p_att_feats, state, att_masks)
+
+
+class Att2in2Core(_CoreBase):
+    """models/AttModel.py:561-601 (parameters a2c, i2h, h2h, attention.*)."""
+
+    def __init__(self, opt):
+        super().__init__()
+        self.rnn_size = opt.rnn_size
+        self.a2c = nn.Linear(opt.rnn_size, 2 * opt.rnn_size)
+        self.i2h = nn.Linear(opt.input_encoding_size, 5 * opt.rnn_size)
+        self.h2h = nn.Linear(opt.rnn_size, 5 * opt.rnn_size)
+        self.dropout = nn.Dropout(opt.drop_prob_lm)
+        self.attention = Attention(opt)
+
+
+class TopDownCore(_CoreBase):
+    """models/AttModel.py:421-446 (parameters att_lstm.*, lang_lstm.*, attention.*)."""
+
+    def __init__(self, opt, use_maxout=False):
+        super().__init__()
+        self.drop_prob_lm = opt.drop_prob_lm
+        self.att_lstm = nn.LSTMCell(opt.input_encoding_size + opt.rnn_size * 2, opt.rnn_size)
+        self.lang_lstm = nn.LSTMCell(opt.rnn_size * 2, opt.rnn_size)
+        self.attention = Attention(opt)
+
+
+class AttModel(CaptionModel):
+    """models/AttModel.py:55-253."""
+
+    kind = None
+
+    def __init__(self, opt):
+        super().__init__()
+        self.vocab_size = opt.vocab_size
+        self.input_encoding_size = opt.input_encoding_size
+        self.rnn_size = opt.rnn_size
+        self.num_layers = opt.num_layers
+        self.drop_prob_lm = opt.drop_prob_lm
+        self.seq_length = opt.seq_length
+        self.fc_feat_size = opt.fc_feat_size
+        self.att_feat_size = opt.att_feat_size
+        self.att_hid_size = opt.att_hid_size
+        self.use_bn = getattr(opt, "use_bn", 0)
+        if self.use_bn:
+            raise NotImplementedError("use_bn != 0 (BatchNorm around att_embed) is not on the B200 hot path yet")
+        if getattr(opt, "logit_layers", 1) != 1:
+            raise NotImplementedError("logit_layers > 1 is not on the B200 hot path")
+        for name, v in (("rnn_size", self.rnn_size), ("input_encoding_size", self.input_encoding_size),
+                        ("att_hid_size", self.att_hid_size), ("att_feat_size", self.att_feat_size),
+                        ("fc_feat_size", self.fc_feat_size)):
+            if v % 8:
+                raise ValueError(f"{name}={v} must be a multiple of 8 (16-byte bf16 rows for TMA)")
+        self.ss_prob = 0.0
+        self.logit_layers = 1
+        self.embed = nn.Sequential(nn.Embedding(self.vocab_size + 1, self.input_encoding_size), nn.ReLU(),
+                                   nn.Dropout(self.drop_prob_lm))
+        self.fc_embed = nn.Sequential(nn.Linear(self.fc_feat_size, self.rnn_size), nn.ReLU(), nn.Dropout(self.drop_prob_lm))
+        self.att_embed = nn.Sequential(nn.Linear(self.att_feat_size, self.rnn_size), nn.ReLU(), nn.Dropout(self.drop_prob_lm))
+        self.logit = nn.Linear(self.rnn_size, self.vocab_size + 1)
+        self.ctx2att = nn.Linear(self.rnn_size, self.att_hid_size)
+        self.done_beams = []
+        self._engine = None
+
+    # the engine is created lazily (needs the CUDA device) and is not part of the state_dict
+    @property
+    def engine(self):
+        if self._engine is None:
+            self._engine = DecoderEngine(self)
+        return self._engine
+
+    def _bind_core(self):
+        owner = self
+        self.core._owner = lambda: owner  # plain closure: no module cycle in the registry
+
+    def init_hidden(self, bsz):
+        weight = next(self.parameters())
+        return (weight.new_zeros(self.num_layers, bsz, self.rnn_size), weight.new_zeros(self.num_layers, bsz, self.rnn_size))
+
+    def clip_att(self, att_feats, att_masks):
+        if att_masks is not None:
+            max_len = att_masks.long().sum(1).max()
+            att_feats = att_feats[:, :max_len].contiguous()
+            att_masks = att_masks[:, :max_len].contiguous()
+        return att_feats, att_masks
+
+    def _check_train_features(self):
+        if self.training and self.drop_prob_lm > 0:
+            raise NotImplementedError("drop_prob_lm > 0 in training mode is not on the B200 hot path yet (use eval() or p=0)")
+
+    def _prepare_feature(self, fc_feats, att_feats, att_masks):
+        """Returns (fc, att, p_att, masks) like the reference; att / p_att are the bf16 operand tiles."""
+        f = self.engine.prepare(fc_feats, att_feats, att_masks)
+        fc = fc_feats if self.kind == "att2in2" else f.fc
+        return fc, f.att, f.p_att, f.masks
+
+    # ---- teacher-forced forward -----------------------------------------------------------------------
+    def _active_steps(self, seq):
+        """Number of steps the reference executes before its all-zero-column break (AttModel.py:148-151)."""
+        T = seq.size(1) - 1
+        if T <= 1:
+            return T
+        empty = (seq[:, 1:T].sum(0) == 0).nonzero()
+        return T if empty.numel() == 0 else int(empty[0]) + 1
+
+    def _forward(self, fc_feats, attri_feats, att_feats, seq, att_masks=None):
+        self._check_train_features()
+        if self.training and self.ss_prob > 0.0:
+            raise NotImplementedError("scheduled sampling (ss_prob > 0) is not on the B200 hot path yet")
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            from .autograd import decoder_logprobs
+            return decoder_logprobs(self, fc_feats, att_feats, seq, att_masks)
+        eng, lib = self.engine, _lib.load()
+        feats = eng.prepare(fc_feats, att_feats, att_masks)
+        n_steps = self._active_steps(seq)
+        logits = eng.teacher_forced_logits(feats, seq, n_steps)
+        B, T, V = logits.shape
+        out = torch.zeros(B, T, V, device=logits.device)
+        if n_steps == T:
+            check(lib.uic_log_softmax_rows(ptr(logits), V, ptr(out), V, B * T, V, stream()))
+        else:  # steps after the break stay zero (:123)
+            for t in range(n_steps):
+                check(lib.uic_log_softmax_rows(ptr(logits[:, t]), T * V, ptr(out[:, t]), T * V, B, V, stream()))
+        return out
+
+    def _forward_loss(self, fc_feats, attri_feats, att_feats, labels, masks, att_masks=None):
+        """Additive fast path: fused teacher-forced forward + masked XE without the
+        (B, T, V) log-prob tensor.  Equals crit(model(fc, attri, att, labels, att_masks), labels[:,1:], masks[:,1:])."""
+        self._check_train_features()
+        from .autograd import decoder_loss
+        return decoder_loss(self, fc_feats, att_feats, labels, masks, att_masks)
+
+    # ---- single step API --------------------------------------------------------------------------------
+    def _feats_from_api(self, fc, att, p_att, att_masks, rows):
+        H, A = self.rnn_size, self.att_hid_size
+        n_img = att.size(0)
+        att3 = att.reshape(n_img, -1, H)
+        L = att3.size(1)
+        # the reference's beam path hands in per-beam expanded copies (AttModel.py:181-184): rows == n_img
+        att_b = att3 if att3.dtype == BF16 else _lib.cast_bf16(att3.reshape(-1, H).float()).view(n_img, L, H)
+        p3 = p_att.reshape(n_img, L, A)
+        p_b = p3 if p3.dtype == BF16 else _lib.cast_bf16(p3.reshape(-1, A).float()).view(n_img, L, A)
+        masks = None if att_masks is None else att_masks.reshape(n_img, L).float().contiguous()
+        fc_b = None
+        if self.kind == "topdown":
+            fc_b = fc if fc.dtype == BF16 else _lib.cast_bf16(fc.float().contiguous())
+        if rows % n_img:
+            raise ValueError(f"{rows} rows do not divide over {n_img} images")
+        return Features(att_b.contiguous(), p_b.contiguous(), fc_b, masks, n_img, L), rows // n_img
+
+    def _step_api(self, xt_or_it, is_token, fc, att, p_att, state, att_masks, want_logprobs):
+        eng, lib = self.engine, _lib.load()
+        w = eng.w
+        R = xt_or_it.size(0)
+        dev = att.device
+        feats, beams = self._feats_from_api(fc, att, p_att, att_masks, R)
+        H, E = w.H, w.E
+        sl = Slots(self.kind, E, H)
+        X = torch.zeros(R, w.Kx, dtype=BF16, device=dev)
+        if feats.fc is not None:
+            fc_rows = feats.fc if feats.fc.size(0) == R else feats.fc.repeat_interleave(beams, 0)
+            X[:, sl.fc[0]:sl.fc[1]] = fc_rows
+        if is_token:
+            eng._embed(xt_or_it.contiguous().long(), X, sl)
+        else:
+            _lib.cast_bf16(xt_or_it.float().contiguous(), X[:, sl.xt[0]:sl.xt[1]])
+        h0, c0 = state[0].float(), state[1].float().contiguous().clone()
+        if self.kind == "att2in2":
+            _lib.cast_bf16(h0[-1].contiguous(), X[:, sl.h_out[0]:sl.h_out[1]])
+        else:
+            _lib.cast_bf16(h0[0].contiguous(), X[:, sl.h_att_prev[0]:sl.h_att_prev[1]])
+            _lib.cast_bf16(h0[1].contiguous(), X[:, sl.h_lang[0]:sl.h_lang[1]])
+        ws = eng._workspace(R, dev)
+        h_out = eng.core_step(X, c0, feats, ws, beams=beams)
+        if self.kind == "att2in2":
+            h_state = h_out.float().unsqueeze(0)
+        else:
+            h_state = torch.stack([X[:, sl.h_att[0]:sl.h_att[1]].float(), h_out.float()])
+        new_state = (h_state, c0)
+        if not want_logprobs:
+            return h_out.float(), new_state
+        eng.logits_of(h_out, ws["logits"])
+        out = torch.empty(R, w.V, device=dev)
+        check(lib.uic_log_softmax_rows(ptr(ws["logits"]), w.V, ptr(out), w.V, R, w.V, stream()))
+        return out, new_state
+
+    @torch.no_grad()
+    def get_logprobs_state(self, it, fc_feats, att_feats, p_att_feats, att_masks, state):
+        """models/AttModel.py:158-165."""
+        return self._step_api(it, True, fc_feats, att_feats, p_att_feats, state, att_masks, True)
+
+    @torch.no_grad()
+    def _core_api(self, xt, fc_feats, att_feats, p_att_feats, state, att_masks):
+        return self._step_api(xt, False, fc_feats, att_feats, p_att_feats, state, att_masks, False)
+
+    # ---- sampling ---------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def _sample_beam(self, fc_feats, att_feats, att_masks=None, opt={}):
+        """models/AttModel.py:167-196; every image of the batch is searched at once on the device."""
+        beam_size = opt.get("beam_size", 10)
+        if opt.get("group_size", 1) != 1:
+            raise NotImplementedError("diverse beam search (group_size > 1) is not on the B200 hot path yet")
+        assert beam_size <= self.vocab_size + 1, "lets assume this for now, otherwise this corner case causes a few headaches down the road. can be dealt with in future if needed"
+        eng = self.engine
+        feats = eng.prepare(fc_feats, att_feats, att_masks)
+        done_seq, done_lp, done_p, done_unaug, done_cnt = eng.beam(
+            feats, self.seq_length, beam_size, opt.get("decoding_constraint", 0), opt.get("max_ppl", 0))
+        # one D2H for everything the reference keeps on the CPU (seq, seqLogprobs, done_beams)
+        done_seq_c, done_lp_c = done_seq.long().cpu(), done_lp.cpu()
+        done_p_c, done_unaug_c, done_cnt_c = done_p.cpu(), done_unaug.cpu(), done_cnt.cpu()
+        self._done_tables = (done_seq_c, done_lp_c, done_p_c, done_unaug_c, done_cnt_c)
+        self.done_beams = _LazyDoneBeams(self._done_tables)
+        return done_seq_c[:, 0].contiguous(), done_lp_c[:, 0].contiguous()
+
+    @torch.no_grad()
+    def _sample(self, fc_feats, attri_feats, att_feats, att_masks=None, opt={}):
+        """models/AttModel.py:198-253."""
+        sample_max = opt.get("sample_max", 1)
+        beam_size = opt.get("beam_size", 1)
+        temperature = opt.get("temperature", 1.0)
+        decoding_constraint = opt.get("decoding_constraint", 0)
+        if beam_size > 1:
+            return self._sample_beam(fc_feats, att_feats, att_masks, opt)
+        if not sample_max:
+            raise NotImplementedError("multinomial sampling (sample_max=0, SCST) is the next row of the scope table, "
+                                      f"not built yet (temperature={temperature})")
+        eng = self.engine
+        feats = eng.prepare(fc_feats, att_feats, att_masks)
+        seq, lp = eng.greedy(feats, self.seq_length, decoding_constraint)
+        return seq.clone(), lp.clone()
+
+
+class _LazyDoneBeams:
+    """`model.done_beams[k]` -> list of dicts {'seq','logps','unaug_p','p'} like the reference
+    (models/CaptionModel.py:157-162), materialised from the device tables on first access."""
+
+    def __init__(self, tables):
+        self._t = tables
+
+    def __len__(self):
+        return self._t[0].size(0)
+
+    def __getitem__(self, k):
+        seq, lp, p, unaug, cnt = self._t
+        return [{"seq": seq[k, j].clone(), "logps": lp[k, j].clone(), "unaug_p": float(unaug[k, j]), "p": float(p[k, j])}
+                for j in range(int(cnt[k]))]
+
+    def __iter__(self):
+        return (self[k] for k in range(len(self)))
+
+
+class Att2in2Model(AttModel):
+    """models/AttModel.py:670-675."""
+    kind = "att2in2"
+
+    def __init__(self, opt):
+        super().__init__(opt)
+        self.core = Att2in2Core(opt)
+        delattr(self, "fc_embed")
+        self.fc_embed = lambda x: x
+        self._bind_core()
+
+
+class TopDownModel(AttModel):
+    """models/AttModel.py:686-690."""
+    kind = "topdown"
+
+    def __init__(self, opt):
+        super().__init__(opt)
+        self.num_layers = 2
+        self.core = TopDownCore(opt)
+        self._bind_core()
+
+
+def setup(opt):
+    """models/__init__.py:22-59 for the models on the hot path."""
+    if opt.caption_model == "att2in2":
+        return Att2in2Model(opt)
+    if opt.caption_model == "topdown":
+        return TopDownModel(opt)
+    raise Exception("Caption model not supported: {}".format(opt.caption_model))
