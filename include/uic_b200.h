@@ -48,6 +48,12 @@ int uic_version(void);
 int64_t uic_launch_count(void);
 /* 0 = tcgen05 tensor-core GEMM (default), 1 = CUDA-core verification GEMM (tests/debug only). */
 int uic_set_gemm_impl(int impl);
+/* Live per-kernel device timing: while enabled, every launch is bracketed by a CUDA event pair on
+ * its stream (do not enable during CUDA-graph capture).  uic_profile_dump synchronises, writes one
+ * "name launches total_ms" line per kernel label into `out` (host buffer) and returns the number
+ * of labels; uic_profile_enable(0/1) clears the records. */
+int uic_profile_enable(int on);
+int64_t uic_profile_dump(char* out, int64_t cap);
 /* Fails with UIC_ERR_DEVICE unless the current device is compute capability 10.x. */
 int uic_check_device(void);
 

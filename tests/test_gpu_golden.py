@@ -36,10 +36,13 @@ def test_teacher_forced_logprobs_and_loss(golden):
     sel = masks[:, 1:].bool()
     err = (out - ref).abs()[sel]
     scale = ref.abs()[sel].clamp_min(1.0)
-    assert float((err / scale).max()) < REL * (30 if "plain" not in golden else 1), float((err / scale).max())
+    # plain fixtures: the north-star tolerance.  The peaked fixtures scale logit.weight by 80, which
+    # scales the bf16 operand rounding of the logit GEMM by the same factor.
+    tol = REL if "plain" in golden["name"] else 80 * REL
+    assert float((err / scale).max()) < tol, float((err / scale).max())
     crit = uic.LanguageModelCriterion(opt)
     loss = crit(out, labels[:, 1:], masks[:, 1:])
-    assert abs(float(loss) - float(golden["out"]["loss"])) <= REL * abs(float(golden["out"]["loss"])) * 3
+    assert abs(float(loss) - float(golden["out"]["loss"])) <= tol * abs(float(golden["out"]["loss"]))
 
 
 @pytest.mark.parametrize("tag,o", [("greedy", {}), ("greedy_dc", {"decoding_constraint": 1})])

@@ -217,7 +217,7 @@ def test_row_topk(R, V, k):
         if flags:
             lp[torch.arange(R), prev] = float("-inf")
         lp[:, V - 1] -= 1000.0
-        ref_val, ref_idx = torch.sort(lp, 1, descending=True, stable=True)
+        ref_val, ref_idx = torch.sort(lp, dim=1, descending=True, stable=True)
         assert torch.equal(idx.long(), ref_idx[:, :k])
         torch.testing.assert_close(val, ref_val[:, :k], rtol=1e-5, atol=3e-5)
 

@@ -21,6 +21,8 @@ SIGNATURES = {
     "uic_launch_count": (_i64, []),
     "uic_set_gemm_impl": (_i, [_i]),
     "uic_check_device": (_i, []),
+    "uic_profile_enable": (_i, [_i]),
+    "uic_profile_dump": (_i64, [C.c_char_p, _i64]),
     "uic_gemm_bf16": (_i, [_p, _i64, _p, _i64, _p, _i64, _p, _i64, _p, _i, _i, _i, _i, _p]),
     "uic_cast_f32_bf16": (_i, [_p, _i64, _p, _i64, _i64, _i64, _i, _p]),
     "uic_embed_rows": (_i, [_p, _i64, _p, _p, _i64, _i, _i, _i, _p]),
@@ -84,6 +86,24 @@ def require_device():
 
 def launch_count():
     return int(load().uic_launch_count())
+
+
+def profile(on):
+    """Enable/disable (and clear) the library's live per-kernel event timing."""
+    check(load().uic_profile_enable(int(on)))
+
+
+def profile_dump():
+    """{label: (launches, total_ms)} since profile(True); synchronises the recorded events."""
+    buf = C.create_string_buffer(1 << 16)
+    n = load().uic_profile_dump(buf, len(buf))
+    if n < 0:
+        check(int(n))
+    out = {}
+    for line in buf.value.decode().splitlines():
+        name, cnt, ms = line.rsplit(" ", 2)
+        out[name] = (int(cnt), float(ms))
+    return out
 
 
 # ---- typed convenience wrappers (validate dtype/contiguity like torch would) -----------------------

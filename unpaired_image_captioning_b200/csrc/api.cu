@@ -7,6 +7,8 @@
 #include <cstring>
 #include <mutex>
 #include <unordered_map>
+#include <utility>
+#include <vector>
 
 #include "uic_internal.h"
 
@@ -24,7 +26,33 @@ int set_error(int code, const char* fmt, ...) {
   return code;
 }
 
-void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+// ---- launch accounting / live per-kernel timing ----------------------------------------------
+struct ProfRec {
+  const char* name;
+  cudaEvent_t a, b;
+};
+static std::atomic<int> g_prof_on{0};
+static std::mutex g_prof_mu;
+static std::vector<ProfRec> g_prof;
+static thread_local int g_prof_open = -1;
+
+void launch_begin(const char* name, cudaStream_t stream) {
+  if (!g_prof_on.load(std::memory_order_relaxed)) return;
+  ProfRec r{name, nullptr, nullptr};
+  if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return;
+  cudaEventRecord(r.a, stream);
+  std::lock_guard<std::mutex> lock(g_prof_mu);
+  g_prof.push_back(r);
+  g_prof_open = static_cast<int>(g_prof.size()) - 1;
+}
+
+void launch_end(cudaStream_t stream) {
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  if (g_prof_open < 0) return;
+  std::lock_guard<std::mutex> lock(g_prof_mu);
+  if (g_prof_open < static_cast<int>(g_prof.size())) cudaEventRecord(g_prof[g_prof_open].b, stream);
+  g_prof_open = -1;
+}
 
 int gemm_impl() {
   int v = g_gemm_impl.load(std::memory_order_relaxed);
@@ -129,6 +157,45 @@ int uic_set_gemm_impl(int impl) {
   g_gemm_impl.store(impl);
   return 0;
 }
+int uic_profile_enable(int on) {
+  std::lock_guard<std::mutex> lock(g_prof_mu);
+  for (auto& r : g_prof) {
+    cudaEventDestroy(r.a);
+    cudaEventDestroy(r.b);
+  }
+  g_prof.clear();
+  g_prof_on.store(on ? 1 : 0);
+  return 0;
+}
+
+int64_t uic_profile_dump(char* out, int64_t cap) {
+  REQUIRE(out != nullptr && cap > 0, UIC_ERR_ARG, "uic_profile_dump: no buffer");
+  std::lock_guard<std::mutex> lock(g_prof_mu);
+  struct Agg {
+    long long n = 0;
+    double ms = 0;
+  };
+  std::vector<std::pair<const char*, Agg>> agg;
+  for (auto& r : g_prof) {
+    float ms = 0.0f;
+    if (cudaEventSynchronize(r.b) != cudaSuccess || cudaEventElapsedTime(&ms, r.a, r.b) != cudaSuccess) continue;
+    size_t i = 0;
+    for (; i < agg.size(); ++i)
+      if (strcmp(agg[i].first, r.name) == 0) break;
+    if (i == agg.size()) agg.push_back({r.name, Agg()});
+    agg[i].second.n += 1;
+    agg[i].second.ms += ms;
+  }
+  int64_t used = 0;
+  for (auto& a : agg) {
+    int w = snprintf(out + used, static_cast<size_t>(cap - used), "%s %lld %.6f\n", a.first, a.second.n, a.second.ms);
+    if (w < 0 || used + w >= cap) break;
+    used += w;
+  }
+  out[used < cap ? used : cap - 1] = '\0';
+  return static_cast<int64_t>(agg.size());
+}
+
 int uic_check_device(void) {
   int dev = 0;
   UIC_CUDA_OK(cudaGetDevice(&dev));

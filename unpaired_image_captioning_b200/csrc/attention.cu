@@ -218,9 +218,10 @@ static int launch_att(const AttParams& p, int n_img, cudaStream_t stream) {
     UIC_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   }
   dim3 grid(n_img, (p.beams + NB - 1) / NB);
+  launch_begin("att_step_fwd", stream);
   kern<<<grid, ATT_THREADS, smem, stream>>>(p);
   UIC_CUDA_OK(cudaGetLastError());
-  count_launch();
+  launch_end(stream);
   return 0;
 }
 

@@ -157,10 +157,11 @@ int beam_step(const float* topk_val, const int32_t* topk_idx, int32_t* beam_seq,
               int64_t* next_tok, int t, int seq_length, int n_img, int beams, int flags, cudaStream_t stream) {
   if (beams > BEAM_MAX || seq_length > BEAM_T_MAX)
     return set_error(UIC_ERR_SHAPE, "beam_step: beams=%d (max %d), seq_length=%d (max %d)", beams, BEAM_MAX, seq_length, BEAM_T_MAX);
+  launch_begin("beam_step", stream);
   beam_step_kernel<<<n_img, 32, 0, stream>>>(topk_val, topk_idx, beam_seq, beam_lp, beam_sum, done_seq, done_lp, done_p,
                                              done_unaug, done_cnt, parent_row, next_tok, t, seq_length, beams, flags);
   UIC_CUDA_OK(cudaGetLastError());
-  count_launch();
+  launch_end(stream);
   return 0;
 }
 

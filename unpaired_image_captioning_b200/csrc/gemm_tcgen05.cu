@@ -13,6 +13,11 @@
 // Tile: BLOCK_M = 128 (one tcgen05.mma M=128, cta_group::1), BLOCK_N in {64,128}, BLOCK_K = 64
 // (= one 128-byte swizzle row of bf16).  8 warps: warp 0 TMA producer, warp 1 MMA issuer (one
 // elected thread), warp 2 TMEM allocator, warps 4-7 epilogue (TMEM -> registers -> global).
+#include <map>
+#include <mutex>
+#include <string>
+#include <tuple>
+
 #include "uic_internal.h"
 #include "uic_ptx.cuh"
 
@@ -247,6 +252,21 @@ __global__ void gemm_bf16_simt_kernel(const __nv_bfloat16* __restrict__ A, long 
 // ------------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------------
+// Interned "gemm_MxNxK" labels for the live profiler (pointers must outlive the records).
+static const char* gemm_label(int M, int N, int K) {
+  static std::mutex mu;
+  static std::map<std::tuple<int, int, int>, std::string> names;
+  std::lock_guard<std::mutex> lock(mu);
+  auto key = std::make_tuple(M, N, K);
+  auto it = names.find(key);
+  if (it == names.end()) {
+    char buf[64];
+    snprintf(buf, sizeof(buf), "gemm_%dx%dx%d", M, N, K);
+    it = names.emplace(key, buf).first;
+  }
+  return it->second.c_str();
+}
+
 template <int BN, int STAGES, bool A_MN, bool B_MN>
 static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const GemmEpilogue& ep, int M, int N, int K,
                      cudaStream_t stream) {
@@ -258,9 +278,10 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const GemmEpi
     configured = true;
   }
   dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM);
+  launch_begin(gemm_label(M, N, K), stream);
   kern<<<grid, GEMM_THREADS, smem, stream>>>(ta, tb, ep, M, N, K);
   UIC_CUDA_OK(cudaGetLastError());
-  count_launch();
+  launch_end(stream);
   return 0;
 }
 
@@ -283,10 +304,11 @@ int gemm_bf16(const void* A, long long lda, const void* B, long long ldb, float*
                   (flags & UIC_GEMM_ACCUMULATE) ? 1 : 0};
   if (gemm_impl() == GEMM_IMPL_SIMT) {
     dim3 grid((N + 15) / 16, (M + 15) / 16), block(16, 16);
+    launch_begin("gemm_bf16_simt", stream);
     gemm_bf16_simt_kernel<<<grid, block, 0, stream>>>(static_cast<const __nv_bfloat16*>(A), lda, a_mn,
                                                       static_cast<const __nv_bfloat16*>(B), ldb, b_mn, ep, M, N, K);
     UIC_CUDA_OK(cudaGetLastError());
-    count_launch();
+    launch_end(stream);
     return 0;
   }
   // TMA needs 16-byte aligned bases and row pitches.

@@ -52,10 +52,11 @@ int cast_f32_bf16(const float* src, long long ld_src, void* dst, long long ld_ds
   const int vec = (cols % 8 == 0) && (ld_src % 4 == 0) && (ld_dst % 8 == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0) &&
                   ((reinterpret_cast<uintptr_t>(dst) & 15) == 0);
   const long long work = vec ? rows * (cols / 8) : rows * cols;
+  launch_begin("cast_f32_bf16", stream);
   cast_f32_bf16_kernel<<<blocks_for(work, 256), 256, 0, stream>>>(src, ld_src, static_cast<__nv_bfloat16*>(dst), ld_dst, rows,
                                                                    cols, relu, vec);
   UIC_CUDA_OK(cudaGetLastError());
-  count_launch();
+  launch_end(stream);
   return 0;
 }
 
@@ -82,10 +83,11 @@ int embed_rows(const void* table, long long ld_table, const int64_t* tok, void* 
   const int vec = (E % 8 == 0) && (ld_table % 8 == 0) && (ld_out % 8 == 0) && ((reinterpret_cast<uintptr_t>(table) & 15) == 0) &&
                   ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
   const long long work = static_cast<long long>(rows) * (vec ? E / 8 : E);
+  launch_begin("embed_rows", stream);
   embed_rows_kernel<<<blocks_for(work, 256), 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(table), ld_table, tok,
                                                                 static_cast<__nv_bfloat16*>(out), ld_out, rows, E, V, vec);
   UIC_CUDA_OK(cudaGetLastError());
-  count_launch();
+  launch_end(stream);
   return 0;
 }
 
@@ -148,20 +150,22 @@ __global__ void lstm_cell_fwd_kernel(const float* __restrict__ gates, long long 
 int lstm_maxout_fwd(const float* sums, long long ld_sums, const float* a2c, long long ld_a2c, const float* c_prev, float* c_out,
                     float* h_f32, void* h_a, long long ld_ha, void* h_b, long long ld_hb, int rows, int H, cudaStream_t stream) {
   HOut o{h_f32, static_cast<__nv_bfloat16*>(h_a), ld_ha, static_cast<__nv_bfloat16*>(h_b), ld_hb};
+  launch_begin("lstm_maxout_fwd", stream);
   lstm_maxout_fwd_kernel<<<blocks_for(static_cast<long long>(rows) * H, 256), 256, 0, stream>>>(sums, ld_sums, a2c, ld_a2c, c_prev,
                                                                                                  c_out, o, rows, H);
   UIC_CUDA_OK(cudaGetLastError());
-  count_launch();
+  launch_end(stream);
   return 0;
 }
 
 int lstm_cell_fwd(const float* gates, long long ld_gates, const float* c_prev, float* c_out, float* h_f32, void* h_a,
                   long long ld_ha, void* h_b, long long ld_hb, int rows, int H, cudaStream_t stream) {
   HOut o{h_f32, static_cast<__nv_bfloat16*>(h_a), ld_ha, static_cast<__nv_bfloat16*>(h_b), ld_hb};
+  launch_begin("lstm_cell_fwd", stream);
   lstm_cell_fwd_kernel<<<blocks_for(static_cast<long long>(rows) * H, 256), 256, 0, stream>>>(gates, ld_gates, c_prev, c_out, o,
                                                                                                rows, H);
   UIC_CUDA_OK(cudaGetLastError());
-  count_launch();
+  launch_end(stream);
   return 0;
 }
 
@@ -185,11 +189,12 @@ __global__ void beam_gather_kernel(const int32_t* __restrict__ parent, const __n
 
 int beam_gather(const int32_t* parent_row, const void* x_src, void* x_dst, long long ld_x, int col0_a, int ncol_a, int col0_b,
                 int ncol_b, const float* c_src, float* c_dst, int n_state, int rows, int H, cudaStream_t stream) {
+  launch_begin("beam_gather", stream);
   beam_gather_kernel<<<rows, 128, 0, stream>>>(parent_row, static_cast<const __nv_bfloat16*>(x_src),
                                                static_cast<__nv_bfloat16*>(x_dst), ld_x, col0_a, ncol_a, col0_b, ncol_b, c_src,
                                                c_dst, n_state, rows, H);
   UIC_CUDA_OK(cudaGetLastError());
-  count_launch();
+  launch_end(stream);
   return 0;
 }
 
@@ -209,9 +214,10 @@ __global__ void zero_padded_rows_kernel(__nv_bfloat16* __restrict__ x, const flo
 }
 
 int zero_padded_rows(void* x, const float* masks, int n_img, int L, int H, cudaStream_t stream) {
+  launch_begin("zero_padded_rows", stream);
   zero_padded_rows_kernel<<<n_img * L, 128, 0, stream>>>(static_cast<__nv_bfloat16*>(x), masks, L, H);
   UIC_CUDA_OK(cudaGetLastError());
-  count_launch();
+  launch_end(stream);
   return 0;
 }
 

@@ -12,7 +12,11 @@ namespace uic {
 enum { GEMM_IMPL_TCGEN05 = 0, GEMM_IMPL_SIMT = 1 };
 
 int set_error(int code, const char* fmt, ...);
-void count_launch();
+// Launch accounting: every kernel launch is bracketed by launch_begin / launch_end.  They count
+// launches (uic_launch_count) and, when profiling is enabled (uic_profile_enable), record a CUDA
+// event pair on the launching stream so bench.py can report per-kernel device time live.
+void launch_begin(const char* name, cudaStream_t stream);
+void launch_end(cudaStream_t stream);
 int gemm_impl();
 
 // Cached cuTensorMapEncodeTiled for a row-major bf16 matrix [rows, cols] with pitch ld (elements),

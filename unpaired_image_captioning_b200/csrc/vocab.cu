@@ -80,9 +80,10 @@ __global__ void __launch_bounds__(ROW_THREADS) log_softmax_rows_kernel(const flo
 }
 
 int log_softmax_rows(const float* logits, long long ld, float* out, long long ld_out, int rows, int V, cudaStream_t stream) {
+  launch_begin("log_softmax_rows", stream);
   log_softmax_rows_kernel<<<rows, ROW_THREADS, 0, stream>>>(logits, ld, out, ld_out, V);
   UIC_CUDA_OK(cudaGetLastError());
-  count_launch();
+  launch_end(stream);
   return 0;
 }
 
@@ -108,9 +109,10 @@ __global__ void __launch_bounds__(ROW_THREADS) lse_xent_fwd_kernel(const float* 
 
 int lse_xent_fwd(const float* logits, long long ld, const int64_t* target, const float* mask, float* lse, float* nll, int rows,
                  int V, cudaStream_t stream) {
+  launch_begin("lse_xent_fwd", stream);
   lse_xent_fwd_kernel<<<rows, ROW_THREADS, 0, stream>>>(logits, ld, target, mask, lse, nll, V);
   UIC_CUDA_OK(cudaGetLastError());
-  count_launch();
+  launch_end(stream);
   return 0;
 }
 
@@ -174,10 +176,11 @@ __global__ void __launch_bounds__(ROW_THREADS) greedy_step_kernel(const float* _
 
 int greedy_step(const float* logits, long long ld, int64_t* seq, float* seq_lp, uint8_t* unfinished, int64_t* next_tok,
                 int32_t* n_unfinished, int t, int seq_length, int rows, int V, int flags, cudaStream_t stream) {
+  launch_begin("greedy_step", stream);
   greedy_step_kernel<<<rows, ROW_THREADS, 0, stream>>>(logits, ld, seq, seq_lp, unfinished, next_tok, n_unfinished, t, seq_length,
                                                        V, flags);
   UIC_CUDA_OK(cudaGetLastError());
-  count_launch();
+  launch_end(stream);
   return 0;
 }
 
@@ -270,6 +273,7 @@ __global__ void __launch_bounds__(ROW_THREADS) row_topk_kernel(const float* __re
 
 int row_topk(const float* logits, long long ld, const int64_t* prev_tok, float* topk_val, int32_t* topk_idx, int rows, int V,
              int k, int flags, cudaStream_t stream) {
+  launch_begin("row_topk", stream);
   if (k <= 4)
     row_topk_kernel<4><<<rows, ROW_THREADS, 0, stream>>>(logits, ld, prev_tok, topk_val, topk_idx, V, k, flags);
   else if (k <= 8)
@@ -277,7 +281,7 @@ int row_topk(const float* logits, long long ld, const int64_t* prev_tok, float* 
   else
     row_topk_kernel<16><<<rows, ROW_THREADS, 0, stream>>>(logits, ld, prev_tok, topk_val, topk_idx, V, k, flags);
   UIC_CUDA_OK(cudaGetLastError());
-  count_launch();
+  launch_end(stream);
   return 0;
 }
 

@@ -109,6 +109,8 @@ class DecoderEngine:
         self._packed = None
         self._graphs = {}
         self.use_graphs = True
+        self._capture_launches = 0
+        self._replayed_launches = 0
         self.lib = _lib.load()
 
     # ---- weights ---------------------------------------------------------------------------------
@@ -318,17 +320,25 @@ class DecoderEngine:
         if entry is None:
             s = alloc()
             self._load_feats(s, feats)
+            n0 = _lib.launch_count()
             run(s)
+            n_kernels = _lib.launch_count() - n0      # library launches inside one decode loop
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 out = run(s)
-            entry = (g, s, out)
+            self._capture_launches += n_kernels        # issued into the graph, not onto the device
+            entry = (g, s, out, n_kernels)
             self._graphs[key] = entry
-        g, s, out = entry
+        g, s, out, n_kernels = entry
         self._load_feats(s, feats)
         g.replay()
+        self._replayed_launches += n_kernels
         return out
+
+    def launches(self):
+        """Kernels of this library executed on the device so far (eager launches + graph replays)."""
+        return _lib.launch_count() - self._capture_launches + self._replayed_launches
 
     @staticmethod
     def _load_feats(s, feats):
