@@ -138,6 +138,47 @@ int uic_beam_step(const float* topk_val, const int32_t* topk_idx, int32_t* beam_
 int uic_beam_gather(const int32_t* parent_row, const void* x_src, void* x_dst, int64_t ld_x, int col0_a, int ncol_a,
                     int col0_b, int ncol_b, const float* c_src, float* c_dst, int n_state, int rows, int H, void* stream);
 
+/* ---- backward (the reference gets these from torch autograd, trainer.py:173) --------------------
+ * Gradients that feed a tcgen05 dgrad/wgrad GEMM are emitted directly as bf16 operands. */
+
+/* nn.LSTMCell backward.  dh = dh0 + dh1 + dh2 (each optional, own pitch); gates are the saved
+ * pre-activations (rows x 4H); writes d gates (bf16) and dc_prev. */
+int uic_lstm_cell_bwd(const float* gates, int64_t ld_gates, const float* c_prev, const float* c, const float* dh0, int64_t ld0,
+                      const float* dh1, int64_t ld1, const float* dh2, int64_t ld2, const float* dc_next, void* dgates_bf16,
+                      int64_t ld_dg, float* dc_prev, int rows, int H, void* stream);
+/* Att2in2 maxout cell backward (models/AttModel.py:585-597): writes d sums (rows x 5H, bf16),
+ * d a2c (rows x 2H, bf16) and dc_prev. */
+int uic_lstm_maxout_bwd(const float* sums, int64_t ld_sums, const float* a2c, int64_t ld_a2c, const float* c_prev, const float* c,
+                        const float* dh0, int64_t ld0, const float* dh1, int64_t ld1, const float* dc_next, void* dsums_bf16,
+                        int64_t ld_ds, void* da2c_bf16, int64_t ld_da, float* dc_prev, int rows, int H, void* stream);
+/* Attention step backward for rows == images (teacher forcing): from d ctx and the saved alpha,
+ * de[r,l] = alpha (d alpha - sum alpha d alpha) and d att_h[r,a] = w_a sum_l de (1 - tanh^2). */
+int uic_att_step_bwd(const float* dctx, int64_t ld_dctx, const float* alpha, const void* p_att_bf16, const void* att_bf16,
+                     const float* att_h, int64_t ld_att_h, const float* w_alpha, float* de, void* datt_h_bf16, int64_t ld_dah,
+                     int rows, int L, int A, int H, void* stream);
+/* Deferred gradients of the feature tiles over all T steps at once:
+ * d att (B,L,H) fp32, d p_att (B,L,A) bf16 and d w_alpha (A, accumulated).  The per-step vectors are
+ * addressed as base + t*stride_t + b*ld. */
+int uic_att_tiles_bwd(const float* de_all, const float* alpha_all, const float* dctx_all, int64_t dctx_stride_t, int64_t ld_dctx,
+                      const float* att_h_all, int64_t ah_stride_t, int64_t ld_ah, const void* p_att_bf16, const float* w_alpha,
+                      float* datt, void* dp_att_bf16, float* dw_alpha, int T, int B, int L, int A, int H, void* stream);
+/* d logits = (softmax(logits) - onehot(target)) * mask * inv_norm[0] * grad_scale, bf16, pitch ld_d
+ * (>= V, padding columns are zeroed).  Backward of uic_lse_xent_fwd / misc/criterion.py:143-150. */
+int uic_lse_xent_bwd(const float* logits, int64_t ld, const float* lse, const int64_t* target, const float* mask,
+                     const float* inv_norm, float grad_scale, void* dlogits_bf16, int64_t ld_d, int rows, int V, void* stream);
+/* d logits = d lp - exp(lp) * rowsum(d lp): backward of uic_log_softmax_rows for the dense API path. */
+int uic_log_softmax_bwd(const float* dlp, int64_t ld_dlp, const float* lp, int64_t ld_lp, void* dlogits_bf16, int64_t ld_d,
+                        int rows, int V, void* stream);
+/* out[c] += sum_r x[r,c] (bias gradients); x is bf16 (is_bf16 != 0) or fp32. */
+int uic_col_sum(const void* x, int is_bf16, int64_t ld, float* out, int rows, int cols, void* stream);
+/* dEmb[tok[r], :] += dxt[r, :] where ReLU(Emb) was active (backward of uic_embed_rows). */
+int uic_embed_bwd(const float* dxt, int64_t ld, const int64_t* tok, const void* table_relu_bf16, float* demb, int64_t rows, int E,
+                  int V, void* stream);
+/* out_bf16[i] = y_bf16[i] > 0 ? x[i] : 0 (ReLU backward fused with the operand cast). */
+int uic_relu_bwd_cast(const float* x, const void* y_bf16, void* out_bf16, int64_t n, void* stream);
+/* dst[b, j] = sum_t src[t*stride_t + b*ld + col0 + j]. */
+int uic_reduce_time(const float* src, int64_t stride_t, int64_t ld, int col0, float* dst, int T, int rows, int n, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -14,4 +14,5 @@ run att tests/test_gpu_kernels.py -m gpu -k att_step
 run misc tests/test_gpu_kernels.py -m gpu -k "not gemm and not att_step"
 run golden tests/test_gpu_golden.py -m gpu
 run oracle tests/test_gpu_oracle.py -m gpu
+run train tests/test_gpu_train.py -m gpu
 for f in "$@"; do :; done

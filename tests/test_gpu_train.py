@@ -1,0 +1,85 @@
+"""Gradients of the CUDA training path (fused loss and dense log-prob API) against the reference's
+autograd gradients stored in the golden fixtures, and against the CPU oracle at real layer sizes."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+import unpaired_image_captioning_b200 as uic  # noqa: E402
+from oracle import decoder_oracle as O  # noqa: E402
+from unpaired_image_captioning_b200 import synth  # noqa: E402
+from parity import load_model, opt_kwargs_from_sd  # noqa: E402
+
+
+def _grad_errors(model, ref_grads):
+    """max |g - ref| / max |ref| per parameter."""
+    errs = {}
+    for name, p in model.named_parameters():
+        ref = ref_grads[name].to(p.device)
+        g = p.grad if p.grad is not None else torch.zeros_like(p)
+        denom = float(ref.abs().max())
+        errs[name] = float((g - ref).abs().max()) / denom if denom > 0 else float(g.abs().max())
+    return errs
+
+
+def _setup(golden):
+    T = golden["greedy"]["seq"].shape[1]
+    model, opt = load_model(uic, synth, golden["sd"], golden["kind"], opt_kwargs_from_sd(golden["sd"], golden["kind"], T))
+    model.train()
+    i = golden["in"]
+    cu = lambda t: None if t is None else t.cuda()
+    return model, opt, cu(i["fc"]), cu(i["att"]), cu(i["labels"]), cu(i["masks"]), cu(i.get("att_masks"))
+
+
+@pytest.mark.parametrize("mode", ["fused", "dense"])
+def test_gradients_match_reference_autograd(golden, mode):
+    model, opt, fc, att, labels, masks, am = _setup(golden)
+    if mode == "fused":
+        loss = model(fc, None, att, labels, masks, am, mode="forward_loss")
+    else:
+        out = model(fc, None, att, labels, am)
+        assert out.requires_grad
+        loss = uic.LanguageModelCriterion(opt)(out, labels[:, 1:], masks[:, 1:])
+    loss.backward()
+    ref_loss = float(golden["out"]["loss"])
+    tol = 2e-2 if "plain" in golden["name"] else 8e-2      # peaked fixtures scale logit.weight by 80
+    assert abs(float(loss) - ref_loss) <= tol * abs(ref_loss)
+    errs = _grad_errors(model, golden["grad"])
+    bad = {k: v for k, v in errs.items() if v > tol}
+    assert not bad, bad
+
+
+@pytest.mark.parametrize("kind,L,B", [("att2in2", 49, 6), ("topdown", 36, 8)])
+def test_gradients_match_oracle_at_real_widths(kind, L, B):
+    opt = synth.make_opt(caption_model=kind, vocab_size=9999, rnn_size=512, input_encoding_size=512, att_hid_size=512, seq_length=16)
+    sd = synth.init_state_dict(opt, seed=3)
+    fc, att = synth.make_features(B, L, 2048, seed=3)
+    labels, masks = synth.make_captions(B, 16, 9999, seed=3)
+    ref_loss, ref_grads = O.loss_and_grads(sd, kind, fc, att, labels, masks)
+    model = uic.setup(opt)
+    model.load_state_dict(sd)
+    model = model.cuda().train()
+    loss = model(fc.cuda(), None, att.cuda(), labels.cuda(), masks.cuda(), None, mode="forward_loss")
+    loss.backward()
+    assert abs(float(loss) - float(ref_loss)) < 1e-3 * float(ref_loss)
+    errs = _grad_errors(model, ref_grads)
+    bad = {k: v for k, v in errs.items() if v > 3e-2}
+    assert not bad, bad
+
+
+def test_loss_matches_dense_criterion_and_uses_global_normaliser():
+    opt, cfg = synth.opt_for("tiny_topdown")
+    sd = synth.init_state_dict(opt, seed=9)
+    model = uic.setup(opt)
+    model.load_state_dict(sd)
+    model = model.cuda().train()
+    fc, att = synth.make_features(5, 7, 64, seed=9)
+    labels, masks = synth.make_captions(5, 6, 51, seed=9, min_len=2)
+    fc, att, labels, masks = fc.cuda(), att.cuda(), labels.cuda(), masks.cuda()
+    fused = model(fc, None, att, labels, masks, None, mode="forward_loss")
+    with torch.no_grad():
+        dense = uic.LanguageModelCriterion(opt)(model(fc, None, att, labels, None), labels[:, 1:], masks[:, 1:])
+    torch.testing.assert_close(fused.detach(), dense, rtol=1e-4, atol=1e-5)
+    twice = masks[:, 1:].sum() * 2
+    half = model(fc, None, att, labels, masks, None, mode="forward_loss", global_mask_sum=twice)
+    torch.testing.assert_close(half.detach() * 2, fused.detach(), rtol=1e-5, atol=1e-6)

@@ -36,6 +36,16 @@ SIGNATURES = {
     "uic_row_topk": (_i, [_p, _i64, _p, _p, _p, _i, _i, _i, _i, _p]),
     "uic_beam_step": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p]),
     "uic_beam_gather": (_i, [_p, _p, _p, _i64, _i, _i, _i, _i, _p, _p, _i, _i, _i, _p]),
+    "uic_lstm_cell_bwd": (_i, [_p, _i64, _p, _p, _p, _i64, _p, _i64, _p, _i64, _p, _p, _i64, _p, _i, _i, _p]),
+    "uic_lstm_maxout_bwd": (_i, [_p, _i64, _p, _i64, _p, _p, _p, _i64, _p, _i64, _p, _p, _i64, _p, _i64, _p, _i, _i, _p]),
+    "uic_att_step_bwd": (_i, [_p, _i64, _p, _p, _p, _p, _i64, _p, _p, _p, _i64, _i, _i, _i, _i, _p]),
+    "uic_att_tiles_bwd": (_i, [_p, _p, _p, _i64, _i64, _p, _i64, _i64, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p]),
+    "uic_lse_xent_bwd": (_i, [_p, _i64, _p, _p, _p, _p, _f, _p, _i64, _i, _i, _p]),
+    "uic_log_softmax_bwd": (_i, [_p, _i64, _p, _i64, _p, _i64, _i, _i, _p]),
+    "uic_col_sum": (_i, [_p, _i, _i64, _p, _i, _i, _p]),
+    "uic_embed_bwd": (_i, [_p, _i64, _p, _p, _p, _i64, _i, _i, _p]),
+    "uic_relu_bwd_cast": (_i, [_p, _p, _p, _i64, _p]),
+    "uic_reduce_time": (_i, [_p, _i64, _i64, _i, _p, _i, _i, _i, _p]),
 }
 
 GEMM_RELU, GEMM_ACCUMULATE, GEMM_A_MN, GEMM_B_MN = 1, 2, 4, 8

@@ -309,3 +309,87 @@ int uic_beam_gather(const int32_t* parent_row, const void* x_src, void* x_dst, i
 }
 
 }  // extern "C"
+
+// ---- backward entry points ------------------------------------------------------------------------
+extern "C" {
+
+int uic_lstm_cell_bwd(const float* gates, int64_t ld_gates, const float* c_prev, const float* c, const float* dh0, int64_t ld0,
+                      const float* dh1, int64_t ld1, const float* dh2, int64_t ld2, const float* dc_next, void* dgates_bf16,
+                      int64_t ld_dg, float* dc_prev, int rows, int H, void* stream) {
+  REQUIRE(gates && c && dgates_bf16 && dc_prev, UIC_ERR_ARG, "uic_lstm_cell_bwd: null pointer");
+  if (rows == 0) return 0;
+  return lstm_cell_bwd(gates, ld_gates, c_prev, c, dh0, ld0, dh1, ld1, dh2, ld2, dc_next, dgates_bf16, ld_dg, dc_prev, rows, H,
+                       ST(stream));
+}
+
+int uic_lstm_maxout_bwd(const float* sums, int64_t ld_sums, const float* a2c, int64_t ld_a2c, const float* c_prev, const float* c,
+                        const float* dh0, int64_t ld0, const float* dh1, int64_t ld1, const float* dc_next, void* dsums_bf16,
+                        int64_t ld_ds, void* da2c_bf16, int64_t ld_da, float* dc_prev, int rows, int H, void* stream) {
+  REQUIRE(sums && a2c && c && dsums_bf16 && da2c_bf16 && dc_prev, UIC_ERR_ARG, "uic_lstm_maxout_bwd: null pointer");
+  if (rows == 0) return 0;
+  return lstm_maxout_bwd(sums, ld_sums, a2c, ld_a2c, c_prev, c, dh0, ld0, dh1, ld1, dc_next, dsums_bf16, ld_ds, da2c_bf16, ld_da,
+                         dc_prev, rows, H, ST(stream));
+}
+
+int uic_att_step_bwd(const float* dctx, int64_t ld_dctx, const float* alpha, const void* p_att_bf16, const void* att_bf16,
+                     const float* att_h, int64_t ld_att_h, const float* w_alpha, float* de, void* datt_h_bf16, int64_t ld_dah,
+                     int rows, int L, int A, int H, void* stream) {
+  REQUIRE(dctx && alpha && p_att_bf16 && att_bf16 && att_h && w_alpha && de && datt_h_bf16, UIC_ERR_ARG,
+          "uic_att_step_bwd: null pointer");
+  if (rows == 0) return 0;
+  return att_step_bwd(dctx, ld_dctx, alpha, p_att_bf16, att_bf16, att_h, ld_att_h, w_alpha, de, datt_h_bf16, ld_dah, rows, L, A, H,
+                      ST(stream));
+}
+
+int uic_att_tiles_bwd(const float* de_all, const float* alpha_all, const float* dctx_all, int64_t dctx_stride_t, int64_t ld_dctx,
+                      const float* att_h_all, int64_t ah_stride_t, int64_t ld_ah, const void* p_att_bf16, const float* w_alpha,
+                      float* datt, void* dp_att_bf16, float* dw_alpha, int T, int B, int L, int A, int H, void* stream) {
+  REQUIRE(de_all && alpha_all && dctx_all && att_h_all && p_att_bf16 && w_alpha && datt && dp_att_bf16 && dw_alpha, UIC_ERR_ARG,
+          "uic_att_tiles_bwd: null pointer");
+  if (B == 0 || T == 0) return 0;
+  return att_tiles_bwd(de_all, alpha_all, dctx_all, dctx_stride_t, ld_dctx, att_h_all, ah_stride_t, ld_ah, p_att_bf16, w_alpha, datt,
+                       dp_att_bf16, dw_alpha, T, B, L, A, H, ST(stream));
+}
+
+int uic_lse_xent_bwd(const float* logits, int64_t ld, const float* lse, const int64_t* target, const float* mask,
+                     const float* inv_norm, float grad_scale, void* dlogits_bf16, int64_t ld_d, int rows, int V, void* stream) {
+  REQUIRE(logits && lse && target && mask && inv_norm && dlogits_bf16, UIC_ERR_ARG, "uic_lse_xent_bwd: null pointer");
+  REQUIRE(ld_d >= V, UIC_ERR_SHAPE, "uic_lse_xent_bwd: ld_d=%lld < V=%d", (long long)ld_d, V);
+  if (rows == 0) return 0;
+  return lse_xent_bwd(logits, ld, lse, target, mask, inv_norm, grad_scale, dlogits_bf16, ld_d, rows, V, ST(stream));
+}
+
+int uic_log_softmax_bwd(const float* dlp, int64_t ld_dlp, const float* lp, int64_t ld_lp, void* dlogits_bf16, int64_t ld_d,
+                        int rows, int V, void* stream) {
+  REQUIRE(dlp && lp && dlogits_bf16, UIC_ERR_ARG, "uic_log_softmax_bwd: null pointer");
+  REQUIRE(ld_d >= V, UIC_ERR_SHAPE, "uic_log_softmax_bwd: ld_d=%lld < V=%d", (long long)ld_d, V);
+  if (rows == 0) return 0;
+  return log_softmax_bwd(dlp, ld_dlp, lp, ld_lp, dlogits_bf16, ld_d, rows, V, ST(stream));
+}
+
+int uic_col_sum(const void* x, int is_bf16, int64_t ld, float* out, int rows, int cols, void* stream) {
+  REQUIRE(x && out, UIC_ERR_ARG, "uic_col_sum: null pointer");
+  if (rows == 0 || cols == 0) return 0;
+  return col_sum(x, is_bf16, ld, out, rows, cols, ST(stream));
+}
+
+int uic_embed_bwd(const float* dxt, int64_t ld, const int64_t* tok, const void* table_relu_bf16, float* demb, int64_t rows, int E,
+                  int V, void* stream) {
+  REQUIRE(dxt && tok && table_relu_bf16 && demb, UIC_ERR_ARG, "uic_embed_bwd: null pointer");
+  if (rows == 0) return 0;
+  return embed_bwd(dxt, ld, tok, table_relu_bf16, demb, rows, E, V, ST(stream));
+}
+
+int uic_relu_bwd_cast(const float* x, const void* y_bf16, void* out_bf16, int64_t n, void* stream) {
+  REQUIRE(x && y_bf16 && out_bf16, UIC_ERR_ARG, "uic_relu_bwd_cast: null pointer");
+  if (n == 0) return 0;
+  return relu_bwd_cast(x, y_bf16, out_bf16, n, ST(stream));
+}
+
+int uic_reduce_time(const float* src, int64_t stride_t, int64_t ld, int col0, float* dst, int T, int rows, int n, void* stream) {
+  REQUIRE(src && dst, UIC_ERR_ARG, "uic_reduce_time: null pointer");
+  if (rows == 0 || n == 0) return 0;
+  return reduce_time(src, stride_t, ld, col0, dst, T, rows, n, ST(stream));
+}
+
+}  // extern "C"

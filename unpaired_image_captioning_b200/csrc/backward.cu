@@ -1,0 +1,482 @@
+// Backward kernels of the teacher-forced decoder step (BPTT through Att2in2Core / TopDownCore,
+// Attention, log-softmax + masked cross-entropy).  The reference gets all of this from autograd
+// over ~30 ATen kernels per step (trainer.py:173); here every step's backward is a handful of
+// fused kernels plus tcgen05 dgrad GEMMs, and everything that can be deferred is time-batched:
+//   * weight gradients: one wgrad GEMM per weight over all T steps (K = T*B), MN-major operands;
+//   * the gradients w.r.t. the feature tiles (att, p_att) are NOT read-modify-written every step:
+//     each step only stores de (B, L); one pass at the end rebuilds sum_t(...) per tile element.
+#include "uic_internal.h"
+#include "uic_ptx.cuh"
+
+namespace uic {
+
+static inline int grid_for(long long work, int threads) {
+  long long b = (work + threads - 1) / threads;
+  const long long cap = 148LL * 16;
+  return static_cast<int>(b < 1 ? 1 : (b > cap ? cap : b));
+}
+
+struct Addends {  // up to three fp32 (rows x H) matrices with their own pitches, any may be null
+  const float* p[3];
+  long long ld[3];
+};
+__device__ __forceinline__ float add3(const Addends& a, int r, int j) {
+  float v = 0.0f;
+#pragma unroll
+  for (int q = 0; q < 3; ++q)
+    if (a.p[q]) v += a.p[q][static_cast<long long>(r) * a.ld[q] + j];
+  return v;
+}
+
+// ---- torch.nn.LSTMCell backward (gate order i, f, g, o) ---------------------------------------------
+__global__ void lstm_cell_bwd_kernel(const float* __restrict__ gates, long long ld_gates, const float* __restrict__ c_prev,
+                                     const float* __restrict__ c, Addends dh, const float* __restrict__ dc_next,
+                                     __nv_bfloat16* __restrict__ dgates, long long ld_dg, float* __restrict__ dc_prev, int rows,
+                                     int H) {
+  const long long total = static_cast<long long>(rows) * H;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int r = static_cast<int>(idx / H), j = static_cast<int>(idx - static_cast<long long>(r) * H);
+    const float* g4 = gates + r * ld_gates;
+    const float ig = sigmoid_acc(g4[j]), fg = sigmoid_acc(g4[H + j]), gg = tanhf(g4[2 * H + j]), og = sigmoid_acc(g4[3 * H + j]);
+    const float tc = tanhf(c[idx]);
+    const float dhv = add3(dh, r, j);
+    const float dc = (dc_next ? dc_next[idx] : 0.0f) + dhv * og * (1.0f - tc * tc);
+    const float cp = c_prev ? c_prev[idx] : 0.0f;
+    __nv_bfloat16* d = dgates + r * ld_dg;
+    d[j] = __float2bfloat16_rn(dc * gg * ig * (1.0f - ig));
+    d[H + j] = __float2bfloat16_rn(dc * cp * fg * (1.0f - fg));
+    d[2 * H + j] = __float2bfloat16_rn(dc * ig * (1.0f - gg * gg));
+    d[3 * H + j] = __float2bfloat16_rn(dhv * tc * og * (1.0f - og));
+    dc_prev[idx] = dc * fg;
+  }
+}
+
+int lstm_cell_bwd(const float* gates, long long ld_gates, const float* c_prev, const float* c, const float* dh0, long long ld0,
+                  const float* dh1, long long ld1, const float* dh2, long long ld2, const float* dc_next, void* dgates,
+                  long long ld_dg, float* dc_prev, int rows, int H, cudaStream_t stream) {
+  Addends a{{dh0, dh1, dh2}, {ld0, ld1, ld2}};
+  launch_begin("lstm_cell_bwd", stream);
+  lstm_cell_bwd_kernel<<<grid_for(static_cast<long long>(rows) * H, 256), 256, 0, stream>>>(
+      gates, ld_gates, c_prev, c, a, dc_next, static_cast<__nv_bfloat16*>(dgates), ld_dg, dc_prev, rows, H);
+  UIC_CUDA_OK(cudaGetLastError());
+  launch_end(stream);
+  return 0;
+}
+
+// ---- Att2in2 maxout cell backward (models/AttModel.py:585-597) ------------------------------------------
+__global__ void lstm_maxout_bwd_kernel(const float* __restrict__ sums, long long ld_sums, const float* __restrict__ a2c,
+                                       long long ld_a2c, const float* __restrict__ c_prev, const float* __restrict__ c,
+                                       Addends dh, const float* __restrict__ dc_next, __nv_bfloat16* __restrict__ dsums,
+                                       long long ld_ds, __nv_bfloat16* __restrict__ da2c, long long ld_da,
+                                       float* __restrict__ dc_prev, int rows, int H) {
+  const long long total = static_cast<long long>(rows) * H;
+  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
+       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int r = static_cast<int>(idx / H), j = static_cast<int>(idx - static_cast<long long>(r) * H);
+    const float* s = sums + r * ld_sums;
+    const float* a = a2c + r * ld_a2c;
+    const float ig = sigmoid_acc(s[j]), fg = sigmoid_acc(s[H + j]), og = sigmoid_acc(s[2 * H + j]);
+    const float p1 = s[3 * H + j] + a[j], p2 = s[4 * H + j] + a[H + j];
+    const float g = fmaxf(p1, p2);
+    const float tc = tanhf(c[idx]);
+    const float dhv = add3(dh, r, j);
+    const float dc = (dc_next ? dc_next[idx] : 0.0f) + dhv * og * (1.0f - tc * tc);
+    const float cp = c_prev ? c_prev[idx] : 0.0f;
+    const float dg = dc * ig;
+    // torch.max(a, b) routes the gradient to the larger input and splits it on exact ties
+    const float d1 = p1 > p2 ? dg : (p1 == p2 ? 0.5f * dg : 0.0f);
+    const float d2 = dg - d1;
+    __nv_bfloat16* d = dsums + r * ld_ds;
+    d[j] = __float2bfloat16_rn(dc * g * ig * (1.0f - ig));
+    d[H + j] = __float2bfloat16_rn(dc * cp * fg * (1.0f - fg));
+    d[2 * H + j] = __float2bfloat16_rn(dhv * tc * og * (1.0f - og));
+    d[3 * H + j] = __float2bfloat16_rn(d1);
+    d[4 * H + j] = __float2bfloat16_rn(d2);
+    da2c[r * ld_da + j] = __float2bfloat16_rn(d1);
+    da2c[r * ld_da + H + j] = __float2bfloat16_rn(d2);
+    dc_prev[idx] = dc * fg;
+  }
+}
+
+int lstm_maxout_bwd(const float* sums, long long ld_sums, const float* a2c, long long ld_a2c, const float* c_prev, const float* c,
+                    const float* dh0, long long ld0, const float* dh1, long long ld1, const float* dc_next, void* dsums,
+                    long long ld_ds, void* da2c, long long ld_da, float* dc_prev, int rows, int H, cudaStream_t stream) {
+  Addends a{{dh0, dh1, nullptr}, {ld0, ld1, 0}};
+  launch_begin("lstm_maxout_bwd", stream);
+  lstm_maxout_bwd_kernel<<<grid_for(static_cast<long long>(rows) * H, 256), 256, 0, stream>>>(
+      sums, ld_sums, a2c, ld_a2c, c_prev, c, a, dc_next, static_cast<__nv_bfloat16*>(dsums), ld_ds,
+      static_cast<__nv_bfloat16*>(da2c), ld_da, dc_prev, rows, H);
+  UIC_CUDA_OK(cudaGetLastError());
+  launch_end(stream);
+  return 0;
+}
+
+// ---- attention step backward: de (rows, L) and d att_h (rows, A) --------------------------------------
+// One CTA per row (= image in teacher-forced training).  Phase 1 streams the att tile to get
+// d alpha_l = <dctx, att_l>; the softmax Jacobian gives de_l = alpha_l (d alpha_l - sum alpha d alpha);
+// phase 2 streams the p_att tile for d att_h[a] = w_a sum_l de_l (1 - tanh^2(p_att[l,a] + att_h[a])).
+constexpr int ATTB_THREADS = 256;
+constexpr int ATTB_WARPS = ATTB_THREADS / 32;
+constexpr int ATTB_MAXC = 4;  // A, H <= 1024
+
+__global__ void __launch_bounds__(ATTB_THREADS) att_step_bwd_kernel(const float* __restrict__ dctx, long long ld_dctx,
+                                                                    const float* __restrict__ alpha,
+                                                                    const __nv_bfloat16* __restrict__ p_att,
+                                                                    const __nv_bfloat16* __restrict__ att,
+                                                                    const float* __restrict__ att_h, long long ld_att_h,
+                                                                    const float* __restrict__ w_alpha, float* __restrict__ de,
+                                                                    __nv_bfloat16* __restrict__ datt_h, long long ld_dah, int L,
+                                                                    int A, int H) {
+  extern __shared__ float sm[];
+  float* s_de = sm;           // [L]   d alpha, then de
+  float* s_acc = sm + L;      // [A]   d att_h accumulator
+  __shared__ float s_red[ATTB_WARPS];
+  const int r = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const __nv_bfloat16* a_img = att + static_cast<long long>(r) * L * H;
+  const __nv_bfloat16* p_img = p_att + static_cast<long long>(r) * L * A;
+  const float* al = alpha + static_cast<long long>(r) * L;
+  for (int i = threadIdx.x; i < A; i += ATTB_THREADS) s_acc[i] = 0.0f;
+
+  // phase 1: d alpha_l
+  float dc[ATTB_MAXC * 8];
+#pragma unroll
+  for (int c = 0; c < ATTB_MAXC; ++c)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int h = c * 256 + lane * 8 + k;
+      dc[c * 8 + k] = h < H ? dctx[static_cast<long long>(r) * ld_dctx + h] : 0.0f;
+    }
+  for (int l = warp; l < L; l += ATTB_WARPS) {
+    float part = 0.0f;
+#pragma unroll
+    for (int c = 0; c < ATTB_MAXC; ++c) {
+      const int h0 = c * 256 + lane * 8;
+      if (h0 < H) {
+        const uint4 q = ldg_nc_v4(a_img + static_cast<long long>(l) * H + h0);
+        const uint32_t u[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 f = bf16x2_to_f2(u[k]);
+          part = fmaf(f.x, dc[c * 8 + 2 * k], part);
+          part = fmaf(f.y, dc[c * 8 + 2 * k + 1], part);
+        }
+      }
+    }
+    part = warp_sum(part);
+    if (lane == 0) s_de[l] = part;
+  }
+  __syncthreads();
+  float s = 0.0f;
+  for (int l = threadIdx.x; l < L; l += ATTB_THREADS) s = fmaf(al[l], s_de[l], s);
+  s = warp_sum(s);
+  if (lane == 0) s_red[warp] = s;
+  __syncthreads();
+  float tot = 0.0f;
+#pragma unroll
+  for (int q = 0; q < ATTB_WARPS; ++q) tot += s_red[q];
+  __syncthreads();
+  for (int l = threadIdx.x; l < L; l += ATTB_THREADS) {
+    const float v = al[l] * (s_de[l] - tot);
+    s_de[l] = v;
+    de[static_cast<long long>(r) * L + l] = v;
+  }
+  __syncthreads();
+
+  // phase 2: d att_h
+  float ah[ATTB_MAXC * 8], acc[ATTB_MAXC * 8];
+#pragma unroll
+  for (int c = 0; c < ATTB_MAXC; ++c)
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int a = c * 256 + lane * 8 + k;
+      ah[c * 8 + k] = a < A ? att_h[static_cast<long long>(r) * ld_att_h + a] : 0.0f;
+      acc[c * 8 + k] = 0.0f;
+    }
+  for (int l = warp; l < L; l += ATTB_WARPS) {
+    const float del = s_de[l];
+#pragma unroll
+    for (int c = 0; c < ATTB_MAXC; ++c) {
+      const int a0 = c * 256 + lane * 8;
+      if (a0 < A) {
+        const uint4 q = ldg_nc_v4(p_img + static_cast<long long>(l) * A + a0);
+        const uint32_t u[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 f = bf16x2_to_f2(u[k]);
+          const float t0 = tanh_approx(f.x + ah[c * 8 + 2 * k]), t1 = tanh_approx(f.y + ah[c * 8 + 2 * k + 1]);
+          acc[c * 8 + 2 * k] = fmaf(del, 1.0f - t0 * t0, acc[c * 8 + 2 * k]);
+          acc[c * 8 + 2 * k + 1] = fmaf(del, 1.0f - t1 * t1, acc[c * 8 + 2 * k + 1]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < ATTB_MAXC; ++c) {
+    const int a0 = c * 256 + lane * 8;
+    if (a0 < A) {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) atomicAdd(&s_acc[a0 + k], acc[c * 8 + k]);
+    }
+  }
+  __syncthreads();
+  for (int a = threadIdx.x; a < A; a += ATTB_THREADS)
+    datt_h[static_cast<long long>(r) * ld_dah + a] = __float2bfloat16_rn(s_acc[a] * w_alpha[a]);
+}
+
+int att_step_bwd(const float* dctx, long long ld_dctx, const float* alpha, const void* p_att, const void* att, const float* att_h,
+                 long long ld_att_h, const float* w_alpha, float* de, void* datt_h, long long ld_dah, int rows, int L, int A,
+                 int H, cudaStream_t stream) {
+  if (A % 8 || H % 8 || A > 1024 || H > 1024) return set_error(UIC_ERR_SHAPE, "att_step_bwd: A=%d H=%d", A, H);
+  const size_t smem = sizeof(float) * (static_cast<size_t>(L) + A);
+  if (smem > 48 * 1024) return set_error(UIC_ERR_SHAPE, "att_step_bwd: L=%d too large", L);
+  launch_begin("att_step_bwd", stream);
+  att_step_bwd_kernel<<<rows, ATTB_THREADS, smem, stream>>>(dctx, ld_dctx, alpha, static_cast<const __nv_bfloat16*>(p_att),
+                                                            static_cast<const __nv_bfloat16*>(att), att_h, ld_att_h, w_alpha, de,
+                                                            static_cast<__nv_bfloat16*>(datt_h), ld_dah, L, A, H);
+  UIC_CUDA_OK(cudaGetLastError());
+  launch_end(stream);
+  return 0;
+}
+
+// ---- deferred tile gradients: d att (B,L,H), d p_att (B,L,A), d w_alpha (A) ----------------------------
+//   d att[b,l,h]   = sum_t alpha_t[b,l] * dctx_t[b,h]
+//   d p_att[b,l,a] = w_a * sum_t de_t[b,l] * (1 - tanh^2(p_att[b,l,a] + att_h_t[b,a]))
+//   d w_alpha[a]   = sum_{b,l,t} de_t[b,l] * tanh(p_att[b,l,a] + att_h_t[b,a])
+// One CTA per (image, chunk of regions); the per-step vectors of the image are staged in shared memory.
+constexpr int TILE_THREADS = 256;
+
+__global__ void __launch_bounds__(TILE_THREADS) att_tiles_bwd_kernel(
+    const float* __restrict__ de_all, const float* __restrict__ alpha_all, const float* __restrict__ dctx_all,
+    long long dctx_stride_t, long long ld_dctx, const float* __restrict__ att_h_all, long long ah_stride_t, long long ld_ah,
+    const __nv_bfloat16* __restrict__ p_att, const float* __restrict__ w_alpha, float* __restrict__ datt,
+    __nv_bfloat16* __restrict__ dp_att, float* __restrict__ dw_alpha, int T, int B, int L, int A, int H, int l_chunk) {
+  extern __shared__ float sm[];
+  float* s_ah = sm;                       // [T][A]
+  float* s_dctx = s_ah + T * A;           // [T][H]
+  float* s_de = s_dctx + T * H;           // [T][l_chunk]
+  float* s_al = s_de + T * l_chunk;       // [T][l_chunk]
+  const int b = blockIdx.x;
+  const int l0 = blockIdx.y * l_chunk;
+  const int nl = min(l_chunk, L - l0);
+  for (int i = threadIdx.x; i < T * A; i += TILE_THREADS) {
+    const int t = i / A, a = i - t * A;
+    s_ah[i] = att_h_all[t * ah_stride_t + static_cast<long long>(b) * ld_ah + a];
+  }
+  for (int i = threadIdx.x; i < T * H; i += TILE_THREADS) {
+    const int t = i / H, h = i - t * H;
+    s_dctx[i] = dctx_all[t * dctx_stride_t + static_cast<long long>(b) * ld_dctx + h];
+  }
+  for (int i = threadIdx.x; i < T * l_chunk; i += TILE_THREADS) {
+    const int t = i / l_chunk, q = i - t * l_chunk;
+    const bool ok = q < nl;
+    const long long off = (static_cast<long long>(t) * B + b) * L + l0 + q;
+    s_de[i] = ok ? de_all[off] : 0.0f;
+    s_al[i] = ok ? alpha_all[off] : 0.0f;
+  }
+  __syncthreads();
+  for (int a = threadIdx.x; a < A; a += TILE_THREADS) {
+    const float wa = w_alpha[a];
+    float dw = 0.0f;
+    for (int q = 0; q < nl; ++q) {
+      const long long off = (static_cast<long long>(b) * L + l0 + q) * A + a;
+      const float p = __bfloat162float(p_att[off]);
+      float acc = 0.0f;
+      for (int t = 0; t < T; ++t) {
+        const float th = tanh_approx(p + s_ah[t * A + a]);
+        const float d = s_de[t * l_chunk + q];
+        acc = fmaf(d, 1.0f - th * th, acc);
+        dw = fmaf(d, th, dw);
+      }
+      dp_att[off] = __float2bfloat16_rn(acc * wa);
+    }
+    atomicAdd(dw_alpha + a, dw);
+  }
+  for (int h = threadIdx.x; h < H; h += TILE_THREADS) {
+    for (int q = 0; q < nl; ++q) {
+      float acc = 0.0f;
+      for (int t = 0; t < T; ++t) acc = fmaf(s_al[t * l_chunk + q], s_dctx[t * H + h], acc);
+      datt[(static_cast<long long>(b) * L + l0 + q) * H + h] = acc;
+    }
+  }
+}
+
+int att_tiles_bwd(const float* de_all, const float* alpha_all, const float* dctx_all, long long dctx_stride_t, long long ld_dctx,
+                  const float* att_h_all, long long ah_stride_t, long long ld_ah, const void* p_att, const float* w_alpha,
+                  float* datt, void* dp_att, float* dw_alpha, int T, int B, int L, int A, int H, cudaStream_t stream) {
+  int l_chunk = L < 32 ? L : 28;
+  if (L >= 32 && L <= 40) l_chunk = L;
+  const size_t smem = sizeof(float) * (static_cast<size_t>(T) * (A + H) + 2 * static_cast<size_t>(T) * l_chunk);
+  if (smem > 200 * 1024) return set_error(UIC_ERR_SHAPE, "att_tiles_bwd: T=%d A=%d H=%d need %zu bytes of shared memory", T, A, H, smem);
+  if (smem > 48 * 1024)
+    UIC_CUDA_OK(cudaFuncSetAttribute(att_tiles_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  dim3 grid(B, (L + l_chunk - 1) / l_chunk);
+  launch_begin("att_tiles_bwd", stream);
+  att_tiles_bwd_kernel<<<grid, TILE_THREADS, smem, stream>>>(de_all, alpha_all, dctx_all, dctx_stride_t, ld_dctx, att_h_all,
+                                                             ah_stride_t, ld_ah, static_cast<const __nv_bfloat16*>(p_att), w_alpha,
+                                                             datt, static_cast<__nv_bfloat16*>(dp_att), dw_alpha, T, B, L, A, H,
+                                                             l_chunk);
+  UIC_CUDA_OK(cudaGetLastError());
+  launch_end(stream);
+  return 0;
+}
+
+// ---- masked cross-entropy backward: d logits = (softmax - onehot) * mask * scale, bf16 -------------------
+__global__ void __launch_bounds__(256) lse_xent_bwd_kernel(const float* __restrict__ logits, long long ld,
+                                                           const float* __restrict__ lse, const int64_t* __restrict__ target,
+                                                           const float* __restrict__ mask, const float* __restrict__ inv_norm,
+                                                           float grad_scale, __nv_bfloat16* __restrict__ dlogits, long long ld_d,
+                                                           int V) {
+  const int r = blockIdx.x;
+  const float* row = logits + static_cast<long long>(r) * ld;
+  __nv_bfloat16* drow = dlogits + static_cast<long long>(r) * ld_d;
+  const float sc = mask[r] * inv_norm[0] * grad_scale;
+  const float l = lse[r];
+  long long t = target[r];
+  t = t < 0 ? 0 : (t >= V ? V - 1 : t);
+  for (int v = threadIdx.x; v < ld_d; v += 256) {
+    float g = 0.0f;
+    if (v < V && sc != 0.0f) g = (__expf(row[v] - l) - (v == t ? 1.0f : 0.0f)) * sc;
+    drow[v] = __float2bfloat16_rn(g);
+  }
+}
+
+int lse_xent_bwd(const float* logits, long long ld, const float* lse, const int64_t* target, const float* mask,
+                 const float* inv_norm, float grad_scale, void* dlogits, long long ld_d, int rows, int V, cudaStream_t stream) {
+  launch_begin("lse_xent_bwd", stream);
+  lse_xent_bwd_kernel<<<rows, 256, 0, stream>>>(logits, ld, lse, target, mask, inv_norm, grad_scale,
+                                                static_cast<__nv_bfloat16*>(dlogits), ld_d, V);
+  UIC_CUDA_OK(cudaGetLastError());
+  launch_end(stream);
+  return 0;
+}
+
+// ---- log_softmax backward for the dense (B,T,V) API path: d logits = d lp - exp(lp) * sum(d lp) ----------
+__global__ void __launch_bounds__(256) log_softmax_bwd_kernel(const float* __restrict__ dlp, long long ld_dlp,
+                                                              const float* __restrict__ lp, long long ld_lp,
+                                                              __nv_bfloat16* __restrict__ dlogits, long long ld_d, int V) {
+  __shared__ float s_red[8];
+  const int r = blockIdx.x;
+  const float* g = dlp + static_cast<long long>(r) * ld_dlp;
+  const float* y = lp + static_cast<long long>(r) * ld_lp;
+  float s = 0.0f;
+  for (int v = threadIdx.x; v < V; v += 256) s += g[v];
+  s = warp_sum(s);
+  if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  float tot = 0.0f;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) tot += s_red[q];
+  __nv_bfloat16* d = dlogits + static_cast<long long>(r) * ld_d;
+  for (int v = threadIdx.x; v < ld_d; v += 256) d[v] = __float2bfloat16_rn(v < V ? g[v] - __expf(y[v]) * tot : 0.0f);
+}
+
+int log_softmax_bwd(const float* dlp, long long ld_dlp, const float* lp, long long ld_lp, void* dlogits, long long ld_d, int rows,
+                    int V, cudaStream_t stream) {
+  launch_begin("log_softmax_bwd", stream);
+  log_softmax_bwd_kernel<<<rows, 256, 0, stream>>>(dlp, ld_dlp, lp, ld_lp, static_cast<__nv_bfloat16*>(dlogits), ld_d, V);
+  UIC_CUDA_OK(cudaGetLastError());
+  launch_end(stream);
+  return 0;
+}
+
+// ---- column sums (bias gradients): out[c] += sum_r x[r, c] ------------------------------------------------
+template <typename T>
+__global__ void col_sum_kernel(const T* __restrict__ x, long long ld, float* __restrict__ out, int rows, int cols) {
+  __shared__ float s[8][33];
+  const int c = blockIdx.x * 32 + threadIdx.x;
+  float acc = 0.0f;
+  if (c < cols)
+    for (int r = blockIdx.y * 8 + threadIdx.y; r < rows; r += gridDim.y * 8) acc += static_cast<float>(x[static_cast<long long>(r) * ld + c]);
+  s[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && c < cols) {
+    float t = 0.0f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) t += s[q][threadIdx.x];
+    atomicAdd(out + c, t);
+  }
+}
+
+int col_sum(const void* x, int is_bf16, long long ld, float* out, int rows, int cols, cudaStream_t stream) {
+  dim3 block(32, 8);
+  int gy = (rows + 255) / 256;
+  gy = gy < 1 ? 1 : (gy > 64 ? 64 : gy);
+  dim3 grid((cols + 31) / 32, gy);
+  launch_begin("col_sum", stream);
+  if (is_bf16)
+    col_sum_kernel<__nv_bfloat16><<<grid, block, 0, stream>>>(static_cast<const __nv_bfloat16*>(x), ld, out, rows, cols);
+  else
+    col_sum_kernel<float><<<grid, block, 0, stream>>>(static_cast<const float*>(x), ld, out, rows, cols);
+  UIC_CUDA_OK(cudaGetLastError());
+  launch_end(stream);
+  return 0;
+}
+
+// ---- embedding backward: dEmb[tok[r], e] += dxt[r, e] where relu(emb) was active -----------------------------
+__global__ void embed_bwd_kernel(const float* __restrict__ dxt, long long ld, const int64_t* __restrict__ tok,
+                                 const __nv_bfloat16* __restrict__ table_relu, float* __restrict__ demb, long long rows, int E,
+                                 int V) {
+  const long long total = rows * E;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = i / E;
+    const int e = static_cast<int>(i - r * E);
+    long long t = tok[r];
+    t = t < 0 ? 0 : (t >= V ? V - 1 : t);
+    if (__bfloat162float(table_relu[t * E + e]) > 0.0f) atomicAdd(demb + t * E + e, dxt[r * ld + e]);
+  }
+}
+
+int embed_bwd(const float* dxt, long long ld, const int64_t* tok, const void* table_relu, float* demb, long long rows, int E, int V,
+              cudaStream_t stream) {
+  launch_begin("embed_bwd", stream);
+  embed_bwd_kernel<<<grid_for(rows * E, 256), 256, 0, stream>>>(dxt, ld, tok, static_cast<const __nv_bfloat16*>(table_relu), demb,
+                                                                rows, E, V);
+  UIC_CUDA_OK(cudaGetLastError());
+  launch_end(stream);
+  return 0;
+}
+
+// ---- out_bf16 = x_f32 where y_bf16 > 0 else 0 (ReLU backward + operand cast) -----------------------------------
+__global__ void relu_bwd_cast_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ y,
+                                     __nv_bfloat16* __restrict__ out, long long n) {
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long long>(gridDim.x) * blockDim.x)
+    out[i] = __float2bfloat16_rn(__bfloat162float(y[i]) > 0.0f ? x[i] : 0.0f);
+}
+
+int relu_bwd_cast(const float* x, const void* y, void* out, long long n, cudaStream_t stream) {
+  launch_begin("relu_bwd_cast", stream);
+  relu_bwd_cast_kernel<<<grid_for(n, 256), 256, 0, stream>>>(x, static_cast<const __nv_bfloat16*>(y),
+                                                             static_cast<__nv_bfloat16*>(out), n);
+  UIC_CUDA_OK(cudaGetLastError());
+  launch_end(stream);
+  return 0;
+}
+
+// ---- dst[b, j] = sum_t src[t, b, col0 + j] (gradient of a feature that is re-fed every step) ------------------
+__global__ void reduce_time_kernel(const float* __restrict__ src, long long stride_t, long long ld, int col0, float* __restrict__ dst,
+                                   int T, int rows, int n) {
+  const long long total = static_cast<long long>(rows) * n;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long b = i / n;
+    const int j = static_cast<int>(i - b * n);
+    float acc = 0.0f;
+    for (int t = 0; t < T; ++t) acc += src[t * stride_t + b * ld + col0 + j];
+    dst[i] = acc;
+  }
+}
+
+int reduce_time(const float* src, long long stride_t, long long ld, int col0, float* dst, int T, int rows, int n,
+                cudaStream_t stream) {
+  launch_begin("reduce_time", stream);
+  reduce_time_kernel<<<grid_for(static_cast<long long>(rows) * n, 256), 256, 0, stream>>>(src, stride_t, ld, col0, dst, T, rows, n);
+  UIC_CUDA_OK(cudaGetLastError());
+  launch_end(stream);
+  return 0;
+}
+
+}  // namespace uic

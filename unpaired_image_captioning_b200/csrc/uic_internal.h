@@ -60,3 +60,29 @@ int beam_gather(const int32_t* parent_row, const void* x_src, void* x_dst, long 
                 int ncol_b, const float* c_src, float* c_dst, int n_state, int rows, int H, cudaStream_t stream);
 
 }  // namespace uic
+
+namespace uic {
+// backward kernels (backward.cu)
+int lstm_cell_bwd(const float* gates, long long ld_gates, const float* c_prev, const float* c, const float* dh0, long long ld0,
+                  const float* dh1, long long ld1, const float* dh2, long long ld2, const float* dc_next, void* dgates,
+                  long long ld_dg, float* dc_prev, int rows, int H, cudaStream_t stream);
+int lstm_maxout_bwd(const float* sums, long long ld_sums, const float* a2c, long long ld_a2c, const float* c_prev, const float* c,
+                    const float* dh0, long long ld0, const float* dh1, long long ld1, const float* dc_next, void* dsums,
+                    long long ld_ds, void* da2c, long long ld_da, float* dc_prev, int rows, int H, cudaStream_t stream);
+int att_step_bwd(const float* dctx, long long ld_dctx, const float* alpha, const void* p_att, const void* att, const float* att_h,
+                 long long ld_att_h, const float* w_alpha, float* de, void* datt_h, long long ld_dah, int rows, int L, int A,
+                 int H, cudaStream_t stream);
+int att_tiles_bwd(const float* de_all, const float* alpha_all, const float* dctx_all, long long dctx_stride_t, long long ld_dctx,
+                  const float* att_h_all, long long ah_stride_t, long long ld_ah, const void* p_att, const float* w_alpha,
+                  float* datt, void* dp_att, float* dw_alpha, int T, int B, int L, int A, int H, cudaStream_t stream);
+int lse_xent_bwd(const float* logits, long long ld, const float* lse, const int64_t* target, const float* mask,
+                 const float* inv_norm, float grad_scale, void* dlogits, long long ld_d, int rows, int V, cudaStream_t stream);
+int log_softmax_bwd(const float* dlp, long long ld_dlp, const float* lp, long long ld_lp, void* dlogits, long long ld_d, int rows,
+                    int V, cudaStream_t stream);
+int col_sum(const void* x, int is_bf16, long long ld, float* out, int rows, int cols, cudaStream_t stream);
+int embed_bwd(const float* dxt, long long ld, const int64_t* tok, const void* table_relu, float* demb, long long rows, int E, int V,
+              cudaStream_t stream);
+int relu_bwd_cast(const float* x, const void* y, void* out, long long n, cudaStream_t stream);
+int reduce_time(const float* src, long long stride_t, long long ld, int col0, float* dst, int T, int rows, int n,
+                cudaStream_t stream);
+}  // namespace uic

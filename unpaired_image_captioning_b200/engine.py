@@ -122,7 +122,7 @@ class DecoderEngine:
         return self._packed
 
     # ---- prologue ---------------------------------------------------------------------------------
-    def prepare(self, fc_feats, att_feats, att_masks=None):
+    def prepare(self, fc_feats, att_feats, att_masks=None, keep_inputs=False):
         """clip_att + fc_embed + att_embed + ctx2att (models/AttModel.py:99-117)."""
         w = self.w
         if att_masks is not None:  # clip to the longest valid length (:99-105)
@@ -140,8 +140,12 @@ class DecoderEngine:
         fc = None
         if self.kind == "topdown":
             fc = torch.empty(B, H, dtype=BF16, device=x.device)
-            gemm(_lib.cast_bf16(fc_feats.float().contiguous()), w.w_fc, w.b_fc, out_bf16=fc, relu=True)
-        return Features(att.view(B, L, H), p_att.view(B, L, A), fc, att_masks, B, L)
+            fc_in = _lib.cast_bf16(fc_feats.float().contiguous())
+            gemm(fc_in, w.w_fc, w.b_fc, out_bf16=fc, relu=True)
+        feats = Features(att.view(B, L, H), p_att.view(B, L, A), fc, att_masks, B, L)
+        if keep_inputs:  # bf16 operand copies of the raw features, needed by the prologue wgrads
+            feats.x_in, feats.fc_in = x, (fc_in if self.kind == "topdown" else None)
+        return feats
 
     # ---- one decoder step: X, c -> logits -------------------------------------------------------------
     def _workspace(self, R, dev):
@@ -192,8 +196,9 @@ class DecoderEngine:
             ctx = cols(X, sl.ctx)
             check(lib.uic_att_step_fwd(ptr(ws["att_h"]), A, ptr(feats.p_att), ptr(feats.att), ptr(w.w_alpha), ptr(feats.masks),
                                        ptr(ctx), ldx, None, 0, ptr(alpha), feats.B, beams, feats.L, A, H, st))
-            gemm(X[:, E + 2 * H:], w.w2, w.b2, out_f32=G)
-            check(lib.uic_lstm_cell_fwd(ptr(G), 4 * H, ptr(c[1]), ptr(c_out[1]), None, ptr(cols(Xn, sl.h_lang)), Xn.stride(0),
+            G2 = ws.get("G2", G)  # teacher-forced runs keep both gate tensors for backward
+            gemm(X[:, E + 2 * H:], w.w2, w.b2, out_f32=G2)
+            check(lib.uic_lstm_cell_fwd(ptr(G2), 4 * H, ptr(c[1]), ptr(c_out[1]), None, ptr(cols(Xn, sl.h_lang)), Xn.stride(0),
                                         ptr(h_all), h_all.stride(0) if h_all is not None else 0, R, H, st))
         return cols(Xn, sl.h_out)
 

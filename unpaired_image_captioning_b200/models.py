@@ -193,12 +193,15 @@ class AttModel(CaptionModel):
                 check(lib.uic_log_softmax_rows(ptr(logits[:, t]), T * V, ptr(out[:, t]), T * V, B, V, stream()))
         return out
 
-    def _forward_loss(self, fc_feats, attri_feats, att_feats, labels, masks, att_masks=None):
+    def _forward_loss(self, fc_feats, attri_feats, att_feats, labels, masks, att_masks=None, global_mask_sum=None):
         """Additive fast path: fused teacher-forced forward + masked XE without the
-        (B, T, V) log-prob tensor.  Equals crit(model(fc, attri, att, labels, att_masks), labels[:,1:], masks[:,1:])."""
+        (B, T, V) log-prob tensor.  Equals crit(model(fc, attri, att, labels, att_masks), labels[:,1:], masks[:,1:]).
+        `global_mask_sum` (data parallel): the loss normaliser summed over all ranks (dp.global_mask_sum)."""
         self._check_train_features()
+        if self.training and self.ss_prob > 0.0:
+            raise NotImplementedError("scheduled sampling (ss_prob > 0) is not on the B200 hot path yet")
         from .autograd import decoder_loss
-        return decoder_loss(self, fc_feats, att_feats, labels, masks, att_masks)
+        return decoder_loss(self, fc_feats, att_feats, labels, masks, att_masks, global_mask_sum)
 
     # ---- single step API --------------------------------------------------------------------------------
     def _feats_from_api(self, fc, att, p_att, att_masks, rows):
