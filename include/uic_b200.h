@@ -36,6 +36,7 @@ extern "C" {
 #define UIC_GEMM_ACCUMULATE 2   /* c_f32 += result (used for gradient accumulation) */
 #define UIC_GEMM_A_MN_MAJOR 4   /* A is stored [K, M] row-major instead of [M, K] */
 #define UIC_GEMM_B_MN_MAJOR 8   /* B is stored [K, N] row-major instead of [N, K] */
+#define UIC_GEMM_OUT_F16 16     /* the 16-bit output buffer receives IEEE fp16 instead of bf16 (p_att tiles) */
 
 /* sampling flags (uic_greedy_step / uic_row_topk) */
 #define UIC_SAMPLE_DECODING_CONSTRAINT 1 /* -inf on the previous token (AttModel.py:220-223, CaptionModel.py:130-131) */
@@ -85,12 +86,17 @@ int uic_zero_padded_rows(void* x_bf16, const float* att_masks, int n_img, int L,
  *   e[l]  = sum_a w_alpha[a] * tanh(p_att[i,l,a] + att_h[r,a])        (alpha_net bias cancels in softmax)
  *   alpha = softmax_l(e);  if att_masks: alpha = alpha*m / sum(alpha*m)
  *   ctx[r,:] = sum_l alpha[l] * att[i,l,:]
- * att_h is the h2att projection INCLUDING its bias (fp32, pitch ld_att_h).  p_att / att are bf16,
- * read once per image and shared by the image's beams.  Outputs (each optional): ctx_bf16, ctx_f32,
- * alpha (rows x L fp32, saved for backward). */
-int uic_att_step_fwd(const float* att_h, int64_t ld_att_h, const void* p_att_bf16, const void* att_bf16,
+ * att_h is the h2att projection INCLUDING its bias (fp32, pitch ld_att_h).  p_att is FP16 (n_img,L,A)
+ * and att is bf16 (n_img,L,H); both are read once per image and shared by the image's beams.
+ * Outputs (each optional): ctx_bf16, ctx_f32, alpha (rows x L fp32, saved for backward).
+ * `workspace`: uic_att_step_workspace_bytes(...) bytes, 16-byte aligned, zeroed ONCE by the caller
+ * (the kernel leaves its arrival counters at zero); it holds the partial results when the regions
+ * of an image are split over several CTAs. */
+int uic_att_step_fwd(const float* att_h, int64_t ld_att_h, const void* p_att_f16, const void* att_bf16,
                      const float* w_alpha, const float* att_masks, void* ctx_bf16, int64_t ld_ctx_bf16, float* ctx_f32,
-                     int64_t ld_ctx_f32, float* alpha, int n_img, int beams, int L, int A, int H, void* stream);
+                     int64_t ld_ctx_f32, float* alpha, void* workspace, int64_t workspace_bytes, int n_img, int beams, int L,
+                     int A, int H, void* stream);
+int64_t uic_att_step_workspace_bytes(int n_img, int beams, int L, int H);
 
 /* ---- LSTM pointwise ------------------------------------------------------------------------- */
 /* Att2in2 maxout cell (models/AttModel.py:584-601): sums = i2h(xt)+h2h(h) (rows x 5H, pitch ld_sums),
@@ -157,8 +163,9 @@ int uic_att_step_bwd(const float* dctx, int64_t ld_dctx, const float* alpha, con
                      const float* att_h, int64_t ld_att_h, const float* w_alpha, float* de, void* datt_h_bf16, int64_t ld_dah,
                      int rows, int L, int A, int H, void* stream);
 /* Deferred gradients of the feature tiles over all T steps at once:
- * d att (B,L,H) fp32, d p_att (B,L,A) bf16 and d w_alpha (A, accumulated).  The per-step vectors are
- * addressed as base + t*stride_t + b*ld. */
+ * d att (B,L,H) fp32, d p_att (B,L,A) bf16, and accumulated into dw_alpha (2A floats, zeroed by the
+ * caller): [0,A) d w_alpha, [A,2A) the fp32 column sum of d p_att (= d bias of ctx2att).  The
+ * per-step vectors are addressed as base + t*stride_t + b*ld. */
 int uic_att_tiles_bwd(const float* de_all, const float* alpha_all, const float* dctx_all, int64_t dctx_stride_t, int64_t ld_dctx,
                       const float* att_h_all, int64_t ah_stride_t, int64_t ld_ah, const void* p_att_bf16, const float* w_alpha,
                       float* datt, void* dp_att_bf16, float* dw_alpha, int T, int B, int L, int A, int H, void* stream);
@@ -174,8 +181,9 @@ int uic_col_sum(const void* x, int is_bf16, int64_t ld, float* out, int rows, in
 /* dEmb[tok[r], :] += dxt[r, :] where ReLU(Emb) was active (backward of uic_embed_rows). */
 int uic_embed_bwd(const float* dxt, int64_t ld, const int64_t* tok, const void* table_relu_bf16, float* demb, int64_t rows, int E,
                   int V, void* stream);
-/* out_bf16[i] = y_bf16[i] > 0 ? x[i] : 0 (ReLU backward fused with the operand cast). */
-int uic_relu_bwd_cast(const float* x, const void* y_bf16, void* out_bf16, int64_t n, void* stream);
+/* x[i] = y_bf16[i] > 0 ? x[i] : 0 in place, and out_bf16[i] = bf16(x[i]): ReLU backward fused with
+ * the operand cast (the fp32 copy is what the bias gradient is summed from). */
+int uic_relu_bwd_cast(float* x, const void* y_bf16, void* out_bf16, int64_t n, void* stream);
 /* dst[b, j] = sum_t src[t*stride_t + b*ld + col0 + j]. */
 int uic_reduce_time(const float* src, int64_t stride_t, int64_t ld, int col0, float* dst, int T, int rows, int n, void* stream);
 

@@ -109,11 +109,12 @@ def _att_reference(att_h, p_att, att, w, masks, beams):
 
 @pytest.mark.parametrize("B,beams,L,A,H,use_masks", [
     (5, 1, 7, 32, 32, False), (5, 3, 7, 32, 32, True), (4, 5, 36, 512, 512, False), (3, 2, 196, 512, 512, True),
-    (2, 3, 196, 512, 1024, False), (3, 10, 20, 64, 40, False), (16, 1, 196, 512, 512, False), (2, 1, 5, 264, 776, True)])
+    (2, 3, 196, 512, 1024, False), (3, 10, 20, 64, 40, False), (16, 1, 196, 512, 512, False), (2, 1, 5, 264, 776, True),
+    (3, 3, 196, 512, 512, True), (2, 1, 400, 256, 512, False), (4, 1, 3, 32, 64, False), (2, 5, 600, 512, 512, True)])
 def test_att_step_fwd(B, beams, L, A, H, use_masks):
     lib = _lib.load()
     R = B * beams
-    p_att, att = _rand_bf16(B, L, A, seed=11), _rand_bf16(B, L, H, seed=12).abs()
+    p_att, att = _rand_bf16(B, L, A, seed=11).to(torch.float16), _rand_bf16(B, L, H, seed=12).abs()
     att_h_full = torch.randn(R, A + 24, device=DEV)   # pitch larger than A, like the fused gate GEMM output
     att_h = att_h_full[:, 8:8 + A]
     w = torch.randn(A, device=DEV) * 0.2
@@ -124,8 +125,9 @@ def test_att_step_fwd(B, beams, L, A, H, use_masks):
     ctx_b = torch.empty(R, H, device=DEV, dtype=torch.bfloat16)
     ctx_f = torch.empty(R, H, device=DEV)
     alpha = torch.empty(R, L, device=DEV)
-    check(lib.uic_att_step_fwd(ptr(att_h), att_h_full.stride(0), ptr(p_att), ptr(att), ptr(w), ptr(masks), ptr(ctx_b), H,
-                               ptr(ctx_f), H, ptr(alpha), B, beams, L, A, H, stream()))
+    for _ in range(2):   # twice: the split-merge arrival counters must be left at zero by the kernel
+        ctx_f.zero_()
+        _lib.att_step(att_h, att_h_full.stride(0), p_att, att, w, masks, ctx_b, H, ctx_f, H, alpha, B, beams, L, A, H)
     ref_ctx, ref_alpha = _att_reference(att_h, p_att, att, w, masks, beams)
     torch.testing.assert_close(alpha, ref_alpha, rtol=5e-3, atol=2e-5)     # tanh.approx.f32 inside the score
     torch.testing.assert_close(ctx_f, ref_ctx, rtol=5e-3, atol=5e-4)

@@ -27,7 +27,8 @@ SIGNATURES = {
     "uic_cast_f32_bf16": (_i, [_p, _i64, _p, _i64, _i64, _i64, _i, _p]),
     "uic_embed_rows": (_i, [_p, _i64, _p, _p, _i64, _i, _i, _i, _p]),
     "uic_zero_padded_rows": (_i, [_p, _p, _i, _i, _i, _p]),
-    "uic_att_step_fwd": (_i, [_p, _i64, _p, _p, _p, _p, _p, _i64, _p, _i64, _p, _i, _i, _i, _i, _i, _p]),
+    "uic_att_step_fwd": (_i, [_p, _i64, _p, _p, _p, _p, _p, _i64, _p, _i64, _p, _p, _i64, _i, _i, _i, _i, _i, _p]),
+    "uic_att_step_workspace_bytes": (_i64, [_i, _i, _i, _i]),
     "uic_lstm_maxout_fwd": (_i, [_p, _i64, _p, _i64, _p, _p, _p, _p, _i64, _p, _i64, _i, _i, _p]),
     "uic_lstm_cell_fwd": (_i, [_p, _i64, _p, _p, _p, _p, _i64, _p, _i64, _i, _i, _p]),
     "uic_log_softmax_rows": (_i, [_p, _i64, _p, _i64, _i, _i, _p]),
@@ -48,7 +49,7 @@ SIGNATURES = {
     "uic_reduce_time": (_i, [_p, _i64, _i64, _i, _p, _i, _i, _i, _p]),
 }
 
-GEMM_RELU, GEMM_ACCUMULATE, GEMM_A_MN, GEMM_B_MN = 1, 2, 4, 8
+GEMM_RELU, GEMM_ACCUMULATE, GEMM_A_MN, GEMM_B_MN, GEMM_OUT_F16 = 1, 2, 4, 8, 16
 SAMPLE_DECODING_CONSTRAINT, BEAM_MAX_PPL = 1, 2
 
 _lib = None
@@ -130,14 +131,40 @@ def gemm(a, b, bias=None, out_f32=None, out_bf16=None, relu=False, accumulate=Fa
     N, Kb = (b.shape[1], b.shape[0]) if b_mn else b.shape
     if K != Kb:
         raise ValueError(f"gemm: K mismatch {K} vs {Kb}")
-    for o, dt in ((out_f32, torch.float32), (out_bf16, torch.bfloat16)):
-        if o is not None and (o.dtype != dt or o.shape != (M, N) or o.stride(1) != 1):
+    out_f16 = out_bf16 is not None and out_bf16.dtype == torch.float16   # 16-bit output buffer may be fp16 (p_att tiles)
+    for o, dts in ((out_f32, (torch.float32,)), (out_bf16, (torch.bfloat16, torch.float16))):
+        if o is not None and (o.dtype not in dts or o.shape != (M, N) or o.stride(1) != 1):
             raise ValueError("gemm: bad output tensor")
     if bias is not None and (bias.dtype != torch.float32 or bias.numel() != N or not bias.is_contiguous()):
         raise ValueError("gemm: bias must be contiguous fp32 of length N")
-    flags = (GEMM_RELU if relu else 0) | (GEMM_ACCUMULATE if accumulate else 0) | (GEMM_A_MN if a_mn else 0) | (GEMM_B_MN if b_mn else 0)
+    flags = ((GEMM_RELU if relu else 0) | (GEMM_ACCUMULATE if accumulate else 0) | (GEMM_A_MN if a_mn else 0) |
+             (GEMM_B_MN if b_mn else 0) | (GEMM_OUT_F16 if out_f16 else 0))
     check(load().uic_gemm_bf16(ptr(a), a.stride(0), ptr(b), b.stride(0), ptr(out_f32), out_f32.stride(0) if out_f32 is not None else 0,
                                ptr(out_bf16), out_bf16.stride(0) if out_bf16 is not None else 0, ptr(bias), M, N, K, flags, stream()))
+
+
+_att_ws = {}
+
+
+def att_workspace(n_img, beams, L, H, device):
+    """Cached, zero-initialised workspace of uic_att_step_fwd for this shape (stream-ordered reuse)."""
+    key = (n_img, beams, L, H, str(device))
+    ws = _att_ws.get(key)
+    if ws is None:
+        nbytes = int(load().uic_att_step_workspace_bytes(n_img, beams, L, H))
+        ws = torch.zeros(max(nbytes, 16), dtype=torch.uint8, device=device)
+        _att_ws[key] = ws
+    return ws
+
+
+def att_step(att_h, ld_att_h, p_att, att, w_alpha, masks, ctx_bf16, ld_ctx_bf16, ctx_f32, ld_ctx_f32, alpha, n_img, beams, L, A, H):
+    """uic_att_step_fwd with dtype checks and the cached workspace.  att_h / ctx_* may be views
+    (pass their row pitch); p_att is fp16 (n_img, L, A), att is bf16 (n_img, L, H), both contiguous."""
+    if p_att.dtype != torch.float16 or att.dtype != torch.bfloat16 or not p_att.is_contiguous() or not att.is_contiguous():
+        raise ValueError("att_step: p_att must be contiguous fp16 and att contiguous bf16")
+    ws = att_workspace(n_img, beams, L, H, att.device)
+    check(load().uic_att_step_fwd(ptr(att_h), ld_att_h, ptr(p_att), ptr(att), ptr(w_alpha), ptr(masks), ptr(ctx_bf16), ld_ctx_bf16,
+                                  ptr(ctx_f32), ld_ctx_f32, ptr(alpha), ptr(ws), ws.numel(), n_img, beams, L, A, H, stream()))
 
 
 def cast_bf16(src, dst=None, relu=False):

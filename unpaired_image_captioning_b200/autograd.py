@@ -233,24 +233,22 @@ def bptt(r, dh_all):
     # ---- feature tiles and the prologue layers -----------------------------------------------------------
     datt = torch.empty(B * L, H, **f32)
     dp_att = torch.empty(B * L, A, dtype=BF16, device=dev)
-    dw_alpha = torch.zeros(A, **f32)
+    dw_alpha = torch.zeros(2 * A, **f32)                                  # [d w_alpha | d bias of ctx2att]
     check(lib.uic_att_tiles_bwd(ptr(de), ptr(r.alpha), ptr(dctx_ptr), dctx_stride, dctx_ld, ptr(ah_ptr), ah_stride, ah_ld,
                                 ptr(feats.p_att), ptr(w.w_alpha), ptr(datt), ptr(dp_att), ptr(dw_alpha), T, B, L, A, H, st))
-    g["core.attention.alpha_net.weight"] = dw_alpha.view(1, A)
+    g["core.attention.alpha_net.weight"] = dw_alpha[:A].view(1, A)
     g["core.attention.alpha_net.bias"] = torch.zeros(1, **f32)            # the bias cancels inside the softmax
     att2d = feats.att.view(B * L, H)
     dWc = torch.empty(A, H, **f32)
     gemm(dp_att, att2d, out_f32=dWc, a_mn=True, b_mn=True)
-    dbc = torch.zeros(A, **f32)
-    check(lib.uic_col_sum(ptr(dp_att), 1, A, ptr(dbc), B * L, A, st))
-    g["ctx2att.weight"], g["ctx2att.bias"] = dWc, dbc
+    g["ctx2att.weight"], g["ctx2att.bias"] = dWc, dw_alpha[A:]
     gemm(dp_att, w.w_ctx2att, out_f32=datt, b_mn=True, accumulate=True)   # d att += d p_att @ W_ctx2att
     d_pre = torch.empty(B * L, H, dtype=BF16, device=dev)
     check(lib.uic_relu_bwd_cast(ptr(datt), ptr(att2d), ptr(d_pre), B * L * H, st))
     dWe = torch.empty(H, feats.x_in.size(1), **f32)
     gemm(d_pre, feats.x_in, out_f32=dWe, a_mn=True, b_mn=True)
     dbe = torch.zeros(H, **f32)
-    check(lib.uic_col_sum(ptr(d_pre), 1, H, ptr(dbe), B * L, H, st))
+    check(lib.uic_col_sum(ptr(datt), 0, H, ptr(dbe), B * L, H, st))       # fp32 masked copy left by relu_bwd_cast
     g["att_embed.0.weight"], g["att_embed.0.bias"] = dWe, dbe
     return g
 

@@ -233,12 +233,17 @@ int uic_zero_padded_rows(void* x_bf16, const float* att_masks, int n_img, int L,
 
 int uic_att_step_fwd(const float* att_h, int64_t ld_att_h, const void* p_att, const void* att, const float* w_alpha,
                      const float* masks, void* ctx_bf16, int64_t ld_ctx_bf16, float* ctx_f32, int64_t ld_ctx_f32, float* alpha,
-                     int n_img, int beams, int L, int A, int H, void* stream) {
+                     void* workspace, int64_t workspace_bytes, int n_img, int beams, int L, int A, int H, void* stream) {
   REQUIRE(att_h && p_att && att && w_alpha, UIC_ERR_ARG, "uic_att_step_fwd: null input");
   REQUIRE(ctx_bf16 || ctx_f32, UIC_ERR_ARG, "uic_att_step_fwd: no output buffer");
   if (n_img == 0) return 0;
-  return att_step_fwd(att_h, ld_att_h, p_att, att, w_alpha, masks, ctx_bf16, ld_ctx_bf16, ctx_f32, ld_ctx_f32, alpha, n_img,
-                      beams, L, A, H, ST(stream));
+  return att_step_fwd(att_h, ld_att_h, p_att, att, w_alpha, masks, ctx_bf16, ld_ctx_bf16, ctx_f32, ld_ctx_f32, alpha, workspace,
+                      workspace_bytes, n_img, beams, L, A, H, ST(stream));
+}
+
+int64_t uic_att_step_workspace_bytes(int n_img, int beams, int L, int H) {
+  if (n_img <= 0 || beams <= 0 || L <= 0 || H <= 0) return 0;
+  return att_step_workspace_bytes(n_img, beams, L, H);
 }
 
 int uic_lstm_maxout_fwd(const float* sums, int64_t ld_sums, const float* a2c, int64_t ld_a2c, const float* c_prev, float* c_out,
@@ -380,7 +385,7 @@ int uic_embed_bwd(const float* dxt, int64_t ld, const int64_t* tok, const void* 
   return embed_bwd(dxt, ld, tok, table_relu_bf16, demb, rows, E, V, ST(stream));
 }
 
-int uic_relu_bwd_cast(const float* x, const void* y_bf16, void* out_bf16, int64_t n, void* stream) {
+int uic_relu_bwd_cast(float* x, const void* y_bf16, void* out_bf16, int64_t n, void* stream) {
   REQUIRE(x && y_bf16 && out_bf16, UIC_ERR_ARG, "uic_relu_bwd_cast: null pointer");
   if (n == 0) return 0;
   return relu_bwd_cast(x, y_bf16, out_bf16, n, ST(stream));

@@ -5,6 +5,8 @@
 //   * weight gradients: one wgrad GEMM per weight over all T steps (K = T*B), MN-major operands;
 //   * the gradients w.r.t. the feature tiles (att, p_att) are NOT read-modify-written every step:
 //     each step only stores de (B, L); one pass at the end rebuilds sum_t(...) per tile element.
+#include <cuda_fp16.h>
+
 #include "uic_internal.h"
 #include "uic_ptx.cuh"
 
@@ -122,7 +124,7 @@ constexpr int ATTB_MAXC = 4;  // A, H <= 1024
 
 __global__ void __launch_bounds__(ATTB_THREADS) att_step_bwd_kernel(const float* __restrict__ dctx, long long ld_dctx,
                                                                     const float* __restrict__ alpha,
-                                                                    const __nv_bfloat16* __restrict__ p_att,
+                                                                    const __half* __restrict__ p_att,
                                                                     const __nv_bfloat16* __restrict__ att,
                                                                     const float* __restrict__ att_h, long long ld_att_h,
                                                                     const float* __restrict__ w_alpha, float* __restrict__ de,
@@ -135,7 +137,7 @@ __global__ void __launch_bounds__(ATTB_THREADS) att_step_bwd_kernel(const float*
   const int r = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const __nv_bfloat16* a_img = att + static_cast<long long>(r) * L * H;
-  const __nv_bfloat16* p_img = p_att + static_cast<long long>(r) * L * A;
+  const __half* p_img = p_att + static_cast<long long>(r) * L * A;
   const float* al = alpha + static_cast<long long>(r) * L;
   for (int i = threadIdx.x; i < A; i += ATTB_THREADS) s_acc[i] = 0.0f;
 
@@ -204,7 +206,7 @@ __global__ void __launch_bounds__(ATTB_THREADS) att_step_bwd_kernel(const float*
         const uint32_t u[4] = {q.x, q.y, q.z, q.w};
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          const float2 f = bf16x2_to_f2(u[k]);
+          const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&u[k]));
           const float t0 = tanh_approx(f.x + ah[c * 8 + 2 * k]), t1 = tanh_approx(f.y + ah[c * 8 + 2 * k + 1]);
           acc[c * 8 + 2 * k] = fmaf(del, 1.0f - t0 * t0, acc[c * 8 + 2 * k]);
           acc[c * 8 + 2 * k + 1] = fmaf(del, 1.0f - t1 * t1, acc[c * 8 + 2 * k + 1]);
@@ -232,7 +234,7 @@ int att_step_bwd(const float* dctx, long long ld_dctx, const float* alpha, const
   const size_t smem = sizeof(float) * (static_cast<size_t>(L) + A);
   if (smem > 48 * 1024) return set_error(UIC_ERR_SHAPE, "att_step_bwd: L=%d too large", L);
   launch_begin("att_step_bwd", stream);
-  att_step_bwd_kernel<<<rows, ATTB_THREADS, smem, stream>>>(dctx, ld_dctx, alpha, static_cast<const __nv_bfloat16*>(p_att),
+  att_step_bwd_kernel<<<rows, ATTB_THREADS, smem, stream>>>(dctx, ld_dctx, alpha, static_cast<const __half*>(p_att),
                                                             static_cast<const __nv_bfloat16*>(att), att_h, ld_att_h, w_alpha, de,
                                                             static_cast<__nv_bfloat16*>(datt_h), ld_dah, L, A, H);
   UIC_CUDA_OK(cudaGetLastError());
@@ -250,7 +252,7 @@ constexpr int TILE_THREADS = 256;
 __global__ void __launch_bounds__(TILE_THREADS) att_tiles_bwd_kernel(
     const float* __restrict__ de_all, const float* __restrict__ alpha_all, const float* __restrict__ dctx_all,
     long long dctx_stride_t, long long ld_dctx, const float* __restrict__ att_h_all, long long ah_stride_t, long long ld_ah,
-    const __nv_bfloat16* __restrict__ p_att, const float* __restrict__ w_alpha, float* __restrict__ datt,
+    const __half* __restrict__ p_att, const float* __restrict__ w_alpha, float* __restrict__ datt,
     __nv_bfloat16* __restrict__ dp_att, float* __restrict__ dw_alpha, int T, int B, int L, int A, int H, int l_chunk) {
   extern __shared__ float sm[];
   float* s_ah = sm;                       // [T][A]
@@ -278,10 +280,10 @@ __global__ void __launch_bounds__(TILE_THREADS) att_tiles_bwd_kernel(
   __syncthreads();
   for (int a = threadIdx.x; a < A; a += TILE_THREADS) {
     const float wa = w_alpha[a];
-    float dw = 0.0f;
+    float dw = 0.0f, dbias = 0.0f;
     for (int q = 0; q < nl; ++q) {
       const long long off = (static_cast<long long>(b) * L + l0 + q) * A + a;
-      const float p = __bfloat162float(p_att[off]);
+      const float p = __half2float(p_att[off]);
       float acc = 0.0f;
       for (int t = 0; t < T; ++t) {
         const float th = tanh_approx(p + s_ah[t * A + a]);
@@ -290,8 +292,10 @@ __global__ void __launch_bounds__(TILE_THREADS) att_tiles_bwd_kernel(
         dw = fmaf(d, th, dw);
       }
       dp_att[off] = __float2bfloat16_rn(acc * wa);
+      dbias += acc * wa;
     }
     atomicAdd(dw_alpha + a, dw);
+    atomicAdd(dw_alpha + A + a, dbias);  // fp32 column sum of d p_att = d bias of ctx2att
   }
   for (int h = threadIdx.x; h < H; h += TILE_THREADS) {
     for (int q = 0; q < nl; ++q) {
@@ -314,7 +318,7 @@ int att_tiles_bwd(const float* de_all, const float* alpha_all, const float* dctx
   dim3 grid(B, (L + l_chunk - 1) / l_chunk);
   launch_begin("att_tiles_bwd", stream);
   att_tiles_bwd_kernel<<<grid, TILE_THREADS, smem, stream>>>(de_all, alpha_all, dctx_all, dctx_stride_t, ld_dctx, att_h_all,
-                                                             ah_stride_t, ld_ah, static_cast<const __nv_bfloat16*>(p_att), w_alpha,
+                                                             ah_stride_t, ld_ah, static_cast<const __half*>(p_att), w_alpha,
                                                              datt, static_cast<__nv_bfloat16*>(dp_att), dw_alpha, T, B, L, A, H,
                                                              l_chunk);
   UIC_CUDA_OK(cudaGetLastError());
@@ -440,14 +444,17 @@ int embed_bwd(const float* dxt, long long ld, const int64_t* tok, const void* ta
 }
 
 // ---- out_bf16 = x_f32 where y_bf16 > 0 else 0 (ReLU backward + operand cast) -----------------------------------
-__global__ void relu_bwd_cast_kernel(const float* __restrict__ x, const __nv_bfloat16* __restrict__ y,
+__global__ void relu_bwd_cast_kernel(float* __restrict__ x, const __nv_bfloat16* __restrict__ y,
                                      __nv_bfloat16* __restrict__ out, long long n) {
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
-       i += static_cast<long long>(gridDim.x) * blockDim.x)
-    out[i] = __float2bfloat16_rn(__bfloat162float(y[i]) > 0.0f ? x[i] : 0.0f);
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const float v = __bfloat162float(y[i]) > 0.0f ? x[i] : 0.0f;
+    x[i] = v;  // masked fp32 copy stays in place: the bias gradient is summed from it at full precision
+    out[i] = __float2bfloat16_rn(v);
+  }
 }
 
-int relu_bwd_cast(const float* x, const void* y, void* out, long long n, cudaStream_t stream) {
+int relu_bwd_cast(float* x, const void* y, void* out, long long n, cudaStream_t stream) {
   launch_begin("relu_bwd_cast", stream);
   relu_bwd_cast_kernel<<<grid_for(n, 256), 256, 0, stream>>>(x, static_cast<const __nv_bfloat16*>(y),
                                                              static_cast<__nv_bfloat16*>(out), n);

@@ -18,6 +18,8 @@
 #include <string>
 #include <tuple>
 
+#include <cuda_fp16.h>
+
 #include "uic_internal.h"
 #include "uic_ptx.cuh"
 
@@ -35,7 +37,23 @@ struct GemmEpilogue {
   const float* bias;
   int relu;
   int accumulate;
+  int out_f16;  // the 16-bit output is IEEE fp16 instead of bf16
 };
+
+__device__ __forceinline__ uint32_t pack16(float a, float b, int f16) {
+  if (f16) {
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+  }
+  return f2_to_bf16x2(a, b);
+}
+__device__ __forceinline__ __nv_bfloat16 store16(float a, int f16) {
+  if (f16) {
+    __half h = __float2half_rn(a);
+    return *reinterpret_cast<__nv_bfloat16*>(&h);
+  }
+  return __float2bfloat16_rn(a);
+}
 
 template <int BN, int STAGES>
 struct GemmSmem {
@@ -187,15 +205,15 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
 #pragma unroll
           for (int j = 0; j < 32; j += 8) {
             uint4 q;
-            q.x = f2_to_bf16x2(f[j], f[j + 1]);
-            q.y = f2_to_bf16x2(f[j + 2], f[j + 3]);
-            q.z = f2_to_bf16x2(f[j + 4], f[j + 5]);
-            q.w = f2_to_bf16x2(f[j + 6], f[j + 7]);
+            q.x = pack16(f[j], f[j + 1], ep.out_f16);
+            q.y = pack16(f[j + 2], f[j + 3], ep.out_f16);
+            q.z = pack16(f[j + 4], f[j + 5], ep.out_f16);
+            q.w = pack16(f[j + 6], f[j + 7], ep.out_f16);
             *reinterpret_cast<uint4*>(dst + j) = q;
           }
         } else {
           for (int j = 0; j < 32; ++j)
-            if (col0 + j < N) dst[j] = __float2bfloat16_rn(f[j]);
+            if (col0 + j < N) dst[j] = store16(f[j], ep.out_f16);
         }
       }
       }  // row_ok
@@ -245,7 +263,7 @@ __global__ void gemm_bf16_simt_kernel(const __nv_bfloat16* __restrict__ A, long 
     if (ep.accumulate && ep.c_f32) acc += ep.c_f32[static_cast<long long>(row) * ep.ldc + col];
     if (ep.relu) acc = fmaxf(acc, 0.0f);
     if (ep.c_f32) ep.c_f32[static_cast<long long>(row) * ep.ldc + col] = acc;
-    if (ep.c_bf16) ep.c_bf16[static_cast<long long>(row) * ep.ldcb + col] = __float2bfloat16_rn(acc);
+    if (ep.c_bf16) ep.c_bf16[static_cast<long long>(row) * ep.ldcb + col] = store16(acc, ep.out_f16);
   }
 }
 
@@ -301,7 +319,7 @@ int gemm_bf16(const void* A, long long lda, const void* B, long long ldb, float*
   const bool a_mn = flags & UIC_GEMM_A_MN_MAJOR;
   const bool b_mn = flags & UIC_GEMM_B_MN_MAJOR;
   GemmEpilogue ep{c_f32, ldc, static_cast<__nv_bfloat16*>(c_bf16), ldcb, bias, (flags & UIC_GEMM_RELU) ? 1 : 0,
-                  (flags & UIC_GEMM_ACCUMULATE) ? 1 : 0};
+                  (flags & UIC_GEMM_ACCUMULATE) ? 1 : 0, (flags & UIC_GEMM_OUT_F16) ? 1 : 0};
   if (gemm_impl() == GEMM_IMPL_SIMT) {
     dim3 grid((N + 15) / 16, (M + 15) / 16), block(16, 16);
     launch_begin("gemm_bf16_simt", stream);

@@ -41,7 +41,8 @@ int embed_rows(const void* table, long long ld_table, const int64_t* tok, void* 
                cudaStream_t stream);
 int att_step_fwd(const float* att_h, long long ld_att_h, const void* p_att, const void* att, const float* w_alpha,
                  const float* masks, void* ctx_bf16, long long ld_ctx_bf16, float* ctx_f32, long long ld_ctx_f32, float* alpha,
-                 int n_img, int beams, int L, int A, int H, cudaStream_t stream);
+                 void* workspace, long long workspace_bytes, int n_img, int beams, int L, int A, int H, cudaStream_t stream);
+long long att_step_workspace_bytes(int n_img, int beams, int L, int H);
 int lstm_maxout_fwd(const float* sums, long long ld_sums, const float* a2c, long long ld_a2c, const float* c_prev, float* c_out,
                     float* h_f32, void* h_a, long long ld_ha, void* h_b, long long ld_hb, int rows, int H, cudaStream_t stream);
 int lstm_cell_fwd(const float* gates, long long ld_gates, const float* c_prev, float* c_out, float* h_f32, void* h_a,
@@ -82,7 +83,7 @@ int log_softmax_bwd(const float* dlp, long long ld_dlp, const float* lp, long lo
 int col_sum(const void* x, int is_bf16, long long ld, float* out, int rows, int cols, cudaStream_t stream);
 int embed_bwd(const float* dxt, long long ld, const int64_t* tok, const void* table_relu, float* demb, long long rows, int E, int V,
               cudaStream_t stream);
-int relu_bwd_cast(const float* x, const void* y, void* out, long long n, cudaStream_t stream);
+int relu_bwd_cast(float* x, const void* y, void* out, long long n, cudaStream_t stream);
 int reduce_time(const float* src, long long stride_t, long long ld, int col0, float* dst, int T, int rows, int n,
                 cudaStream_t stream);
 }  // namespace uic

@@ -135,7 +135,7 @@ class DecoderEngine:
         gemm(x, w.w_att_embed, w.b_att_embed, out_bf16=att, relu=True)
         if att_masks is not None:
             check(self.lib.uic_zero_padded_rows(ptr(att), ptr(att_masks), B, L, H, stream()))
-        p_att = torch.empty(B * L, A, dtype=BF16, device=x.device)
+        p_att = torch.empty(B * L, A, dtype=torch.float16, device=x.device)   # fp16: added to att_h with HADD2 in the step kernel
         gemm(att, w.w_ctx2att, w.b_ctx2att, out_bf16=p_att)
         fc = None
         if self.kind == "topdown":
@@ -178,8 +178,8 @@ class DecoderEngine:
         if self.kind == "att2in2":
             S = ws["S"]
             gemm(X, w.w1, w.b1, out_f32=S)
-            check(lib.uic_att_step_fwd(ptr(S[:, 5 * H:]), S.stride(0), ptr(feats.p_att), ptr(feats.att), ptr(w.w_alpha),
-                                       ptr(feats.masks), ptr(ws["ctx"]), H, None, 0, ptr(alpha), feats.B, beams, feats.L, A, H, st))
+            _lib.att_step(S[:, 5 * H:], S.stride(0), feats.p_att, feats.att, w.w_alpha, feats.masks, ws["ctx"], H, None, 0, alpha,
+                          feats.B, beams, feats.L, A, H)
             gemm(ws["ctx"], w.w_a2c, w.b_a2c, out_f32=ws["a2c"])
             h_dst = cols(Xn, sl.h_out)
             check(lib.uic_lstm_maxout_fwd(ptr(S), S.stride(0), ptr(ws["a2c"]), 2 * H, ptr(c[0]), ptr(c_out[0]), None,
@@ -194,8 +194,8 @@ class DecoderEngine:
                                         ptr(cols(Xn, sl.h_att_prev)), Xn.stride(0), R, H, st))
             gemm(cols(X, sl.h_att), w.w_h2att, w.b_h2att, out_f32=ws["att_h"])
             ctx = cols(X, sl.ctx)
-            check(lib.uic_att_step_fwd(ptr(ws["att_h"]), A, ptr(feats.p_att), ptr(feats.att), ptr(w.w_alpha), ptr(feats.masks),
-                                       ptr(ctx), ldx, None, 0, ptr(alpha), feats.B, beams, feats.L, A, H, st))
+            _lib.att_step(ws["att_h"], A, feats.p_att, feats.att, w.w_alpha, feats.masks, ctx, ldx, None, 0, alpha,
+                          feats.B, beams, feats.L, A, H)
             G2 = ws.get("G2", G)  # teacher-forced runs keep both gate tensors for backward
             gemm(X[:, E + 2 * H:], w.w2, w.b2, out_f32=G2)
             check(lib.uic_lstm_cell_fwd(ptr(G2), 4 * H, ptr(c[1]), ptr(c_out[1]), None, ptr(cols(Xn, sl.h_lang)), Xn.stride(0),

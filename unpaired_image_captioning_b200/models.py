@@ -51,16 +51,14 @@ class Attention(nn.Module):
         if R % n_img:
             raise ValueError(f"Attention: {R} rows do not divide over {n_img} images")
         att_b = att if att.dtype == BF16 else _lib.cast_bf16(att.reshape(-1, H).float())
-        p_att = p_att_feats.reshape(-1, A)
-        p_b = p_att if p_att.dtype == BF16 else _lib.cast_bf16(p_att.float())
+        p_b = p_att_feats.reshape(n_img, L, A).to(torch.float16).contiguous()   # operand tiles: p_att fp16, att bf16
         att_h = torch.empty(R, A, device=h.device)
         _lib.gemm(_lib.cast_bf16(h.float().contiguous()), _lib.cast_bf16(self.h2att.weight.detach()),
                   self.h2att.bias.detach().float().contiguous(), out_f32=att_h)
         ctx = torch.empty(R, H, device=h.device)
         masks = None if att_masks is None else att_masks.reshape(n_img, L).float().contiguous()
         w = self.alpha_net.weight.detach().float().reshape(-1).contiguous()
-        check(lib.uic_att_step_fwd(ptr(att_h), A, ptr(p_b), ptr(att_b), ptr(w), ptr(masks), None, 0, ptr(ctx), H, None,
-                                   n_img, R // n_img, L, A, H, stream()))
+        _lib.att_step(att_h, A, p_b, att_b.reshape(n_img, L, H).contiguous(), w, masks, None, 0, ctx, H, None, n_img, R // n_img, L, A, H)
         return ctx
 
 
@@ -211,8 +209,7 @@ class AttModel(CaptionModel):
         L = att3.size(1)
         # the reference's beam path hands in per-beam expanded copies (AttModel.py:181-184): rows == n_img
         att_b = att3 if att3.dtype == BF16 else _lib.cast_bf16(att3.reshape(-1, H).float()).view(n_img, L, H)
-        p3 = p_att.reshape(n_img, L, A)
-        p_b = p3 if p3.dtype == BF16 else _lib.cast_bf16(p3.reshape(-1, A).float()).view(n_img, L, A)
+        p_b = p_att.reshape(n_img, L, A).to(torch.float16)
         masks = None if att_masks is None else att_masks.reshape(n_img, L).float().contiguous()
         fc_b = None
         if self.kind == "topdown":

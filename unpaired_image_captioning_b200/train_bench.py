@@ -53,4 +53,4 @@ def train_samples_per_s(args, world, rank, local):
             "config": {"workload": "configs[2]: TopDown XE training (fwd + loss + bwd + allreduce + clip + Adam)",
                        "caption_model": opt.caption_model, "rows_per_gpu": B, "att_regions": st["cfg"]["att_size"],
                        "rnn_size": opt.rnn_size, "vocab": opt.vocab_size + 1, "seq_length": opt.seq_length},
-            "scaling": "weak", "loss": float(one_train_step(st=st))}
+            "scaling": "weak", "loss": float(one_train_step(st=st).detach())}
