@@ -67,6 +67,14 @@ int uic_check_device(void);
 int uic_gemm_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, float* c_f32, int64_t ldc, void* c_bf16,
                   int64_t ldcb, const float* bias, int M, int N, int K, int flags, void* stream);
 
+/* Same, with the attention-operand epilogue: when exp_scale != 0, output columns >= exp_col0 become
+ * exp_scale * exp(2 x).  The additive attention needs tanh(p_att + att_h) for every (region, unit,
+ * beam, step); with E = exp(2 p_att)/16 stored once per image (ctx2att, fp16) and
+ * F = 16 exp(2 att_h) produced by the h2att projection each step, tanh(p + a) = 1 - 2 / (E F + 1)
+ * costs one FMA and (a share of) one reciprocal instead of one MUFU.TANH (a quarter-rate op). */
+int uic_gemm_bf16_ex(const void* A, int64_t lda, const void* B, int64_t ldb, float* c_f32, int64_t ldc, void* c_16, int64_t ldc16,
+                     const float* bias, int M, int N, int K, int flags, int exp_col0, float exp_scale, void* stream);
+
 /* ---- elementwise / layout ------------------------------------------------------------------ */
 /* dst_bf16[r, c] = bf16(relu?(src[r, c])) for an (rows x cols) fp32 matrix. Used to stage fp32
  * features and weights as tensor-core operands. */
@@ -86,8 +94,11 @@ int uic_zero_padded_rows(void* x_bf16, const float* att_masks, int n_img, int L,
  *   e[l]  = sum_a w_alpha[a] * tanh(p_att[i,l,a] + att_h[r,a])        (alpha_net bias cancels in softmax)
  *   alpha = softmax_l(e);  if att_masks: alpha = alpha*m / sum(alpha*m)
  *   ctx[r,:] = sum_l alpha[l] * att[i,l,:]
- * att_h is the h2att projection INCLUDING its bias (fp32, pitch ld_att_h).  p_att is FP16 (n_img,L,A)
- * and att is bf16 (n_img,L,H); both are read once per image and shared by the image's beams.
+ * Operands are passed in the exponential form produced by uic_gemm_bf16_ex:
+ *   att_h  -> F[r,a]   = 16 * exp(2 * (h2att(h)[r,a] + bias))   fp32, pitch ld_att_h
+ *   p_att  -> E[i,l,a] = exp(2 * p_att[i,l,a]) / 16             FP16 (n_img, L, A)
+ * so that tanh(p_att + att_h) = 1 - 2 / (E F + 1).  att is bf16 (n_img,L,H).  Both tiles are read
+ * once per image and shared by the image's beams.
  * Outputs (each optional): ctx_bf16, ctx_f32, alpha (rows x L fp32, saved for backward).
  * `workspace`: uic_att_step_workspace_bytes(...) bytes, 16-byte aligned, zeroed ONCE by the caller
  * (the kernel leaves its arrival counters at zero); it holds the partial results when the regions

@@ -83,6 +83,23 @@ def test_gemm_mn_major_operands(a_mn, b_mn, M, N, K):
     torch.testing.assert_close(out, ref, rtol=2e-4, atol=2e-4)
 
 
+def test_gemm_exponential_attention_epilogue():
+    """Columns >= exp_col0 come out as scale * exp(2x); fp16 output is clamped to the fp16 range."""
+    M, N, K = 70, 96, 64
+    a, b = _rand_bf16(M, K, seed=31, scale=0.3), _rand_bf16(N, K, seed=32, scale=0.3)
+    bias = torch.randn(N, device=DEV) * 0.1
+    ref = a.float() @ b.float().t() + bias
+    out = torch.empty(M, N, device=DEV)
+    _lib.gemm(a, b, bias, out_f32=out, exp_col0=40, exp_scale=16.0)
+    torch.testing.assert_close(out[:, :40], ref[:, :40], rtol=2e-4, atol=2e-4)
+    torch.testing.assert_close(out[:, 40:], 16.0 * torch.exp(2 * ref[:, 40:]), rtol=2e-3, atol=1e-4)
+    out16 = torch.empty(M, N, device=DEV, dtype=torch.float16)
+    _lib.gemm(a, b, bias + 6.0, out_bf16=out16, exp_col0=0, exp_scale=1 / 16)
+    want = (torch.exp(2 * (ref + 6.0)) / 16).clamp(max=65504.0)
+    torch.testing.assert_close(out16.float(), want, rtol=3e-3, atol=1e-3)
+    assert torch.isfinite(out16.float()).all()
+
+
 def test_gemm_rejects_bad_arguments():
     a, b = _rand_bf16(16, 24), _rand_bf16(8, 24)
     with pytest.raises(ValueError):
@@ -125,10 +142,15 @@ def test_att_step_fwd(B, beams, L, A, H, use_masks):
     ctx_b = torch.empty(R, H, device=DEV, dtype=torch.bfloat16)
     ctx_f = torch.empty(R, H, device=DEV)
     alpha = torch.empty(R, L, device=DEV)
+    # operands in the exponential form the GEMM epilogues produce: E = exp(2 p)/16 (fp16), F = 16 exp(2 att_h)
+    e_tile = _lib.exp_tile(p_att)
+    f_full = (torch.exp(2.0 * att_h_full) * _lib.ATT_F_SCALE).contiguous()
+    f_view = f_full[:, 8:8 + A]
     for _ in range(2):   # twice: the split-merge arrival counters must be left at zero by the kernel
         ctx_f.zero_()
-        _lib.att_step(att_h, att_h_full.stride(0), p_att, att, w, masks, ctx_b, H, ctx_f, H, alpha, B, beams, L, A, H)
-    ref_ctx, ref_alpha = _att_reference(att_h, p_att, att, w, masks, beams)
+        _lib.att_step(f_view, f_full.stride(0), e_tile, att, w, masks, ctx_b, H, ctx_f, H, alpha, B, beams, L, A, H)
+    p_eff = 0.5 * torch.log(e_tile.float() * 16.0)          # the value the fp16 tile actually encodes
+    ref_ctx, ref_alpha = _att_reference(att_h, p_eff, att, w, masks, beams)
     torch.testing.assert_close(alpha, ref_alpha, rtol=5e-3, atol=2e-5)     # tanh.approx.f32 inside the score
     torch.testing.assert_close(ctx_f, ref_ctx, rtol=5e-3, atol=5e-4)
     torch.testing.assert_close(ctx_b.float(), ref_ctx, rtol=1e-2, atol=1e-2)

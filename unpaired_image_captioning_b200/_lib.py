@@ -24,6 +24,7 @@ SIGNATURES = {
     "uic_profile_enable": (_i, [_i]),
     "uic_profile_dump": (_i64, [C.c_char_p, _i64]),
     "uic_gemm_bf16": (_i, [_p, _i64, _p, _i64, _p, _i64, _p, _i64, _p, _i, _i, _i, _i, _p]),
+    "uic_gemm_bf16_ex": (_i, [_p, _i64, _p, _i64, _p, _i64, _p, _i64, _p, _i, _i, _i, _i, _i, _f, _p]),
     "uic_cast_f32_bf16": (_i, [_p, _i64, _p, _i64, _i64, _i64, _i, _p]),
     "uic_embed_rows": (_i, [_p, _i64, _p, _p, _i64, _i, _i, _i, _p]),
     "uic_zero_padded_rows": (_i, [_p, _p, _i, _i, _i, _p]),
@@ -122,7 +123,17 @@ def _is_bf16(t):
     return t.dtype == torch.bfloat16 and t.is_cuda and t.stride(-1) == 1
 
 
-def gemm(a, b, bias=None, out_f32=None, out_bf16=None, relu=False, accumulate=False, a_mn=False, b_mn=False):
+ATT_E_SCALE, ATT_F_SCALE = 1.0 / 16.0, 16.0   # E = exp(2 p_att)/16 (fp16 tile), F = 16 exp(2 att_h): E*F = exp(2(p+a))
+
+
+def exp_tile(p_att):
+    """Raw ctx2att output -> the fp16 operand tile E = exp(2 p)/16 (API-compat path only; the engine gets
+    it straight from the ctx2att GEMM epilogue)."""
+    return (torch.exp(2.0 * p_att.float()) * ATT_E_SCALE).clamp_(max=65504.0).to(torch.float16)
+
+
+def gemm(a, b, bias=None, out_f32=None, out_bf16=None, relu=False, accumulate=False, a_mn=False, b_mn=False,
+         exp_col0=0, exp_scale=0.0):
     """D[M,N] = act(A @ B^T + bias).  `a` is (M,K) [or (K,M) if a_mn], `b` is (N,K) [or (K,N) if b_mn];
     both 2-D bf16 views whose last stride is 1 (row pitch arbitrary)."""
     if not (_is_bf16(a) and _is_bf16(b) and a.dim() == 2 and b.dim() == 2):
@@ -139,8 +150,9 @@ def gemm(a, b, bias=None, out_f32=None, out_bf16=None, relu=False, accumulate=Fa
         raise ValueError("gemm: bias must be contiguous fp32 of length N")
     flags = ((GEMM_RELU if relu else 0) | (GEMM_ACCUMULATE if accumulate else 0) | (GEMM_A_MN if a_mn else 0) |
              (GEMM_B_MN if b_mn else 0) | (GEMM_OUT_F16 if out_f16 else 0))
-    check(load().uic_gemm_bf16(ptr(a), a.stride(0), ptr(b), b.stride(0), ptr(out_f32), out_f32.stride(0) if out_f32 is not None else 0,
-                               ptr(out_bf16), out_bf16.stride(0) if out_bf16 is not None else 0, ptr(bias), M, N, K, flags, stream()))
+    check(load().uic_gemm_bf16_ex(ptr(a), a.stride(0), ptr(b), b.stride(0), ptr(out_f32), out_f32.stride(0) if out_f32 is not None else 0,
+                                  ptr(out_bf16), out_bf16.stride(0) if out_bf16 is not None else 0, ptr(bias), M, N, K, flags,
+                                  int(exp_col0), float(exp_scale), stream()))
 
 
 _att_ws = {}

@@ -211,6 +211,13 @@ int uic_gemm_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, float*
   return gemm_bf16(A, lda, B, ldb, c_f32, ldc, c_bf16, ldcb, bias, M, N, K, flags, ST(stream));
 }
 
+int uic_gemm_bf16_ex(const void* A, int64_t lda, const void* B, int64_t ldb, float* c_f32, int64_t ldc, void* c_16, int64_t ldc16,
+                     const float* bias, int M, int N, int K, int flags, int exp_col0, float exp_scale, void* stream) {
+  REQUIRE(A && B, UIC_ERR_ARG, "uic_gemm_bf16_ex: null operand");
+  REQUIRE(exp_col0 >= 0, UIC_ERR_ARG, "uic_gemm_bf16_ex: exp_col0=%d", exp_col0);
+  return gemm_bf16(A, lda, B, ldb, c_f32, ldc, c_16, ldc16, bias, M, N, K, flags, ST(stream), exp_col0, exp_scale);
+}
+
 int uic_cast_f32_bf16(const float* src, int64_t ld_src, void* dst, int64_t ld_dst, int64_t rows, int64_t cols, int relu,
                       void* stream) {
   REQUIRE(src && dst, UIC_ERR_ARG, "uic_cast_f32_bf16: null pointer");

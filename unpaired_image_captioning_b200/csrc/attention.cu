@@ -5,17 +5,19 @@
 // HBM-bound by design: per image and step the kernel reads p_att[i] (L x A fp16) and att[i]
 // (L x H bf16) exactly once, no matter how many beams share the image.
 //
-// Structure (round-1 pass 2, after the first ncu capture showed the register-resident version was
-// latency bound at 15 % of HBM peak with 8 warps/SM):
-//   * grid = (image x L-split, beam group); each CTA owns a contiguous run of regions and streams
-//     them through a 3-stage shared-memory ring filled by bulk async copies (cp.async.bulk +
-//     mbarrier complete_tx), so the loads in flight do not depend on registers or occupancy;
-//   * per stage (<= 8 regions): phase 1, one warp per region: e[r][j] = w . tanh(p_att[r] + att_h[j])
-//     with packed tanh.approx.f16x2 (half the MUFU work of the fp32 form, same 2^-11 error) and an
-//     fp32 dot product; phase 2, one thread per pair of feature columns: online-softmax update of
-//     ctx[j][col] over the stage's regions (6 accumulator registers instead of 48);
-//   * L-splits of an image are merged by the last CTA to arrive (threadfence reduction) from a
-//     small fp32 workspace; no second launch.
+// Structure (third iteration, see profiles/ for the ncu captures that drove it):
+//   v1 kept a region per warp in registers with one prefetch in flight: latency bound, 15 % of HBM.
+//   v2 staged 8-region tiles per CTA with two block-wide phases per stage: 3x the instructions
+//      (addressing, bookkeeping, barrier spinning) for no gain.
+//   v3 (this file): every warp is autonomous.  Warp w of a CTA owns regions w, w+8, ... of the CTA's
+//      run and streams them through its PRIVATE 4-slot shared-memory ring: lane 0 issues two bulk
+//      async copies (cp.async.bulk, mbarrier complete_tx) per region, four regions ahead, so loads
+//      in flight do not depend on registers or occupancy and no block-wide barrier exists in the
+//      steady state.  Per region the warp computes e[j] = w . tanh(p_att + att_h[j]) for its beams
+//      with packed tanh.approx.f16x2 (half the MUFU work of the fp32 form, same 2^-11 error; p_att
+//      is fp16 so the add is one HADD2), an fp32 dot product, a warp-shuffle reduction, an online
+//      softmax and the fp32 context accumulation.  Warps are merged once through shared memory;
+//      L-splits of an image are merged by the last CTA to arrive (threadfence reduction).
 #include <cuda_fp16.h>
 
 #include "uic_internal.h"
@@ -25,8 +27,7 @@ namespace uic {
 
 constexpr int ATT_THREADS = 256;
 constexpr int ATT_WARPS = ATT_THREADS / 32;
-constexpr int ATT_STAGE_ROWS = 8;   // capacity of one ring slot (regions); the host may use 6..8
-constexpr int ATT_NSTAGES = 3;
+constexpr int ATT_SLOTS = 4;        // regions in flight per warp
 constexpr int ATT_MAX_SPLIT = 8;
 
 struct AttParams {
@@ -44,12 +45,12 @@ struct AttParams {
   float* ws_partial;   // [img][group][split][NB][H + 2]
   int* ws_counter;     // [img][group], zero between launches
   int beams, L, A, H;
-  int rows_per_stage, stages_per_cta, total_stages, nsplit;
+  int rows_per_cta, nsplit;
 };
 
-__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(smem_dst)),
-               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+__device__ __forceinline__ void bulk_g2s(uint32_t smem_dst, const void* gsrc, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_dst), "l"(gsrc),
+               "r"(bytes), "r"(bar)
                : "memory");
 }
 __device__ __forceinline__ uint32_t tanh_f16x2(uint32_t x) {
@@ -62,13 +63,25 @@ __device__ __forceinline__ uint32_t hadd2_u32(uint32_t a, uint32_t b) {
   return *reinterpret_cast<uint32_t*>(&r);
 }
 
-template <int NB, int CA, int CHP>
-__global__ void __launch_bounds__(ATT_THREADS, (CA <= 2 && CHP <= 1) ? 3 : 1) att_step_fwd_kernel(AttParams p) {
+// out[0..8) = base[a0 .. a0+8) (zero past n): two 16-byte loads when aligned, scalar otherwise.
+__device__ __forceinline__ void load8(const float* __restrict__ base, int a0, int n, float* out) {
+  if (a0 + 8 <= n && (reinterpret_cast<uintptr_t>(base + a0) & 15) == 0) {
+    const float4 lo = __ldg(reinterpret_cast<const float4*>(base + a0));
+    const float4 hi = __ldg(reinterpret_cast<const float4*>(base + a0) + 1);
+    out[0] = lo.x; out[1] = lo.y; out[2] = lo.z; out[3] = lo.w;
+    out[4] = hi.x; out[5] = hi.y; out[6] = hi.z; out[7] = hi.w;
+  } else {
+#pragma unroll
+    for (int k = 0; k < 8; ++k) out[k] = (a0 + k < n) ? __ldg(base + a0 + k) : 0.0f;
+  }
+}
+
+// CA = ceil(A / 256), CH = ceil(H / 256): lane owns elements [256c + 8*lane, +8) of chunk c.
+template <int NB, int CA, int CH>
+__global__ void __launch_bounds__(ATT_THREADS, (NB * (CA + CH) <= 12) ? 2 : 1) att_step_fwd_kernel(AttParams p) {
   extern __shared__ __align__(128) uint8_t att_smem[];
-  __shared__ uint64_t full_bar[ATT_NSTAGES];
-  __shared__ float s_e[ATT_STAGE_ROWS * NB];
-  __shared__ float s_wp[ATT_WARPS][ATT_STAGE_ROWS * NB];
-  __shared__ float s_wscale[ATT_WARPS][NB];
+  __shared__ uint64_t s_bar[ATT_WARPS][ATT_SLOTS];
+  __shared__ float s_m[NB][ATT_WARPS], s_s[NB][ATT_WARPS];
   __shared__ int s_last;
 
   const int L = p.L, A = p.A, H = p.H;
@@ -77,166 +90,219 @@ __global__ void __launch_bounds__(ATT_THREADS, (CA <= 2 && CHP <= 1) ? 3 : 1) at
   const int beam0 = grp * NB;
   const int nb = min(NB, p.beams - beam0);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
-  const int rs = p.rows_per_stage;
-  const int stage0 = split * p.stages_per_cta;
-  const int n_iters = min(p.stages_per_cta, p.total_stages - stage0);
-  const uint32_t stage_bytes = ATT_STAGE_ROWS * (A + H) * 2;
+  const int row_begin = split * p.rows_per_cta;
+  const int row_end = min(L, row_begin + p.rows_per_cta);
+  const uint32_t row_bytes_p = A * 2, row_bytes_a = H * 2, slot_bytes = row_bytes_p + row_bytes_a;
   const __half* p_img = p.p_att + static_cast<long long>(img) * L * A;
   const __nv_bfloat16* a_img = p.att + static_cast<long long>(img) * L * H;
   const float* m_img = p.masks ? p.masks + static_cast<long long>(img) * L : nullptr;
 
-  auto issue = [&](int it) {  // one thread: arm the slot's barrier and start both bulk copies
-    const int s = it % ATT_NSTAGES;
-    const int l0 = (stage0 + it) * rs;
-    const int n = min(rs, L - l0);
-    uint8_t* slot = att_smem + s * stage_bytes;
-    const uint32_t bp = n * A * 2, ba = n * H * 2;
-    mbar_arrive_expect_tx(&full_bar[s], bp + ba);
-    bulk_g2s(slot, p_img + static_cast<long long>(l0) * A, bp, &full_bar[s]);
-    bulk_g2s(slot + ATT_STAGE_ROWS * A * 2, a_img + static_cast<long long>(l0) * H, ba, &full_bar[s]);
-  };
+  const uint32_t ring = smem_u32(att_smem) + warp * ATT_SLOTS * slot_bytes;   // this warp's private ring
+  const uint32_t bar0 = smem_u32(&s_bar[warp][0]);
 
-  if (tid == 0) {
-    for (int s = 0; s < ATT_NSTAGES; ++s) mbar_init(&full_bar[s], 1);
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < ATT_SLOTS; ++s) mbar_init(&s_bar[warp][s], 1);
     fence_barrier_init();
   }
-  __syncthreads();
-  if (tid == 0)
-    for (int it = 0; it < ATT_NSTAGES && it < n_iters; ++it) issue(it);
+  __syncwarp();
+  auto issue = [&](int l, int s) {  // lane 0 only
+    mbar_arrive_expect_tx(&s_bar[warp][s], slot_bytes);
+    bulk_g2s(ring + s * slot_bytes, p_img + static_cast<long long>(l) * A, row_bytes_p, bar0 + s * 8);
+    bulk_g2s(ring + s * slot_bytes + row_bytes_p, a_img + static_cast<long long>(l) * H, row_bytes_a, bar0 + s * 8);
+  };
+  if (lane == 0) {
+#pragma unroll
+    for (int s = 0; s < ATT_SLOTS; ++s) {
+      const int l = row_begin + warp + s * ATT_WARPS;
+      if (l < row_end) issue(l, s);
+    }
+  }
 
-  // per-lane constants for phase 1: alpha_net weight (fp32) and att_h of each beam as half2
+  // per-lane constants: -2 * alpha_net weight and F = 16 exp(2 att_h) of each beam (fp32)
   float w[CA * 8];
-  uint32_t ah2[NB][CA * 4];
+  float F[NB][CA * 8];
 #pragma unroll
   for (int c = 0; c < CA; ++c) {
     const int a0 = c * 256 + lane * 8;
+    load8(p.w_alpha, a0, A, &w[c * 8]);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) w[c * 8 + k] = (a0 + k < A) ? __ldg(p.w_alpha + a0 + k) : 0.0f;
+    for (int k = 0; k < 8; ++k) w[c * 8 + k] *= -2.0f;
 #pragma unroll
     for (int j = 0; j < NB; ++j) {
       const long long row = static_cast<long long>(img) * p.beams + beam0 + (j < nb ? j : 0);
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const int a = a0 + 2 * k;
-        const float x0 = (a < A) ? __ldg(p.att_h + row * p.ld_att_h + a) : 0.0f;
-        const float x1 = (a + 1 < A) ? __ldg(p.att_h + row * p.ld_att_h + a + 1) : 0.0f;
-        __half2 h2 = __floats2half2_rn(x0, x1);
-        ah2[j][c * 4 + k] = *reinterpret_cast<uint32_t*>(&h2);
-      }
+      load8(p.att_h + row * p.ld_att_h, a0, A, &F[j][c * 8]);
     }
   }
 
-  // online softmax state: lane l < NB*8 tracks beam j = l % NB (replicated in every warp)
-  const int my_j = lane % NB;
-  float m_run = -INFINITY, s_run = 0.0f;
-  float acc[NB][CHP * 2];
+  float m_run[NB], s_run[NB];
+  float acc[NB][CH * 8];
+#pragma unroll
+  for (int j = 0; j < NB; ++j) {
+    m_run[j] = -INFINITY;
+    s_run[j] = 0.0f;
+#pragma unroll
+    for (int k = 0; k < CH * 8; ++k) acc[j][k] = 0.0f;
+  }
+
+  int slot = 0;
+  uint32_t parity = 0;
+  for (int l = row_begin + warp; l < row_end; l += ATT_WARPS) {
+    mbar_wait(&s_bar[warp][slot], parity);
+    const uint32_t base = ring + slot * slot_bytes;
+    uint4 q[CA], av[CH];
+#pragma unroll
+    for (int c = 0; c < CA; ++c) {
+      const int a0 = c * 256 + lane * 8;
+      q[c] = make_uint4(0, 0, 0, 0);
+      if (a0 < A) asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(q[c].x), "=r"(q[c].y), "=r"(q[c].z), "=r"(q[c].w) : "r"(base + a0 * 2));
+    }
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+      const int h0 = c * 256 + lane * 8;
+      av[c] = make_uint4(0, 0, 0, 0);
+      if (h0 < H)
+        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(av[c].x), "=r"(av[c].y), "=r"(av[c].z), "=r"(av[c].w) : "r"(base + row_bytes_p + h0 * 2));
+    }
+    const float mask_l = m_img ? __ldg(m_img + l) : 1.0f;
+
+    // ---- scores ------------------------------------------------------------------------------
+    // tanh(p + a) = 1 - 2 / (E F + 1); the constant sum(w) drops out of the softmax, so the score is
+    // e = sum_a (-2 w_a) / (E_a F_a + 1).  One reciprocal serves a PAIR of units:
+    //   w1/d1 + w2/d2 = (w1 d2 + w2 d1) / (d1 d2)          (d <= 1 + 65504 * F: no fp32 overflow for |att_h| < 30)
+    float Ef[CA * 8];
+#pragma unroll
+    for (int c = 0; c < CA; ++c) {
+      const uint32_t u[4] = {q[c].x, q[c].y, q[c].z, q[c].w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 t = __half22float2(*reinterpret_cast<const __half2*>(&u[k]));
+        Ef[c * 8 + 2 * k] = t.x;
+        Ef[c * 8 + 2 * k + 1] = t.y;
+      }
+    }
+    float e[NB];
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+      float p0 = 0.0f, p1 = 0.0f;
+#pragma unroll
+      for (int k = 0; k < CA * 8; k += 2) {
+        const float d1 = fmaf(Ef[k], F[j][k], 1.0f);
+        const float d2 = fmaf(Ef[k + 1], F[j][k + 1], 1.0f);
+        const float r = rcp_approx(d1 * d2);
+        const float num = fmaf(w[k + 1], d1, w[k] * d2);
+        if ((k & 2) == 0) p0 = fmaf(r, num, p0); else p1 = fmaf(r, num, p1);
+      }
+      e[j] = p0 + p1;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int j = 0; j < NB; ++j) e[j] += __shfl_xor_sync(0xffffffffu, e[j], o);
+    }
+    if (p.alpha != nullptr && lane < nb) {
+      float ej = e[0];
+#pragma unroll
+      for (int j = 1; j < NB; ++j) ej = (lane == j) ? e[j] : ej;
+      p.alpha[(static_cast<long long>(img) * p.beams + beam0 + lane) * L + l] = ej;  // raw score, normalised at the end
+    }
+
+    // ---- online softmax + context ---------------------------------------------------------------
+    float af[CH * 8];
+#pragma unroll
+    for (int c = 0; c < CH; ++c) {
+      const uint32_t u[4] = {av[c].x, av[c].y, av[c].z, av[c].w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        af[c * 8 + 2 * k] = __uint_as_float(u[k] << 16);
+        af[c * 8 + 2 * k + 1] = __uint_as_float(u[k] & 0xffff0000u);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+      if (e[j] > m_run[j]) {  // warp-uniform: rare after the first few regions
+        const float scale = __expf(m_run[j] - e[j]);
+        m_run[j] = e[j];
+        s_run[j] *= scale;
+#pragma unroll
+        for (int k = 0; k < CH * 8; ++k) acc[j][k] *= scale;
+      }
+      const float pl = __expf(e[j] - m_run[j]) * mask_l;
+      s_run[j] += pl;
+#pragma unroll
+      for (int k = 0; k < CH * 8; ++k) acc[j][k] = fmaf(pl, af[k], acc[j][k]);
+    }
+    // Refill the slot only now: the FMAs above consumed every lane's registers loaded from it, so no
+    // shared-memory read of this slot can still be in flight when the async copy lands.
+    __syncwarp();
+    if (lane == 0) {
+      const int ln = l + ATT_SLOTS * ATT_WARPS;
+      if (ln < row_end) issue(ln, slot);
+    }
+    if (++slot == ATT_SLOTS) {
+      slot = 0;
+      parity ^= 1;
+    }
+  }
+
+  // ---- merge the warps of this CTA through shared memory (the rings are idle now) ----------------------
+  __syncthreads();
+  float* s_acc = reinterpret_cast<float*>(att_smem);  // [ATT_WARPS][NB][H]
+  if (lane == 0) {
+#pragma unroll
+    for (int j = 0; j < NB; ++j) {
+      s_m[j][warp] = m_run[j];
+      s_s[j][warp] = s_run[j];
+    }
+  }
 #pragma unroll
   for (int j = 0; j < NB; ++j)
 #pragma unroll
-    for (int k = 0; k < CHP * 2; ++k) acc[j][k] = 0.0f;
-
-  for (int it = 0; it < n_iters; ++it) {
-    const int s = it % ATT_NSTAGES;
-    const int l0 = (stage0 + it) * rs;
-    const int n = min(rs, L - l0);
-    const uint8_t* slot = att_smem + s * stage_bytes;
-    mbar_wait(&full_bar[s], (it / ATT_NSTAGES) & 1);
-
-    // ---- phase 1: scores, one warp per region -----------------------------------------------
-    if (warp < n) {
-      const uint8_t* prow = slot + static_cast<size_t>(warp) * A * 2;
-      uint4 q[CA];
-#pragma unroll
-      for (int c = 0; c < CA; ++c) {
-        const int a0 = c * 256 + lane * 8;
-        q[c] = (a0 < A) ? *reinterpret_cast<const uint4*>(prow + a0 * 2) : make_uint4(0, 0, 0, 0);
-      }
-#pragma unroll
-      for (int j = 0; j < NB; ++j) {
-        float part = 0.0f;
-#pragma unroll
-        for (int c = 0; c < CA; ++c) {
-          const uint32_t u[4] = {q[c].x, q[c].y, q[c].z, q[c].w};
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            uint32_t t2 = tanh_f16x2(hadd2_u32(u[k], ah2[j][c * 4 + k]));
-            const float2 t = __half22float2(*reinterpret_cast<__half2*>(&t2));
-            part = fmaf(w[c * 8 + 2 * k], t.x, part);
-            part = fmaf(w[c * 8 + 2 * k + 1], t.y, part);
-          }
-        }
-        const float e = warp_sum(part);
-        if (lane == 0) {
-          s_e[warp * NB + j] = e;
-          if (p.alpha != nullptr && j < nb)
-            p.alpha[(static_cast<long long>(img) * p.beams + beam0 + j) * L + l0 + warp] = e;  // raw score, normalised at the end
-        }
+    for (int c = 0; c < CH; ++c) {
+      const int h0 = c * 256 + lane * 8;
+      if (h0 < H) {
+        float* dst = s_acc + (static_cast<size_t>(warp) * NB + j) * H + h0;
+        *reinterpret_cast<float4*>(dst) = make_float4(acc[j][c * 8], acc[j][c * 8 + 1], acc[j][c * 8 + 2], acc[j][c * 8 + 3]);
+        *reinterpret_cast<float4*>(dst + 4) = make_float4(acc[j][c * 8 + 4], acc[j][c * 8 + 5], acc[j][c * 8 + 6], acc[j][c * 8 + 7]);
       }
     }
-    __syncthreads();
-
-    // ---- softmax bookkeeping, replicated per warp (no block-wide sync needed) -------------------
-    {
-      const int r = lane / NB;
-      const bool valid = lane < n * NB;
-      float m_st = -INFINITY;
-      for (int rr = 0; rr < n; ++rr) m_st = fmaxf(m_st, s_e[rr * NB + my_j]);
-      const float m_new = fmaxf(m_run, m_st);
-      const float scale = __expf(m_run - m_new);  // 0 on the first stage (m_run = -inf)
-      const float mk = (valid && m_img) ? m_img[l0 + r] : 1.0f;
-      const float pv = valid ? __expf(s_e[lane] - m_new) * mk : 0.0f;
-      if (lane < ATT_STAGE_ROWS * NB) s_wp[warp][lane] = pv;
-      if (lane < NB) s_wscale[warp][lane] = scale;
-      __syncwarp();
-      float s_st = 0.0f;
-      for (int rr = 0; rr < n; ++rr) s_st += s_wp[warp][rr * NB + my_j];
-      s_run = s_run * scale + s_st;
-      m_run = m_new;
-    }
-
-    // ---- phase 2: context accumulation, one thread per pair of feature columns ---------------------
-    {
-      float sc[NB];
-      bool rescale = false;
-#pragma unroll
-      for (int j = 0; j < NB; ++j) {
-        sc[j] = s_wscale[warp][j];
-        rescale |= sc[j] != 1.0f;
-      }
-      if (rescale) {
-#pragma unroll
-        for (int j = 0; j < NB; ++j)
-#pragma unroll
-          for (int k = 0; k < CHP * 2; ++k) acc[j][k] *= sc[j];
-      }
-      const uint8_t* abase = slot + ATT_STAGE_ROWS * A * 2;
-#pragma unroll
-      for (int i = 0; i < CHP; ++i) {
-        const int col = 2 * (tid + ATT_THREADS * i);
-        if (col < H) {
-          for (int rr = 0; rr < n; ++rr) {
-            const float2 a = bf16x2_to_f2(*reinterpret_cast<const uint32_t*>(abase + (static_cast<size_t>(rr) * H + col) * 2));
-#pragma unroll
-            for (int j = 0; j < NB; ++j) {
-              const float pj = s_wp[warp][rr * NB + j];
-              acc[j][2 * i] = fmaf(pj, a.x, acc[j][2 * i]);
-              acc[j][2 * i + 1] = fmaf(pj, a.y, acc[j][2 * i + 1]);
-            }
-          }
-        }
-      }
-    }
-    __syncthreads();  // every warp is done with slot s (and with s_e)
-    if (tid == 0 && it + ATT_NSTAGES < n_iters) issue(it + ATT_NSTAGES);
-  }
-
-  // beam j's running (max, sum) live in lane j of every warp
-  float Mj[NB], Sj[NB];
+  __syncthreads();
+  float Mj[NB], Sj[NB], fw[NB][ATT_WARPS];
 #pragma unroll
   for (int j = 0; j < NB; ++j) {
-    Mj[j] = __shfl_sync(0xffffffffu, m_run, j);
-    Sj[j] = __shfl_sync(0xffffffffu, s_run, j);
+    float mx = -INFINITY;
+#pragma unroll
+    for (int q2 = 0; q2 < ATT_WARPS; ++q2) mx = fmaxf(mx, s_m[j][q2]);
+    float ss = 0.0f;
+#pragma unroll
+    for (int q2 = 0; q2 < ATT_WARPS; ++q2) {
+      const float mq = s_m[j][q2];
+      fw[j][q2] = (mq == -INFINITY) ? 0.0f : __expf(mq - mx);
+      ss += s_s[j][q2] * fw[j][q2];
+    }
+    Mj[j] = mx;
+    Sj[j] = ss;
   }
+  // thread `tid` owns the column pairs col = 2*(tid + 256*i)
+  constexpr int CHP = (CH + 1) / 2;
+  float out[NB][CHP * 2];
+#pragma unroll
+  for (int j = 0; j < NB; ++j)
+#pragma unroll
+    for (int i = 0; i < CHP; ++i) {
+      const int col = 2 * (tid + ATT_THREADS * i);
+      float2 v = make_float2(0.0f, 0.0f);
+      if (col < H) {
+#pragma unroll
+        for (int q2 = 0; q2 < ATT_WARPS; ++q2) {
+          const float2 a = *reinterpret_cast<const float2*>(s_acc + (static_cast<size_t>(q2) * NB + j) * H + col);
+          v.x = fmaf(a.x, fw[j][q2], v.x);
+          v.y = fmaf(a.y, fw[j][q2], v.y);
+        }
+      }
+      out[j][2 * i] = v.x;
+      out[j][2 * i + 1] = v.y;
+    }
 
   if (p.nsplit > 1) {
     // ---- publish this split's partial, last arriver merges ------------------------------------------
@@ -246,7 +312,7 @@ __global__ void __launch_bounds__(ATT_THREADS, (CA <= 2 && CHP <= 1) ? 3 : 1) at
 #pragma unroll
       for (int i = 0; i < CHP; ++i) {
         const int col = 2 * (tid + ATT_THREADS * i);
-        if (col < H) *reinterpret_cast<float2*>(part + j * (H + 2) + col) = make_float2(acc[j][2 * i], acc[j][2 * i + 1]);
+        if (col < H) *reinterpret_cast<float2*>(part + j * (H + 2) + col) = make_float2(out[j][2 * i], out[j][2 * i + 1]);
       }
       if (tid == 0) {
         part[j * (H + 2) + H] = Mj[j];
@@ -274,7 +340,8 @@ __global__ void __launch_bounds__(ATT_THREADS, (CA <= 2 && CHP <= 1) ? 3 : 1) at
       for (int k = 0; k < ATT_MAX_SPLIT; ++k) {
         f[k] = 0.0f;
         if (k < p.nsplit) {
-          f[k] = __expf(__ldcg(base + (k * NB + j) * (H + 2) + H) - mx);
+          const float mk = __ldcg(base + (k * NB + j) * (H + 2) + H);
+          f[k] = (mk == -INFINITY) ? 0.0f : __expf(mk - mx);
           ssum += __ldcg(base + (k * NB + j) * (H + 2) + H + 1) * f[k];
         }
       }
@@ -292,8 +359,8 @@ __global__ void __launch_bounds__(ATT_THREADS, (CA <= 2 && CHP <= 1) ? 3 : 1) at
             }
           }
         }
-        acc[j][2 * i] = v.x;
-        acc[j][2 * i + 1] = v.y;
+        out[j][2 * i] = v.x;
+        out[j][2 * i + 1] = v.y;
       }
       Mj[j] = mx;
       Sj[j] = ssum;
@@ -310,7 +377,7 @@ __global__ void __launch_bounds__(ATT_THREADS, (CA <= 2 && CHP <= 1) ? 3 : 1) at
       for (int i = 0; i < CHP; ++i) {
         const int col = 2 * (tid + ATT_THREADS * i);
         if (col < H) {
-          const float v0 = acc[j][2 * i] * inv, v1 = acc[j][2 * i + 1] * inv;
+          const float v0 = out[j][2 * i] * inv, v1 = out[j][2 * i + 1] * inv;
           if (p.ctx_bf16) *reinterpret_cast<uint32_t*>(p.ctx_bf16 + row * p.ld_ctx_bf16 + col) = f2_to_bf16x2(v0, v1);
           if (p.ctx_f32) *reinterpret_cast<float2*>(p.ctx_f32 + row * p.ld_ctx_f32 + col) = make_float2(v0, v1);
         }
@@ -328,26 +395,18 @@ __global__ void __launch_bounds__(ATT_THREADS, (CA <= 2 && CHP <= 1) ? 3 : 1) at
 
 // ---- host side -------------------------------------------------------------------------------------------
 struct AttPlan {
-  int rows_per_stage, total_stages, nsplit, stages_per_cta;
+  int rows_per_cta, nsplit;
 };
 
 static AttPlan make_plan(int L) {
+  // about 50 regions per CTA, in multiples of 8 so that the 8 warps of a CTA get equal shares
+  int target = (L + 24) / 49;
+  target = target < 1 ? 1 : (target > ATT_MAX_SPLIT ? ATT_MAX_SPLIT : target);
+  const int groups8 = (L + 7) / 8;
+  const int k = (groups8 + target - 1) / target;
   AttPlan pl;
-  int best_rs = ATT_STAGE_ROWS, best_waste = 1 << 30;
-  for (int rs = ATT_STAGE_ROWS; rs >= 6; --rs) {  // fewest idle score warps in the last stage
-    const int waste = ((L + rs - 1) / rs) * rs - L;
-    if (waste < best_waste) {
-      best_waste = waste;
-      best_rs = rs;
-    }
-  }
-  if (L < 6) best_rs = L;
-  pl.rows_per_stage = best_rs;
-  pl.total_stages = (L + best_rs - 1) / best_rs;
-  int nsplit = (pl.total_stages + 3) / 7;  // about 7 stages (~50 regions) per CTA
-  nsplit = nsplit < 1 ? 1 : (nsplit > ATT_MAX_SPLIT ? ATT_MAX_SPLIT : nsplit);
-  pl.stages_per_cta = (pl.total_stages + nsplit - 1) / nsplit;
-  pl.nsplit = (pl.total_stages + pl.stages_per_cta - 1) / pl.stages_per_cta;
+  pl.rows_per_cta = 8 * k;
+  pl.nsplit = (L + pl.rows_per_cta - 1) / pl.rows_per_cta;
   return pl;
 }
 
@@ -366,12 +425,15 @@ long long att_step_workspace_bytes(int n_img, int beams, int L, int H) {
   return counters + partial;
 }
 
-template <int NB, int CA, int CHP>
+template <int NB, int CA, int CH>
 static int launch_att(AttParams& p, int n_img, const AttPlan& pl, cudaStream_t stream) {
-  const size_t smem = static_cast<size_t>(ATT_NSTAGES) * ATT_STAGE_ROWS * (p.A + p.H) * 2;
-  auto kern = att_step_fwd_kernel<NB, CA, CHP>;
+  const size_t ring = static_cast<size_t>(ATT_WARPS) * ATT_SLOTS * (p.A + p.H) * 2;
+  const size_t merge = static_cast<size_t>(ATT_WARPS) * NB * p.H * 4;
+  const size_t smem = ring > merge ? ring : merge;
+  auto kern = att_step_fwd_kernel<NB, CA, CH>;
   if (smem > 200 * 1024) return set_error(UIC_ERR_SHAPE, "att_step_fwd: A=%d H=%d need %zu bytes of shared memory", p.A, p.H, smem);
-  if (smem > 48 * 1024) UIC_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  if (smem > 40 * 1024)  // dynamic + the kernel's static shared memory may exceed the 48 KB default
+    UIC_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   dim3 grid(n_img * pl.nsplit, (p.beams + NB - 1) / NB);
   launch_begin("att_step_fwd", stream);
   kern<<<grid, ATT_THREADS, smem, stream>>>(p);
@@ -380,12 +442,14 @@ static int launch_att(AttParams& p, int n_img, const AttPlan& pl, cudaStream_t s
   return 0;
 }
 
-template <int CA, int CHP>
-static int dispatch_nb(AttParams& p, int n_img, const AttPlan& pl, cudaStream_t stream) {
-  switch (beams_per_group(p.beams)) {
-    case 1: return launch_att<1, CA, CHP>(p, n_img, pl, stream);
-    case 2: return launch_att<2, CA, CHP>(p, n_img, pl, stream);
-    default: return launch_att<3, CA, CHP>(p, n_img, pl, stream);
+template <int CA, int CH>
+static int dispatch_nb(AttParams& p, int n_img, const AttPlan& pl, int nb_max, cudaStream_t stream) {
+  int nb = beams_per_group(p.beams);
+  nb = nb > nb_max ? nb_max : nb;
+  switch (nb) {
+    case 1: return launch_att<1, CA, CH>(p, n_img, pl, stream);
+    case 2: return launch_att<2, CA, CH>(p, n_img, pl, stream);
+    default: return launch_att<3, CA, CH>(p, n_img, pl, stream);
   }
 }
 
@@ -426,15 +490,13 @@ int att_step_fwd(const float* att_h, long long ld_att_h, const void* p_att, cons
   p.L = L;
   p.A = A;
   p.H = H;
-  p.rows_per_stage = pl.rows_per_stage;
-  p.stages_per_cta = pl.stages_per_cta;
-  p.total_stages = pl.total_stages;
+  p.rows_per_cta = pl.rows_per_cta;
   p.nsplit = pl.nsplit;
-  const int ca = (A + 255) / 256, chp = (H + 511) / 512;
-  if (ca <= 1 && chp <= 1) return dispatch_nb<1, 1>(p, n_img, pl, stream);
-  if (ca <= 2 && chp <= 1) return dispatch_nb<2, 1>(p, n_img, pl, stream);
-  if (ca <= 2 && chp <= 2) return dispatch_nb<2, 2>(p, n_img, pl, stream);
-  return dispatch_nb<4, 2>(p, n_img, pl, stream);
+  const int ca = (A + 255) / 256, ch = (H + 255) / 256;
+  if (ca <= 1 && ch <= 1) return dispatch_nb<1, 1>(p, n_img, pl, 3, stream);
+  if (ca <= 2 && ch <= 2) return dispatch_nb<2, 2>(p, n_img, pl, 3, stream);
+  if (ca <= 2 && ch <= 4) return dispatch_nb<2, 4>(p, n_img, pl, 3, stream);
+  return dispatch_nb<4, 4>(p, n_img, pl, 3, stream);
 }
 
 }  // namespace uic

@@ -207,9 +207,10 @@ __global__ void __launch_bounds__(ATTB_THREADS) att_step_bwd_kernel(const float*
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&u[k]));
-          const float t0 = tanh_approx(f.x + ah[c * 8 + 2 * k]), t1 = tanh_approx(f.y + ah[c * 8 + 2 * k + 1]);
-          acc[c * 8 + 2 * k] = fmaf(del, 1.0f - t0 * t0, acc[c * 8 + 2 * k]);
-          acc[c * 8 + 2 * k + 1] = fmaf(del, 1.0f - t1 * t1, acc[c * 8 + 2 * k + 1]);
+          // operands are E = exp(2 p)/16 and F = 16 exp(2 att_h): tanh = 1 - 2r, 1 - tanh^2 = 4 r (1 - r), r = 1/(E F + 1)
+          const float r0 = rcp_approx(fmaf(f.x, ah[c * 8 + 2 * k], 1.0f)), r1 = rcp_approx(fmaf(f.y, ah[c * 8 + 2 * k + 1], 1.0f));
+          acc[c * 8 + 2 * k] = fmaf(del, 4.0f * r0 * (1.0f - r0), acc[c * 8 + 2 * k]);
+          acc[c * 8 + 2 * k + 1] = fmaf(del, 4.0f * r1 * (1.0f - r1), acc[c * 8 + 2 * k + 1]);
         }
       }
     }
@@ -286,10 +287,10 @@ __global__ void __launch_bounds__(TILE_THREADS) att_tiles_bwd_kernel(
       const float p = __half2float(p_att[off]);
       float acc = 0.0f;
       for (int t = 0; t < T; ++t) {
-        const float th = tanh_approx(p + s_ah[t * A + a]);
+        const float r = rcp_approx(fmaf(p, s_ah[t * A + a], 1.0f));   // p = E, s_ah = F (exponential operand form)
         const float d = s_de[t * l_chunk + q];
-        acc = fmaf(d, 1.0f - th * th, acc);
-        dw = fmaf(d, th, dw);
+        acc = fmaf(d, 4.0f * r * (1.0f - r), acc);
+        dw = fmaf(d, 1.0f - 2.0f * r, dw);
       }
       dp_att[off] = __float2bfloat16_rn(acc * wa);
       dbias += acc * wa;

@@ -38,6 +38,8 @@ struct GemmEpilogue {
   int relu;
   int accumulate;
   int out_f16;  // the 16-bit output is IEEE fp16 instead of bf16
+  int exp_col0;     // columns >= exp_col0 become exp_scale * exp(2 x) when exp_scale != 0
+  float exp_scale;
 };
 
 __device__ __forceinline__ uint32_t pack16(float a, float b, int f16) {
@@ -189,6 +191,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
 #pragma unroll
         for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
       }
+      if (ep.exp_scale != 0.0f && col0 + 32 > ep.exp_col0) {  // attention operands: scale * exp(2x), see attention.cu
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (col0 + j >= ep.exp_col0) f[j] = fminf(ep.exp_scale * __expf(2.0f * f[j]), ep.out_f16 ? 65504.0f : 1.0e30f);
+      }
       if (ep.c_f32 != nullptr) {
         float* dst = ep.c_f32 + static_cast<long long>(row) * ep.ldc + col0;
         if (full && vec_f32) {
@@ -262,6 +269,7 @@ __global__ void gemm_bf16_simt_kernel(const __nv_bfloat16* __restrict__ A, long 
     if (ep.bias) acc += ep.bias[col];
     if (ep.accumulate && ep.c_f32) acc += ep.c_f32[static_cast<long long>(row) * ep.ldc + col];
     if (ep.relu) acc = fmaxf(acc, 0.0f);
+    if (ep.exp_scale != 0.0f && col >= ep.exp_col0) acc = fminf(ep.exp_scale * __expf(2.0f * acc), ep.out_f16 ? 65504.0f : 1.0e30f);
     if (ep.c_f32) ep.c_f32[static_cast<long long>(row) * ep.ldc + col] = acc;
     if (ep.c_bf16) ep.c_bf16[static_cast<long long>(row) * ep.ldcb + col] = store16(acc, ep.out_f16);
   }
@@ -313,13 +321,14 @@ static int dispatch_major(bool a_mn, bool b_mn, const CUtensorMap& ta, const CUt
 }
 
 int gemm_bf16(const void* A, long long lda, const void* B, long long ldb, float* c_f32, long long ldc, void* c_bf16,
-              long long ldcb, const float* bias, int M, int N, int K, int flags, cudaStream_t stream) {
+              long long ldcb, const float* bias, int M, int N, int K, int flags, cudaStream_t stream, int exp_col0,
+              float exp_scale) {
   if (M <= 0 || N <= 0 || K <= 0) return set_error(UIC_ERR_SHAPE, "gemm_bf16: empty problem M=%d N=%d K=%d", M, N, K);
   if (c_f32 == nullptr && c_bf16 == nullptr) return set_error(UIC_ERR_ARG, "gemm_bf16: no output buffer");
   const bool a_mn = flags & UIC_GEMM_A_MN_MAJOR;
   const bool b_mn = flags & UIC_GEMM_B_MN_MAJOR;
   GemmEpilogue ep{c_f32, ldc, static_cast<__nv_bfloat16*>(c_bf16), ldcb, bias, (flags & UIC_GEMM_RELU) ? 1 : 0,
-                  (flags & UIC_GEMM_ACCUMULATE) ? 1 : 0, (flags & UIC_GEMM_OUT_F16) ? 1 : 0};
+                  (flags & UIC_GEMM_ACCUMULATE) ? 1 : 0, (flags & UIC_GEMM_OUT_F16) ? 1 : 0, exp_col0, exp_scale};
   if (gemm_impl() == GEMM_IMPL_SIMT) {
     dim3 grid((N + 15) / 16, (M + 15) / 16), block(16, 16);
     launch_begin("gemm_bf16_simt", stream);

@@ -33,7 +33,8 @@ int get_tensor_map_bf16(CUtensorMap* out, const void* base, long long rows, long
 
 // kernels.  Each returns 0 or a negative UIC_ERR_* (after set_error).
 int gemm_bf16(const void* A, long long lda, const void* B, long long ldb, float* c_f32, long long ldc, void* c_bf16,
-              long long ldcb, const float* bias, int M, int N, int K, int flags, cudaStream_t stream);
+              long long ldcb, const float* bias, int M, int N, int K, int flags, cudaStream_t stream, int exp_col0 = 0,
+              float exp_scale = 0.0f);
 int cast_f32_bf16(const float* src, long long ld_src, void* dst, long long ld_dst, long long rows, long long cols, int relu,
                   cudaStream_t stream);
 int zero_padded_rows(void* x, const float* masks, int n_img, int L, int H, cudaStream_t stream);

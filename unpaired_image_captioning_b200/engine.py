@@ -135,8 +135,10 @@ class DecoderEngine:
         gemm(x, w.w_att_embed, w.b_att_embed, out_bf16=att, relu=True)
         if att_masks is not None:
             check(self.lib.uic_zero_padded_rows(ptr(att), ptr(att_masks), B, L, H, stream()))
-        p_att = torch.empty(B * L, A, dtype=torch.float16, device=x.device)   # fp16: added to att_h with HADD2 in the step kernel
-        gemm(att, w.w_ctx2att, w.b_ctx2att, out_bf16=p_att)
+        # p_att is stored in the exponential operand form E = exp(2 p_att)/16 (fp16): the step kernel then
+        # gets tanh(p_att + att_h) = 1 - 2/(E F + 1) from an FMA and a shared reciprocal (MUFU.TANH is quarter rate)
+        p_att = torch.empty(B * L, A, dtype=torch.float16, device=x.device)
+        gemm(att, w.w_ctx2att, w.b_ctx2att, out_bf16=p_att, exp_col0=0, exp_scale=_lib.ATT_E_SCALE)
         fc = None
         if self.kind == "topdown":
             fc = torch.empty(B, H, dtype=BF16, device=x.device)
@@ -177,7 +179,7 @@ class DecoderEngine:
 
         if self.kind == "att2in2":
             S = ws["S"]
-            gemm(X, w.w1, w.b1, out_f32=S)
+            gemm(X, w.w1, w.b1, out_f32=S, exp_col0=5 * H, exp_scale=_lib.ATT_F_SCALE)   # S[:, 5H:] = F = 16 exp(2 att_h)
             _lib.att_step(S[:, 5 * H:], S.stride(0), feats.p_att, feats.att, w.w_alpha, feats.masks, ws["ctx"], H, None, 0, alpha,
                           feats.B, beams, feats.L, A, H)
             gemm(ws["ctx"], w.w_a2c, w.b_a2c, out_f32=ws["a2c"])
@@ -192,7 +194,7 @@ class DecoderEngine:
             # the next step's h_att_prev slot
             check(lib.uic_lstm_cell_fwd(ptr(G), 4 * H, ptr(c[0]), ptr(c_out[0]), None, ptr(cols(X, sl.h_att)), ldx,
                                         ptr(cols(Xn, sl.h_att_prev)), Xn.stride(0), R, H, st))
-            gemm(cols(X, sl.h_att), w.w_h2att, w.b_h2att, out_f32=ws["att_h"])
+            gemm(cols(X, sl.h_att), w.w_h2att, w.b_h2att, out_f32=ws["att_h"], exp_col0=0, exp_scale=_lib.ATT_F_SCALE)
             ctx = cols(X, sl.ctx)
             _lib.att_step(ws["att_h"], A, feats.p_att, feats.att, w.w_alpha, feats.masks, ctx, ldx, None, 0, alpha,
                           feats.B, beams, feats.L, A, H)

@@ -51,10 +51,13 @@ class Attention(nn.Module):
         if R % n_img:
             raise ValueError(f"Attention: {R} rows do not divide over {n_img} images")
         att_b = att if att.dtype == BF16 else _lib.cast_bf16(att.reshape(-1, H).float())
-        p_b = p_att_feats.reshape(n_img, L, A).to(torch.float16).contiguous()   # operand tiles: p_att fp16, att bf16
-        att_h = torch.empty(R, A, device=h.device)
+        # operand tiles: fp16 tensors are already in the engine's exponential form E = exp(2 p_att)/16
+        # (what _prepare_feature returns); anything else is a raw ctx2att output and is converted here
+        p3 = p_att_feats.reshape(n_img, L, A)
+        p_b = (p3 if p3.dtype == torch.float16 else _lib.exp_tile(p3)).contiguous()
+        att_h = torch.empty(R, A, device=h.device)   # F = 16 exp(2 (h2att(h) + b))
         _lib.gemm(_lib.cast_bf16(h.float().contiguous()), _lib.cast_bf16(self.h2att.weight.detach()),
-                  self.h2att.bias.detach().float().contiguous(), out_f32=att_h)
+                  self.h2att.bias.detach().float().contiguous(), out_f32=att_h, exp_col0=0, exp_scale=_lib.ATT_F_SCALE)
         ctx = torch.empty(R, H, device=h.device)
         masks = None if att_masks is None else att_masks.reshape(n_img, L).float().contiguous()
         w = self.alpha_net.weight.detach().float().reshape(-1).contiguous()
@@ -157,7 +160,9 @@ class AttModel(CaptionModel):
             raise NotImplementedError("drop_prob_lm > 0 in training mode is not on the B200 hot path yet (use eval() or p=0)")
 
     def _prepare_feature(self, fc_feats, att_feats, att_masks):
-        """Returns (fc, att, p_att, masks) like the reference; att / p_att are the bf16 operand tiles."""
+        """Returns (fc, att, p_att, masks) like the reference.  att is the bf16 operand tile; p_att is the
+        fp16 tile in the engine's exponential form exp(2 * ctx2att(att)) / 16 (see engine.prepare) and is
+        accepted as such by get_logprobs_state / core / core.attention."""
         f = self.engine.prepare(fc_feats, att_feats, att_masks)
         fc = fc_feats if self.kind == "att2in2" else f.fc
         return fc, f.att, f.p_att, f.masks
@@ -209,7 +214,8 @@ class AttModel(CaptionModel):
         L = att3.size(1)
         # the reference's beam path hands in per-beam expanded copies (AttModel.py:181-184): rows == n_img
         att_b = att3 if att3.dtype == BF16 else _lib.cast_bf16(att3.reshape(-1, H).float()).view(n_img, L, H)
-        p_b = p_att.reshape(n_img, L, A).to(torch.float16)
+        p3 = p_att.reshape(n_img, L, A)
+        p_b = p3 if p3.dtype == torch.float16 else _lib.exp_tile(p3)   # fp16 = already E = exp(2 p_att)/16
         masks = None if att_masks is None else att_masks.reshape(n_img, L).float().contiguous()
         fc_b = None
         if self.kind == "topdown":
