@@ -49,6 +49,11 @@ int uic_version(void);
 int64_t uic_launch_count(void);
 /* 0 = tcgen05 tensor-core GEMM (default), 1 = CUDA-core verification GEMM (tests/debug only). */
 int uic_set_gemm_impl(int impl);
+/* Debug aid: with a non-NULL device buffer of 128 int64, CTA (0,0) of every following GEMM launch
+ * records clock64() at its pipeline events ([0] setup done, [1+kb] operands of k-block kb landed,
+ * [50+kb] TMA for kb issued, [40] last MMA issued, [41] accumulator ready, [42] epilogue done,
+ * [43]/[44] CTA exit/entry).  NULL turns it off. */
+int uic_gemm_set_trace(void* device_buffer_128_i64);
 /* Live per-kernel device timing: while enabled, every launch is bracketed by a CUDA event pair on
  * its stream (do not enable during CUDA-graph capture).  uic_profile_dump synchronises, writes one
  * "name launches total_ms" line per kernel label into `out` (host buffer) and returns the number

@@ -21,6 +21,7 @@ SIGNATURES = {
     "uic_launch_count": (_i64, []),
     "uic_set_gemm_impl": (_i, [_i]),
     "uic_check_device": (_i, []),
+    "uic_gemm_set_trace": (_i, [_p]),
     "uic_profile_enable": (_i, [_i]),
     "uic_profile_dump": (_i64, [C.c_char_p, _i64]),
     "uic_gemm_bf16": (_i, [_p, _i64, _p, _i64, _p, _i64, _p, _i64, _p, _i, _i, _i, _i, _p]),

@@ -54,6 +54,9 @@ void launch_end(cudaStream_t stream) {
   g_prof_open = -1;
 }
 
+static std::atomic<long long*> g_gemm_trace{nullptr};
+long long* gemm_trace_buffer() { return g_gemm_trace.load(std::memory_order_relaxed); }
+
 int gemm_impl() {
   int v = g_gemm_impl.load(std::memory_order_relaxed);
   if (v < 0) {
@@ -157,6 +160,11 @@ int uic_set_gemm_impl(int impl) {
   g_gemm_impl.store(impl);
   return 0;
 }
+int uic_gemm_set_trace(void* device_buffer_128_i64) {
+  g_gemm_trace.store(static_cast<long long*>(device_buffer_128_i64));
+  return 0;
+}
+
 int uic_profile_enable(int on) {
   std::lock_guard<std::mutex> lock(g_prof_mu);
   for (auto& r : g_prof) {

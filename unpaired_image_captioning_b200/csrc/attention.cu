@@ -119,21 +119,26 @@ __global__ void __launch_bounds__(ATT_THREADS, (NB * (CA + CH) <= 12) ? 2 : 1) a
     }
   }
 
-  // per-lane constants: -2 * alpha_net weight and F = 16 exp(2 att_h) of each beam (fp32)
+  // per-lane constant: -2 * alpha_net weight.  F = 16 exp(2 att_h) of the CTA's beams lives in shared
+  // memory (NB * CA * 8 registers per lane would push the loop into local-memory spills, ncu pass 4):
+  // quad (j, c, half) is stored as [lane][4] so that a warp's LDS.128 is conflict-free.
   float w[CA * 8];
-  float F[NB][CA * 8];
+  float* s_F = reinterpret_cast<float*>(att_smem + static_cast<size_t>(ATT_WARPS) * ATT_SLOTS * slot_bytes);
 #pragma unroll
   for (int c = 0; c < CA; ++c) {
-    const int a0 = c * 256 + lane * 8;
-    load8(p.w_alpha, a0, A, &w[c * 8]);
+    load8(p.w_alpha, c * 256 + lane * 8, A, &w[c * 8]);
 #pragma unroll
     for (int k = 0; k < 8; ++k) w[c * 8 + k] *= -2.0f;
-#pragma unroll
-    for (int j = 0; j < NB; ++j) {
-      const long long row = static_cast<long long>(img) * p.beams + beam0 + (j < nb ? j : 0);
-      load8(p.att_h + row * p.ld_att_h, a0, A, &F[j][c * 8]);
-    }
   }
+  for (int jc = warp; jc < NB * CA; jc += ATT_WARPS) {
+    const int j = jc / CA, c = jc - j * CA;
+    const long long row = static_cast<long long>(img) * p.beams + beam0 + (j < nb ? j : 0);
+    float x[8];
+    load8(p.att_h + row * p.ld_att_h, c * 256 + lane * 8, A, x);
+    *reinterpret_cast<float4*>(s_F + (jc * 2 + 0) * 128 + lane * 4) = make_float4(x[0], x[1], x[2], x[3]);
+    *reinterpret_cast<float4*>(s_F + (jc * 2 + 1) * 128 + lane * 4) = make_float4(x[4], x[5], x[6], x[7]);
+  }
+  __syncthreads();
 
   float m_run[NB], s_run[NB];
   float acc[NB][CH * 8];
@@ -184,11 +189,19 @@ __global__ void __launch_bounds__(ATT_THREADS, (NB * (CA + CH) <= 12) ? 2 : 1) a
     float e[NB];
 #pragma unroll
     for (int j = 0; j < NB; ++j) {
+      float Fj[CA * 8];
+#pragma unroll
+      for (int c = 0; c < CA; ++c) {
+        const float4 lo = *reinterpret_cast<const float4*>(s_F + ((j * CA + c) * 2 + 0) * 128 + lane * 4);
+        const float4 hi = *reinterpret_cast<const float4*>(s_F + ((j * CA + c) * 2 + 1) * 128 + lane * 4);
+        Fj[c * 8 + 0] = lo.x; Fj[c * 8 + 1] = lo.y; Fj[c * 8 + 2] = lo.z; Fj[c * 8 + 3] = lo.w;
+        Fj[c * 8 + 4] = hi.x; Fj[c * 8 + 5] = hi.y; Fj[c * 8 + 6] = hi.z; Fj[c * 8 + 7] = hi.w;
+      }
       float p0 = 0.0f, p1 = 0.0f;
 #pragma unroll
       for (int k = 0; k < CA * 8; k += 2) {
-        const float d1 = fmaf(Ef[k], F[j][k], 1.0f);
-        const float d2 = fmaf(Ef[k + 1], F[j][k + 1], 1.0f);
+        const float d1 = fmaf(Ef[k], Fj[k], 1.0f);
+        const float d2 = fmaf(Ef[k + 1], Fj[k + 1], 1.0f);
         const float r = rcp_approx(d1 * d2);
         const float num = fmaf(w[k + 1], d1, w[k] * d2);
         if ((k & 2) == 0) p0 = fmaf(r, num, p0); else p1 = fmaf(r, num, p1);
@@ -398,9 +411,13 @@ struct AttPlan {
   int rows_per_cta, nsplit;
 };
 
-static AttPlan make_plan(int L) {
-  // about 50 regions per CTA, in multiples of 8 so that the 8 warps of a CTA get equal shares
-  int target = (L + 24) / 49;
+static AttPlan make_plan(int L, int n_img) {
+  // Splitting an image's regions over several CTAs costs a fixed prologue/epilogue per CTA (about half
+  // of the kernel at 7 regions per warp, ncu pass 4), so it is only used to create parallelism for small
+  // batches: aim for ~2 CTAs per SM, in multiples of 8 regions so the 8 warps of a CTA get equal shares.
+  int target = (2 * 148 + n_img - 1) / n_img;
+  const int by_len = (L + 24) / 49;
+  target = target > by_len ? by_len : target;
   target = target < 1 ? 1 : (target > ATT_MAX_SPLIT ? ATT_MAX_SPLIT : target);
   const int groups8 = (L + 7) / 8;
   const int k = (groups8 + target - 1) / target;
@@ -417,7 +434,7 @@ static int beams_per_group(int beams) {
 }
 
 long long att_step_workspace_bytes(int n_img, int beams, int L, int H) {
-  const AttPlan pl = make_plan(L);
+  const AttPlan pl = make_plan(L, n_img);
   const int nb = beams_per_group(beams);
   const int groups = (beams + nb - 1) / nb;
   const long long counters = ((static_cast<long long>(n_img) * groups * 4 + 255) / 256) * 256;
@@ -427,7 +444,7 @@ long long att_step_workspace_bytes(int n_img, int beams, int L, int H) {
 
 template <int NB, int CA, int CH>
 static int launch_att(AttParams& p, int n_img, const AttPlan& pl, cudaStream_t stream) {
-  const size_t ring = static_cast<size_t>(ATT_WARPS) * ATT_SLOTS * (p.A + p.H) * 2;
+  const size_t ring = static_cast<size_t>(ATT_WARPS) * ATT_SLOTS * (p.A + p.H) * 2 + static_cast<size_t>(NB) * CA * 256 * 4;
   const size_t merge = static_cast<size_t>(ATT_WARPS) * NB * p.H * 4;
   const size_t smem = ring > merge ? ring : merge;
   auto kern = att_step_fwd_kernel<NB, CA, CH>;
@@ -464,7 +481,7 @@ int att_step_fwd(const float* att_h, long long ld_att_h, const void* p_att, cons
   if ((ctx_bf16 && (ld_ctx_bf16 % 2 || (reinterpret_cast<uintptr_t>(ctx_bf16) & 3))) ||
       (ctx_f32 && (ld_ctx_f32 % 2 || (reinterpret_cast<uintptr_t>(ctx_f32) & 7))))
     return set_error(UIC_ERR_ALIGN, "att_step_fwd: ctx outputs need even pitches and 4/8-byte alignment");
-  const AttPlan pl = make_plan(L);
+  const AttPlan pl = make_plan(L, n_img);
   const long long need = att_step_workspace_bytes(n_img, beams, L, H);
   if (workspace == nullptr || workspace_bytes < need || (reinterpret_cast<uintptr_t>(workspace) & 15))
     return set_error(UIC_ERR_ARG, "att_step_fwd: workspace of %lld bytes (16-byte aligned, zeroed once) required, got %lld", need,

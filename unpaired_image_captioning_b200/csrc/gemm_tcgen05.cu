@@ -10,13 +10,22 @@
 //   backward: dgrad (B operand MN-major = the untransposed weight) and wgrad (both operands
 //             MN-major = the untransposed activations), so no transposed copies are ever made.
 //
-// Tile: BLOCK_M = 128 (one tcgen05.mma M=128, cta_group::1), BLOCK_N in {64,128}, BLOCK_K = 64
-// (= one 128-byte swizzle row of bf16).  8 warps: warp 0 TMA producer, warp 1 MMA issuer (one
-// elected thread), warp 2 TMEM allocator, warps 4-7 epilogue (TMEM -> registers -> global).
+// Structure (second iteration; the first one's pipeline trace showed 3 stages leaving the k-loop
+// TMA-latency bound at ~560 cycles per k-block and a row-per-thread epilogue taking 3x the k-loop):
+//   * persistent: grid = min(#tiles, #SMs); every CTA walks tiles t = blockIdx.x, +gridDim.x, ...
+//     (m fastest, so concurrently running CTAs share the weight tile in L2);
+//   * tile 128 x BN (BN in {64,128}), BLOCK_K = 64 (one 128-byte swizzle row), 6-8 stage TMA ring;
+//   * warp 0 = TMA producer, warp 1 = MMA issuer (one elected thread, tcgen05.mma cta_group::1, M = 128),
+//     warp 2 = TMEM allocator, warps 4-7 = epilogue;
+//   * two TMEM accumulator buffers: the epilogue of tile i overlaps the k-loop of tile i+1;
+//   * epilogue: tcgen05.ld (row per lane) -> per-warp shared-memory transpose -> 16-byte stores that
+//     cover 4 rows x 128 contiguous bytes per warp instruction; the bias is loaded as one float4 per lane.
+#include <cstdlib>
 #include <map>
 #include <mutex>
 #include <string>
 #include <tuple>
+#include <type_traits>
 
 #include <cuda_fp16.h>
 
@@ -27,7 +36,9 @@ namespace uic {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int GEMM_THREADS = 256;
+constexpr int GEMM_THREADS = 384;  // 4 control warps + 8 epilogue warps
+constexpr int EPI_WARPS = 8;
+constexpr int EPI_PITCH = 36;  // floats per staged row: 32 + 4 keeps every 16-byte access conflict-free
 
 struct GemmEpilogue {
   float* c_f32;
@@ -37,10 +48,17 @@ struct GemmEpilogue {
   const float* bias;
   int relu;
   int accumulate;
-  int out_f16;  // the 16-bit output is IEEE fp16 instead of bf16
-  int exp_col0;     // columns >= exp_col0 become exp_scale * exp(2 x) when exp_scale != 0
+  int out_f16;   // the 16-bit output is IEEE fp16 instead of bf16
+  int exp_col0;  // columns >= exp_col0 become exp_scale * exp(2 x) when exp_scale != 0
   float exp_scale;
+  long long* trace;  // optional device buffer: CTA 0 records clock64() at pipeline events of its first tile
+  int debug;         // UIC_GEMM_DEBUG bits (experiments only): 1 = no global stores, 2 = no TMEM load, 4 = no smem transpose
 };
+
+#define UIC_TRACE(slot)                                                              \
+  do {                                                                               \
+    if (ep.trace != nullptr && blockIdx.x == 0 && it == 0) ep.trace[slot] = clock64(); \
+  } while (0)
 
 __device__ __forceinline__ uint32_t pack16(float a, float b, int f16) {
   if (f16) {
@@ -56,18 +74,25 @@ __device__ __forceinline__ __nv_bfloat16 store16(float a, int f16) {
   }
   return __float2bfloat16_rn(a);
 }
+__device__ __forceinline__ float epi_act(float v, int col, const GemmEpilogue& ep) {
+  if (ep.relu) v = fmaxf(v, 0.0f);
+  if (ep.exp_scale != 0.0f && col >= ep.exp_col0) v = fminf(ep.exp_scale * __expf(2.0f * v), ep.out_f16 ? 65504.0f : 1.0e30f);
+  return v;
+}
 
 template <int BN, int STAGES>
 struct GemmSmem {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int EPI_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int EPI_BYTES = EPI_WARPS * 32 * EPI_PITCH * 4;  // one 32 x 32 fp32 staging tile per epilogue warp
+  static constexpr int BAR_OFFSET = EPI_OFFSET + EPI_BYTES;
   static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;  // barriers + alignment slack
 };
 
 template <int BN, int STAGES, bool A_MN, bool B_MN>
-__global__ void __launch_bounds__(GEMM_THREADS)
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                          GemmEpilogue ep, int M, int N, int K) {
   using L = GemmSmem<BN, STAGES>;
@@ -75,14 +100,16 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
   uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tmem_full_bar = empty_bar + STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
+  uint64_t* tmem_full_bar = empty_bar + STAGES;   // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;   // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int n0 = blockIdx.x * BN;
-  const int m0 = blockIdx.y * BM;
   const int num_kb = (K + BK - 1) / BK;
+  const int tiles_m = (M + BM - 1) / BM;
+  const int tiles_n = (N + BN - 1) / BN;
+  const int num_tiles = tiles_m * tiles_n;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
@@ -93,11 +120,14 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    mbar_init(tmem_full_bar, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tmem_full_bar[b], 1);
+      mbar_init(&tmem_empty_bar[b], EPI_WARPS);  // one arrival per epilogue warp
+    }
     fence_barrier_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_slot, BN);
+    tmem_alloc(tmem_slot, 2 * BN);
     tmem_relinquish();
   }
   tcgen05_fence_before();
@@ -108,24 +138,29 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
-        mbar_wait(&empty_bar[s], ph ^ 1);
-        mbar_arrive_expect_tx(&full_bar[s], L::STAGE_BYTES);
-        uint8_t* sa = smem + s * L::STAGE_BYTES;
-        uint8_t* sb = sa + L::A_BYTES;
-        if (!A_MN) {
-          tma_load_2d(sa, &tmap_a, &full_bar[s], kb * BK, m0);
-        } else {  // A stored [K, M]: two boxes of 64 m-columns x 64 k-rows
+      int g = 0;  // global k-block counter: ring position carries over from tile to tile
+      for (int tile = blockIdx.x, it = 0; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int m0 = (tile % tiles_m) * BM, n0 = (tile / tiles_m) * BN;
+        for (int kb = 0; kb < num_kb; ++kb, ++g) {
+          const int s = g % STAGES;
+          const uint32_t ph = (g / STAGES) & 1;
+          mbar_wait(&empty_bar[s], ph ^ 1);
+          if (kb < 32) UIC_TRACE(50 + kb);
+          mbar_arrive_expect_tx(&full_bar[s], L::STAGE_BYTES);
+          uint8_t* sa = smem + s * L::STAGE_BYTES;
+          uint8_t* sb = sa + L::A_BYTES;
+          if (!A_MN) {
+            tma_load_2d(sa, &tmap_a, &full_bar[s], kb * BK, m0);
+          } else {  // A stored [K, M]: two boxes of 64 m-columns x 64 k-rows
 #pragma unroll
-          for (int i = 0; i < BM / 64; ++i) tma_load_2d(sa + i * (BK * 128), &tmap_a, &full_bar[s], m0 + 64 * i, kb * BK);
-        }
-        if (!B_MN) {
-          tma_load_2d(sb, &tmap_b, &full_bar[s], kb * BK, n0);
-        } else {
+            for (int i = 0; i < BM / 64; ++i) tma_load_2d(sa + i * (BK * 128), &tmap_a, &full_bar[s], m0 + 64 * i, kb * BK);
+          }
+          if (!B_MN) {
+            tma_load_2d(sb, &tmap_b, &full_bar[s], kb * BK, n0);
+          } else {
 #pragma unroll
-          for (int i = 0; i < BN / 64; ++i) tma_load_2d(sb + i * (BK * 128), &tmap_b, &full_bar[s], n0 + 64 * i, kb * BK);
+            for (int i = 0; i < BN / 64; ++i) tma_load_2d(sb + i * (BK * 128), &tmap_b, &full_bar[s], n0 + 64 * i, kb * BK);
+          }
         }
       }
     }
@@ -133,103 +168,174 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     // ===== MMA issuer (single thread) =====
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_bf16(BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int s = kb % STAGES;
-        const uint32_t ph = (kb / STAGES) & 1;
-        mbar_wait(&full_bar[s], ph);
+      int g = 0;
+      for (int tile = blockIdx.x, it = 0; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        mbar_wait(&tmem_empty_bar[acc], ((it >> 1) & 1) ^ 1);  // epilogue has drained this accumulator
         tcgen05_fence_after();
-        const uint32_t a_base = smem_u32(smem + s * L::STAGE_BYTES);
-        const uint32_t b_base = a_base + L::A_BYTES;
+        const uint32_t tmem_d = tmem_base + acc * BN;
+        UIC_TRACE(0);
+        for (int kb = 0; kb < num_kb; ++kb, ++g) {
+          const int s = g % STAGES;
+          const uint32_t ph = (g / STAGES) & 1;
+          mbar_wait(&full_bar[s], ph);
+          if (kb < 32) UIC_TRACE(1 + kb);
+          tcgen05_fence_after();
+          const uint32_t a_base = smem_u32(smem + s * L::STAGE_BYTES);
+          const uint32_t b_base = a_base + L::A_BYTES;
 #pragma unroll
-        for (int k = 0; k < BK / 16; ++k) {
-          // K-major : 8-row groups 1024 B apart (SBO); a 16-element K step is 32 B inside the swizzle row.
-          // MN-major: 64-element MN chunks BK*128 B apart (LBO), 8-k-row groups 1024 B apart (SBO);
-          //           a 16-row K step is 2048 B.
-          const uint64_t da = A_MN ? make_smem_desc_sw128(a_base + k * 2048, BK * 128, 1024)
-                                   : make_smem_desc_sw128(a_base + k * 32, 16, 1024);
-          const uint64_t db = B_MN ? make_smem_desc_sw128(b_base + k * 2048, BK * 128, 1024)
-                                   : make_smem_desc_sw128(b_base + k * 32, 16, 1024);
-          umma_bf16_ss(tmem_base, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+          for (int k = 0; k < BK / 16; ++k) {
+            // K-major : 8-row groups 1024 B apart (SBO); a 16-element K step is 32 B inside the swizzle row.
+            // MN-major: 64-element MN chunks BK*128 B apart (LBO), 8-k-row groups 1024 B apart (SBO);
+            //           a 16-row K step is 2048 B.
+            const uint64_t da = A_MN ? make_smem_desc_sw128(a_base + k * 2048, BK * 128, 1024)
+                                     : make_smem_desc_sw128(a_base + k * 32, 16, 1024);
+            const uint64_t db = B_MN ? make_smem_desc_sw128(b_base + k * 2048, BK * 128, 1024)
+                                     : make_smem_desc_sw128(b_base + k * 32, 16, 1024);
+            umma_bf16_ss(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[s]);  // frees the smem slot once these MMAs have read it
         }
-        umma_commit(&empty_bar[s]);  // frees the smem slot once these MMAs have read it
+        umma_commit(&tmem_full_bar[acc]);  // accumulator complete
+        UIC_TRACE(40);
       }
-      umma_commit(tmem_full_bar);  // accumulator complete
     }
   } else if (warp >= 4) {
-    // ===== epilogue: TMEM -> registers -> global =====
-    const int ew = warp - 4;  // == warp % 4: the TMEM lane quarter this warp may access
-    mbar_wait(tmem_full_bar, 0);
-    tcgen05_fence_after();
-    const int row = m0 + ew * 32 + lane;
-    const bool row_ok = row < M;
+    // ===== epilogue: TMEM -> registers -> smem transpose -> coalesced global stores =====
+    const int ew = warp & 3;            // the TMEM lane quarter this warp may access (hardware rule: warp % 4)
+    const int ehalf = (warp - 4) >> 2;  // warps 4-7 take the first half of the tile's column chunks, warps 8-11 the second
+    constexpr int CHUNKS = BN / 32 / 2;
+    const uint32_t stage_s = smem_u32(smem + L::EPI_OFFSET) + (warp - 4) * 32 * EPI_PITCH * 4;  // this warp's 32 x 32 fp32 staging tile
+    const int q = lane & 7, rsub = lane >> 3;  // this lane stores columns 4q..4q+3 of rows rsub, rsub+4, ...
     const bool vec_f32 = ep.c_f32 != nullptr && (ep.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(ep.c_f32) & 15) == 0);
-    const bool vec_bf16 = ep.c_bf16 != nullptr && (ep.ldcb % 8 == 0) && ((reinterpret_cast<uintptr_t>(ep.c_bf16) & 15) == 0);
-#pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
-      uint32_t v[32];
-      __syncwarp();  // tcgen05.ld is .sync.aligned: reconverge after the per-row predicated stores
-      tmem_ld_32x32(tmem_base + (static_cast<uint32_t>(ew * 32) << 16) + c * 32, v);
-      tmem_ld_wait();
-      const int col0 = n0 + c * 32;
-      if (row_ok && col0 < N) {
-      float f[32];
+    const bool vec_16 = ep.c_bf16 != nullptr && (ep.ldcb % 4 == 0) && ((reinterpret_cast<uintptr_t>(ep.c_bf16) & 7) == 0);
+    const bool vec_bias = ep.bias != nullptr && ((reinterpret_cast<uintptr_t>(ep.bias) & 15) == 0);
+    for (int tile = blockIdx.x, it = 0; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int m0 = (tile % tiles_m) * BM, n0 = (tile / tiles_m) * BN;
+      const int acc = it & 1;
+      // bias of this lane's four columns in each of the warp's chunks: loaded while the k-loop still runs
+      float4 bias4[CHUNKS];
 #pragma unroll
-      for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-      const bool full = col0 + 32 <= N;
-      if (ep.bias != nullptr) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (full || col0 + j < N) f[j] += __ldg(ep.bias + col0 + j);
-      }
-      if (ep.accumulate && ep.c_f32 != nullptr) {
-        const float* src = ep.c_f32 + static_cast<long long>(row) * ep.ldc + col0;
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (full || col0 + j < N) f[j] += src[j];
-      }
-      if (ep.relu) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.0f);
-      }
-      if (ep.exp_scale != 0.0f && col0 + 32 > ep.exp_col0) {  // attention operands: scale * exp(2x), see attention.cu
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (col0 + j >= ep.exp_col0) f[j] = fminf(ep.exp_scale * __expf(2.0f * f[j]), ep.out_f16 ? 65504.0f : 1.0e30f);
-      }
-      if (ep.c_f32 != nullptr) {
-        float* dst = ep.c_f32 + static_cast<long long>(row) * ep.ldc + col0;
-        if (full && vec_f32) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-        } else {
-          for (int j = 0; j < 32; ++j)
-            if (col0 + j < N) dst[j] = f[j];
-        }
-      }
-      if (ep.c_bf16 != nullptr) {
-        __nv_bfloat16* dst = ep.c_bf16 + static_cast<long long>(row) * ep.ldcb + col0;
-        if (full && vec_bf16) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 8) {
-            uint4 q;
-            q.x = pack16(f[j], f[j + 1], ep.out_f16);
-            q.y = pack16(f[j + 2], f[j + 3], ep.out_f16);
-            q.z = pack16(f[j + 4], f[j + 5], ep.out_f16);
-            q.w = pack16(f[j + 6], f[j + 7], ep.out_f16);
-            *reinterpret_cast<uint4*>(dst + j) = q;
+      for (int cc = 0; cc < CHUNKS; ++cc) {
+        bias4[cc] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        const int cq = n0 + (ehalf * CHUNKS + cc) * 32 + 4 * q;
+        if (ep.bias != nullptr) {
+          if (vec_bias && cq + 4 <= N) {
+            bias4[cc] = __ldg(reinterpret_cast<const float4*>(ep.bias + cq));
+          } else {
+            if (cq < N) bias4[cc].x = __ldg(ep.bias + cq);
+            if (cq + 1 < N) bias4[cc].y = __ldg(ep.bias + cq + 1);
+            if (cq + 2 < N) bias4[cc].z = __ldg(ep.bias + cq + 2);
+            if (cq + 3 < N) bias4[cc].w = __ldg(ep.bias + cq + 3);
           }
-        } else {
-          for (int j = 0; j < 32; ++j)
-            if (col0 + j < N) dst[j] = store16(f[j], ep.out_f16);
         }
       }
-      }  // row_ok
+      mbar_wait(&tmem_full_bar[acc], (it >> 1) & 1);
+      if (threadIdx.x == 128) UIC_TRACE(41);
+      tcgen05_fence_after();
+      const int row_base = m0 + ew * 32;
+#pragma unroll
+      for (int cc = 0; cc < CHUNKS; ++cc) {
+        const int c = ehalf * CHUNKS + cc;
+        const int col0 = n0 + c * 32;
+        uint32_t v[32];
+        __syncwarp();
+        if (!(ep.debug & 2)) tmem_ld_32x32(tmem_base + acc * BN + (static_cast<uint32_t>(ew * 32) << 16) + c * 32, v);
+        const float4 b4 = bias4[cc];
+        const int cq = col0 + 4 * q;
+        tmem_ld_wait();
+        if (col0 >= N || row_base >= M) continue;  // warp-uniform
+        if (ep.debug & 4) continue;
+        // lane = row: stage the 32 accumulators of this row (explicit shared-space stores: the staging
+        // pointer is derived through an integer alignment cast, so generic ST/LD would be emitted otherwise)
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(stage_s + (lane * EPI_PITCH + j) * 4), "r"(v[j]), "r"(v[j + 1]),
+                       "r"(v[j + 2]), "r"(v[j + 3])
+                       : "memory");
+        __syncwarp();
+        // The activation mode is uniform per 32-column chunk: decide it ONCE and run a specialised store
+        // loop (the first version evaluated the epilogue flags per element: ~40 instructions per value,
+        // which made the epilogue 3x longer than the k-loop).
+        const bool chunk_vec = (col0 + 32 <= N);
+        const bool exp_all = ep.exp_scale != 0.0f && col0 >= ep.exp_col0;
+        const bool exp_mixed = ep.exp_scale != 0.0f && !exp_all && col0 + 32 > ep.exp_col0;
+        auto store_rows = [&](auto mode_c) {
+          constexpr int MODE = decltype(mode_c)::value;  // 0 plain, 1 relu, 2 exp on the whole chunk, 3 generic
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int r = i * 4 + rsub;
+            const int row = row_base + r;
+            float4 f;
+            asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(f.x), "=f"(f.y), "=f"(f.z), "=f"(f.w) : "r"(stage_s + (r * EPI_PITCH + 4 * q) * 4));
+            if (row >= M) continue;
+            f.x += b4.x; f.y += b4.y; f.z += b4.z; f.w += b4.w;
+            if (MODE != 3) {
+              if (ep.c_f32 != nullptr) {
+                float4* dst = reinterpret_cast<float4*>(ep.c_f32 + static_cast<long long>(row) * ep.ldc + cq);
+                if (ep.accumulate) {
+                  const float4 o = *dst;
+                  f.x += o.x; f.y += o.y; f.z += o.z; f.w += o.w;
+                }
+                if (MODE == 1) { f.x = fmaxf(f.x, 0.0f); f.y = fmaxf(f.y, 0.0f); f.z = fmaxf(f.z, 0.0f); f.w = fmaxf(f.w, 0.0f); }
+                if (MODE == 2) {
+                  const float cap = ep.out_f16 ? 65504.0f : 1.0e30f;
+                  f.x = fminf(ep.exp_scale * __expf(2.0f * f.x), cap); f.y = fminf(ep.exp_scale * __expf(2.0f * f.y), cap);
+                  f.z = fminf(ep.exp_scale * __expf(2.0f * f.z), cap); f.w = fminf(ep.exp_scale * __expf(2.0f * f.w), cap);
+                }
+                *dst = f;
+              } else {
+                if (MODE == 1) { f.x = fmaxf(f.x, 0.0f); f.y = fmaxf(f.y, 0.0f); f.z = fmaxf(f.z, 0.0f); f.w = fmaxf(f.w, 0.0f); }
+                if (MODE == 2) {
+                  const float cap = ep.out_f16 ? 65504.0f : 1.0e30f;
+                  f.x = fminf(ep.exp_scale * __expf(2.0f * f.x), cap); f.y = fminf(ep.exp_scale * __expf(2.0f * f.y), cap);
+                  f.z = fminf(ep.exp_scale * __expf(2.0f * f.z), cap); f.w = fminf(ep.exp_scale * __expf(2.0f * f.w), cap);
+                }
+              }
+              if (ep.c_bf16 != nullptr)
+                *reinterpret_cast<uint2*>(ep.c_bf16 + static_cast<long long>(row) * ep.ldcb + cq) =
+                    make_uint2(pack16(f.x, f.y, ep.out_f16), pack16(f.z, f.w, ep.out_f16));
+            } else {  // tails, unaligned outputs, chunk straddling exp_col0: element-wise with all the flags
+              float e4[4] = {f.x, f.y, f.z, f.w};
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                if (cq + k >= N) continue;
+                if (ep.c_f32 != nullptr) {
+                  float* dst = ep.c_f32 + static_cast<long long>(row) * ep.ldc + cq + k;
+                  if (ep.accumulate) e4[k] += *dst;
+                  e4[k] = epi_act(e4[k], cq + k, ep);
+                  *dst = e4[k];
+                } else {
+                  e4[k] = epi_act(e4[k], cq + k, ep);
+                }
+                if (ep.c_bf16 != nullptr) ep.c_bf16[static_cast<long long>(row) * ep.ldcb + cq + k] = store16(e4[k], ep.out_f16);
+              }
+            }
+          }
+        };
+        const bool fast = chunk_vec && !exp_mixed && (ep.c_f32 == nullptr || vec_f32) && (ep.c_bf16 == nullptr || vec_16) && !(ep.debug & 1);
+        if (ep.debug & 1) {
+        } else if (!fast) {
+          store_rows(std::integral_constant<int, 3>{});
+        } else if (exp_all) {
+          store_rows(std::integral_constant<int, 2>{});
+        } else if (ep.relu) {
+          store_rows(std::integral_constant<int, 1>{});
+        } else {
+          store_rows(std::integral_constant<int, 0>{});
+        }
+      }
+      // all four epilogue warps have read this accumulator: hand it back to the MMA issuer
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty_bar[acc]);
+      if (threadIdx.x == 128) UIC_TRACE(42);
     }
   }
 
   tcgen05_fence_before();
   __syncthreads();
-  if (warp == 2) tmem_dealloc(tmem_base, BN);
+  if (warp == 2) tmem_dealloc(tmem_base, 2 * BN);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -268,8 +374,7 @@ __global__ void gemm_bf16_simt_kernel(const __nv_bfloat16* __restrict__ A, long 
   if (row < M && col < N) {
     if (ep.bias) acc += ep.bias[col];
     if (ep.accumulate && ep.c_f32) acc += ep.c_f32[static_cast<long long>(row) * ep.ldc + col];
-    if (ep.relu) acc = fmaxf(acc, 0.0f);
-    if (ep.exp_scale != 0.0f && col >= ep.exp_col0) acc = fminf(ep.exp_scale * __expf(2.0f * acc), ep.out_f16 ? 65504.0f : 1.0e30f);
+    acc = epi_act(acc, col, ep);
     if (ep.c_f32) ep.c_f32[static_cast<long long>(row) * ep.ldc + col] = acc;
     if (ep.c_bf16) ep.c_bf16[static_cast<long long>(row) * ep.ldcb + col] = store16(acc, ep.out_f16);
   }
@@ -293,6 +398,25 @@ static const char* gemm_label(int M, int N, int K) {
   return it->second.c_str();
 }
 
+static int gemm_debug_flags() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("UIC_GEMM_DEBUG");
+    v = e ? atoi(e) : 0;
+  }
+  return v;
+}
+
+static int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      n = 148;
+  }
+  return n;
+}
+
 template <int BN, int STAGES, bool A_MN, bool B_MN>
 static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const GemmEpilogue& ep, int M, int N, int K,
                      cudaStream_t stream) {
@@ -303,7 +427,8 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const GemmEpi
     UIC_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
-  dim3 grid((N + BN - 1) / BN, (M + BM - 1) / BM);
+  const long long tiles = static_cast<long long>((M + BM - 1) / BM) * ((N + BN - 1) / BN);
+  const int grid = static_cast<int>(tiles < sm_count() ? tiles : sm_count());
   launch_begin(gemm_label(M, N, K), stream);
   kern<<<grid, GEMM_THREADS, smem, stream>>>(ta, tb, ep, M, N, K);
   UIC_CUDA_OK(cudaGetLastError());
@@ -328,7 +453,7 @@ int gemm_bf16(const void* A, long long lda, const void* B, long long ldb, float*
   const bool a_mn = flags & UIC_GEMM_A_MN_MAJOR;
   const bool b_mn = flags & UIC_GEMM_B_MN_MAJOR;
   GemmEpilogue ep{c_f32, ldc, static_cast<__nv_bfloat16*>(c_bf16), ldcb, bias, (flags & UIC_GEMM_RELU) ? 1 : 0,
-                  (flags & UIC_GEMM_ACCUMULATE) ? 1 : 0, (flags & UIC_GEMM_OUT_F16) ? 1 : 0, exp_col0, exp_scale};
+                  (flags & UIC_GEMM_ACCUMULATE) ? 1 : 0, (flags & UIC_GEMM_OUT_F16) ? 1 : 0, exp_col0, exp_scale, gemm_trace_buffer(), gemm_debug_flags()};
   if (gemm_impl() == GEMM_IMPL_SIMT) {
     dim3 grid((N + 15) / 16, (M + 15) / 16), block(16, 16);
     launch_begin("gemm_bf16_simt", stream);
@@ -353,8 +478,12 @@ int gemm_bf16(const void* A, long long lda, const void* B, long long ldb, float*
   if (rc) return rc;
   rc = b_mn ? get_tensor_map_bf16(&tb, B, K, N, ldb, 64, 64) : get_tensor_map_bf16(&tb, B, N, K, ldb, bn, 64);
   if (rc) return rc;
-  if (bn == 64) return dispatch_major<64, 4>(a_mn, b_mn, ta, tb, ep, M, N, K, stream);
-  return dispatch_major<128, 3>(a_mn, b_mn, ta, tb, ep, M, N, K, stream);
+  if (gemm_debug_flags() & 8) {  // experiment: shallow ring, most of the 228 KB stays L1
+    if (bn == 64) return dispatch_major<64, 3>(a_mn, b_mn, ta, tb, ep, M, N, K, stream);
+    return dispatch_major<128, 2>(a_mn, b_mn, ta, tb, ep, M, N, K, stream);
+  }
+  if (bn == 64) return dispatch_major<64, 7>(a_mn, b_mn, ta, tb, ep, M, N, K, stream);
+  return dispatch_major<128, 5>(a_mn, b_mn, ta, tb, ep, M, N, K, stream);
 }
 
 }  // namespace uic

@@ -18,6 +18,7 @@ int set_error(int code, const char* fmt, ...);
 void launch_begin(const char* name, cudaStream_t stream);
 void launch_end(cudaStream_t stream);
 int gemm_impl();
+long long* gemm_trace_buffer();
 
 // Cached cuTensorMapEncodeTiled for a row-major bf16 matrix [rows, cols] with pitch ld (elements),
 // box = box_rows x box_cols, 128-byte swizzle, zero fill out of bounds.

@@ -53,7 +53,24 @@ template <typename F>
 __device__ __forceinline__ void for_each_in_row(const float* row, int V, F&& f) {
   if ((reinterpret_cast<uintptr_t>(row) & 15) == 0) {
     const int v4 = V >> 2;
-    for (int i = threadIdx.x; i < v4; i += ROW_THREADS) {
+    // batches of four 16-byte loads issued back to back before any of them is consumed: the rows
+    // are L2-resident (just written by the logit GEMM), so the scan is latency- not bandwidth-bound
+    constexpr int U = 4;
+    int i = threadIdx.x;
+    for (; i + (U - 1) * ROW_THREADS < v4; i += U * ROW_THREADS) {
+      float4 q[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) q[u] = *reinterpret_cast<const float4*>(row + 4 * (i + u * ROW_THREADS));
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int b = 4 * (i + u * ROW_THREADS);
+        f(b, q[u].x);
+        f(b + 1, q[u].y);
+        f(b + 2, q[u].z);
+        f(b + 3, q[u].w);
+      }
+    }
+    for (; i < v4; i += ROW_THREADS) {
       const float4 q = *reinterpret_cast<const float4*>(row + 4 * i);
       f(4 * i, q.x);
       f(4 * i + 1, q.y);
