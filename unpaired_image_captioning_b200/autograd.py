@@ -35,14 +35,16 @@ class _Run:
 # ----------------------------------------------------------------------------------------------------
 # forward
 # ----------------------------------------------------------------------------------------------------
-def teacher_forced_run(model, fc_feats, att_feats, seq, att_masks, save=True):
+def teacher_forced_run(model, fc_feats, att_feats, seq, att_masks, save=True, all_steps=False):
     eng = model.engine
     w, lib, st = eng.w, eng.lib, stream()
     kind, H, E, A = eng.kind, w.H, w.E, w.A
     feats = eng.prepare(fc_feats, att_feats, att_masks, keep_inputs=True)
     B, L, dev = feats.B, feats.L, feats.att.device
     T_total = seq.size(1) - 1
-    T = model._active_steps(seq)
+    # The reference stops at the first all-zero token column (AttModel.py:148-151).  Those steps carry mask 0,
+    # so the fused loss (and its gradients) are identical if they are simply run: no host sync needed there.
+    T = T_total if all_steps else model._active_steps(seq)
     sl = Slots(kind, E, H)
     r = _Run()
     r.model, r.feats, r.B, r.L, r.T, r.T_total, r.sl = model, feats, B, L, T, T_total, sl
@@ -276,7 +278,7 @@ def _finish(r, grads, grad_scale, names, params):
 class _DecoderLossFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, model, fc_feats, att_feats, labels, masks, att_masks, global_mask_sum, *params):
-        r = teacher_forced_run(model, fc_feats, att_feats, labels, att_masks)
+        r = teacher_forced_run(model, fc_feats, att_feats, labels, att_masks, all_steps=True)
         T_total = r.T_total
         target = labels[:, 1:T_total + 1].contiguous().view(-1).long()
         mask = masks[:, 1:T_total + 1].contiguous().view(-1).float()

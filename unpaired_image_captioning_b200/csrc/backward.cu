@@ -387,33 +387,73 @@ int log_softmax_bwd(const float* dlp, long long ld_dlp, const float* lp, long lo
 }
 
 // ---- column sums (bias gradients): out[c] += sum_r x[r, c] ------------------------------------------------
-template <typename T>
-__global__ void col_sum_kernel(const T* __restrict__ x, long long ld, float* __restrict__ out, int rows, int cols) {
-  __shared__ float s[8][33];
-  const int c = blockIdx.x * 32 + threadIdx.x;
-  float acc = 0.0f;
-  if (c < cols)
-    for (int r = blockIdx.y * 8 + threadIdx.y; r < rows; r += gridDim.y * 8) acc += static_cast<float>(x[static_cast<long long>(r) * ld + c]);
-  s[threadIdx.y][threadIdx.x] = acc;
-  __syncthreads();
-  if (threadIdx.y == 0 && c < cols) {
-    float t = 0.0f;
+// Each lane owns VEC consecutive columns (one 16-byte load per row), a CTA covers 32*VEC columns and a slice
+// of the rows (8 warps x 4 rows in flight each); partial sums are merged through shared memory and atomics.
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256) col_sum_kernel(const T* __restrict__ x, long long ld, float* __restrict__ out, int rows,
+                                                      int cols, int vec_ok) {
+  __shared__ float s[8][32 * VEC + 1];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c0 = (blockIdx.x * 32 + lane) * VEC;
+  float acc[VEC];
 #pragma unroll
-    for (int q = 0; q < 8; ++q) t += s[q][threadIdx.x];
-    atomicAdd(out + c, t);
+  for (int k = 0; k < VEC; ++k) acc[k] = 0.0f;
+  const int rows_per_cta = (rows + gridDim.y - 1) / gridDim.y;
+  const int r_begin = blockIdx.y * rows_per_cta, r_end = min(rows, r_begin + rows_per_cta);
+  if (c0 < cols) {
+    if (vec_ok && c0 + VEC <= cols) {
+      for (int r = r_begin + warp; r < r_end; r += 8) {
+        const uint4 q = ldg_nc_v4(x + static_cast<long long>(r) * ld + c0);
+        if (sizeof(T) == 2) {
+          const uint32_t u[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float2 f = bf16x2_to_f2(u[k]);
+            acc[(2 * k) % VEC] += f.x;
+            acc[(2 * k + 1) % VEC] += f.y;
+          }
+        } else {
+          acc[0] += __uint_as_float(q.x);
+          acc[1 % VEC] += __uint_as_float(q.y);
+          acc[2 % VEC] += __uint_as_float(q.z);
+          acc[3 % VEC] += __uint_as_float(q.w);
+        }
+      }
+    } else {
+      for (int r = r_begin + warp; r < r_end; r += 8)
+#pragma unroll
+        for (int k = 0; k < VEC; ++k)
+          if (c0 + k < cols) acc[k] += static_cast<float>(x[static_cast<long long>(r) * ld + c0 + k]);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) s[warp][lane * VEC + k] = acc[k];
+  __syncthreads();
+  for (int c = threadIdx.x; c < 32 * VEC; c += 256) {
+    const int col = blockIdx.x * 32 * VEC + c;
+    if (col < cols) {
+      float t = 0.0f;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) t += s[q][c];
+      atomicAdd(out + col, t);
+    }
   }
 }
 
 int col_sum(const void* x, int is_bf16, long long ld, float* out, int rows, int cols, cudaStream_t stream) {
-  dim3 block(32, 8);
-  int gy = (rows + 255) / 256;
-  gy = gy < 1 ? 1 : (gy > 64 ? 64 : gy);
-  dim3 grid((cols + 31) / 32, gy);
+  const int vec = is_bf16 ? 8 : 4;
+  const int vec_ok = (ld % vec == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+  const int gx = (cols + 32 * vec - 1) / (32 * vec);
+  int gy = (2 * 148 + gx - 1) / gx;  // about two CTAs per SM
+  const int max_gy = (rows + 31) / 32;
+  gy = gy > max_gy ? max_gy : gy;
+  gy = gy < 1 ? 1 : gy;
+  dim3 grid(gx, gy);
   launch_begin("col_sum", stream);
   if (is_bf16)
-    col_sum_kernel<__nv_bfloat16><<<grid, block, 0, stream>>>(static_cast<const __nv_bfloat16*>(x), ld, out, rows, cols);
+    col_sum_kernel<__nv_bfloat16, 8><<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(x), ld, out, rows, cols, vec_ok);
   else
-    col_sum_kernel<float><<<grid, block, 0, stream>>>(static_cast<const float*>(x), ld, out, rows, cols);
+    col_sum_kernel<float, 4><<<grid, 256, 0, stream>>>(static_cast<const float*>(x), ld, out, rows, cols, vec_ok);
   UIC_CUDA_OK(cudaGetLastError());
   launch_end(stream);
   return 0;

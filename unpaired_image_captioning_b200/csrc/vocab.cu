@@ -1,7 +1,9 @@
 // Row kernels over the vocabulary axis: log-softmax, fused masked cross-entropy, greedy argmax
-// step and per-row top-k for beam search.  One CTA per decoder row; every kernel makes a single
-// online (max, sum-exp) pass over the row with 16-byte loads, then a block reduction with warp
-// shuffles.  The logits were just written by the logit GEMM, so these reads are L2 hits.
+// step and per-row top-k for beam search.  One CTA per decoder row.  The logits were just written
+// by the logit GEMM, so the reads are L2 hits and the kernels are latency/issue bound: each thread
+// pulls batches of 16 values (four 16-byte loads issued back to back), reduces a batch to its
+// (max, sum-exp) with branch-free code, and only enters the arg-max / top-k update when the batch
+// maximum can beat the thread's current threshold (rare after the first batches).
 #include "uic_internal.h"
 #include "uic_ptx.cuh"
 
@@ -9,18 +11,12 @@ namespace uic {
 
 constexpr int ROW_THREADS = 256;
 constexpr int ROW_WARPS = ROW_THREADS / 32;
+constexpr int ROW_U = 4;               // 16-byte loads per batch
+constexpr int ROW_BATCH = 4 * ROW_U;   // values per batch
 
 struct MaxSum {
   float m, s;
 };
-__device__ __forceinline__ void ms_push(MaxSum& a, float x) {
-  if (x > a.m) {
-    a.s = a.s * __expf(a.m - x) + 1.0f;  // exp(-inf) = 0 for the first element
-    a.m = x;
-  } else {
-    a.s += __expf(x - a.m);
-  }
-}
 __device__ __forceinline__ MaxSum ms_merge(MaxSum a, MaxSum b) {
   MaxSum r;
   r.m = fmaxf(a.m, b.m);
@@ -48,39 +44,48 @@ __device__ __forceinline__ MaxSum ms_block_reduce(MaxSum v, MaxSum* s_part) {
   return r;
 }
 
-// Visit every element of a row once; float4 loads when the row start is 16-byte aligned.
+// Calls f(x, idx) once per batch of this thread: x[16] values (-inf padding), idx[16] their column
+// indices, in increasing index order.  16-byte loads when the row start is 16-byte aligned.
 template <typename F>
-__device__ __forceinline__ void for_each_in_row(const float* row, int V, F&& f) {
-  if ((reinterpret_cast<uintptr_t>(row) & 15) == 0) {
-    const int v4 = V >> 2;
-    // batches of four 16-byte loads issued back to back before any of them is consumed: the rows
-    // are L2-resident (just written by the logit GEMM), so the scan is latency- not bandwidth-bound
-    constexpr int U = 4;
-    int i = threadIdx.x;
-    for (; i + (U - 1) * ROW_THREADS < v4; i += U * ROW_THREADS) {
-      float4 q[U];
+__device__ __forceinline__ void scan_row_batches(const float* __restrict__ row, int V, F&& f) {
+  const bool vec = (reinterpret_cast<uintptr_t>(row) & 15) == 0;
+  const int v4 = (V + 3) >> 2;  // float4 slots, the last one may be partial
+  for (int i = threadIdx.x; i < v4; i += ROW_U * ROW_THREADS) {
+    float x[ROW_BATCH];
+    int idx[ROW_BATCH];
 #pragma unroll
-      for (int u = 0; u < U; ++u) q[u] = *reinterpret_cast<const float4*>(row + 4 * (i + u * ROW_THREADS));
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const int b = 4 * (i + u * ROW_THREADS);
-        f(b, q[u].x);
-        f(b + 1, q[u].y);
-        f(b + 2, q[u].z);
-        f(b + 3, q[u].w);
+    for (int u = 0; u < ROW_U; ++u) {
+      const int slot = i + u * ROW_THREADS;
+      const int b = 4 * slot;
+      float4 q = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+      if (slot < v4) {
+        if (vec && b + 4 <= V) {
+          q = *reinterpret_cast<const float4*>(row + b);
+        } else {
+          if (b < V) q.x = row[b];
+          if (b + 1 < V) q.y = row[b + 1];
+          if (b + 2 < V) q.z = row[b + 2];
+          if (b + 3 < V) q.w = row[b + 3];
+        }
       }
+      x[4 * u] = q.x; x[4 * u + 1] = q.y; x[4 * u + 2] = q.z; x[4 * u + 3] = q.w;
+      idx[4 * u] = b; idx[4 * u + 1] = b + 1; idx[4 * u + 2] = b + 2; idx[4 * u + 3] = b + 3;
     }
-    for (; i < v4; i += ROW_THREADS) {
-      const float4 q = *reinterpret_cast<const float4*>(row + 4 * i);
-      f(4 * i, q.x);
-      f(4 * i + 1, q.y);
-      f(4 * i + 2, q.z);
-      f(4 * i + 3, q.w);
-    }
-    for (int i = (v4 << 2) + threadIdx.x; i < V; i += ROW_THREADS) f(i, row[i]);
-  } else {
-    for (int i = threadIdx.x; i < V; i += ROW_THREADS) f(i, row[i]);
+    f(x, idx);
   }
+}
+
+// (max, sum exp) of one batch, merged into the running pair; returns the batch maximum.
+__device__ __forceinline__ float ms_push_batch(MaxSum& a, const float (&x)[ROW_BATCH]) {
+  float bm = x[0];
+#pragma unroll
+  for (int k = 1; k < ROW_BATCH; ++k) bm = fmaxf(bm, x[k]);
+  if (bm == -INFINITY) return bm;
+  float bs = 0.0f;
+#pragma unroll
+  for (int k = 0; k < ROW_BATCH; ++k) bs += __expf(x[k] - bm);  // exp(-inf) = 0 for the padding
+  a = ms_merge(a, MaxSum{bm, bs});
+  return bm;
 }
 
 // ---- log_softmax (models/AttModel.py:163) ---------------------------------------------------------
@@ -90,10 +95,24 @@ __global__ void __launch_bounds__(ROW_THREADS) log_softmax_rows_kernel(const flo
   const float* row = logits + static_cast<long long>(blockIdx.x) * ld;
   float* orow = out + static_cast<long long>(blockIdx.x) * ld_out;
   MaxSum a{-INFINITY, 0.0f};
-  for_each_in_row(row, V, [&](int, float x) { ms_push(a, x); });
+  scan_row_batches(row, V, [&](const float(&x)[ROW_BATCH], const int(&)[ROW_BATCH]) { ms_push_batch(a, x); });
   const MaxSum r = ms_block_reduce(a, s_part);
   const float log_s = logf(r.s);
-  for_each_in_row(row, V, [&](int i, float x) { orow[i] = (x - r.m) - log_s; });
+  const bool vec_out = (reinterpret_cast<uintptr_t>(orow) & 15) == 0;
+  scan_row_batches(row, V, [&](const float(&x)[ROW_BATCH], const int(&idx)[ROW_BATCH]) {
+#pragma unroll
+    for (int u = 0; u < ROW_U; ++u) {
+      const int b = idx[4 * u];
+      if (vec_out && b + 4 <= V) {
+        *reinterpret_cast<float4*>(orow + b) = make_float4((x[4 * u] - r.m) - log_s, (x[4 * u + 1] - r.m) - log_s,
+                                                           (x[4 * u + 2] - r.m) - log_s, (x[4 * u + 3] - r.m) - log_s);
+      } else {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+          if (b + k < V) orow[b + k] = (x[4 * u + k] - r.m) - log_s;
+      }
+    }
+  });
 }
 
 int log_softmax_rows(const float* logits, long long ld, float* out, long long ld_out, int rows, int V, cudaStream_t stream) {
@@ -113,7 +132,7 @@ __global__ void __launch_bounds__(ROW_THREADS) lse_xent_fwd_kernel(const float* 
   const int r = blockIdx.x;
   const float* row = logits + static_cast<long long>(r) * ld;
   MaxSum a{-INFINITY, 0.0f};
-  for_each_in_row(row, V, [&](int, float x) { ms_push(a, x); });
+  scan_row_batches(row, V, [&](const float(&x)[ROW_BATCH], const int(&)[ROW_BATCH]) { ms_push_batch(a, x); });
   const MaxSum red = ms_block_reduce(a, s_part);
   if (threadIdx.x == 0) {
     const float log_s = logf(red.s);
@@ -156,12 +175,17 @@ __global__ void __launch_bounds__(ROW_THREADS) greedy_step_kernel(const float* _
   const int banned = ((flags & UIC_SAMPLE_DECODING_CONSTRAINT) && t > 0) ? static_cast<int>(seq[static_cast<long long>(r) * T + t - 1]) : -1;
   MaxSum a{-INFINITY, 0.0f};
   Best b{-INFINITY, 0x7fffffff};
-  for_each_in_row(row, V, [&](int i, float x) {
-    ms_push(a, x);
-    const float xs = (i == banned) ? -INFINITY : x;
-    if (better(xs, i, b)) {
-      b.v = xs;
-      b.i = i;
+  scan_row_batches(row, V, [&](const float(&x)[ROW_BATCH], const int(&idx)[ROW_BATCH]) {
+    const float bm = ms_push_batch(a, x);
+    if (bm > b.v || b.i == 0x7fffffff) {  // indices increase within and across batches: ">" keeps the first maximum
+#pragma unroll
+      for (int k = 0; k < ROW_BATCH; ++k) {
+        const float xs = (idx[k] == banned) ? -INFINITY : x[k];
+        if (idx[k] < V && (xs > b.v || b.i == 0x7fffffff)) {
+          b.v = xs;
+          b.i = idx[k];
+        }
+      }
     }
   });
 #pragma unroll
@@ -216,30 +240,37 @@ __global__ void __launch_bounds__(ROW_THREADS) row_topk_kernel(const float* __re
   const int banned = ((flags & UIC_SAMPLE_DECODING_CONSTRAINT) && prev_tok) ? static_cast<int>(prev_tok[r]) : -1;
 
   float val[KMAX];
-  int idx[KMAX];
+  int idx_k[KMAX];
 #pragma unroll
   for (int q = 0; q < KMAX; ++q) {
     val[q] = -INFINITY;
-    idx[q] = 0x7fffffff;
+    idx_k[q] = 0x7fffffff;
   }
   MaxSum a{-INFINITY, 0.0f};
-  for_each_in_row(row, V, [&](int i, float x) {
-    ms_push(a, x);
-    float xs = (i == V - 1) ? x - 1000.0f : x;  // UNK suppression (:133)
-    if (i == banned) xs = -INFINITY;            // decoding constraint (:130-131)
-    // indices arrive in increasing order per thread, so ">" keeps the smaller index on ties
-    if (xs > val[KMAX - 1] || (idx[KMAX - 1] == 0x7fffffff)) {
-      val[KMAX - 1] = xs;
-      idx[KMAX - 1] = i;
+  scan_row_batches(row, V, [&](const float(&x)[ROW_BATCH], const int(&idx)[ROW_BATCH]) {
+    const float bm = ms_push_batch(a, x);
+    // the edits only lower values, so a batch whose raw maximum cannot beat the current k-th value is skipped
+    if (bm > val[KMAX - 1] || idx_k[KMAX - 1] == 0x7fffffff) {
 #pragma unroll
-      for (int q = KMAX - 1; q > 0; --q) {
-        if (val[q] > val[q - 1] || idx[q - 1] == 0x7fffffff) {
-          const float tv = val[q];
-          val[q] = val[q - 1];
-          val[q - 1] = tv;
-          const int ti = idx[q];
-          idx[q] = idx[q - 1];
-          idx[q - 1] = ti;
+      for (int e = 0; e < ROW_BATCH; ++e) {
+        if (idx[e] >= V) continue;
+        float xs = (idx[e] == V - 1) ? x[e] - 1000.0f : x[e];  // UNK suppression (:133)
+        if (idx[e] == banned) xs = -INFINITY;                   // decoding constraint (:130-131)
+        // indices arrive in increasing order per thread, so ">" keeps the smaller index on ties
+        if (xs > val[KMAX - 1] || idx_k[KMAX - 1] == 0x7fffffff) {
+          val[KMAX - 1] = xs;
+          idx_k[KMAX - 1] = idx[e];
+#pragma unroll
+          for (int q = KMAX - 1; q > 0; --q) {
+            if (val[q] > val[q - 1] || idx_k[q - 1] == 0x7fffffff) {
+              const float tv = val[q];
+              val[q] = val[q - 1];
+              val[q - 1] = tv;
+              const int ti = idx_k[q];
+              idx_k[q] = idx_k[q - 1];
+              idx_k[q - 1] = ti;
+            }
+          }
         }
       }
     }
@@ -247,7 +278,7 @@ __global__ void __launch_bounds__(ROW_THREADS) row_topk_kernel(const float* __re
 #pragma unroll
   for (int q = 0; q < KMAX; ++q) {
     s_val[threadIdx.x * KMAX + q] = val[q];
-    s_idx[threadIdx.x * KMAX + q] = idx[q];
+    s_idx[threadIdx.x * KMAX + q] = idx_k[q];
   }
   const MaxSum red = ms_block_reduce(a, s_part);
   const float log_s = logf(red.s);
