@@ -147,6 +147,26 @@ int uic_greedy_step(const float* logits, int64_t ld_logits, int64_t* seq, float*
 int uic_row_topk(const float* logits, int64_t ld_logits, const int64_t* prev_tok, float* topk_val, int32_t* topk_idx,
                  int rows, int V, int k, int flags, void* stream);
 
+/* Fused vocabulary projection + statistics for sampling: logits = h W^T + b are reduced inside the GEMM
+ * epilogue and NEVER written to memory (replaces self.logit + F.log_softmax + torch.max / torch.sort of
+ * models/AttModel.py:163,229 and models/CaptionModel.py:61,128-133 for inference).  For every row and
+ * each of uic_logit_stats_parts(V) column parts it stores one entry of uic_logit_stats_entry_floats(kslots)
+ * floats (2 + 2*kslots rounded up to a multiple of 4): max, sum exp(x - max), the kslots best keys (logit,
+ * with -1000 on the UNK column V-1 when unk_suppress != 0 and -inf on the banned token) and their columns
+ * (int bits, 0x7fffffff = empty slot), padding.  `stats` is (rows, parts, entry) fp32, 16-byte aligned.
+ * banned_tok may be NULL; row r reads banned_tok[r * banned_stride].  kslots: 1, 3, 5 or 8. */
+int uic_logit_stats_parts(int V);
+int uic_logit_stats_entry_floats(int kslots);
+int uic_logit_stats(const void* h_bf16, int64_t ld_h, const void* w_logit_bf16, int64_t ld_w, const float* bias,
+                    const int64_t* banned_tok, int64_t banned_stride, float* stats, int rows, int V, int H, int kslots, int unk_suppress,
+                    void* stream);
+/* Merges the parts of uic_logit_stats: same outputs as uic_row_topk (k <= kslots). */
+int uic_beam_topk_merge(const float* stats, int parts, int kslots, float* topk_val, int32_t* topk_idx, int rows, int k,
+                        void* stream);
+/* Merges the parts of uic_logit_stats (kslots = 1): same bookkeeping as uic_greedy_step. */
+int uic_greedy_merge(const float* stats, int parts, int64_t* seq, float* seq_logprobs, uint8_t* unfinished, int64_t* next_tok,
+                     int32_t* n_unfinished, int t, int seq_length, int rows, void* stream);
+
 /* One beam-search bookkeeping step for all images at once (models/CaptionModel.py:48-97,155-172):
  * merges the beams x k candidates of each image (c-major, q-minor stable order), forks the
  * sequence tables, records finished hypotheses (token 0 or last step) into the sorted done lists,

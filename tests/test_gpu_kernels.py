@@ -266,3 +266,91 @@ def test_greedy_step_sequence_semantics():
     for t in range(3):
         torch.testing.assert_close(lp[:, t], refs[t], rtol=1e-5, atol=2e-5)
     assert float(lp[:, 3:].abs().max()) == 0.0 and int(seq[:, 3:].abs().max()) == 0
+
+
+# ---------------------------------------------------------------------------------------------------
+# fused logit statistics (logit GEMM whose epilogue keeps max / sum-exp / best keys instead of logits)
+# ---------------------------------------------------------------------------------------------------
+def _stats_inputs(R, V, H, seed):
+    h = _rand_bf16(R, H, seed=seed)
+    w = _rand_bf16(V, H, seed=seed + 1, scale=0.5)
+    bias = torch.randn(V, device=DEV) * 0.5
+    logits = h.float() @ w.float().t() + bias
+    return h, w, bias, logits
+
+
+@pytest.mark.parametrize("R,V,H,k,kslots", [(6, 52, 64, 3, 3), (300, 10000, 512, 3, 3), (129, 10000, 512, 5, 5), (50, 10000, 512, 2, 3),
+                                            (40, 9489, 512, 8, 8), (17, 300, 128, 1, 1), (768, 10000, 512, 3, 3)])
+def test_logit_stats_topk_equals_reference_order(R, V, H, k, kslots):
+    """uic_logit_stats + uic_beam_topk_merge == log_softmax, UNK - 1000, banned -inf, stable sort
+    (models/CaptionModel.py:130-140), without materialising the logits."""
+    lib = _lib.load()
+    h, w, bias, logits = _stats_inputs(R, V, H, seed=R + V)
+    bias[V - 1] += 30.0                                   # UNK would win without the -1000 edit
+    prev = torch.randint(0, V - 1, (R,), device=DEV)
+    logits = h.float() @ w.float().t() + bias
+    parts = lib.uic_logit_stats_parts(V)
+    stats = torch.empty(R, parts, lib.uic_logit_stats_entry_floats(kslots), device=DEV)
+    val, idx = torch.empty(R, k, device=DEV), torch.empty(R, k, device=DEV, dtype=torch.int32)
+    for constrained in (False, True):
+        if constrained:   # ban each row's current best token: the constraint must change the answer
+            prev = logits[:, :V - 1].argmax(1)
+        check(lib.uic_logit_stats(ptr(h), H, ptr(w), H, ptr(bias), ptr(prev) if constrained else None, 1, ptr(stats),
+                                  R, V, H, kslots, 1, stream()))
+        check(lib.uic_beam_topk_merge(ptr(stats), parts, kslots, ptr(val), ptr(idx), R, k, stream()))
+        lp = torch.log_softmax(logits, 1)
+        if constrained:
+            lp[torch.arange(R), prev] = float("-inf")
+        lp[:, V - 1] -= 1000.0
+        ref_val, ref_idx = torch.sort(lp, dim=1, descending=True, stable=True)
+        torch.testing.assert_close(val, ref_val[:, :k], rtol=1e-4, atol=2e-4)
+        gap = (ref_val[:, :k] - ref_val[:, 1:k + 1]).abs()           # an order flip needs a near-tie
+        prev_gap = torch.cat([torch.full((R, 1), 1.0, device=DEV), gap[:, :-1]], 1)
+        clear = (gap > 1e-3) & (prev_gap > 1e-3)
+        assert bool(clear.float().mean() > 0.9)
+        assert torch.equal(idx.long()[clear], ref_idx[:, :k][clear])
+        assert int((idx == V - 1).sum()) == 0
+
+
+def test_logit_stats_without_unk_suppression_keeps_unk():
+    lib = _lib.load()
+    R, V, H = 33, 1000, 128
+    h, w, bias, _ = _stats_inputs(R, V, H, seed=5)
+    bias[V - 1] += 50.0
+    logits = h.float() @ w.float().t() + bias
+    parts = lib.uic_logit_stats_parts(V)
+    stats = torch.empty(R, parts, 4, device=DEV)
+    val, idx = torch.empty(R, 1, device=DEV), torch.empty(R, 1, device=DEV, dtype=torch.int32)
+    check(lib.uic_logit_stats(ptr(h), H, ptr(w), H, ptr(bias), None, 0, ptr(stats), R, V, H, 1, 0, stream()))
+    check(lib.uic_beam_topk_merge(ptr(stats), parts, 1, ptr(val), ptr(idx), R, 1, stream()))
+    assert bool((idx == V - 1).all())
+    torch.testing.assert_close(val[:, 0], torch.log_softmax(logits, 1)[:, V - 1], rtol=1e-4, atol=2e-4)
+
+
+def test_greedy_merge_equals_greedy_step():
+    """The fused greedy path writes the same tokens / log-probs / counters as logits + uic_greedy_step."""
+    lib = _lib.load()
+    R, V, H, T = 70, 10000, 512, 4
+    parts = lib.uic_logit_stats_parts(V)
+    stats = torch.empty(R, parts, 4, device=DEV)
+
+    def state():
+        return (torch.zeros(R, T, dtype=torch.int64, device=DEV), torch.zeros(R, T, device=DEV),
+                torch.zeros(R, dtype=torch.uint8, device=DEV), torch.zeros(R, dtype=torch.int64, device=DEV),
+                torch.zeros(T, dtype=torch.int32, device=DEV))
+
+    a, b = state(), state()
+    logits = torch.empty(R, V, device=DEV)
+    for t in range(3):
+        h, w = _rand_bf16(R, H, seed=10 + t), _rand_bf16(V, H, seed=20 + t, scale=0.05)
+        bias = torch.randn(V, device=DEV) * 0.1
+        bias[0] += 4.0                                     # some rows finish (token 0) at every step
+        _lib.gemm(h, w, bias=bias, out_f32=logits)
+        flags = _lib.SAMPLE_DECODING_CONSTRAINT if t > 0 else 0
+        check(lib.uic_greedy_step(ptr(logits), V, ptr(a[0]), ptr(a[1]), ptr(a[2]), ptr(a[3]), ptr(a[4]), t, T, R, V, flags, stream()))
+        banned = b[0][:, t - 1:] if t > 0 else None
+        check(lib.uic_logit_stats(ptr(h), H, ptr(w), H, ptr(bias), ptr(banned), T, ptr(stats), R, V, H, 1, 0, stream()))
+        check(lib.uic_greedy_merge(ptr(stats), parts, ptr(b[0]), ptr(b[1]), ptr(b[2]), ptr(b[3]), ptr(b[4]), t, T, R, stream()))
+    assert torch.equal(a[0], b[0]) and torch.equal(a[2], b[2]) and torch.equal(a[3], b[3]) and torch.equal(a[4], b[4])
+    assert 0 < int(a[4][0]) < R
+    torch.testing.assert_close(a[1], b[1], rtol=1e-4, atol=2e-4)

@@ -226,6 +226,34 @@ int uic_gemm_bf16_ex(const void* A, int64_t lda, const void* B, int64_t ldb, flo
   return gemm_bf16(A, lda, B, ldb, c_f32, ldc, c_16, ldc16, bias, M, N, K, flags, ST(stream), exp_col0, exp_scale);
 }
 
+int uic_logit_stats_parts(int V) { return V > 0 ? logit_stats_parts(V) : 0; }
+int uic_logit_stats_entry_floats(int kslots) { return kslots > 0 ? logit_stats_entry_floats(kslots) : 0; }
+
+int uic_logit_stats(const void* h_bf16, int64_t ld_h, const void* w_logit_bf16, int64_t ld_w, const float* bias,
+                    const int64_t* banned_tok, int64_t banned_stride, float* stats, int rows, int V, int H, int kslots, int unk_suppress,
+                    void* stream) {
+  REQUIRE(h_bf16 && w_logit_bf16 && stats, UIC_ERR_ARG, "uic_logit_stats: null pointer");
+  if (rows == 0) return 0;
+  return logit_stats(h_bf16, ld_h, w_logit_bf16, ld_w, bias, reinterpret_cast<const long long*>(banned_tok), banned_stride, stats,
+                     rows, V, H, kslots, unk_suppress, ST(stream));
+}
+
+int uic_beam_topk_merge(const float* stats, int parts, int kslots, float* topk_val, int32_t* topk_idx, int rows, int k,
+                        void* stream) {
+  REQUIRE(stats && topk_val && topk_idx, UIC_ERR_ARG, "uic_beam_topk_merge: null pointer");
+  REQUIRE(k >= 1 && parts >= 1, UIC_ERR_ARG, "uic_beam_topk_merge: k=%d parts=%d", k, parts);
+  if (rows == 0) return 0;
+  return beam_topk_merge(stats, parts, kslots, topk_val, topk_idx, rows, k, ST(stream));
+}
+
+int uic_greedy_merge(const float* stats, int parts, int64_t* seq, float* seq_logprobs, uint8_t* unfinished, int64_t* next_tok,
+                     int32_t* n_unfinished, int t, int seq_length, int rows, void* stream) {
+  REQUIRE(stats && seq && seq_logprobs && unfinished && next_tok && n_unfinished, UIC_ERR_ARG, "uic_greedy_merge: null pointer");
+  REQUIRE(t >= 0 && t < seq_length && parts >= 1, UIC_ERR_ARG, "uic_greedy_merge: t=%d seq_length=%d parts=%d", t, seq_length, parts);
+  if (rows == 0) return 0;
+  return greedy_merge(stats, parts, seq, seq_logprobs, unfinished, next_tok, n_unfinished, t, seq_length, rows, ST(stream));
+}
+
 int uic_cast_f32_bf16(const float* src, int64_t ld_src, void* dst, int64_t ld_dst, int64_t rows, int64_t cols, int relu,
                       void* stream) {
   REQUIRE(src && dst, UIC_ERR_ARG, "uic_cast_f32_bf16: null pointer");

@@ -77,7 +77,7 @@ __device__ __forceinline__ void load8(const float* __restrict__ base, int a0, in
 }
 
 // CA = ceil(A / 256), CH = ceil(H / 256): lane owns elements [256c + 8*lane, +8) of chunk c.
-template <int NB, int CA, int CH>
+template <int NB, int CA, int CH, bool EXACT>
 __global__ void __launch_bounds__(ATT_THREADS, (NB * (CA + CH) <= 12) ? 2 : 1) att_step_fwd_kernel(AttParams p) {
   extern __shared__ __align__(128) uint8_t att_smem[];
   __shared__ uint64_t s_bar[ATT_WARPS][ATT_SLOTS];
@@ -107,7 +107,7 @@ __global__ void __launch_bounds__(ATT_THREADS, (NB * (CA + CH) <= 12) ? 2 : 1) a
   }
   __syncwarp();
   auto issue = [&](int l, int s) {  // lane 0 only
-    mbar_arrive_expect_tx(&s_bar[warp][s], slot_bytes);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar0 + s * 8), "r"(slot_bytes) : "memory");
     bulk_g2s(ring + s * slot_bytes, p_img + static_cast<long long>(l) * A, row_bytes_p, bar0 + s * 8);
     bulk_g2s(ring + s * slot_bytes + row_bytes_p, a_img + static_cast<long long>(l) * H, row_bytes_a, bar0 + s * 8);
   };
@@ -153,20 +153,20 @@ __global__ void __launch_bounds__(ATT_THREADS, (NB * (CA + CH) <= 12) ? 2 : 1) a
   int slot = 0;
   uint32_t parity = 0;
   for (int l = row_begin + warp; l < row_end; l += ATT_WARPS) {
-    mbar_wait(&s_bar[warp][slot], parity);
+    mbar_wait_addr(bar0 + slot * 8, parity);
     const uint32_t base = ring + slot * slot_bytes;
     uint4 q[CA], av[CH];
 #pragma unroll
     for (int c = 0; c < CA; ++c) {
       const int a0 = c * 256 + lane * 8;
       q[c] = make_uint4(0, 0, 0, 0);
-      if (a0 < A) asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(q[c].x), "=r"(q[c].y), "=r"(q[c].z), "=r"(q[c].w) : "r"(base + a0 * 2));
+      if (EXACT || a0 < A) asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(q[c].x), "=r"(q[c].y), "=r"(q[c].z), "=r"(q[c].w) : "r"(base + a0 * 2));
     }
 #pragma unroll
     for (int c = 0; c < CH; ++c) {
       const int h0 = c * 256 + lane * 8;
       av[c] = make_uint4(0, 0, 0, 0);
-      if (h0 < H)
+      if (EXACT || h0 < H)
         asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(av[c].x), "=r"(av[c].y), "=r"(av[c].z), "=r"(av[c].w) : "r"(base + row_bytes_p + h0 * 2));
     }
     const float mask_l = m_img ? __ldg(m_img + l) : 1.0f;
@@ -442,12 +442,12 @@ long long att_step_workspace_bytes(int n_img, int beams, int L, int H) {
   return counters + partial;
 }
 
-template <int NB, int CA, int CH>
+template <int NB, int CA, int CH, bool EXACT>
 static int launch_att(AttParams& p, int n_img, const AttPlan& pl, cudaStream_t stream) {
   const size_t ring = static_cast<size_t>(ATT_WARPS) * ATT_SLOTS * (p.A + p.H) * 2 + static_cast<size_t>(NB) * CA * 256 * 4;
   const size_t merge = static_cast<size_t>(ATT_WARPS) * NB * p.H * 4;
   const size_t smem = ring > merge ? ring : merge;
-  auto kern = att_step_fwd_kernel<NB, CA, CH>;
+  auto kern = att_step_fwd_kernel<NB, CA, CH, EXACT>;
   if (smem > 200 * 1024) return set_error(UIC_ERR_SHAPE, "att_step_fwd: A=%d H=%d need %zu bytes of shared memory", p.A, p.H, smem);
   if (smem > 40 * 1024)  // dynamic + the kernel's static shared memory may exceed the 48 KB default
     UIC_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
@@ -463,10 +463,18 @@ template <int CA, int CH>
 static int dispatch_nb(AttParams& p, int n_img, const AttPlan& pl, int nb_max, cudaStream_t stream) {
   int nb = beams_per_group(p.beams);
   nb = nb > nb_max ? nb_max : nb;
+  const bool exact = (p.A == 256 * CA) && (p.H == 256 * CH);
+  if (exact) {
+    switch (nb) {
+      case 1: return launch_att<1, CA, CH, true>(p, n_img, pl, stream);
+      case 2: return launch_att<2, CA, CH, true>(p, n_img, pl, stream);
+      default: return launch_att<3, CA, CH, true>(p, n_img, pl, stream);
+    }
+  }
   switch (nb) {
-    case 1: return launch_att<1, CA, CH>(p, n_img, pl, stream);
-    case 2: return launch_att<2, CA, CH>(p, n_img, pl, stream);
-    default: return launch_att<3, CA, CH>(p, n_img, pl, stream);
+    case 1: return launch_att<1, CA, CH, false>(p, n_img, pl, stream);
+    case 2: return launch_att<2, CA, CH, false>(p, n_img, pl, stream);
+    default: return launch_att<3, CA, CH, false>(p, n_img, pl, stream);
   }
 }
 

@@ -53,6 +53,13 @@ struct GemmEpilogue {
   float exp_scale;
   long long* trace;  // optional device buffer: CTA 0 records clock64() at pipeline events of its first tile
   int debug;         // UIC_GEMM_DEBUG bits (experiments only): 1 = no global stores, 2 = no TMEM load, 4 = no smem transpose
+  // fused vocabulary statistics (STATS > 0 kernels): per (row, column part) the running (max, sum exp) of
+  // x = acc + bias and the STATS best keys (UNK column shifted by -1000, banned token -inf) with their columns
+  float* stats;
+  const long long* banned;
+  long long banned_stride;
+  int parts;
+  int unk_col;  // column that gets -1000 (beam search only), -1 = none
 };
 
 #define UIC_TRACE(slot)                                                              \
@@ -80,6 +87,41 @@ __device__ __forceinline__ float epi_act(float v, int col, const GemmEpilogue& e
   return v;
 }
 
+// Branch-free insertion of (x, c) into a list sorted by value (descending).  Strict ">" keeps the earlier entry on
+// ties, so feeding columns in increasing order reproduces a stable descending sort.  -inf keys are never inserted.
+template <int K>
+__device__ __forceinline__ void topk_insert(float (&v)[K], int (&i)[K], float x, int c) {
+  bool p[K];
+#pragma unroll
+  for (int q = 0; q < K; ++q) p[q] = x > v[q];
+#pragma unroll
+  for (int q = K - 1; q > 0; --q) {
+    v[q] = p[q - 1] ? v[q - 1] : (p[q] ? x : v[q]);
+    i[q] = p[q - 1] ? i[q - 1] : (p[q] ? c : i[q]);
+  }
+  v[0] = p[0] ? x : v[0];
+  i[0] = p[0] ? c : i[0];
+}
+// Same, for candidates that arrive out of column order: equal values rank by the smaller column.
+template <int K>
+__device__ __forceinline__ void topk_insert_tie(float (&v)[K], int (&i)[K], float x, int c) {
+  bool p[K];
+#pragma unroll
+  for (int q = 0; q < K; ++q) p[q] = x > v[q] || (x == v[q] && c < i[q]);
+#pragma unroll
+  for (int q = K - 1; q > 0; --q) {
+    v[q] = p[q - 1] ? v[q - 1] : (p[q] ? x : v[q]);
+    i[q] = p[q - 1] ? i[q - 1] : (p[q] ? c : i[q]);
+  }
+  v[0] = p[0] ? x : v[0];
+  i[0] = p[0] ? c : i[0];
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 template <int BN, int STAGES>
 struct GemmSmem {
   static constexpr int A_BYTES = BM * BK * 2;
@@ -91,7 +133,7 @@ struct GemmSmem {
   static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;  // barriers + alignment slack
 };
 
-template <int BN, int STAGES, bool A_MN, bool B_MN>
+template <int BN, int STAGES, bool A_MN, bool B_MN, int STATS>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                          GemmEpilogue ep, int M, int N, int K) {
@@ -213,6 +255,99 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     for (int tile = blockIdx.x, it = 0; tile < num_tiles; tile += gridDim.x, ++it) {
       const int m0 = (tile % tiles_m) * BM, n0 = (tile / tiles_m) * BN;
       const int acc = it & 1;
+      if constexpr (STATS > 0) {
+        // ---- fused vocabulary statistics: the (rows, V) logits are never written to memory ----------------
+        constexpr int EMPTY = 0x7fffffff;
+        float* s_bias = reinterpret_cast<float*>(smem + L::EPI_OFFSET) + acc * BN;  // double-buffered by accumulator
+        const int et = threadIdx.x - 128;
+        if (et < BN) s_bias[et] = (ep.bias != nullptr && n0 + et < N) ? __ldg(ep.bias + n0 + et) : 0.0f;
+        asm volatile("bar.sync 1, 256;" ::: "memory");  // the 8 epilogue warps only
+        mbar_wait(&tmem_full_bar[acc], (it >> 1) & 1);
+        tcgen05_fence_after();
+        const int row = m0 + ew * 32 + lane;
+        int banned = -1;
+        if (ep.banned != nullptr && row < M) banned = static_cast<int>(ep.banned[static_cast<long long>(row) * ep.banned_stride]);
+        constexpr float LOG2E = 1.4426950408889634f;
+        constexpr int ES = (2 + 2 * STATS + 3) / 4 * 4;  // floats per (row, part) entry, see logit_stats_entry_floats
+        float run_m = -INFINITY, run_s = 0.0f;
+        // Two candidate lists (even / odd columns) so that consecutive insertions are independent instruction chains;
+        // ids are column offsets inside this warp's half tile (compile-time constants in the unrolled loops).
+        float va[STATS], vb[STATS];
+        int ia[STATS], ib[STATS];
+#pragma unroll
+        for (int qq = 0; qq < STATS; ++qq) {
+          va[qq] = vb[qq] = -INFINITY;
+          ia[qq] = ib[qq] = EMPTY;
+        }
+#pragma unroll
+        for (int cc = 0; cc < CHUNKS; ++cc) {
+          const int c = ehalf * CHUNKS + cc;
+          const int col0 = n0 + c * 32;
+          uint32_t v[32];
+          __syncwarp();
+          tmem_ld_32x32(tmem_base + acc * BN + (static_cast<uint32_t>(ew * 32) << 16) + c * 32, v);
+          tmem_ld_wait();
+          if (col0 >= N) continue;  // warp-uniform
+          float x[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]) + s_bias[c * 32 + j];
+          if (col0 + 32 > N) {  // ragged last tile (warp-uniform)
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j >= N) x[j] = -INFINITY;
+          }
+          float bm = x[0];
+#pragma unroll
+          for (int j = 1; j < 32; ++j) bm = fmaxf(bm, x[j]);
+          {
+            const float off = -bm * LOG2E;
+            float bs0 = 0.0f, bs1 = 0.0f;
+#pragma unroll
+            for (int j = 0; j < 32; j += 2) {
+              bs0 += ex2_approx(fmaf(x[j], LOG2E, off));
+              bs1 += ex2_approx(fmaf(x[j + 1], LOG2E, off));
+            }
+            const float nm = fmaxf(run_m, bm);
+            run_s = run_s * ex2_approx((run_m - nm) * LOG2E) + (bs0 + bs1) * ex2_approx((bm - nm) * LOG2E);
+            run_m = nm;
+          }
+          // beam-search edits of the candidate keys; the statistics above use the unedited logits
+          if (ep.unk_col >= col0 && ep.unk_col < col0 + 32) {  // UNK suppression (CaptionModel.py:133), warp-uniform
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (col0 + j == ep.unk_col) x[j] -= 1000.0f;
+          }
+          const int bj = banned - col0;
+          if (__any_sync(0xffffffffu, static_cast<unsigned>(bj) < 32u)) {  // decoding constraint (:130-131, AttModel.py:220-223)
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (j == bj) x[j] = -INFINITY;
+          }
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            topk_insert<STATS>(va, ia, x[j], cc * 32 + j);
+            topk_insert<STATS>(vb, ib, x[j + 1], cc * 32 + j + 1);
+          }
+        }
+#pragma unroll
+        for (int qq = 0; qq < STATS; ++qq) topk_insert_tie<STATS>(va, ia, vb[qq], ib[qq]);
+        if (row < M) {
+          float out[ES];
+          out[0] = run_m;
+          out[1] = run_s;
+          const int cbase = n0 + ehalf * CHUNKS * 32;
+#pragma unroll
+          for (int qq = 0; qq < STATS; ++qq) {
+            out[2 + qq] = va[qq];
+            out[2 + STATS + qq] = __int_as_float(ia[qq] == EMPTY ? EMPTY : cbase + ia[qq]);
+          }
+#pragma unroll
+          for (int qq = 2 + 2 * STATS; qq < ES; ++qq) out[qq] = 0.0f;
+          float4* dst = reinterpret_cast<float4*>(ep.stats + (static_cast<long long>(row) * ep.parts + (tile / tiles_m) * 2 + ehalf) * ES);
+#pragma unroll
+          for (int qq = 0; qq < ES / 4; ++qq) dst[qq] = make_float4(out[4 * qq], out[4 * qq + 1], out[4 * qq + 2], out[4 * qq + 3]);
+        }
+      } else {
       // bias of this lane's four columns in each of the warp's chunks: loaded while the k-loop still runs
       float4 bias4[CHUNKS];
 #pragma unroll
@@ -325,6 +460,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           store_rows(std::integral_constant<int, 0>{});
         }
       }
+      }  // STATS == 0
       // all four epilogue warps have read this accumulator: hand it back to the MMA issuer
       tcgen05_fence_before();
       __syncwarp();
@@ -417,10 +553,10 @@ static int sm_count() {
   return n;
 }
 
-template <int BN, int STAGES, bool A_MN, bool B_MN>
+template <int BN, int STAGES, bool A_MN, bool B_MN, int STATS = 0>
 static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const GemmEpilogue& ep, int M, int N, int K,
                      cudaStream_t stream) {
-  auto kern = gemm_bf16_tcgen05_kernel<BN, STAGES, A_MN, B_MN>;
+  auto kern = gemm_bf16_tcgen05_kernel<BN, STAGES, A_MN, B_MN, STATS>;
   constexpr int smem = GemmSmem<BN, STAGES>::TOTAL;
   static bool configured = false;  // benign race: attribute set is idempotent
   if (!configured) {
@@ -453,7 +589,7 @@ int gemm_bf16(const void* A, long long lda, const void* B, long long ldb, float*
   const bool a_mn = flags & UIC_GEMM_A_MN_MAJOR;
   const bool b_mn = flags & UIC_GEMM_B_MN_MAJOR;
   GemmEpilogue ep{c_f32, ldc, static_cast<__nv_bfloat16*>(c_bf16), ldcb, bias, (flags & UIC_GEMM_RELU) ? 1 : 0,
-                  (flags & UIC_GEMM_ACCUMULATE) ? 1 : 0, (flags & UIC_GEMM_OUT_F16) ? 1 : 0, exp_col0, exp_scale, gemm_trace_buffer(), gemm_debug_flags()};
+                  (flags & UIC_GEMM_ACCUMULATE) ? 1 : 0, (flags & UIC_GEMM_OUT_F16) ? 1 : 0, exp_col0, exp_scale, gemm_trace_buffer(), gemm_debug_flags(), nullptr, nullptr, 0, 0, -1};
   if (gemm_impl() == GEMM_IMPL_SIMT) {
     dim3 grid((N + 15) / 16, (M + 15) / 16), block(16, 16);
     launch_begin("gemm_bf16_simt", stream);
@@ -484,6 +620,30 @@ int gemm_bf16(const void* A, long long lda, const void* B, long long ldb, float*
   }
   if (bn == 64) return dispatch_major<64, 7>(a_mn, b_mn, ta, tb, ep, M, N, K, stream);
   return dispatch_major<128, 5>(a_mn, b_mn, ta, tb, ep, M, N, K, stream);
+}
+
+int logit_stats_parts(int N) { return 2 * ((N + 127) / 128); }
+int logit_stats_entry_floats(int kslots) { return (2 + 2 * kslots + 3) / 4 * 4; }
+
+// Logit projection with the fused statistics epilogue: stats[row][part][logit_stats_entry_floats(kslots)].
+int logit_stats(const void* A, long long lda, const void* B, long long ldb, const float* bias, const long long* banned,
+                long long banned_stride, float* stats, int M, int N, int K, int kslots, int unk_suppress, cudaStream_t stream) {
+  if (M <= 0 || N <= 0 || K <= 0) return set_error(UIC_ERR_SHAPE, "logit_stats: empty problem M=%d N=%d K=%d", M, N, K);
+  if (kslots != 1 && kslots != 3 && kslots != 5 && kslots != 8)
+    return set_error(UIC_ERR_ARG, "logit_stats: kslots must be 1, 3, 5 or 8 (got %d)", kslots);
+  if ((reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15) || (lda % 8) || (ldb % 8) ||
+      (reinterpret_cast<uintptr_t>(stats) & 15))
+    return set_error(UIC_ERR_ALIGN, "logit_stats: operands and stats must be 16-byte aligned with pitches that are multiples of 8 elements");
+  GemmEpilogue ep{nullptr, 0, nullptr, 0, bias, 0, 0, 0, 0, 0.0f, nullptr, 0, stats, banned, banned_stride, logit_stats_parts(N), unk_suppress ? N - 1 : -1};
+  CUtensorMap ta, tb;
+  int rc = get_tensor_map_bf16(&ta, A, M, K, lda, BM, 64);
+  if (rc) return rc;
+  rc = get_tensor_map_bf16(&tb, B, N, K, ldb, 128, 64);
+  if (rc) return rc;
+  if (kslots == 1) return launch_tc<128, 5, false, false, 1>(ta, tb, ep, M, N, K, stream);
+  if (kslots == 3) return launch_tc<128, 5, false, false, 3>(ta, tb, ep, M, N, K, stream);
+  if (kslots == 5) return launch_tc<128, 5, false, false, 5>(ta, tb, ep, M, N, K, stream);
+  return launch_tc<128, 5, false, false, 8>(ta, tb, ep, M, N, K, stream);
 }
 
 }  // namespace uic

@@ -36,6 +36,14 @@ int get_tensor_map_bf16(CUtensorMap* out, const void* base, long long rows, long
 int gemm_bf16(const void* A, long long lda, const void* B, long long ldb, float* c_f32, long long ldc, void* c_bf16,
               long long ldcb, const float* bias, int M, int N, int K, int flags, cudaStream_t stream, int exp_col0 = 0,
               float exp_scale = 0.0f);
+int logit_stats_parts(int N);
+int logit_stats_entry_floats(int kslots);
+int logit_stats(const void* A, long long lda, const void* B, long long ldb, const float* bias, const long long* banned,
+                long long banned_stride, float* stats, int M, int N, int K, int kslots, int unk_suppress, cudaStream_t stream);
+int beam_topk_merge(const float* stats, int parts, int kslots, float* topk_val, int32_t* topk_idx, int rows, int k,
+                    cudaStream_t stream);
+int greedy_merge(const float* stats, int parts, int64_t* seq, float* seq_lp, uint8_t* unfinished, int64_t* next_tok,
+                 int32_t* n_unfinished, int t, int seq_length, int rows, cudaStream_t stream);
 int cast_f32_bf16(const float* src, long long ld_src, void* dst, long long ld_dst, long long rows, long long cols, int relu,
                   cudaStream_t stream);
 int zero_padded_rows(void* x, const float* masks, int n_img, int L, int H, cudaStream_t stream);

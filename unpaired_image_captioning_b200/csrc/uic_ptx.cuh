@@ -58,6 +58,30 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+// Same by 32-bit shared address (avoids re-deriving the address from a generic pointer in hot loops).
+__device__ __forceinline__ bool mbar_try_wait_addr(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_addr(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait_addr(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait_addr(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) {
+      printf("uic: mbarrier wait timed out (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x);
+      __trap();
+    }
+  }
+}
 // Bounded wait: a protocol bug becomes a trap (launch failure) instead of a hung GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;

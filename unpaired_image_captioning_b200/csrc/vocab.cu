@@ -333,4 +333,174 @@ int row_topk(const float* logits, long long ld, const int64_t* prev_tok, float* 
   return 0;
 }
 
+// ---- merges of the fused logit statistics (gemm_tcgen05.cu, STATS epilogue) ----------------------------------
+// stats[row][part][ES] with ES = logit_stats_entry_floats(KS): (max, sum exp, KS keys, KS columns, padding).
+// One warp per row; lanes read consecutive parts with 16-byte loads.
+constexpr int MERGE_ROWS_PER_CTA = 4;
+
+struct RowStats {
+  float M, log_s;
+};
+
+// Merges the (max, sum exp) pairs of a row and leaves each lane with the best KS candidates of its share of
+// the parts (sorted by key descending, smaller column first on ties).
+template <int KS>
+__device__ __forceinline__ RowStats merge_row_stats(const float* __restrict__ st, int parts, float (&kv)[KS], int (&ki)[KS]) {
+  constexpr int EMPTY = 0x7fffffff;
+  constexpr int ES = (2 + 2 * KS + 3) / 4 * 4;
+  const int lane = threadIdx.x & 31;
+  MaxSum a{-INFINITY, 0.0f};
+#pragma unroll
+  for (int q = 0; q < KS; ++q) {
+    kv[q] = -INFINITY;
+    ki[q] = EMPTY;
+  }
+  const float4* base = reinterpret_cast<const float4*>(st);
+  float4 nxt[ES / 4];
+  if (lane < parts) {
+#pragma unroll
+    for (int w = 0; w < ES / 4; ++w) nxt[w] = base[static_cast<long long>(lane) * (ES / 4) + w];
+  }
+  for (int p = lane; p < parts; p += 32) {
+    float e[ES];
+#pragma unroll
+    for (int w = 0; w < ES / 4; ++w) {
+      e[4 * w] = nxt[w].x;
+      e[4 * w + 1] = nxt[w].y;
+      e[4 * w + 2] = nxt[w].z;
+      e[4 * w + 3] = nxt[w].w;
+    }
+    if (p + 32 < parts) {  // the next entry's loads fly while this one is merged
+#pragma unroll
+      for (int w = 0; w < ES / 4; ++w) nxt[w] = base[static_cast<long long>(p + 32) * (ES / 4) + w];
+    }
+    a = ms_merge(a, MaxSum{e[0], e[1]});
+#pragma unroll
+    for (int c = 0; c < KS; ++c) {
+      const float x = e[2 + c];
+      const int col = __float_as_int(e[2 + KS + c]);
+      bool pr[KS];
+#pragma unroll
+      for (int q = 0; q < KS; ++q) pr[q] = col != EMPTY && (x > kv[q] || (x == kv[q] && col < ki[q]));
+#pragma unroll
+      for (int q = KS - 1; q > 0; --q) {
+        kv[q] = pr[q - 1] ? kv[q - 1] : (pr[q] ? x : kv[q]);
+        ki[q] = pr[q - 1] ? ki[q - 1] : (pr[q] ? col : ki[q]);
+      }
+      kv[0] = pr[0] ? x : kv[0];
+      ki[0] = pr[0] ? col : ki[0];
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    MaxSum other;
+    other.m = __shfl_xor_sync(0xffffffffu, a.m, o);
+    other.s = __shfl_xor_sync(0xffffffffu, a.s, o);
+    a = ms_merge(a, other);
+  }
+  return RowStats{a.m, logf(a.s)};
+}
+
+// Pops the globally best remaining candidate of the warp (every lane holds a sorted list).
+template <int KS>
+__device__ __forceinline__ Best warp_pop_best(float (&kv)[KS], int (&ki)[KS]) {
+  constexpr int EMPTY = 0x7fffffff;
+  Best b{kv[0], ki[0]};
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, b.v, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, b.i, o);
+    if (oi != EMPTY && (b.i == EMPTY || better(ov, oi, b))) {
+      b.v = ov;
+      b.i = oi;
+    }
+  }
+  if (ki[0] == b.i && b.i != EMPTY) {  // the owner shifts its list up
+#pragma unroll
+    for (int q = 0; q + 1 < KS; ++q) {
+      kv[q] = kv[q + 1];
+      ki[q] = ki[q + 1];
+    }
+    kv[KS - 1] = -INFINITY;
+    ki[KS - 1] = EMPTY;
+  }
+  return b;
+}
+
+template <int KS>
+__global__ void __launch_bounds__(32 * MERGE_ROWS_PER_CTA) beam_topk_merge_kernel(const float* __restrict__ stats, int parts,
+                                                                                   float* __restrict__ topk_val,
+                                                                                   int32_t* __restrict__ topk_idx, int rows, int k) {
+  const int r = blockIdx.x * MERGE_ROWS_PER_CTA + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  float kv[KS];
+  int ki[KS];
+  const RowStats rs = merge_row_stats<KS>(stats + static_cast<long long>(r) * parts * ((2 + 2 * KS + 3) / 4 * 4), parts, kv, ki);
+  for (int round = 0; round < k; ++round) {
+    const Best b = warp_pop_best<KS>(kv, ki);
+    if ((threadIdx.x & 31) == 0) {
+      // the key already carries the beam-search edits (UNK - 1000, banned -inf): ys[q, c] of the reference
+      topk_val[static_cast<long long>(r) * k + round] = (b.v - rs.M) - rs.log_s;
+      topk_idx[static_cast<long long>(r) * k + round] = b.i;
+    }
+  }
+}
+
+int beam_topk_merge(const float* stats, int parts, int kslots, float* topk_val, int32_t* topk_idx, int rows, int k,
+                    cudaStream_t stream) {
+  if (k > kslots) return set_error(UIC_ERR_ARG, "beam_topk_merge: k=%d > kslots=%d", k, kslots);
+  if (kslots != 1 && kslots != 3 && kslots != 5 && kslots != 8)
+    return set_error(UIC_ERR_ARG, "beam_topk_merge: kslots must be 1, 3, 5 or 8");
+  const int grid = (rows + MERGE_ROWS_PER_CTA - 1) / MERGE_ROWS_PER_CTA;
+  launch_begin("beam_topk_merge", stream);
+  if (kslots == 1)
+    beam_topk_merge_kernel<1><<<grid, 32 * MERGE_ROWS_PER_CTA, 0, stream>>>(stats, parts, topk_val, topk_idx, rows, k);
+  else if (kslots == 3)
+    beam_topk_merge_kernel<3><<<grid, 32 * MERGE_ROWS_PER_CTA, 0, stream>>>(stats, parts, topk_val, topk_idx, rows, k);
+  else if (kslots == 5)
+    beam_topk_merge_kernel<5><<<grid, 32 * MERGE_ROWS_PER_CTA, 0, stream>>>(stats, parts, topk_val, topk_idx, rows, k);
+  else if (kslots == 8)
+    beam_topk_merge_kernel<8><<<grid, 32 * MERGE_ROWS_PER_CTA, 0, stream>>>(stats, parts, topk_val, topk_idx, rows, k);
+  UIC_CUDA_OK(cudaGetLastError());
+  launch_end(stream);
+  return 0;
+}
+
+// Greedy step from the fused statistics (kslots = 1): same bookkeeping as greedy_step_kernel.
+__global__ void __launch_bounds__(32 * MERGE_ROWS_PER_CTA) greedy_merge_kernel(const float* __restrict__ stats, int parts,
+                                                                                int64_t* __restrict__ seq, float* __restrict__ seq_lp,
+                                                                                uint8_t* __restrict__ unfinished,
+                                                                                int64_t* __restrict__ next_tok,
+                                                                                int32_t* __restrict__ n_unfinished, int t, int T,
+                                                                                int rows) {
+  if (t > 0 && n_unfinished[t - 1] == 0) return;  // the reference has left its loop (AttModel.py:250-251)
+  const int r = blockIdx.x * MERGE_ROWS_PER_CTA + (threadIdx.x >> 5);
+  if (r >= rows) return;
+  float kv[1];
+  int ki[1];
+  const RowStats rs = merge_row_stats<1>(stats + static_cast<long long>(r) * parts * 4, parts, kv, ki);
+  const Best b = warp_pop_best<1>(kv, ki);
+  if ((threadIdx.x & 31) == 0) {
+    long long it = b.i;
+    const bool u = (t == 0 ? true : unfinished[r] != 0) && it > 0;
+    it = u ? it : 0;
+    seq[static_cast<long long>(r) * T + t] = it;
+    seq_lp[static_cast<long long>(r) * T + t] = (b.v - rs.M) - rs.log_s;
+    unfinished[r] = u ? 1 : 0;
+    next_tok[r] = it;
+    if (u) atomicAdd(&n_unfinished[t], 1);
+  }
+}
+
+int greedy_merge(const float* stats, int parts, int64_t* seq, float* seq_lp, uint8_t* unfinished, int64_t* next_tok,
+                 int32_t* n_unfinished, int t, int seq_length, int rows, cudaStream_t stream) {
+  const int grid = (rows + MERGE_ROWS_PER_CTA - 1) / MERGE_ROWS_PER_CTA;
+  launch_begin("greedy_merge", stream);
+  greedy_merge_kernel<<<grid, 32 * MERGE_ROWS_PER_CTA, 0, stream>>>(stats, parts, seq, seq_lp, unfinished, next_tok, n_unfinished, t,
+                                                                    seq_length, rows);
+  UIC_CUDA_OK(cudaGetLastError());
+  launch_end(stream);
+  return 0;
+}
+
 }  // namespace uic

@@ -109,6 +109,7 @@ class DecoderEngine:
         self._packed = None
         self._graphs = {}
         self.use_graphs = True
+        self.fused_vocab = True   # sampling: logit GEMM with fused LSE/top-k statistics (False: write logits + row kernels)
         self._capture_launches = 0
         self._replayed_launches = 0
         self.lib = _lib.load()
@@ -226,7 +227,7 @@ class DecoderEngine:
         w, lib = self.w, self.lib
         B, dev, T = feats.B, feats.att.device, seq_length
         flags = _lib.SAMPLE_DECODING_CONSTRAINT if decoding_constraint else 0
-        key = ("greedy", B, feats.L, T, flags, feats.masks is not None)
+        key = ("greedy", B, feats.L, T, flags, feats.masks is not None, self.fused_vocab)
 
         def alloc():
             s = {"att": torch.empty_like(feats.att), "p_att": torch.empty_like(feats.p_att),
@@ -235,7 +236,9 @@ class DecoderEngine:
                  "ws": self._workspace(B, dev),
                  "seq": torch.zeros(B, T, dtype=torch.int64, device=dev), "lp": torch.zeros(B, T, device=dev),
                  "unf": torch.zeros(B, dtype=torch.uint8, device=dev), "tok": torch.zeros(B, dtype=torch.int64, device=dev),
-                 "nunf": torch.zeros(T, dtype=torch.int32, device=dev)}
+                 "nunf": torch.zeros(T, dtype=torch.int32, device=dev),
+                 "parts": int(lib.uic_logit_stats_parts(w.V))}
+            s["stats"] = torch.empty(B, s["parts"], 4, dtype=torch.float32, device=dev)
             s["feats"] = Features(s["att"], s["p_att"], s["fc"], s["masks"], B, feats.L)
             s["X"], s["c"], s["sl"] = self._new_state(B, dev, s["feats"], 1)
             s["img_idx"] = torch.arange(B, device=dev, dtype=torch.int64)
@@ -250,9 +253,18 @@ class DecoderEngine:
             self._embed(s["tok"], X, sl)
             for t in range(T):
                 h = self.core_step(X, c, f, ws)
-                self.logits_of(h, ws["logits"])
-                check(lib.uic_greedy_step(ptr(ws["logits"]), w.V, ptr(s["seq"]), ptr(s["lp"]), ptr(s["unf"]), ptr(s["tok"]),
-                                          ptr(s["nunf"]), t, T, B, w.V, flags, stream()))
+                if self.fused_vocab:
+                    # logit GEMM with the statistics epilogue (max / sum-exp / arg-max per column part) + merge:
+                    # the (B, V) logits are never written
+                    banned = s["seq"][:, t - 1:] if (flags and t > 0) else None
+                    check(lib.uic_logit_stats(ptr(h), h.stride(0), ptr(w.w_logit), w.H, ptr(w.b_logit), ptr(banned), T,
+                                              ptr(s["stats"]), B, w.V, w.H, 1, 0, stream()))
+                    check(lib.uic_greedy_merge(ptr(s["stats"]), s["parts"], ptr(s["seq"]), ptr(s["lp"]), ptr(s["unf"]), ptr(s["tok"]),
+                                               ptr(s["nunf"]), t, T, B, stream()))
+                else:
+                    self.logits_of(h, ws["logits"])
+                    check(lib.uic_greedy_step(ptr(ws["logits"]), w.V, ptr(s["seq"]), ptr(s["lp"]), ptr(s["unf"]), ptr(s["tok"]),
+                                              ptr(s["nunf"]), t, T, B, w.V, flags, stream()))
                 if t + 1 < T:
                     self._embed(s["tok"], X, sl)
             return s["seq"], s["lp"]
@@ -266,7 +278,7 @@ class DecoderEngine:
         R = B * b
         tk_flags = _lib.SAMPLE_DECODING_CONSTRAINT if decoding_constraint else 0
         bs_flags = _lib.BEAM_MAX_PPL if max_ppl else 0
-        key = ("beam", B, b, feats.L, T, tk_flags, bs_flags, feats.masks is not None)
+        key = ("beam", B, b, feats.L, T, tk_flags, bs_flags, feats.masks is not None, self.fused_vocab)
 
         def alloc():
             s = {"att": torch.empty_like(feats.att), "p_att": torch.empty_like(feats.p_att),
@@ -279,7 +291,9 @@ class DecoderEngine:
                  "done_seq": torch.zeros(B, b, T, dtype=torch.int32, device=dev), "done_lp": torch.zeros(B, b, T, device=dev),
                  "done_p": torch.zeros(B, b, dtype=torch.float64, device=dev), "done_unaug": torch.zeros(B, b, device=dev),
                  "done_cnt": torch.zeros(B, dtype=torch.int32, device=dev),
-                 "parent": torch.zeros(R, dtype=torch.int32, device=dev), "tok": torch.zeros(R, dtype=torch.int64, device=dev)}
+                 "parent": torch.zeros(R, dtype=torch.int32, device=dev), "tok": torch.zeros(R, dtype=torch.int64, device=dev),
+                 "parts": int(lib.uic_logit_stats_parts(w.V)), "kslots": 1 if b == 1 else 3 if b <= 3 else 5 if b <= 5 else 8}
+            s["stats"] = torch.empty(R, s["parts"], int(lib.uic_logit_stats_entry_floats(s["kslots"])), dtype=torch.float32, device=dev)
             s["feats"] = Features(s["att"], s["p_att"], s["fc"], s["masks"], B, feats.L)
             s["X"], s["c"], s["sl"] = self._new_state(R, dev, s["feats"], b)
             s["X2"], s["c2"] = torch.zeros_like(s["X"]), torch.zeros_like(s["c"])
@@ -301,9 +315,16 @@ class DecoderEngine:
                 X, c = bufs[t % 2]
                 Xn, cn = bufs[(t + 1) % 2]
                 h = self.core_step(X, c, f, ws, beams=b)
-                self.logits_of(h, ws["logits"])
-                check(lib.uic_row_topk(ptr(ws["logits"]), w.V, ptr(s["tok"]) if (tk_flags and t > 0) else None, ptr(s["tk_val"]),
-                                       ptr(s["tk_idx"]), R, w.V, b, tk_flags if t > 0 else 0, stream()))
+                if self.fused_vocab and b <= 8:
+                    banned = s["tok"] if (tk_flags and t > 0) else None
+                    check(lib.uic_logit_stats(ptr(h), h.stride(0), ptr(w.w_logit), w.H, ptr(w.b_logit), ptr(banned), 1,
+                                              ptr(s["stats"]), R, w.V, w.H, s["kslots"], 1, stream()))
+                    check(lib.uic_beam_topk_merge(ptr(s["stats"]), s["parts"], s["kslots"], ptr(s["tk_val"]), ptr(s["tk_idx"]), R, b,
+                                                  stream()))
+                else:
+                    self.logits_of(h, ws["logits"])
+                    check(lib.uic_row_topk(ptr(ws["logits"]), w.V, ptr(s["tok"]) if (tk_flags and t > 0) else None, ptr(s["tk_val"]),
+                                           ptr(s["tk_idx"]), R, w.V, b, tk_flags if t > 0 else 0, stream()))
                 check(lib.uic_beam_step(ptr(s["tk_val"]), ptr(s["tk_idx"]), ptr(s["beam_seq"]), ptr(s["beam_lp"]), ptr(s["beam_sum"]),
                                         ptr(s["done_seq"]), ptr(s["done_lp"]), ptr(s["done_p"]), ptr(s["done_unaug"]),
                                         ptr(s["done_cnt"]), ptr(s["parent"]), ptr(s["tok"]), t, T, B, b, bs_flags, stream()))
