@@ -107,12 +107,12 @@ int uic_zero_padded_rows(void* x_bf16, const float* att_masks, int n_img, int L,
  * Outputs (each optional): ctx_bf16, ctx_f32, alpha (rows x L fp32, saved for backward).
  * `workspace`: uic_att_step_workspace_bytes(...) bytes, 16-byte aligned, zeroed ONCE by the caller
  * (the kernel leaves its arrival counters at zero); it holds the partial results when the regions
- * of an image are split over several CTAs. */
+ * of an image are split over several CTAs (slices of at most 64 regions; L <= 32 slices). */
 int uic_att_step_fwd(const float* att_h, int64_t ld_att_h, const void* p_att_f16, const void* att_bf16,
                      const float* w_alpha, const float* att_masks, void* ctx_bf16, int64_t ld_ctx_bf16, float* ctx_f32,
                      int64_t ld_ctx_f32, float* alpha, void* workspace, int64_t workspace_bytes, int n_img, int beams, int L,
                      int A, int H, void* stream);
-int64_t uic_att_step_workspace_bytes(int n_img, int beams, int L, int H);
+int64_t uic_att_step_workspace_bytes(int n_img, int beams, int L, int A, int H);
 
 /* ---- LSTM pointwise ------------------------------------------------------------------------- */
 /* Att2in2 maxout cell (models/AttModel.py:584-601): sums = i2h(xt)+h2h(h) (rows x 5H, pitch ld_sums),

@@ -30,7 +30,7 @@ SIGNATURES = {
     "uic_embed_rows": (_i, [_p, _i64, _p, _p, _i64, _i, _i, _i, _p]),
     "uic_zero_padded_rows": (_i, [_p, _p, _i, _i, _i, _p]),
     "uic_att_step_fwd": (_i, [_p, _i64, _p, _p, _p, _p, _p, _i64, _p, _i64, _p, _p, _i64, _i, _i, _i, _i, _i, _p]),
-    "uic_att_step_workspace_bytes": (_i64, [_i, _i, _i, _i]),
+    "uic_att_step_workspace_bytes": (_i64, [_i, _i, _i, _i, _i]),
     "uic_lstm_maxout_fwd": (_i, [_p, _i64, _p, _i64, _p, _p, _p, _p, _i64, _p, _i64, _i, _i, _p]),
     "uic_lstm_cell_fwd": (_i, [_p, _i64, _p, _p, _p, _p, _i64, _p, _i64, _i, _i, _p]),
     "uic_log_softmax_rows": (_i, [_p, _i64, _p, _i64, _i, _i, _p]),
@@ -164,12 +164,12 @@ def gemm(a, b, bias=None, out_f32=None, out_bf16=None, relu=False, accumulate=Fa
 _att_ws = {}
 
 
-def att_workspace(n_img, beams, L, H, device):
+def att_workspace(n_img, beams, L, A, H, device):
     """Cached, zero-initialised workspace of uic_att_step_fwd for this shape (stream-ordered reuse)."""
-    key = (n_img, beams, L, H, str(device))
+    key = (n_img, beams, L, A, H, str(device))
     ws = _att_ws.get(key)
     if ws is None:
-        nbytes = int(load().uic_att_step_workspace_bytes(n_img, beams, L, H))
+        nbytes = int(load().uic_att_step_workspace_bytes(n_img, beams, L, A, H))
         ws = torch.zeros(max(nbytes, 16), dtype=torch.uint8, device=device)
         _att_ws[key] = ws
     return ws
@@ -180,7 +180,7 @@ def att_step(att_h, ld_att_h, p_att, att, w_alpha, masks, ctx_bf16, ld_ctx_bf16,
     (pass their row pitch); p_att is fp16 (n_img, L, A), att is bf16 (n_img, L, H), both contiguous."""
     if p_att.dtype != torch.float16 or att.dtype != torch.bfloat16 or not p_att.is_contiguous() or not att.is_contiguous():
         raise ValueError("att_step: p_att must be contiguous fp16 and att contiguous bf16")
-    ws = att_workspace(n_img, beams, L, H, att.device)
+    ws = att_workspace(n_img, beams, L, A, H, att.device)
     check(load().uic_att_step_fwd(ptr(att_h), ld_att_h, ptr(p_att), ptr(att), ptr(w_alpha), ptr(masks), ptr(ctx_bf16), ld_ctx_bf16,
                                   ptr(ctx_f32), ld_ctx_f32, ptr(alpha), ptr(ws), ws.numel(), n_img, beams, L, A, H, stream()))
 

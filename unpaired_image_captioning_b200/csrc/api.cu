@@ -140,6 +140,44 @@ int get_tensor_map_bf16(CUtensorMap* out, const void* base, long long rows, long
   return 0;
 }
 
+// A row-major bf16 matrix [rows, cols] (cols % 64 == 0, contiguous rows) seen as [cols / 64 slabs][rows][64]:
+// one box = box_rows rows of ALL slabs, stored slab by slab, each slab a 128-byte-swizzled tile like the 2-D
+// boxes above.  One TMA instruction then stages box_rows full rows.
+int get_tensor_map_bf16_slabs(CUtensorMap* out, const void* base, long long rows, long long cols, int box_rows) {
+  static std::mutex mu;
+  static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> cache;
+  MapKey key{base, rows, cols, -1, box_rows, 64};
+  {
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = cache.find(key);
+    if (it != cache.end()) {
+      *out = it->second;
+      return 0;
+    }
+  }
+  EncodeTiledFn fn = encode_fn();
+  if (fn == nullptr) return set_error(UIC_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+  if (cols % 64 != 0 || cols / 64 > 256) return set_error(UIC_ERR_SHAPE, "slab tensor map: cols=%lld must be a multiple of 64", cols);
+  cuuint64_t dims[3] = {64, static_cast<cuuint64_t>(rows), static_cast<cuuint64_t>(cols / 64)};
+  cuuint64_t strides[2] = {static_cast<cuuint64_t>(cols) * 2, 128};
+  cuuint32_t box[3] = {64, static_cast<cuuint32_t>(box_rows), static_cast<cuuint32_t>(cols / 64)};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUtensorMap m;
+  CUresult r = fn(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return set_error(UIC_ERR_CUDA, "cuTensorMapEncodeTiled (slabs) failed (%d) for base=%p rows=%lld cols=%lld box_rows=%d",
+                     static_cast<int>(r), base, rows, cols, box_rows);
+  {
+    std::lock_guard<std::mutex> lock(mu);
+    if (cache.size() > 65536) cache.clear();
+    cache.emplace(key, m);
+  }
+  *out = m;
+  return 0;
+}
+
 }  // namespace uic
 
 // ---- extern "C" ---------------------------------------------------------------------------------
@@ -284,9 +322,9 @@ int uic_att_step_fwd(const float* att_h, int64_t ld_att_h, const void* p_att, co
                       workspace_bytes, n_img, beams, L, A, H, ST(stream));
 }
 
-int64_t uic_att_step_workspace_bytes(int n_img, int beams, int L, int H) {
+int64_t uic_att_step_workspace_bytes(int n_img, int beams, int L, int A, int H) {
   if (n_img <= 0 || beams <= 0 || L <= 0 || H <= 0) return 0;
-  return att_step_workspace_bytes(n_img, beams, L, H);
+  return att_step_workspace_bytes(n_img, beams, L, A, H);
 }
 
 int uic_lstm_maxout_fwd(const float* sums, int64_t ld_sums, const float* a2c, int64_t ld_a2c, const float* c_prev, float* c_out,

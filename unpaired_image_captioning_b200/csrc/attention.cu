@@ -1,34 +1,49 @@
-// Fused additive-attention step: score -> softmax -> context in ONE pass over the image's
-// feature tiles (reference: Attention.forward, models/AttModel.py:538-558, eight separate ATen
-// kernels and a materialised (rows, L, A) tanh tensor).
+// Fused additive-attention step: score -> softmax -> context with ONE read of the image's feature
+// tiles (reference: Attention.forward, models/AttModel.py:538-558, eight separate ATen kernels and a
+// materialised (rows, L, A) tanh tensor).
 //
 // HBM-bound by design: per image and step the kernel reads p_att[i] (L x A fp16) and att[i]
 // (L x H bf16) exactly once, no matter how many beams share the image.
 //
-// Structure (third iteration, see profiles/ for the ncu captures that drove it):
+// Structure (sixth iteration, see profiles/ for the ncu captures and timelines that drove it):
 //   v1 kept a region per warp in registers with one prefetch in flight: latency bound, 15 % of HBM.
-//   v2 staged 8-region tiles per CTA with two block-wide phases per stage: 3x the instructions
-//      (addressing, bookkeeping, barrier spinning) for no gain.
-//   v3 (this file): every warp is autonomous.  Warp w of a CTA owns regions w, w+8, ... of the CTA's
-//      run and streams them through its PRIVATE 4-slot shared-memory ring: lane 0 issues two bulk
-//      async copies (cp.async.bulk, mbarrier complete_tx) per region, four regions ahead, so loads
-//      in flight do not depend on registers or occupancy and no block-wide barrier exists in the
-//      steady state.  Per region the warp computes e[j] = w . tanh(p_att + att_h[j]) for its beams
-//      with packed tanh.approx.f16x2 (half the MUFU work of the fp32 form, same 2^-11 error; p_att
-//      is fp16 so the add is one HADD2), an fp32 dot product, a warp-shuffle reduction, an online
-//      softmax and the fp32 context accumulation.  Warps are merged once through shared memory;
-//      L-splits of an image are merged by the last CTA to arrive (threadfence reduction).
+//   v2 staged 8-region tiles per CTA with two block-wide phases per stage: 3x the instructions.
+//   v3 made every warp autonomous (private rings, online softmax, fp32 context accumulators in
+//      registers): 645 instructions per region, a third of them bookkeeping; 26 % of HBM.
+//   v4 gave a CTA a 49-region slice, all loads up front, exact softmax, context on mma.sync: 35 % fewer
+//      instructions but the same time -- a CTA lived ~10 us of which 3 were arithmetic, the rest exposed
+//      load latency, three block barriers and the fence/atomic of the slice merge.
+//   v5 made the CTAs persistent and warp-specialised (8 score warps, 4 context warps): the context warps'
+//      short dependent chains were starved by the always-ready score warps (1.5 us per batch instead of
+//      0.25) and throttled the ring.
+//   v6 (this file): persistent, HOMOGENEOUS warps, no block barrier after start-up.  The work is the flat
+//      list of 16-region batches of all (image, beam group) jobs; CTA c owns a contiguous range of it and
+//      streams it through a 3-stage shared-memory ring (one bulk copy for the batch's p_att rows, one
+//      128B-swizzled TMA box per 64 columns of its att rows, att_h when the image changes).  Per batch i
+//      every one of the 8 warps
+//        - scores its two regions: e[j] = sum_a w_a tanh(p_att[l,a] + att_h[j,a]) for the job's beams, in
+//          the exponential form described below, and publishes them in shared memory (mbarrier);
+//        - in between, finishes batch i-1: online softmax at batch granularity (redundantly per warp, it
+//          is tiny) and the context product of ITS 16-column tiles on the tensor cores,
+//          D[col, beam] += att^T[col, region] * alpha[region, beam] (mma.sync m16n8k16, bf16 weights, fp32
+//          accumulate, operands straight from the swizzled boxes through ldmatrix.trans);
+//        - the last warp to finish batch i-1 refills its stage with batch i+2.
+//      An image cut by a CTA-range boundary is finished by the last warp to arrive at its workspace
+//      counter (threadfence reduction), column set by column set.
 #include <cuda_fp16.h>
+
+#include <type_traits>
 
 #include "uic_internal.h"
 #include "uic_ptx.cuh"
 
 namespace uic {
 
-constexpr int ATT_THREADS = 256;
-constexpr int ATT_WARPS = ATT_THREADS / 32;
-constexpr int ATT_SLOTS = 4;        // regions in flight per warp
-constexpr int ATT_MAX_SPLIT = 8;
+constexpr int ATT_WARPS = 8;
+constexpr int ATT_THREADS = 32 * ATT_WARPS;
+constexpr int ATT_STAGES = 3;
+constexpr int ATT_BATCH = 16;  // regions per batch = the K of one MMA
+constexpr int ATT_SLAB_BYTES = ATT_BATCH * 128;  // one TMA box: 16 regions x 64 bf16 columns, 128-byte swizzle
 
 struct AttParams {
   const float* att_h;
@@ -42,10 +57,16 @@ struct AttParams {
   float* ctx_f32;
   long long ld_ctx_f32;
   float* alpha;
-  float* ws_partial;   // [img][group][split][NB][H + 2]
-  int* ws_counter;     // [img][group], zero between launches
+  float* ws_partial;   // [job][segment][warp][lane][4 + 4 MT]
+  int* ws_counter;     // [job][ATT_WARPS], zero between launches
   int beams, L, A, H;
-  int rows_per_cta, nsplit;
+  int n_grp;           // beam groups per image (job = img * n_grp + grp)
+  int nbpi;            // batches per image
+  int total_batches;   // jobs * nbpi
+  int max_seg;         // segments an image can be cut into
+  int f_bufs;          // att_h buffers in shared memory (2, or 3 when every image is a single batch)
+  int slab_map;        // the tensor map is the 3-D slab view: one TMA instruction stages a batch's att rows
+  long long* trace;    // debug (uic_gemm_set_trace buffer): CTA 0 records globaltimer at its pipeline events
 };
 
 __device__ __forceinline__ void bulk_g2s(uint32_t smem_dst, const void* gsrc, uint32_t bytes, uint32_t bar) {
@@ -53,428 +74,573 @@ __device__ __forceinline__ void bulk_g2s(uint32_t smem_dst, const void* gsrc, ui
                "r"(bytes), "r"(bar)
                : "memory");
 }
-__device__ __forceinline__ uint32_t tanh_f16x2(uint32_t x) {
-  uint32_t y;
-  asm("tanh.approx.f16x2 %0, %1;" : "=r"(y) : "r"(x));
+__device__ __forceinline__ void mbar_expect_tx_addr(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_addr(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ float att_ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-__device__ __forceinline__ uint32_t hadd2_u32(uint32_t a, uint32_t b) {
-  __half2 r = __hadd2(*reinterpret_cast<__half2*>(&a), *reinterpret_cast<__half2*>(&b));
-  return *reinterpret_cast<uint32_t*>(&r);
+__device__ __forceinline__ long long att_now() {
+  long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+#define ATT_TRACE(slot)                                                                                  \
+  do {                                                                                                  \
+    if (p.trace != nullptr && blockIdx.x == 0 && warp == 0 && lane == 0 && (slot) < 128) p.trace[slot] = att_now(); \
+  } while (0)
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t addr, uint32_t (&r)[4]) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16_16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-// out[0..8) = base[a0 .. a0+8) (zero past n): two 16-byte loads when aligned, scalar otherwise.
-__device__ __forceinline__ void load8(const float* __restrict__ base, int a0, int n, float* out) {
-  if (a0 + 8 <= n && (reinterpret_cast<uintptr_t>(base + a0) & 15) == 0) {
-    const float4 lo = __ldg(reinterpret_cast<const float4*>(base + a0));
-    const float4 hi = __ldg(reinterpret_cast<const float4*>(base + a0) + 1);
-    out[0] = lo.x; out[1] = lo.y; out[2] = lo.z; out[3] = lo.w;
-    out[4] = hi.x; out[5] = hi.y; out[6] = hi.z; out[7] = hi.w;
-  } else {
-#pragma unroll
-    for (int k = 0; k < 8; ++k) out[k] = (a0 + k < n) ? __ldg(base + a0 + k) : 0.0f;
+struct AttSmem {  // byte offsets from the 1024-byte aligned base of a CTA's dynamic shared memory
+  uint32_t p_off, stage_bytes, off_F, off_e, off_bar, total;
+};
+__host__ __device__ inline AttSmem att_smem_layout(int A, int H, int NB, int f_bufs) {
+  AttSmem s;
+  s.p_off = (H + 63) / 64 * ATT_SLAB_BYTES;  // att boxes first (their swizzle atoms need 1024-byte alignment), p_att rows after
+  s.stage_bytes = (s.p_off + ATT_BATCH * A * 2 + 1023) / 1024 * 1024;
+  s.off_F = ATT_STAGES * s.stage_bytes;                       // [f_bufs][NB][A] fp32
+  s.off_e = s.off_F + f_bufs * NB * A * 4;                    // [STAGES][NB][16] fp32
+  s.off_bar = s.off_e + ATT_STAGES * NB * ATT_BATCH * 4;      // full / scored / consumed [STAGES] mbarriers
+  s.total = s.off_bar + 3 * ATT_STAGES * 8 + 1024;            // + alignment slack
+  return s;
+}
+
+// Owner of batch b when `total` batches are cut into `ctas` contiguous ranges [c*total/ctas, (c+1)*total/ctas).
+__device__ __forceinline__ int att_owner(long long b, long long ctas, long long total) {
+  return static_cast<int>(((b + 1) * ctas - 1) / total);
+}
+
+// Position of a batch in the job list (every warp keeps identical copies and advances them in step).
+struct AttCursor {
+  int kb, img, grp, job, fbuf, stage;
+  uint32_t parity;
+};
+__device__ __forceinline__ void att_advance(AttCursor& c, int nbpi, int n_grp, int f_bufs) {
+  if (++c.kb == nbpi) {
+    c.kb = 0;
+    ++c.job;
+    if (++c.fbuf == f_bufs) c.fbuf = 0;
+    if (++c.grp == n_grp) {
+      c.grp = 0;
+      ++c.img;
+    }
+  }
+  if (++c.stage == ATT_STAGES) {
+    c.stage = 0;
+    c.parity ^= 1;
   }
 }
 
-// CA = ceil(A / 256), CH = ceil(H / 256): lane owns elements [256c + 8*lane, +8) of chunk c.
-template <int NB, int CA, int CH, bool EXACT>
-__global__ void __launch_bounds__(ATT_THREADS, (NB * (CA + CH) <= 12) ? 2 : 1) att_step_fwd_kernel(AttParams p) {
-  extern __shared__ __align__(128) uint8_t att_smem[];
-  __shared__ uint64_t s_bar[ATT_WARPS][ATT_SLOTS];
-  __shared__ float s_m[NB][ATT_WARPS], s_s[NB][ATT_WARPS];
-  __shared__ int s_last;
+// CA = ceil(A / 256): lane owns units [256c + 128h + 4*lane, +4), h = 0, 1.  MT = 16-column context tiles per warp.
+template <int NB, int CA, int MT>
+__global__ void __launch_bounds__(ATT_THREADS, (CA <= 2 && MT <= 4) ? 2 : 1)
+att_step_fwd_kernel(const __grid_constant__ CUtensorMap tmap_att, AttParams p) {
+  extern __shared__ uint8_t att_smem_raw[];
 
   const int L = p.L, A = p.A, H = p.H;
-  const int img = blockIdx.x / p.nsplit, split = blockIdx.x - img * p.nsplit;
-  const int grp = blockIdx.y, n_grp = gridDim.y;
-  const int beam0 = grp * NB;
-  const int nb = min(NB, p.beams - beam0);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
-  const int row_begin = split * p.rows_per_cta;
-  const int row_end = min(L, row_begin + p.rows_per_cta);
-  const uint32_t row_bytes_p = A * 2, row_bytes_a = H * 2, slot_bytes = row_bytes_p + row_bytes_a;
-  const __half* p_img = p.p_att + static_cast<long long>(img) * L * A;
-  const __nv_bfloat16* a_img = p.att + static_cast<long long>(img) * L * H;
-  const float* m_img = p.masks ? p.masks + static_cast<long long>(img) * L : nullptr;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long ctas = gridDim.x, total = p.total_batches;
+  const int b_start = static_cast<int>(blockIdx.x * total / ctas);
+  const int nloc = static_cast<int>((blockIdx.x + 1) * total / ctas) - b_start;
+  if (nloc <= 0) return;
 
-  const uint32_t ring = smem_u32(att_smem) + warp * ATT_SLOTS * slot_bytes;   // this warp's private ring
-  const uint32_t bar0 = smem_u32(&s_bar[warp][0]);
+  const AttSmem sm = att_smem_layout(A, H, NB, p.f_bufs);
+  uint8_t* att_smem = att_smem_raw + ((1024 - (smem_u32(att_smem_raw) & 1023)) & 1023);
+  const uint32_t s_base = smem_u32(att_smem);
+  const uint32_t bar_full = s_base + sm.off_bar, bar_scored = bar_full + ATT_STAGES * 8, bar_consumed = bar_scored + ATT_STAGES * 8;
+  const float* s_F = reinterpret_cast<const float*>(att_smem + sm.off_F);
+  float* s_e = reinterpret_cast<float*>(att_smem + sm.off_e);
 
-  if (lane == 0) {
+  if (threadIdx.x == 0) {
 #pragma unroll
-    for (int s = 0; s < ATT_SLOTS; ++s) mbar_init(&s_bar[warp][s], 1);
+    for (int s = 0; s < ATT_STAGES; ++s) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_full + s * 8), "r"(1));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_scored + s * 8), "r"(ATT_WARPS));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_consumed + s * 8), "r"(ATT_WARPS));
+    }
     fence_barrier_init();
+    tma_prefetch_desc(&tmap_att);
   }
-  __syncwarp();
-  auto issue = [&](int l, int s) {  // lane 0 only
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar0 + s * 8), "r"(slot_bytes) : "memory");
-    bulk_g2s(ring + s * slot_bytes, p_img + static_cast<long long>(l) * A, row_bytes_p, bar0 + s * 8);
-    bulk_g2s(ring + s * slot_bytes + row_bytes_p, a_img + static_cast<long long>(l) * H, row_bytes_a, bar0 + s * 8);
+  __syncthreads();  // the only block-wide barrier
+  ATT_TRACE(0);
+  if (p.trace != nullptr && threadIdx.x == 0 && blockIdx.x < 448) p.trace[128 + 2 * blockIdx.x] = att_now();  // (1024-slot debug buffer)
+
+  // ---- the producer: whichever lane 0 calls it ----------------------------------------------------------
+  // Requests the batch under the producer cursor: the p_att rows are contiguous in both memories, the att rows
+  // come as 64-column TMA boxes (rows past the image belong to the next one or are zero-filled: their weights
+  // are zero), and the job's att_h rows (as F) come along when the batch is the first of its image here.
+  const int n_slabs = (H + 63) >> 6;
+  AttCursor pr;
+  {
+    const int job0 = b_start / p.nbpi;
+    pr.job = job0;
+    pr.kb = b_start - job0 * p.nbpi;
+    pr.img = job0 / p.n_grp;
+    pr.grp = job0 - pr.img * p.n_grp;
+    pr.fbuf = 0;
+    pr.stage = 0;
+    pr.parity = 0;
+  }
+  AttCursor sc = pr;  // the batch being scored
+  int pr_index = 0;   // local index of the batch under the producer cursor
+  auto produce = [&]() {
+    const int l0 = pr.kb * ATT_BATCH;
+    const int nrows = min(ATT_BATCH, L - l0);
+    const bool first = (pr.kb == 0) || (pr_index == 0);
+    const uint32_t bar = bar_full + pr.stage * 8;
+    const uint32_t st = s_base + pr.stage * sm.stage_bytes;
+    const long long l = static_cast<long long>(pr.img) * L + l0;
+    mbar_expect_tx_addr(bar, n_slabs * ATT_SLAB_BYTES + nrows * A * 2 + (first ? NB * A * 4 : 0));
+    bulk_g2s(st + sm.p_off, p.p_att + l * A, nrows * A * 2, bar);
+    if (p.slab_map) {
+      asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(st),
+                   "l"(reinterpret_cast<uint64_t>(&tmap_att)), "r"(bar), "r"(0), "r"(static_cast<int>(l)), "r"(0)
+                   : "memory");
+    } else {
+      for (int sl = 0; sl < n_slabs; ++sl)
+        asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+                         st + sl * ATT_SLAB_BYTES),
+                     "l"(reinterpret_cast<uint64_t>(&tmap_att)), "r"(bar), "r"(sl * 64), "r"(static_cast<int>(l))
+                     : "memory");
+    }
+    if (first) {
+      const int nb = min(NB, p.beams - pr.grp * NB);
+#pragma unroll
+      for (int j = 0; j < NB; ++j) {
+        const long long row = static_cast<long long>(pr.img) * p.beams + pr.grp * NB + (j < nb ? j : 0);
+        bulk_g2s(s_base + sm.off_F + ((pr.fbuf * NB + j) * A) * 4, p.att_h + row * p.ld_att_h, A * 4, bar);
+      }
+    }
   };
-  if (lane == 0) {
-#pragma unroll
-    for (int s = 0; s < ATT_SLOTS; ++s) {
-      const int l = row_begin + warp + s * ATT_WARPS;
-      if (l < row_end) issue(l, s);
-    }
-  }
+  // The ring starts full.  Afterwards batch b + 3 is requested once all warps have finished batch b; the att_h
+  // buffer it may overwrite then belongs to an image whose regions have all been scored (f_bufs = 3 when every
+  // image is a single batch, else two buffers suffice because a whole image spans at least two batches).
+  // (every CTA starts at the same time: asking for one batch first, and for the next two when it has landed, lets
+  // HBM deliver 296 first batches instead of 888 before anybody can start)
+  if (threadIdx.x == 0) produce();
+  att_advance(pr, p.nbpi, p.n_grp, p.f_bufs);
+  ++pr_index;
 
-  // per-lane constant: -2 * alpha_net weight.  F = 16 exp(2 att_h) of the CTA's beams lives in shared
-  // memory (NB * CA * 8 registers per lane would push the loop into local-memory spills, ncu pass 4):
-  // quad (j, c, half) is stored as [lane][4] so that a warp's LDS.128 is conflict-free.
+  // ---- per-lane constants ---------------------------------------------------------------------------------
+  // tanh(p + a) = 1 - 2 / (E F + 1) with E = exp(2 p)/16 (fp16 tile) and F = 16 exp(2 att_h); the constant
+  // sum(w) drops out of the softmax, so the score is e = sum_a (-2 w_a) / (E_a F_a + 1).  One reciprocal
+  // serves a PAIR of units: w1/d1 + w2/d2 = (w1 d2 + w2 d1) / (d1 d2)   (no fp32 overflow for |att_h| < 30).
   float w[CA * 8];
-  float* s_F = reinterpret_cast<float*>(att_smem + static_cast<size_t>(ATT_WARPS) * ATT_SLOTS * slot_bytes);
 #pragma unroll
-  for (int c = 0; c < CA; ++c) {
-    load8(p.w_alpha, c * 256 + lane * 8, A, &w[c * 8]);
+  for (int c = 0; c < CA; ++c)
 #pragma unroll
-    for (int k = 0; k < 8; ++k) w[c * 8 + k] *= -2.0f;
-  }
-  for (int jc = warp; jc < NB * CA; jc += ATT_WARPS) {
-    const int j = jc / CA, c = jc - j * CA;
-    const long long row = static_cast<long long>(img) * p.beams + beam0 + (j < nb ? j : 0);
-    float x[8];
-    load8(p.att_h + row * p.ld_att_h, c * 256 + lane * 8, A, x);
-    *reinterpret_cast<float4*>(s_F + (jc * 2 + 0) * 128 + lane * 4) = make_float4(x[0], x[1], x[2], x[3]);
-    *reinterpret_cast<float4*>(s_F + (jc * 2 + 1) * 128 + lane * 4) = make_float4(x[4], x[5], x[6], x[7]);
-  }
-  __syncthreads();
+    for (int h = 0; h < 2; ++h) {
+      const int u0 = c * 256 + h * 128 + lane * 4;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) w[c * 8 + h * 4 + k] = (u0 + k < A) ? -2.0f * __ldg(p.w_alpha + u0 + k) : 0.0f;
+    }
+  const int g = lane >> 2, t = lane & 3;
+  const int n_mtiles = (H + 15) >> 4;
+  // Tile warp + 8 q is the (warp & 3)-th 16-column group of box 2 q + warp / 4.  ldmatrix address of this lane:
+  // row k_in of the box, 16-byte chunk 2 (warp & 3) + m_in / 8, XOR-swizzled with the row (SWIZZLE_128B).
+  const int k_in = (lane & 7) + ((lane >> 4) & 1) * 8, m_in = ((lane >> 3) & 1) * 8;
+  const uint32_t a_off = (warp >> 2) * ATT_SLAB_BYTES + k_in * 128 + (((2 * (warp & 3) + (m_in >> 3)) ^ (k_in & 7)) << 4);
 
-  float m_run[NB], s_run[NB];
-  float acc[NB][CH * 8];
+  float m_run = -INFINITY, s_run = 0.0f;  // of beam g (lanes with g >= NB idle along)
+  float acc[MT][4];
 #pragma unroll
-  for (int j = 0; j < NB; ++j) {
-    m_run[j] = -INFINITY;
-    s_run[j] = 0.0f;
-#pragma unroll
-    for (int k = 0; k < CH * 8; ++k) acc[j][k] = 0.0f;
-  }
+  for (int q = 0; q < MT; ++q) acc[q][0] = acc[q][1] = acc[q][2] = acc[q][3] = 0.0f;
 
-  int slot = 0;
-  uint32_t parity = 0;
-  for (int l = row_begin + warp; l < row_end; l += ATT_WARPS) {
-    mbar_wait_addr(bar0 + slot * 8, parity);
-    const uint32_t base = ring + slot * slot_bytes;
-    uint4 q[CA], av[CH];
+  // ---- scoring of one region of the batch under `sc` ---------------------------------------------------------
+  // Scores NR = 1 or 2 regions (r and r + 8) of the batch under `sc`: the pair shares the att_h (F) loads and one
+  // transposed butterfly (lanes 0-15 end up with the sums of the first region, lanes 16-31 with the second's).
+  auto score_regions = [&](int r, auto nr_tag) {
+    constexpr int NR = decltype(nr_tag)::value;
+    const uint32_t prow = s_base + sc.stage * sm.stage_bytes + sm.p_off + r * A * 2;
+    const float* Fimg = s_F + sc.fbuf * NB * A;
+    float Ef[NR][CA * 8];
 #pragma unroll
-    for (int c = 0; c < CA; ++c) {
-      const int a0 = c * 256 + lane * 8;
-      q[c] = make_uint4(0, 0, 0, 0);
-      if (EXACT || a0 < A) asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(q[c].x), "=r"(q[c].y), "=r"(q[c].z), "=r"(q[c].w) : "r"(base + a0 * 2));
-    }
+    for (int x = 0; x < NR; ++x)
 #pragma unroll
-    for (int c = 0; c < CH; ++c) {
-      const int h0 = c * 256 + lane * 8;
-      av[c] = make_uint4(0, 0, 0, 0);
-      if (EXACT || h0 < H)
-        asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(av[c].x), "=r"(av[c].y), "=r"(av[c].z), "=r"(av[c].w) : "r"(base + row_bytes_p + h0 * 2));
-    }
-    const float mask_l = m_img ? __ldg(m_img + l) : 1.0f;
-
-    // ---- scores ------------------------------------------------------------------------------
-    // tanh(p + a) = 1 - 2 / (E F + 1); the constant sum(w) drops out of the softmax, so the score is
-    // e = sum_a (-2 w_a) / (E_a F_a + 1).  One reciprocal serves a PAIR of units:
-    //   w1/d1 + w2/d2 = (w1 d2 + w2 d1) / (d1 d2)          (d <= 1 + 65504 * F: no fp32 overflow for |att_h| < 30)
-    float Ef[CA * 8];
+      for (int c = 0; c < CA; ++c)
 #pragma unroll
-    for (int c = 0; c < CA; ++c) {
-      const uint32_t u[4] = {q[c].x, q[c].y, q[c].z, q[c].w};
+        for (int h = 0; h < 2; ++h) {
+          const int u0 = c * 256 + h * 128 + lane * 4;
+          uint32_t u[2] = {0, 0};
+          if (u0 < A)
+            asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(u[0]), "=r"(u[1]) : "r"(prow + x * ATT_WARPS * A * 2 + u0 * 2));
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float2 t = __half22float2(*reinterpret_cast<const __half2*>(&u[k]));
-        Ef[c * 8 + 2 * k] = t.x;
-        Ef[c * 8 + 2 * k + 1] = t.y;
-      }
-    }
-    float e[NB];
-#pragma unroll
-    for (int j = 0; j < NB; ++j) {
-      float Fj[CA * 8];
-#pragma unroll
-      for (int c = 0; c < CA; ++c) {
-        const float4 lo = *reinterpret_cast<const float4*>(s_F + ((j * CA + c) * 2 + 0) * 128 + lane * 4);
-        const float4 hi = *reinterpret_cast<const float4*>(s_F + ((j * CA + c) * 2 + 1) * 128 + lane * 4);
-        Fj[c * 8 + 0] = lo.x; Fj[c * 8 + 1] = lo.y; Fj[c * 8 + 2] = lo.z; Fj[c * 8 + 3] = lo.w;
-        Fj[c * 8 + 4] = hi.x; Fj[c * 8 + 5] = hi.y; Fj[c * 8 + 6] = hi.z; Fj[c * 8 + 7] = hi.w;
-      }
-      float p0 = 0.0f, p1 = 0.0f;
-#pragma unroll
-      for (int k = 0; k < CA * 8; k += 2) {
-        const float d1 = fmaf(Ef[k], Fj[k], 1.0f);
-        const float d2 = fmaf(Ef[k + 1], Fj[k + 1], 1.0f);
-        const float r = rcp_approx(d1 * d2);
-        const float num = fmaf(w[k + 1], d1, w[k] * d2);
-        if ((k & 2) == 0) p0 = fmaf(r, num, p0); else p1 = fmaf(r, num, p1);
-      }
-      e[j] = p0 + p1;
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-      for (int j = 0; j < NB; ++j) e[j] += __shfl_xor_sync(0xffffffffu, e[j], o);
-    }
-    if (p.alpha != nullptr && lane < nb) {
-      float ej = e[0];
-#pragma unroll
-      for (int j = 1; j < NB; ++j) ej = (lane == j) ? e[j] : ej;
-      p.alpha[(static_cast<long long>(img) * p.beams + beam0 + lane) * L + l] = ej;  // raw score, normalised at the end
-    }
-
-    // ---- online softmax + context ---------------------------------------------------------------
-    float af[CH * 8];
-#pragma unroll
-    for (int c = 0; c < CH; ++c) {
-      const uint32_t u[4] = {av[c].x, av[c].y, av[c].z, av[c].w};
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        af[c * 8 + 2 * k] = __uint_as_float(u[k] << 16);
-        af[c * 8 + 2 * k + 1] = __uint_as_float(u[k] & 0xffff0000u);
-      }
-    }
-#pragma unroll
-    for (int j = 0; j < NB; ++j) {
-      if (e[j] > m_run[j]) {  // warp-uniform: rare after the first few regions
-        const float scale = __expf(m_run[j] - e[j]);
-        m_run[j] = e[j];
-        s_run[j] *= scale;
-#pragma unroll
-        for (int k = 0; k < CH * 8; ++k) acc[j][k] *= scale;
-      }
-      const float pl = __expf(e[j] - m_run[j]) * mask_l;
-      s_run[j] += pl;
-#pragma unroll
-      for (int k = 0; k < CH * 8; ++k) acc[j][k] = fmaf(pl, af[k], acc[j][k]);
-    }
-    // Refill the slot only now: the FMAs above consumed every lane's registers loaded from it, so no
-    // shared-memory read of this slot can still be in flight when the async copy lands.
-    __syncwarp();
-    if (lane == 0) {
-      const int ln = l + ATT_SLOTS * ATT_WARPS;
-      if (ln < row_end) issue(ln, slot);
-    }
-    if (++slot == ATT_SLOTS) {
-      slot = 0;
-      parity ^= 1;
-    }
-  }
-
-  // ---- merge the warps of this CTA through shared memory (the rings are idle now) ----------------------
-  __syncthreads();
-  float* s_acc = reinterpret_cast<float*>(att_smem);  // [ATT_WARPS][NB][H]
-  if (lane == 0) {
-#pragma unroll
-    for (int j = 0; j < NB; ++j) {
-      s_m[j][warp] = m_run[j];
-      s_s[j][warp] = s_run[j];
-    }
-  }
-#pragma unroll
-  for (int j = 0; j < NB; ++j)
-#pragma unroll
-    for (int c = 0; c < CH; ++c) {
-      const int h0 = c * 256 + lane * 8;
-      if (h0 < H) {
-        float* dst = s_acc + (static_cast<size_t>(warp) * NB + j) * H + h0;
-        *reinterpret_cast<float4*>(dst) = make_float4(acc[j][c * 8], acc[j][c * 8 + 1], acc[j][c * 8 + 2], acc[j][c * 8 + 3]);
-        *reinterpret_cast<float4*>(dst + 4) = make_float4(acc[j][c * 8 + 4], acc[j][c * 8 + 5], acc[j][c * 8 + 6], acc[j][c * 8 + 7]);
-      }
-    }
-  __syncthreads();
-  float Mj[NB], Sj[NB], fw[NB][ATT_WARPS];
-#pragma unroll
-  for (int j = 0; j < NB; ++j) {
-    float mx = -INFINITY;
-#pragma unroll
-    for (int q2 = 0; q2 < ATT_WARPS; ++q2) mx = fmaxf(mx, s_m[j][q2]);
-    float ss = 0.0f;
-#pragma unroll
-    for (int q2 = 0; q2 < ATT_WARPS; ++q2) {
-      const float mq = s_m[j][q2];
-      fw[j][q2] = (mq == -INFINITY) ? 0.0f : __expf(mq - mx);
-      ss += s_s[j][q2] * fw[j][q2];
-    }
-    Mj[j] = mx;
-    Sj[j] = ss;
-  }
-  // thread `tid` owns the column pairs col = 2*(tid + 256*i)
-  constexpr int CHP = (CH + 1) / 2;
-  float out[NB][CHP * 2];
-#pragma unroll
-  for (int j = 0; j < NB; ++j)
-#pragma unroll
-    for (int i = 0; i < CHP; ++i) {
-      const int col = 2 * (tid + ATT_THREADS * i);
-      float2 v = make_float2(0.0f, 0.0f);
-      if (col < H) {
-#pragma unroll
-        for (int q2 = 0; q2 < ATT_WARPS; ++q2) {
-          const float2 a = *reinterpret_cast<const float2*>(s_acc + (static_cast<size_t>(q2) * NB + j) * H + col);
-          v.x = fmaf(a.x, fw[j][q2], v.x);
-          v.y = fmaf(a.y, fw[j][q2], v.y);
+          for (int k = 0; k < 2; ++k) {
+            const float2 t2 = __half22float2(*reinterpret_cast<const __half2*>(&u[k]));
+            Ef[x][c * 8 + h * 4 + 2 * k] = t2.x;
+            Ef[x][c * 8 + h * 4 + 2 * k + 1] = t2.y;
+          }
         }
-      }
-      out[j][2 * i] = v.x;
-      out[j][2 * i + 1] = v.y;
-    }
-
-  if (p.nsplit > 1) {
-    // ---- publish this split's partial, last arriver merges ------------------------------------------
-    float* part = p.ws_partial + ((static_cast<long long>(img) * n_grp + grp) * p.nsplit + split) * NB * (H + 2);
+    float e[NR][NB];
 #pragma unroll
     for (int j = 0; j < NB; ++j) {
+      float p0[NR], p1[NR];
 #pragma unroll
-      for (int i = 0; i < CHP; ++i) {
-        const int col = 2 * (tid + ATT_THREADS * i);
-        if (col < H) *reinterpret_cast<float2*>(part + j * (H + 2) + col) = make_float2(out[j][2 * i], out[j][2 * i + 1]);
-      }
-      if (tid == 0) {
-        part[j * (H + 2) + H] = Mj[j];
-        part[j * (H + 2) + H + 1] = Sj[j];
-      }
-    }
-    __threadfence();
-    __syncthreads();
-    if (tid == 0) {
-      const int old = atomicAdd(p.ws_counter + img * n_grp + grp, 1);
-      s_last = (old == p.nsplit - 1);
-      if (s_last) p.ws_counter[img * n_grp + grp] = 0;  // ready for the next launch
-    }
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
-    const float* base = p.ws_partial + (static_cast<long long>(img) * n_grp + grp) * p.nsplit * NB * (H + 2);
+      for (int x = 0; x < NR; ++x) p0[x] = p1[x] = 0.0f;
 #pragma unroll
-    for (int j = 0; j < NB; ++j) {
-      float mx = -INFINITY;
-      for (int k = 0; k < p.nsplit; ++k) mx = fmaxf(mx, __ldcg(base + (k * NB + j) * (H + 2) + H));
-      float ssum = 0.0f;
-      float f[ATT_MAX_SPLIT];
+      for (int c = 0; c < CA; ++c)
 #pragma unroll
-      for (int k = 0; k < ATT_MAX_SPLIT; ++k) {
-        f[k] = 0.0f;
-        if (k < p.nsplit) {
-          const float mk = __ldcg(base + (k * NB + j) * (H + 2) + H);
-          f[k] = (mk == -INFINITY) ? 0.0f : __expf(mk - mx);
-          ssum += __ldcg(base + (k * NB + j) * (H + 2) + H + 1) * f[k];
-        }
-      }
+        for (int h = 0; h < 2; ++h) {
+          const int u0 = c * 256 + h * 128 + lane * 4;
+          float4 f = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+          if (u0 < A) f = *reinterpret_cast<const float4*>(Fimg + j * A + u0);
+          const int k = c * 8 + h * 4;
 #pragma unroll
-      for (int i = 0; i < CHP; ++i) {
-        const int col = 2 * (tid + ATT_THREADS * i);
-        float2 v = make_float2(0.0f, 0.0f);
-        if (col < H) {
-#pragma unroll
-          for (int k = 0; k < ATT_MAX_SPLIT; ++k) {
-            if (k < p.nsplit) {
-              const float2 a = __ldcg(reinterpret_cast<const float2*>(base + (k * NB + j) * (H + 2) + col));
-              v.x = fmaf(a.x, f[k], v.x);
-              v.y = fmaf(a.y, f[k], v.y);
+          for (int x = 0; x < NR; ++x) {
+            {
+              const float d1 = fmaf(Ef[x][k], f.x, 1.0f), d2 = fmaf(Ef[x][k + 1], f.y, 1.0f);
+              p0[x] = fmaf(rcp_approx(d1 * d2), fmaf(w[k + 1], d1, w[k] * d2), p0[x]);
+            }
+            {
+              const float d1 = fmaf(Ef[x][k + 2], f.z, 1.0f), d2 = fmaf(Ef[x][k + 3], f.w, 1.0f);
+              p1[x] = fmaf(rcp_approx(d1 * d2), fmaf(w[k + 3], d1, w[k + 2] * d2), p1[x]);
             }
           }
         }
-        out[j][2 * i] = v.x;
-        out[j][2 * i + 1] = v.y;
-      }
-      Mj[j] = mx;
-      Sj[j] = ssum;
+#pragma unroll
+      for (int x = 0; x < NR; ++x) e[x][j] = p0[x] + p1[x];
     }
-  }
+    float v[NB];
+    if constexpr (NR == 2) {
+      const bool hi = lane >= 16;
+#pragma unroll
+      for (int j = 0; j < NB; ++j) {
+        const float keep = hi ? e[1][j] : e[0][j], give = hi ? e[0][j] : e[1][j];
+        v[j] = keep + __shfl_xor_sync(0xffffffffu, give, 16);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < NB; ++j) v[j] = e[0][j] + __shfl_xor_sync(0xffffffffu, e[0][j], 16);
+    }
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) {
+#pragma unroll
+      for (int j = 0; j < NB; ++j) v[j] += __shfl_xor_sync(0xffffffffu, v[j], o);
+    }
+    const int jl = lane & 15;
+    if (jl < NB && (NR == 2 || lane < 16)) {
+      float ej = v[0];
+#pragma unroll
+      for (int j = 1; j < NB; ++j) ej = (jl == j) ? v[j] : ej;
+      s_e[(sc.stage * NB + jl) * ATT_BATCH + r + (lane >> 4) * ATT_WARPS] = ej;
+    }
+  };
 
-  // ---- outputs -----------------------------------------------------------------------------------------
+  // ---- softmax update + context MMA (+ image finalisation) of the batch under `cx` ---------------------------
+  AttCursor cx = sc;
+  auto context = [&](bool range_end) {
+    const int beam0 = cx.grp * NB;
+    const int nb = min(NB, p.beams - beam0);
+    const int l0 = cx.kb * ATT_BATCH;
+    const int nrows = min(ATT_BATCH, L - l0);
+    const int kk[4] = {2 * t, 2 * t + 1, 2 * t + 8, 2 * t + 9};
+    float mk[4] = {1.0f, 1.0f, 1.0f, 1.0f};
+    if (p.masks != nullptr) {
+      const float* m_img = p.masks + static_cast<long long>(cx.img) * L + l0;
 #pragma unroll
-  for (int j = 0; j < NB; ++j) {
-    if (j < nb) {
-      const long long row = static_cast<long long>(img) * p.beams + beam0 + j;
-      const float inv = 1.0f / Sj[j];
+      for (int q = 0; q < 4; ++q)
+        if (kk[q] < nrows) mk[q] = __ldg(m_img + kk[q]);
+    }
+    mbar_wait_addr_sleepy(bar_scored + cx.stage * 8, cx.parity);  // all eight warps have scored this batch
+    ATT_TRACE(50 + pr_index);
+
+    // online softmax at batch granularity: this lane's four regions of beam g
+    const float* se = s_e + (cx.stage * NB + (g < NB ? g : 0)) * ATT_BATCH;
+    const float2 ea = *reinterpret_cast<const float2*>(se + 2 * t);
+    const float2 eb = *reinterpret_cast<const float2*>(se + 2 * t + 8);
+    float ev[4] = {ea.x, ea.y, eb.x, eb.y};
+    float mb = -INFINITY;
 #pragma unroll
-      for (int i = 0; i < CHP; ++i) {
-        const int col = 2 * (tid + ATT_THREADS * i);
-        if (col < H) {
-          const float v0 = out[j][2 * i] * inv, v1 = out[j][2 * i + 1] * inv;
-          if (p.ctx_bf16) *reinterpret_cast<uint32_t*>(p.ctx_bf16 + row * p.ld_ctx_bf16 + col) = f2_to_bf16x2(v0, v1);
-          if (p.ctx_f32) *reinterpret_cast<float2*>(p.ctx_f32 + row * p.ld_ctx_f32 + col) = make_float2(v0, v1);
-        }
-      }
-      if (p.alpha != nullptr) {  // raw scores (possibly written by the other splits) -> weights
-        __syncthreads();
-        for (int l = tid; l < L; l += ATT_THREADS) {
-          const float mk = m_img ? m_img[l] : 1.0f;
-          p.alpha[row * L + l] = __expf(__ldcg(p.alpha + row * L + l) - Mj[j]) * mk * inv;
-        }
+    for (int q = 0; q < 4; ++q) {
+      if (kk[q] >= nrows) ev[q] = -INFINITY;
+      mb = fmaxf(mb, ev[q]);
+    }
+    mb = fmaxf(mb, __shfl_xor_sync(0xffffffffu, mb, 1));
+    mb = fmaxf(mb, __shfl_xor_sync(0xffffffffu, mb, 2));
+    const float m_new = fmaxf(m_run, mb);  // finite: every batch has at least one region
+    float scale = 1.0f, pl[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+    if (g < NB) {
+      constexpr float LOG2E = 1.4426950408889634f;
+      const float off = -m_new * LOG2E;
+      scale = att_ex2(fmaf(m_run, LOG2E, off));  // 0 for the first batch of an image (m_run = -inf)
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        if (kk[q] < nrows) pl[q] = att_ex2(fmaf(ev[q], LOG2E, off)) * mk[q];
+    }
+    float ps = (pl[0] + pl[1]) + (pl[2] + pl[3]);
+    ps += __shfl_xor_sync(0xffffffffu, ps, 1);
+    ps += __shfl_xor_sync(0xffffffffu, ps, 2);
+    s_run = fmaf(s_run, scale, ps);
+    m_run = m_new;
+    const uint32_t b0 = f2_to_bf16x2(pl[0], pl[1]), b1 = f2_to_bf16x2(pl[2], pl[3]);
+    if (p.alpha != nullptr && warp == 0) {  // raw scores for the backward pass, normalised when the image is finished
+      for (int idx = lane; idx < NB * ATT_BATCH; idx += 32) {
+        const int j = idx / ATT_BATCH, r = idx - j * ATT_BATCH;
+        if (j < nb && r < nrows)
+          p.alpha[(static_cast<long long>(cx.img) * p.beams + beam0 + j) * L + l0 + r] = s_e[(cx.stage * NB + j) * ATT_BATCH + r];
       }
     }
+
+    // context: D[m = column][n = beam] += A[m][k = region] * B[k][n].  Accumulator columns n = 2t, 2t+1 belong
+    // to the beams whose running max lives in lanes 8t and 8t+4.
+    const float sc0 = __shfl_sync(0xffffffffu, scale, 8 * t), sc1 = __shfl_sync(0xffffffffu, scale, 8 * t + 4);
+#pragma unroll
+    for (int q = 0; q < MT; ++q) {  // (unconditional: sixteen independent multiplies are cheaper than a vote and a branch)
+      acc[q][0] *= sc0;
+      acc[q][1] *= sc1;
+      acc[q][2] *= sc0;
+      acc[q][3] *= sc1;
+    }
+    const uint32_t arow = s_base + cx.stage * sm.stage_bytes + a_off;
+#pragma unroll
+    for (int q = 0; q < MT; ++q) {
+      if (warp + ATT_WARPS * q < n_mtiles) {  // warp-uniform
+        uint32_t a[4];
+        ldmatrix_x4_trans(arow + q * 2 * ATT_SLAB_BYTES, a);
+        mma_bf16_16816(acc[q], a, b0, b1);
+      }
+    }
+    ATT_TRACE(70 + pr_index);
+    // Hand the stage back.  The warps take turns (batch index mod 8) at waiting for the other seven and requesting
+    // the batch three ahead into it, so the wait costs each warp one batch in eight.
+    __syncwarp();
+    if (lane == 0) mbar_arrive_addr(bar_consumed + cx.stage * 8);
+    if (pr_index < nloc) {
+      if ((pr_index & (ATT_WARPS - 1)) == warp) {
+        mbar_wait_addr_sleepy(bar_consumed + cx.stage * 8, cx.parity);
+        if (lane == 0) produce();
+      }
+      att_advance(pr, p.nbpi, p.n_grp, p.f_bufs);
+      ++pr_index;
+    }
+
+    // ---- image finished (or the range ends inside it) -----------------------------------------------------
+    if (cx.kb == p.nbpi - 1 || range_end) {
+      const long long first_b = static_cast<long long>(cx.job) * p.nbpi;
+      const int c_first = att_owner(first_b, ctas, total), c_last = att_owner(first_b + p.nbpi - 1, ctas, total);
+      const int nseg = c_last - c_first + 1, seg = static_cast<int>(blockIdx.x) - c_first;
+      // statistics of the accumulator columns' beams
+      float Mn[2] = {__shfl_sync(0xffffffffu, m_run, 8 * t), __shfl_sync(0xffffffffu, m_run, 8 * t + 4)};
+      float Sn[2] = {__shfl_sync(0xffffffffu, s_run, 8 * t), __shfl_sync(0xffffffffu, s_run, 8 * t + 4)};
+      const int n0 = 2 * t;
+      bool finish = true;
+      if (nseg > 1) {
+        // Every lane owns a private record of 1 + MT float4: (M0, M1, S0, S1) and its accumulators.
+        constexpr int REC = 4 + 4 * MT;
+        float4* rec = reinterpret_cast<float4*>(p.ws_partial) +
+                      (((static_cast<long long>(cx.job) * p.max_seg + seg) * ATT_WARPS + warp) * 32 + lane) * (REC / 4);
+        if (n0 < NB) {
+          rec[0] = make_float4(Mn[0], Mn[1], Sn[0], Sn[1]);
+#pragma unroll
+          for (int q = 0; q < MT; ++q) rec[1 + q] = make_float4(acc[q][0], acc[q][1], acc[q][2], acc[q][3]);
+        }
+        __threadfence();
+        __syncwarp();
+        int last = 0;
+        if (lane == 0) {
+          int* cnt = p.ws_counter + cx.job * ATT_WARPS + warp;
+          last = (atomicAdd(cnt, 1) == nseg - 1);
+          if (last) *cnt = 0;  // ready for the next launch
+        }
+        last = __shfl_sync(0xffffffffu, last, 0);
+        finish = last != 0;
+        if (finish && n0 < NB) {
+          __threadfence();
+          const float4* base = reinterpret_cast<const float4*>(p.ws_partial) +
+                               ((static_cast<long long>(cx.job) * p.max_seg * ATT_WARPS + warp) * 32 + lane) * (REC / 4);
+          const long long seg_stride = static_cast<long long>(ATT_WARPS) * 32 * (REC / 4);
+          float mx0 = -INFINITY, mx1 = -INFINITY;
+          for (int sgm = 0; sgm < nseg; ++sgm) {
+            const float4 st = __ldcg(base + sgm * seg_stride);
+            mx0 = fmaxf(mx0, st.x);
+            mx1 = fmaxf(mx1, st.y);
+          }
+          float ss0 = 0.0f, ss1 = 0.0f;
+#pragma unroll
+          for (int q = 0; q < MT; ++q) acc[q][0] = acc[q][1] = acc[q][2] = acc[q][3] = 0.0f;
+          for (int sgm = 0; sgm < nseg; ++sgm) {
+            const float4* r4 = base + sgm * seg_stride;
+            const float4 st = __ldcg(r4);
+            float4 v[MT];
+#pragma unroll
+            for (int q = 0; q < MT; ++q) v[q] = __ldcg(r4 + 1 + q);
+            const float f0 = __expf(st.x - mx0), f1 = __expf(st.y - mx1);
+            ss0 = fmaf(st.z, f0, ss0);
+            ss1 = fmaf(st.w, f1, ss1);
+#pragma unroll
+            for (int q = 0; q < MT; ++q) {
+              acc[q][0] = fmaf(v[q].x, f0, acc[q][0]);
+              acc[q][1] = fmaf(v[q].y, f1, acc[q][1]);
+              acc[q][2] = fmaf(v[q].z, f0, acc[q][2]);
+              acc[q][3] = fmaf(v[q].w, f1, acc[q][3]);
+            }
+          }
+          Mn[0] = mx0;
+          Mn[1] = mx1;
+          Sn[0] = ss0;
+          Sn[1] = ss1;
+        }
+      }
+      if (finish) {
+        // Element (q, e4) of the accumulators is column colb + 128 q + 8 (e4 >> 1) of beam n0 + (e4 & 1): one base
+        // pointer per beam plus compile-time offsets.
+        const int colb = warp * 16 + g;
+        const float inv[2] = {1.0f / Sn[0], 1.0f / Sn[1]};
+        const long long row0 = static_cast<long long>(cx.img) * p.beams + beam0;
+        const long long r_n[2] = {row0 + (n0 < nb ? n0 : 0), row0 + (n0 + 1 < nb ? n0 + 1 : 0)};
+        if (p.ctx_bf16 != nullptr) {
+          __nv_bfloat16* o_n[2] = {p.ctx_bf16 + r_n[0] * p.ld_ctx_bf16 + colb, p.ctx_bf16 + r_n[1] * p.ld_ctx_bf16 + colb};
+#pragma unroll
+          for (int q = 0; q < MT; ++q)
+#pragma unroll
+            for (int e4 = 0; e4 < 4; ++e4) {
+              const int off = 128 * q + 8 * (e4 >> 1);
+              if (n0 + (e4 & 1) < nb && colb + off < H) o_n[e4 & 1][off] = __float2bfloat16_rn(acc[q][e4] * inv[e4 & 1]);
+            }
+        }
+        if (p.ctx_f32 != nullptr) {
+          float* o_n[2] = {p.ctx_f32 + r_n[0] * p.ld_ctx_f32 + colb, p.ctx_f32 + r_n[1] * p.ld_ctx_f32 + colb};
+#pragma unroll
+          for (int q = 0; q < MT; ++q)
+#pragma unroll
+            for (int e4 = 0; e4 < 4; ++e4) {
+              const int off = 128 * q + 8 * (e4 >> 1);
+              if (n0 + (e4 & 1) < nb && colb + off < H) o_n[e4 & 1][off] = acc[q][e4] * inv[e4 & 1];
+            }
+        }
+        if (p.alpha != nullptr && warp == 0) {  // raw scores (possibly written by other CTAs) -> weights
+          __syncwarp();
+          const float* mfull = p.masks ? p.masks + static_cast<long long>(cx.img) * L : nullptr;
+          for (int j = 0; j < nb; ++j) {
+            // beam j's statistics live in accumulator column n = j, i.e. in the lanes with t == j / 2
+            const float Mj = __shfl_sync(0xffffffffu, (j & 1) ? Mn[1] : Mn[0], (j >> 1));
+            const float Sj = __shfl_sync(0xffffffffu, (j & 1) ? Sn[1] : Sn[0], (j >> 1));
+            float* arow_g = p.alpha + (row0 + j) * L;
+            for (int l = lane; l < L; l += 32) {
+              const float mkl = mfull ? mfull[l] : 1.0f;
+              arow_g[l] = __expf(__ldcg(arow_g + l) - Mj) * mkl / Sj;
+            }
+          }
+        }
+      }
+      m_run = -INFINITY;
+      s_run = 0.0f;
+#pragma unroll
+      for (int q = 0; q < MT; ++q) acc[q][0] = acc[q][1] = acc[q][2] = acc[q][3] = 0.0f;
+    }
+  };
+
+  // ---- main loop: score batch i, finishing batch i-1 between its two regions -----------------------------------
+  for (int i = 0; i <= nloc; ++i) {
+    if (i < nloc) {
+      const int nrows = min(ATT_BATCH, L - sc.kb * ATT_BATCH);
+      mbar_wait_addr_sleepy(bar_full + sc.stage * 8, sc.parity);
+      ATT_TRACE(1 + 4 * i);
+      if (i == 0) {
+        for (int k = 1; k < ATT_STAGES && k < nloc; ++k) {
+          if (threadIdx.x == 0) produce();
+          att_advance(pr, p.nbpi, p.n_grp, p.f_bufs);
+          ++pr_index;
+        }
+      }
+      if (warp + ATT_WARPS < nrows)
+        score_regions(warp, std::integral_constant<int, 2>{});
+      else if (warp < nrows)
+        score_regions(warp, std::integral_constant<int, 1>{});
+      __syncwarp();
+      if (lane == 0) mbar_arrive_addr(bar_scored + sc.stage * 8);
+      ATT_TRACE(2 + 4 * i);
+    }
+    if (i > 0) context(i == nloc);  // batch i - 1: every warp scored it a whole batch ago, nobody waits
+    ATT_TRACE(3 + 4 * i);
+    if (i < nloc) {
+      cx = sc;
+      att_advance(sc, p.nbpi, p.n_grp, p.f_bufs);
+    }
   }
+  ATT_TRACE(100);
+  if (p.trace != nullptr && threadIdx.x == 0 && blockIdx.x < 448) p.trace[129 + 2 * blockIdx.x] = att_now();
 }
 
 // ---- host side -------------------------------------------------------------------------------------------
-struct AttPlan {
-  int rows_per_cta, nsplit;
-};
-
-static AttPlan make_plan(int L, int n_img) {
-  // Splitting an image's regions over several CTAs costs a fixed prologue/epilogue per CTA (about half
-  // of the kernel at 7 regions per warp, ncu pass 4), so it is only used to create parallelism for small
-  // batches: aim for ~2 CTAs per SM, in multiples of 8 regions so the 8 warps of a CTA get equal shares.
-  int target = (2 * 148 + n_img - 1) / n_img;
-  const int by_len = (L + 24) / 49;
-  target = target > by_len ? by_len : target;
-  target = target < 1 ? 1 : (target > ATT_MAX_SPLIT ? ATT_MAX_SPLIT : target);
-  const int groups8 = (L + 7) / 8;
-  const int k = (groups8 + target - 1) / target;
-  AttPlan pl;
-  pl.rows_per_cta = 8 * k;
-  pl.nsplit = (L + pl.rows_per_cta - 1) / pl.rows_per_cta;
-  return pl;
-}
-
 static int beams_per_group(int beams) {
   if (beams <= 3) return beams;
   const int groups = (beams + 2) / 3;
   return (beams + groups - 1) / groups;
 }
 
-long long att_step_workspace_bytes(int n_img, int beams, int L, int H) {
-  const AttPlan pl = make_plan(L, n_img);
-  const int nb = beams_per_group(beams);
-  const int groups = (beams + nb - 1) / nb;
-  const long long counters = ((static_cast<long long>(n_img) * groups * 4 + 255) / 256) * 256;
-  const long long partial = pl.nsplit > 1 ? static_cast<long long>(n_img) * groups * pl.nsplit * nb * (H + 2) * 4 : 0;
-  return counters + partial;
+struct AttPlan {
+  int nb, groups, nbpi, ctas, max_seg, mt, f_bufs;
+  long long total;
+};
+
+static AttPlan make_plan(int n_img, int beams, int L, int A, int H) {
+  AttPlan pl;
+  pl.nb = beams_per_group(beams);
+  pl.groups = (beams + pl.nb - 1) / pl.nb;
+  pl.nbpi = (L + ATT_BATCH - 1) / ATT_BATCH;
+  pl.total = static_cast<long long>(n_img) * pl.groups * pl.nbpi;
+  const int per_sm = ((A + 255) / 256 <= 2 && H <= 512) ? 2 : 1;  // matches the kernel's launch bounds
+  const long long slots = 148LL * per_sm;
+  pl.ctas = static_cast<int>(pl.total < slots ? pl.total : slots);
+  const long long q = pl.total / pl.ctas;  // every range holds at least q >= 1 batches
+  long long ms = (pl.nbpi + q - 1) / q + 1;
+  pl.max_seg = static_cast<int>(ms > pl.nbpi ? pl.nbpi : ms);
+  pl.mt = H <= 512 ? 4 : 8;
+  pl.f_bufs = pl.nbpi == 1 ? 3 : 2;
+  return pl;
 }
 
-template <int NB, int CA, int CH, bool EXACT>
-static int launch_att(AttParams& p, int n_img, const AttPlan& pl, cudaStream_t stream) {
-  const size_t ring = static_cast<size_t>(ATT_WARPS) * ATT_SLOTS * (p.A + p.H) * 2 + static_cast<size_t>(NB) * CA * 256 * 4;
-  const size_t merge = static_cast<size_t>(ATT_WARPS) * NB * p.H * 4;
-  const size_t smem = ring > merge ? ring : merge;
-  auto kern = att_step_fwd_kernel<NB, CA, CH, EXACT>;
-  if (smem > 200 * 1024) return set_error(UIC_ERR_SHAPE, "att_step_fwd: A=%d H=%d need %zu bytes of shared memory", p.A, p.H, smem);
+long long att_step_workspace_bytes(int n_img, int beams, int L, int A, int H) {
+  const AttPlan pl = make_plan(n_img, beams, L, A, H);
+  const long long jobs = static_cast<long long>(n_img) * pl.groups;
+  const long long counters = ((jobs * ATT_WARPS * 4 + 255) / 256) * 256;
+  return counters + jobs * pl.max_seg * ATT_WARPS * 32 * (4 + 4 * pl.mt) * 4;
+}
+
+template <int NB, int CA, int MT>
+static int launch_att(AttParams& p, const AttPlan& pl, int n_img, cudaStream_t stream) {
+  const size_t smem = att_smem_layout(p.A, p.H, NB, pl.f_bufs).total;
+  auto kern = att_step_fwd_kernel<NB, CA, MT>;
+  if (smem > 226 * 1024) return set_error(UIC_ERR_SHAPE, "att_step_fwd: A=%d H=%d need %zu bytes of shared memory", p.A, p.H, smem);
   if (smem > 40 * 1024)  // dynamic + the kernel's static shared memory may exceed the 48 KB default
     UIC_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-  dim3 grid(n_img * pl.nsplit, (p.beams + NB - 1) / NB);
+  // att as a 2-D tensor [n_img * L regions][H columns]: boxes of 16 regions x 64 columns, 128-byte swizzle
+  CUtensorMap tm;
+  p.slab_map = (p.H % 64 == 0);
+  int rc = p.slab_map ? get_tensor_map_bf16_slabs(&tm, p.att, static_cast<long long>(n_img) * p.L, p.H, ATT_BATCH) : -1;
+  if (rc) {  // H is not a multiple of 64 (or the driver refuses the slab view): one 2-D box per 64 columns
+    p.slab_map = 0;
+    rc = get_tensor_map_bf16(&tm, p.att, static_cast<long long>(n_img) * p.L, p.H, p.H, ATT_BATCH, 64);
+    if (rc) return rc;
+  }
   launch_begin("att_step_fwd", stream);
-  kern<<<grid, ATT_THREADS, smem, stream>>>(p);
+  kern<<<pl.ctas, ATT_THREADS, smem, stream>>>(tm, p);
   UIC_CUDA_OK(cudaGetLastError());
   launch_end(stream);
   return 0;
 }
 
-template <int CA, int CH>
-static int dispatch_nb(AttParams& p, int n_img, const AttPlan& pl, int nb_max, cudaStream_t stream) {
-  int nb = beams_per_group(p.beams);
-  nb = nb > nb_max ? nb_max : nb;
-  const bool exact = (p.A == 256 * CA) && (p.H == 256 * CH);
-  if (exact) {
-    switch (nb) {
-      case 1: return launch_att<1, CA, CH, true>(p, n_img, pl, stream);
-      case 2: return launch_att<2, CA, CH, true>(p, n_img, pl, stream);
-      default: return launch_att<3, CA, CH, true>(p, n_img, pl, stream);
-    }
-  }
-  switch (nb) {
-    case 1: return launch_att<1, CA, CH, false>(p, n_img, pl, stream);
-    case 2: return launch_att<2, CA, CH, false>(p, n_img, pl, stream);
-    default: return launch_att<3, CA, CH, false>(p, n_img, pl, stream);
+template <int CA, int MT>
+static int dispatch_nb(AttParams& p, const AttPlan& pl, int n_img, cudaStream_t stream) {
+  switch (pl.nb) {
+    case 1: return launch_att<1, CA, MT>(p, pl, n_img, stream);
+    case 2: return launch_att<2, CA, MT>(p, pl, n_img, stream);
+    default: return launch_att<3, CA, MT>(p, pl, n_img, stream);
   }
 }
 
@@ -486,16 +652,15 @@ int att_step_fwd(const float* att_h, long long ld_att_h, const void* p_att, cons
     return set_error(UIC_ERR_SHAPE, "att_step_fwd: A=%d and H=%d must be multiples of 8 and <= 1024", A, H);
   if ((reinterpret_cast<uintptr_t>(p_att) & 15) || (reinterpret_cast<uintptr_t>(att) & 15))
     return set_error(UIC_ERR_ALIGN, "att_step_fwd: feature tiles must be 16-byte aligned");
-  if ((ctx_bf16 && (ld_ctx_bf16 % 2 || (reinterpret_cast<uintptr_t>(ctx_bf16) & 3))) ||
-      (ctx_f32 && (ld_ctx_f32 % 2 || (reinterpret_cast<uintptr_t>(ctx_f32) & 7))))
-    return set_error(UIC_ERR_ALIGN, "att_step_fwd: ctx outputs need even pitches and 4/8-byte alignment");
-  const AttPlan pl = make_plan(L, n_img);
-  const long long need = att_step_workspace_bytes(n_img, beams, L, H);
+  if ((reinterpret_cast<uintptr_t>(att_h) & 15) || (ld_att_h % 4))
+    return set_error(UIC_ERR_ALIGN, "att_step_fwd: att_h must be 16-byte aligned with a pitch that is a multiple of 4 floats");
+  const AttPlan pl = make_plan(n_img, beams, L, A, H);
+  const long long need = att_step_workspace_bytes(n_img, beams, L, A, H);
   if (workspace == nullptr || workspace_bytes < need || (reinterpret_cast<uintptr_t>(workspace) & 15))
     return set_error(UIC_ERR_ARG, "att_step_fwd: workspace of %lld bytes (16-byte aligned, zeroed once) required, got %lld", need,
                      workspace_bytes);
-  const int nbg = beams_per_group(beams);
-  const int groups = (beams + nbg - 1) / nbg;
+  const long long jobs = static_cast<long long>(n_img) * pl.groups;
+  if (pl.total > 0x7fffffffLL) return set_error(UIC_ERR_SHAPE, "att_step_fwd: too many region batches");
   AttParams p{};
   p.att_h = att_h;
   p.ld_att_h = ld_att_h;
@@ -510,18 +675,25 @@ int att_step_fwd(const float* att_h, long long ld_att_h, const void* p_att, cons
   p.alpha = alpha;
   // counters first (they must stay zero between launches), partials after them
   p.ws_counter = static_cast<int*>(workspace);
-  p.ws_partial = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + ((static_cast<long long>(n_img) * groups * 4 + 255) / 256) * 256);
+  p.ws_partial = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + ((jobs * ATT_WARPS * 4 + 255) / 256) * 256);
   p.beams = beams;
   p.L = L;
   p.A = A;
   p.H = H;
-  p.rows_per_cta = pl.rows_per_cta;
-  p.nsplit = pl.nsplit;
-  const int ca = (A + 255) / 256, ch = (H + 255) / 256;
-  if (ca <= 1 && ch <= 1) return dispatch_nb<1, 1>(p, n_img, pl, 3, stream);
-  if (ca <= 2 && ch <= 2) return dispatch_nb<2, 2>(p, n_img, pl, 3, stream);
-  if (ca <= 2 && ch <= 4) return dispatch_nb<2, 4>(p, n_img, pl, 3, stream);
-  return dispatch_nb<4, 4>(p, n_img, pl, 3, stream);
+  p.n_grp = pl.groups;
+  p.nbpi = pl.nbpi;
+  p.total_batches = static_cast<int>(pl.total);
+  p.max_seg = pl.max_seg;
+  p.f_bufs = pl.f_bufs;
+  p.trace = gemm_trace_buffer();
+  const int ca = (A + 255) / 256;
+  if (H <= 512) {
+    if (ca <= 1) return dispatch_nb<1, 4>(p, pl, n_img, stream);
+    if (ca <= 2) return dispatch_nb<2, 4>(p, pl, n_img, stream);
+    return dispatch_nb<4, 4>(p, pl, n_img, stream);
+  }
+  if (ca <= 2) return dispatch_nb<2, 8>(p, pl, n_img, stream);
+  return dispatch_nb<4, 8>(p, pl, n_img, stream);
 }
 
 }  // namespace uic

@@ -24,6 +24,8 @@ long long* gemm_trace_buffer();
 // box = box_rows x box_cols, 128-byte swizzle, zero fill out of bounds.
 int get_tensor_map_bf16(CUtensorMap* out, const void* base, long long rows, long long cols, long long ld, int box_rows,
                         int box_cols);
+// [rows, cols] (cols % 64 == 0) as [cols/64 slabs][rows][64]: one box = box_rows rows of all slabs (see api.cu).
+int get_tensor_map_bf16_slabs(CUtensorMap* out, const void* base, long long rows, long long cols, int box_rows);
 
 #define UIC_CUDA_OK(expr)                                                                                   \
   do {                                                                                                      \
@@ -52,7 +54,7 @@ int embed_rows(const void* table, long long ld_table, const int64_t* tok, void* 
 int att_step_fwd(const float* att_h, long long ld_att_h, const void* p_att, const void* att, const float* w_alpha,
                  const float* masks, void* ctx_bf16, long long ld_ctx_bf16, float* ctx_f32, long long ld_ctx_f32, float* alpha,
                  void* workspace, long long workspace_bytes, int n_img, int beams, int L, int A, int H, cudaStream_t stream);
-long long att_step_workspace_bytes(int n_img, int beams, int L, int H);
+long long att_step_workspace_bytes(int n_img, int beams, int L, int A, int H);
 int lstm_maxout_fwd(const float* sums, long long ld_sums, const float* a2c, long long ld_a2c, const float* c_prev, float* c_out,
                     float* h_f32, void* h_a, long long ld_ha, void* h_b, long long ld_hb, int rows, int H, cudaStream_t stream);
 int lstm_cell_fwd(const float* gates, long long ld_gates, const float* c_prev, float* c_out, float* h_f32, void* h_a,

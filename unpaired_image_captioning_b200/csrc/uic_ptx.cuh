@@ -72,6 +72,30 @@ __device__ __forceinline__ bool mbar_try_wait_addr(uint32_t bar, uint32_t parity
       : "memory");
   return ok != 0;
 }
+// try_wait with a suspend-time hint (ns): the warp sleeps in hardware instead of spinning through the issue slots.
+__device__ __forceinline__ bool mbar_try_wait_addr_hint(uint32_t bar, uint32_t parity, uint32_t ns) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity), "r"(ns)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_addr_sleepy(uint32_t bar, uint32_t parity) {
+  if (mbar_try_wait_addr(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait_addr_hint(bar, parity, 2000)) {
+    if (clock64() - t0 > 4000000000LL) {
+      printf("uic: mbarrier wait timed out (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x);
+      __trap();
+    }
+  }
+}
 __device__ __forceinline__ void mbar_wait_addr(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait_addr(bar, parity)) return;
   const long long t0 = clock64();
