@@ -28,8 +28,9 @@
 //          D[col, beam] += att^T[col, region] * alpha[region, beam] (mma.sync m16n8k16, bf16 weights, fp32
 //          accumulate, operands straight from the swizzled boxes through ldmatrix.trans);
 //        - the last warp to finish batch i-1 refills its stage with batch i+2.
-//      An image cut by a CTA-range boundary is finished by the last warp to arrive at its workspace
-//      counter (threadfence reduction), column set by column set.
+//      With at least half as many jobs as CTA slots a CTA owns whole jobs and nothing is merged; smaller
+//      batches cut every job into equal segments, one CTA each, and the last warp to arrive at the job's
+//      workspace counter finishes it (threadfence reduction), column set by column set.
 #include <cuda_fp16.h>
 
 #include <type_traits>
@@ -62,8 +63,8 @@ struct AttParams {
   int beams, L, A, H;
   int n_grp;           // beam groups per image (job = img * n_grp + grp)
   int nbpi;            // batches per image
-  int total_batches;   // jobs * nbpi
-  int max_seg;         // segments an image can be cut into
+  int segs;            // segments per job (1: CTAs own whole jobs, no merging; > 1: one CTA per segment)
+  int items;           // jobs * segs
   int f_bufs;          // att_h buffers in shared memory (2, or 3 when every image is a single batch)
   int slab_map;        // the tensor map is the 3-D slab view: one TMA instruction stages a batch's att rows
   long long* trace;    // debug (uic_gemm_set_trace buffer): CTA 0 records globaltimer at its pipeline events
@@ -119,9 +120,11 @@ __host__ __device__ inline AttSmem att_smem_layout(int A, int H, int NB, int f_b
   return s;
 }
 
-// Owner of batch b when `total` batches are cut into `ctas` contiguous ranges [c*total/ctas, (c+1)*total/ctas).
-__device__ __forceinline__ int att_owner(long long b, long long ctas, long long total) {
-  return static_cast<int>(((b + 1) * ctas - 1) / total);
+// First batch of work item `it` (item = segment `it % segs` of job `it / segs`; a job's nbpi batches are cut into
+// `segs` nearly equal runs).
+__device__ __forceinline__ int att_item_begin(int it, int segs, int nbpi) {
+  const int job = it / segs, sg = it - job * segs;
+  return job * nbpi + (sg * nbpi) / segs;
 }
 
 // Position of a batch in the job list (every warp keeps identical copies and advances them in step).
@@ -153,9 +156,11 @@ att_step_fwd_kernel(const __grid_constant__ CUtensorMap tmap_att, AttParams p) {
 
   const int L = p.L, A = p.A, H = p.H;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const long long ctas = gridDim.x, total = p.total_batches;
-  const int b_start = static_cast<int>(blockIdx.x * total / ctas);
-  const int nloc = static_cast<int>((blockIdx.x + 1) * total / ctas) - b_start;
+  // CTA c owns the work items [c * items / ctas, (c + 1) * items / ctas): a contiguous run of batches
+  const int item0 = static_cast<int>(static_cast<long long>(blockIdx.x) * p.items / gridDim.x);
+  const int item1 = static_cast<int>(static_cast<long long>(blockIdx.x + 1) * p.items / gridDim.x);
+  const int b_start = att_item_begin(item0, p.segs, p.nbpi);
+  const int nloc = att_item_begin(item1, p.segs, p.nbpi) - b_start;
   if (nloc <= 0) return;
 
   const AttSmem sm = att_smem_layout(A, H, NB, p.f_bufs);
@@ -430,9 +435,7 @@ att_step_fwd_kernel(const __grid_constant__ CUtensorMap tmap_att, AttParams p) {
 
     // ---- image finished (or the range ends inside it) -----------------------------------------------------
     if (cx.kb == p.nbpi - 1 || range_end) {
-      const long long first_b = static_cast<long long>(cx.job) * p.nbpi;
-      const int c_first = att_owner(first_b, ctas, total), c_last = att_owner(first_b + p.nbpi - 1, ctas, total);
-      const int nseg = c_last - c_first + 1, seg = static_cast<int>(blockIdx.x) - c_first;
+      const int nseg = p.segs, seg = item0 - cx.job * p.segs;  // (segs > 1: this CTA owns exactly one item)
       // statistics of the accumulator columns' beams
       float Mn[2] = {__shfl_sync(0xffffffffu, m_run, 8 * t), __shfl_sync(0xffffffffu, m_run, 8 * t + 4)};
       float Sn[2] = {__shfl_sync(0xffffffffu, s_run, 8 * t), __shfl_sync(0xffffffffu, s_run, 8 * t + 4)};
@@ -442,7 +445,7 @@ att_step_fwd_kernel(const __grid_constant__ CUtensorMap tmap_att, AttParams p) {
         // Every lane owns a private record of 1 + MT float4: (M0, M1, S0, S1) and its accumulators.
         constexpr int REC = 4 + 4 * MT;
         float4* rec = reinterpret_cast<float4*>(p.ws_partial) +
-                      (((static_cast<long long>(cx.job) * p.max_seg + seg) * ATT_WARPS + warp) * 32 + lane) * (REC / 4);
+                      (((static_cast<long long>(cx.job) * p.segs + seg) * ATT_WARPS + warp) * 32 + lane) * (REC / 4);
         if (n0 < NB) {
           rec[0] = make_float4(Mn[0], Mn[1], Sn[0], Sn[1]);
 #pragma unroll
@@ -461,7 +464,7 @@ att_step_fwd_kernel(const __grid_constant__ CUtensorMap tmap_att, AttParams p) {
         if (finish && n0 < NB) {
           __threadfence();
           const float4* base = reinterpret_cast<const float4*>(p.ws_partial) +
-                               ((static_cast<long long>(cx.job) * p.max_seg * ATT_WARPS + warp) * 32 + lane) * (REC / 4);
+                               ((static_cast<long long>(cx.job) * p.segs * ATT_WARPS + warp) * 32 + lane) * (REC / 4);
           const long long seg_stride = static_cast<long long>(ATT_WARPS) * 32 * (REC / 4);
           float mx0 = -INFINITY, mx1 = -INFINITY;
           for (int sgm = 0; sgm < nseg; ++sgm) {
@@ -565,7 +568,9 @@ att_step_fwd_kernel(const __grid_constant__ CUtensorMap tmap_att, AttParams p) {
       if (lane == 0) mbar_arrive_addr(bar_scored + sc.stage * 8);
       ATT_TRACE(2 + 4 * i);
     }
-    if (i > 0) context(i == nloc);  // batch i - 1: every warp scored it a whole batch ago, nobody waits
+    // batch i - 1: every warp scored it a whole batch ago, nobody waits (finishing it BEFORE scoring batch i was
+    // measured too: same time)
+    if (i > 0) context(i == nloc);
     ATT_TRACE(3 + 4 * i);
     if (i < nloc) {
       cx = sc;
@@ -584,8 +589,7 @@ static int beams_per_group(int beams) {
 }
 
 struct AttPlan {
-  int nb, groups, nbpi, ctas, max_seg, mt, f_bufs;
-  long long total;
+  int nb, groups, nbpi, ctas, segs, items, mt, f_bufs;
 };
 
 static AttPlan make_plan(int n_img, int beams, int L, int A, int H) {
@@ -593,13 +597,17 @@ static AttPlan make_plan(int n_img, int beams, int L, int A, int H) {
   pl.nb = beams_per_group(beams);
   pl.groups = (beams + pl.nb - 1) / pl.nb;
   pl.nbpi = (L + ATT_BATCH - 1) / ATT_BATCH;
-  pl.total = static_cast<long long>(n_img) * pl.groups * pl.nbpi;
+  const long long jobs = static_cast<long long>(n_img) * pl.groups;
   const int per_sm = ((A + 255) / 256 <= 2 && H <= 512) ? 2 : 1;  // matches the kernel's launch bounds
   const long long slots = 148LL * per_sm;
-  pl.ctas = static_cast<int>(pl.total < slots ? pl.total : slots);
-  const long long q = pl.total / pl.ctas;  // every range holds at least q >= 1 batches
-  long long ms = (pl.nbpi + q - 1) / q + 1;
-  pl.max_seg = static_cast<int>(ms > pl.nbpi ? pl.nbpi : ms);
+  // Whole jobs per CTA (no merging) unless that would leave more than half of the slots empty: then every job
+  // is cut into `segs` segments of whole batches, one CTA each.
+  long long segs = slots / (jobs > 0 ? jobs : 1);
+  segs = segs < 1 ? 1 : (segs > pl.nbpi ? pl.nbpi : segs);
+  pl.segs = static_cast<int>(segs);
+  const long long items = jobs * segs;
+  pl.items = static_cast<int>(items);
+  pl.ctas = static_cast<int>(items < slots ? items : slots);
   pl.mt = H <= 512 ? 4 : 8;
   pl.f_bufs = pl.nbpi == 1 ? 3 : 2;
   return pl;
@@ -609,7 +617,7 @@ long long att_step_workspace_bytes(int n_img, int beams, int L, int A, int H) {
   const AttPlan pl = make_plan(n_img, beams, L, A, H);
   const long long jobs = static_cast<long long>(n_img) * pl.groups;
   const long long counters = ((jobs * ATT_WARPS * 4 + 255) / 256) * 256;
-  return counters + jobs * pl.max_seg * ATT_WARPS * 32 * (4 + 4 * pl.mt) * 4;
+  return counters + (pl.segs > 1 ? jobs * pl.segs * ATT_WARPS * 32 * (4 + 4 * pl.mt) * 4 : 0);
 }
 
 template <int NB, int CA, int MT>
@@ -660,7 +668,7 @@ int att_step_fwd(const float* att_h, long long ld_att_h, const void* p_att, cons
     return set_error(UIC_ERR_ARG, "att_step_fwd: workspace of %lld bytes (16-byte aligned, zeroed once) required, got %lld", need,
                      workspace_bytes);
   const long long jobs = static_cast<long long>(n_img) * pl.groups;
-  if (pl.total > 0x7fffffffLL) return set_error(UIC_ERR_SHAPE, "att_step_fwd: too many region batches");
+  if (jobs * pl.nbpi > 0x7fffffffLL) return set_error(UIC_ERR_SHAPE, "att_step_fwd: too many region batches");
   AttParams p{};
   p.att_h = att_h;
   p.ld_att_h = ld_att_h;
@@ -682,8 +690,8 @@ int att_step_fwd(const float* att_h, long long ld_att_h, const void* p_att, cons
   p.H = H;
   p.n_grp = pl.groups;
   p.nbpi = pl.nbpi;
-  p.total_batches = static_cast<int>(pl.total);
-  p.max_seg = pl.max_seg;
+  p.segs = pl.segs;
+  p.items = pl.items;
   p.f_bufs = pl.f_bufs;
   p.trace = gemm_trace_buffer();
   const int ca = (A + 255) / 256;
