@@ -49,11 +49,13 @@ int uic_version(void);
 int64_t uic_launch_count(void);
 /* 0 = tcgen05 tensor-core GEMM (default), 1 = CUDA-core verification GEMM (tests/debug only). */
 int uic_set_gemm_impl(int impl);
-/* Debug aid: with a non-NULL device buffer of 128 int64, CTA (0,0) of every following GEMM launch
- * records clock64() at its pipeline events ([0] setup done, [1+kb] operands of k-block kb landed,
- * [50+kb] TMA for kb issued, [40] last MMA issued, [41] accumulator ready, [42] epilogue done,
- * [43]/[44] CTA exit/entry).  NULL turns it off. */
-int uic_gemm_set_trace(void* device_buffer_128_i64);
+/* Debug aid: with a non-NULL device buffer of 1024 int64, CTA 0 of every following GEMM launch records
+ * clock64() at its pipeline events ([0] setup done, [1+kb] operands of k-block kb landed, [50+kb] TMA for kb
+ * issued, [40] last MMA issued, [41] accumulator ready, [42] epilogue done) and CTA 0 of every attention
+ * launch the %globaltimer of its batch pipeline ([0] start, [1+4i..] batch i: data ready / scored / previous
+ * batch finished, [100] end); slots [128+2c], [129+2c] receive the %globaltimer at entry / exit of CTA c < 448
+ * of both kernels.  NULL turns it off. */
+int uic_gemm_set_trace(void* device_buffer_1024_i64);
 /* Live per-kernel device timing: while enabled, every launch is bracketed by a CUDA event pair on
  * its stream (do not enable during CUDA-graph capture).  uic_profile_dump synchronises, writes one
  * "name launches total_ms" line per kernel label into `out` (host buffer) and returns the number
@@ -166,6 +168,21 @@ int uic_beam_topk_merge(const float* stats, int parts, int kslots, float* topk_v
 /* Merges the parts of uic_logit_stats (kslots = 1): same bookkeeping as uic_greedy_step. */
 int uic_greedy_merge(const float* stats, int parts, int64_t* seq, float* seq_logprobs, uint8_t* unfinished, int64_t* next_tok,
                      int32_t* n_unfinished, int t, int seq_length, int rows, void* stream);
+
+/* The whole tail of a beam-search step in one launch: uic_beam_topk_merge + uic_beam_step and, when move_state != 0,
+ * uic_beam_gather + uic_embed_rows for the next step (x_dst[r, xt_col0 : xt_col0 + E] = emb_table[next_tok[r]]).
+ * Same results as the four separate calls; the candidate tables stay in shared memory.  beams <= kslots. */
+int uic_beam_advance(const float* stats, int parts, int kslots, int32_t* beam_seq, float* beam_lp, float* beam_sum,
+                     int32_t* done_seq, float* done_lp, double* done_p, float* done_unaug, int32_t* done_cnt,
+                     int32_t* parent_row, int64_t* next_tok, int t, int seq_length, int n_img, int beams, int flags,
+                     int move_state, const void* x_src, void* x_dst, int64_t ld_x, int col0_a, int ncol_a, int col0_b,
+                     int ncol_b, const float* c_src, float* c_dst, int n_state, int H, const void* emb_table_bf16,
+                     int64_t ld_table, int xt_col0, int E, int V, void* stream);
+/* Greedy analogue: uic_greedy_merge and, when x_xt_bf16 != NULL, the next step's embedding rows
+ * x_xt_bf16[r, 0:E] = emb_table[token r] (pitch ld_x), in one launch. */
+int uic_greedy_advance(const float* stats, int parts, int64_t* seq, float* seq_logprobs, uint8_t* unfinished, int64_t* next_tok,
+                       int32_t* n_unfinished, int t, int seq_length, int rows, const void* emb_table_bf16, int64_t ld_table,
+                       void* x_xt_bf16, int64_t ld_x, int E, int V, void* stream);
 
 /* One beam-search bookkeeping step for all images at once (models/CaptionModel.py:48-97,155-172):
  * merges the beams x k candidates of each image (c-major, q-minor stable order), forks the

@@ -11,7 +11,7 @@ from unpaired_image_captioning_b200 import _lib  # noqa: E402
 _lib.require_device()
 lib = _lib.load()
 SHAPES = [(768, 1024, 512), (768, 3072, 1024), (768, 10000, 512), (256, 10000, 512), (50176, 512, 2048), (8704, 10000, 512)]
-trace = torch.zeros(128, dtype=torch.int64, device="cuda")
+trace = torch.zeros(1024, dtype=torch.int64, device="cuda")
 for M, N, K in SHAPES:
     a = torch.randn(M, K, device="cuda").to(torch.bfloat16)
     b = (torch.randn(N, K, device="cuda") * 0.05).to(torch.bfloat16)

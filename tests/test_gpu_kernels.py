@@ -354,3 +354,82 @@ def test_greedy_merge_equals_greedy_step():
     assert torch.equal(a[0], b[0]) and torch.equal(a[2], b[2]) and torch.equal(a[3], b[3]) and torch.equal(a[4], b[4])
     assert 0 < int(a[4][0]) < R
     torch.testing.assert_close(a[1], b[1], rtol=1e-4, atol=2e-4)
+
+
+@pytest.mark.parametrize("B,b,kslots", [(5, 3, 3), (9, 2, 3), (4, 5, 5), (3, 8, 8), (7, 1, 1)])
+def test_beam_advance_equals_the_four_step_chain(B, b, kslots):
+    """uic_beam_advance == uic_beam_topk_merge + uic_beam_step + uic_beam_gather + uic_embed_rows, step by step."""
+    lib = _lib.load()
+    V, Hh, E, T = 300, 64, 32, 6
+    R = B * b
+    parts = lib.uic_logit_stats_parts(V)
+    es = lib.uic_logit_stats_entry_floats(kslots)
+    table = _rand_bf16(V, E, seed=3)
+    ld_x = E + 2 * Hh + 8
+    ga, na, gb, nb_ = E, Hh, E + Hh, Hh      # two state column ranges after the embedding columns
+
+    def state():
+        g = torch.Generator(device="cpu").manual_seed(11)
+        return {"beam_seq": torch.zeros(B, b, T, dtype=torch.int32, device=DEV), "beam_lp": torch.zeros(B, b, T, device=DEV),
+                "beam_sum": torch.zeros(B, b, device=DEV), "done_seq": torch.zeros(B, b, T, dtype=torch.int32, device=DEV),
+                "done_lp": torch.zeros(B, b, T, device=DEV), "done_p": torch.zeros(B, b, dtype=torch.float64, device=DEV),
+                "done_unaug": torch.zeros(B, b, device=DEV), "done_cnt": torch.zeros(B, dtype=torch.int32, device=DEV),
+                "parent": torch.zeros(R, dtype=torch.int32, device=DEV), "tok": torch.zeros(R, dtype=torch.int64, device=DEV),
+                "X": [torch.randn(R, ld_x, generator=g).to(DEV).to(torch.bfloat16), torch.zeros(R, ld_x, device=DEV, dtype=torch.bfloat16)],
+                "c": [torch.randn(2, R, Hh, generator=g).to(DEV), torch.zeros(2, R, Hh, device=DEV)]}
+
+    u, f = state(), state()
+    tkv, tki = torch.empty(R, b, device=DEV), torch.empty(R, b, dtype=torch.int32, device=DEV)
+    for t in range(T):
+        h, w, bias, _ = _stats_inputs(R, V, Hh, seed=40 + t)
+        bias[0] += 3.0                                   # some beams finish early
+        stats = torch.empty(R, parts, es, device=DEV)
+        check(lib.uic_logit_stats(ptr(h), Hh, ptr(w), Hh, ptr(bias), None, 0, ptr(stats), R, V, Hh, kslots, 1, stream()))
+        src, dst = t % 2, (t + 1) % 2
+        move = int(t + 1 < T)
+        # unfused chain
+        check(lib.uic_beam_topk_merge(ptr(stats), parts, kslots, ptr(tkv), ptr(tki), R, b, stream()))
+        check(lib.uic_beam_step(ptr(tkv), ptr(tki), ptr(u["beam_seq"]), ptr(u["beam_lp"]), ptr(u["beam_sum"]), ptr(u["done_seq"]),
+                                ptr(u["done_lp"]), ptr(u["done_p"]), ptr(u["done_unaug"]), ptr(u["done_cnt"]), ptr(u["parent"]),
+                                ptr(u["tok"]), t, T, B, b, 0, stream()))
+        if move:
+            check(lib.uic_beam_gather(ptr(u["parent"]), ptr(u["X"][src]), ptr(u["X"][dst]), ld_x, ga, na, gb, nb_, ptr(u["c"][src]),
+                                      ptr(u["c"][dst]), 2, R, Hh, stream()))
+            check(lib.uic_embed_rows(ptr(table), E, ptr(u["tok"]), ptr(u["X"][dst]), ld_x, R, E, V, stream()))
+        # fused
+        check(lib.uic_beam_advance(ptr(stats), parts, kslots, ptr(f["beam_seq"]), ptr(f["beam_lp"]), ptr(f["beam_sum"]),
+                                   ptr(f["done_seq"]), ptr(f["done_lp"]), ptr(f["done_p"]), ptr(f["done_unaug"]), ptr(f["done_cnt"]),
+                                   ptr(f["parent"]), ptr(f["tok"]), t, T, B, b, 0, move, ptr(f["X"][src]), ptr(f["X"][dst]), ld_x,
+                                   ga, na, gb, nb_, ptr(f["c"][src]), ptr(f["c"][dst]), 2, Hh, ptr(table), E, 0, E, V, stream()))
+        for k in ("beam_seq", "beam_lp", "beam_sum", "done_seq", "done_lp", "done_p", "done_unaug", "done_cnt", "parent", "tok"):
+            assert torch.equal(u[k], f[k]), (k, t)
+        if move:
+            assert torch.equal(u["X"][dst][:, :E + 2 * Hh], f["X"][dst][:, :E + 2 * Hh]) and torch.equal(u["c"][dst], f["c"][dst])
+    assert int(u["done_cnt"].sum()) > 0
+
+
+def test_greedy_advance_equals_merge_plus_embed():
+    lib = _lib.load()
+    R, V, H, T, E = 70, 1000, 128, 4, 48
+    parts = lib.uic_logit_stats_parts(V)
+    stats = torch.empty(R, parts, 4, device=DEV)
+    table = _rand_bf16(V, E, seed=9)
+
+    def state():
+        return (torch.zeros(R, T, dtype=torch.int64, device=DEV), torch.zeros(R, T, device=DEV),
+                torch.zeros(R, dtype=torch.uint8, device=DEV), torch.zeros(R, dtype=torch.int64, device=DEV),
+                torch.zeros(T, dtype=torch.int32, device=DEV), torch.zeros(R, E + 16, device=DEV, dtype=torch.bfloat16))
+
+    a, b = state(), state()
+    for t in range(3):
+        h, w = _rand_bf16(R, H, seed=10 + t), _rand_bf16(V, H, seed=20 + t, scale=0.05)
+        bias = torch.randn(V, device=DEV) * 0.1
+        bias[0] += 3.0
+        check(lib.uic_logit_stats(ptr(h), H, ptr(w), H, ptr(bias), None, 0, ptr(stats), R, V, H, 1, 0, stream()))
+        check(lib.uic_greedy_merge(ptr(stats), parts, ptr(a[0]), ptr(a[1]), ptr(a[2]), ptr(a[3]), ptr(a[4]), t, T, R, stream()))
+        check(lib.uic_embed_rows(ptr(table), E, ptr(a[3]), ptr(a[5][:, 8:]), E + 16, R, E, V, stream()))
+        check(lib.uic_greedy_advance(ptr(stats), parts, ptr(b[0]), ptr(b[1]), ptr(b[2]), ptr(b[3]), ptr(b[4]), t, T, R, ptr(table), E,
+                                     ptr(b[5][:, 8:]), E + 16, E, V, stream()))
+        for x, y in zip(a, b):
+            assert torch.equal(x, y)
+    assert 0 < int(a[4][0]) < R

@@ -198,8 +198,8 @@ int uic_set_gemm_impl(int impl) {
   g_gemm_impl.store(impl);
   return 0;
 }
-int uic_gemm_set_trace(void* device_buffer_128_i64) {
-  g_gemm_trace.store(static_cast<long long*>(device_buffer_128_i64));
+int uic_gemm_set_trace(void* device_buffer_1024_i64) {
+  g_gemm_trace.store(static_cast<long long*>(device_buffer_1024_i64));
   return 0;
 }
 
@@ -371,6 +371,41 @@ int uic_row_topk(const float* logits, int64_t ld, const int64_t* prev_tok, float
   REQUIRE(!(flags & UIC_SAMPLE_DECODING_CONSTRAINT) || prev_tok, UIC_ERR_ARG, "uic_row_topk: constraint needs prev_tok");
   if (rows == 0) return 0;
   return row_topk(logits, ld, prev_tok, topk_val, topk_idx, rows, V, k, flags, ST(stream));
+}
+
+int uic_beam_advance(const float* stats, int parts, int kslots, int32_t* beam_seq, float* beam_lp, float* beam_sum,
+                     int32_t* done_seq, float* done_lp, double* done_p, float* done_unaug, int32_t* done_cnt,
+                     int32_t* parent_row, int64_t* next_tok, int t, int seq_length, int n_img, int beams, int flags,
+                     int move_state, const void* x_src, void* x_dst, int64_t ld_x, int col0_a, int ncol_a, int col0_b,
+                     int ncol_b, const float* c_src, float* c_dst, int n_state, int H, const void* emb_table_bf16,
+                     int64_t ld_table, int xt_col0, int E, int V, void* stream) {
+  REQUIRE(stats && beam_seq && beam_lp && beam_sum && done_seq && done_lp && done_p && done_unaug && done_cnt && parent_row && next_tok,
+          UIC_ERR_ARG, "uic_beam_advance: null pointer");
+  REQUIRE(parts > 0 && beams > 0 && seq_length > 0 && t >= 0 && t < seq_length, UIC_ERR_SHAPE,
+          "uic_beam_advance: parts=%d beams=%d t=%d seq_length=%d", parts, beams, t, seq_length);
+  REQUIRE((reinterpret_cast<uintptr_t>(stats) & 15) == 0, UIC_ERR_ALIGN, "uic_beam_advance: stats must be 16-byte aligned");
+  if (move_state) {
+    REQUIRE(x_src && x_dst && emb_table_bf16 && (n_state == 0 || (c_src && c_dst)), UIC_ERR_ARG, "uic_beam_advance: null state buffer");
+    REQUIRE(x_src != x_dst && c_src != c_dst, UIC_ERR_ARG, "uic_beam_advance: the state must move between two different buffers");
+    REQUIRE(E > 0 && V > 0 && H > 0 && ncol_a >= 0 && ncol_b >= 0, UIC_ERR_SHAPE, "uic_beam_advance: bad state shape");
+  }
+  if (n_img == 0) return 0;
+  return beam_advance(stats, parts, kslots, beam_seq, beam_lp, beam_sum, done_seq, done_lp, done_p, done_unaug, done_cnt, parent_row,
+                      next_tok, t, seq_length, n_img, beams, flags, move_state, x_src, x_dst, ld_x, col0_a, ncol_a, col0_b, ncol_b,
+                      c_src, c_dst, n_state, H, emb_table_bf16, ld_table, xt_col0, E, V, ST(stream));
+}
+
+int uic_greedy_advance(const float* stats, int parts, int64_t* seq, float* seq_logprobs, uint8_t* unfinished, int64_t* next_tok,
+                       int32_t* n_unfinished, int t, int seq_length, int rows, const void* emb_table_bf16, int64_t ld_table,
+                       void* x_xt_bf16, int64_t ld_x, int E, int V, void* stream) {
+  REQUIRE(stats && seq && seq_logprobs && unfinished && next_tok && n_unfinished, UIC_ERR_ARG, "uic_greedy_advance: null pointer");
+  REQUIRE(parts > 0 && seq_length > 0 && t >= 0 && t < seq_length, UIC_ERR_SHAPE, "uic_greedy_advance: parts=%d t=%d seq_length=%d",
+          parts, t, seq_length);
+  REQUIRE((reinterpret_cast<uintptr_t>(stats) & 15) == 0, UIC_ERR_ALIGN, "uic_greedy_advance: stats must be 16-byte aligned");
+  REQUIRE(x_xt_bf16 == nullptr || (emb_table_bf16 && E > 0 && V > 0), UIC_ERR_ARG, "uic_greedy_advance: embedding table missing");
+  if (rows == 0) return 0;
+  return greedy_advance(stats, parts, seq, seq_logprobs, unfinished, next_tok, n_unfinished, t, seq_length, rows, emb_table_bf16,
+                        ld_table, x_xt_bf16, ld_x, E, V, ST(stream));
 }
 
 int uic_beam_step(const float* topk_val, const int32_t* topk_idx, int32_t* beam_seq, float* beam_lp, float* beam_sum,

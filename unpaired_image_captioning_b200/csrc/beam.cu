@@ -15,6 +15,7 @@
 //     truncated to `beams` entries (:175): running insertion is equivalent to the final stable sort.
 #include "uic_internal.h"
 #include "uic_ptx.cuh"
+#include "uic_vocab.cuh"
 
 namespace uic {
 
@@ -22,19 +23,18 @@ constexpr int BEAM_MAX = 16;
 constexpr int BEAM_T_MAX = 64;
 constexpr int CAND_PER_LANE = BEAM_MAX * BEAM_MAX / 32;
 
-__global__ void __launch_bounds__(32) beam_step_kernel(const float* __restrict__ topk_val, const int32_t* __restrict__ topk_idx,
-                                                       int32_t* __restrict__ beam_seq, float* __restrict__ beam_lp,
-                                                       float* __restrict__ beam_sum, int32_t* __restrict__ done_seq,
-                                                       float* __restrict__ done_lp, double* __restrict__ done_p,
-                                                       float* __restrict__ done_unaug, int32_t* __restrict__ done_cnt,
-                                                       int32_t* __restrict__ parent_row, int64_t* __restrict__ next_tok, int t,
-                                                       int T, int b, int flags) {
+// One image, one warp.  tkv / tki: the image's (beams x beams) candidate tables [q * b + c] (global or shared).
+__device__ __forceinline__ void beam_step_image(const float* tkv, const int32_t* tki, int32_t* __restrict__ beam_seq,
+                                                float* __restrict__ beam_lp, float* __restrict__ beam_sum,
+                                                int32_t* __restrict__ done_seq, float* __restrict__ done_lp,
+                                                double* __restrict__ done_p, float* __restrict__ done_unaug,
+                                                int32_t* __restrict__ done_cnt, int32_t* __restrict__ parent_row,
+                                                int64_t* __restrict__ next_tok, int img, int t, int T, int b, int flags) {
   __shared__ int32_t s_seq[BEAM_MAX * BEAM_T_MAX];
   __shared__ float s_lp[BEAM_MAX * BEAM_T_MAX];
   __shared__ int s_q[BEAM_MAX], s_tok[BEAM_MAX];
   __shared__ float s_p[BEAM_MAX], s_r[BEAM_MAX];
-  const int img = blockIdx.x;
-  const int lane = threadIdx.x;
+  const int lane = threadIdx.x & 31;
   const long long row0 = static_cast<long long>(img) * b;
   int32_t* seq_img = beam_seq + row0 * T;
   float* lp_img = beam_lp + row0 * T;
@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(32) beam_step_kernel(const float* __restrict__
     cp[i] = -INFINITY;
     if (!used[i]) {
       const int c = n / rows, q = n - c * rows;
-      cp[i] = sum_img[q] + topk_val[(row0 + q) * b + c];
+      cp[i] = sum_img[q] + tkv[q * b + c];
     }
   }
   // ---- stable top-`b` selection: b rounds of warp arg-max, ties -> smaller candidate number ----
@@ -83,8 +83,8 @@ __global__ void __launch_bounds__(32) beam_step_kernel(const float* __restrict__
       const int c = bn / rows, q = bn - c * rows;
       s_q[vix] = q;
       s_p[vix] = bv;
-      s_tok[vix] = topk_idx[(row0 + q) * b + c];
-      s_r[vix] = topk_val[(row0 + q) * b + c];
+      s_tok[vix] = tki[q * b + c];
+      s_r[vix] = tkv[q * b + c];
     }
   }
   // ---- fork the tables: stage the old prefixes, then write parents' prefixes + the new token ----
@@ -152,6 +152,18 @@ __global__ void __launch_bounds__(32) beam_step_kernel(const float* __restrict__
   if (lane == 0) done_cnt[img] = cnt;
 }
 
+__global__ void __launch_bounds__(32) beam_step_kernel(const float* __restrict__ topk_val, const int32_t* __restrict__ topk_idx,
+                                                       int32_t* __restrict__ beam_seq, float* __restrict__ beam_lp,
+                                                       float* __restrict__ beam_sum, int32_t* __restrict__ done_seq,
+                                                       float* __restrict__ done_lp, double* __restrict__ done_p,
+                                                       float* __restrict__ done_unaug, int32_t* __restrict__ done_cnt,
+                                                       int32_t* __restrict__ parent_row, int64_t* __restrict__ next_tok, int t,
+                                                       int T, int b, int flags) {
+  const long long off = static_cast<long long>(blockIdx.x) * b * b;
+  beam_step_image(topk_val + off, topk_idx + off, beam_seq, beam_lp, beam_sum, done_seq, done_lp, done_p, done_unaug, done_cnt,
+                  parent_row, next_tok, blockIdx.x, t, T, b, flags);
+}
+
 int beam_step(const float* topk_val, const int32_t* topk_idx, int32_t* beam_seq, float* beam_lp, float* beam_sum,
               int32_t* done_seq, float* done_lp, double* done_p, float* done_unaug, int32_t* done_cnt, int32_t* parent_row,
               int64_t* next_tok, int t, int seq_length, int n_img, int beams, int flags, cudaStream_t stream) {
@@ -160,6 +172,168 @@ int beam_step(const float* topk_val, const int32_t* topk_idx, int32_t* beam_seq,
   launch_begin("beam_step", stream);
   beam_step_kernel<<<n_img, 32, 0, stream>>>(topk_val, topk_idx, beam_seq, beam_lp, beam_sum, done_seq, done_lp, done_p,
                                              done_unaug, done_cnt, parent_row, next_tok, t, seq_length, beams, flags);
+  UIC_CUDA_OK(cudaGetLastError());
+  launch_end(stream);
+  return 0;
+}
+
+// ---- fused step tail of the sampling loops ------------------------------------------------------------------------
+// Everything between the statistics GEMM of step t and the gate GEMM of step t + 1 in ONE launch per step (it was
+// four: uic_beam_topk_merge, uic_beam_step, uic_beam_gather, uic_embed_rows -- each a few microseconds of launch
+// latency and dependent-kernel gap on a 130 us step).  One CTA of four warps per image:
+//   1. warps merge the statistics parts of the image's beam rows into their top-`beams` candidates (shared memory);
+//   2. warp 0 runs the beam bookkeeping above on them;
+//   3. all warps move the recurrent state of the chosen parents into the other state buffer and write the next
+//      step's word embeddings next to it.
+struct AdvanceIO {
+  // state re-ordering (uic_beam_gather): two column ranges of the bf16 activation matrix + n_state fp32 matrices
+  const __nv_bfloat16* x_src;
+  __nv_bfloat16* x_dst;
+  long long ld_x;
+  int col0_a, ncol_a, col0_b, ncol_b;
+  const float* c_src;
+  float* c_dst;
+  int n_state, rows, H;
+  // next input (uic_embed_rows): x_dst[r, xt_col0 : xt_col0 + E] = table[tok[r]]
+  const __nv_bfloat16* table;
+  long long ld_table;
+  int xt_col0, E, V;
+};
+
+__device__ __forceinline__ void copy_row_bf16(__nv_bfloat16* dst, const __nv_bfloat16* src, int n, int tid, int nthreads) {
+  if (((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src)) & 15) == 0 && (n & 7) == 0) {
+    for (int c = tid; c < n / 8; c += nthreads) reinterpret_cast<uint4*>(dst)[c] = reinterpret_cast<const uint4*>(src)[c];
+  } else {
+    for (int c = tid; c < n; c += nthreads) dst[c] = src[c];
+  }
+}
+__device__ __forceinline__ void copy_row_f32(float* dst, const float* src, int n, int tid, int nthreads) {
+  if (((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src)) & 15) == 0 && (n & 3) == 0) {
+    for (int c = tid; c < n / 4; c += nthreads) reinterpret_cast<float4*>(dst)[c] = reinterpret_cast<const float4*>(src)[c];
+  } else {
+    for (int c = tid; c < n; c += nthreads) dst[c] = src[c];
+  }
+}
+
+constexpr int ADV_THREADS = 128;
+
+template <int KS>
+__global__ void __launch_bounds__(ADV_THREADS) beam_advance_kernel(const float* __restrict__ stats, int parts,
+                                                                    int32_t* __restrict__ beam_seq, float* __restrict__ beam_lp,
+                                                                    float* __restrict__ beam_sum, int32_t* __restrict__ done_seq,
+                                                                    float* __restrict__ done_lp, double* __restrict__ done_p,
+                                                                    float* __restrict__ done_unaug, int32_t* __restrict__ done_cnt,
+                                                                    int32_t* __restrict__ parent_row, int64_t* __restrict__ next_tok,
+                                                                    int t, int T, int b, int flags, int move_state, AdvanceIO io) {
+  __shared__ float s_tkv[KS * KS];
+  __shared__ int32_t s_tki[KS * KS];
+  constexpr int ES = (2 + 2 * KS + 3) / 4 * 4;
+  const int img = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long long row0 = static_cast<long long>(img) * b;
+  // 1. candidates of every beam row: ys[q, c] = log-prob of the c-th best column after the beam-search edits
+  for (int q = warp; q < b; q += ADV_THREADS / 32) {
+    float kv[KS];
+    int ki[KS];
+    const RowStats rs = merge_row_stats<KS>(stats + (row0 + q) * parts * ES, parts, kv, ki);
+    for (int c = 0; c < b; ++c) {
+      const Best best = warp_pop_best<KS>(kv, ki);
+      if (lane == 0) {
+        s_tkv[q * b + c] = (best.v - rs.M) - rs.log_s;
+        s_tki[q * b + c] = best.i;
+      }
+    }
+  }
+  __syncthreads();
+  // 2. beam bookkeeping
+  if (warp == 0)
+    beam_step_image(s_tkv, s_tki, beam_seq, beam_lp, beam_sum, done_seq, done_lp, done_p, done_unaug, done_cnt, parent_row,
+                    next_tok, img, t, T, b, flags);
+  if (!move_state) return;
+  __syncthreads();
+  // 3. state of the parents + next embeddings into the other buffer
+  for (int v = 0; v < b; ++v) {
+    const long long r = row0 + v;
+    const long long q = parent_row[r];
+    copy_row_bf16(io.x_dst + r * io.ld_x + io.col0_a, io.x_src + q * io.ld_x + io.col0_a, io.ncol_a, threadIdx.x, ADV_THREADS);
+    copy_row_bf16(io.x_dst + r * io.ld_x + io.col0_b, io.x_src + q * io.ld_x + io.col0_b, io.ncol_b, threadIdx.x, ADV_THREADS);
+    for (int s = 0; s < io.n_state; ++s)
+      copy_row_f32(io.c_dst + (static_cast<long long>(s) * io.rows + r) * io.H, io.c_src + (static_cast<long long>(s) * io.rows + q) * io.H,
+                   io.H, threadIdx.x, ADV_THREADS);
+    long long tk = next_tok[r];
+    tk = tk < 0 ? 0 : (tk >= io.V ? io.V - 1 : tk);
+    copy_row_bf16(io.x_dst + r * io.ld_x + io.xt_col0, io.table + tk * io.ld_table, io.E, threadIdx.x, ADV_THREADS);
+  }
+}
+
+int beam_advance(const float* stats, int parts, int kslots, int32_t* beam_seq, float* beam_lp, float* beam_sum, int32_t* done_seq,
+                 float* done_lp, double* done_p, float* done_unaug, int32_t* done_cnt, int32_t* parent_row, int64_t* next_tok, int t,
+                 int seq_length, int n_img, int beams, int flags, int move_state, const void* x_src, void* x_dst, long long ld_x,
+                 int col0_a, int ncol_a, int col0_b, int ncol_b, const float* c_src, float* c_dst, int n_state, int H,
+                 const void* table, long long ld_table, int xt_col0, int E, int V, cudaStream_t stream) {
+  if (beams > kslots || seq_length > BEAM_T_MAX)
+    return set_error(UIC_ERR_SHAPE, "beam_advance: beams=%d (kslots %d), seq_length=%d (max %d)", beams, kslots, seq_length, BEAM_T_MAX);
+  AdvanceIO io{static_cast<const __nv_bfloat16*>(x_src), static_cast<__nv_bfloat16*>(x_dst), ld_x, col0_a, ncol_a, col0_b, ncol_b,
+               c_src, c_dst, n_state, n_img * beams, H, static_cast<const __nv_bfloat16*>(table), ld_table, xt_col0, E, V};
+  launch_begin("beam_advance", stream);
+#define UIC_ADV(KS_)                                                                                                         \
+  beam_advance_kernel<KS_><<<n_img, ADV_THREADS, 0, stream>>>(stats, parts, beam_seq, beam_lp, beam_sum, done_seq, done_lp, done_p, \
+                                                              done_unaug, done_cnt, parent_row, next_tok, t, seq_length, beams,     \
+                                                              flags, move_state, io)
+  if (kslots == 1)
+    UIC_ADV(1);
+  else if (kslots == 3)
+    UIC_ADV(3);
+  else if (kslots == 5)
+    UIC_ADV(5);
+  else if (kslots == 8)
+    UIC_ADV(8);
+  else
+    return set_error(UIC_ERR_ARG, "beam_advance: kslots must be 1, 3, 5 or 8");
+#undef UIC_ADV
+  UIC_CUDA_OK(cudaGetLastError());
+  launch_end(stream);
+  return 0;
+}
+
+// Greedy analogue: uic_greedy_merge + uic_embed_rows of the next step in one launch (one warp per row).
+__global__ void __launch_bounds__(ADV_THREADS) greedy_advance_kernel(const float* __restrict__ stats, int parts,
+                                                                      int64_t* __restrict__ seq, float* __restrict__ seq_lp,
+                                                                      uint8_t* __restrict__ unfinished, int64_t* __restrict__ next_tok,
+                                                                      int32_t* __restrict__ n_unfinished, int t, int T, int rows,
+                                                                      const __nv_bfloat16* __restrict__ table, long long ld_table,
+                                                                      __nv_bfloat16* __restrict__ x, long long ld_x, int E, int V) {
+  if (t > 0 && n_unfinished[t - 1] == 0) return;  // the reference has left its loop (AttModel.py:250-251)
+  const int r = blockIdx.x * (ADV_THREADS / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (r >= rows) return;
+  float kv[1];
+  int ki[1];
+  const RowStats rs = merge_row_stats<1>(stats + static_cast<long long>(r) * parts * 4, parts, kv, ki);
+  const Best best = warp_pop_best<1>(kv, ki);
+  long long it = best.i;
+  const bool u = (t == 0 ? true : unfinished[r] != 0) && it > 0;
+  it = u ? it : 0;
+  __syncwarp();
+  if (lane == 0) {
+    seq[static_cast<long long>(r) * T + t] = it;
+    seq_lp[static_cast<long long>(r) * T + t] = (best.v - rs.M) - rs.log_s;
+    unfinished[r] = u ? 1 : 0;
+    next_tok[r] = it;
+    if (u) atomicAdd(&n_unfinished[t], 1);
+  }
+  if (x != nullptr) {
+    const long long tk = it >= V ? V - 1 : it;
+    copy_row_bf16(x + static_cast<long long>(r) * ld_x, table + tk * ld_table, E, lane, 32);
+  }
+}
+
+int greedy_advance(const float* stats, int parts, int64_t* seq, float* seq_lp, uint8_t* unfinished, int64_t* next_tok,
+                   int32_t* n_unfinished, int t, int seq_length, int rows, const void* table, long long ld_table, void* x_xt,
+                   long long ld_x, int E, int V, cudaStream_t stream) {
+  const int per = ADV_THREADS / 32;
+  launch_begin("greedy_advance", stream);
+  greedy_advance_kernel<<<(rows + per - 1) / per, ADV_THREADS, 0, stream>>>(stats, parts, seq, seq_lp, unfinished, next_tok, n_unfinished,
+                                                                           t, seq_length, rows, static_cast<const __nv_bfloat16*>(table),
+                                                                           ld_table, static_cast<__nv_bfloat16*>(x_xt), ld_x, E, V);
   UIC_CUDA_OK(cudaGetLastError());
   launch_end(stream);
   return 0;

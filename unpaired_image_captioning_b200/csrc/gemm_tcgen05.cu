@@ -148,6 +148,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  if (ep.trace != nullptr && threadIdx.x == 0 && blockIdx.x < 448) {  // (1024-slot debug buffer) CTA entry time
+    long long tnow;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tnow));
+    ep.trace[128 + 2 * blockIdx.x] = tnow;
+  }
   const int num_kb = (K + BK - 1) / BK;
   const int tiles_m = (M + BM - 1) / BM;
   const int tiles_n = (N + BN - 1) / BN;
@@ -472,6 +477,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   tcgen05_fence_before();
   __syncthreads();
   if (warp == 2) tmem_dealloc(tmem_base, 2 * BN);
+  if (ep.trace != nullptr && threadIdx.x == 0 && blockIdx.x < 448) {  // CTA exit time
+    long long tnow;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tnow));
+    ep.trace[129 + 2 * blockIdx.x] = tnow;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------

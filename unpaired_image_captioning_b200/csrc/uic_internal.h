@@ -69,6 +69,14 @@ int row_topk(const float* logits, long long ld, const int64_t* prev_tok, float* 
 int beam_step(const float* topk_val, const int32_t* topk_idx, int32_t* beam_seq, float* beam_lp, float* beam_sum,
               int32_t* done_seq, float* done_lp, double* done_p, float* done_unaug, int32_t* done_cnt, int32_t* parent_row,
               int64_t* next_tok, int t, int seq_length, int n_img, int beams, int flags, cudaStream_t stream);
+int beam_advance(const float* stats, int parts, int kslots, int32_t* beam_seq, float* beam_lp, float* beam_sum, int32_t* done_seq,
+                 float* done_lp, double* done_p, float* done_unaug, int32_t* done_cnt, int32_t* parent_row, int64_t* next_tok, int t,
+                 int seq_length, int n_img, int beams, int flags, int move_state, const void* x_src, void* x_dst, long long ld_x,
+                 int col0_a, int ncol_a, int col0_b, int ncol_b, const float* c_src, float* c_dst, int n_state, int H,
+                 const void* table, long long ld_table, int xt_col0, int E, int V, cudaStream_t stream);
+int greedy_advance(const float* stats, int parts, int64_t* seq, float* seq_lp, uint8_t* unfinished, int64_t* next_tok,
+                   int32_t* n_unfinished, int t, int seq_length, int rows, const void* table, long long ld_table, void* x_xt,
+                   long long ld_x, int E, int V, cudaStream_t stream);
 int beam_gather(const int32_t* parent_row, const void* x_src, void* x_dst, long long ld_x, int col0_a, int ncol_a, int col0_b,
                 int ncol_b, const float* c_src, float* c_dst, int n_state, int rows, int H, cudaStream_t stream);
 

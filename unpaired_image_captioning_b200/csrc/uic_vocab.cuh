@@ -1,0 +1,122 @@
+// Device helpers shared by the vocabulary kernels (vocab.cu) and the fused beam / greedy advance kernels
+// (beam.cu): running (max, sum-exp) pairs, ordered candidates and the merge of the statistics written by the
+// logit GEMM's STATS epilogue (gemm_tcgen05.cu).
+#pragma once
+#include "uic_internal.h"
+
+namespace uic {
+
+struct MaxSum {
+  float m, s;
+};
+__device__ __forceinline__ MaxSum ms_merge(MaxSum a, MaxSum b) {
+  MaxSum r;
+  r.m = fmaxf(a.m, b.m);
+  if (r.m == -INFINITY) {
+    r.s = 0.0f;
+    return r;
+  }
+  r.s = a.s * __expf(a.m - r.m) + b.s * __expf(b.m - r.m);
+  return r;
+}
+struct Best {
+  float v;
+  int i;
+};
+__device__ __forceinline__ bool better(float v, int i, const Best& b) { return v > b.v || (v == b.v && i < b.i); }
+
+// ---- merges of the fused logit statistics (gemm_tcgen05.cu, STATS epilogue) ----------------------------------
+// stats[row][part][ES] with ES = logit_stats_entry_floats(KS): (max, sum exp, KS keys, KS columns, padding).
+// One warp per row; lanes read consecutive parts with 16-byte loads.
+constexpr int MERGE_ROWS_PER_CTA = 4;  // rows (warps) per CTA of the stand-alone merge kernels
+
+struct RowStats {
+  float M, log_s;
+};
+
+// Merges the (max, sum exp) pairs of a row and leaves each lane with the best KS candidates of its share of
+// the parts (sorted by key descending, smaller column first on ties).
+template <int KS>
+__device__ __forceinline__ RowStats merge_row_stats(const float* __restrict__ st, int parts, float (&kv)[KS], int (&ki)[KS]) {
+  constexpr int EMPTY = 0x7fffffff;
+  constexpr int ES = (2 + 2 * KS + 3) / 4 * 4;
+  const int lane = threadIdx.x & 31;
+  MaxSum a{-INFINITY, 0.0f};
+#pragma unroll
+  for (int q = 0; q < KS; ++q) {
+    kv[q] = -INFINITY;
+    ki[q] = EMPTY;
+  }
+  const float4* base = reinterpret_cast<const float4*>(st);
+  float4 nxt[ES / 4];
+  if (lane < parts) {
+#pragma unroll
+    for (int w = 0; w < ES / 4; ++w) nxt[w] = base[static_cast<long long>(lane) * (ES / 4) + w];
+  }
+  for (int p = lane; p < parts; p += 32) {
+    float e[ES];
+#pragma unroll
+    for (int w = 0; w < ES / 4; ++w) {
+      e[4 * w] = nxt[w].x;
+      e[4 * w + 1] = nxt[w].y;
+      e[4 * w + 2] = nxt[w].z;
+      e[4 * w + 3] = nxt[w].w;
+    }
+    if (p + 32 < parts) {  // the next entry's loads fly while this one is merged
+#pragma unroll
+      for (int w = 0; w < ES / 4; ++w) nxt[w] = base[static_cast<long long>(p + 32) * (ES / 4) + w];
+    }
+    a = ms_merge(a, MaxSum{e[0], e[1]});
+#pragma unroll
+    for (int c = 0; c < KS; ++c) {
+      const float x = e[2 + c];
+      const int col = __float_as_int(e[2 + KS + c]);
+      bool pr[KS];
+#pragma unroll
+      for (int q = 0; q < KS; ++q) pr[q] = col != EMPTY && (x > kv[q] || (x == kv[q] && col < ki[q]));
+#pragma unroll
+      for (int q = KS - 1; q > 0; --q) {
+        kv[q] = pr[q - 1] ? kv[q - 1] : (pr[q] ? x : kv[q]);
+        ki[q] = pr[q - 1] ? ki[q - 1] : (pr[q] ? col : ki[q]);
+      }
+      kv[0] = pr[0] ? x : kv[0];
+      ki[0] = pr[0] ? col : ki[0];
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    MaxSum other;
+    other.m = __shfl_xor_sync(0xffffffffu, a.m, o);
+    other.s = __shfl_xor_sync(0xffffffffu, a.s, o);
+    a = ms_merge(a, other);
+  }
+  return RowStats{a.m, logf(a.s)};
+}
+
+// Pops the globally best remaining candidate of the warp (every lane holds a sorted list).
+template <int KS>
+__device__ __forceinline__ Best warp_pop_best(float (&kv)[KS], int (&ki)[KS]) {
+  constexpr int EMPTY = 0x7fffffff;
+  Best b{kv[0], ki[0]};
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, b.v, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, b.i, o);
+    if (oi != EMPTY && (b.i == EMPTY || better(ov, oi, b))) {
+      b.v = ov;
+      b.i = oi;
+    }
+  }
+  if (ki[0] == b.i && b.i != EMPTY) {  // the owner shifts its list up
+#pragma unroll
+    for (int q = 0; q + 1 < KS; ++q) {
+      kv[q] = kv[q + 1];
+      ki[q] = ki[q + 1];
+    }
+    kv[KS - 1] = -INFINITY;
+    ki[KS - 1] = EMPTY;
+  }
+  return b;
+}
+
+}  // namespace uic

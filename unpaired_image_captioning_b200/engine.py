@@ -259,8 +259,11 @@ class DecoderEngine:
                     banned = s["seq"][:, t - 1:] if (flags and t > 0) else None
                     check(lib.uic_logit_stats(ptr(h), h.stride(0), ptr(w.w_logit), w.H, ptr(w.b_logit), ptr(banned), T,
                                               ptr(s["stats"]), B, w.V, w.H, 1, 0, stream()))
-                    check(lib.uic_greedy_merge(ptr(s["stats"]), s["parts"], ptr(s["seq"]), ptr(s["lp"]), ptr(s["unf"]), ptr(s["tok"]),
-                                               ptr(s["nunf"]), t, T, B, stream()))
+                    # merge of the parts + the next step's embedding rows in one launch
+                    xt = X[:, sl.xt[0]:] if t + 1 < T else None
+                    check(lib.uic_greedy_advance(ptr(s["stats"]), s["parts"], ptr(s["seq"]), ptr(s["lp"]), ptr(s["unf"]), ptr(s["tok"]),
+                                                 ptr(s["nunf"]), t, T, B, ptr(w.emb_relu), w.E, ptr(xt), X.stride(0), w.E, w.V, stream()))
+                    continue
                 else:
                     self.logits_of(h, ws["logits"])
                     check(lib.uic_greedy_step(ptr(ws["logits"]), w.V, ptr(s["seq"]), ptr(s["lp"]), ptr(s["unf"]), ptr(s["tok"]),
@@ -319,8 +322,13 @@ class DecoderEngine:
                     banned = s["tok"] if (tk_flags and t > 0) else None
                     check(lib.uic_logit_stats(ptr(h), h.stride(0), ptr(w.w_logit), w.H, ptr(w.b_logit), ptr(banned), 1,
                                               ptr(s["stats"]), R, w.V, w.H, s["kslots"], 1, stream()))
-                    check(lib.uic_beam_topk_merge(ptr(s["stats"]), s["parts"], s["kslots"], ptr(s["tk_val"]), ptr(s["tk_idx"]), R, b,
-                                                  stream()))
+                    # merge + beam bookkeeping + state re-ordering + next embeddings in one launch
+                    check(lib.uic_beam_advance(ptr(s["stats"]), s["parts"], s["kslots"], ptr(s["beam_seq"]), ptr(s["beam_lp"]),
+                                               ptr(s["beam_sum"]), ptr(s["done_seq"]), ptr(s["done_lp"]), ptr(s["done_p"]),
+                                               ptr(s["done_unaug"]), ptr(s["done_cnt"]), ptr(s["parent"]), ptr(s["tok"]), t, T, B, b,
+                                               bs_flags, int(t + 1 < T), ptr(X), ptr(Xn), X.stride(0), ga, na, gb, nb, ptr(c), ptr(cn),
+                                               sl.n_state, w.H, ptr(w.emb_relu), w.E, sl.xt[0], w.E, w.V, stream()))
+                    continue
                 else:
                     self.logits_of(h, ws["logits"])
                     check(lib.uic_row_topk(ptr(ws["logits"]), w.V, ptr(s["tok"]) if (tk_flags and t > 0) else None, ptr(s["tk_val"]),
