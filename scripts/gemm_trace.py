@@ -11,6 +11,8 @@ from unpaired_image_captioning_b200 import _lib  # noqa: E402
 _lib.require_device()
 lib = _lib.load()
 SHAPES = [(768, 1024, 512), (768, 3072, 1024), (768, 10000, 512), (256, 10000, 512), (50176, 512, 2048), (8704, 10000, 512)]
+if len(sys.argv) > 1:   # e.g. "384x3072x1024,128x3072x1024": how the k-block period scales with the number of CTAs
+    SHAPES = [tuple(int(v) for v in sh.split("x")) for sh in sys.argv[1].split(",")]
 trace = torch.zeros(1024, dtype=torch.int64, device="cuda")
 for M, N, K in SHAPES:
     a = torch.randn(M, K, device="cuda").to(torch.bfloat16)

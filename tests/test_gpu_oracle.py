@@ -61,3 +61,25 @@ def test_beam_peaked_exact(kind, L, beam):
     rows = (seq == ref_seq).all(1)
     assert float(rows.float().mean()) >= 0.8, (seq, ref_seq)
     torch.testing.assert_close(lp[rows], ref_lp[rows], rtol=2e-2, atol=2e-2)
+
+
+def test_config5_layer_sizes_beam5_and_greedy():
+    """BASELINE.json configs[4] at a reduced batch: att2in2 with rnn 1024, vocab 30k, 20 steps, beam 5 (the wide
+    attention / H > 512 kernel variants, two beam groups per image, kslots = 5 statistics)."""
+    opt = synth.make_opt(caption_model="att2in2", vocab_size=29999, rnn_size=1024, input_encoding_size=512, att_hid_size=512,
+                         seq_length=20)
+    sd = synth.init_state_dict(opt, seed=9, peaked=40.0, eos_bias=2.0)
+    fc, att = synth.make_features(3, 196, 2048, seed=9)
+    model = uic.setup(opt)
+    model.load_state_dict(sd)
+    model = model.cuda().eval()
+    ref_seq, ref_lp, _ = O.sample_beam(sd, "att2in2", fc, att, 20, 5)
+    seq, lp = model(fc.cuda(), None, att.cuda(), None, opt={"beam_size": 5}, mode="sample")
+    rows = (seq == ref_seq).all(1)
+    assert float(rows.float().mean()) >= 0.66, (seq, ref_seq)
+    torch.testing.assert_close(lp[rows], ref_lp[rows], rtol=2e-2, atol=2e-2)
+    g_ref, g_lp, margins = O.sample_greedy(sd, "att2in2", fc, att, 20, return_margins=True)
+    g_seq, g_lpc = model(fc.cuda(), None, att.cuda(), None, opt={"beam_size": 1}, mode="sample")
+    exact, exempt, failures = compare_greedy(g_seq.cpu(), g_ref, margins, tol=2e-2)
+    assert not failures, failures
+    assert exact >= 1
