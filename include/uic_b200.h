@@ -156,12 +156,17 @@ int uic_row_topk(const float* logits, int64_t ld_logits, const int64_t* prev_tok
  * floats (2 + 2*kslots rounded up to a multiple of 4): max, sum exp(x - max), the kslots best keys (logit,
  * with -1000 on the UNK column V-1 when unk_suppress != 0 and -inf on the banned token) and their columns
  * (int bits, 0x7fffffff = empty slot), padding.  `stats` is (rows, parts, entry) fp32, 16-byte aligned.
- * banned_tok may be NULL; row r reads banned_tok[r * banned_stride].  kslots: 1, 3, 5 or 8. */
+ * banned_tok may be NULL; row r reads banned_tok[r * banned_stride].  kslots: 1, 3, 5 or 8.
+ * temperature > 0 turns the best-key search into multinomial sampling (models/AttModel.py:231-239,
+ * torch.multinomial(exp(logprobs / temperature), 1)) by Gumbel-max: keys become x / temperature + g with
+ * g = -log(-log(u)), u a counter-based hash of (seed, step, row, column) (csrc/uic_vocab.cuh; restated in
+ * oracle/decoder_oracle.py).  `seed` points to DEVICE memory (so a captured CUDA graph can be replayed with a new
+ * seed).  temperature = 0: deterministic (seed may be NULL, step is ignored). */
 int uic_logit_stats_parts(int V);
 int uic_logit_stats_entry_floats(int kslots);
 int uic_logit_stats(const void* h_bf16, int64_t ld_h, const void* w_logit_bf16, int64_t ld_w, const float* bias,
                     const int64_t* banned_tok, int64_t banned_stride, float* stats, int rows, int V, int H, int kslots, int unk_suppress,
-                    void* stream);
+                    float temperature, const uint64_t* seed, int step, void* stream);
 /* Merges the parts of uic_logit_stats: same outputs as uic_row_topk (k <= kslots). */
 int uic_beam_topk_merge(const float* stats, int parts, int kslots, float* topk_val, int32_t* topk_idx, int rows, int k,
                         void* stream);
@@ -179,10 +184,11 @@ int uic_beam_advance(const float* stats, int parts, int kslots, int32_t* beam_se
                      int ncol_b, const float* c_src, float* c_dst, int n_state, int H, const void* emb_table_bf16,
                      int64_t ld_table, int xt_col0, int E, int V, void* stream);
 /* Greedy analogue: uic_greedy_merge and, when x_xt_bf16 != NULL, the next step's embedding rows
- * x_xt_bf16[r, 0:E] = emb_table[token r] (pitch ld_x), in one launch. */
+ * x_xt_bf16[r, 0:E] = emb_table[token r] (pitch ld_x), in one launch.  With temperature > 0 (same temperature and
+ * seed as the uic_logit_stats call of step t) the winner's key is converted back to its unperturbed log-prob. */
 int uic_greedy_advance(const float* stats, int parts, int64_t* seq, float* seq_logprobs, uint8_t* unfinished, int64_t* next_tok,
                        int32_t* n_unfinished, int t, int seq_length, int rows, const void* emb_table_bf16, int64_t ld_table,
-                       void* x_xt_bf16, int64_t ld_x, int E, int V, void* stream);
+                       void* x_xt_bf16, int64_t ld_x, int E, int V, float temperature, const uint64_t* seed, void* stream);
 
 /* One beam-search bookkeeping step for all images at once (models/CaptionModel.py:48-97,155-172):
  * merges the beams x k candidates of each image (c-major, q-minor stable order), forks the

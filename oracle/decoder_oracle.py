@@ -21,6 +21,7 @@ the live reference when /root/reference is present (`tests/test_oracle_vs_refere
 """
 from __future__ import annotations
 
+import numpy as np
 import torch
 import torch.nn.functional as F
 
@@ -204,6 +205,95 @@ def sample_greedy(sd, kind, fc_feats, att_feats, seq_length, att_masks=None,
         if int(unfinished.sum()) == 0:                                  # :250
             break
     return (seq, seq_lp, margins) if return_margins else (seq, seq_lp)
+
+
+# ------------------------------------------------------------------------------------------------
+# multinomial sampling -- models/AttModel.py:198-253 with sample_max=0 (self-critical roll-outs)
+# The reference calls torch.multinomial(exp(logprobs / T), 1): token v with probability softmax(x / T)[v].
+# Its random stream cannot be shared with a device kernel, so the product path (csrc/uic_vocab.cuh) and this
+# oracle both draw by Gumbel-max -- argmax_v (logprob_v / T + g_v), the same distribution -- with g a pure
+# function of (seed, step, row, column) restated here in numpy uint32 arithmetic.
+# ------------------------------------------------------------------------------------------------
+def _rng_mix(h):
+    h = h.astype(np.uint32)
+    h ^= h >> np.uint32(16)
+    h = (h * np.uint32(0x7feb352d)).astype(np.uint32)
+    h ^= h >> np.uint32(15)
+    h = (h * np.uint32(0x846ca68b)).astype(np.uint32)
+    h ^= h >> np.uint32(16)
+    return h
+
+
+def gumbel_noise(seed, step, rows, cols):
+    """(rows, cols) fp32 standard Gumbel noise of decoding step `step` (csrc/uic_vocab.cuh: rng_step_key, rng_row_key,
+    rng_gumbel)."""
+    with np.errstate(over="ignore"):
+        seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+        step_key = np.uint32((seed ^ (seed >> 32)) & 0xFFFFFFFF) ^ np.uint32((step * 0x9E3779B1) & 0xFFFFFFFF)
+        r = np.arange(rows, dtype=np.uint64)
+        row_key = _rng_mix(((np.uint64(step_key) + r * np.uint64(0x85EBCA77)) & np.uint64(0xFFFFFFFF)).astype(np.uint32))
+        c = ((np.arange(cols, dtype=np.uint64) * np.uint64(0xC2B2AE3D)) & np.uint64(0xFFFFFFFF)).astype(np.uint32)
+        h = _rng_mix(row_key[:, None] ^ c[None, :])
+    u = ((h >> np.uint32(9)).astype(np.float32) + np.float32(0.5)) * np.float32(1.0 / 8388608.0)
+    return torch.from_numpy(-np.log(-np.log(u))).float()
+
+
+@torch.no_grad()
+def sample_multinomial(sd, kind, fc_feats, att_feats, seq_length, temperature=1.0, seed=0, att_masks=None,
+                       decoding_constraint=0, return_margins=False):
+    B = fc_feats.size(0)
+    state = init_hidden(sd, kind, B)
+    fc, att, p_att, masks = prepare_features(sd, kind, fc_feats, att_feats, att_masks)
+    seq = torch.zeros(B, seq_length, dtype=torch.int64)
+    seq_lp = torch.zeros(B, seq_length)
+    margins = torch.full((B, seq_length), float("inf"))
+    it = torch.zeros(B, dtype=torch.int64)
+    unfinished = None
+    for t in range(seq_length + 1):
+        lp, state = logprobs_state(sd, kind, it, fc, att, p_att, masks, state)
+        if decoding_constraint and t > 0:                               # :220-223
+            lp = lp.clone()
+            lp.scatter_(1, seq[:, t - 1:t], float("-inf"))
+        if t == seq_length:                                             # :226-227
+            break
+        keys = lp / temperature + gumbel_noise(seed, t, B, lp.size(1))  # :232-237 (same distribution as multinomial)
+        it = keys.argmax(1)
+        top2 = keys.topk(2, dim=1).values
+        margins[:, t] = top2[:, 0] - top2[:, 1]
+        best = lp.gather(1, it[:, None]).squeeze(1)                     # :238
+        unfinished = (it > 0) if t == 0 else unfinished & (it > 0)      # :242-245
+        it = it * unfinished.to(it.dtype)                               # :246
+        seq[:, t] = it
+        seq_lp[:, t] = best                                             # :248 (not masked)
+        if int(unfinished.sum()) == 0:                                  # :250
+            break
+    return (seq, seq_lp, margins) if return_margins else (seq, seq_lp)
+
+
+def reward_loss(sample_logprobs, seq, reward):
+    """misc/criterion.py:104-124 (RewardCriterion)."""
+    mask = (seq > 0).float()
+    mask = torch.cat([torch.ones(mask.size(0), 1), mask[:, :-1]], 1)
+    return torch.sum(-sample_logprobs * reward * mask) / torch.sum(mask)
+
+
+def rl_loss_and_grads(sd, kind, fc_feats, att_feats, seq, reward, att_masks=None):
+    """Self-critical step of trainer.py:166-173 for given sampled tokens: the roll-out's log-probs are those of
+    teacher forcing on [BOS, seq] (AttModel.py:205-248 feeds `it * unfinished`, i.e. 0 after the end token)."""
+    leaf = {k: v.detach().clone().requires_grad_(True) for k, v in sd.items()}
+    B, T = seq.shape
+    labels = torch.cat([torch.zeros(B, 1, dtype=torch.int64), seq, torch.zeros(B, 1, dtype=torch.int64)], 1)
+    fc, att, p_att, masks = prepare_features(leaf, kind, fc_feats, att_feats, att_masks)
+    state = init_hidden(leaf, kind, B)
+    lps = []
+    for t in range(T):
+        lp, state = logprobs_state(leaf, kind, labels[:, t], fc, att, p_att, masks, state)
+        lps.append(lp.gather(1, labels[:, t + 1:t + 2]).squeeze(1))
+    sample_lp = torch.stack(lps, 1)
+    loss = reward_loss(sample_lp, seq, reward)
+    loss.backward()
+    grads = {k: (v.grad if v.grad is not None else torch.zeros_like(v)) for k, v in leaf.items()}
+    return loss.detach(), grads, sample_lp.detach()
 
 
 # ------------------------------------------------------------------------------------------------

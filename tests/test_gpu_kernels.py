@@ -296,7 +296,7 @@ def test_logit_stats_topk_equals_reference_order(R, V, H, k, kslots):
         if constrained:   # ban each row's current best token: the constraint must change the answer
             prev = logits[:, :V - 1].argmax(1)
         check(lib.uic_logit_stats(ptr(h), H, ptr(w), H, ptr(bias), ptr(prev) if constrained else None, 1, ptr(stats),
-                                  R, V, H, kslots, 1, stream()))
+                                  R, V, H, kslots, 1, 0.0, None, 0, stream()))
         check(lib.uic_beam_topk_merge(ptr(stats), parts, kslots, ptr(val), ptr(idx), R, k, stream()))
         lp = torch.log_softmax(logits, 1)
         if constrained:
@@ -321,7 +321,7 @@ def test_logit_stats_without_unk_suppression_keeps_unk():
     parts = lib.uic_logit_stats_parts(V)
     stats = torch.empty(R, parts, 4, device=DEV)
     val, idx = torch.empty(R, 1, device=DEV), torch.empty(R, 1, device=DEV, dtype=torch.int32)
-    check(lib.uic_logit_stats(ptr(h), H, ptr(w), H, ptr(bias), None, 0, ptr(stats), R, V, H, 1, 0, stream()))
+    check(lib.uic_logit_stats(ptr(h), H, ptr(w), H, ptr(bias), None, 0, ptr(stats), R, V, H, 1, 0, 0.0, None, 0, stream()))
     check(lib.uic_beam_topk_merge(ptr(stats), parts, 1, ptr(val), ptr(idx), R, 1, stream()))
     assert bool((idx == V - 1).all())
     torch.testing.assert_close(val[:, 0], torch.log_softmax(logits, 1)[:, V - 1], rtol=1e-4, atol=2e-4)
@@ -349,7 +349,7 @@ def test_greedy_merge_equals_greedy_step():
         flags = _lib.SAMPLE_DECODING_CONSTRAINT if t > 0 else 0
         check(lib.uic_greedy_step(ptr(logits), V, ptr(a[0]), ptr(a[1]), ptr(a[2]), ptr(a[3]), ptr(a[4]), t, T, R, V, flags, stream()))
         banned = b[0][:, t - 1:] if t > 0 else None
-        check(lib.uic_logit_stats(ptr(h), H, ptr(w), H, ptr(bias), ptr(banned), T, ptr(stats), R, V, H, 1, 0, stream()))
+        check(lib.uic_logit_stats(ptr(h), H, ptr(w), H, ptr(bias), ptr(banned), T, ptr(stats), R, V, H, 1, 0, 0.0, None, 0, stream()))
         check(lib.uic_greedy_merge(ptr(stats), parts, ptr(b[0]), ptr(b[1]), ptr(b[2]), ptr(b[3]), ptr(b[4]), t, T, R, stream()))
     assert torch.equal(a[0], b[0]) and torch.equal(a[2], b[2]) and torch.equal(a[3], b[3]) and torch.equal(a[4], b[4])
     assert 0 < int(a[4][0]) < R
@@ -384,7 +384,7 @@ def test_beam_advance_equals_the_four_step_chain(B, b, kslots):
         h, w, bias, _ = _stats_inputs(R, V, Hh, seed=40 + t)
         bias[0] += 3.0                                   # some beams finish early
         stats = torch.empty(R, parts, es, device=DEV)
-        check(lib.uic_logit_stats(ptr(h), Hh, ptr(w), Hh, ptr(bias), None, 0, ptr(stats), R, V, Hh, kslots, 1, stream()))
+        check(lib.uic_logit_stats(ptr(h), Hh, ptr(w), Hh, ptr(bias), None, 0, ptr(stats), R, V, Hh, kslots, 1, 0.0, None, 0, stream()))
         src, dst = t % 2, (t + 1) % 2
         move = int(t + 1 < T)
         # unfused chain
@@ -425,11 +425,11 @@ def test_greedy_advance_equals_merge_plus_embed():
         h, w = _rand_bf16(R, H, seed=10 + t), _rand_bf16(V, H, seed=20 + t, scale=0.05)
         bias = torch.randn(V, device=DEV) * 0.1
         bias[0] += 3.0
-        check(lib.uic_logit_stats(ptr(h), H, ptr(w), H, ptr(bias), None, 0, ptr(stats), R, V, H, 1, 0, stream()))
+        check(lib.uic_logit_stats(ptr(h), H, ptr(w), H, ptr(bias), None, 0, ptr(stats), R, V, H, 1, 0, 0.0, None, 0, stream()))
         check(lib.uic_greedy_merge(ptr(stats), parts, ptr(a[0]), ptr(a[1]), ptr(a[2]), ptr(a[3]), ptr(a[4]), t, T, R, stream()))
         check(lib.uic_embed_rows(ptr(table), E, ptr(a[3]), ptr(a[5][:, 8:]), E + 16, R, E, V, stream()))
         check(lib.uic_greedy_advance(ptr(stats), parts, ptr(b[0]), ptr(b[1]), ptr(b[2]), ptr(b[3]), ptr(b[4]), t, T, R, ptr(table), E,
-                                     ptr(b[5][:, 8:]), E + 16, E, V, stream()))
+                                     ptr(b[5][:, 8:]), E + 16, E, V, 0.0, None, stream()))
         for x, y in zip(a, b):
             assert torch.equal(x, y)
     assert 0 < int(a[4][0]) < R

@@ -7,9 +7,9 @@ gujiuxiang/unpaired_image_captioning (pivot_based_eccv2018/models + misc/criteri
     seq, lp = model(fc, attri, att, att_masks, opt={'beam_size': 3}, mode='sample')
     loss = uic.LanguageModelCriterion(opt)(logprobs, labels[:, 1:], masks[:, 1:])
 """
-from .criterion import LanguageModelCriterion  # noqa: F401
+from .criterion import LanguageModelCriterion, RewardCriterion  # noqa: F401
 from .models import (Att2in2Core, Att2in2Model, AttModel, Attention, CaptionModel, TopDownCore,  # noqa: F401
                      TopDownModel, setup)
 
-__all__ = ["setup", "LanguageModelCriterion", "AttModel", "Att2in2Model", "TopDownModel", "Attention",
+__all__ = ["setup", "LanguageModelCriterion", "RewardCriterion", "AttModel", "Att2in2Model", "TopDownModel", "Attention",
            "Att2in2Core", "TopDownCore", "CaptionModel"]

@@ -39,12 +39,12 @@ SIGNATURES = {
     "uic_row_topk": (_i, [_p, _i64, _p, _p, _p, _i, _i, _i, _i, _p]),
     "uic_logit_stats_parts": (_i, [_i]),
     "uic_logit_stats_entry_floats": (_i, [_i]),
-    "uic_logit_stats": (_i, [_p, _i64, _p, _i64, _p, _p, _i64, _p, _i, _i, _i, _i, _i, _p]),
+    "uic_logit_stats": (_i, [_p, _i64, _p, _i64, _p, _p, _i64, _p, _i, _i, _i, _i, _i, _f, _p, _i, _p]),
     "uic_beam_topk_merge": (_i, [_p, _i, _i, _p, _p, _i, _i, _p]),
     "uic_greedy_merge": (_i, [_p, _i, _p, _p, _p, _p, _p, _i, _i, _i, _p]),
     "uic_beam_advance": (_i, [_p, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p, _p, _i64, _i, _i, _i, _i, _p, _p,
                               _i, _i, _p, _i64, _i, _i, _i, _p]),
-    "uic_greedy_advance": (_i, [_p, _i, _p, _p, _p, _p, _p, _i, _i, _i, _p, _i64, _p, _i64, _i, _i, _p]),
+    "uic_greedy_advance": (_i, [_p, _i, _p, _p, _p, _p, _p, _i, _i, _i, _p, _i64, _p, _i64, _i, _i, _f, _p, _p]),
     "uic_beam_step": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p]),
     "uic_beam_gather": (_i, [_p, _p, _p, _i64, _i, _i, _i, _i, _p, _p, _i, _i, _i, _p]),
     "uic_lstm_cell_bwd": (_i, [_p, _i64, _p, _p, _p, _i64, _p, _i64, _p, _i64, _p, _p, _i64, _p, _i, _i, _p]),

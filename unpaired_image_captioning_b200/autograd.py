@@ -324,6 +324,40 @@ class _DecoderLogprobsFn(torch.autograd.Function):
         return (None,) * 5 + tuple(_finish(r, g, None, names, params))
 
 
+class _DecoderTokenLogprobsFn(torch.autograd.Function):
+    """Log-probs of given tokens under teacher forcing, (B, T_total), differentiable: the policy-gradient path of
+    self-critical training (trainer.py:166-173 back-propagates through the sampled roll-out, which is the same
+    computation as teacher forcing on the sampled tokens).  The (B, T, V) log-probs are never materialised."""
+
+    @staticmethod
+    def forward(ctx, model, fc_feats, att_feats, labels, att_masks, *params):
+        r = teacher_forced_run(model, fc_feats, att_feats, labels, att_masks, all_steps=True)
+        T_total = r.T_total
+        target = labels[:, 1:T_total + 1].contiguous().view(-1).long()
+        ones = torch.ones(target.numel(), dtype=torch.float32, device=target.device)
+        one = torch.ones(1, dtype=torch.float32, device=target.device)
+        o = _logit_stage(r, target, ones, one, want_grad=False)
+        ctx.run, ctx.target, ctx.one = r, target, one
+        return -o["nll"].view(r.B, T_total)
+
+    @staticmethod
+    def backward(ctx, dlp):
+        r = ctx.run
+        # d loss / d logits = (softmax - onehot) * (-d loss / d logprob): the fused XE backward with per-token weights
+        weights = (-dlp).contiguous().float().view(-1)
+        o = _logit_stage(r, ctx.target, weights, ctx.one, want_grad=True)
+        names, params = _param_list(r.model)
+        g = bptt(r, o["dh"])
+        g["logit.weight"], g["logit.bias"] = o["dW"], o["db"]
+        return (None,) * 5 + tuple(_finish(r, g, None, names, params))
+
+
+def decoder_token_logprobs(model, fc_feats, att_feats, labels, att_masks=None):
+    """labels: (B, T_total + 1) int64 with the BOS column in front (token t is the target of step t - 1)."""
+    _, params = _param_list(model)
+    return _DecoderTokenLogprobsFn.apply(model, fc_feats, att_feats, labels, att_masks, *params)
+
+
 def decoder_loss(model, fc_feats, att_feats, labels, masks, att_masks=None, global_mask_sum=None):
     _, params = _param_list(model)
     return _DecoderLossFn.apply(model, fc_feats, att_feats, labels, masks, att_masks, global_mask_sum, *params)

@@ -1,4 +1,5 @@
-"""misc/criterion.py:138-159 -- LanguageModelCriterion (masked cross-entropy over log-probs).
+"""misc/criterion.py:138-159 -- LanguageModelCriterion (masked cross-entropy over log-probs), and
+misc/criterion.py:104-124 -- RewardCriterion (the self-critical policy-gradient loss).
 
 Drop-in signature `LanguageModelCriterion(opt)(input, target, mask)`.  The gather/mask/sum runs on
 whatever device `input` lives on with the library's row kernels when it is a CUDA tensor that does
@@ -29,3 +30,19 @@ class LanguageModelCriterion(nn.Module):
         if "stackcap" in self.caption_model:
             return self.xe_loss(input[0], target, mask) + self.xe_loss(input[1], target, mask) + self.xe_loss(input[2], target, mask)
         return self.xe_loss(input, target, mask)
+
+
+class RewardCriterion(nn.Module):
+    """misc/criterion.py:104-124: `loss = -sum(logprob * reward * mask) / sum(mask)` with
+    `mask[:, t] = 1` for the first step and wherever the previous sampled token is not 0 (so the step that emits
+    the end token still counts).  `input` are the sample log-probs returned by
+    `model(..., opt={'sample_max': 0}, mode='sample')`; when gradients are enabled they carry the decoder's
+    autograd graph (teacher forcing on the sampled tokens), so `loss.backward()` works as in `trainer.py:166-173`."""
+
+    def forward(self, input, seq, reward):
+        input = input.contiguous().view(-1)
+        reward = reward.contiguous().view(-1).to(input.dtype)
+        mask = (seq > 0).to(input.dtype)
+        mask = torch.cat([mask.new_ones(mask.size(0), 1), mask[:, :-1]], 1).contiguous().view(-1)
+        output = -input * reward * mask
+        return torch.sum(output) / torch.sum(mask)

@@ -269,11 +269,12 @@ int uic_logit_stats_entry_floats(int kslots) { return kslots > 0 ? logit_stats_e
 
 int uic_logit_stats(const void* h_bf16, int64_t ld_h, const void* w_logit_bf16, int64_t ld_w, const float* bias,
                     const int64_t* banned_tok, int64_t banned_stride, float* stats, int rows, int V, int H, int kslots, int unk_suppress,
-                    void* stream) {
+                    float temperature, const uint64_t* seed, int step, void* stream) {
   REQUIRE(h_bf16 && w_logit_bf16 && stats, UIC_ERR_ARG, "uic_logit_stats: null pointer");
   if (rows == 0) return 0;
   return logit_stats(h_bf16, ld_h, w_logit_bf16, ld_w, bias, reinterpret_cast<const long long*>(banned_tok), banned_stride, stats,
-                     rows, V, H, kslots, unk_suppress, ST(stream));
+                     rows, V, H, kslots, unk_suppress, temperature,
+                     reinterpret_cast<const unsigned long long*>(seed), step, ST(stream));
 }
 
 int uic_beam_topk_merge(const float* stats, int parts, int kslots, float* topk_val, int32_t* topk_idx, int rows, int k,
@@ -397,7 +398,7 @@ int uic_beam_advance(const float* stats, int parts, int kslots, int32_t* beam_se
 
 int uic_greedy_advance(const float* stats, int parts, int64_t* seq, float* seq_logprobs, uint8_t* unfinished, int64_t* next_tok,
                        int32_t* n_unfinished, int t, int seq_length, int rows, const void* emb_table_bf16, int64_t ld_table,
-                       void* x_xt_bf16, int64_t ld_x, int E, int V, void* stream) {
+                       void* x_xt_bf16, int64_t ld_x, int E, int V, float temperature, const uint64_t* seed, void* stream) {
   REQUIRE(stats && seq && seq_logprobs && unfinished && next_tok && n_unfinished, UIC_ERR_ARG, "uic_greedy_advance: null pointer");
   REQUIRE(parts > 0 && seq_length > 0 && t >= 0 && t < seq_length, UIC_ERR_SHAPE, "uic_greedy_advance: parts=%d t=%d seq_length=%d",
           parts, t, seq_length);
@@ -405,7 +406,7 @@ int uic_greedy_advance(const float* stats, int parts, int64_t* seq, float* seq_l
   REQUIRE(x_xt_bf16 == nullptr || (emb_table_bf16 && E > 0 && V > 0), UIC_ERR_ARG, "uic_greedy_advance: embedding table missing");
   if (rows == 0) return 0;
   return greedy_advance(stats, parts, seq, seq_logprobs, unfinished, next_tok, n_unfinished, t, seq_length, rows, emb_table_bf16,
-                        ld_table, x_xt_bf16, ld_x, E, V, ST(stream));
+                        ld_table, x_xt_bf16, ld_x, E, V, temperature, reinterpret_cast<const unsigned long long*>(seed), ST(stream));
 }
 
 int uic_beam_step(const float* topk_val, const int32_t* topk_idx, int32_t* beam_seq, float* beam_lp, float* beam_sum,

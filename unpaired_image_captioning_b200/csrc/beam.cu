@@ -301,7 +301,8 @@ __global__ void __launch_bounds__(ADV_THREADS) greedy_advance_kernel(const float
                                                                       uint8_t* __restrict__ unfinished, int64_t* __restrict__ next_tok,
                                                                       int32_t* __restrict__ n_unfinished, int t, int T, int rows,
                                                                       const __nv_bfloat16* __restrict__ table, long long ld_table,
-                                                                      __nv_bfloat16* __restrict__ x, long long ld_x, int E, int V) {
+                                                                      __nv_bfloat16* __restrict__ x, long long ld_x, int E, int V,
+                                                                      float temperature, const unsigned long long* __restrict__ seed) {
   if (t > 0 && n_unfinished[t - 1] == 0) return;  // the reference has left its loop (AttModel.py:250-251)
   const int r = blockIdx.x * (ADV_THREADS / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (r >= rows) return;
@@ -313,9 +314,11 @@ __global__ void __launch_bounds__(ADV_THREADS) greedy_advance_kernel(const float
   const bool u = (t == 0 ? true : unfinished[r] != 0) && it > 0;
   it = u ? it : 0;
   __syncwarp();
+  // sampling: the key is x / T + g(row, column); the reported log-prob is that of the unperturbed logit (AttModel.py:238)
+  const float xbest = temperature > 0.0f ? (best.v - rng_gumbel(rng_row_key(rng_step_key(*seed, t), r), best.i)) * temperature : best.v;
   if (lane == 0) {
     seq[static_cast<long long>(r) * T + t] = it;
-    seq_lp[static_cast<long long>(r) * T + t] = (best.v - rs.M) - rs.log_s;
+    seq_lp[static_cast<long long>(r) * T + t] = (xbest - rs.M) - rs.log_s;
     unfinished[r] = u ? 1 : 0;
     next_tok[r] = it;
     if (u) atomicAdd(&n_unfinished[t], 1);
@@ -328,12 +331,13 @@ __global__ void __launch_bounds__(ADV_THREADS) greedy_advance_kernel(const float
 
 int greedy_advance(const float* stats, int parts, int64_t* seq, float* seq_lp, uint8_t* unfinished, int64_t* next_tok,
                    int32_t* n_unfinished, int t, int seq_length, int rows, const void* table, long long ld_table, void* x_xt,
-                   long long ld_x, int E, int V, cudaStream_t stream) {
+                   long long ld_x, int E, int V, float temperature, const unsigned long long* seed, cudaStream_t stream) {
+  if (temperature > 0.0f && seed == nullptr) return set_error(UIC_ERR_ARG, "greedy_advance: sampling needs a seed (device pointer)");
   const int per = ADV_THREADS / 32;
   launch_begin("greedy_advance", stream);
   greedy_advance_kernel<<<(rows + per - 1) / per, ADV_THREADS, 0, stream>>>(stats, parts, seq, seq_lp, unfinished, next_tok, n_unfinished,
                                                                            t, seq_length, rows, static_cast<const __nv_bfloat16*>(table),
-                                                                           ld_table, static_cast<__nv_bfloat16*>(x_xt), ld_x, E, V);
+                                                                           ld_table, static_cast<__nv_bfloat16*>(x_xt), ld_x, E, V, temperature, seed);
   UIC_CUDA_OK(cudaGetLastError());
   launch_end(stream);
   return 0;

@@ -31,6 +31,7 @@
 
 #include "uic_internal.h"
 #include "uic_ptx.cuh"
+#include "uic_vocab.cuh"
 
 namespace uic {
 
@@ -60,6 +61,10 @@ struct GemmEpilogue {
   long long banned_stride;
   int parts;
   int unk_col;  // column that gets -1000 (beam search only), -1 = none
+  int sample;   // multinomial sampling: candidate keys become x / T + Gumbel noise (uic_vocab.cuh)
+  float inv_temperature;
+  const unsigned long long* seed;  // device memory: a captured CUDA graph can be replayed with a new seed
+  int step;
 };
 
 #define UIC_TRACE(slot)                                                              \
@@ -315,6 +320,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             const float nm = fmaxf(run_m, bm);
             run_s = run_s * ex2_approx((run_m - nm) * LOG2E) + (bs0 + bs1) * ex2_approx((bm - nm) * LOG2E);
             run_m = nm;
+          }
+          if (ep.sample) {  // multinomial sampling by Gumbel-max (AttModel.py:231-239); -inf stays -inf
+            const uint32_t rk = rng_row_key(rng_step_key(*ep.seed, ep.step), row);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) x[j] = fmaf(x[j], ep.inv_temperature, rng_gumbel(rk, col0 + j));
           }
           // beam-search edits of the candidate keys; the statistics above use the unedited logits
           if (ep.unk_col >= col0 && ep.unk_col < col0 + 32) {  // UNK suppression (CaptionModel.py:133), warp-uniform
@@ -637,14 +647,17 @@ int logit_stats_entry_floats(int kslots) { return (2 + 2 * kslots + 3) / 4 * 4; 
 
 // Logit projection with the fused statistics epilogue: stats[row][part][logit_stats_entry_floats(kslots)].
 int logit_stats(const void* A, long long lda, const void* B, long long ldb, const float* bias, const long long* banned,
-                long long banned_stride, float* stats, int M, int N, int K, int kslots, int unk_suppress, cudaStream_t stream) {
+                long long banned_stride, float* stats, int M, int N, int K, int kslots, int unk_suppress, float temperature,
+                const unsigned long long* seed, int step, cudaStream_t stream) {
   if (M <= 0 || N <= 0 || K <= 0) return set_error(UIC_ERR_SHAPE, "logit_stats: empty problem M=%d N=%d K=%d", M, N, K);
   if (kslots != 1 && kslots != 3 && kslots != 5 && kslots != 8)
     return set_error(UIC_ERR_ARG, "logit_stats: kslots must be 1, 3, 5 or 8 (got %d)", kslots);
+  if (temperature > 0.0f && seed == nullptr) return set_error(UIC_ERR_ARG, "logit_stats: sampling needs a seed (device pointer)");
   if ((reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15) || (lda % 8) || (ldb % 8) ||
       (reinterpret_cast<uintptr_t>(stats) & 15))
     return set_error(UIC_ERR_ALIGN, "logit_stats: operands and stats must be 16-byte aligned with pitches that are multiples of 8 elements");
-  GemmEpilogue ep{nullptr, 0, nullptr, 0, bias, 0, 0, 0, 0, 0.0f, nullptr, 0, stats, banned, banned_stride, logit_stats_parts(N), unk_suppress ? N - 1 : -1};
+  GemmEpilogue ep{nullptr, 0, nullptr, 0, bias, 0, 0, 0, 0, 0.0f, nullptr, 0, stats, banned, banned_stride, logit_stats_parts(N), unk_suppress ? N - 1 : -1,
+                  temperature > 0.0f ? 1 : 0, temperature > 0.0f ? 1.0f / temperature : 1.0f, seed, step};
   CUtensorMap ta, tb;
   int rc = get_tensor_map_bf16(&ta, A, M, K, lda, BM, 64);
   if (rc) return rc;

@@ -41,7 +41,8 @@ int gemm_bf16(const void* A, long long lda, const void* B, long long ldb, float*
 int logit_stats_parts(int N);
 int logit_stats_entry_floats(int kslots);
 int logit_stats(const void* A, long long lda, const void* B, long long ldb, const float* bias, const long long* banned,
-                long long banned_stride, float* stats, int M, int N, int K, int kslots, int unk_suppress, cudaStream_t stream);
+                long long banned_stride, float* stats, int M, int N, int K, int kslots, int unk_suppress, float temperature,
+                const unsigned long long* seed, int step, cudaStream_t stream);
 int beam_topk_merge(const float* stats, int parts, int kslots, float* topk_val, int32_t* topk_idx, int rows, int k,
                     cudaStream_t stream);
 int greedy_merge(const float* stats, int parts, int64_t* seq, float* seq_lp, uint8_t* unfinished, int64_t* next_tok,
@@ -76,7 +77,7 @@ int beam_advance(const float* stats, int parts, int kslots, int32_t* beam_seq, f
                  const void* table, long long ld_table, int xt_col0, int E, int V, cudaStream_t stream);
 int greedy_advance(const float* stats, int parts, int64_t* seq, float* seq_lp, uint8_t* unfinished, int64_t* next_tok,
                    int32_t* n_unfinished, int t, int seq_length, int rows, const void* table, long long ld_table, void* x_xt,
-                   long long ld_x, int E, int V, cudaStream_t stream);
+                   long long ld_x, int E, int V, float temperature, const unsigned long long* seed, cudaStream_t stream);
 int beam_gather(const int32_t* parent_row, const void* x_src, void* x_dst, long long ld_x, int col0_a, int ncol_a, int col0_b,
                 int ncol_b, const float* c_src, float* c_dst, int n_state, int rows, int H, cudaStream_t stream);
 

@@ -6,6 +6,31 @@
 
 namespace uic {
 
+// ---- counter-based noise for multinomial sampling ------------------------------------------------------------------
+// torch.multinomial(exp(logprobs / T), 1) (models/AttModel.py:231-239) draws token v with probability
+// softmax(x / T)[v]; so does argmax_v (x_v / T + g_v) with independent standard Gumbel noise g (Gumbel-max).
+// g is a pure function of (seed, step, row, column): the GEMM epilogue perturbs the keys with it, the merge
+// recomputes it for the winner to recover the unperturbed logit, and the oracle restates it in numpy.
+__host__ __device__ __forceinline__ uint32_t rng_mix(uint32_t h) {  // "lowbias32" finaliser
+  h ^= h >> 16;
+  h *= 0x7feb352dU;
+  h ^= h >> 15;
+  h *= 0x846ca68bU;
+  h ^= h >> 16;
+  return h;
+}
+__host__ __device__ __forceinline__ uint32_t rng_step_key(unsigned long long seed, int step) {
+  return static_cast<uint32_t>(seed ^ (seed >> 32)) ^ (static_cast<uint32_t>(step) * 0x9E3779B1U);
+}
+__host__ __device__ __forceinline__ uint32_t rng_row_key(uint32_t step_key, int row) {
+  return rng_mix(step_key + static_cast<uint32_t>(row) * 0x85EBCA77U);
+}
+__device__ __forceinline__ float rng_gumbel(uint32_t row_key, int col) {
+  const uint32_t h = rng_mix(row_key ^ (static_cast<uint32_t>(col) * 0xC2B2AE3DU));
+  const float u = (static_cast<float>(h >> 9) + 0.5f) * (1.0f / 8388608.0f);  // 23 bits + 1/2: exact in fp32, strictly inside (0, 1)
+  return -__logf(-__logf(u));
+}
+
 struct MaxSum {
   float m, s;
 };

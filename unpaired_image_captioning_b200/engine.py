@@ -223,11 +223,17 @@ class DecoderEngine:
         check(self.lib.uic_embed_rows(ptr(w.emb_relu), w.E, ptr(tok), ptr(X[:, sl.xt[0]:]), X.stride(0), X.shape[0], w.E, w.V, stream()))
 
     # ---- greedy (models/AttModel.py:198-253, sample_max = 1) -------------------------------------------
-    def greedy(self, feats, seq_length, decoding_constraint=0):
+    def greedy(self, feats, seq_length, decoding_constraint=0, temperature=0.0, seed=None):
+        """sample_max = 1 (temperature 0) or multinomial sampling with `temperature` (models/AttModel.py:231-239):
+        the arg-max of the logits perturbed by Gumbel noise, which is a function of (seed, step, row, column).
+        `seed`: an int, or None to draw one from torch's CUDA generator (so torch.manual_seed controls it)."""
         w, lib = self.w, self.lib
         B, dev, T = feats.B, feats.att.device, seq_length
         flags = _lib.SAMPLE_DECODING_CONSTRAINT if decoding_constraint else 0
-        key = ("greedy", B, feats.L, T, flags, feats.masks is not None, self.fused_vocab)
+        temperature = float(temperature)
+        if temperature > 0.0 and not self.fused_vocab:
+            raise NotImplementedError("multinomial sampling runs in the fused statistics epilogue (engine.fused_vocab)")
+        key = ("greedy", B, feats.L, T, flags, feats.masks is not None, self.fused_vocab, temperature)
 
         def alloc():
             s = {"att": torch.empty_like(feats.att), "p_att": torch.empty_like(feats.p_att),
@@ -236,7 +242,7 @@ class DecoderEngine:
                  "ws": self._workspace(B, dev),
                  "seq": torch.zeros(B, T, dtype=torch.int64, device=dev), "lp": torch.zeros(B, T, device=dev),
                  "unf": torch.zeros(B, dtype=torch.uint8, device=dev), "tok": torch.zeros(B, dtype=torch.int64, device=dev),
-                 "nunf": torch.zeros(T, dtype=torch.int32, device=dev),
+                 "nunf": torch.zeros(T, dtype=torch.int32, device=dev), "seed": torch.zeros(1, dtype=torch.int64, device=dev),
                  "parts": int(lib.uic_logit_stats_parts(w.V))}
             s["stats"] = torch.empty(B, s["parts"], 4, dtype=torch.float32, device=dev)
             s["feats"] = Features(s["att"], s["p_att"], s["fc"], s["masks"], B, feats.L)
@@ -258,11 +264,12 @@ class DecoderEngine:
                     # the (B, V) logits are never written
                     banned = s["seq"][:, t - 1:] if (flags and t > 0) else None
                     check(lib.uic_logit_stats(ptr(h), h.stride(0), ptr(w.w_logit), w.H, ptr(w.b_logit), ptr(banned), T,
-                                              ptr(s["stats"]), B, w.V, w.H, 1, 0, stream()))
+                                              ptr(s["stats"]), B, w.V, w.H, 1, 0, temperature, ptr(s["seed"]), t, stream()))
                     # merge of the parts + the next step's embedding rows in one launch
                     xt = X[:, sl.xt[0]:] if t + 1 < T else None
                     check(lib.uic_greedy_advance(ptr(s["stats"]), s["parts"], ptr(s["seq"]), ptr(s["lp"]), ptr(s["unf"]), ptr(s["tok"]),
-                                                 ptr(s["nunf"]), t, T, B, ptr(w.emb_relu), w.E, ptr(xt), X.stride(0), w.E, w.V, stream()))
+                                                 ptr(s["nunf"]), t, T, B, ptr(w.emb_relu), w.E, ptr(xt), X.stride(0), w.E, w.V, temperature, ptr(s["seed"]),
+                                                 stream()))
                     continue
                 else:
                     self.logits_of(h, ws["logits"])
@@ -272,7 +279,14 @@ class DecoderEngine:
                     self._embed(s["tok"], X, sl)
             return s["seq"], s["lp"]
 
-        return self._decode(key, alloc, run, feats)
+        def pre(s):
+            if temperature > 0.0:
+                if seed is None:
+                    s["seed"].random_()
+                else:
+                    s["seed"].fill_(int(seed))
+
+        return self._decode(key, alloc, run, feats, pre)
 
     # ---- beam search (models/AttModel.py:167-196 + models/CaptionModel.py:33-177) -------------------------
     def beam(self, feats, seq_length, beam_size, decoding_constraint=0, max_ppl=0):
@@ -321,7 +335,7 @@ class DecoderEngine:
                 if self.fused_vocab and b <= 8:
                     banned = s["tok"] if (tk_flags and t > 0) else None
                     check(lib.uic_logit_stats(ptr(h), h.stride(0), ptr(w.w_logit), w.H, ptr(w.b_logit), ptr(banned), 1,
-                                              ptr(s["stats"]), R, w.V, w.H, s["kslots"], 1, stream()))
+                                              ptr(s["stats"]), R, w.V, w.H, s["kslots"], 1, 0.0, None, 0, stream()))
                     # merge + beam bookkeeping + state re-ordering + next embeddings in one launch
                     check(lib.uic_beam_advance(ptr(s["stats"]), s["parts"], s["kslots"], ptr(s["beam_seq"]), ptr(s["beam_lp"]),
                                                ptr(s["beam_sum"]), ptr(s["done_seq"]), ptr(s["done_lp"]), ptr(s["done_p"]),
@@ -344,18 +358,22 @@ class DecoderEngine:
 
         return self._decode(key, alloc, run, feats)
 
-    def _decode(self, key, alloc, run, feats):
+    def _decode(self, key, alloc, run, feats, pre=None):
         """First call per shape: allocate the static buffers, run the loop eagerly once (warms every
         kernel), then capture it into a CUDA graph; later calls only refresh the feature tiles and
         replay.  No host synchronisation happens inside the loop either way."""
         if not self.use_graphs:
             s = alloc()
             self._load_feats(s, feats)
+            if pre is not None:
+                pre(s)
             return run(s)
         entry = self._graphs.get(key)
         if entry is None:
             s = alloc()
             self._load_feats(s, feats)
+            if pre is not None:
+                pre(s)
             n0 = _lib.launch_count()
             run(s)
             n_kernels = _lib.launch_count() - n0      # library launches inside one decode loop
@@ -368,6 +386,8 @@ class DecoderEngine:
             self._graphs[key] = entry
         g, s, out, n_kernels = entry
         self._load_feats(s, feats)
+        if pre is not None:
+            pre(s)      # per-call device-side inputs of the captured loop (the sampling seed)
         g.replay()
         self._replayed_launches += n_kernels
         return out

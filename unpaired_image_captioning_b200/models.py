@@ -288,22 +288,39 @@ class AttModel(CaptionModel):
         self.done_beams = _LazyDoneBeams(self._done_tables)
         return done_seq_c[:, 0].contiguous(), done_lp_c[:, 0].contiguous()
 
-    @torch.no_grad()
     def _sample(self, fc_feats, attri_feats, att_feats, att_masks=None, opt={}):
-        """models/AttModel.py:198-253."""
+        """models/AttModel.py:198-253.  sample_max = 0 draws from softmax(logits / temperature) on the device (Gumbel-max
+        inside the logit GEMM's epilogue, seeded from torch's CUDA generator).  With gradients enabled the returned
+        sample log-probs are differentiable (self-critical training, trainer.py:166-173)."""
         sample_max = opt.get("sample_max", 1)
         beam_size = opt.get("beam_size", 1)
         temperature = opt.get("temperature", 1.0)
         decoding_constraint = opt.get("decoding_constraint", 0)
-        if beam_size > 1:
-            return self._sample_beam(fc_feats, att_feats, att_masks, opt)
-        if not sample_max:
-            raise NotImplementedError("multinomial sampling (sample_max=0, SCST) is the next row of the scope table, "
-                                      f"not built yet (temperature={temperature})")
-        eng = self.engine
-        feats = eng.prepare(fc_feats, att_feats, att_masks)
-        seq, lp = eng.greedy(feats, self.seq_length, decoding_constraint)
-        return seq.clone(), lp.clone()
+        with torch.no_grad():
+            if beam_size > 1:
+                return self._sample_beam(fc_feats, att_feats, att_masks, opt)
+            eng = self.engine
+            feats = eng.prepare(fc_feats, att_feats, att_masks)
+            if sample_max:
+                seq, lp = eng.greedy(feats, self.seq_length, decoding_constraint)
+                return seq.clone(), lp.clone()
+            if not temperature > 0.0:
+                raise ValueError(f"sample_max=0 needs temperature > 0 (got {temperature})")
+            seq, lp = eng.greedy(feats, self.seq_length, decoding_constraint, temperature=temperature, seed=opt.get("seed"))
+            seq, lp = seq.clone(), lp.clone()
+        if not (torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())):
+            return seq, lp
+        # differentiable log-probs of the sampled tokens; the steps the reference never reaches (after every row has
+        # finished, AttModel.py:250-251) stay zero
+        from . import autograd as AG
+        B = seq.size(0)
+        labels = torch.cat([seq.new_zeros(B, 1), seq, seq.new_zeros(B, 1)], 1)
+        if decoding_constraint:
+            raise NotImplementedError("differentiable sampling with decoding_constraint is not built")
+        lp_g = AG.decoder_token_logprobs(self, fc_feats, att_feats, labels, att_masks)[:, :self.seq_length]
+        all_fin = ((seq == 0).cumsum(1) > 0).all(0)                     # (T,) every row has emitted its end token by step t
+        unwritten = (all_fin.cumsum(0) - all_fin.long()) > 0            # the loop broke before step t
+        return seq, lp_g * (~unwritten).to(lp_g.dtype)
 
 
 class _LazyDoneBeams:
