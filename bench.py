@@ -176,7 +176,7 @@ def run_reference(args, world, rank):
                              "sample": f"{sample} images x {args.steps} steps, oracle/decoder_oracle.py sample_beam, torch CPU fp32"},
             "e2e": {"value": value, "unit": "captions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    _emit(line)
 
 
 def _config(cfg, opt, sample_note=None):
@@ -310,9 +310,18 @@ def run_b200(args, world, rank, local):
                 "gpu_launches": int(launches * args.steps),
                 "greedy_captions_per_s": world * B / (ms_greedy * 1e-3), "greedy_ms_per_step": ms_greedy,
                 "train": train, "roofline": roofline, "kernel_shares": shares, "cpu_baseline": cpu}
-        print(json.dumps(line))
+        _emit(line)
     if world > 1:
         torch.distributed.destroy_process_group()
+
+
+_RESULT_OUT = None
+
+
+def _emit(line):
+    out = _RESULT_OUT if _RESULT_OUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 
 
 def main():
@@ -325,6 +334,12 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    # stdout carries exactly ONE line, the JSON result: everything libraries print on file descriptor 1 (NCCL's
+    # version banner, for one) goes to stderr instead
+    global _RESULT_OUT
+    sys.stdout.flush()
+    _RESULT_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     world, rank, local = _dist()
     if args.impl == "reference":
         run_reference(args, world, rank)

@@ -15,4 +15,5 @@ run misc tests/test_gpu_kernels.py -m gpu -k "not gemm and not att_step"
 run golden tests/test_gpu_golden.py -m gpu
 run oracle tests/test_gpu_oracle.py -m gpu
 run train tests/test_gpu_train.py -m gpu
+run sampling tests/test_gpu_sampling.py -m gpu
 for f in "$@"; do :; done
