@@ -57,6 +57,15 @@ void launch_end(cudaStream_t stream) {
 static std::atomic<long long*> g_gemm_trace{nullptr};
 long long* gemm_trace_buffer() { return g_gemm_trace.load(std::memory_order_relaxed); }
 
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("UIC_PDL");
+    v = (e != nullptr && strcmp(e, "0") == 0) ? 0 : 1;
+  }
+  return v != 0;
+}
+
 int gemm_impl() {
   int v = g_gemm_impl.load(std::memory_order_relaxed);
   if (v < 0) {

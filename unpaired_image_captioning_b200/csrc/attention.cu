@@ -154,6 +154,7 @@ __global__ void __launch_bounds__(ATT_THREADS, (CA <= 2 && MT <= 4) ? 2 : 1)
 att_step_fwd_kernel(const __grid_constant__ CUtensorMap tmap_att, AttParams p) {
   extern __shared__ uint8_t att_smem_raw[];
 
+  pdl_launch_dependents();
   const int L = p.L, A = p.A, H = p.H;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // CTA c owns the work items [c * items / ctas, (c + 1) * items / ctas): a contiguous run of batches
@@ -181,6 +182,7 @@ att_step_fwd_kernel(const __grid_constant__ CUtensorMap tmap_att, AttParams p) {
     tma_prefetch_desc(&tmap_att);
   }
   __syncthreads();  // the only block-wide barrier
+  pdl_wait();       // (programmatic dependent launch: the set-up above overlapped the previous kernel's tail)
   ATT_TRACE(0);
   if (p.trace != nullptr && threadIdx.x == 0 && blockIdx.x < 448) p.trace[128 + 2 * blockIdx.x] = att_now();  // (1024-slot debug buffer)
 
@@ -637,7 +639,7 @@ static int launch_att(AttParams& p, const AttPlan& pl, int n_img, cudaStream_t s
     if (rc) return rc;
   }
   launch_begin("att_step_fwd", stream);
-  kern<<<pl.ctas, ATT_THREADS, smem, stream>>>(tm, p);
+  UIC_CUDA_OK(launch_pdl(kern, dim3(pl.ctas), dim3(ATT_THREADS), smem, stream, tm, p));
   UIC_CUDA_OK(cudaGetLastError());
   launch_end(stream);
   return 0;

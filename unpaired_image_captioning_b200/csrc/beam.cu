@@ -227,6 +227,8 @@ __global__ void __launch_bounds__(ADV_THREADS) beam_advance_kernel(const float* 
                                                                     int t, int T, int b, int flags, int move_state, AdvanceIO io) {
   __shared__ float s_tkv[KS * KS];
   __shared__ int32_t s_tki[KS * KS];
+  pdl_launch_dependents();
+  pdl_wait();
   constexpr int ES = (2 + 2 * KS + 3) / 4 * 4;
   const int img = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long row0 = static_cast<long long>(img) * b;
@@ -276,9 +278,9 @@ int beam_advance(const float* stats, int parts, int kslots, int32_t* beam_seq, f
                c_src, c_dst, n_state, n_img * beams, H, static_cast<const __nv_bfloat16*>(table), ld_table, xt_col0, E, V};
   launch_begin("beam_advance", stream);
 #define UIC_ADV(KS_)                                                                                                         \
-  beam_advance_kernel<KS_><<<n_img, ADV_THREADS, 0, stream>>>(stats, parts, beam_seq, beam_lp, beam_sum, done_seq, done_lp, done_p, \
-                                                              done_unaug, done_cnt, parent_row, next_tok, t, seq_length, beams,     \
-                                                              flags, move_state, io)
+  UIC_CUDA_OK(launch_pdl(beam_advance_kernel<KS_>, dim3(n_img), dim3(ADV_THREADS), 0, stream, stats, parts, beam_seq, beam_lp, beam_sum, \
+                         done_seq, done_lp, done_p, done_unaug, done_cnt, parent_row, next_tok, t, seq_length, beams, flags,       \
+                         move_state, io))
   if (kslots == 1)
     UIC_ADV(1);
   else if (kslots == 3)
@@ -303,6 +305,8 @@ __global__ void __launch_bounds__(ADV_THREADS) greedy_advance_kernel(const float
                                                                       const __nv_bfloat16* __restrict__ table, long long ld_table,
                                                                       __nv_bfloat16* __restrict__ x, long long ld_x, int E, int V,
                                                                       float temperature, const unsigned long long* __restrict__ seed) {
+  pdl_launch_dependents();
+  pdl_wait();
   if (t > 0 && n_unfinished[t - 1] == 0) return;  // the reference has left its loop (AttModel.py:250-251)
   const int r = blockIdx.x * (ADV_THREADS / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
   if (r >= rows) return;
@@ -335,9 +339,9 @@ int greedy_advance(const float* stats, int parts, int64_t* seq, float* seq_lp, u
   if (temperature > 0.0f && seed == nullptr) return set_error(UIC_ERR_ARG, "greedy_advance: sampling needs a seed (device pointer)");
   const int per = ADV_THREADS / 32;
   launch_begin("greedy_advance", stream);
-  greedy_advance_kernel<<<(rows + per - 1) / per, ADV_THREADS, 0, stream>>>(stats, parts, seq, seq_lp, unfinished, next_tok, n_unfinished,
-                                                                           t, seq_length, rows, static_cast<const __nv_bfloat16*>(table),
-                                                                           ld_table, static_cast<__nv_bfloat16*>(x_xt), ld_x, E, V, temperature, seed);
+  UIC_CUDA_OK(launch_pdl(greedy_advance_kernel, dim3((rows + per - 1) / per), dim3(ADV_THREADS), 0, stream, stats, parts, seq, seq_lp, unfinished,
+                         next_tok, n_unfinished, t, seq_length, rows, static_cast<const __nv_bfloat16*>(table), ld_table,
+                         static_cast<__nv_bfloat16*>(x_xt), ld_x, E, V, temperature, seed));
   UIC_CUDA_OK(cudaGetLastError());
   launch_end(stream);
   return 0;

@@ -153,6 +153,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  pdl_launch_dependents();
   if (ep.trace != nullptr && threadIdx.x == 0 && blockIdx.x < 448) {  // (1024-slot debug buffer) CTA entry time
     long long tnow;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tnow));
@@ -186,6 +187,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();  // everything above overlapped the previous kernel's tail; operands and outputs are touched below
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -586,7 +588,7 @@ static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const GemmEpi
   const long long tiles = static_cast<long long>((M + BM - 1) / BM) * ((N + BN - 1) / BN);
   const int grid = static_cast<int>(tiles < sm_count() ? tiles : sm_count());
   launch_begin(gemm_label(M, N, K), stream);
-  kern<<<grid, GEMM_THREADS, smem, stream>>>(ta, tb, ep, M, N, K);
+  UIC_CUDA_OK(launch_pdl(kern, dim3(grid), dim3(GEMM_THREADS), smem, stream, ta, tb, ep, M, N, K));
   UIC_CUDA_OK(cudaGetLastError());
   launch_end(stream);
   return 0;

@@ -63,6 +63,8 @@ int cast_f32_bf16(const float* src, long long ld_src, void* dst, long long ld_ds
 // ---- embedding rows -------------------------------------------------------------------------------
 __global__ void embed_rows_kernel(const __nv_bfloat16* __restrict__ table, long long ld_table, const int64_t* __restrict__ tok,
                                   __nv_bfloat16* __restrict__ out, long long ld_out, int rows, int E, int V, int vec) {
+  pdl_launch_dependents();
+  pdl_wait();
   const int per_row = vec ? E / 8 : E;
   const long long total = static_cast<long long>(rows) * per_row;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
@@ -84,8 +86,8 @@ int embed_rows(const void* table, long long ld_table, const int64_t* tok, void* 
                   ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
   const long long work = static_cast<long long>(rows) * (vec ? E / 8 : E);
   launch_begin("embed_rows", stream);
-  embed_rows_kernel<<<blocks_for(work, 256), 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(table), ld_table, tok,
-                                                                static_cast<__nv_bfloat16*>(out), ld_out, rows, E, V, vec);
+  UIC_CUDA_OK(launch_pdl(embed_rows_kernel, dim3(blocks_for(work, 256)), dim3(256), 0, stream, static_cast<const __nv_bfloat16*>(table),
+                         ld_table, tok, static_cast<__nv_bfloat16*>(out), ld_out, rows, E, V, vec));
   UIC_CUDA_OK(cudaGetLastError());
   launch_end(stream);
   return 0;
@@ -111,6 +113,8 @@ __device__ __forceinline__ void store_h(const HOut& o, int r, int j, int H, floa
 __global__ void lstm_maxout_fwd_kernel(const float* __restrict__ sums, long long ld_sums, const float* __restrict__ a2c,
                                        long long ld_a2c, const float* __restrict__ c_prev, float* __restrict__ c_out, HOut o,
                                        int rows, int H) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long total = static_cast<long long>(rows) * H;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -131,6 +135,8 @@ __global__ void lstm_maxout_fwd_kernel(const float* __restrict__ sums, long long
 // torch.nn.LSTMCell pointwise part (gate order i, f, g, o), used at models/AttModel.py:434,441.
 __global__ void lstm_cell_fwd_kernel(const float* __restrict__ gates, long long ld_gates, const float* __restrict__ c_prev,
                                      float* __restrict__ c_out, HOut o, int rows, int H) {
+  pdl_launch_dependents();
+  pdl_wait();
   const long long total = static_cast<long long>(rows) * H;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
@@ -151,8 +157,8 @@ int lstm_maxout_fwd(const float* sums, long long ld_sums, const float* a2c, long
                     float* h_f32, void* h_a, long long ld_ha, void* h_b, long long ld_hb, int rows, int H, cudaStream_t stream) {
   HOut o{h_f32, static_cast<__nv_bfloat16*>(h_a), ld_ha, static_cast<__nv_bfloat16*>(h_b), ld_hb};
   launch_begin("lstm_maxout_fwd", stream);
-  lstm_maxout_fwd_kernel<<<blocks_for(static_cast<long long>(rows) * H, 256), 256, 0, stream>>>(sums, ld_sums, a2c, ld_a2c, c_prev,
-                                                                                                 c_out, o, rows, H);
+  UIC_CUDA_OK(launch_pdl(lstm_maxout_fwd_kernel, dim3(blocks_for(static_cast<long long>(rows) * H, 256)), dim3(256), 0, stream, sums, ld_sums,
+                         a2c, ld_a2c, c_prev, c_out, o, rows, H));
   UIC_CUDA_OK(cudaGetLastError());
   launch_end(stream);
   return 0;
@@ -162,8 +168,8 @@ int lstm_cell_fwd(const float* gates, long long ld_gates, const float* c_prev, f
                   long long ld_ha, void* h_b, long long ld_hb, int rows, int H, cudaStream_t stream) {
   HOut o{h_f32, static_cast<__nv_bfloat16*>(h_a), ld_ha, static_cast<__nv_bfloat16*>(h_b), ld_hb};
   launch_begin("lstm_cell_fwd", stream);
-  lstm_cell_fwd_kernel<<<blocks_for(static_cast<long long>(rows) * H, 256), 256, 0, stream>>>(gates, ld_gates, c_prev, c_out, o,
-                                                                                               rows, H);
+  UIC_CUDA_OK(launch_pdl(lstm_cell_fwd_kernel, dim3(blocks_for(static_cast<long long>(rows) * H, 256)), dim3(256), 0, stream, gates, ld_gates,
+                         c_prev, c_out, o, rows, H));
   UIC_CUDA_OK(cudaGetLastError());
   launch_end(stream);
   return 0;

@@ -34,6 +34,31 @@ int get_tensor_map_bf16_slabs(CUtensorMap* out, const void* base, long long rows
       return ::uic::set_error(UIC_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
   } while (0)
 
+// Programmatic dependent launch (PDL): a kernel launched through launch_pdl may be scheduled while its stream
+// predecessor is still draining, so its launch latency and set-up (barrier init, TMEM allocation, descriptor
+// prefetch) overlap the predecessor's tail.  Contract for such a kernel: call pdl_launch_dependents() first and
+// pdl_wait() before the first access to any global memory a predecessor writes, or that it writes itself.
+// pdl_wait() returns when every predecessor grid has completed and flushed.  UIC_PDL=0 turns the attribute off.
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+}
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+#endif
+
 // kernels.  Each returns 0 or a negative UIC_ERR_* (after set_error).
 int gemm_bf16(const void* A, long long lda, const void* B, long long ldb, float* c_f32, long long ldc, void* c_bf16,
               long long ldcb, const float* bias, int M, int N, int K, int flags, cudaStream_t stream, int exp_col0 = 0,
