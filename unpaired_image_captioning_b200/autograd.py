@@ -292,9 +292,11 @@ class _DecoderLossFn(torch.autograd.Function):
     def backward(ctx, grad_out):
         r, o = ctx.run, ctx.logit
         names, params = _param_list(r.model)
-        g = bptt(r, o["dh"])
-        g["logit.weight"], g["logit.bias"] = o["dW"], o["db"]
-        return (None,) * 7 + tuple(_finish(r, g, grad_out, names, params))
+        # every gradient is linear in (d h, d W_logit, d b_logit): scaling these three by the incoming gradient
+        # replaces one strided multiply per parameter (24 launches) by three
+        g = bptt(r, o["dh"] * grad_out)
+        g["logit.weight"], g["logit.bias"] = o["dW"] * grad_out, o["db"] * grad_out
+        return (None,) * 7 + tuple(_finish(r, g, None, names, params))
 
 
 class _DecoderLogprobsFn(torch.autograd.Function):
