@@ -287,10 +287,13 @@ def run_b200(args, world, rank, local):
         peak, how = _peaks()
         alg_bytes = B * cfg["att_size"] * (opt.att_hid_size + opt.rnn_size) * 2      # p_att + att tiles, bf16, once per image
         achieved = alg_bytes / (ms_att / n_att * 1e-3) / 1e9
+        traffic, traffic_src = _ncu_traffic()
         roofline = {"kernel": "att_step_fwd", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": None, "peak_source": how,
+                    "frac": achieved / peak, "traffic": traffic, "peak_source": how,
                     "algorithmic_bytes_per_launch": alg_bytes, "us_per_launch": ms_att / n_att * 1e3,
-                    "note": "tiles (103 MB) are partly L2-resident across steps; see profiles/ for the ncu DRAM bytes"}
+                    "traffic_source": traffic_src,
+                    "note": "duration: live CUDA-event pairs around every launch of an eager decode in this run; traffic: "
+                            "dram__bytes_read.sum + dram__bytes_write.sum of the committed ncu --set full capture of the same launch"}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -313,6 +316,27 @@ def run_b200(args, world, rank, local):
         _emit(line)
     if world > 1:
         torch.distributed.destroy_process_group()
+
+
+def _ncu_traffic():
+    """DRAM bytes per launch of the attention kernel from the newest committed `ncu --set full` capture of this workload
+    (profiles/*att_step_fwd_ncu_raw.csv, written by scripts/gpu_round5.sh); (None, reason) when there is none."""
+    import csv
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*att_step_fwd_ncu_raw.csv")))
+    if not files:
+        return None, "no ncu capture under profiles/"
+    try:
+        rows = list(csv.reader(open(files[-1])))
+        head, units, vals = rows[0], rows[1], rows[2]
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        total = 0.0
+        for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            i = head.index(key)
+            total += float(vals[i].replace(",", "")) * scale[units[i]]
+        return total, os.path.relpath(files[-1], ROOT)
+    except (ValueError, KeyError, IndexError, OSError) as exc:
+        return None, f"unreadable capture {os.path.basename(files[-1])}: {exc}"
 
 
 _RESULT_OUT = None

@@ -198,7 +198,16 @@ struct AdvanceIO {
   const __nv_bfloat16* table;
   long long ld_table;
   int xt_col0, E, V;
+  long long* trace;  // debug (uic_gemm_set_trace buffer): CTA 0 records %globaltimer after each phase in slots 110..113
 };
+#define ADV_TRACE(slot)                                                         \
+  do {                                                                         \
+    if (io.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0) {          \
+      long long tnow;                                                          \
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tnow));                  \
+      io.trace[slot] = tnow;                                                   \
+    }                                                                          \
+  } while (0)
 
 __device__ __forceinline__ void copy_row_bf16(__nv_bfloat16* dst, const __nv_bfloat16* src, int n, int tid, int nthreads) {
   if (((reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src)) & 15) == 0 && (n & 7) == 0) {
@@ -229,6 +238,7 @@ __global__ void __launch_bounds__(ADV_THREADS) beam_advance_kernel(const float* 
   __shared__ int32_t s_tki[KS * KS];
   pdl_launch_dependents();
   pdl_wait();
+  ADV_TRACE(110);
   constexpr int ES = (2 + 2 * KS + 3) / 4 * 4;
   const int img = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long row0 = static_cast<long long>(img) * b;
@@ -246,25 +256,31 @@ __global__ void __launch_bounds__(ADV_THREADS) beam_advance_kernel(const float* 
     }
   }
   __syncthreads();
+  ADV_TRACE(111);
   // 2. beam bookkeeping
   if (warp == 0)
     beam_step_image(s_tkv, s_tki, beam_seq, beam_lp, beam_sum, done_seq, done_lp, done_p, done_unaug, done_cnt, parent_row,
                     next_tok, img, t, T, b, flags);
   if (!move_state) return;
   __syncthreads();
-  // 3. state of the parents + next embeddings into the other buffer
-  for (int v = 0; v < b; ++v) {
+  ADV_TRACE(112);
+  // 3. state of the parents + next embeddings into the other buffer: one warp per beam row, so the rows' loads are
+  //    all in flight together
+  const int lane3 = threadIdx.x & 31;
+  for (int v = warp; v < b; v += ADV_THREADS / 32) {
     const long long r = row0 + v;
     const long long q = parent_row[r];
-    copy_row_bf16(io.x_dst + r * io.ld_x + io.col0_a, io.x_src + q * io.ld_x + io.col0_a, io.ncol_a, threadIdx.x, ADV_THREADS);
-    copy_row_bf16(io.x_dst + r * io.ld_x + io.col0_b, io.x_src + q * io.ld_x + io.col0_b, io.ncol_b, threadIdx.x, ADV_THREADS);
-    for (int s = 0; s < io.n_state; ++s)
-      copy_row_f32(io.c_dst + (static_cast<long long>(s) * io.rows + r) * io.H, io.c_src + (static_cast<long long>(s) * io.rows + q) * io.H,
-                   io.H, threadIdx.x, ADV_THREADS);
     long long tk = next_tok[r];
     tk = tk < 0 ? 0 : (tk >= io.V ? io.V - 1 : tk);
-    copy_row_bf16(io.x_dst + r * io.ld_x + io.xt_col0, io.table + tk * io.ld_table, io.E, threadIdx.x, ADV_THREADS);
+    copy_row_bf16(io.x_dst + r * io.ld_x + io.col0_a, io.x_src + q * io.ld_x + io.col0_a, io.ncol_a, lane3, 32);
+    copy_row_bf16(io.x_dst + r * io.ld_x + io.col0_b, io.x_src + q * io.ld_x + io.col0_b, io.ncol_b, lane3, 32);
+    copy_row_bf16(io.x_dst + r * io.ld_x + io.xt_col0, io.table + tk * io.ld_table, io.E, lane3, 32);
+    for (int s = 0; s < io.n_state; ++s)
+      copy_row_f32(io.c_dst + (static_cast<long long>(s) * io.rows + r) * io.H, io.c_src + (static_cast<long long>(s) * io.rows + q) * io.H,
+                   io.H, lane3, 32);
   }
+  __syncthreads();
+  ADV_TRACE(113);
 }
 
 int beam_advance(const float* stats, int parts, int kslots, int32_t* beam_seq, float* beam_lp, float* beam_sum, int32_t* done_seq,
@@ -275,7 +291,8 @@ int beam_advance(const float* stats, int parts, int kslots, int32_t* beam_seq, f
   if (beams > kslots || seq_length > BEAM_T_MAX)
     return set_error(UIC_ERR_SHAPE, "beam_advance: beams=%d (kslots %d), seq_length=%d (max %d)", beams, kslots, seq_length, BEAM_T_MAX);
   AdvanceIO io{static_cast<const __nv_bfloat16*>(x_src), static_cast<__nv_bfloat16*>(x_dst), ld_x, col0_a, ncol_a, col0_b, ncol_b,
-               c_src, c_dst, n_state, n_img * beams, H, static_cast<const __nv_bfloat16*>(table), ld_table, xt_col0, E, V};
+               c_src, c_dst, n_state, n_img * beams, H, static_cast<const __nv_bfloat16*>(table), ld_table, xt_col0, E, V,
+               gemm_trace_buffer()};
   launch_begin("beam_advance", stream);
 #define UIC_ADV(KS_)                                                                                                         \
   UIC_CUDA_OK(launch_pdl(beam_advance_kernel<KS_>, dim3(n_img), dim3(ADV_THREADS), 0, stream, stats, parts, beam_seq, beam_lp, beam_sum, \

@@ -72,40 +72,47 @@ __device__ __forceinline__ RowStats merge_row_stats(const float* __restrict__ st
     kv[q] = -INFINITY;
     ki[q] = EMPTY;
   }
+  // Lanes take parts lane, lane + 32, ...; the entries of four such rounds are requested back to back (the parts were
+  // written by the GEMM epilogue a moment ago: L2 hits whose latency would otherwise be paid once per round).
   const float4* base = reinterpret_cast<const float4*>(st);
-  float4 nxt[ES / 4];
-  if (lane < parts) {
+  constexpr int ROUNDS = 4;
+  for (int p0 = lane; p0 < parts; p0 += 32 * ROUNDS) {
+    float4 ent[ROUNDS][ES / 4];
 #pragma unroll
-    for (int w = 0; w < ES / 4; ++w) nxt[w] = base[static_cast<long long>(lane) * (ES / 4) + w];
-  }
-  for (int p = lane; p < parts; p += 32) {
-    float e[ES];
+    for (int rd = 0; rd < ROUNDS; ++rd) {
+      const int p = p0 + 32 * rd;
+      if (p < parts) {
 #pragma unroll
-    for (int w = 0; w < ES / 4; ++w) {
-      e[4 * w] = nxt[w].x;
-      e[4 * w + 1] = nxt[w].y;
-      e[4 * w + 2] = nxt[w].z;
-      e[4 * w + 3] = nxt[w].w;
-    }
-    if (p + 32 < parts) {  // the next entry's loads fly while this one is merged
-#pragma unroll
-      for (int w = 0; w < ES / 4; ++w) nxt[w] = base[static_cast<long long>(p + 32) * (ES / 4) + w];
-    }
-    a = ms_merge(a, MaxSum{e[0], e[1]});
-#pragma unroll
-    for (int c = 0; c < KS; ++c) {
-      const float x = e[2 + c];
-      const int col = __float_as_int(e[2 + KS + c]);
-      bool pr[KS];
-#pragma unroll
-      for (int q = 0; q < KS; ++q) pr[q] = col != EMPTY && (x > kv[q] || (x == kv[q] && col < ki[q]));
-#pragma unroll
-      for (int q = KS - 1; q > 0; --q) {
-        kv[q] = pr[q - 1] ? kv[q - 1] : (pr[q] ? x : kv[q]);
-        ki[q] = pr[q - 1] ? ki[q - 1] : (pr[q] ? col : ki[q]);
+        for (int w = 0; w < ES / 4; ++w) ent[rd][w] = base[static_cast<long long>(p) * (ES / 4) + w];
       }
-      kv[0] = pr[0] ? x : kv[0];
-      ki[0] = pr[0] ? col : ki[0];
+    }
+#pragma unroll
+    for (int rd = 0; rd < ROUNDS; ++rd) {
+      if (p0 + 32 * rd >= parts) break;
+      float e[ES];
+#pragma unroll
+      for (int w = 0; w < ES / 4; ++w) {
+        e[4 * w] = ent[rd][w].x;
+        e[4 * w + 1] = ent[rd][w].y;
+        e[4 * w + 2] = ent[rd][w].z;
+        e[4 * w + 3] = ent[rd][w].w;
+      }
+      a = ms_merge(a, MaxSum{e[0], e[1]});
+#pragma unroll
+      for (int c = 0; c < KS; ++c) {
+        const float x = e[2 + c];
+        const int col = __float_as_int(e[2 + KS + c]);
+        bool pr[KS];
+#pragma unroll
+        for (int q = 0; q < KS; ++q) pr[q] = col != EMPTY && (x > kv[q] || (x == kv[q] && col < ki[q]));
+#pragma unroll
+        for (int q = KS - 1; q > 0; --q) {
+          kv[q] = pr[q - 1] ? kv[q - 1] : (pr[q] ? x : kv[q]);
+          ki[q] = pr[q - 1] ? ki[q - 1] : (pr[q] ? col : ki[q]);
+        }
+        kv[0] = pr[0] ? x : kv[0];
+        ki[0] = pr[0] ? col : ki[0];
+      }
     }
   }
 #pragma unroll
