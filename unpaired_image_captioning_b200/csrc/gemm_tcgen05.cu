@@ -65,6 +65,10 @@ struct GemmEpilogue {
   float inv_temperature;
   const unsigned long long* seed;  // device memory: a captured CUDA graph can be replayed with a new seed
   int step;
+  // Persistent tile walk: consecutive tiles share the B tile (m fastest, default) or the A tile (n fastest).  When A is
+  // the big operand (feature prologue: 50176 x 2048 against 512 x 2048) the m-fastest walk re-reads every A tile from HBM
+  // once per column of tiles; n-fastest reads it once and finds it in L2 for the others.
+  int n_fastest;
 };
 
 #define UIC_TRACE(slot)                                                              \
@@ -194,7 +198,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     if (lane == 0) {
       int g = 0;  // global k-block counter: ring position carries over from tile to tile
       for (int tile = blockIdx.x, it = 0; tile < num_tiles; tile += gridDim.x, ++it) {
-        const int m0 = (tile % tiles_m) * BM, n0 = (tile / tiles_m) * BN;
+        const int m0 = (ep.n_fastest ? tile / tiles_n : tile % tiles_m) * BM, n0 = (ep.n_fastest ? tile % tiles_n : tile / tiles_m) * BN;
         for (int kb = 0; kb < num_kb; ++kb, ++g) {
           const int s = g % STAGES;
           const uint32_t ph = (g / STAGES) & 1;
@@ -265,7 +269,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     const bool vec_16 = ep.c_bf16 != nullptr && (ep.ldcb % 4 == 0) && ((reinterpret_cast<uintptr_t>(ep.c_bf16) & 7) == 0);
     const bool vec_bias = ep.bias != nullptr && ((reinterpret_cast<uintptr_t>(ep.bias) & 15) == 0);
     for (int tile = blockIdx.x, it = 0; tile < num_tiles; tile += gridDim.x, ++it) {
-      const int m0 = (tile % tiles_m) * BM, n0 = (tile / tiles_m) * BN;
+      const int m0 = (ep.n_fastest ? tile / tiles_n : tile % tiles_m) * BM, n0 = (ep.n_fastest ? tile % tiles_n : tile / tiles_m) * BN;
       const int acc = it & 1;
       if constexpr (STATS > 0) {
         // ---- fused vocabulary statistics: the (rows, V) logits are never written to memory ----------------
@@ -360,7 +364,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           }
 #pragma unroll
           for (int qq = 2 + 2 * STATS; qq < ES; ++qq) out[qq] = 0.0f;
-          float4* dst = reinterpret_cast<float4*>(ep.stats + (static_cast<long long>(row) * ep.parts + (tile / tiles_m) * 2 + ehalf) * ES);
+          float4* dst = reinterpret_cast<float4*>(ep.stats + (static_cast<long long>(row) * ep.parts + (n0 / BN) * 2 + ehalf) * ES);
 #pragma unroll
           for (int qq = 0; qq < ES / 4; ++qq) dst[qq] = make_float4(out[4 * qq], out[4 * qq + 1], out[4 * qq + 2], out[4 * qq + 3]);
         }
@@ -612,6 +616,8 @@ int gemm_bf16(const void* A, long long lda, const void* B, long long ldb, float*
   const bool b_mn = flags & UIC_GEMM_B_MN_MAJOR;
   GemmEpilogue ep{c_f32, ldc, static_cast<__nv_bfloat16*>(c_bf16), ldcb, bias, (flags & UIC_GEMM_RELU) ? 1 : 0,
                   (flags & UIC_GEMM_ACCUMULATE) ? 1 : 0, (flags & UIC_GEMM_OUT_F16) ? 1 : 0, exp_col0, exp_scale, gemm_trace_buffer(), gemm_debug_flags(), nullptr, nullptr, 0, 0, -1};
+  // tile walk: keep the bigger operand's tile hot (see GemmEpilogue::n_fastest); the smaller one must fit L2 comfortably
+  ep.n_fastest = (M > N && static_cast<long long>(N) * K * 2 <= (32LL << 20)) ? 1 : 0;
   if (gemm_impl() == GEMM_IMPL_SIMT) {
     dim3 grid((N + 15) / 16, (M + 15) / 16), block(16, 16);
     launch_begin("gemm_bf16_simt", stream);
