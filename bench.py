@@ -214,11 +214,11 @@ def run_b200(args, world, rank, local):
 
     # ---- device-resident legs ------------------------------------------------------------------
     def beam_step():
-        feats = eng.prepare(fc_d, att_d)
+        feats = eng.prepare(fc_d, att_d, lazy=True)
         eng.beam(feats, T, beam)
 
     def greedy_step():
-        feats = eng.prepare(fc_d, att_d)
+        feats = eng.prepare(fc_d, att_d, lazy=True)
         eng.greedy(feats, T)
 
     ms_beam = _timed(beam_step, args.steps, args.warmup, world)

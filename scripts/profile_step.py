@@ -30,7 +30,7 @@ def step():
         from unpaired_image_captioning_b200.train_bench import one_train_step
         one_train_step(model, opt, cfg, fc, att)
         return
-    feats = eng.prepare(fc, att)
+    feats = eng.prepare(fc, att, lazy=True)
     if mode == "beam":
         eng.beam(feats, opt.seq_length, cfg["beam_size"])
     else:

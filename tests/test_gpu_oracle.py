@@ -83,3 +83,14 @@ def test_config5_layer_sizes_beam5_and_greedy():
     exact, exempt, failures = compare_greedy(g_seq.cpu(), g_ref, margins, tol=2e-2)
     assert not failures, failures
     assert exact >= 1
+
+
+def test_bf16_feature_cache_is_consumed_directly():
+    """Features handed over as bf16 (a host/device feature cache in the operand precision) give the same captions as the
+    fp32 tensors they were rounded from, up to that rounding."""
+    opt, sd, model, fc, att, *_ = _case("att2in2", 6, 49, seed=5, peaked=40.0, eos_bias=2.0)
+    att_bf = att.cuda().to(torch.bfloat16)
+    seq_a, lp_a = model(fc.cuda(), None, att_bf.float(), None, opt={"beam_size": 3}, mode="sample")
+    seq_b, lp_b = model(fc.cuda(), None, att_bf, None, opt={"beam_size": 3}, mode="sample")
+    assert torch.equal(seq_a, seq_b)
+    torch.testing.assert_close(lp_a, lp_b, rtol=0, atol=0)

@@ -100,6 +100,24 @@ class Features:
     def __init__(self, att, p_att, fc, masks, B, L):
         self.att, self.p_att, self.fc, self.masks, self.B, self.L = att, p_att, fc, masks, B, L
 
+    @property
+    def device(self):
+        return self.att.device
+
+
+class LazyFeatures:
+    """Clipped raw inputs of the prologue; `materialize(out)` runs it into the given Features buffers."""
+
+    def __init__(self, engine, fc_feats, att_feats, masks, B, L):
+        self.engine, self.fc_feats, self.att_feats, self.masks, self.B, self.L = engine, fc_feats, att_feats, masks, B, L
+
+    @property
+    def device(self):
+        return self.att_feats.device
+
+    def materialize(self, out):
+        return self.engine.prepare(self.fc_feats, self.att_feats, self.masks, out=out, clip=False)
+
 
 class DecoderEngine:
     def __init__(self, model):
@@ -123,32 +141,52 @@ class DecoderEngine:
         return self._packed
 
     # ---- prologue ---------------------------------------------------------------------------------
-    def prepare(self, fc_feats, att_feats, att_masks=None, keep_inputs=False):
-        """clip_att + fc_embed + att_embed + ctx2att (models/AttModel.py:99-117)."""
+    def prepare(self, fc_feats, att_feats, att_masks=None, keep_inputs=False, lazy=False, out=None, clip=True):
+        """clip_att + fc_embed + att_embed + ctx2att (models/AttModel.py:99-117).
+
+        lazy=True only clips and returns a LazyFeatures: the decode loops then run the prologue straight into the
+        static buffers of their CUDA graph (`out`), instead of producing the tiles here and copying 200 MB across."""
         w = self.w
-        if att_masks is not None:  # clip to the longest valid length (:99-105)
+        if att_masks is not None and clip:  # clip to the longest valid length (:99-105)
             keep = int(att_masks.long().sum(1).max())
             att_feats, att_masks = att_feats[:, :keep], att_masks[:, :keep].contiguous().float()
         B, L, D = att_feats.shape
         H, A = w.H, w.A
-        x = _lib.cast_bf16(att_feats.reshape(B * L, D).float() if att_feats.dtype != torch.float32 else att_feats.reshape(B * L, D))
-        att = torch.empty(B * L, H, dtype=BF16, device=x.device)
+        if lazy:
+            return LazyFeatures(self, fc_feats, att_feats, att_masks, B, L)
+        if att_feats.dtype == BF16:   # a bf16 feature cache is consumed as is (no staging pass, half the H2D bytes)
+            x = att_feats.reshape(B * L, D)
+            x = x if x.is_contiguous() else x.contiguous()
+        else:
+            x = _lib.cast_bf16(att_feats.reshape(B * L, D).float() if att_feats.dtype != torch.float32 else att_feats.reshape(B * L, D))
+        att = torch.empty(B * L, H, dtype=BF16, device=x.device) if out is None else out.att.view(B * L, H)
         gemm(x, w.w_att_embed, w.b_att_embed, out_bf16=att, relu=True)
         if att_masks is not None:
             check(self.lib.uic_zero_padded_rows(ptr(att), ptr(att_masks), B, L, H, stream()))
         # p_att is stored in the exponential operand form E = exp(2 p_att)/16 (fp16): the step kernel then
         # gets tanh(p_att + att_h) = 1 - 2/(E F + 1) from an FMA and a shared reciprocal (MUFU.TANH is quarter rate)
-        p_att = torch.empty(B * L, A, dtype=torch.float16, device=x.device)
+        p_att = torch.empty(B * L, A, dtype=torch.float16, device=x.device) if out is None else out.p_att.view(B * L, A)
         gemm(att, w.w_ctx2att, w.b_ctx2att, out_bf16=p_att, exp_col0=0, exp_scale=_lib.ATT_E_SCALE)
         fc = None
         if self.kind == "topdown":
-            fc = torch.empty(B, H, dtype=BF16, device=x.device)
+            fc = torch.empty(B, H, dtype=BF16, device=x.device) if out is None else out.fc
             fc_in = _lib.cast_bf16(fc_feats.float().contiguous())
             gemm(fc_in, w.w_fc, w.b_fc, out_bf16=fc, relu=True)
+        if out is not None:
+            if att_masks is not None:
+                out.masks.copy_(att_masks)
+            return out
         feats = Features(att.view(B, L, H), p_att.view(B, L, A), fc, att_masks, B, L)
         if keep_inputs:  # bf16 operand copies of the raw features, needed by the prologue wgrads
             feats.x_in, feats.fc_in = x, (fc_in if self.kind == "topdown" else None)
         return feats
+
+    def _feature_buffers(self, feats):
+        """Static per-graph copies of the feature tiles (shapes of `feats`, a Features or a LazyFeatures)."""
+        w, dev, B, L = self.w, feats.device, feats.B, feats.L
+        return {"att": torch.empty(B, L, w.H, dtype=BF16, device=dev), "p_att": torch.empty(B, L, w.A, dtype=torch.float16, device=dev),
+                "fc": torch.empty(B, w.H, dtype=BF16, device=dev) if self.kind == "topdown" else None,
+                "masks": None if feats.masks is None else torch.empty(B, L, dtype=torch.float32, device=dev)}
 
     # ---- one decoder step: X, c -> logits -------------------------------------------------------------
     def _workspace(self, R, dev):
@@ -228,7 +266,7 @@ class DecoderEngine:
         the arg-max of the logits perturbed by Gumbel noise, which is a function of (seed, step, row, column).
         `seed`: an int, or None to draw one from torch's CUDA generator (so torch.manual_seed controls it)."""
         w, lib = self.w, self.lib
-        B, dev, T = feats.B, feats.att.device, seq_length
+        B, dev, T = feats.B, feats.device, seq_length
         flags = _lib.SAMPLE_DECODING_CONSTRAINT if decoding_constraint else 0
         temperature = float(temperature)
         if temperature > 0.0 and not self.fused_vocab:
@@ -236,9 +274,7 @@ class DecoderEngine:
         key = ("greedy", B, feats.L, T, flags, feats.masks is not None, self.fused_vocab, temperature)
 
         def alloc():
-            s = {"att": torch.empty_like(feats.att), "p_att": torch.empty_like(feats.p_att),
-                 "fc": None if feats.fc is None else torch.empty_like(feats.fc),
-                 "masks": None if feats.masks is None else torch.empty_like(feats.masks),
+            s = {**self._feature_buffers(feats),
                  "ws": self._workspace(B, dev),
                  "seq": torch.zeros(B, T, dtype=torch.int64, device=dev), "lp": torch.zeros(B, T, device=dev),
                  "unf": torch.zeros(B, dtype=torch.uint8, device=dev), "tok": torch.zeros(B, dtype=torch.int64, device=dev),
@@ -291,16 +327,14 @@ class DecoderEngine:
     # ---- beam search (models/AttModel.py:167-196 + models/CaptionModel.py:33-177) -------------------------
     def beam(self, feats, seq_length, beam_size, decoding_constraint=0, max_ppl=0):
         w, lib = self.w, self.lib
-        B, dev, T, b = feats.B, feats.att.device, seq_length, beam_size
+        B, dev, T, b = feats.B, feats.device, seq_length, beam_size
         R = B * b
         tk_flags = _lib.SAMPLE_DECODING_CONSTRAINT if decoding_constraint else 0
         bs_flags = _lib.BEAM_MAX_PPL if max_ppl else 0
         key = ("beam", B, b, feats.L, T, tk_flags, bs_flags, feats.masks is not None, self.fused_vocab)
 
         def alloc():
-            s = {"att": torch.empty_like(feats.att), "p_att": torch.empty_like(feats.p_att),
-                 "fc": None if feats.fc is None else torch.empty_like(feats.fc),
-                 "masks": None if feats.masks is None else torch.empty_like(feats.masks),
+            s = {**self._feature_buffers(feats),
                  "ws": self._workspace(R, dev),
                  "tk_val": torch.empty(R, b, device=dev), "tk_idx": torch.empty(R, b, dtype=torch.int32, device=dev),
                  "beam_seq": torch.zeros(B, b, T, dtype=torch.int32, device=dev), "beam_lp": torch.zeros(B, b, T, device=dev),
@@ -398,6 +432,9 @@ class DecoderEngine:
 
     @staticmethod
     def _load_feats(s, feats):
+        if isinstance(feats, LazyFeatures):
+            feats.materialize(s["feats"])
+            return
         s["att"].copy_(feats.att)
         s["p_att"].copy_(feats.p_att)
         if feats.fc is not None:

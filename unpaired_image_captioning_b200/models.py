@@ -278,7 +278,7 @@ class AttModel(CaptionModel):
             raise NotImplementedError("diverse beam search (group_size > 1) is not on the B200 hot path yet")
         assert beam_size <= self.vocab_size + 1, "lets assume this for now, otherwise this corner case causes a few headaches down the road. can be dealt with in future if needed"
         eng = self.engine
-        feats = eng.prepare(fc_feats, att_feats, att_masks)
+        feats = eng.prepare(fc_feats, att_feats, att_masks, lazy=True)
         done_seq, done_lp, done_p, done_unaug, done_cnt = eng.beam(
             feats, self.seq_length, beam_size, opt.get("decoding_constraint", 0), opt.get("max_ppl", 0))
         # one D2H for everything the reference keeps on the CPU (seq, seqLogprobs, done_beams)
@@ -300,7 +300,7 @@ class AttModel(CaptionModel):
             if beam_size > 1:
                 return self._sample_beam(fc_feats, att_feats, att_masks, opt)
             eng = self.engine
-            feats = eng.prepare(fc_feats, att_feats, att_masks)
+            feats = eng.prepare(fc_feats, att_feats, att_masks, lazy=True)
             if sample_max:
                 seq, lp = eng.greedy(feats, self.seq_length, decoding_constraint)
                 return seq.clone(), lp.clone()
