@@ -233,30 +233,42 @@ def run_b200(args, world, rank, local):
     # its sequences back; the copy of step i+1 is issued on a side stream while step i decodes (two device
     # buffer sets), as a loader would.  Each timed step still contains exactly one H2D and one D2H.
     copy_stream = torch.cuda.Stream()
-    dev_bufs = [(torch.empty_like(fc_d), torch.empty_like(att_d)) for _ in range(2)]
-    pipe = {"i": 0, "ready": None}
 
-    def _prefetch(slot):
-        with torch.cuda.stream(copy_stream):
-            dev_bufs[slot][0].copy_(fc_h, non_blocking=True)
-            dev_bufs[slot][1].copy_(att_h, non_blocking=True)
-            ev = torch.cuda.Event()
-            ev.record(copy_stream)
-        return ev
+    def make_e2e(att_host):
+        dev_bufs = [(torch.empty_like(fc_d), torch.empty(att_host.shape, dtype=att_host.dtype, device=fc_d.device)) for _ in range(2)]
+        pipe = {"i": 0, "ready": None}
 
-    def e2e_step():
-        slot = pipe["i"] % 2
-        ev = pipe["ready"] if pipe["ready"] is not None else _prefetch(slot)
-        torch.cuda.current_stream().wait_event(ev)
-        pipe["ready"] = _prefetch(1 - slot)      # next step's batch, overlapped with this step's decode
-        pipe["i"] += 1
-        fc, att = dev_bufs[slot]
-        seq, lp = model(fc, None, att, None, opt=sample_opt, mode="sample")   # returns CPU tensors (D2H inside)
-        return seq
+        def _prefetch(slot):
+            with torch.cuda.stream(copy_stream):
+                dev_bufs[slot][0].copy_(fc_h, non_blocking=True)
+                dev_bufs[slot][1].copy_(att_host, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+            return ev
 
-    ms_e2e = _timed_wall(e2e_step, args.steps, args.warmup, world)
+        def e2e_step():
+            slot = pipe["i"] % 2
+            ev = pipe["ready"] if pipe["ready"] is not None else _prefetch(slot)
+            torch.cuda.current_stream().wait_event(ev)
+            pipe["ready"] = _prefetch(1 - slot)      # next step's batch, overlapped with this step's decode
+            pipe["i"] += 1
+            fc, att = dev_bufs[slot]
+            seq, lp = model(fc, None, att, None, opt=sample_opt, mode="sample")   # returns CPU tensors (D2H inside)
+            return seq
+
+        return e2e_step
+
+    ms_e2e = _timed_wall(make_e2e(att_h), args.steps, args.warmup, world)
     h2d = fc_h.numel() * 4 + att_h.numel() * 4
     d2h = B * beam * T * (8 + 4) + B * beam * (8 + 4) + B * 4      # done tables: seq(int64 after cast)+logps, p, unaug, cnt
+    # the same loop fed from a bf16 feature cache on the host: half the PCIe bytes, no staging cast.
+    # Reported beside the contract's e2e number, which keeps the reference's fp32 inputs.
+    att_h16 = att_h.to(torch.bfloat16).pin_memory()
+    ms_e2e16 = _timed_wall(make_e2e(att_h16), args.steps, args.warmup, world)
+    e2e_bf16 = {"value": world * B / (ms_e2e16 * 1e-3), "unit": "captions/s", "ms_per_step": ms_e2e16,
+                "h2d_bytes_per_step": fc_h.numel() * 4 + att_h16.numel() * 2, "d2h_bytes_per_step": d2h,
+                "note": "host features cached in bf16 (the precision the kernels consume); not the contract's e2e"}
+    del att_h16
 
     # ---- training leg (teacher-forced fwd + XE + bwd + Adam), if the autograd path is present -------
     train = None
@@ -310,6 +322,7 @@ def run_b200(args, world, rank, local):
                 "data": "synthetic", "config": _config(cfg, opt), "clocks": clocks,
                 "e2e": {"value": world * B / (ms_e2e * 1e-3), "unit": "captions/s", "h2d_bytes_per_step": h2d,
                         "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e},
+                "e2e_bf16_feature_cache": e2e_bf16,
                 "gpu_launches": int(launches * args.steps),
                 "greedy_captions_per_s": world * B / (ms_greedy * 1e-3), "greedy_ms_per_step": ms_greedy,
                 "train": train, "roofline": roofline, "kernel_shares": shares, "cpu_baseline": cpu}
