@@ -190,6 +190,14 @@ int uic_greedy_advance(const float* stats, int parts, int64_t* seq, float* seq_l
                        int32_t* n_unfinished, int t, int seq_length, int rows, const void* emb_table_bf16, int64_t ld_table,
                        void* x_xt_bf16, int64_t ld_x, int E, int V, float temperature, const uint64_t* seed, void* stream);
 
+/* Scheduled sampling (models/AttModel.py:130-143): input token of teacher-forced step t = with probability ss_prob per
+ * row a draw from softmax(logits of step t-1) (statistics from uic_logit_stats(kslots = 1, temperature = 1, seed, step = t)),
+ * else gt_tok[r * gt_stride]; written to tokens_out[r], its embedding row to x_xt_bf16[r, 0:E].  The per-row coin is
+ * the same counter-based hash (column 0x7fffffff).  `seed`: device pointer. */
+int uic_ss_advance(const float* stats, int parts, const int64_t* gt_tok, int64_t gt_stride, float ss_prob, const uint64_t* seed,
+                   int t, int64_t* tokens_out, int rows, const void* emb_table_bf16, int64_t ld_table, void* x_xt_bf16, int64_t ld_x,
+                   int E, int V, void* stream);
+
 /* One beam-search bookkeeping step for all images at once (models/CaptionModel.py:48-97,155-172):
  * merges the beams x k candidates of each image (c-major, q-minor stable order), forks the
  * sequence tables, records finished hypotheses (token 0 or last step) into the sorted done lists,

@@ -135,20 +135,42 @@ def logprobs_state(sd, kind, it, fc, att, p_att, att_masks, state):
 # ------------------------------------------------------------------------------------------------
 # teacher-forced forward -- models/AttModel.py:119-156 (ss_prob == 0)
 # ------------------------------------------------------------------------------------------------
-def teacher_forced(sd, kind, fc_feats, att_feats, seq, att_masks=None):
+def teacher_forced(sd, kind, fc_feats, att_feats, seq, att_masks=None, ss_prob=0.0, ss_seed=0, return_tokens=False,
+                   inputs=None):
+    """models/AttModel.py:119-156.  ss_prob > 0: scheduled sampling as in training mode (:130-143) -- per row a uniform
+    draw against ss_prob decides whether the input token of step i is a sample from exp(outputs[:, i-1]) (detached)
+    instead of seq[:, i].  The draws use the counter-based noise shared with the product path (see gumbel_noise):
+    Gumbel-max for the token (same distribution as the reference's torch.multinomial) and column 0x7fffffff of the
+    same hash for the coin.  `inputs` (B, T): feed exactly these tokens instead (to compare losses and gradients for
+    the draws another implementation made)."""
     B, T = fc_feats.size(0), seq.size(1) - 1
     V = sd["logit.weight"].size(0)
     state = init_hidden(sd, kind, B)
     fc, att, p_att, masks = prepare_features(sd, kind, fc_feats, att_feats, att_masks)
-    steps = []
+    steps, used, margins = [], [], []
     for i in range(T):
+        it = seq[:, i].clone()
+        margin = torch.full((B,), float("inf"))
+        if inputs is not None:
+            it = inputs[:, i].clone()
+        elif i >= 1 and ss_prob > 0.0:                                  # :130-143
+            coin = uniform_noise(ss_seed, i, B)
+            keys = steps[-1].detach() + gumbel_noise(ss_seed, i, B, V)
+            top2 = keys.topk(2, dim=1)
+            sample_mask = coin < ss_prob
+            it[sample_mask] = top2.indices[:, 0][sample_mask]
+            margin[sample_mask] = (top2.values[:, 0] - top2.values[:, 1])[sample_mask]
         if i >= 1 and int(seq[:, i].sum()) == 0:                        # :148-151
             break
-        lp, state = logprobs_state(sd, kind, seq[:, i], fc, att, p_att, masks, state)
+        lp, state = logprobs_state(sd, kind, it, fc, att, p_att, masks, state)
         steps.append(lp)
+        used.append(it)
+        margins.append(margin)
     out = torch.stack(steps, 1)
     if out.size(1) < T:                                                 # untouched steps stay 0 (:123)
         out = torch.cat([out, out.new_zeros(B, T - out.size(1), V)], 1)
+    if return_tokens:
+        return out, torch.stack(used, 1), torch.stack(margins, 1)
     return out
 
 
@@ -160,15 +182,15 @@ def xe_loss(logprobs, target, mask):
     return -(picked * mask).sum() / mask.sum()
 
 
-def train_loss(sd, kind, fc_feats, att_feats, labels, masks, att_masks=None):
+def train_loss(sd, kind, fc_feats, att_feats, labels, masks, att_masks=None, ss_prob=0.0, ss_seed=0, inputs=None):
     """The call pattern of trainer.py:164-165."""
-    out = teacher_forced(sd, kind, fc_feats, att_feats, labels, att_masks)
+    out = teacher_forced(sd, kind, fc_feats, att_feats, labels, att_masks, ss_prob, ss_seed, inputs=inputs)
     return xe_loss(out, labels[:, 1:], masks[:, 1:])
 
 
-def loss_and_grads(sd, kind, fc_feats, att_feats, labels, masks, att_masks=None):
+def loss_and_grads(sd, kind, fc_feats, att_feats, labels, masks, att_masks=None, ss_prob=0.0, ss_seed=0, inputs=None):
     leaf = {k: v.detach().clone().requires_grad_(True) for k, v in sd.items()}
-    loss = train_loss(leaf, kind, fc_feats, att_feats, labels, masks, att_masks)
+    loss = train_loss(leaf, kind, fc_feats, att_feats, labels, masks, att_masks, ss_prob, ss_seed, inputs)
     loss.backward()
     grads = {k: (v.grad if v.grad is not None else torch.zeros_like(v)) for k, v in leaf.items()}
     return loss.detach(), grads
@@ -222,6 +244,19 @@ def _rng_mix(h):
     h = (h * np.uint32(0x846ca68b)).astype(np.uint32)
     h ^= h >> np.uint32(16)
     return h
+
+
+def uniform_noise(seed, step, rows):
+    """(rows,) fp32 uniforms in (0, 1): the per-row draw of decoding step `step` (rng_uniform at RNG_ROW_DRAW_COL)."""
+    with np.errstate(over="ignore"):
+        seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+        step_key = np.uint32((seed ^ (seed >> 32)) & 0xFFFFFFFF) ^ np.uint32((step * 0x9E3779B1) & 0xFFFFFFFF)
+        r = np.arange(rows, dtype=np.uint64)
+        row_key = _rng_mix(((np.uint64(step_key) + r * np.uint64(0x85EBCA77)) & np.uint64(0xFFFFFFFF)).astype(np.uint32))
+        c = np.uint32((0x7FFFFFFF * 0xC2B2AE3D) & 0xFFFFFFFF)
+        h = _rng_mix(row_key ^ c)
+    u = ((h >> np.uint32(9)).astype(np.float32) + np.float32(0.5)) * np.float32(1.0 / 8388608.0)
+    return torch.from_numpy(u).float()
 
 
 def gumbel_noise(seed, step, rows, cols):

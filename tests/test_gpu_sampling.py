@@ -122,3 +122,43 @@ def test_self_critical_gradients_match_oracle(kind, L, B):
         errs[name] = float(gr.abs().max()) if float(ref.abs().max()) < 1e-7 else float((gr - ref).norm()) / float(ref.norm())
     bad = {k: v for k, v in errs.items() if v > 6e-2}
     assert not bad, bad
+
+
+@pytest.mark.parametrize("kind,L,B", [("att2in2", 49, 12), ("topdown", 36, 12)])
+def test_scheduled_sampling_matches_oracle(kind, L, B):
+    """Training-mode forward with ss_prob > 0 (models/AttModel.py:130-143): the input tokens actually used, the loss and
+    the gradients against the oracle's restatement with the same counter-based draws."""
+    opt = synth.make_opt(caption_model=kind, vocab_size=9999, rnn_size=512, input_encoding_size=512, att_hid_size=512, seq_length=16)
+    sd = synth.init_state_dict(opt, seed=17)
+    fc, att = synth.make_features(B, L, 2048, seed=17)
+    labels, masks = synth.make_captions(B, 16, 9999, seed=17)
+    model = uic.setup(opt)
+    model.load_state_dict(sd)
+    model = model.cuda().train()
+    model.ss_prob, model.ss_seed = 0.5, 909
+    _, ref_used, ref_margins = O.teacher_forced(sd, kind, fc, att, labels, ss_prob=0.5, ss_seed=909, return_tokens=True)
+    # the product path, with the tokens it fed kept for inspection
+    from unpaired_image_captioning_b200 import autograd as AG
+    ss = model._scheduled_sampling(torch.device("cuda"))
+    r = AG.teacher_forced_run(model, fc.cuda(), att.cuda(), labels.cuda(), None, all_steps=True, ss=ss)
+    used = r.tokens.t().cpu()                                            # (B, T)
+    n = min(used.size(1), ref_used.size(1))
+    exact, exempt, failures = compare_greedy(used[:, :n], ref_used[:, :n], ref_margins[:, :n], tol=5e-2)
+    assert not failures, failures
+    assert exact >= B // 2
+    sampled = torch.isfinite(ref_margins[:, 1:n])
+    assert 0.3 < float(sampled.float().mean()) < 0.7
+    assert int((ref_used[:, 1:n] != labels[:, 1:n])[sampled].sum()) > 0   # the draws really replace ground truth
+    # loss + gradients through the public fast path, against the oracle fed with the draws the product path made
+    # (identical to its own wherever the margins are clear)
+    loss = model(fc.cuda(), None, att.cuda(), labels.cuda(), masks.cuda(), None, mode="forward_loss")
+    loss.backward()
+    ref_loss, ref_grads = O.loss_and_grads(sd, kind, fc, att, labels, masks, inputs=used)
+    assert abs(float(loss.detach()) - float(ref_loss)) < 2e-3 * float(ref_loss)
+    errs = {}
+    for name, p in model.named_parameters():
+        ref = ref_grads[name].cuda()
+        gr = p.grad if p.grad is not None else torch.zeros_like(p)
+        errs[name] = float(gr.abs().max()) if float(ref.abs().max()) < 1e-7 else float((gr - ref).norm()) / float(ref.norm())
+    bad = {k: v for k, v in errs.items() if v > 6e-2}
+    assert not bad, bad

@@ -67,3 +67,24 @@ def test_reward_criterion_matches_the_reference_formula():
     want = (-lp * reward * mask).sum() / mask.sum()
     assert abs(float(got) - float(want)) < 1e-6
     assert abs(float(O.reward_loss(lp, seq, reward)) - float(want)) < 1e-6
+
+
+def test_scheduled_sampling_oracle_semantics():
+    """ss_prob = 0 is plain teacher forcing; ss_prob = 1 replaces every input from step 1 on; the coin is uniform."""
+    opt, cfg = synth.opt_for("tiny_att2in2")
+    sd = synth.init_state_dict(opt, seed=5)
+    fc, att = synth.make_features(16, 7, opt.att_feat_size, seed=5)
+    labels, masks = synth.make_captions(16, opt.seq_length, opt.vocab_size, seed=5)
+    plain = O.teacher_forced(sd, "att2in2", fc, att, labels)
+    out0, used0, _ = O.teacher_forced(sd, "att2in2", fc, att, labels, ss_prob=0.0, ss_seed=3, return_tokens=True)
+    assert torch.equal(plain, out0) and torch.equal(used0, labels[:, :used0.size(1)])
+    out1, used1, margins = O.teacher_forced(sd, "att2in2", fc, att, labels, ss_prob=1.0, ss_seed=3, return_tokens=True)
+    assert torch.equal(used1[:, 0], labels[:, 0]) and bool(torch.isfinite(margins[:, 1:]).all())
+    assert not torch.equal(used1[:, 1:], labels[:, 1:used1.size(1)])
+    out_h, used_h, m_h = O.teacher_forced(sd, "att2in2", fc, att, labels, ss_prob=0.5, ss_seed=3, return_tokens=True)
+    frac = float(torch.isfinite(m_h[:, 1:]).float().mean())
+    assert 0.3 < frac < 0.7, frac
+    out_h2, used_h2, _ = O.teacher_forced(sd, "att2in2", fc, att, labels, ss_prob=0.5, ss_seed=3, return_tokens=True)
+    assert torch.equal(used_h, used_h2) and torch.equal(out_h, out_h2)
+    u = torch.cat([O.uniform_noise(11, t, 4096) for t in range(4)])
+    assert abs(float(u.mean()) - 0.5) < 0.02 and float(u.min()) > 0.0 and float(u.max()) < 1.0

@@ -35,7 +35,10 @@ class _Run:
 # ----------------------------------------------------------------------------------------------------
 # forward
 # ----------------------------------------------------------------------------------------------------
-def teacher_forced_run(model, fc_feats, att_feats, seq, att_masks, save=True, all_steps=False):
+def teacher_forced_run(model, fc_feats, att_feats, seq, att_masks, save=True, all_steps=False, ss=None):
+    """ss = (ss_prob, seed tensor) turns on scheduled sampling (models/AttModel.py:130-143): from step 1 on, each row's
+    input token is replaced with probability ss_prob by a draw from the model's distribution of the previous step
+    (Gumbel-max in the logit GEMM's statistics epilogue; no gradient flows through the draw, as in the reference)."""
     eng = model.engine
     w, lib, st = eng.w, eng.lib, stream()
     kind, H, E, A = eng.kind, w.H, w.E, w.A
@@ -64,7 +67,18 @@ def teacher_forced_run(model, fc_feats, att_feats, seq, att_masks, save=True, al
         r.G2 = torch.empty(T, B, 4 * H, dtype=torch.float32, device=dev)
         r.ah = torch.empty(T, B, A, dtype=torch.float32, device=dev)
         r.X[:T, :, sl.fc[0]:sl.fc[1]] = feats.fc                       # fc is re-fed at every step (:432)
+    if ss is not None:
+        ss_prob, ss_seed = float(ss[0]), ss[1]
+        parts = int(lib.uic_logit_stats_parts(w.V))
+        ss_stats = torch.empty(B, parts, 4, dtype=torch.float32, device=dev)
+        seq_l = seq.long().contiguous()
     for t in range(T):
+        if ss is not None and t >= 1:
+            h_prev = r.h_all[:, t - 1]                                   # (B, H) view, row pitch T_total * H
+            check(lib.uic_logit_stats(ptr(h_prev), h_prev.stride(0), ptr(w.w_logit), H, ptr(w.b_logit), None, 0, ptr(ss_stats),
+                                      B, w.V, H, 1, 0, 1.0, ptr(ss_seed), t, st))
+            check(lib.uic_ss_advance(ptr(ss_stats), parts, ptr(seq_l[:, t]), seq_l.stride(0), ss_prob, ptr(ss_seed), t,
+                                     ptr(r.tokens[t]), B, ptr(w.emb_relu), E, ptr(r.X[t][:, sl.xt[0]:]), w.Kx, E, w.V, st))
         if kind == "att2in2":
             ws = {"S": r.S[t], "ctx": r.ctx[t], "a2c": r.a2c[t]}
         else:
@@ -277,8 +291,8 @@ def _finish(r, grads, grad_scale, names, params):
 
 class _DecoderLossFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, model, fc_feats, att_feats, labels, masks, att_masks, global_mask_sum, *params):
-        r = teacher_forced_run(model, fc_feats, att_feats, labels, att_masks, all_steps=True)
+    def forward(ctx, model, fc_feats, att_feats, labels, masks, att_masks, global_mask_sum, ss, *params):
+        r = teacher_forced_run(model, fc_feats, att_feats, labels, att_masks, all_steps=True, ss=ss)
         T_total = r.T_total
         target = labels[:, 1:T_total + 1].contiguous().view(-1).long()
         mask = masks[:, 1:T_total + 1].contiguous().view(-1).float()
@@ -296,13 +310,13 @@ class _DecoderLossFn(torch.autograd.Function):
         # replaces one strided multiply per parameter (24 launches) by three
         g = bptt(r, o["dh"] * grad_out)
         g["logit.weight"], g["logit.bias"] = o["dW"] * grad_out, o["db"] * grad_out
-        return (None,) * 7 + tuple(_finish(r, g, None, names, params))
+        return (None,) * 8 + tuple(_finish(r, g, None, names, params))
 
 
 class _DecoderLogprobsFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, model, fc_feats, att_feats, seq, att_masks, *params):
-        r = teacher_forced_run(model, fc_feats, att_feats, seq, att_masks)
+    def forward(ctx, model, fc_feats, att_feats, seq, att_masks, ss, *params):
+        r = teacher_forced_run(model, fc_feats, att_feats, seq, att_masks, ss=ss)
         B, T_total, V = r.B, r.T_total, r.model.engine.w.V
         out = torch.zeros(B, T_total, V, dtype=torch.float32, device=r.h_all.device)
         _logit_stage(r, None, None, None, logprobs_out=out.view(B * T_total, V), want_grad=False)
@@ -323,7 +337,7 @@ class _DecoderLogprobsFn(torch.autograd.Function):
         names, params = _param_list(r.model)
         g = bptt(r, o["dh"])
         g["logit.weight"], g["logit.bias"] = o["dW"], o["db"]
-        return (None,) * 5 + tuple(_finish(r, g, None, names, params))
+        return (None,) * 6 + tuple(_finish(r, g, None, names, params))
 
 
 class _DecoderTokenLogprobsFn(torch.autograd.Function):
@@ -360,11 +374,11 @@ def decoder_token_logprobs(model, fc_feats, att_feats, labels, att_masks=None):
     return _DecoderTokenLogprobsFn.apply(model, fc_feats, att_feats, labels, att_masks, *params)
 
 
-def decoder_loss(model, fc_feats, att_feats, labels, masks, att_masks=None, global_mask_sum=None):
+def decoder_loss(model, fc_feats, att_feats, labels, masks, att_masks=None, global_mask_sum=None, ss=None):
     _, params = _param_list(model)
-    return _DecoderLossFn.apply(model, fc_feats, att_feats, labels, masks, att_masks, global_mask_sum, *params)
+    return _DecoderLossFn.apply(model, fc_feats, att_feats, labels, masks, att_masks, global_mask_sum, ss, *params)
 
 
-def decoder_logprobs(model, fc_feats, att_feats, seq, att_masks=None):
+def decoder_logprobs(model, fc_feats, att_feats, seq, att_masks=None, ss=None):
     _, params = _param_list(model)
-    return _DecoderLogprobsFn.apply(model, fc_feats, att_feats, seq, att_masks, *params)
+    return _DecoderLogprobsFn.apply(model, fc_feats, att_feats, seq, att_masks, ss, *params)

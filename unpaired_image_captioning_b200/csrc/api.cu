@@ -418,6 +418,17 @@ int uic_greedy_advance(const float* stats, int parts, int64_t* seq, float* seq_l
                         ld_table, x_xt_bf16, ld_x, E, V, temperature, reinterpret_cast<const unsigned long long*>(seed), ST(stream));
 }
 
+int uic_ss_advance(const float* stats, int parts, const int64_t* gt_tok, int64_t gt_stride, float ss_prob, const uint64_t* seed,
+                   int t, int64_t* tokens_out, int rows, const void* emb_table_bf16, int64_t ld_table, void* x_xt_bf16, int64_t ld_x,
+                   int E, int V, void* stream) {
+  REQUIRE(stats && gt_tok && seed && tokens_out && emb_table_bf16 && x_xt_bf16, UIC_ERR_ARG, "uic_ss_advance: null pointer");
+  REQUIRE(parts > 0 && E > 0 && V > 0 && t >= 0, UIC_ERR_SHAPE, "uic_ss_advance: parts=%d E=%d V=%d t=%d", parts, E, V, t);
+  REQUIRE((reinterpret_cast<uintptr_t>(stats) & 15) == 0, UIC_ERR_ALIGN, "uic_ss_advance: stats must be 16-byte aligned");
+  if (rows == 0) return 0;
+  return ss_advance(stats, parts, gt_tok, gt_stride, ss_prob, reinterpret_cast<const unsigned long long*>(seed), t, tokens_out, rows,
+                    emb_table_bf16, ld_table, x_xt_bf16, ld_x, E, V, ST(stream));
+}
+
 int uic_beam_step(const float* topk_val, const int32_t* topk_idx, int32_t* beam_seq, float* beam_lp, float* beam_sum,
                   int32_t* done_seq, float* done_lp, double* done_p, float* done_unaug, int32_t* done_cnt, int32_t* parent_row,
                   int64_t* next_tok, int t, int seq_length, int n_img, int beams, int flags, void* stream) {

@@ -350,6 +350,43 @@ __global__ void __launch_bounds__(ADV_THREADS) greedy_advance_kernel(const float
   }
 }
 
+// Scheduled sampling (models/AttModel.py:130-143): the input token of teacher-forced step t is, with probability ss_prob
+// per row, a draw from the model's own distribution of step t - 1 (Gumbel-max over the statistics of that step's logits,
+// temperature 1) instead of the ground-truth token; the choice is written to tokens_out and its embedding row to x_xt.
+__global__ void __launch_bounds__(ADV_THREADS) ss_advance_kernel(const float* __restrict__ stats, int parts,
+                                                                  const int64_t* __restrict__ gt_tok, long long gt_stride,
+                                                                  float ss_prob, const unsigned long long* __restrict__ seed, int t,
+                                                                  int64_t* __restrict__ tokens_out, int rows,
+                                                                  const __nv_bfloat16* __restrict__ table, long long ld_table,
+                                                                  __nv_bfloat16* __restrict__ x, long long ld_x, int E, int V) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const int r = blockIdx.x * (ADV_THREADS / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (r >= rows) return;
+  float kv[1];
+  int ki[1];
+  merge_row_stats<1>(stats + static_cast<long long>(r) * parts * 4, parts, kv, ki);
+  const Best best = warp_pop_best<1>(kv, ki);
+  const uint32_t rk = rng_row_key(rng_step_key(*seed, t), r);
+  long long tk = rng_uniform(rk, RNG_ROW_DRAW_COL) < ss_prob ? static_cast<long long>(best.i) : gt_tok[r * gt_stride];
+  tk = tk < 0 ? 0 : (tk >= V ? V - 1 : tk);
+  if (lane == 0) tokens_out[r] = tk;
+  copy_row_bf16(x + static_cast<long long>(r) * ld_x, table + tk * ld_table, E, lane, 32);
+}
+
+int ss_advance(const float* stats, int parts, const int64_t* gt_tok, long long gt_stride, float ss_prob,
+               const unsigned long long* seed, int t, int64_t* tokens_out, int rows, const void* table, long long ld_table,
+               void* x_xt, long long ld_x, int E, int V, cudaStream_t stream) {
+  const int per = ADV_THREADS / 32;
+  launch_begin("ss_advance", stream);
+  UIC_CUDA_OK(launch_pdl(ss_advance_kernel, dim3((rows + per - 1) / per), dim3(ADV_THREADS), 0, stream, stats, parts, gt_tok, gt_stride,
+                         ss_prob, seed, t, tokens_out, rows, static_cast<const __nv_bfloat16*>(table), ld_table,
+                         static_cast<__nv_bfloat16*>(x_xt), ld_x, E, V));
+  UIC_CUDA_OK(cudaGetLastError());
+  launch_end(stream);
+  return 0;
+}
+
 int greedy_advance(const float* stats, int parts, int64_t* seq, float* seq_lp, uint8_t* unfinished, int64_t* next_tok,
                    int32_t* n_unfinished, int t, int seq_length, int rows, const void* table, long long ld_table, void* x_xt,
                    long long ld_x, int E, int V, float temperature, const unsigned long long* seed, cudaStream_t stream) {

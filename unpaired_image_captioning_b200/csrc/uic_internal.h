@@ -103,6 +103,9 @@ int beam_advance(const float* stats, int parts, int kslots, int32_t* beam_seq, f
 int greedy_advance(const float* stats, int parts, int64_t* seq, float* seq_lp, uint8_t* unfinished, int64_t* next_tok,
                    int32_t* n_unfinished, int t, int seq_length, int rows, const void* table, long long ld_table, void* x_xt,
                    long long ld_x, int E, int V, float temperature, const unsigned long long* seed, cudaStream_t stream);
+int ss_advance(const float* stats, int parts, const int64_t* gt_tok, long long gt_stride, float ss_prob,
+               const unsigned long long* seed, int t, int64_t* tokens_out, int rows, const void* table, long long ld_table,
+               void* x_xt, long long ld_x, int E, int V, cudaStream_t stream);
 int beam_gather(const int32_t* parent_row, const void* x_src, void* x_dst, long long ld_x, int col0_a, int ncol_a, int col0_b,
                 int ncol_b, const float* c_src, float* c_dst, int n_state, int rows, int H, cudaStream_t stream);
 

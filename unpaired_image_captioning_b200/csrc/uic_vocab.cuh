@@ -25,11 +25,12 @@ __host__ __device__ __forceinline__ uint32_t rng_step_key(unsigned long long see
 __host__ __device__ __forceinline__ uint32_t rng_row_key(uint32_t step_key, int row) {
   return rng_mix(step_key + static_cast<uint32_t>(row) * 0x85EBCA77U);
 }
-__device__ __forceinline__ float rng_gumbel(uint32_t row_key, int col) {
+__host__ __device__ __forceinline__ float rng_uniform(uint32_t row_key, int col) {
   const uint32_t h = rng_mix(row_key ^ (static_cast<uint32_t>(col) * 0xC2B2AE3DU));
-  const float u = (static_cast<float>(h >> 9) + 0.5f) * (1.0f / 8388608.0f);  // 23 bits + 1/2: exact in fp32, strictly inside (0, 1)
-  return -__logf(-__logf(u));
+  return (static_cast<float>(h >> 9) + 0.5f) * (1.0f / 8388608.0f);  // 23 bits + 1/2: exact in fp32, strictly inside (0, 1)
 }
+__device__ __forceinline__ float rng_gumbel(uint32_t row_key, int col) { return -__logf(-__logf(rng_uniform(row_key, col))); }
+constexpr int RNG_ROW_DRAW_COL = 0x7fffffff;  // "column" of a per-row uniform draw (scheduled-sampling coin), outside any vocabulary
 
 struct MaxSum {
   float m, s;

@@ -168,6 +168,20 @@ class AttModel(CaptionModel):
         return fc, f.att, f.p_att, f.masks
 
     # ---- teacher-forced forward -----------------------------------------------------------------------
+    def _scheduled_sampling(self, device):
+        """(ss_prob, device seed) when scheduled sampling applies (training mode and ss_prob > 0, AttModel.py:130), else None.
+        The seed is drawn from torch's CUDA generator per forward call; set `self.ss_seed` to an int to pin it."""
+        if not (self.training and self.ss_prob > 0.0):
+            return None
+        seed = getattr(self, "_ss_seed_dev", None)
+        if seed is None or seed.device != device:
+            seed = self._ss_seed_dev = torch.zeros(1, dtype=torch.int64, device=device)
+        if getattr(self, "ss_seed", None) is None:
+            seed.random_()
+        else:
+            seed.fill_(int(self.ss_seed))
+        return (float(self.ss_prob), seed)
+
     def _active_steps(self, seq):
         """Number of steps the reference executes before its all-zero-column break (AttModel.py:148-151)."""
         T = seq.size(1) - 1
@@ -178,11 +192,10 @@ class AttModel(CaptionModel):
 
     def _forward(self, fc_feats, attri_feats, att_feats, seq, att_masks=None):
         self._check_train_features()
-        if self.training and self.ss_prob > 0.0:
-            raise NotImplementedError("scheduled sampling (ss_prob > 0) is not on the B200 hot path yet")
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+        ss = self._scheduled_sampling(att_feats.device)
+        if ss is not None or (torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())):
             from .autograd import decoder_logprobs
-            return decoder_logprobs(self, fc_feats, att_feats, seq, att_masks)
+            return decoder_logprobs(self, fc_feats, att_feats, seq, att_masks, ss)
         eng, lib = self.engine, _lib.load()
         feats = eng.prepare(fc_feats, att_feats, att_masks)
         n_steps = self._active_steps(seq)
@@ -201,10 +214,8 @@ class AttModel(CaptionModel):
         (B, T, V) log-prob tensor.  Equals crit(model(fc, attri, att, labels, att_masks), labels[:,1:], masks[:,1:]).
         `global_mask_sum` (data parallel): the loss normaliser summed over all ranks (dp.global_mask_sum)."""
         self._check_train_features()
-        if self.training and self.ss_prob > 0.0:
-            raise NotImplementedError("scheduled sampling (ss_prob > 0) is not on the B200 hot path yet")
         from .autograd import decoder_loss
-        return decoder_loss(self, fc_feats, att_feats, labels, masks, att_masks, global_mask_sum)
+        return decoder_loss(self, fc_feats, att_feats, labels, masks, att_masks, global_mask_sum, self._scheduled_sampling(att_feats.device))
 
     # ---- single step API --------------------------------------------------------------------------------
     def _feats_from_api(self, fc, att, p_att, att_masks, rows):
