@@ -190,6 +190,13 @@ int uic_greedy_advance(const float* stats, int parts, int64_t* seq, float* seq_l
                        int32_t* n_unfinished, int t, int seq_length, int rows, const void* emb_table_bf16, int64_t ld_table,
                        void* x_xt_bf16, int64_t ld_x, int E, int V, float temperature, const uint64_t* seed, void* stream);
 
+/* In-place nn.Dropout(p) in training mode (models/AttModel.py:73-84 embed / fc_embed / att_embed, :431,599 core output):
+ * x[r, c] = keep ? x[r, c] / (1 - p) : 0 with keep = u(seed, site, row0 + r * row_stride, c) >= p, u the library's
+ * counter-based uniform.  Calling it again on the gradient of the same tensor applies the same mask (the backward).
+ * is_bf16: 1 = bf16 storage, 0 = fp32.  `seed`: device pointer. */
+int uic_dropout(void* x, int is_bf16, int64_t ld, int64_t rows, int cols, float p, const uint64_t* seed, int site, int64_t row0,
+                int64_t row_stride, void* stream);
+
 /* Scheduled sampling (models/AttModel.py:130-143): input token of teacher-forced step t = with probability ss_prob per
  * row a draw from softmax(logits of step t-1) (statistics from uic_logit_stats(kslots = 1, temperature = 1, seed, step = t)),
  * else gt_tok[r * gt_stride]; written to tokens_out[r], its embedding row to x_xt_bf16[r, 0:E].  The per-row coin is

@@ -40,13 +40,34 @@ def _linear(sd, prefix, x):
 # ------------------------------------------------------------------------------------------------
 # feature prologue -- models/AttModel.py:99-117 (clip_att, _prepare_feature), :30-53 (pack_wrapper)
 # ------------------------------------------------------------------------------------------------
-def prepare_features(sd, kind, fc_feats, att_feats, att_masks=None):
+DROP_XT, DROP_ATT, DROP_FC, DROP_OUT = 0, 1, 2, 3   # dropout sites (row ids: t*B+b | b*L+l | b | b*T+t), as in _lib.py
+
+
+def dropout_mask(drop, site, row_ids, cols):
+    """Training-mode nn.Dropout as the product path draws it (csrc/pointwise.cu dropout_kernel): keep = u >= p with u the
+    counter-based uniform of (seed, 0x40000000 + site, row, col); returns the fp32 multiplier keep / (1 - p), shape
+    (len(row_ids), cols).  drop = (p, seed)."""
+    p, seed = float(drop[0]), int(drop[1]) & 0xFFFFFFFFFFFFFFFF
+    with np.errstate(over="ignore"):
+        step = 0x40000000 + site
+        step_key = np.uint32((seed ^ (seed >> 32)) & 0xFFFFFFFF) ^ np.uint32((step * 0x9E3779B1) & 0xFFFFFFFF)
+        r = np.asarray(row_ids, dtype=np.uint64)
+        row_key = _rng_mix(((np.uint64(step_key) + r * np.uint64(0x85EBCA77)) & np.uint64(0xFFFFFFFF)).astype(np.uint32))
+        c = ((np.arange(cols, dtype=np.uint64) * np.uint64(0xC2B2AE3D)) & np.uint64(0xFFFFFFFF)).astype(np.uint32)
+        h = _rng_mix(row_key[:, None] ^ c[None, :])
+    u = ((h >> np.uint32(9)).astype(np.float32) + np.float32(0.5)) * np.float32(1.0 / 8388608.0)
+    return torch.from_numpy((u >= np.float32(p)).astype(np.float32) / np.float32(1.0 - p))
+
+
+def prepare_features(sd, kind, fc_feats, att_feats, att_masks=None, drop=None):
     if att_masks is not None:  # clip_att (:99-105)
         keep = int(att_masks.long().sum(1).max())
         att_feats = att_feats[:, :keep].contiguous()
         att_masks = att_masks[:, :keep].contiguous()
-    if kind == "topdown":  # fc_embed = Linear+ReLU (:76-78); identity for att2in2 (:674-675)
+    if kind == "topdown":  # fc_embed = Linear+ReLU(+Dropout) (:76-78); identity for att2in2 (:674-675)
         fc = torch.relu(_linear(sd, "fc_embed.0", fc_feats))
+        if drop is not None:
+            fc = fc * dropout_mask(drop, DROP_FC, np.arange(fc.size(0)), fc.size(1))
     else:
         fc = fc_feats
     # att_embed = Linear+ReLU (:79-84, use_bn=0, dropout off).  With masks the reference packs the
@@ -56,6 +77,9 @@ def prepare_features(sd, kind, fc_feats, att_feats, att_masks=None):
         n_valid = att_masks.long().sum(1)
         valid = (torch.arange(att.size(1))[None, :] < n_valid[:, None]).to(att.dtype)
         att = att * valid[:, :, None]
+    if drop is not None:                                               # att_embed's nn.Dropout (:79-84)
+        B_, L_, H_ = att.shape
+        att = att * dropout_mask(drop, DROP_ATT, np.arange(B_ * L_), H_).view(B_, L_, H_)
     p_att = _linear(sd, "ctx2att", att)  # :115 (bias also lands on padded rows, like the reference)
     return fc, att, p_att, att_masks
 
@@ -125,10 +149,16 @@ def init_hidden(sd, kind, rows):
     return (z, z.clone())
 
 
-def logprobs_state(sd, kind, it, fc, att, p_att, att_masks, state):
-    """models/AttModel.py:158-165: embed -> core -> logit -> log_softmax."""
+def logprobs_state(sd, kind, it, fc, att, p_att, att_masks, state, drop=None, t=0, T=0):
+    """models/AttModel.py:158-165: embed -> core -> logit -> log_softmax.  drop = (p, seed): training-mode dropout on
+    the embedding (:75) and on the core's output (:431,599) at teacher-forced step t of T."""
     xt = torch.relu(sd["embed.0.weight"][it])                           # :73-75,160
+    B = xt.size(0)
+    if drop is not None:
+        xt = xt * dropout_mask(drop, DROP_XT, t * B + np.arange(B), xt.size(1))
     out, state = CORES[kind](sd, xt, fc, att, p_att, state, att_masks)  # :162
+    if drop is not None:
+        out = out * dropout_mask(drop, DROP_OUT, np.arange(B) * T + t, out.size(1))
     return torch.log_softmax(_linear(sd, "logit", out), dim=1), state    # :163
 
 
@@ -136,7 +166,7 @@ def logprobs_state(sd, kind, it, fc, att, p_att, att_masks, state):
 # teacher-forced forward -- models/AttModel.py:119-156 (ss_prob == 0)
 # ------------------------------------------------------------------------------------------------
 def teacher_forced(sd, kind, fc_feats, att_feats, seq, att_masks=None, ss_prob=0.0, ss_seed=0, return_tokens=False,
-                   inputs=None):
+                   inputs=None, drop=None):
     """models/AttModel.py:119-156.  ss_prob > 0: scheduled sampling as in training mode (:130-143) -- per row a uniform
     draw against ss_prob decides whether the input token of step i is a sample from exp(outputs[:, i-1]) (detached)
     instead of seq[:, i].  The draws use the counter-based noise shared with the product path (see gumbel_noise):
@@ -146,7 +176,7 @@ def teacher_forced(sd, kind, fc_feats, att_feats, seq, att_masks=None, ss_prob=0
     B, T = fc_feats.size(0), seq.size(1) - 1
     V = sd["logit.weight"].size(0)
     state = init_hidden(sd, kind, B)
-    fc, att, p_att, masks = prepare_features(sd, kind, fc_feats, att_feats, att_masks)
+    fc, att, p_att, masks = prepare_features(sd, kind, fc_feats, att_feats, att_masks, drop)
     steps, used, margins = [], [], []
     for i in range(T):
         it = seq[:, i].clone()
@@ -162,7 +192,7 @@ def teacher_forced(sd, kind, fc_feats, att_feats, seq, att_masks=None, ss_prob=0
             margin[sample_mask] = (top2.values[:, 0] - top2.values[:, 1])[sample_mask]
         if i >= 1 and int(seq[:, i].sum()) == 0:                        # :148-151
             break
-        lp, state = logprobs_state(sd, kind, it, fc, att, p_att, masks, state)
+        lp, state = logprobs_state(sd, kind, it, fc, att, p_att, masks, state, drop, i, T)
         steps.append(lp)
         used.append(it)
         margins.append(margin)
@@ -182,15 +212,15 @@ def xe_loss(logprobs, target, mask):
     return -(picked * mask).sum() / mask.sum()
 
 
-def train_loss(sd, kind, fc_feats, att_feats, labels, masks, att_masks=None, ss_prob=0.0, ss_seed=0, inputs=None):
+def train_loss(sd, kind, fc_feats, att_feats, labels, masks, att_masks=None, ss_prob=0.0, ss_seed=0, inputs=None, drop=None):
     """The call pattern of trainer.py:164-165."""
-    out = teacher_forced(sd, kind, fc_feats, att_feats, labels, att_masks, ss_prob, ss_seed, inputs=inputs)
+    out = teacher_forced(sd, kind, fc_feats, att_feats, labels, att_masks, ss_prob, ss_seed, inputs=inputs, drop=drop)
     return xe_loss(out, labels[:, 1:], masks[:, 1:])
 
 
-def loss_and_grads(sd, kind, fc_feats, att_feats, labels, masks, att_masks=None, ss_prob=0.0, ss_seed=0, inputs=None):
+def loss_and_grads(sd, kind, fc_feats, att_feats, labels, masks, att_masks=None, ss_prob=0.0, ss_seed=0, inputs=None, drop=None):
     leaf = {k: v.detach().clone().requires_grad_(True) for k, v in sd.items()}
-    loss = train_loss(leaf, kind, fc_feats, att_feats, labels, masks, att_masks, ss_prob, ss_seed, inputs)
+    loss = train_loss(leaf, kind, fc_feats, att_feats, labels, masks, att_masks, ss_prob, ss_seed, inputs, drop)
     loss.backward()
     grads = {k: (v.grad if v.grad is not None else torch.zeros_like(v)) for k, v in leaf.items()}
     return loss.detach(), grads

@@ -162,3 +162,54 @@ def test_scheduled_sampling_matches_oracle(kind, L, B):
         errs[name] = float(gr.abs().max()) if float(ref.abs().max()) < 1e-7 else float((gr - ref).norm()) / float(ref.norm())
     bad = {k: v for k, v in errs.items() if v > 6e-2}
     assert not bad, bad
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_dropout_kernel_matches_oracle_mask(dtype):
+    seed_t = torch.tensor([123456789], dtype=torch.int64, device=DEV)
+    drop = (0.3, seed_t)
+    x = torch.randn(300, 72, device=DEV).to(dtype)
+    y = x.clone()
+    view = y[:, 8:8 + 40]                                      # pitched view: ld 72, 40 columns
+    _lib.dropout(view, drop, _lib.DROP_XT, row0=17, row_stride=3)
+    mask = O.dropout_mask((0.3, 123456789), O.DROP_XT, 17 + 3 * torch.arange(300).numpy(), 40).to(DEV)
+    want = (x[:, 8:48].float() * mask).to(dtype)
+    torch.testing.assert_close(y[:, 8:48].float(), want.float(), rtol=1e-2 if dtype == torch.bfloat16 else 1e-6, atol=1e-6)
+    assert torch.equal(y[:, :8], x[:, :8]) and torch.equal(y[:, 48:], x[:, 48:])
+    assert torch.equal((y[:, 8:48] == 0), (mask == 0) | (x[:, 8:48] == 0))
+
+
+@pytest.mark.parametrize("kind,L,B", [("att2in2", 49, 6), ("topdown", 36, 8)])
+def test_training_with_dropout_matches_oracle(kind, L, B):
+    """drop_prob_lm = 0.5 in training mode (the reference's default): loss and every gradient against the oracle with the
+    same counter-based masks on embed / fc_embed / att_embed / core output."""
+    opt = synth.make_opt(caption_model=kind, vocab_size=9999, rnn_size=512, input_encoding_size=512, att_hid_size=512, seq_length=16,
+                         drop_prob_lm=0.5)
+    sd = synth.init_state_dict(opt, seed=23)
+    fc, att = synth.make_features(B, L, 2048, seed=23)
+    labels, masks = synth.make_captions(B, 16, 9999, seed=23)
+    model = uic.setup(opt)
+    model.load_state_dict(sd)
+    model = model.cuda().train()
+    model.dropout_seed = 4242
+    loss = model(fc.cuda(), None, att.cuda(), labels.cuda(), masks.cuda(), None, mode="forward_loss")
+    loss.backward()
+    ref_loss, ref_grads = O.loss_and_grads(sd, kind, fc, att, labels, masks, drop=(0.5, 4242))
+    plain_loss = O.train_loss(sd, kind, fc, att, labels, masks)
+    assert abs(float(ref_loss) - float(plain_loss)) > 1e-4 * float(plain_loss)        # the masks matter
+    assert abs(float(loss.detach()) - float(ref_loss)) < 2e-3 * float(ref_loss)
+    errs = {}
+    for name, p in model.named_parameters():
+        ref = ref_grads[name].cuda()
+        gr = p.grad if p.grad is not None else torch.zeros_like(p)
+        errs[name] = float(gr.abs().max()) if float(ref.abs().max()) < 1e-7 else float((gr - ref).norm()) / float(ref.norm())
+    # (kept activations are doubled at p = 0.5 and so is their bf16 rounding: the 8-row fc_embed gradients are the noisiest)
+    bad = {k: v for k, v in errs.items() if v > 9e-2}
+    assert not bad, bad
+    # eval mode ignores dropout
+    model.eval()
+    with torch.no_grad():
+        out = model(fc.cuda(), None, att.cuda(), labels.cuda(), None)
+    ref = O.teacher_forced(sd, kind, fc, att, labels)
+    sel = masks[:, 1:].bool()
+    assert float(((out.cpu() - ref).abs() / ref.abs().clamp_min(1.0))[sel].max()) < 2e-3

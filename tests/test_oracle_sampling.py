@@ -88,3 +88,22 @@ def test_scheduled_sampling_oracle_semantics():
     assert torch.equal(used_h, used_h2) and torch.equal(out_h, out_h2)
     u = torch.cat([O.uniform_noise(11, t, 4096) for t in range(4)])
     assert abs(float(u.mean()) - 0.5) < 0.02 and float(u.min()) > 0.0 and float(u.max()) < 1.0
+
+
+def test_dropout_mask_oracle():
+    m = O.dropout_mask((0.3, 5), O.DROP_ATT, range(2000), 128)
+    assert abs(float((m > 0).float().mean()) - 0.7) < 0.01
+    assert abs(float(m.max()) - 1.0 / 0.7) < 1e-6 and float(m.min()) == 0.0
+    assert torch.equal(m, O.dropout_mask((0.3, 5), O.DROP_ATT, range(2000), 128))
+    assert not torch.equal(m, O.dropout_mask((0.3, 5), O.DROP_OUT, range(2000), 128))
+    assert not torch.equal(m, O.dropout_mask((0.3, 6), O.DROP_ATT, range(2000), 128))
+    # rows are addressed by id: a slice of the ids gives the slice of the mask
+    assert torch.equal(m[100:200], O.dropout_mask((0.3, 5), O.DROP_ATT, range(100, 200), 128))
+    opt, cfg = synth.opt_for("tiny_topdown")
+    sd = synth.init_state_dict(opt, seed=5)
+    fc, att = synth.make_features(4, 5, opt.att_feat_size, seed=5)
+    labels, masks = synth.make_captions(4, opt.seq_length, opt.vocab_size, seed=5)
+    plain = O.teacher_forced(sd, "topdown", fc, att, labels)
+    dropped = O.teacher_forced(sd, "topdown", fc, att, labels, drop=(0.5, 9))
+    assert not torch.allclose(plain, dropped)
+    assert torch.equal(dropped, O.teacher_forced(sd, "topdown", fc, att, labels, drop=(0.5, 9)))

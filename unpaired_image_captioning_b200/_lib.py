@@ -45,6 +45,7 @@ SIGNATURES = {
     "uic_beam_advance": (_i, [_p, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p, _p, _i64, _i, _i, _i, _i, _p, _p,
                               _i, _i, _p, _i64, _i, _i, _i, _p]),
     "uic_greedy_advance": (_i, [_p, _i, _p, _p, _p, _p, _p, _i, _i, _i, _p, _i64, _p, _i64, _i, _i, _f, _p, _p]),
+    "uic_dropout": (_i, [_p, _i, _i64, _i64, _i, _f, _p, _i, _i64, _i64, _p]),
     "uic_ss_advance": (_i, [_p, _i, _p, _i64, _f, _p, _i, _p, _i, _p, _i64, _p, _i64, _i, _i, _p]),
     "uic_beam_step": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p]),
     "uic_beam_gather": (_i, [_p, _p, _p, _i64, _i, _i, _i, _i, _p, _p, _i, _i, _i, _p]),
@@ -197,3 +198,15 @@ def cast_bf16(src, dst=None, relu=False):
         dst = torch.empty(src.shape, dtype=torch.bfloat16, device=src.device)
     check(load().uic_cast_f32_bf16(ptr(src), src.stride(0), ptr(dst), dst.stride(0), src.shape[0], src.shape[1], int(relu), stream()))
     return dst
+
+
+DROP_XT, DROP_ATT, DROP_FC, DROP_OUT = 0, 1, 2, 3   # dropout sites (row ids: t*B+b | b*L+l | b | b*T+t)
+
+
+def dropout(x, drop, site, row0=0, row_stride=1):
+    """In-place training-mode dropout on a 2-D view (fp32 or bf16, unit inner stride); drop = (p, device seed tensor).
+    The same call on the gradient of that tensor is its backward."""
+    if x.dim() != 2 or x.stride(1) != 1 or x.dtype not in (torch.float32, torch.bfloat16):
+        raise ValueError("dropout: 2-D fp32/bf16 view with unit inner stride expected")
+    check(load().uic_dropout(ptr(x), int(x.dtype == torch.bfloat16), x.stride(0), x.shape[0], x.shape[1], float(drop[0]), ptr(drop[1]),
+                             int(site), int(row0), int(row_stride), stream()))

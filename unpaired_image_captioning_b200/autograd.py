@@ -35,14 +35,16 @@ class _Run:
 # ----------------------------------------------------------------------------------------------------
 # forward
 # ----------------------------------------------------------------------------------------------------
-def teacher_forced_run(model, fc_feats, att_feats, seq, att_masks, save=True, all_steps=False, ss=None):
+def teacher_forced_run(model, fc_feats, att_feats, seq, att_masks, save=True, all_steps=False, ss=None, drop=None):
     """ss = (ss_prob, seed tensor) turns on scheduled sampling (models/AttModel.py:130-143): from step 1 on, each row's
     input token is replaced with probability ss_prob by a draw from the model's distribution of the previous step
-    (Gumbel-max in the logit GEMM's statistics epilogue; no gradient flows through the draw, as in the reference)."""
+    (Gumbel-max in the logit GEMM's statistics epilogue; no gradient flows through the draw, as in the reference).
+    drop = (p, seed tensor) applies the training-mode nn.Dropout layers of the reference (embed, fc_embed, att_embed,
+    core output) with the library's counter-based masks; bptt re-applies the same masks to the gradients."""
     eng = model.engine
     w, lib, st = eng.w, eng.lib, stream()
     kind, H, E, A = eng.kind, w.H, w.E, w.A
-    feats = eng.prepare(fc_feats, att_feats, att_masks, keep_inputs=True)
+    feats = eng.prepare(fc_feats, att_feats, att_masks, keep_inputs=True, drop=drop)
     B, L, dev = feats.B, feats.L, feats.att.device
     T_total = seq.size(1) - 1
     # The reference stops at the first all-zero token column (AttModel.py:148-151).  Those steps carry mask 0,
@@ -50,7 +52,7 @@ def teacher_forced_run(model, fc_feats, att_feats, seq, att_masks, save=True, al
     T = T_total if all_steps else model._active_steps(seq)
     sl = Slots(kind, E, H)
     r = _Run()
-    r.model, r.feats, r.B, r.L, r.T, r.T_total, r.sl = model, feats, B, L, T, T_total, sl
+    r.model, r.feats, r.B, r.L, r.T, r.T_total, r.sl, r.drop = model, feats, B, L, T, T_total, sl, drop
     r.X = torch.zeros(T + 1, B, w.Kx, dtype=BF16, device=dev)
     r.c = torch.zeros(T + 1, sl.n_state, B, H, dtype=torch.float32, device=dev)
     r.alpha = torch.empty(T, B, L, dtype=torch.float32, device=dev)
@@ -58,6 +60,8 @@ def teacher_forced_run(model, fc_feats, att_feats, seq, att_masks, save=True, al
     r.tokens = seq[:, :T].t().contiguous().long()                      # (T, B): step-major like X
     X2d = r.X.view((T + 1) * B, w.Kx)
     check(lib.uic_embed_rows(ptr(w.emb_relu), E, ptr(r.tokens), ptr(X2d[:, sl.xt[0]:]), w.Kx, T * B, E, w.V, st))
+    if drop is not None:   # self.embed's nn.Dropout; rows are t * B + b
+        _lib.dropout(X2d[:T * B, sl.xt[0]:sl.xt[0] + E], drop, _lib.DROP_XT)
     if kind == "att2in2":
         r.S = torch.empty(T, B, 5 * H + A, dtype=torch.float32, device=dev)
         r.ctx = torch.empty(T, B, H, dtype=BF16, device=dev)
@@ -79,11 +83,15 @@ def teacher_forced_run(model, fc_feats, att_feats, seq, att_masks, save=True, al
                                       B, w.V, H, 1, 0, 1.0, ptr(ss_seed), t, st))
             check(lib.uic_ss_advance(ptr(ss_stats), parts, ptr(seq_l[:, t]), seq_l.stride(0), ss_prob, ptr(ss_seed), t,
                                      ptr(r.tokens[t]), B, ptr(w.emb_relu), E, ptr(r.X[t][:, sl.xt[0]:]), w.Kx, E, w.V, st))
+            if drop is not None:
+                _lib.dropout(r.X[t][:, sl.xt[0]:sl.xt[0] + E], drop, _lib.DROP_XT, row0=t * B)
         if kind == "att2in2":
             ws = {"S": r.S[t], "ctx": r.ctx[t], "a2c": r.a2c[t]}
         else:
             ws = {"G": r.G1[t], "G2": r.G2[t], "att_h": r.ah[t]}
         eng.core_step(r.X[t], r.c[t], feats, ws, X_next=r.X[t + 1], c_out=r.c[t + 1], h_all=r.h_all[:, t], alpha=r.alpha[t])
+        if drop is not None:   # the core's output dropout feeds the logit layer only (AttModel.py:431,599); rows are b * T + t
+            _lib.dropout(r.h_all[:, t], drop, _lib.DROP_OUT, row0=t, row_stride=T_total)
     return r
 
 
@@ -148,6 +156,8 @@ def bptt(r, dh_all):
     B, L, T, T_total, sl, feats = r.B, r.L, r.T, r.T_total, r.sl, r.feats
     dev = dh_all.device
     f32 = dict(dtype=torch.float32, device=dev)
+    if r.drop is not None:   # output dropout: the same mask on the gradient (rows b * T + t, like the forward)
+        _lib.dropout(dh_all, r.drop, _lib.DROP_OUT)
     dh3 = dh_all.view(B, T_total, H)
     ld_dh = T_total * H
     de = torch.empty(T, B, L, **f32)
@@ -230,6 +240,8 @@ def bptt(r, dh_all):
         # fc_embed: the embedded fc vector is an input of every step
         dfc = torch.empty(B, H, **f32)
         check(lib.uic_reduce_time(ptr(dXa), B * K1, K1, H + E, ptr(dfc), T, B, H, st))
+        if r.drop is not None:
+            _lib.dropout(dfc, r.drop, _lib.DROP_FC)
         dfc_pre = torch.empty(B, H, dtype=BF16, device=dev)
         check(lib.uic_relu_bwd_cast(ptr(dfc), ptr(feats.fc), ptr(dfc_pre), B * H, st))
         dWfc = torch.empty(H, feats.fc_in.size(1), **f32)
@@ -242,6 +254,8 @@ def bptt(r, dh_all):
         ah_ptr, ah_stride, ah_ld = r.ah, B * A, A
 
     # ---- embedding ------------------------------------------------------------------------------------
+    if r.drop is not None:
+        _lib.dropout(dxt2d[:, :E], r.drop, _lib.DROP_XT)
     demb = torch.zeros(V, E, **f32)
     check(lib.uic_embed_bwd(ptr(dxt2d), ld_dxt, ptr(r.tokens), ptr(w.emb_relu), ptr(demb), T * B, E, V, st))
     g["embed.0.weight"] = demb
@@ -259,6 +273,8 @@ def bptt(r, dh_all):
     gemm(dp_att, att2d, out_f32=dWc, a_mn=True, b_mn=True)
     g["ctx2att.weight"], g["ctx2att.bias"] = dWc, dw_alpha[A:]
     gemm(dp_att, w.w_ctx2att, out_f32=datt, b_mn=True, accumulate=True)   # d att += d p_att @ W_ctx2att
+    if r.drop is not None:
+        _lib.dropout(datt, r.drop, _lib.DROP_ATT)
     d_pre = torch.empty(B * L, H, dtype=BF16, device=dev)
     check(lib.uic_relu_bwd_cast(ptr(datt), ptr(att2d), ptr(d_pre), B * L * H, st))
     dWe = torch.empty(H, feats.x_in.size(1), **f32)
@@ -291,8 +307,8 @@ def _finish(r, grads, grad_scale, names, params):
 
 class _DecoderLossFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, model, fc_feats, att_feats, labels, masks, att_masks, global_mask_sum, ss, *params):
-        r = teacher_forced_run(model, fc_feats, att_feats, labels, att_masks, all_steps=True, ss=ss)
+    def forward(ctx, model, fc_feats, att_feats, labels, masks, att_masks, global_mask_sum, ss, drop, *params):
+        r = teacher_forced_run(model, fc_feats, att_feats, labels, att_masks, all_steps=True, ss=ss, drop=drop)
         T_total = r.T_total
         target = labels[:, 1:T_total + 1].contiguous().view(-1).long()
         mask = masks[:, 1:T_total + 1].contiguous().view(-1).float()
@@ -310,13 +326,13 @@ class _DecoderLossFn(torch.autograd.Function):
         # replaces one strided multiply per parameter (24 launches) by three
         g = bptt(r, o["dh"] * grad_out)
         g["logit.weight"], g["logit.bias"] = o["dW"] * grad_out, o["db"] * grad_out
-        return (None,) * 8 + tuple(_finish(r, g, None, names, params))
+        return (None,) * 9 + tuple(_finish(r, g, None, names, params))
 
 
 class _DecoderLogprobsFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, model, fc_feats, att_feats, seq, att_masks, ss, *params):
-        r = teacher_forced_run(model, fc_feats, att_feats, seq, att_masks, ss=ss)
+    def forward(ctx, model, fc_feats, att_feats, seq, att_masks, ss, drop, *params):
+        r = teacher_forced_run(model, fc_feats, att_feats, seq, att_masks, ss=ss, drop=drop)
         B, T_total, V = r.B, r.T_total, r.model.engine.w.V
         out = torch.zeros(B, T_total, V, dtype=torch.float32, device=r.h_all.device)
         _logit_stage(r, None, None, None, logprobs_out=out.view(B * T_total, V), want_grad=False)
@@ -337,7 +353,7 @@ class _DecoderLogprobsFn(torch.autograd.Function):
         names, params = _param_list(r.model)
         g = bptt(r, o["dh"])
         g["logit.weight"], g["logit.bias"] = o["dW"], o["db"]
-        return (None,) * 6 + tuple(_finish(r, g, None, names, params))
+        return (None,) * 7 + tuple(_finish(r, g, None, names, params))
 
 
 class _DecoderTokenLogprobsFn(torch.autograd.Function):
@@ -374,11 +390,11 @@ def decoder_token_logprobs(model, fc_feats, att_feats, labels, att_masks=None):
     return _DecoderTokenLogprobsFn.apply(model, fc_feats, att_feats, labels, att_masks, *params)
 
 
-def decoder_loss(model, fc_feats, att_feats, labels, masks, att_masks=None, global_mask_sum=None, ss=None):
+def decoder_loss(model, fc_feats, att_feats, labels, masks, att_masks=None, global_mask_sum=None, ss=None, drop=None):
     _, params = _param_list(model)
-    return _DecoderLossFn.apply(model, fc_feats, att_feats, labels, masks, att_masks, global_mask_sum, ss, *params)
+    return _DecoderLossFn.apply(model, fc_feats, att_feats, labels, masks, att_masks, global_mask_sum, ss, drop, *params)
 
 
-def decoder_logprobs(model, fc_feats, att_feats, seq, att_masks=None, ss=None):
+def decoder_logprobs(model, fc_feats, att_feats, seq, att_masks=None, ss=None, drop=None):
     _, params = _param_list(model)
-    return _DecoderLogprobsFn.apply(model, fc_feats, att_feats, seq, att_masks, ss, *params)
+    return _DecoderLogprobsFn.apply(model, fc_feats, att_feats, seq, att_masks, ss, drop, *params)

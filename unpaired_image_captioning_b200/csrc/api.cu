@@ -429,6 +429,16 @@ int uic_ss_advance(const float* stats, int parts, const int64_t* gt_tok, int64_t
                     emb_table_bf16, ld_table, x_xt_bf16, ld_x, E, V, ST(stream));
 }
 
+int uic_dropout(void* x, int is_bf16, int64_t ld, int64_t rows, int cols, float p, const uint64_t* seed, int site, int64_t row0,
+                int64_t row_stride, void* stream) {
+  REQUIRE(x && seed, UIC_ERR_ARG, "uic_dropout: null pointer");
+  REQUIRE(p >= 0.0f && p < 1.0f, UIC_ERR_ARG, "uic_dropout: p=%f must be in [0, 1)", p);
+  REQUIRE(cols > 0 && ld >= cols && rows >= 0, UIC_ERR_SHAPE, "uic_dropout: rows=%lld cols=%d ld=%lld", static_cast<long long>(rows), cols,
+          static_cast<long long>(ld));
+  if (rows == 0) return 0;
+  return dropout(x, is_bf16, ld, rows, cols, p, reinterpret_cast<const unsigned long long*>(seed), site, row0, row_stride, ST(stream));
+}
+
 int uic_beam_step(const float* topk_val, const int32_t* topk_idx, int32_t* beam_seq, float* beam_lp, float* beam_sum,
                   int32_t* done_seq, float* done_lp, double* done_p, float* done_unaug, int32_t* done_cnt, int32_t* parent_row,
                   int64_t* next_tok, int t, int seq_length, int n_img, int beams, int flags, void* stream) {

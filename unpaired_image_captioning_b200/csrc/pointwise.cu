@@ -3,6 +3,7 @@
 // streaming kernels: 16-byte vector accesses where alignment allows, grid sized from the data.
 #include "uic_internal.h"
 #include "uic_ptx.cuh"
+#include "uic_vocab.cuh"
 
 namespace uic {
 
@@ -170,6 +171,42 @@ int lstm_cell_fwd(const float* gates, long long ld_gates, const float* c_prev, f
   launch_begin("lstm_cell_fwd", stream);
   UIC_CUDA_OK(launch_pdl(lstm_cell_fwd_kernel, dim3(blocks_for(static_cast<long long>(rows) * H, 256)), dim3(256), 0, stream, gates, ld_gates,
                          c_prev, c_out, o, rows, H));
+  UIC_CUDA_OK(cudaGetLastError());
+  launch_end(stream);
+  return 0;
+}
+
+// ---- dropout (nn.Dropout of embed / fc_embed / att_embed and the core output, models/AttModel.py:73-84,431,599) --------
+// keep(row, col) = u >= p with u the counter-based uniform of (seed, site, row, col) (uic_vocab.cuh); kept values are
+// scaled by 1 / (1 - p).  The SAME call on a gradient buffer applies the same mask: that is the whole backward.
+template <typename T>
+__global__ void dropout_kernel(T* __restrict__ x, long long ld, long long rows, int cols, float p, float scale,
+                               const unsigned long long* __restrict__ seed, int site, long long row0, long long row_stride) {
+  pdl_launch_dependents();
+  pdl_wait();
+  const uint32_t sk = rng_step_key(*seed, 0x40000000 + site);
+  const long long total = rows * cols;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = i / cols;
+    const int c = static_cast<int>(i - r * cols);
+    const bool keep = rng_uniform(rng_row_key(sk, static_cast<int>(row0 + r * row_stride)), c) >= p;
+    T& v = x[r * ld + c];
+    v = keep ? static_cast<T>(static_cast<float>(v) * scale) : static_cast<T>(0.0f);
+  }
+}
+
+int dropout(void* x, int is_bf16, long long ld, long long rows, int cols, float p, const unsigned long long* seed, int site,
+            long long row0, long long row_stride, cudaStream_t stream) {
+  const float scale = 1.0f / (1.0f - p);
+  const int grid = blocks_for(rows * cols, 256);
+  launch_begin("dropout", stream);
+  if (is_bf16)
+    UIC_CUDA_OK(launch_pdl(dropout_kernel<__nv_bfloat16>, dim3(grid), dim3(256), 0, stream, static_cast<__nv_bfloat16*>(x), ld, rows, cols, p,
+                           scale, seed, site, row0, row_stride));
+  else
+    UIC_CUDA_OK(launch_pdl(dropout_kernel<float>, dim3(grid), dim3(256), 0, stream, static_cast<float*>(x), ld, rows, cols, p, scale, seed,
+                           site, row0, row_stride));
   UIC_CUDA_OK(cudaGetLastError());
   launch_end(stream);
   return 0;

@@ -106,6 +106,8 @@ int greedy_advance(const float* stats, int parts, int64_t* seq, float* seq_lp, u
 int ss_advance(const float* stats, int parts, const int64_t* gt_tok, long long gt_stride, float ss_prob,
                const unsigned long long* seed, int t, int64_t* tokens_out, int rows, const void* table, long long ld_table,
                void* x_xt, long long ld_x, int E, int V, cudaStream_t stream);
+int dropout(void* x, int is_bf16, long long ld, long long rows, int cols, float p, const unsigned long long* seed, int site,
+            long long row0, long long row_stride, cudaStream_t stream);
 int beam_gather(const int32_t* parent_row, const void* x_src, void* x_dst, long long ld_x, int col0_a, int ncol_a, int col0_b,
                 int ncol_b, const float* c_src, float* c_dst, int n_state, int rows, int H, cudaStream_t stream);
 

@@ -141,7 +141,7 @@ class DecoderEngine:
         return self._packed
 
     # ---- prologue ---------------------------------------------------------------------------------
-    def prepare(self, fc_feats, att_feats, att_masks=None, keep_inputs=False, lazy=False, out=None, clip=True):
+    def prepare(self, fc_feats, att_feats, att_masks=None, keep_inputs=False, lazy=False, out=None, clip=True, drop=None):
         """clip_att + fc_embed + att_embed + ctx2att (models/AttModel.py:99-117).
 
         lazy=True only clips and returns a LazyFeatures: the decode loops then run the prologue straight into the
@@ -163,6 +163,8 @@ class DecoderEngine:
         gemm(x, w.w_att_embed, w.b_att_embed, out_bf16=att, relu=True)
         if att_masks is not None:
             check(self.lib.uic_zero_padded_rows(ptr(att), ptr(att_masks), B, L, H, stream()))
+        if drop is not None:   # att_embed's nn.Dropout (training mode, AttModel.py:79-84): ctx2att sees the dropped tile
+            _lib.dropout(att, drop, _lib.DROP_ATT)
         # p_att is stored in the exponential operand form E = exp(2 p_att)/16 (fp16): the step kernel then
         # gets tanh(p_att + att_h) = 1 - 2/(E F + 1) from an FMA and a shared reciprocal (MUFU.TANH is quarter rate)
         p_att = torch.empty(B * L, A, dtype=torch.float16, device=x.device) if out is None else out.p_att.view(B * L, A)
@@ -172,6 +174,8 @@ class DecoderEngine:
             fc = torch.empty(B, H, dtype=BF16, device=x.device) if out is None else out.fc
             fc_in = _lib.cast_bf16(fc_feats.float().contiguous())
             gemm(fc_in, w.w_fc, w.b_fc, out_bf16=fc, relu=True)
+            if drop is not None:
+                _lib.dropout(fc, drop, _lib.DROP_FC)
         if out is not None:
             if att_masks is not None:
                 out.masks.copy_(att_masks)

@@ -155,9 +155,19 @@ class AttModel(CaptionModel):
             att_masks = att_masks[:, :max_len].contiguous()
         return att_feats, att_masks
 
-    def _check_train_features(self):
-        if self.training and self.drop_prob_lm > 0:
-            raise NotImplementedError("drop_prob_lm > 0 in training mode is not on the B200 hot path yet (use eval() or p=0)")
+    def _dropout(self, device):
+        """(p, device seed) when the reference's nn.Dropout layers are active (training mode, drop_prob_lm > 0), else None.
+        The seed is drawn from torch's CUDA generator per forward call; set `self.dropout_seed` to an int to pin it."""
+        if not (self.training and self.drop_prob_lm > 0):
+            return None
+        seed = getattr(self, "_drop_seed_dev", None)
+        if seed is None or seed.device != device:
+            seed = self._drop_seed_dev = torch.zeros(1, dtype=torch.int64, device=device)
+        if getattr(self, "dropout_seed", None) is None:
+            seed.random_()
+        else:
+            seed.fill_(int(self.dropout_seed))
+        return (float(self.drop_prob_lm), seed)
 
     def _prepare_feature(self, fc_feats, att_feats, att_masks):
         """Returns (fc, att, p_att, masks) like the reference.  att is the bf16 operand tile; p_att is the
@@ -191,11 +201,10 @@ class AttModel(CaptionModel):
         return T if empty.numel() == 0 else int(empty[0]) + 1
 
     def _forward(self, fc_feats, attri_feats, att_feats, seq, att_masks=None):
-        self._check_train_features()
-        ss = self._scheduled_sampling(att_feats.device)
-        if ss is not None or (torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())):
+        ss, drop = self._scheduled_sampling(att_feats.device), self._dropout(att_feats.device)
+        if ss is not None or drop is not None or (torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())):
             from .autograd import decoder_logprobs
-            return decoder_logprobs(self, fc_feats, att_feats, seq, att_masks, ss)
+            return decoder_logprobs(self, fc_feats, att_feats, seq, att_masks, ss, drop)
         eng, lib = self.engine, _lib.load()
         feats = eng.prepare(fc_feats, att_feats, att_masks)
         n_steps = self._active_steps(seq)
@@ -213,9 +222,9 @@ class AttModel(CaptionModel):
         """Additive fast path: fused teacher-forced forward + masked XE without the
         (B, T, V) log-prob tensor.  Equals crit(model(fc, attri, att, labels, att_masks), labels[:,1:], masks[:,1:]).
         `global_mask_sum` (data parallel): the loss normaliser summed over all ranks (dp.global_mask_sum)."""
-        self._check_train_features()
         from .autograd import decoder_loss
-        return decoder_loss(self, fc_feats, att_feats, labels, masks, att_masks, global_mask_sum, self._scheduled_sampling(att_feats.device))
+        return decoder_loss(self, fc_feats, att_feats, labels, masks, att_masks, global_mask_sum,
+                            self._scheduled_sampling(att_feats.device), self._dropout(att_feats.device))
 
     # ---- single step API --------------------------------------------------------------------------------
     def _feats_from_api(self, fc, att, p_att, att_masks, rows):
@@ -307,6 +316,9 @@ class AttModel(CaptionModel):
         beam_size = opt.get("beam_size", 1)
         temperature = opt.get("temperature", 1.0)
         decoding_constraint = opt.get("decoding_constraint", 0)
+        if self.training and self.drop_prob_lm > 0:
+            raise NotImplementedError("sampling with active dropout (training mode, drop_prob_lm > 0) is not built: the decode "
+                                      "loops run the deterministic network; call model.eval() or set drop_prob_lm = 0")
         with torch.no_grad():
             if beam_size > 1:
                 return self._sample_beam(fc_feats, att_feats, att_masks, opt)
