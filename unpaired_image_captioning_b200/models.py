@@ -338,8 +338,8 @@ class AttModel(CaptionModel):
         from . import autograd as AG
         B = seq.size(0)
         labels = torch.cat([seq.new_zeros(B, 1), seq, seq.new_zeros(B, 1)], 1)
-        if decoding_constraint:
-            raise NotImplementedError("differentiable sampling with decoding_constraint is not built")
+        # (decoding_constraint only adds -inf to the banned token AFTER the log-softmax, AttModel.py:220-223: the log-prob
+        # of the sampled token -- never the banned one -- is the plain teacher-forced one)
         lp_g = AG.decoder_token_logprobs(self, fc_feats, att_feats, labels, att_masks)[:, :self.seq_length]
         all_fin = ((seq == 0).cumsum(1) > 0).all(0)                     # (T,) every row has emitted its end token by step t
         unwritten = (all_fin.cumsum(0) - all_fin.long()) > 0            # the loop broke before step t
