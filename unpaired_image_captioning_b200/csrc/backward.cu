@@ -120,44 +120,57 @@ int lstm_maxout_bwd(const float* sums, long long ld_sums, const float* a2c, long
 // phase 2 streams the p_att tile for d att_h[a] = w_a sum_l de_l (1 - tanh^2(p_att[l,a] + att_h[a])).
 constexpr int ATTB_THREADS = 256;
 constexpr int ATTB_WARPS = ATTB_THREADS / 32;
-constexpr int ATTB_MAXC = 4;  // A, H <= 1024
+constexpr int ATTB_GROUP = 2;  // regions whose loads a warp issues before it consumes the first (the kernel is latency bound)
 
-__global__ void __launch_bounds__(ATTB_THREADS) att_step_bwd_kernel(const float* __restrict__ dctx, long long ld_dctx,
-                                                                    const float* __restrict__ alpha,
-                                                                    const __half* __restrict__ p_att,
-                                                                    const __nv_bfloat16* __restrict__ att,
-                                                                    const float* __restrict__ att_h, long long ld_att_h,
-                                                                    const float* __restrict__ w_alpha, float* __restrict__ de,
-                                                                    __nv_bfloat16* __restrict__ datt_h, long long ld_dah, int L,
-                                                                    int A, int H) {
+// C = 256-wide chunks of max(A, H): lane owns elements [256c + 8*lane, +8) of chunk c.
+template <int C>
+__global__ void __launch_bounds__(ATTB_THREADS, C <= 2 ? 4 : 2) att_step_bwd_kernel(const float* __restrict__ dctx, long long ld_dctx,
+                                                                                   const float* __restrict__ alpha,
+                                                                                   const __half* __restrict__ p_att,
+                                                                                   const __nv_bfloat16* __restrict__ att,
+                                                                                   const float* __restrict__ att_h, long long ld_att_h,
+                                                                                   const float* __restrict__ w_alpha, float* __restrict__ de,
+                                                                                   __nv_bfloat16* __restrict__ datt_h, long long ld_dah,
+                                                                                   int L, int A, int H) {
   extern __shared__ float sm[];
-  float* s_de = sm;           // [L]   d alpha, then de
-  float* s_acc = sm + L;      // [A]   d att_h accumulator
+  float* s_de = sm;           // [L]              d alpha, then de
+  float* s_acc = sm + ((L + 3) & ~3);  // [ATTB_WARPS][A]  per-warp d att_h partial sums (16-byte aligned)
   __shared__ float s_red[ATTB_WARPS];
   const int r = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const __nv_bfloat16* a_img = att + static_cast<long long>(r) * L * H;
   const __half* p_img = p_att + static_cast<long long>(r) * L * A;
   const float* al = alpha + static_cast<long long>(r) * L;
-  for (int i = threadIdx.x; i < A; i += ATTB_THREADS) s_acc[i] = 0.0f;
 
-  // phase 1: d alpha_l
-  float dc[ATTB_MAXC * 8];
+  // phase 1: d alpha_l = <dctx, att_l>
+  float dc[C * 8];
 #pragma unroll
-  for (int c = 0; c < ATTB_MAXC; ++c)
+  for (int c = 0; c < C; ++c)
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       const int h = c * 256 + lane * 8 + k;
       dc[c * 8 + k] = h < H ? dctx[static_cast<long long>(r) * ld_dctx + h] : 0.0f;
     }
-  for (int l = warp; l < L; l += ATTB_WARPS) {
-    float part = 0.0f;
+  for (int l0 = warp; l0 < L; l0 += ATTB_WARPS * ATTB_GROUP) {
+    uint4 q[ATTB_GROUP][C];
 #pragma unroll
-    for (int c = 0; c < ATTB_MAXC; ++c) {
-      const int h0 = c * 256 + lane * 8;
-      if (h0 < H) {
-        const uint4 q = ldg_nc_v4(a_img + static_cast<long long>(l) * H + h0);
-        const uint32_t u[4] = {q.x, q.y, q.z, q.w};
+    for (int gi = 0; gi < ATTB_GROUP; ++gi) {
+      const int l = l0 + gi * ATTB_WARPS;
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        const int h0 = c * 256 + lane * 8;
+        q[gi][c] = make_uint4(0, 0, 0, 0);
+        if (l < L && h0 < H) q[gi][c] = ldg_nc_v4(a_img + static_cast<long long>(l) * H + h0);
+      }
+    }
+#pragma unroll
+    for (int gi = 0; gi < ATTB_GROUP; ++gi) {
+      const int l = l0 + gi * ATTB_WARPS;
+      if (l >= L) break;  // warp-uniform
+      float part = 0.0f;
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        const uint32_t u[4] = {q[gi][c].x, q[gi][c].y, q[gi][c].z, q[gi][c].w};
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const float2 f = bf16x2_to_f2(u[k]);
@@ -165,9 +178,9 @@ __global__ void __launch_bounds__(ATTB_THREADS) att_step_bwd_kernel(const float*
           part = fmaf(f.y, dc[c * 8 + 2 * k + 1], part);
         }
       }
+      part = warp_sum(part);
+      if (lane == 0) s_de[l] = part;
     }
-    part = warp_sum(part);
-    if (lane == 0) s_de[l] = part;
   }
   __syncthreads();
   float s = 0.0f;
@@ -177,7 +190,7 @@ __global__ void __launch_bounds__(ATTB_THREADS) att_step_bwd_kernel(const float*
   __syncthreads();
   float tot = 0.0f;
 #pragma unroll
-  for (int q = 0; q < ATTB_WARPS; ++q) tot += s_red[q];
+  for (int q2 = 0; q2 < ATTB_WARPS; ++q2) tot += s_red[q2];
   __syncthreads();
   for (int l = threadIdx.x; l < L; l += ATTB_THREADS) {
     const float v = al[l] * (s_de[l] - tot);
@@ -186,58 +199,86 @@ __global__ void __launch_bounds__(ATTB_THREADS) att_step_bwd_kernel(const float*
   }
   __syncthreads();
 
-  // phase 2: d att_h
-  float ah[ATTB_MAXC * 8], acc[ATTB_MAXC * 8];
+  // phase 2: d att_h[a] = w_a sum_l de_l (1 - tanh^2(p_att[l,a] + att_h[a]))
+  float ah[C * 8], acc[C * 8];
 #pragma unroll
-  for (int c = 0; c < ATTB_MAXC; ++c)
+  for (int c = 0; c < C; ++c)
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
       const int a = c * 256 + lane * 8 + k;
       ah[c * 8 + k] = a < A ? att_h[static_cast<long long>(r) * ld_att_h + a] : 0.0f;
       acc[c * 8 + k] = 0.0f;
     }
-  for (int l = warp; l < L; l += ATTB_WARPS) {
-    const float del = s_de[l];
+  for (int l0 = warp; l0 < L; l0 += ATTB_WARPS * ATTB_GROUP) {
+    uint4 q[ATTB_GROUP][C];
 #pragma unroll
-    for (int c = 0; c < ATTB_MAXC; ++c) {
-      const int a0 = c * 256 + lane * 8;
-      if (a0 < A) {
-        const uint4 q = ldg_nc_v4(p_img + static_cast<long long>(l) * A + a0);
-        const uint32_t u[4] = {q.x, q.y, q.z, q.w};
+    for (int gi = 0; gi < ATTB_GROUP; ++gi) {
+      const int l = l0 + gi * ATTB_WARPS;
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        const int a0 = c * 256 + lane * 8;
+        q[gi][c] = make_uint4(0, 0, 0, 0);
+        if (l < L && a0 < A) q[gi][c] = ldg_nc_v4(p_img + static_cast<long long>(l) * A + a0);
+      }
+    }
+#pragma unroll
+    for (int gi = 0; gi < ATTB_GROUP; ++gi) {
+      const int l = l0 + gi * ATTB_WARPS;
+      if (l >= L) break;  // warp-uniform
+      const float del = 4.0f * s_de[l];
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        const uint32_t u[4] = {q[gi][c].x, q[gi][c].y, q[gi][c].z, q[gi][c].w};
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
           const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&u[k]));
           // operands are E = exp(2 p)/16 and F = 16 exp(2 att_h): tanh = 1 - 2r, 1 - tanh^2 = 4 r (1 - r), r = 1/(E F + 1)
           const float r0 = rcp_approx(fmaf(f.x, ah[c * 8 + 2 * k], 1.0f)), r1 = rcp_approx(fmaf(f.y, ah[c * 8 + 2 * k + 1], 1.0f));
-          acc[c * 8 + 2 * k] = fmaf(del, 4.0f * r0 * (1.0f - r0), acc[c * 8 + 2 * k]);
-          acc[c * 8 + 2 * k + 1] = fmaf(del, 4.0f * r1 * (1.0f - r1), acc[c * 8 + 2 * k + 1]);
+          acc[c * 8 + 2 * k] = fmaf(del, r0 * (1.0f - r0), acc[c * 8 + 2 * k]);
+          acc[c * 8 + 2 * k + 1] = fmaf(del, r1 * (1.0f - r1), acc[c * 8 + 2 * k + 1]);
         }
       }
     }
   }
 #pragma unroll
-  for (int c = 0; c < ATTB_MAXC; ++c) {
+  for (int c = 0; c < C; ++c) {
     const int a0 = c * 256 + lane * 8;
     if (a0 < A) {
-#pragma unroll
-      for (int k = 0; k < 8; ++k) atomicAdd(&s_acc[a0 + k], acc[c * 8 + k]);
+      float* dst = s_acc + warp * A + a0;
+      *reinterpret_cast<float4*>(dst) = make_float4(acc[c * 8], acc[c * 8 + 1], acc[c * 8 + 2], acc[c * 8 + 3]);
+      *reinterpret_cast<float4*>(dst + 4) = make_float4(acc[c * 8 + 4], acc[c * 8 + 5], acc[c * 8 + 6], acc[c * 8 + 7]);
     }
   }
   __syncthreads();
-  for (int a = threadIdx.x; a < A; a += ATTB_THREADS)
-    datt_h[static_cast<long long>(r) * ld_dah + a] = __float2bfloat16_rn(s_acc[a] * w_alpha[a]);
+  for (int a = threadIdx.x; a < A; a += ATTB_THREADS) {
+    float v = 0.0f;
+#pragma unroll
+    for (int q2 = 0; q2 < ATTB_WARPS; ++q2) v += s_acc[q2 * A + a];
+    datt_h[static_cast<long long>(r) * ld_dah + a] = __float2bfloat16_rn(v * w_alpha[a]);
+  }
 }
 
 int att_step_bwd(const float* dctx, long long ld_dctx, const float* alpha, const void* p_att, const void* att, const float* att_h,
                  long long ld_att_h, const float* w_alpha, float* de, void* datt_h, long long ld_dah, int rows, int L, int A,
                  int H, cudaStream_t stream) {
   if (A % 8 || H % 8 || A > 1024 || H > 1024) return set_error(UIC_ERR_SHAPE, "att_step_bwd: A=%d H=%d", A, H);
-  const size_t smem = sizeof(float) * (static_cast<size_t>(L) + A);
+  // s_de [L] (padded to 4 floats so that the float4 stores of the partial sums stay aligned) + per-warp partials
+  const int Lp = (L + 3) / 4 * 4;
+  const size_t smem = sizeof(float) * (static_cast<size_t>(Lp) + static_cast<size_t>(ATTB_WARPS) * A);
   if (smem > 48 * 1024) return set_error(UIC_ERR_SHAPE, "att_step_bwd: L=%d too large", L);
+  const int chunks = ((A > H ? A : H) + 255) / 256;
   launch_begin("att_step_bwd", stream);
-  att_step_bwd_kernel<<<rows, ATTB_THREADS, smem, stream>>>(dctx, ld_dctx, alpha, static_cast<const __half*>(p_att),
-                                                            static_cast<const __nv_bfloat16*>(att), att_h, ld_att_h, w_alpha, de,
-                                                            static_cast<__nv_bfloat16*>(datt_h), ld_dah, L, A, H);
+#define UIC_ATTB(C_)                                                                                                          \
+  att_step_bwd_kernel<C_><<<rows, ATTB_THREADS, smem, stream>>>(dctx, ld_dctx, alpha, static_cast<const __half*>(p_att),          \
+                                                                static_cast<const __nv_bfloat16*>(att), att_h, ld_att_h, w_alpha, \
+                                                                de, static_cast<__nv_bfloat16*>(datt_h), ld_dah, L, A, H)
+  if (chunks <= 1)
+    UIC_ATTB(1);
+  else if (chunks <= 2)
+    UIC_ATTB(2);
+  else
+    UIC_ATTB(4);
+#undef UIC_ATTB
   UIC_CUDA_OK(cudaGetLastError());
   launch_end(stream);
   return 0;
