@@ -320,30 +320,54 @@ __global__ void __launch_bounds__(TILE_THREADS) att_tiles_bwd_kernel(
     s_al[i] = ok ? alpha_all[off] : 0.0f;
   }
   __syncthreads();
+  // Four regions per pass: their p_att values are loaded up front and every shared-memory read of att_h / dctx serves four
+  // of them (the first version re-read shared memory once per region and waited for one global load per region).
+  constexpr int QU = 4;
   for (int a = threadIdx.x; a < A; a += TILE_THREADS) {
     const float wa = w_alpha[a];
     float dw = 0.0f, dbias = 0.0f;
-    for (int q = 0; q < nl; ++q) {
-      const long long off = (static_cast<long long>(b) * L + l0 + q) * A + a;
-      const float p = __half2float(p_att[off]);
-      float acc = 0.0f;
-      for (int t = 0; t < T; ++t) {
-        const float r = rcp_approx(fmaf(p, s_ah[t * A + a], 1.0f));   // p = E, s_ah = F (exponential operand form)
-        const float d = s_de[t * l_chunk + q];
-        acc = fmaf(d, 4.0f * r * (1.0f - r), acc);
-        dw = fmaf(d, 1.0f - 2.0f * r, dw);
+    for (int q0 = 0; q0 < nl; q0 += QU) {
+      float p[QU], acc[QU];
+#pragma unroll
+      for (int u = 0; u < QU; ++u) {
+        const int q = min(q0 + u, nl - 1);
+        p[u] = __half2float(p_att[(static_cast<long long>(b) * L + l0 + q) * A + a]);
+        acc[u] = 0.0f;
       }
-      dp_att[off] = __float2bfloat16_rn(acc * wa);
-      dbias += acc * wa;
+      for (int t = 0; t < T; ++t) {
+        const float f = s_ah[t * A + a];  // p = E, s_ah = F (exponential operand form)
+#pragma unroll
+        for (int u = 0; u < QU; ++u) {
+          const float r = rcp_approx(fmaf(p[u], f, 1.0f));
+          const float d = (q0 + u < nl) ? s_de[t * l_chunk + q0 + u] : 0.0f;
+          acc[u] = fmaf(d, 4.0f * r * (1.0f - r), acc[u]);
+          dw = fmaf(d, 1.0f - 2.0f * r, dw);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < QU; ++u) {
+        if (q0 + u < nl) {
+          dp_att[(static_cast<long long>(b) * L + l0 + q0 + u) * A + a] = __float2bfloat16_rn(acc[u] * wa);
+          dbias += acc[u] * wa;
+        }
+      }
     }
     atomicAdd(dw_alpha + a, dw);
     atomicAdd(dw_alpha + A + a, dbias);  // fp32 column sum of d p_att = d bias of ctx2att
   }
   for (int h = threadIdx.x; h < H; h += TILE_THREADS) {
-    for (int q = 0; q < nl; ++q) {
-      float acc = 0.0f;
-      for (int t = 0; t < T; ++t) acc = fmaf(s_al[t * l_chunk + q], s_dctx[t * H + h], acc);
-      datt[(static_cast<long long>(b) * L + l0 + q) * H + h] = acc;
+    for (int q0 = 0; q0 < nl; q0 += QU) {
+      float acc[QU];
+#pragma unroll
+      for (int u = 0; u < QU; ++u) acc[u] = 0.0f;
+      for (int t = 0; t < T; ++t) {
+        const float dcx = s_dctx[t * H + h];
+#pragma unroll
+        for (int u = 0; u < QU; ++u) acc[u] = fmaf((q0 + u < nl) ? s_al[t * l_chunk + q0 + u] : 0.0f, dcx, acc[u]);
+      }
+#pragma unroll
+      for (int u = 0; u < QU; ++u)
+        if (q0 + u < nl) datt[(static_cast<long long>(b) * L + l0 + q0 + u) * H + h] = acc[u];
     }
   }
 }
