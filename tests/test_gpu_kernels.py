@@ -26,7 +26,7 @@ def _rand_bf16(*shape, seed=0, scale=1.0):
 # ---------------------------------------------------------------------------------------------------
 # GEMM (tcgen05) -- shapes cover full tiles, M/N/K tails, the per-step and prologue sizes
 # ---------------------------------------------------------------------------------------------------
-GEMM_SHAPES = [(128, 128, 64), (128, 128, 512), (256, 384, 192), (5, 52, 32), (35, 52, 64), (300, 200, 72),
+GEMM_SHAPES = [(128, 128, 64), (128, 128, 512), (256, 384, 192), (5, 52, 32), (35, 52, 64), (300, 200, 72), (2048, 2040, 328),
                (768, 3072, 1024), (256, 10000, 512), (16 * 17, 10000, 512), (6272, 512, 2048), (48, 2560, 1024)]
 
 
@@ -71,7 +71,7 @@ def test_gemm_epilogues_and_strided_operands():
 
 
 @pytest.mark.parametrize("a_mn,b_mn", [(False, True), (True, False), (True, True)])
-@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (200, 328, 136), (512, 2560, 8704 // 8)])
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (200, 328, 136), (512, 2560, 8704 // 8), (2048, 2048, 520), (1104, 1000, 264)])
 def test_gemm_mn_major_operands(a_mn, b_mn, M, N, K):
     """dgrad (B stored [K,N]) and wgrad (A stored [K,M], B stored [K,N]) forms."""
     a, b = _rand_bf16(M, K, seed=7), _rand_bf16(N, K, seed=8, scale=0.05)

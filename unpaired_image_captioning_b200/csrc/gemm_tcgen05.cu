@@ -14,7 +14,7 @@
 // TMA-latency bound at ~560 cycles per k-block and a row-per-thread epilogue taking 3x the k-loop):
 //   * persistent: grid = min(#tiles, #SMs); every CTA walks tiles t = blockIdx.x, +gridDim.x, ...
 //     (m fastest, so concurrently running CTAs share the weight tile in L2);
-//   * tile 128 x BN (BN in {64,128}), BLOCK_K = 64 (one 128-byte swizzle row), 6-8 stage TMA ring;
+//   * tile 128 x BN (BN in {64,128,256}), BLOCK_K = 64 (one 128-byte swizzle row), 3-7 stage TMA ring;
 //   * warp 0 = TMA producer, warp 1 = MMA issuer (one elected thread, tcgen05.mma cta_group::1, M = 128),
 //     warp 2 = TMEM allocator, warps 4-7 = epilogue;
 //   * two TMEM accumulator buffers: the epilogue of tile i overlaps the k-loop of tile i+1;
@@ -631,10 +631,23 @@ int gemm_bf16(const void* A, long long lda, const void* B, long long ldb, float*
   if ((reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15) || (lda % 8) || (ldb % 8))
     return set_error(UIC_ERR_ALIGN, "gemm_bf16: operands must be 16-byte aligned with pitches that are multiples of 8 "
                      "elements (lda=%lld ldb=%lld)", lda, ldb);
-  // Narrow tiles when the wide grid would leave most SMs idle (per-step GEMMs with few rows).
-  const long long tiles128 = static_cast<long long>((M + BM - 1) / BM) * ((N + 127) / 128);
-  const bool narrow = tiles128 < 120 || N <= 64;
-  const int bn = narrow ? 64 : 128;
+  // Tile width: the k-loop is bound by what one SM can pull in per k-block (A tile + B tile, ~57 B/clk measured:
+  // 430 / 571 / 750 cycles for 128 x {64, 128, 256}), so wide tiles do more math per byte but leave fewer tiles to
+  // spread over the SMs.  Pick the width with the smallest estimated makespan rounds(tiles / SMs) * cycles per k-block.
+  const long long tiles_m = (M + BM - 1) / BM;
+  const int sms = sm_count();
+  int bn = 64;
+  long long best = -1;
+  const int widths[3] = {64, 128, 256}, cycles[3] = {430, 571, 750};
+  for (int i = 0; i < 3; ++i) {
+    if (widths[i] > 64 && N <= widths[i] / 2) continue;  // mostly padding
+    const long long tiles = tiles_m * ((N + widths[i] - 1) / widths[i]);
+    const long long est = ((tiles + sms - 1) / sms) * cycles[i];
+    if (best < 0 || est < best) {
+      best = est;
+      bn = widths[i];
+    }
+  }
   CUtensorMap ta, tb;
   int rc;
   // operand stored [rows = M or N, cols = K] (K-major) or [rows = K, cols = M or N] (MN-major)
@@ -647,6 +660,7 @@ int gemm_bf16(const void* A, long long lda, const void* B, long long ldb, float*
     return dispatch_major<128, 2>(a_mn, b_mn, ta, tb, ep, M, N, K, stream);
   }
   if (bn == 64) return dispatch_major<64, 7>(a_mn, b_mn, ta, tb, ep, M, N, K, stream);
+  if (bn == 256) return dispatch_major<256, 3>(a_mn, b_mn, ta, tb, ep, M, N, K, stream);
   return dispatch_major<128, 5>(a_mn, b_mn, ta, tb, ep, M, N, K, stream);
 }
 
