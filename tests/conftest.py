@@ -27,6 +27,14 @@ def pytest_collection_modifyitems(config, items):
             item.add_marker(skip)
 
 
+@pytest.fixture(autouse=True)
+def _deterministic_torch_rng():
+    """Every test starts from the same torch CPU / CUDA generator state: inputs drawn with torch.randn(..., device='cuda')
+    are then the same in every run, so a tolerance or near-tie check cannot pass in one run and fail in the next."""
+    torch.manual_seed(20241017)
+    yield
+
+
 def load_golden(name):
     """Returns dict with sub-dicts sd / in / out / grad / <sampling tags> of torch tensors."""
     z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))

@@ -31,26 +31,74 @@ __device__ __forceinline__ float add3(const Addends& a, int r, int j) {
 }
 
 // ---- torch.nn.LSTMCell backward (gate order i, f, g, o) ---------------------------------------------
+// VEC consecutive hidden units per thread (16-byte loads, 8-byte bf16 stores when VEC == 4), like the forward kernels.
+template <int VEC>
+__device__ __forceinline__ void ldv_b(const float* p, float (&v)[VEC]) {
+  if constexpr (VEC == 4) {
+    const float4 q = *reinterpret_cast<const float4*>(p);
+    v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+  } else {
+    v[0] = p[0];
+  }
+}
+template <int VEC>
+__device__ __forceinline__ void stv_bf16_b(__nv_bfloat16* p, const float (&v)[VEC]) {
+  if constexpr (VEC == 4)
+    *reinterpret_cast<uint2*>(p) = make_uint2(f2_to_bf16x2(v[0], v[1]), f2_to_bf16x2(v[2], v[3]));
+  else
+    p[0] = __float2bfloat16_rn(v[0]);
+}
+
+template <int VEC>
 __global__ void lstm_cell_bwd_kernel(const float* __restrict__ gates, long long ld_gates, const float* __restrict__ c_prev,
                                      const float* __restrict__ c, Addends dh, const float* __restrict__ dc_next,
                                      __nv_bfloat16* __restrict__ dgates, long long ld_dg, float* __restrict__ dc_prev, int rows,
                                      int H) {
-  const long long total = static_cast<long long>(rows) * H;
-  for (long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; idx < total;
-       idx += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int r = static_cast<int>(idx / H), j = static_cast<int>(idx - static_cast<long long>(r) * H);
+  const int per_row = H / VEC;
+  const long long total = static_cast<long long>(rows) * per_row;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int r = static_cast<int>(i / per_row), j = static_cast<int>(i - static_cast<long long>(r) * per_row) * VEC;
+    const long long idx = static_cast<long long>(r) * H + j;
     const float* g4 = gates + r * ld_gates;
-    const float ig = sigmoid_acc(g4[j]), fg = sigmoid_acc(g4[H + j]), gg = tanhf(g4[2 * H + j]), og = sigmoid_acc(g4[3 * H + j]);
-    const float tc = tanhf(c[idx]);
-    const float dhv = add3(dh, r, j);
-    const float dc = (dc_next ? dc_next[idx] : 0.0f) + dhv * og * (1.0f - tc * tc);
-    const float cp = c_prev ? c_prev[idx] : 0.0f;
+    float gi[VEC], gf[VEC], gg[VEC], go[VEC], cv[VEC], cp[VEC], dcn[VEC], dhv[VEC], tmp[VEC];
+    ldv_b<VEC>(g4 + j, gi);
+    ldv_b<VEC>(g4 + H + j, gf);
+    ldv_b<VEC>(g4 + 2 * H + j, gg);
+    ldv_b<VEC>(g4 + 3 * H + j, go);
+    ldv_b<VEC>(c + idx, cv);
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) cp[v] = dcn[v] = dhv[v] = 0.0f;
+    if (c_prev) ldv_b<VEC>(c_prev + idx, cp);
+    if (dc_next) ldv_b<VEC>(dc_next + idx, dcn);
+#pragma unroll
+    for (int q = 0; q < 3; ++q)
+      if (dh.p[q]) {
+        ldv_b<VEC>(dh.p[q] + static_cast<long long>(r) * dh.ld[q] + j, tmp);
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) dhv[v] += tmp[v];
+      }
+    float di[VEC], df[VEC], dg[VEC], dO[VEC], dcp[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+      const float ig = sigmoid_acc(gi[v]), fg = sigmoid_acc(gf[v]), g = tanhf(gg[v]), og = sigmoid_acc(go[v]);
+      const float tc = tanhf(cv[v]);
+      const float dc = dcn[v] + dhv[v] * og * (1.0f - tc * tc);
+      di[v] = dc * g * ig * (1.0f - ig);
+      df[v] = dc * cp[v] * fg * (1.0f - fg);
+      dg[v] = dc * ig * (1.0f - g * g);
+      dO[v] = dhv[v] * tc * og * (1.0f - og);
+      dcp[v] = dc * fg;
+    }
     __nv_bfloat16* d = dgates + r * ld_dg;
-    d[j] = __float2bfloat16_rn(dc * gg * ig * (1.0f - ig));
-    d[H + j] = __float2bfloat16_rn(dc * cp * fg * (1.0f - fg));
-    d[2 * H + j] = __float2bfloat16_rn(dc * ig * (1.0f - gg * gg));
-    d[3 * H + j] = __float2bfloat16_rn(dhv * tc * og * (1.0f - og));
-    dc_prev[idx] = dc * fg;
+    stv_bf16_b<VEC>(d + j, di);
+    stv_bf16_b<VEC>(d + H + j, df);
+    stv_bf16_b<VEC>(d + 2 * H + j, dg);
+    stv_bf16_b<VEC>(d + 3 * H + j, dO);
+    if constexpr (VEC == 4)
+      *reinterpret_cast<float4*>(dc_prev + idx) = make_float4(dcp[0], dcp[1], dcp[2], dcp[3]);
+    else
+      dc_prev[idx] = dcp[0];
   }
 }
 
@@ -58,9 +106,17 @@ int lstm_cell_bwd(const float* gates, long long ld_gates, const float* c_prev, c
                   const float* dh1, long long ld1, const float* dh2, long long ld2, const float* dc_next, void* dgates,
                   long long ld_dg, float* dc_prev, int rows, int H, cudaStream_t stream) {
   Addends a{{dh0, dh1, dh2}, {ld0, ld1, ld2}};
+  auto a16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+  const bool vec = H % 4 == 0 && ld_gates % 4 == 0 && ld_dg % 4 == 0 && a16(gates) && a16(c_prev) && a16(c) && a16(dc_next) &&
+                   a16(dc_prev) && (reinterpret_cast<uintptr_t>(dgates) & 7) == 0 && a16(dh0) && a16(dh1) && a16(dh2) &&
+                   ld0 % 4 == 0 && ld1 % 4 == 0 && ld2 % 4 == 0;
   launch_begin("lstm_cell_bwd", stream);
-  lstm_cell_bwd_kernel<<<grid_for(static_cast<long long>(rows) * H, 256), 256, 0, stream>>>(
-      gates, ld_gates, c_prev, c, a, dc_next, static_cast<__nv_bfloat16*>(dgates), ld_dg, dc_prev, rows, H);
+  if (vec)
+    lstm_cell_bwd_kernel<4><<<grid_for(static_cast<long long>(rows) * H / 4, 256), 256, 0, stream>>>(
+        gates, ld_gates, c_prev, c, a, dc_next, static_cast<__nv_bfloat16*>(dgates), ld_dg, dc_prev, rows, H);
+  else
+    lstm_cell_bwd_kernel<1><<<grid_for(static_cast<long long>(rows) * H, 256), 256, 0, stream>>>(
+        gates, ld_gates, c_prev, c, a, dc_next, static_cast<__nv_bfloat16*>(dgates), ld_dg, dc_prev, rows, H);
   UIC_CUDA_OK(cudaGetLastError());
   launch_end(stream);
   return 0;

@@ -103,63 +103,123 @@ struct HOut {
   long long ld_hb;
 };
 
-__device__ __forceinline__ void store_h(const HOut& o, int r, int j, int H, float h) {
-  if (o.h_f32) o.h_f32[static_cast<long long>(r) * H + j] = h;
-  const __nv_bfloat16 hb = __float2bfloat16_rn(h);
-  if (o.h_a) o.h_a[static_cast<long long>(r) * o.ld_ha + j] = hb;
-  if (o.h_b) o.h_b[static_cast<long long>(r) * o.ld_hb + j] = hb;
+// VEC consecutive hidden units per thread: 16-byte loads / 8-byte bf16 stores when VEC == 4 (the launchers check alignment),
+// scalar accesses when VEC == 1.  These kernels are a few microseconds of pure launch + memory latency; a quarter of the
+// threads with four independent chains each is what shortens them.
+template <int VEC>
+__device__ __forceinline__ void ldv(const float* p, float (&v)[VEC]) {
+  if constexpr (VEC == 4) {
+    const float4 q = *reinterpret_cast<const float4*>(p);
+    v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+  } else {
+    v[0] = p[0];
+  }
+}
+template <int VEC>
+__device__ __forceinline__ void stv(float* p, const float (&v)[VEC]) {
+  if constexpr (VEC == 4)
+    *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
+  else
+    p[0] = v[0];
+}
+template <int VEC>
+__device__ __forceinline__ void stv_bf16(__nv_bfloat16* p, const float (&v)[VEC]) {
+  if constexpr (VEC == 4)
+    *reinterpret_cast<uint2*>(p) = make_uint2(f2_to_bf16x2(v[0], v[1]), f2_to_bf16x2(v[2], v[3]));
+  else
+    p[0] = __float2bfloat16_rn(v[0]);
+}
+template <int VEC>
+__device__ __forceinline__ void store_h(const HOut& o, int r, int j, int H, const float (&h)[VEC]) {
+  if (o.h_f32) stv<VEC>(o.h_f32 + static_cast<long long>(r) * H + j, h);
+  if (o.h_a) stv_bf16<VEC>(o.h_a + static_cast<long long>(r) * o.ld_ha + j, h);
+  if (o.h_b) stv_bf16<VEC>(o.h_b + static_cast<long long>(r) * o.ld_hb + j, h);
+}
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+static bool aligned8(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 7) == 0; }
+static bool hout_vec_ok(const HOut& o, int H) {
+  return H % 4 == 0 && aligned16(o.h_f32) && aligned8(o.h_a) && aligned8(o.h_b) && o.ld_ha % 4 == 0 && o.ld_hb % 4 == 0;
 }
 
 // Att2in2Core.forward pointwise part, models/AttModel.py:585-597.
+template <int VEC>
 __global__ void lstm_maxout_fwd_kernel(const float* __restrict__ sums, long long ld_sums, const float* __restrict__ a2c,
                                        long long ld_a2c, const float* __restrict__ c_prev, float* __restrict__ c_out, HOut o,
                                        int rows, int H) {
   pdl_launch_dependents();
   pdl_wait();
-  const long long total = static_cast<long long>(rows) * H;
+  const int per_row = H / VEC;
+  const long long total = static_cast<long long>(rows) * per_row;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int r = static_cast<int>(i / H), j = static_cast<int>(i - static_cast<long long>(r) * H);
+    const int r = static_cast<int>(i / per_row), j = static_cast<int>(i - static_cast<long long>(r) * per_row) * VEC;
     const float* s = sums + r * ld_sums;
     const float* a = a2c + r * ld_a2c;
-    const float ig = sigmoid_acc(s[j]);
-    const float fg = sigmoid_acc(s[H + j]);
-    const float og = sigmoid_acc(s[2 * H + j]);
-    const float g = fmaxf(s[3 * H + j] + a[j], s[4 * H + j] + a[H + j]);
-    const float cp = c_prev ? c_prev[i] : 0.0f;
-    const float c = fg * cp + ig * g;
-    c_out[i] = c;
-    store_h(o, r, j, H, og * tanhf(c));
+    float si[VEC], sf[VEC], so[VEC], s3[VEC], s4[VEC], a0[VEC], a1[VEC], cp[VEC], c[VEC], h[VEC];
+    ldv<VEC>(s + j, si);
+    ldv<VEC>(s + H + j, sf);
+    ldv<VEC>(s + 2 * H + j, so);
+    ldv<VEC>(s + 3 * H + j, s3);
+    ldv<VEC>(s + 4 * H + j, s4);
+    ldv<VEC>(a + j, a0);
+    ldv<VEC>(a + H + j, a1);
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) cp[v] = 0.0f;
+    if (c_prev) ldv<VEC>(c_prev + static_cast<long long>(r) * H + j, cp);
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+      const float ig = sigmoid_acc(si[v]), fg = sigmoid_acc(sf[v]), og = sigmoid_acc(so[v]);
+      const float g = fmaxf(s3[v] + a0[v], s4[v] + a1[v]);
+      c[v] = fg * cp[v] + ig * g;
+      h[v] = og * tanhf(c[v]);
+    }
+    stv<VEC>(c_out + static_cast<long long>(r) * H + j, c);
+    store_h<VEC>(o, r, j, H, h);
   }
 }
 
 // torch.nn.LSTMCell pointwise part (gate order i, f, g, o), used at models/AttModel.py:434,441.
+template <int VEC>
 __global__ void lstm_cell_fwd_kernel(const float* __restrict__ gates, long long ld_gates, const float* __restrict__ c_prev,
                                      float* __restrict__ c_out, HOut o, int rows, int H) {
   pdl_launch_dependents();
   pdl_wait();
-  const long long total = static_cast<long long>(rows) * H;
+  const int per_row = H / VEC;
+  const long long total = static_cast<long long>(rows) * per_row;
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    const int r = static_cast<int>(i / H), j = static_cast<int>(i - static_cast<long long>(r) * H);
+    const int r = static_cast<int>(i / per_row), j = static_cast<int>(i - static_cast<long long>(r) * per_row) * VEC;
     const float* g4 = gates + r * ld_gates;
-    const float ig = sigmoid_acc(g4[j]);
-    const float fg = sigmoid_acc(g4[H + j]);
-    const float gg = tanhf(g4[2 * H + j]);
-    const float og = sigmoid_acc(g4[3 * H + j]);
-    const float cp = c_prev ? c_prev[i] : 0.0f;
-    const float c = fg * cp + ig * gg;
-    c_out[i] = c;
-    store_h(o, r, j, H, og * tanhf(c));
+    float gi[VEC], gf[VEC], gg[VEC], go[VEC], cp[VEC], c[VEC], h[VEC];
+    ldv<VEC>(g4 + j, gi);
+    ldv<VEC>(g4 + H + j, gf);
+    ldv<VEC>(g4 + 2 * H + j, gg);
+    ldv<VEC>(g4 + 3 * H + j, go);
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) cp[v] = 0.0f;
+    if (c_prev) ldv<VEC>(c_prev + static_cast<long long>(r) * H + j, cp);
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) {
+      c[v] = sigmoid_acc(gf[v]) * cp[v] + sigmoid_acc(gi[v]) * tanhf(gg[v]);
+      h[v] = sigmoid_acc(go[v]) * tanhf(c[v]);
+    }
+    stv<VEC>(c_out + static_cast<long long>(r) * H + j, c);
+    store_h<VEC>(o, r, j, H, h);
   }
 }
 
 int lstm_maxout_fwd(const float* sums, long long ld_sums, const float* a2c, long long ld_a2c, const float* c_prev, float* c_out,
                     float* h_f32, void* h_a, long long ld_ha, void* h_b, long long ld_hb, int rows, int H, cudaStream_t stream) {
   HOut o{h_f32, static_cast<__nv_bfloat16*>(h_a), ld_ha, static_cast<__nv_bfloat16*>(h_b), ld_hb};
+  const bool vec = hout_vec_ok(o, H) && aligned16(sums) && aligned16(a2c) && aligned16(c_prev) && aligned16(c_out) && ld_sums % 4 == 0 &&
+                   ld_a2c % 4 == 0;
   launch_begin("lstm_maxout_fwd", stream);
-  UIC_CUDA_OK(launch_pdl(lstm_maxout_fwd_kernel, dim3(blocks_for(static_cast<long long>(rows) * H, 256)), dim3(256), 0, stream, sums, ld_sums,
-                         a2c, ld_a2c, c_prev, c_out, o, rows, H));
+  if (vec)
+    UIC_CUDA_OK(launch_pdl(lstm_maxout_fwd_kernel<4>, dim3(blocks_for(static_cast<long long>(rows) * H / 4, 256)), dim3(256), 0, stream, sums,
+                           ld_sums, a2c, ld_a2c, c_prev, c_out, o, rows, H));
+  else
+    UIC_CUDA_OK(launch_pdl(lstm_maxout_fwd_kernel<1>, dim3(blocks_for(static_cast<long long>(rows) * H, 256)), dim3(256), 0, stream, sums,
+                           ld_sums, a2c, ld_a2c, c_prev, c_out, o, rows, H));
   UIC_CUDA_OK(cudaGetLastError());
   launch_end(stream);
   return 0;
@@ -168,9 +228,14 @@ int lstm_maxout_fwd(const float* sums, long long ld_sums, const float* a2c, long
 int lstm_cell_fwd(const float* gates, long long ld_gates, const float* c_prev, float* c_out, float* h_f32, void* h_a,
                   long long ld_ha, void* h_b, long long ld_hb, int rows, int H, cudaStream_t stream) {
   HOut o{h_f32, static_cast<__nv_bfloat16*>(h_a), ld_ha, static_cast<__nv_bfloat16*>(h_b), ld_hb};
+  const bool vec = hout_vec_ok(o, H) && aligned16(gates) && aligned16(c_prev) && aligned16(c_out) && ld_gates % 4 == 0;
   launch_begin("lstm_cell_fwd", stream);
-  UIC_CUDA_OK(launch_pdl(lstm_cell_fwd_kernel, dim3(blocks_for(static_cast<long long>(rows) * H, 256)), dim3(256), 0, stream, gates, ld_gates,
-                         c_prev, c_out, o, rows, H));
+  if (vec)
+    UIC_CUDA_OK(launch_pdl(lstm_cell_fwd_kernel<4>, dim3(blocks_for(static_cast<long long>(rows) * H / 4, 256)), dim3(256), 0, stream, gates,
+                           ld_gates, c_prev, c_out, o, rows, H));
+  else
+    UIC_CUDA_OK(launch_pdl(lstm_cell_fwd_kernel<1>, dim3(blocks_for(static_cast<long long>(rows) * H, 256)), dim3(256), 0, stream, gates,
+                           ld_gates, c_prev, c_out, o, rows, H));
   UIC_CUDA_OK(cudaGetLastError());
   launch_end(stream);
   return 0;
