@@ -15,6 +15,10 @@ Data layout in HBM (R = decoder rows = images x beams, Kx = width of the activat
 """
 from __future__ import annotations
 
+import contextlib
+import gc
+import weakref
+
 import torch
 
 from . import _lib
@@ -94,6 +98,22 @@ class Slots:
             self.n_state = 2
 
 
+@contextlib.contextmanager
+def _no_gc():
+    """Python's cyclic garbage collector switched off for the duration of a CUDA-graph capture (after one explicit
+    collection): an unreachable object graph that holds a torch.cuda.CUDAGraph (an old model's decode graphs, say) would
+    otherwise be finalised whenever the collector happens to run, and its cudaGraphExecDestroy is not permitted while a
+    stream is capturing -- the capture then fails with cudaErrorStreamCaptureInvalidated."""
+    gc.collect()
+    was = gc.isenabled()
+    gc.disable()
+    try:
+        yield
+    finally:
+        if was:
+            gc.enable()
+
+
 class Features:
     """Output of the prologue (models/AttModel.py:107-117): bf16 att / p_att tiles (+ fc for topdown)."""
 
@@ -122,7 +142,7 @@ class LazyFeatures:
 class DecoderEngine:
     def __init__(self, model):
         _lib.require_device()
-        self.model = model
+        self._model_ref = weakref.ref(model)   # the model owns the engine: no reference cycle, both die by refcount
         self.kind = model.kind
         self._packed = None
         self._graphs = {}
@@ -193,6 +213,10 @@ class DecoderEngine:
                 "masks": None if feats.masks is None else torch.empty(B, L, dtype=torch.float32, device=dev)}
 
     # ---- one decoder step: X, c -> logits -------------------------------------------------------------
+    @property
+    def model(self):
+        return self._model_ref()
+
     def _workspace(self, R, dev):
         w = self.w
         ws = {}
@@ -417,8 +441,9 @@ class DecoderEngine:
             n_kernels = _lib.launch_count() - n0      # library launches inside one decode loop
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                out = run(s)
+            with _no_gc():          # a CUDAGraph / tensor finaliser run by the cyclic GC mid-capture invalidates the capture
+                with torch.cuda.graph(g):
+                    out = run(s)
             self._capture_launches += n_kernels        # issued into the graph, not onto the device
             entry = (g, s, out, n_kernels)
             self._graphs[key] = entry

@@ -57,8 +57,10 @@ class GraphedTrainStep:
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize()
         self.graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(self.graph):
-            self.loss = one_train_step(st=st).detach()
+        from .engine import _no_gc
+        with _no_gc():
+            with torch.cuda.graph(self.graph):
+                self.loss = one_train_step(st=st).detach()
 
     def __call__(self):
         self.graph.replay()
