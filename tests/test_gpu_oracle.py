@@ -94,3 +94,25 @@ def test_bf16_feature_cache_is_consumed_directly():
     seq_b, lp_b = model(fc.cuda(), None, att_bf, None, opt={"beam_size": 3}, mode="sample")
     assert torch.equal(seq_a, seq_b)
     torch.testing.assert_close(lp_a, lp_b, rtol=0, atol=0)
+
+
+def test_beam10_default_and_unfused_paths():
+    """beam_size 10 is the reference's default (models/AttModel.py:170) and runs through the logit-materialising kernels
+    (the fused statistics keep at most 8 candidates per part); the same kernels must also reproduce the fused path's
+    beam-3 and greedy results when the fusion is switched off."""
+    opt, sd, model, fc, att, *_ = _case("att2in2", 5, 49, seed=5, peaked=40.0, eos_bias=2.0)
+    ref_seq, ref_lp, _ = O.sample_beam(sd, "att2in2", fc, att, 16, 10)
+    seq, lp = model(fc.cuda(), None, att.cuda(), None, opt={"beam_size": 10}, mode="sample")
+    rows = (seq == ref_seq).all(1)
+    assert float(rows.float().mean()) >= 0.8, (seq, ref_seq)
+    torch.testing.assert_close(lp[rows], ref_lp[rows], rtol=2e-2, atol=2e-2)
+    assert len(model.done_beams[0]) <= 10
+    fused = [model(fc.cuda(), None, att.cuda(), None, opt={"beam_size": b}, mode="sample") for b in (3, 1)]
+    model.engine.fused_vocab = False
+    try:
+        plain = [model(fc.cuda(), None, att.cuda(), None, opt={"beam_size": b}, mode="sample") for b in (3, 1)]
+    finally:
+        model.engine.fused_vocab = True
+    for (s_f, lp_f), (s_p, lp_p) in zip(fused, plain):
+        assert torch.equal(s_f.cpu(), s_p.cpu())
+        torch.testing.assert_close(lp_f.cpu(), lp_p.cpu(), rtol=1e-4, atol=2e-4)
