@@ -65,3 +65,29 @@ def test_sass_uses_blackwell_tensor_and_tma_instructions(lib_path):
     assert "UTCHMMA" in sass      # tcgen05.mma
     assert "UTMALDG" in sass      # TMA tile loads
     assert "LDTM" in sass         # tcgen05.ld (TMEM -> registers)
+
+
+def test_missing_library_fails_loudly(monkeypatch, tmp_path):
+    """No CPU or PyTorch fallback: without libuic_b200.so the binding raises instead of computing something else."""
+    from unpaired_image_captioning_b200 import _lib
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", str(tmp_path / "libuic_b200.so"))
+    with pytest.raises(_lib.UicError, match="no CPU fallback"):
+        _lib.load()
+
+
+def test_empty_batch_returns_empty_results():
+    """Edge case of the reference interface: a batch of zero images yields empty outputs (no kernel is launched)."""
+    import torch
+    import unpaired_image_captioning_b200 as uic
+    from unpaired_image_captioning_b200 import synth
+    opt, cfg = synth.opt_for("tiny_att2in2")
+    model = uic.setup(opt).eval()
+    fc = torch.zeros(0, opt.fc_feat_size)
+    att = torch.zeros(0, 7, opt.att_feat_size)
+    seq, lp = model(fc, None, att, None, opt={"beam_size": 1}, mode="sample")
+    assert seq.shape == (0, opt.seq_length) and lp.shape == (0, opt.seq_length) and seq.dtype == torch.long
+    seq, lp = model(fc, None, att, None, opt={"beam_size": 3}, mode="sample")
+    assert seq.shape == (0, opt.seq_length)
+    out = model(fc, None, att, torch.zeros(0, opt.seq_length + 2, dtype=torch.long))
+    assert out.shape == (0, opt.seq_length + 1, opt.vocab_size + 1)

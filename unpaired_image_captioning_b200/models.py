@@ -201,6 +201,8 @@ class AttModel(CaptionModel):
         return T if empty.numel() == 0 else int(empty[0]) + 1
 
     def _forward(self, fc_feats, attri_feats, att_feats, seq, att_masks=None):
+        if att_feats.size(0) == 0:   # empty batch: the reference's torch ops return an empty (0, T, V) tensor
+            return att_feats.new_zeros((0, seq.size(1) - 1, self.vocab_size + 1), dtype=torch.float32)
         ss, drop = self._scheduled_sampling(att_feats.device), self._dropout(att_feats.device)
         if ss is not None or drop is not None or (torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())):
             from .autograd import decoder_logprobs
@@ -316,6 +318,8 @@ class AttModel(CaptionModel):
         beam_size = opt.get("beam_size", 1)
         temperature = opt.get("temperature", 1.0)
         decoding_constraint = opt.get("decoding_constraint", 0)
+        if att_feats.size(0) == 0:   # empty batch, like the reference: empty (0, seq_length) results
+            return (att_feats.new_zeros((0, self.seq_length), dtype=torch.long), att_feats.new_zeros((0, self.seq_length), dtype=torch.float32))
         if self.training and self.drop_prob_lm > 0:
             raise NotImplementedError("sampling with active dropout (training mode, drop_prob_lm > 0) is not built: the decode "
                                       "loops run the deterministic network; call model.eval() or set drop_prob_lm = 0")
