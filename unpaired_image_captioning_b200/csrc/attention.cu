@@ -149,7 +149,8 @@ __device__ __forceinline__ void att_advance(AttCursor& c, int nbpi, int n_grp, i
 }
 
 // CA = ceil(A / 256): lane owns units [256c + 128h + 4*lane, +4), h = 0, 1.  MT = 16-column context tiles per warp.
-template <int NB, int CA, int MT>
+// EXA: A == 256 * CA exactly (no tail guards / register clears in the scoring loop).
+template <int NB, int CA, int MT, bool EXA>
 __global__ void __launch_bounds__(ATT_THREADS, (CA <= 2 && MT <= 4) ? 2 : 1)
 att_step_fwd_kernel(const __grid_constant__ CUtensorMap tmap_att, AttParams p) {
   extern __shared__ uint8_t att_smem_raw[];
@@ -282,8 +283,9 @@ att_step_fwd_kernel(const __grid_constant__ CUtensorMap tmap_att, AttParams p) {
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           const int u0 = c * 256 + h * 128 + lane * 4;
-          uint32_t u[2] = {0, 0};
-          if (u0 < A)
+          uint32_t u[2];
+          if (!EXA) u[0] = u[1] = 0;
+          if (EXA || u0 < A)
             asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(u[0]), "=r"(u[1]) : "r"(prow + x * ATT_WARPS * A * 2 + u0 * 2));
 #pragma unroll
           for (int k = 0; k < 2; ++k) {
@@ -303,8 +305,9 @@ att_step_fwd_kernel(const __grid_constant__ CUtensorMap tmap_att, AttParams p) {
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           const int u0 = c * 256 + h * 128 + lane * 4;
-          float4 f = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-          if (u0 < A) f = *reinterpret_cast<const float4*>(Fimg + j * A + u0);
+          float4 f;
+          if (!EXA) f = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+          if (EXA || u0 < A) f = *reinterpret_cast<const float4*>(Fimg + j * A + u0);
           const int k = c * 8 + h * 4;
 #pragma unroll
           for (int x = 0; x < NR; ++x) {
@@ -622,10 +625,10 @@ long long att_step_workspace_bytes(int n_img, int beams, int L, int A, int H) {
   return counters + (pl.segs > 1 ? jobs * pl.segs * ATT_WARPS * 32 * (4 + 4 * pl.mt) * 4 : 0);
 }
 
-template <int NB, int CA, int MT>
+template <int NB, int CA, int MT, bool EXA>
 static int launch_att(AttParams& p, const AttPlan& pl, int n_img, cudaStream_t stream) {
   const size_t smem = att_smem_layout(p.A, p.H, NB, pl.f_bufs).total;
-  auto kern = att_step_fwd_kernel<NB, CA, MT>;
+  auto kern = att_step_fwd_kernel<NB, CA, MT, EXA>;
   if (smem > 226 * 1024) return set_error(UIC_ERR_SHAPE, "att_step_fwd: A=%d H=%d need %zu bytes of shared memory", p.A, p.H, smem);
   if (smem > 40 * 1024)  // dynamic + the kernel's static shared memory may exceed the 48 KB default
     UIC_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
@@ -647,10 +650,11 @@ static int launch_att(AttParams& p, const AttPlan& pl, int n_img, cudaStream_t s
 
 template <int CA, int MT>
 static int dispatch_nb(AttParams& p, const AttPlan& pl, int n_img, cudaStream_t stream) {
+  const bool exa = p.A == 256 * CA;
   switch (pl.nb) {
-    case 1: return launch_att<1, CA, MT>(p, pl, n_img, stream);
-    case 2: return launch_att<2, CA, MT>(p, pl, n_img, stream);
-    default: return launch_att<3, CA, MT>(p, pl, n_img, stream);
+    case 1: return exa ? launch_att<1, CA, MT, true>(p, pl, n_img, stream) : launch_att<1, CA, MT, false>(p, pl, n_img, stream);
+    case 2: return exa ? launch_att<2, CA, MT, true>(p, pl, n_img, stream) : launch_att<2, CA, MT, false>(p, pl, n_img, stream);
+    default: return exa ? launch_att<3, CA, MT, true>(p, pl, n_img, stream) : launch_att<3, CA, MT, false>(p, pl, n_img, stream);
   }
 }
 
