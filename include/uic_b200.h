@@ -107,9 +107,12 @@ int uic_zero_padded_rows(void* x_bf16, const float* att_masks, int n_img, int L,
  * so that tanh(p_att + att_h) = 1 - 2 / (E F + 1).  att is bf16 (n_img,L,H).  Both tiles are read
  * once per image and shared by the image's beams.
  * Outputs (each optional): ctx_bf16, ctx_f32, alpha (rows x L fp32, saved for backward).
+ * att_h must be 16-byte aligned with a pitch that is a multiple of 4 floats (its rows are staged by bulk copies);
+ * the context weights are rounded to bf16 for the tensor-core product (fp32 accumulation, fp32 normalisation).
  * `workspace`: uic_att_step_workspace_bytes(...) bytes, 16-byte aligned, zeroed ONCE by the caller
  * (the kernel leaves its arrival counters at zero); it holds the partial results when the regions
- * of an image are split over several CTAs (slices of at most 64 regions; L <= 32 slices). */
+ * of an image are split over several CTAs (small batches only: with at least 148 (image, beam group)
+ * jobs a CTA owns whole images and the workspace is only the counters). */
 int uic_att_step_fwd(const float* att_h, int64_t ld_att_h, const void* p_att_f16, const void* att_bf16,
                      const float* w_alpha, const float* att_masks, void* ctx_bf16, int64_t ld_ctx_bf16, float* ctx_f32,
                      int64_t ld_ctx_f32, float* alpha, void* workspace, int64_t workspace_bytes, int n_img, int beams, int L,
