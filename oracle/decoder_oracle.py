@@ -305,17 +305,18 @@ def gumbel_noise(seed, step, rows, cols):
 
 @torch.no_grad()
 def sample_multinomial(sd, kind, fc_feats, att_feats, seq_length, temperature=1.0, seed=0, att_masks=None,
-                       decoding_constraint=0, return_margins=False):
+                       decoding_constraint=0, return_margins=False, drop=None):
+    """drop = (p, seed): the roll-out of a model in train() mode (self-critical training samples with dropout active)."""
     B = fc_feats.size(0)
     state = init_hidden(sd, kind, B)
-    fc, att, p_att, masks = prepare_features(sd, kind, fc_feats, att_feats, att_masks)
+    fc, att, p_att, masks = prepare_features(sd, kind, fc_feats, att_feats, att_masks, drop)
     seq = torch.zeros(B, seq_length, dtype=torch.int64)
     seq_lp = torch.zeros(B, seq_length)
     margins = torch.full((B, seq_length), float("inf"))
     it = torch.zeros(B, dtype=torch.int64)
     unfinished = None
     for t in range(seq_length + 1):
-        lp, state = logprobs_state(sd, kind, it, fc, att, p_att, masks, state)
+        lp, state = logprobs_state(sd, kind, it, fc, att, p_att, masks, state, drop, t, seq_length + 1)
         if decoding_constraint and t > 0:                               # :220-223
             lp = lp.clone()
             lp.scatter_(1, seq[:, t - 1:t], float("-inf"))
@@ -342,17 +343,17 @@ def reward_loss(sample_logprobs, seq, reward):
     return torch.sum(-sample_logprobs * reward * mask) / torch.sum(mask)
 
 
-def rl_loss_and_grads(sd, kind, fc_feats, att_feats, seq, reward, att_masks=None):
+def rl_loss_and_grads(sd, kind, fc_feats, att_feats, seq, reward, att_masks=None, drop=None):
     """Self-critical step of trainer.py:166-173 for given sampled tokens: the roll-out's log-probs are those of
     teacher forcing on [BOS, seq] (AttModel.py:205-248 feeds `it * unfinished`, i.e. 0 after the end token)."""
     leaf = {k: v.detach().clone().requires_grad_(True) for k, v in sd.items()}
     B, T = seq.shape
     labels = torch.cat([torch.zeros(B, 1, dtype=torch.int64), seq, torch.zeros(B, 1, dtype=torch.int64)], 1)
-    fc, att, p_att, masks = prepare_features(leaf, kind, fc_feats, att_feats, att_masks)
+    fc, att, p_att, masks = prepare_features(leaf, kind, fc_feats, att_feats, att_masks, drop)
     state = init_hidden(leaf, kind, B)
     lps = []
     for t in range(T):
-        lp, state = logprobs_state(leaf, kind, labels[:, t], fc, att, p_att, masks, state)
+        lp, state = logprobs_state(leaf, kind, labels[:, t], fc, att, p_att, masks, state, drop, t, T + 1)
         lps.append(lp.gather(1, labels[:, t + 1:t + 2]).squeeze(1))
     sample_lp = torch.stack(lps, 1)
     loss = reward_loss(sample_lp, seq, reward)

@@ -213,3 +213,44 @@ def test_training_with_dropout_matches_oracle(kind, L, B):
     ref = O.teacher_forced(sd, kind, fc, att, labels)
     sel = masks[:, 1:].bool()
     assert float(((out.cpu() - ref).abs() / ref.abs().clamp_min(1.0))[sel].max()) < 2e-3
+
+
+@pytest.mark.parametrize("kind,L,B", [("att2in2", 49, 8), ("topdown", 36, 8)])
+def test_self_critical_step_in_train_mode_with_dropout(kind, L, B):
+    """trainer.py:166-173 as the reference runs it: model.train() with drop_prob_lm = 0.5, so the roll-out and the
+    log-probs that are differentiated both see the dropout masks.  Roll-out against the oracle (same masks, same
+    Gumbel noise), roll-out log-probs == differentiable log-probs, loss and gradients against the oracle's autograd."""
+    opt = synth.make_opt(caption_model=kind, vocab_size=9999, rnn_size=512, input_encoding_size=512, att_hid_size=512, seq_length=16,
+                         drop_prob_lm=0.5)
+    sd = synth.init_state_dict(opt, seed=29, eos_bias=3.0)
+    fc, att = synth.make_features(B, L, 2048, seed=29)
+    model = uic.setup(opt)
+    model.load_state_dict(sd)
+    model = model.cuda().train()
+    model.dropout_seed = 777
+    o = {"sample_max": 0, "seed": 55}
+    ref_seq, ref_lp, margins = O.sample_multinomial(sd, kind, fc, att, 16, seed=55, return_margins=True, drop=(0.5, 777))
+    with torch.no_grad():
+        seq_ng, lp_ng = model(fc.cuda(), None, att.cuda(), None, opt=o, mode="sample")
+    exact, exempt, failures = compare_greedy(seq_ng.cpu(), ref_seq, margins, tol=5e-2)
+    assert not failures, failures
+    assert exact >= 2
+    plain_seq, _ = O.sample_multinomial(sd, kind, fc, att, 16, seed=55)
+    assert not torch.equal(ref_seq, plain_seq)                         # the masks change the roll-out
+    gen, sample_lp = model(fc.cuda(), None, att.cuda(), None, opt=o, mode="sample")
+    assert torch.equal(gen, seq_ng) and sample_lp.requires_grad
+    written = lp_ng != 0
+    torch.testing.assert_close(sample_lp.detach()[written], lp_ng[written], rtol=2e-2, atol=2e-2)
+    g = torch.Generator().manual_seed(2)
+    reward = torch.randn(B, 1, generator=g).expand(B, 16).contiguous()
+    loss = uic.RewardCriterion()(sample_lp, gen, reward.cuda())
+    loss.backward()
+    ref_loss, ref_grads, _ = O.rl_loss_and_grads(sd, kind, fc, att, gen.cpu(), reward, drop=(0.5, 777))
+    assert abs(float(loss.detach()) - float(ref_loss)) < 2e-2 * max(1.0, abs(float(ref_loss)))
+    errs = {}
+    for name, p in model.named_parameters():
+        ref = ref_grads[name].cuda()
+        gr = p.grad if p.grad is not None else torch.zeros_like(p)
+        errs[name] = float(gr.abs().max()) if float(ref.abs().max()) < 1e-7 else float((gr - ref).norm()) / float(ref.norm())
+    bad = {k: v for k, v in errs.items() if v > 9e-2}
+    assert not bad, bad

@@ -362,8 +362,8 @@ class _DecoderTokenLogprobsFn(torch.autograd.Function):
     computation as teacher forcing on the sampled tokens).  The (B, T, V) log-probs are never materialised."""
 
     @staticmethod
-    def forward(ctx, model, fc_feats, att_feats, labels, att_masks, *params):
-        r = teacher_forced_run(model, fc_feats, att_feats, labels, att_masks, all_steps=True)
+    def forward(ctx, model, fc_feats, att_feats, labels, att_masks, drop, *params):
+        r = teacher_forced_run(model, fc_feats, att_feats, labels, att_masks, all_steps=True, drop=drop)
         T_total = r.T_total
         target = labels[:, 1:T_total + 1].contiguous().view(-1).long()
         ones = torch.ones(target.numel(), dtype=torch.float32, device=target.device)
@@ -381,13 +381,13 @@ class _DecoderTokenLogprobsFn(torch.autograd.Function):
         names, params = _param_list(r.model)
         g = bptt(r, o["dh"])
         g["logit.weight"], g["logit.bias"] = o["dW"], o["db"]
-        return (None,) * 5 + tuple(_finish(r, g, None, names, params))
+        return (None,) * 6 + tuple(_finish(r, g, None, names, params))
 
 
-def decoder_token_logprobs(model, fc_feats, att_feats, labels, att_masks=None):
+def decoder_token_logprobs(model, fc_feats, att_feats, labels, att_masks=None, drop=None):
     """labels: (B, T_total + 1) int64 with the BOS column in front (token t is the target of step t - 1)."""
     _, params = _param_list(model)
-    return _DecoderTokenLogprobsFn.apply(model, fc_feats, att_feats, labels, att_masks, *params)
+    return _DecoderTokenLogprobsFn.apply(model, fc_feats, att_feats, labels, att_masks, drop, *params)
 
 
 def decoder_loss(model, fc_feats, att_feats, labels, masks, att_masks=None, global_mask_sum=None, ss=None, drop=None):

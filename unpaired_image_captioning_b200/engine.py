@@ -128,15 +128,16 @@ class Features:
 class LazyFeatures:
     """Clipped raw inputs of the prologue; `materialize(out)` runs it into the given Features buffers."""
 
-    def __init__(self, engine, fc_feats, att_feats, masks, B, L):
+    def __init__(self, engine, fc_feats, att_feats, masks, B, L, drop=None):
         self.engine, self.fc_feats, self.att_feats, self.masks, self.B, self.L = engine, fc_feats, att_feats, masks, B, L
+        self.drop = drop
 
     @property
     def device(self):
         return self.att_feats.device
 
     def materialize(self, out):
-        return self.engine.prepare(self.fc_feats, self.att_feats, self.masks, out=out, clip=False)
+        return self.engine.prepare(self.fc_feats, self.att_feats, self.masks, out=out, clip=False, drop=self.drop)
 
 
 class DecoderEngine:
@@ -173,7 +174,7 @@ class DecoderEngine:
         B, L, D = att_feats.shape
         H, A = w.H, w.A
         if lazy:
-            return LazyFeatures(self, fc_feats, att_feats, att_masks, B, L)
+            return LazyFeatures(self, fc_feats, att_feats, att_masks, B, L, drop)
         if att_feats.dtype == BF16:   # a bf16 feature cache is consumed as is (no staging pass, half the H2D bytes)
             x = att_feats.reshape(B * L, D)
             x = x if x.is_contiguous() else x.contiguous()
@@ -289,17 +290,23 @@ class DecoderEngine:
         check(self.lib.uic_embed_rows(ptr(w.emb_relu), w.E, ptr(tok), ptr(X[:, sl.xt[0]:]), X.stride(0), X.shape[0], w.E, w.V, stream()))
 
     # ---- greedy (models/AttModel.py:198-253, sample_max = 1) -------------------------------------------
-    def greedy(self, feats, seq_length, decoding_constraint=0, temperature=0.0, seed=None):
+    def greedy(self, feats, seq_length, decoding_constraint=0, temperature=0.0, seed=None, drop=None):
         """sample_max = 1 (temperature 0) or multinomial sampling with `temperature` (models/AttModel.py:231-239):
         the arg-max of the logits perturbed by Gumbel noise, which is a function of (seed, step, row, column).
-        `seed`: an int, or None to draw one from torch's CUDA generator (so torch.manual_seed controls it)."""
+        `seed`: an int, or None to draw one from torch's CUDA generator (so torch.manual_seed controls it).
+        `drop` = (p, device seed tensor): the roll-out runs with the training-mode dropout masks of the teacher-forced
+        path (same counter-based draws: embeddings rows t * B + b, core output rows b * (T + 1) + t), as the reference does
+        when it samples in train() mode for self-critical training; `feats` must have been prepared with the same drop."""
         w, lib = self.w, self.lib
         B, dev, T = feats.B, feats.device, seq_length
         flags = _lib.SAMPLE_DECODING_CONSTRAINT if decoding_constraint else 0
         temperature = float(temperature)
         if temperature > 0.0 and not self.fused_vocab:
             raise NotImplementedError("multinomial sampling runs in the fused statistics epilogue (engine.fused_vocab)")
-        key = ("greedy", B, feats.L, T, flags, feats.masks is not None, self.fused_vocab, temperature)
+        if drop is not None and not self.fused_vocab:
+            raise NotImplementedError("roll-outs with dropout run in the fused statistics path (engine.fused_vocab)")
+        key = ("greedy", B, feats.L, T, flags, feats.masks is not None, self.fused_vocab, temperature,
+               None if drop is None else (float(drop[0]), drop[1].data_ptr()))
 
         def alloc():
             s = {**self._feature_buffers(feats),
@@ -312,6 +319,7 @@ class DecoderEngine:
             s["feats"] = Features(s["att"], s["p_att"], s["fc"], s["masks"], B, feats.L)
             s["X"], s["c"], s["sl"] = self._new_state(B, dev, s["feats"], 1)
             s["img_idx"] = torch.arange(B, device=dev, dtype=torch.int64)
+            s["h_drop"] = torch.empty(B, w.H, dtype=BF16, device=dev) if drop is not None else None
             return s
 
         def run(s):
@@ -321,8 +329,15 @@ class DecoderEngine:
             if self.kind == "topdown":
                 check(lib.uic_embed_rows(ptr(f.fc), w.H, ptr(s["img_idx"]), ptr(X[:, sl.fc[0]:]), X.stride(0), B, w.H, B, stream()))
             self._embed(s["tok"], X, sl)
+            xt_view = X[:, sl.xt[0]:sl.xt[0] + w.E]
+            if drop is not None:
+                _lib.dropout(xt_view, drop, _lib.DROP_XT, row0=0)
             for t in range(T):
                 h = self.core_step(X, c, f, ws)
+                if drop is not None:   # the logit layer sees the dropped output; the recurrent state does not (AttModel.py:431,599)
+                    s["h_drop"].copy_(h)
+                    h = s["h_drop"]
+                    _lib.dropout(h, drop, _lib.DROP_OUT, row0=t, row_stride=T + 1)
                 if self.fused_vocab:
                     # logit GEMM with the statistics epilogue (max / sum-exp / arg-max per column part) + merge:
                     # the (B, V) logits are never written
@@ -334,6 +349,8 @@ class DecoderEngine:
                     check(lib.uic_greedy_advance(ptr(s["stats"]), s["parts"], ptr(s["seq"]), ptr(s["lp"]), ptr(s["unf"]), ptr(s["tok"]),
                                                  ptr(s["nunf"]), t, T, B, ptr(w.emb_relu), w.E, ptr(xt), X.stride(0), w.E, w.V, temperature, ptr(s["seed"]),
                                                  stream()))
+                    if drop is not None and t + 1 < T:
+                        _lib.dropout(xt_view, drop, _lib.DROP_XT, row0=(t + 1) * B)
                     continue
                 else:
                     self.logits_of(h, ws["logits"])

@@ -320,20 +320,21 @@ class AttModel(CaptionModel):
         decoding_constraint = opt.get("decoding_constraint", 0)
         if att_feats.size(0) == 0:   # empty batch, like the reference: empty (0, seq_length) results
             return (att_feats.new_zeros((0, self.seq_length), dtype=torch.long), att_feats.new_zeros((0, self.seq_length), dtype=torch.float32))
-        if self.training and self.drop_prob_lm > 0:
-            raise NotImplementedError("sampling with active dropout (training mode, drop_prob_lm > 0) is not built: the decode "
-                                      "loops run the deterministic network; call model.eval() or set drop_prob_lm = 0")
+        drop = self._dropout(att_feats.device)   # train() mode: the reference samples with its dropout layers active
         with torch.no_grad():
             if beam_size > 1:
+                if drop is not None:
+                    raise NotImplementedError("beam search with active dropout (training mode, drop_prob_lm > 0) is not built: "
+                                              "call model.eval()")
                 return self._sample_beam(fc_feats, att_feats, att_masks, opt)
             eng = self.engine
-            feats = eng.prepare(fc_feats, att_feats, att_masks, lazy=True)
+            feats = eng.prepare(fc_feats, att_feats, att_masks, lazy=True, drop=drop)
             if sample_max:
-                seq, lp = eng.greedy(feats, self.seq_length, decoding_constraint)
+                seq, lp = eng.greedy(feats, self.seq_length, decoding_constraint, drop=drop)
                 return seq.clone(), lp.clone()
             if not temperature > 0.0:
                 raise ValueError(f"sample_max=0 needs temperature > 0 (got {temperature})")
-            seq, lp = eng.greedy(feats, self.seq_length, decoding_constraint, temperature=temperature, seed=opt.get("seed"))
+            seq, lp = eng.greedy(feats, self.seq_length, decoding_constraint, temperature=temperature, seed=opt.get("seed"), drop=drop)
             seq, lp = seq.clone(), lp.clone()
         if not (torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())):
             return seq, lp
@@ -344,7 +345,7 @@ class AttModel(CaptionModel):
         labels = torch.cat([seq.new_zeros(B, 1), seq, seq.new_zeros(B, 1)], 1)
         # (decoding_constraint only adds -inf to the banned token AFTER the log-softmax, AttModel.py:220-223: the log-prob
         # of the sampled token -- never the banned one -- is the plain teacher-forced one)
-        lp_g = AG.decoder_token_logprobs(self, fc_feats, att_feats, labels, att_masks)[:, :self.seq_length]
+        lp_g = AG.decoder_token_logprobs(self, fc_feats, att_feats, labels, att_masks, drop)[:, :self.seq_length]
         all_fin = ((seq == 0).cumsum(1) > 0).all(0)                     # (T,) every row has emitted its end token by step t
         unwritten = (all_fin.cumsum(0) - all_fin.long()) > 0            # the loop broke before step t
         return seq, lp_g * (~unwritten).to(lp_g.dtype)
