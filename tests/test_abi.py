@@ -91,3 +91,14 @@ def test_empty_batch_returns_empty_results():
     assert seq.shape == (0, opt.seq_length)
     out = model(fc, None, att, torch.zeros(0, opt.seq_length + 2, dtype=torch.long))
     assert out.shape == (0, opt.seq_length + 1, opt.vocab_size + 1)
+
+
+def test_header_is_plain_c():
+    """The drop-in boundary is a C ABI: the header must compile as C99 on its own (no C++ or torch types)."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no gcc")
+    r = subprocess.run([gcc, "-fsyntax-only", "-x", "c", "-std=c99", "-Wall", "-pedantic", HEADER], capture_output=True, text=True)
+    assert r.returncode == 0 and not r.stderr.strip(), r.stderr
