@@ -116,3 +116,20 @@ def test_beam10_default_and_unfused_paths():
     for (s_f, lp_f), (s_p, lp_p) in zip(fused, plain):
         assert torch.equal(s_f.cpu(), s_p.cpu())
         torch.testing.assert_close(lp_f.cpu(), lp_p.cpu(), rtol=1e-4, atol=2e-4)
+
+
+def test_decode_graph_cache_is_bounded():
+    """Masked batches are clipped to their longest region count (AttModel.py:99-105), so every new length is a new decode
+    graph with its own static tile buffers: the engine keeps only the most recently used few."""
+    opt, sd, model, fc, att, *_ = _case("att2in2", 4, 24, seed=5, peaked=40.0, eos_bias=2.0)
+    eng = model.engine
+    eng.max_graphs = 3
+    first = None
+    for keep in (24, 20, 16, 12, 8, 24):
+        masks = torch.zeros(4, 24)
+        masks[:, :keep] = 1.0
+        seq, _ = model(fc.cuda(), None, att.cuda(), masks.cuda(), opt={"beam_size": 1}, mode="sample")
+        if keep == 24:
+            first = seq.clone() if first is None else first
+            assert torch.equal(seq, first)            # an evicted shape is simply captured again
+        assert len(eng._graphs) <= 3

@@ -176,6 +176,8 @@ def att_workspace(n_img, beams, L, A, H, device):
     if ws is None:
         nbytes = int(load().uic_att_step_workspace_bytes(n_img, beams, L, A, H))
         ws = torch.zeros(max(nbytes, 16), dtype=torch.uint8, device=device)
+        # (never evicted: captured CUDA graphs hold raw pointers into these tensors; they are a few KB for large batches and
+        # about a megabyte when small batches are cut into segments)
         _att_ws[key] = ws
     return ws
 

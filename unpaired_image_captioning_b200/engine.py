@@ -15,6 +15,7 @@ Data layout in HBM (R = decoder rows = images x beams, Kx = width of the activat
 """
 from __future__ import annotations
 
+import collections
 import contextlib
 import gc
 import weakref
@@ -146,7 +147,8 @@ class DecoderEngine:
         self._model_ref = weakref.ref(model)   # the model owns the engine: no reference cycle, both die by refcount
         self.kind = model.kind
         self._packed = None
-        self._graphs = {}
+        self._graphs = collections.OrderedDict()   # least-recently-used first
+        self.max_graphs = 6     # each entry owns static tile buffers (~200 MB at B=256, L=196): keep a handful of shapes
         self.use_graphs = True
         self.fused_vocab = True   # sampling: logit GEMM with fused LSE/top-k statistics (False: write logits + row kernels)
         self._capture_launches = 0
@@ -448,6 +450,8 @@ class DecoderEngine:
                 pre(s)
             return run(s)
         entry = self._graphs.get(key)
+        if entry is not None:
+            self._graphs.move_to_end(key)
         if entry is None:
             s = alloc()
             self._load_feats(s, feats)
@@ -464,6 +468,8 @@ class DecoderEngine:
             self._capture_launches += n_kernels        # issued into the graph, not onto the device
             entry = (g, s, out, n_kernels)
             self._graphs[key] = entry
+            while len(self._graphs) > self.max_graphs:   # e.g. att_masks clip every batch to a different length
+                self._graphs.popitem(last=False)
         g, s, out, n_kernels = entry
         self._load_feats(s, feats)
         if pre is not None:
