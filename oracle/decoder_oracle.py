@@ -414,8 +414,74 @@ def _beam_search_one(sd, kind, state, logprobs, fc, att, p_att, masks, seq_lengt
 
 
 @torch.no_grad()
+def _diverse_beam_search_one(sd, kind, state, logprobs, fc, att, p_att, masks, seq_length, beam_size, group_size,
+                             diversity_lambda, decoding_constraint, max_ppl):
+    """models/CaptionModel.py:33-177 with group_size > 1 (diverse beam search): `group_size` groups of
+    bdash = beam_size // group_size beams advance staggered by one step each; group divm ranks its candidates with
+    diversity_lambda subtracted once per occurrence of a token among the tokens the groups before it hold at the same
+    local step (:36-45), and stores the unpenalised log-prob."""
+    G, T = group_size, seq_length
+    bdash = beam_size // G
+    seq_t = [torch.zeros(T, bdash, dtype=torch.int64) for _ in range(G)]          # :109-111
+    lp_t = [torch.zeros(T, bdash) for _ in range(G)]
+    sum_t = [torch.zeros(bdash) for _ in range(G)]
+    done_t = [[] for _ in range(G)]
+    state_t = [[s[:, g * bdash:(g + 1) * bdash].clone() for s in state] for g in range(G)]   # :115
+    logprobs_t = list(logprobs.chunk(G, 0))                                       # :116
+    feats = [[x[g * bdash:(g + 1) * bdash] if x is not None else None for x in (fc, att, p_att, masks)] for g in range(G)]
+    for t in range(T + G - 1):                                                    # :124
+        for divm in range(G):
+            lt = t - divm
+            if not (0 <= lt <= T - 1):                                            # :126
+                continue
+            lpf = logprobs_t[divm].float().clone()
+            if decoding_constraint and lt > 0:                                    # :130-131
+                lpf.scatter_(1, seq_t[divm][lt - 1].unsqueeze(1), float("-inf"))
+            lpf[:, -1] -= 1000.0                                                  # :133
+            unaug = lpf.clone()                                                   # :38
+            for prev in range(divm):                                              # :39-44
+                for tok in seq_t[prev][lt].tolist():
+                    lpf[:, tok] -= diversity_lambda
+            ys, ix = torch.sort(lpf, 1, True)                                     # :61
+            rows = 1 if lt == 0 else bdash
+            cands = []
+            for c in range(min(bdash, ys.size(1))):
+                for q in range(rows):
+                    cands.append((sum_t[divm][q] + ys[q, c].item(), int(ix[q, c]), q, unaug[q, ix[q, c]]))
+            cands.sort(key=lambda e: -e[0])
+            st = state_t[divm]
+            new_state = [x.clone() for x in st]
+            if lt >= 1:
+                prev_seq, prev_lp = seq_t[divm][:lt].clone(), lp_t[divm][:lt].clone()
+            for vix in range(bdash):
+                p, tok, q, r = cands[vix]
+                if lt >= 1:
+                    seq_t[divm][:lt, vix] = prev_seq[:, q]
+                    lp_t[divm][:lt, vix] = prev_lp[:, q]
+                for s_new, s_old in zip(new_state, st):
+                    s_new[:, vix] = s_old[:, q]
+                seq_t[divm][lt, vix] = tok
+                lp_t[divm][lt, vix] = r
+                sum_t[divm][vix] = p
+            state_t[divm] = new_state
+            for vix in range(bdash):                                              # :155-167
+                if int(seq_t[divm][lt, vix]) == 0 or lt == T - 1:
+                    p = sum_t[divm][vix].item()
+                    done_t[divm].append({"seq": seq_t[divm][:, vix].clone(), "logps": lp_t[divm][:, vix].clone(),
+                                         "unaug_p": lp_t[divm][:, vix].sum().item(),
+                                         "p": p / (lt + 1) if max_ppl else p})
+                    sum_t[divm][vix] = -1000
+            f = feats[divm]
+            logprobs_t[divm], state_t[divm] = logprobs_state(sd, kind, seq_t[divm][lt], f[0], f[1], f[2], f[3], state_t[divm])  # :171-172
+    out = []
+    for g in range(G):                                                            # :175-176
+        out += sorted(done_t[g], key=lambda d: -d["p"])[:bdash]
+    return out
+
+
+@torch.no_grad()
 def sample_beam(sd, kind, fc_feats, att_feats, seq_length, beam_size=10, att_masks=None,
-                decoding_constraint=0, max_ppl=0):
+                decoding_constraint=0, max_ppl=0, group_size=1, diversity_lambda=0.5):
     """Returns (seq (B,T) int64, seqLogprobs (B,T) fp32, done_beams list-of-lists)."""
     B = fc_feats.size(0)
     fc, att, p_att, masks = prepare_features(sd, kind, fc_feats, att_feats, att_masks)
@@ -432,8 +498,12 @@ def sample_beam(sd, kind, fc_feats, att_feats, seq_length, beam_size=10, att_mas
         m_k = masks[k:k + 1].expand(beam_size, masks.size(1)).contiguous() if masks is not None else None
         it = torch.zeros(beam_size, dtype=torch.int64)
         lp, state = logprobs_state(sd, kind, it, fc_k, att_k, p_att_k, m_k, state)   # :186-190
-        done = _beam_search_one(sd, kind, state, lp, fc_k, att_k, p_att_k, m_k, seq_length,
-                                beam_size, decoding_constraint, max_ppl)
+        if group_size > 1:
+            done = _diverse_beam_search_one(sd, kind, state, lp, fc_k, att_k, p_att_k, m_k, seq_length, beam_size, group_size,
+                                            diversity_lambda, decoding_constraint, max_ppl)
+        else:
+            done = _beam_search_one(sd, kind, state, lp, fc_k, att_k, p_att_k, m_k, seq_length,
+                                    beam_size, decoding_constraint, max_ppl)
         done_beams.append(done)
         seq[:, k] = done[0]["seq"]                                      # :193-194
         seq_lp[:, k] = done[0]["logps"]

@@ -43,3 +43,31 @@ def test_midsize_forward_loss_sampling(ref, kind, seed, use_masks):
             s, lp = O.sample(sd, kind, fc, att, 9, am, dict(o))
             assert torch.equal(s, rs), o
             torch.testing.assert_close(lp, rlp, rtol=1e-5, atol=2e-6)
+
+
+@pytest.mark.parametrize("kind", ["att2in2", "topdown"])
+@pytest.mark.parametrize("o", [{"beam_size": 6, "group_size": 3, "diversity_lambda": 0.5},
+                               {"beam_size": 4, "group_size": 2, "diversity_lambda": 2.0, "decoding_constraint": 1},
+                               {"beam_size": 6, "group_size": 2, "diversity_lambda": 0.7, "max_ppl": 1}])
+def test_diverse_beam_search(ref, kind, o):
+    """group_size > 1 (models/CaptionModel.py:36-45,124-172): sequences, log-probs and the per-group done lists."""
+    models, _ = ref
+    opt = synth.make_opt(caption_model=kind, vocab_size=299, rnn_size=64, input_encoding_size=48,
+                         att_hid_size=40, seq_length=9, fc_feat_size=96, att_feat_size=96)
+    sd = synth.init_state_dict(opt, seed=21, peaked=30.0, eos_bias=0.5)
+    model = models.setup(opt)
+    model.load_state_dict(sd)
+    model.eval()
+    fc, att = synth.make_features(5, 11, 96, seed=21)
+    with torch.no_grad():
+        rs, rlp = model(fc, None, att, None, opt=dict(o), mode="sample")
+    s, lp, done = O.sample_beam(sd, kind, fc, att, 9, o["beam_size"], None, o.get("decoding_constraint", 0), o.get("max_ppl", 0),
+                                o["group_size"], o["diversity_lambda"])
+    assert torch.equal(s, rs), o
+    torch.testing.assert_close(lp, rlp, rtol=1e-5, atol=2e-6)
+    for k in range(5):
+        ref_done = model.done_beams[k]
+        assert len(ref_done) == len(done[k])
+        for a, b in zip(ref_done, done[k]):
+            assert torch.equal(a["seq"], b["seq"])
+            assert abs(a["p"] - b["p"]) < 1e-4 * max(1.0, abs(a["p"]))
