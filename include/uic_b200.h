@@ -211,11 +211,21 @@ int uic_ss_advance(const float* stats, int parts, const int64_t* gt_tok, int64_t
 /* One beam-search bookkeeping step for all images at once (models/CaptionModel.py:48-97,155-172):
  * merges the beams x k candidates of each image (c-major, q-minor stable order), forks the
  * sequence tables, records finished hypotheses (token 0 or last step) into the sorted done lists,
- * and emits parent row + next token for every beam. */
-int uic_beam_step(const float* topk_val, const int32_t* topk_idx, int32_t* beam_seq, float* beam_lp, float* beam_sum,
+ * and emits parent row + next token for every beam.  topk_unaug (may be NULL = topk_val): the candidates'
+ * log-probs before the diversity penalty; they are what the log-prob tables store (:38,86) while topk_val ranks. */
+int uic_beam_step(const float* topk_val, const int32_t* topk_idx, const float* topk_unaug, int32_t* beam_seq, float* beam_lp, float* beam_sum,
                   int32_t* done_seq, float* done_lp, double* done_p, float* done_unaug, int32_t* done_cnt,
                   int32_t* parent_row, int64_t* next_tok, int t, int seq_length, int n_img, int beams, int flags,
                   void* stream);
+/* Diverse beam search (group_size > 1, models/CaptionModel.py:36-45 add_diversity): candidates of group `group` at
+ * its local step t.  cand_val / cand_idx: the n_cand >= beams + group * beams best edited log-probs per row
+ * (uic_row_topk with k = n_cand; a penalty only lowers values, so they contain the penalised top-`beams`).  Each
+ * candidate loses diversity_lambda once per occurrence of its token among beam_seq[g][image][*][t] of the groups
+ * g < group (tables laid out [group][image][beam][seq_length]).  Out: the `beams` best by (penalised value,
+ * smaller column) with the penalised (ranking) and unpenalised (stored) values, ready for uic_beam_step. */
+int uic_diverse_select(const float* cand_val, const int32_t* cand_idx, int n_cand, const int32_t* beam_seq, int group, int n_img,
+                       int beams, int seq_length, int t, float diversity_lambda, float* topk_val, float* topk_unaug,
+                       int32_t* topk_idx, void* stream);
 /* Re-order recurrent state by parent beam (CaptionModel.py:89-91): for two column ranges of the
  * bf16 activation matrix and `n_state` fp32 state matrices (rows x H each, contiguous). */
 int uic_beam_gather(const int32_t* parent_row, const void* x_src, void* x_dst, int64_t ld_x, int col0_a, int ncol_a,

@@ -389,7 +389,7 @@ def test_beam_advance_equals_the_four_step_chain(B, b, kslots):
         move = int(t + 1 < T)
         # unfused chain
         check(lib.uic_beam_topk_merge(ptr(stats), parts, kslots, ptr(tkv), ptr(tki), R, b, stream()))
-        check(lib.uic_beam_step(ptr(tkv), ptr(tki), ptr(u["beam_seq"]), ptr(u["beam_lp"]), ptr(u["beam_sum"]), ptr(u["done_seq"]),
+        check(lib.uic_beam_step(ptr(tkv), ptr(tki), None, ptr(u["beam_seq"]), ptr(u["beam_lp"]), ptr(u["beam_sum"]), ptr(u["done_seq"]),
                                 ptr(u["done_lp"]), ptr(u["done_p"]), ptr(u["done_unaug"]), ptr(u["done_cnt"]), ptr(u["parent"]),
                                 ptr(u["tok"]), t, T, B, b, 0, stream()))
         if move:
@@ -433,3 +433,30 @@ def test_greedy_advance_equals_merge_plus_embed():
         for x, y in zip(a, b):
             assert torch.equal(x, y)
     assert 0 < int(a[4][0]) < R
+
+
+@pytest.mark.parametrize("B,b,group,V", [(5, 2, 0, 50), (5, 2, 2, 50), (3, 4, 3, 40), (7, 1, 5, 30)])
+def test_diverse_select(B, b, group, V):
+    """uic_row_topk(k = b (group + 1)) + uic_diverse_select == sort of the fully penalised row (CaptionModel.py:36-45,61)."""
+    lib = _lib.load()
+    T, lt, lam = 6, 2, 0.75
+    g = torch.Generator().manual_seed(B * 100 + b * 10 + group)
+    R = B * b
+    logits = torch.randn(R, V, generator=g).cuda()
+    tables = torch.randint(0, 12, (group + 1, B, b, T), generator=g, dtype=torch.int32).cuda()   # few distinct tokens: repeats
+    kp = b * (group + 1)
+    cv, ci = torch.empty(R, kp, device=DEV), torch.empty(R, kp, dtype=torch.int32, device=DEV)
+    check(lib.uic_row_topk(ptr(logits), V, None, ptr(cv), ptr(ci), R, V, kp, 0, stream()))
+    tv, tu, ti = torch.empty(R, b, device=DEV), torch.empty(R, b, device=DEV), torch.empty(R, b, dtype=torch.int32, device=DEV)
+    check(lib.uic_diverse_select(ptr(cv), ptr(ci), kp, ptr(tables), group, B, b, T, lt, lam, ptr(tv), ptr(tu), ptr(ti), stream()))
+    lp = torch.log_softmax(logits.double(), 1).float().cpu()
+    lp[:, V - 1] -= 1000.0
+    aug = lp.clone()
+    for r in range(R):
+        for gg in range(group):
+            for j in range(b):
+                aug[r, int(tables[gg, r // b, j, lt])] -= lam
+    ys, ix = torch.sort(aug, dim=1, descending=True, stable=True)
+    assert torch.equal(ti.cpu().long(), ix[:, :b])
+    torch.testing.assert_close(tv.cpu(), ys[:, :b], rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(tu.cpu(), torch.gather(lp, 1, ix[:, :b]), rtol=1e-5, atol=1e-5)

@@ -118,6 +118,45 @@ def test_beam10_default_and_unfused_paths():
         torch.testing.assert_close(lp_f.cpu(), lp_p.cpu(), rtol=1e-4, atol=2e-4)
 
 
+@pytest.mark.parametrize("kind,beam,groups,lam,dc,ppl", [("att2in2", 6, 3, 0.5, 0, 0), ("topdown", 4, 2, 1.5, 1, 1),
+                                                          ("att2in2", 4, 4, 0.5, 0, 0)])
+def test_diverse_beam_search(kind, beam, groups, lam, dc, ppl):
+    """group_size > 1 (models/CaptionModel.py:36-45,100-177): groups run staggered, later groups are penalised for
+    repeating the earlier groups' tokens; done_beams is the groups' lists one after the other."""
+    opt, sd, model, fc, att, *_ = _case(kind, 5, 36, seed=7, peaked=40.0, eos_bias=2.0)
+    ref_seq, ref_lp, ref_done = O.sample_beam(sd, kind, fc, att, 16, beam, decoding_constraint=dc, max_ppl=ppl, group_size=groups,
+                                              diversity_lambda=lam)
+    o = {"beam_size": beam, "group_size": groups, "diversity_lambda": lam, "decoding_constraint": dc, "max_ppl": ppl}
+    seq, lp = model(fc.cuda(), None, att.cuda(), None, opt=o, mode="sample")
+    rows = (seq == ref_seq).all(1)
+    if beam == groups:
+        # one beam per group: the first group IS greedy decoding, which cannot recover from a flipped near-tie the way a wider
+        # beam does -- exempt near-ties like the greedy test, and require identity with the device's own greedy path
+        g_ref, _, margins = O.sample_greedy(sd, kind, fc, att, 16, return_margins=True)
+        assert torch.equal(g_ref, ref_seq)
+        exact, exempt, failures = compare_greedy(seq.cpu(), ref_seq, margins, tol=2e-2)
+        assert not failures, failures
+        g_seq, _ = model(fc.cuda(), None, att.cuda(), None, opt={"beam_size": 1}, mode="sample")
+        assert torch.equal(g_seq.cpu(), seq.cpu())
+    else:
+        assert float(rows.float().mean()) >= 0.8, (seq, ref_seq)
+    torch.testing.assert_close(lp[rows], ref_lp[rows], rtol=2e-2, atol=2e-2)
+    same = total = 0
+    for k in range(5):
+        mine, ref = model.done_beams[k], ref_done[k]
+        assert len(mine) == len(ref)
+        for a, b in zip(mine, ref):
+            total += 1
+            if torch.equal(a["seq"], b["seq"]):
+                same += 1
+                assert abs(a["p"] - float(b["p"])) <= 2e-2 * max(1.0, abs(float(b["p"])))
+                assert abs(a["unaug_p"] - float(b["unaug_p"])) <= 2e-2 * max(1.0, abs(float(b["unaug_p"])))
+    assert same >= (0.5 if beam == groups else 0.7) * total, (same, total)
+    # a replay of the captured loop gives the same tables
+    seq2, lp2 = model(fc.cuda(), None, att.cuda(), None, opt=o, mode="sample")
+    assert torch.equal(seq, seq2) and torch.equal(lp, lp2)
+
+
 def test_decode_graph_cache_is_bounded():
     """Masked batches are clipped to their longest region count (AttModel.py:99-105), so every new length is a new decode
     graph with its own static tile buffers: the engine keeps only the most recently used few."""

@@ -439,7 +439,20 @@ int uic_dropout(void* x, int is_bf16, int64_t ld, int64_t rows, int cols, float 
   return dropout(x, is_bf16, ld, rows, cols, p, reinterpret_cast<const unsigned long long*>(seed), site, row0, row_stride, ST(stream));
 }
 
-int uic_beam_step(const float* topk_val, const int32_t* topk_idx, int32_t* beam_seq, float* beam_lp, float* beam_sum,
+int uic_diverse_select(const float* cand_val, const int32_t* cand_idx, int n_cand, const int32_t* beam_seq, int group, int n_img,
+                       int beams, int seq_length, int t, float diversity_lambda, float* topk_val, float* topk_unaug,
+                       int32_t* topk_idx, void* stream) {
+  REQUIRE(cand_val && cand_idx && topk_val && topk_unaug && topk_idx, UIC_ERR_ARG, "uic_diverse_select: null pointer");
+  REQUIRE(group == 0 || beam_seq, UIC_ERR_ARG, "uic_diverse_select: group %d needs the sequence tables of the earlier groups", group);
+  REQUIRE(beams >= 1 && beams <= 16 && n_cand >= beams && n_cand <= 16, UIC_ERR_SHAPE,
+          "uic_diverse_select: beams=%d candidates=%d (1 <= beams <= candidates <= 16)", beams, n_cand);
+  REQUIRE(group >= 0 && t >= 0 && t < seq_length, UIC_ERR_SHAPE, "uic_diverse_select: group=%d t=%d seq_length=%d", group, t, seq_length);
+  if (n_img == 0) return 0;
+  return diverse_select(cand_val, cand_idx, n_cand, beam_seq, group, n_img, beams, seq_length, t, diversity_lambda, topk_val, topk_unaug,
+                        topk_idx, ST(stream));
+}
+
+int uic_beam_step(const float* topk_val, const int32_t* topk_idx, const float* topk_unaug, int32_t* beam_seq, float* beam_lp, float* beam_sum,
                   int32_t* done_seq, float* done_lp, double* done_p, float* done_unaug, int32_t* done_cnt, int32_t* parent_row,
                   int64_t* next_tok, int t, int seq_length, int n_img, int beams, int flags, void* stream) {
   REQUIRE(topk_val && topk_idx && beam_seq && beam_lp && beam_sum && done_seq && done_lp && done_p && done_unaug && done_cnt &&
@@ -448,7 +461,7 @@ int uic_beam_step(const float* topk_val, const int32_t* topk_idx, int32_t* beam_
   REQUIRE(beams >= 1 && beams <= 16, UIC_ERR_SHAPE, "uic_beam_step: beams=%d must be in [1,16]", beams);
   REQUIRE(t >= 0 && t < seq_length && seq_length <= 64, UIC_ERR_SHAPE, "uic_beam_step: t=%d seq_length=%d (max 64)", t, seq_length);
   if (n_img == 0) return 0;
-  return beam_step(topk_val, topk_idx, beam_seq, beam_lp, beam_sum, done_seq, done_lp, done_p, done_unaug, done_cnt, parent_row,
+  return beam_step(topk_val, topk_idx, topk_unaug, beam_seq, beam_lp, beam_sum, done_seq, done_lp, done_p, done_unaug, done_cnt, parent_row,
                    next_tok, t, seq_length, n_img, beams, flags, ST(stream));
 }
 

@@ -24,7 +24,7 @@ constexpr int BEAM_T_MAX = 64;
 constexpr int CAND_PER_LANE = BEAM_MAX * BEAM_MAX / 32;
 
 // One image, one warp.  tkv / tki: the image's (beams x beams) candidate tables [q * b + c] (global or shared).
-__device__ __forceinline__ void beam_step_image(const float* tkv, const int32_t* tki, int32_t* __restrict__ beam_seq,
+__device__ __forceinline__ void beam_step_image(const float* tkv, const int32_t* tki, const float* tku, int32_t* __restrict__ beam_seq,
                                                 float* __restrict__ beam_lp, float* __restrict__ beam_sum,
                                                 int32_t* __restrict__ done_seq, float* __restrict__ done_lp,
                                                 double* __restrict__ done_p, float* __restrict__ done_unaug,
@@ -84,7 +84,7 @@ __device__ __forceinline__ void beam_step_image(const float* tkv, const int32_t*
       s_q[vix] = q;
       s_p[vix] = bv;
       s_tok[vix] = tki[q * b + c];
-      s_r[vix] = tkv[q * b + c];
+      s_r[vix] = tku != nullptr ? tku[q * b + c] : tkv[q * b + c];  // stored log-prob: without the diversity penalty (:38,86)
     }
   }
   // ---- fork the tables: stage the old prefixes, then write parents' prefixes + the new token ----
@@ -153,6 +153,7 @@ __device__ __forceinline__ void beam_step_image(const float* tkv, const int32_t*
 }
 
 __global__ void __launch_bounds__(32) beam_step_kernel(const float* __restrict__ topk_val, const int32_t* __restrict__ topk_idx,
+                                                       const float* __restrict__ topk_unaug,
                                                        int32_t* __restrict__ beam_seq, float* __restrict__ beam_lp,
                                                        float* __restrict__ beam_sum, int32_t* __restrict__ done_seq,
                                                        float* __restrict__ done_lp, double* __restrict__ done_p,
@@ -160,18 +161,78 @@ __global__ void __launch_bounds__(32) beam_step_kernel(const float* __restrict__
                                                        int32_t* __restrict__ parent_row, int64_t* __restrict__ next_tok, int t,
                                                        int T, int b, int flags) {
   const long long off = static_cast<long long>(blockIdx.x) * b * b;
-  beam_step_image(topk_val + off, topk_idx + off, beam_seq, beam_lp, beam_sum, done_seq, done_lp, done_p, done_unaug, done_cnt,
+  beam_step_image(topk_val + off, topk_idx + off, topk_unaug != nullptr ? topk_unaug + off : nullptr, beam_seq, beam_lp, beam_sum, done_seq, done_lp, done_p, done_unaug, done_cnt,
                   parent_row, next_tok, blockIdx.x, t, T, b, flags);
 }
 
-int beam_step(const float* topk_val, const int32_t* topk_idx, int32_t* beam_seq, float* beam_lp, float* beam_sum,
+int beam_step(const float* topk_val, const int32_t* topk_idx, const float* topk_unaug, int32_t* beam_seq, float* beam_lp, float* beam_sum,
               int32_t* done_seq, float* done_lp, double* done_p, float* done_unaug, int32_t* done_cnt, int32_t* parent_row,
               int64_t* next_tok, int t, int seq_length, int n_img, int beams, int flags, cudaStream_t stream) {
   if (beams > BEAM_MAX || seq_length > BEAM_T_MAX)
     return set_error(UIC_ERR_SHAPE, "beam_step: beams=%d (max %d), seq_length=%d (max %d)", beams, BEAM_MAX, seq_length, BEAM_T_MAX);
   launch_begin("beam_step", stream);
-  beam_step_kernel<<<n_img, 32, 0, stream>>>(topk_val, topk_idx, beam_seq, beam_lp, beam_sum, done_seq, done_lp, done_p,
+  beam_step_kernel<<<n_img, 32, 0, stream>>>(topk_val, topk_idx, topk_unaug, beam_seq, beam_lp, beam_sum, done_seq, done_lp, done_p,
                                              done_unaug, done_cnt, parent_row, next_tok, t, seq_length, beams, flags);
+  UIC_CUDA_OK(cudaGetLastError());
+  launch_end(stream);
+  return 0;
+}
+
+// ---- diverse beam search: candidates of one group after the diversity penalty (models/CaptionModel.py:36-45) ----------
+// Input: per row the K' = k + n_prev best (edited) log-probs and their columns (uic_row_topk with k = K'), enough to
+// contain the penalised top-k (a penalty only lowers values).  Every candidate loses `lambda` once per occurrence of its
+// token among the tokens that the groups before this one hold at local step `lt` (tables beam_seq [group][image][beam][T]);
+// the k best by (penalised value, smaller column) come out with both the penalised and the unpenalised value.
+__global__ void __launch_bounds__(128) diverse_select_kernel(const float* __restrict__ cand_val, const int32_t* __restrict__ cand_idx,
+                                                              int kp, const int32_t* __restrict__ beam_seq, int group, int n_img,
+                                                              int bdash, int T, int lt, float lambda, float* __restrict__ topk_val,
+                                                              float* __restrict__ topk_unaug, int32_t* __restrict__ topk_idx,
+                                                              int rows) {
+  const int r = blockIdx.x * 4 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (r >= rows) return;
+  const int img = r / bdash;
+  float un = -INFINITY, aug = -INFINITY;
+  int col = 0x7fffffff;
+  if (lane < kp) {
+    un = cand_val[static_cast<long long>(r) * kp + lane];
+    col = cand_idx[static_cast<long long>(r) * kp + lane];
+    int hits = 0;
+    for (int g = 0; g < group; ++g)
+      for (int j = 0; j < bdash; ++j)
+        hits += beam_seq[((static_cast<long long>(g) * n_img + img) * bdash + j) * T + lt] == col;
+    aug = un - lambda * static_cast<float>(hits);
+  }
+  bool taken = lane >= kp;
+  for (int round = 0; round < bdash; ++round) {
+    float bv = taken ? -INFINITY : aug;
+    int bi = taken ? 0x7fffffff : col, bl = taken ? 32 : lane;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, bi, o), ol = __shfl_xor_sync(0xffffffffu, bl, o);
+      if (ol < 32 && (bl == 32 || ov > bv || (ov == bv && oi < bi))) {
+        bv = ov;
+        bi = oi;
+        bl = ol;
+      }
+    }
+    const float bu = __shfl_sync(0xffffffffu, un, bl & 31);
+    if (lane == 0) {
+      topk_val[static_cast<long long>(r) * bdash + round] = bv;
+      topk_unaug[static_cast<long long>(r) * bdash + round] = bu;
+      topk_idx[static_cast<long long>(r) * bdash + round] = bi;
+    }
+    if (lane == bl) taken = true;
+  }
+}
+
+int diverse_select(const float* cand_val, const int32_t* cand_idx, int kp, const int32_t* beam_seq, int group, int n_img, int bdash,
+                   int T, int lt, float lambda, float* topk_val, float* topk_unaug, int32_t* topk_idx, cudaStream_t stream) {
+  if (kp > 32 || kp < bdash) return set_error(UIC_ERR_SHAPE, "diverse_select: %d candidates for %d beams (max 32)", kp, bdash);
+  const int rows = n_img * bdash;
+  launch_begin("diverse_select", stream);
+  diverse_select_kernel<<<(rows + 3) / 4, 128, 0, stream>>>(cand_val, cand_idx, kp, beam_seq, group, n_img, bdash, T, lt, lambda, topk_val,
+                                                           topk_unaug, topk_idx, rows);
   UIC_CUDA_OK(cudaGetLastError());
   launch_end(stream);
   return 0;
@@ -259,7 +320,7 @@ __global__ void __launch_bounds__(ADV_THREADS) beam_advance_kernel(const float* 
   ADV_TRACE(111);
   // 2. beam bookkeeping
   if (warp == 0)
-    beam_step_image(s_tkv, s_tki, beam_seq, beam_lp, beam_sum, done_seq, done_lp, done_p, done_unaug, done_cnt, parent_row,
+    beam_step_image(s_tkv, s_tki, nullptr, beam_seq, beam_lp, beam_sum, done_seq, done_lp, done_p, done_unaug, done_cnt, parent_row,
                     next_tok, img, t, T, b, flags);
   if (!move_state) return;
   __syncthreads();

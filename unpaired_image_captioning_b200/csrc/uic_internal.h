@@ -92,7 +92,9 @@ int greedy_step(const float* logits, long long ld, int64_t* seq, float* seq_lp, 
                 int32_t* n_unfinished, int t, int seq_length, int rows, int V, int flags, cudaStream_t stream);
 int row_topk(const float* logits, long long ld, const int64_t* prev_tok, float* topk_val, int32_t* topk_idx, int rows, int V,
              int k, int flags, cudaStream_t stream);
-int beam_step(const float* topk_val, const int32_t* topk_idx, int32_t* beam_seq, float* beam_lp, float* beam_sum,
+int diverse_select(const float* cand_val, const int32_t* cand_idx, int kp, const int32_t* beam_seq, int group, int n_img, int bdash,
+                   int T, int lt, float lambda, float* topk_val, float* topk_unaug, int32_t* topk_idx, cudaStream_t stream);
+int beam_step(const float* topk_val, const int32_t* topk_idx, const float* topk_unaug, int32_t* beam_seq, float* beam_lp, float* beam_sum,
               int32_t* done_seq, float* done_lp, double* done_p, float* done_unaug, int32_t* done_cnt, int32_t* parent_row,
               int64_t* next_tok, int t, int seq_length, int n_img, int beams, int flags, cudaStream_t stream);
 int beam_advance(const float* stats, int parts, int kslots, int32_t* beam_seq, float* beam_lp, float* beam_sum, int32_t* done_seq,

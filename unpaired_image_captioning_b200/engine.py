@@ -428,13 +428,89 @@ class DecoderEngine:
                     self.logits_of(h, ws["logits"])
                     check(lib.uic_row_topk(ptr(ws["logits"]), w.V, ptr(s["tok"]) if (tk_flags and t > 0) else None, ptr(s["tk_val"]),
                                            ptr(s["tk_idx"]), R, w.V, b, tk_flags if t > 0 else 0, stream()))
-                check(lib.uic_beam_step(ptr(s["tk_val"]), ptr(s["tk_idx"]), ptr(s["beam_seq"]), ptr(s["beam_lp"]), ptr(s["beam_sum"]),
+                check(lib.uic_beam_step(ptr(s["tk_val"]), ptr(s["tk_idx"]), None, ptr(s["beam_seq"]), ptr(s["beam_lp"]), ptr(s["beam_sum"]),
                                         ptr(s["done_seq"]), ptr(s["done_lp"]), ptr(s["done_p"]), ptr(s["done_unaug"]),
                                         ptr(s["done_cnt"]), ptr(s["parent"]), ptr(s["tok"]), t, T, B, b, bs_flags, stream()))
                 if t + 1 < T:  # the reference's last get_logprobs_state (CaptionModel.py:171-172) has no observable effect
                     check(lib.uic_beam_gather(ptr(s["parent"]), ptr(X), ptr(Xn), X.stride(0), ga, na, gb, nb, ptr(c), ptr(cn),
                                               sl.n_state, R, w.H, stream()))
                     self._embed(s["tok"], Xn, sl)
+            return s["done_seq"], s["done_lp"], s["done_p"], s["done_unaug"], s["done_cnt"]
+
+        return self._decode(key, alloc, run, feats)
+
+    # ---- diverse beam search (group_size > 1, models/CaptionModel.py:33-177 with add_diversity :36-45) ----------
+    def beam_diverse(self, feats, seq_length, beam_size, group_size, diversity_lambda=0.5, decoding_constraint=0, max_ppl=0):
+        """`group_size` groups of beam_size // group_size beams; group g runs one step behind group g - 1 and its
+        candidates lose diversity_lambda per occurrence of their token among the earlier groups' choices at the same
+        local step.  Every table has a leading group axis; returns (done_seq, done_lp, done_p, done_unaug, done_cnt)
+        shaped (G, B, b', ...)."""
+        w, lib = self.w, self.lib
+        B, dev, T, G = feats.B, feats.device, seq_length, group_size
+        if G < 1 or beam_size % G != 0:
+            raise ValueError(f"beam_size={beam_size} must be a multiple of group_size={G}")
+        b = beam_size // G
+        R = B * b
+        tk_flags = _lib.SAMPLE_DECODING_CONSTRAINT if decoding_constraint else 0
+        bs_flags = _lib.BEAM_MAX_PPL if max_ppl else 0
+        key = ("beam_diverse", B, b, G, float(diversity_lambda), feats.L, T, tk_flags, bs_flags, feats.masks is not None)
+
+        def alloc():
+            s = {**self._feature_buffers(feats),
+                 "ws": self._workspace(R, dev),
+                 "cand_val": torch.empty(R, beam_size, device=dev), "cand_idx": torch.empty(R, beam_size, dtype=torch.int32, device=dev),
+                 "tk_val": torch.empty(R, b, device=dev), "tk_un": torch.empty(R, b, device=dev),
+                 "tk_idx": torch.empty(R, b, dtype=torch.int32, device=dev),
+                 "beam_seq": torch.zeros(G, B, b, T, dtype=torch.int32, device=dev), "beam_lp": torch.zeros(G, B, b, T, device=dev),
+                 "beam_sum": torch.zeros(G, B, b, device=dev),
+                 "done_seq": torch.zeros(G, B, b, T, dtype=torch.int32, device=dev), "done_lp": torch.zeros(G, B, b, T, device=dev),
+                 "done_p": torch.zeros(G, B, b, dtype=torch.float64, device=dev), "done_unaug": torch.zeros(G, B, b, device=dev),
+                 "done_cnt": torch.zeros(G, B, dtype=torch.int32, device=dev),
+                 "parent": torch.zeros(R, dtype=torch.int32, device=dev), "tok": torch.zeros(G, R, dtype=torch.int64, device=dev)}
+            s["feats"] = Features(s["att"], s["p_att"], s["fc"], s["masks"], B, feats.L)
+            s["state"] = []
+            for _ in range(G):
+                X, c, sl = self._new_state(R, dev, s["feats"], b)
+                s["state"].append([(X, c), (torch.zeros_like(X), torch.zeros_like(c))])
+                s["sl"] = sl
+            s["img_idx"] = torch.arange(R, device=dev, dtype=torch.int64) // b
+            return s
+
+        def run(s):
+            f, ws, sl = s["feats"], s["ws"], s["sl"]
+            for k in ("beam_seq", "beam_lp", "beam_sum", "done_seq", "done_lp", "done_p", "done_unaug", "done_cnt", "tok"):
+                s[k].zero_()
+            for g in range(G):
+                for X, c in s["state"][g]:
+                    X.zero_()
+                    c.zero_()
+                    if self.kind == "topdown":
+                        check(lib.uic_embed_rows(ptr(f.fc), w.H, ptr(s["img_idx"]), ptr(X[:, sl.fc[0]:]), X.stride(0), R, w.H, B, stream()))
+                self._embed(s["tok"][g], s["state"][g][0][0], sl)   # BOS (AttModel.py:186-190)
+            (ga, na), (gb, nb) = sl.gather
+            for t in range(T + G - 1):
+                for g in range(G):
+                    lt = t - g                                      # the group's own clock (CaptionModel.py:122-124)
+                    if lt < 0 or lt >= T:
+                        continue
+                    X, c = s["state"][g][lt % 2]
+                    Xn, cn = s["state"][g][(lt + 1) % 2]
+                    tok = s["tok"][g]
+                    h = self.core_step(X, c, f, ws, beams=b)
+                    self.logits_of(h, ws["logits"])
+                    kp = b * (g + 1)                                # enough to survive the penalties on <= g * b tokens
+                    check(lib.uic_row_topk(ptr(ws["logits"]), w.V, ptr(tok) if (tk_flags and lt > 0) else None, ptr(s["cand_val"]),
+                                           ptr(s["cand_idx"]), R, w.V, kp, tk_flags if lt > 0 else 0, stream()))
+                    check(lib.uic_diverse_select(ptr(s["cand_val"]), ptr(s["cand_idx"]), kp, ptr(s["beam_seq"]), g, B, b, T, lt,
+                                                 float(diversity_lambda), ptr(s["tk_val"]), ptr(s["tk_un"]), ptr(s["tk_idx"]), stream()))
+                    check(lib.uic_beam_step(ptr(s["tk_val"]), ptr(s["tk_idx"]), ptr(s["tk_un"]), ptr(s["beam_seq"][g]),
+                                            ptr(s["beam_lp"][g]), ptr(s["beam_sum"][g]), ptr(s["done_seq"][g]), ptr(s["done_lp"][g]),
+                                            ptr(s["done_p"][g]), ptr(s["done_unaug"][g]), ptr(s["done_cnt"][g]), ptr(s["parent"]),
+                                            ptr(tok), lt, T, B, b, bs_flags, stream()))
+                    if lt + 1 < T:
+                        check(lib.uic_beam_gather(ptr(s["parent"]), ptr(X), ptr(Xn), X.stride(0), ga, na, gb, nb, ptr(c), ptr(cn),
+                                                  sl.n_state, R, w.H, stream()))
+                        self._embed(tok, Xn, sl)
             return s["done_seq"], s["done_lp"], s["done_p"], s["done_unaug"], s["done_cnt"]
 
         return self._decode(key, alloc, run, feats)

@@ -296,11 +296,17 @@ class AttModel(CaptionModel):
     def _sample_beam(self, fc_feats, att_feats, att_masks=None, opt={}):
         """models/AttModel.py:167-196; every image of the batch is searched at once on the device."""
         beam_size = opt.get("beam_size", 10)
-        if opt.get("group_size", 1) != 1:
-            raise NotImplementedError("diverse beam search (group_size > 1) is not on the B200 hot path yet")
+        group_size = opt.get("group_size", 1)
         assert beam_size <= self.vocab_size + 1, "lets assume this for now, otherwise this corner case causes a few headaches down the road. can be dealt with in future if needed"
         eng = self.engine
         feats = eng.prepare(fc_feats, att_feats, att_masks, lazy=True)
+        if group_size > 1:   # diverse beam search: tables carry a leading group axis (CaptionModel.py:100-177)
+            tables = eng.beam_diverse(feats, self.seq_length, beam_size, group_size, opt.get("diversity_lambda", 0.5),
+                                      opt.get("decoding_constraint", 0), opt.get("max_ppl", 0))
+            done_seq_c, done_lp_c = tables[0].long().cpu(), tables[1].cpu()
+            self._done_tables = (done_seq_c, done_lp_c, tables[2].cpu(), tables[3].cpu(), tables[4].cpu())
+            self.done_beams = _LazyDoneBeams(self._done_tables)
+            return done_seq_c[0, :, 0].contiguous(), done_lp_c[0, :, 0].contiguous()   # best of the first group (:194-195)
         done_seq, done_lp, done_p, done_unaug, done_cnt = eng.beam(
             feats, self.seq_length, beam_size, opt.get("decoding_constraint", 0), opt.get("max_ppl", 0))
         # one D2H for everything the reference keeps on the CPU (seq, seqLogprobs, done_beams)
@@ -359,10 +365,12 @@ class _LazyDoneBeams:
         self._t = tables
 
     def __len__(self):
-        return self._t[0].size(0)
+        return self._t[0].size(-3)
 
     def __getitem__(self, k):
         seq, lp, p, unaug, cnt = self._t
+        if seq.dim() == 4:   # diverse beam search: the groups' lists one after the other (CaptionModel.py:176)
+            return [e for g in range(seq.size(0)) for e in _LazyDoneBeams((seq[g], lp[g], p[g], unaug[g], cnt[g]))[k]]
         return [{"seq": seq[k, j].clone(), "logps": lp[k, j].clone(), "unaug_p": float(unaug[k, j]), "p": float(p[k, j])}
                 for j in range(int(cnt[k]))]
 
