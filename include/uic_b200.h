@@ -124,7 +124,8 @@ int64_t uic_att_step_workspace_bytes(int n_img, int beams, int L, int A, int H);
  * a2c = a2c(ctx) (rows x 2H, pitch ld_a2c); i,f,o = sigmoid(sums[:, :3H]);
  * g = max(sums[:,3H:4H]+a2c[:, :H], sums[:,4H:]+a2c[:,H:]); c = f*c_prev + i*g; h = o*tanh(c).
  * h is written as fp32 (optional) and as bf16 to up to two destinations (next step's GEMM operand
- * slots).  c_prev == NULL means zero state. */
+ * slots).  c_prev == NULL means zero state.  a2c == NULL: no separate context term -- Att2all2Core
+ * (models/AttModel.py:618-654) adds a2h(ctx) to all five gate sums, which its GEMM accumulates into `sums`. */
 int uic_lstm_maxout_fwd(const float* sums, int64_t ld_sums, const float* a2c, int64_t ld_a2c, const float* c_prev,
                         float* c_out, float* h_f32, void* h_bf16_a, int64_t ld_ha, void* h_bf16_b, int64_t ld_hb, int rows,
                         int H, void* stream);
@@ -240,7 +241,7 @@ int uic_lstm_cell_bwd(const float* gates, int64_t ld_gates, const float* c_prev,
                       const float* dh1, int64_t ld1, const float* dh2, int64_t ld2, const float* dc_next, void* dgates_bf16,
                       int64_t ld_dg, float* dc_prev, int rows, int H, void* stream);
 /* Att2in2 maxout cell backward (models/AttModel.py:585-597): writes d sums (rows x 5H, bf16),
- * d a2c (rows x 2H, bf16) and dc_prev. */
+ * d a2c (rows x 2H, bf16; a2c and da2c_bf16 both NULL for the att2all2 cell) and dc_prev. */
 int uic_lstm_maxout_bwd(const float* sums, int64_t ld_sums, const float* a2c, int64_t ld_a2c, const float* c_prev, const float* c,
                         const float* dh0, int64_t ld0, const float* dh1, int64_t ld1, const float* dc_next, void* dsums_bf16,
                         int64_t ld_ds, void* da2c_bf16, int64_t ld_da, float* dc_prev, int rows, int H, void* stream);

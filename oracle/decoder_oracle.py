@@ -25,7 +25,7 @@ import numpy as np
 import torch
 import torch.nn.functional as F
 
-KINDS = ("att2in2", "topdown")
+KINDS = ("att2in2", "att2all2", "topdown")
 
 
 def num_layers(kind):
@@ -128,6 +128,20 @@ def core_att2in2(sd, xt, fc, att, p_att, state, att_masks=None):
     return h, (h[None], c[None])                                        # :599-601 (dropout p=0)
 
 
+def core_att2all2(sd, xt, fc, att, p_att, state, att_masks=None):
+    """models/AttModel.py:636-654 -- maxout LSTM whose five gate sums all receive the attended context."""
+    h_prev, c_prev = state[0][-1], state[1][-1]
+    H = h_prev.size(1)
+    ctx = attention(sd, h_prev, att, p_att, att_masks)                  # :637
+    sums = _linear(sd, "core.i2h", xt) + _linear(sd, "core.h2h", h_prev) + _linear(sd, "core.a2h", ctx)   # :639
+    sig = torch.sigmoid(sums[:, :3 * H])                                # :640-644
+    i_g, f_g, o_g = sig[:, :H], sig[:, H:2 * H], sig[:, 2 * H:]
+    g = torch.maximum(sums[:, 3 * H:4 * H], sums[:, 4 * H:])            # :646-647
+    c = f_g * c_prev + i_g * g                                          # :648
+    h = o_g * torch.tanh(c)                                             # :649
+    return h, (h[None], c[None])                                        # :651-653 (dropout p=0)
+
+
 def core_topdown(sd, xt, fc, att, p_att, state, att_masks=None):
     """models/AttModel.py:430-446 -- attention LSTM + language LSTM."""
     h_lang_prev = state[0][-1]
@@ -139,7 +153,7 @@ def core_topdown(sd, xt, fc, att, p_att, state, att_masks=None):
     return h_lang, (torch.stack([h_att, h_lang]), torch.stack([c_att, c_lang]))   # :443-446
 
 
-CORES = {"att2in2": core_att2in2, "topdown": core_topdown}
+CORES = {"att2in2": core_att2in2, "att2all2": core_att2all2, "topdown": core_topdown}
 
 
 def init_hidden(sd, kind, rows):

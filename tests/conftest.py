@@ -10,7 +10,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
-GOLDEN_CASES = ["att2in2_plain", "att2in2_peaked", "att2in2_masked",
+GOLDEN_CASES = ["att2in2_plain", "att2in2_peaked", "att2in2_masked", "att2all2_peaked",
                 "topdown_plain", "topdown_peaked", "topdown_masked"]
 
 

@@ -2,7 +2,7 @@
 
 Run in the build container only (needs /root/reference):
 
-    python tests/golden/make_golden.py
+    python tests/golden/make_golden.py [case ...]
 
 For each case it builds the reference model with `models.setup(opt)`, loads a seeded state_dict,
 feeds seeded synthetic inputs through the reference's public API (the call patterns of
@@ -32,6 +32,7 @@ CASES = {
     "att2in2_plain": ("tiny_att2in2", 1234, dict(), False),
     "att2in2_peaked": ("tiny_att2in2", 1238, dict(peaked=80.0, eos_bias=1.0), False),
     "att2in2_masked": ("tiny_att2in2", 1238, dict(peaked=80.0, eos_bias=1.0), True),
+    "att2all2_peaked": ("tiny_att2all2", 1238, dict(peaked=80.0, eos_bias=1.0), False),
     "topdown_plain": ("tiny_topdown", 1234, dict(), False),
     "topdown_peaked": ("tiny_topdown", 1237, dict(peaked=80.0, eos_bias=0.0), False),
     "topdown_masked": ("tiny_topdown", 1237, dict(peaked=80.0, eos_bias=0.0), True),
@@ -100,7 +101,10 @@ def run_case(models, criterion, name, cfg_name, seed, variant, use_masks):
 def main():
     models, criterion = reference_shim.load()
     torch.set_num_threads(1)
+    only = sys.argv[1:]          # optional: case names to (re)generate; default all
     for name, (cfg_name, seed, variant, use_masks) in CASES.items():
+        if only and name not in only:
+            continue
         run_case(models, criterion, name, cfg_name, seed, variant, use_masks)
 
 

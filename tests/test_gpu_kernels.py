@@ -176,6 +176,12 @@ def test_lstm_maxout_and_cell_fwd(R, H):
     torch.testing.assert_close(X[:, H:2 * H].float(), h_ref, rtol=1e-2, atol=1e-2)
     assert torch.equal(X[:, H:2 * H], X[:, 2 * H:]) and float(X[:, :H].abs().max()) == 0.0
 
+    # att2all2 form: no separate context addend (models/AttModel.py:639-648)
+    check(lib.uic_lstm_maxout_fwd(ptr(sums), 5 * H, None, 0, ptr(c_prev), ptr(c_out), ptr(h_f), None, 0, None, 0, R, H, stream()))
+    c_all = sig[:, H:2 * H] * c_prev + sig[:, :H] * torch.maximum(sums[:, 3 * H:4 * H], sums[:, 4 * H:])
+    torch.testing.assert_close(c_out, c_all, rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(h_f, sig[:, 2 * H:] * torch.tanh(c_all), rtol=1e-5, atol=1e-5)
+
     gates = torch.randn(R, 4 * H, device=DEV)
     check(lib.uic_lstm_cell_fwd(ptr(gates), 4 * H, ptr(c_prev), ptr(c_out), ptr(h_f), None, 0, None, 0, R, H, stream()))
     i, f, g, o = gates.chunk(4, 1)

@@ -25,7 +25,7 @@ def _case(kind, B, L, seed, peaked=0.0, eos_bias=0.0, masks=False):
     return opt, sd, model.cuda().eval(), fc, att, labels, lmasks, am
 
 
-@pytest.mark.parametrize("kind,L,masks", [("att2in2", 196, False), ("topdown", 36, False), ("topdown", 36, True)])
+@pytest.mark.parametrize("kind,L,masks", [("att2in2", 196, False), ("att2all2", 100, True), ("topdown", 36, False), ("topdown", 36, True)])
 def test_teacher_forced_and_loss(kind, L, masks):
     opt, sd, model, fc, att, labels, lmasks, am = _case(kind, 8, L, seed=1234, masks=masks)
     ref = O.teacher_forced(sd, kind, fc, att, labels, am)
@@ -40,7 +40,7 @@ def test_teacher_forced_and_loss(kind, L, masks):
     assert abs(float(loss) - float(ref_loss)) < REL * float(ref_loss)
 
 
-@pytest.mark.parametrize("kind,L", [("att2in2", 196), ("topdown", 36)])
+@pytest.mark.parametrize("kind,L", [("att2in2", 196), ("att2all2", 64), ("topdown", 36)])
 def test_greedy_with_margin_exemption(kind, L):
     opt, sd, model, fc, att, *_ = _case(kind, 16, L, seed=77)
     ref_seq, ref_lp, margins = O.sample_greedy(sd, kind, fc, att, 16, return_margins=True)
@@ -52,7 +52,7 @@ def test_greedy_with_margin_exemption(kind, L):
     torch.testing.assert_close(lp.cpu()[first], ref_lp[first], rtol=REL, atol=REL * 10)
 
 
-@pytest.mark.parametrize("kind,L,beam", [("att2in2", 196, 3), ("topdown", 36, 3), ("att2in2", 49, 5)])
+@pytest.mark.parametrize("kind,L,beam", [("att2in2", 196, 3), ("topdown", 36, 3), ("att2in2", 49, 5), ("att2all2", 49, 3)])
 def test_beam_peaked_exact(kind, L, beam):
     """Wide-margin variant (scaled logit weights, raised EOS bias): ids must be identical."""
     opt, sd, model, fc, att, *_ = _case(kind, 6, L, seed=5, peaked=40.0, eos_bias=2.0)

@@ -62,7 +62,7 @@ def test_gradients_match_reference_autograd(golden, mode):
     assert not bad, bad
 
 
-@pytest.mark.parametrize("kind,L,B", [("att2in2", 49, 6), ("topdown", 36, 8)])
+@pytest.mark.parametrize("kind,L,B", [("att2in2", 49, 6), ("att2all2", 49, 6), ("topdown", 36, 8)])
 def test_gradients_match_oracle_at_real_widths(kind, L, B):
     opt = synth.make_opt(caption_model=kind, vocab_size=9999, rnn_size=512, input_encoding_size=512, att_hid_size=512, seq_length=16)
     sd = synth.init_state_dict(opt, seed=3)

@@ -15,7 +15,7 @@ def ref():
     return reference_shim.load()
 
 
-@pytest.mark.parametrize("kind", ["att2in2", "topdown"])
+@pytest.mark.parametrize("kind", ["att2in2", "att2all2", "topdown"])
 @pytest.mark.parametrize("seed,use_masks", [(11, False), (12, True)])
 def test_midsize_forward_loss_sampling(ref, kind, seed, use_masks):
     models, criterion = ref

@@ -65,7 +65,7 @@ def teacher_forced_run(model, fc_feats, att_feats, seq, att_masks, save=True, al
     if kind == "att2in2":
         r.S = torch.empty(T, B, 5 * H + A, dtype=torch.float32, device=dev)
         r.ctx = torch.empty(T, B, H, dtype=BF16, device=dev)
-        r.a2c = torch.empty(T, B, 2 * H, dtype=torch.float32, device=dev)
+        r.a2c = None if w.all_gates else torch.empty(T, B, 2 * H, dtype=torch.float32, device=dev)
     else:
         r.G1 = torch.empty(T, B, 4 * H, dtype=torch.float32, device=dev)
         r.G2 = torch.empty(T, B, 4 * H, dtype=torch.float32, device=dev)
@@ -86,7 +86,7 @@ def teacher_forced_run(model, fc_feats, att_feats, seq, att_masks, save=True, al
             if drop is not None:
                 _lib.dropout(r.X[t][:, sl.xt[0]:sl.xt[0] + E], drop, _lib.DROP_XT, row0=t * B)
         if kind == "att2in2":
-            ws = {"S": r.S[t], "ctx": r.ctx[t], "a2c": r.a2c[t]}
+            ws = {"S": r.S[t], "ctx": r.ctx[t], "a2c": None if r.a2c is None else r.a2c[t]}
         else:
             ws = {"G": r.G1[t], "G2": r.G2[t], "att_h": r.ah[t]}
         eng.core_step(r.X[t], r.c[t], feats, ws, X_next=r.X[t + 1], c_out=r.c[t + 1], h_all=r.h_all[:, t], alpha=r.alpha[t])
@@ -168,33 +168,36 @@ def bptt(r, dh_all):
     if kind == "att2in2":
         NS = 5 * H + A
         dS = torch.empty(T, B, NS, dtype=BF16, device=dev)
-        da2c = torch.empty(T, B, 2 * H, dtype=BF16, device=dev)
+        da2c = None if w.all_gates else torch.empty(T, B, 2 * H, dtype=BF16, device=dev)
         dX = torch.empty(T, B, w.Kx, **f32)
         dctx = torch.empty(T, B, H, **f32)
         for t in reversed(range(T)):
             last = t + 1 == T
-            check(lib.uic_lstm_maxout_bwd(ptr(r.S[t]), NS, ptr(r.a2c[t]), 2 * H, ptr(r.c[t][0]), ptr(r.c[t + 1][0]),
+            check(lib.uic_lstm_maxout_bwd(ptr(r.S[t]), NS, None if da2c is None else ptr(r.a2c[t]), 2 * H, ptr(r.c[t][0]), ptr(r.c[t + 1][0]),
                                           ptr(dh3[:, t]), ld_dh, None if last else ptr(dX[t + 1][:, E:]), w.Kx,
-                                          None if last else ptr(dc[(t + 1) % 2][0]), ptr(dS[t]), NS, ptr(da2c[t]), 2 * H,
+                                          None if last else ptr(dc[(t + 1) % 2][0]), ptr(dS[t]), NS, None if da2c is None else ptr(da2c[t]), 2 * H,
                                           ptr(dc[t % 2][0]), B, H, st))
-            gemm(da2c[t], w.w_a2c, out_f32=dctx[t], b_mn=True)
+            # d ctx through a2c (2H maxout inputs) or a2h (att2all2: all five gate sums)
+            gemm(dS[t][:, :5 * H] if da2c is None else da2c[t], w.w_a2c, out_f32=dctx[t], b_mn=True)
             check(lib.uic_att_step_bwd(ptr(dctx[t]), H, ptr(r.alpha[t]), ptr(feats.p_att), ptr(feats.att), ptr(r.S[t][:, 5 * H:]), NS,
                                        ptr(w.w_alpha), ptr(de[t]), ptr(dS[t][:, 5 * H:]), NS, B, L, A, H, st))
             gemm(dS[t], w.w1, out_f32=dX[t], b_mn=True)
-        dS2, da2 = dS.view(T * B, NS), da2c.view(T * B, 2 * H)
+        dS2 = dS.view(T * B, NS)
+        da2 = dS2[:, :5 * H] if da2c is None else da2c.view(T * B, 2 * H)
+        Na = da2.shape[1]
         dW1 = torch.empty(NS, w.Kx, **f32)
         gemm(dS2, X2d, out_f32=dW1, a_mn=True, b_mn=True)
         db1 = torch.zeros(NS, **f32)
         check(lib.uic_col_sum(ptr(dS2), 1, NS, ptr(db1), T * B, NS, st))
-        dWa = torch.empty(2 * H, H, **f32)
+        dWa = torch.empty(Na, H, **f32)
         gemm(da2, r.ctx.view(T * B, H), out_f32=dWa, a_mn=True, b_mn=True)
-        dba = torch.zeros(2 * H, **f32)
-        check(lib.uic_col_sum(ptr(da2), 1, 2 * H, ptr(dba), T * B, 2 * H, st))
+        dba = torch.zeros(Na, **f32)
+        check(lib.uic_col_sum(ptr(da2), 1, da2.stride(0), ptr(dba), T * B, Na, st))
         g["core.i2h.weight"], g["core.h2h.weight"] = dW1[:5 * H, :E], dW1[:5 * H, E:]
         g["core.attention.h2att.weight"] = dW1[5 * H:, E:]
         g["core.i2h.bias"] = g["core.h2h.bias"] = db1[:5 * H]
         g["core.attention.h2att.bias"] = db1[5 * H:]
-        g["core.a2c.weight"], g["core.a2c.bias"] = dWa, dba
+        g["core.a2h.weight" if da2c is None else "core.a2c.weight"], g["core.a2h.bias" if da2c is None else "core.a2c.bias"] = dWa, dba
         dxt2d, ld_dxt = dX.view(T * B, w.Kx), w.Kx
         dctx_ptr, dctx_stride, dctx_ld = dctx, B * H, H
         ah_ptr, ah_stride, ah_ld = r.S[0][:, 5 * H:], B * NS, NS

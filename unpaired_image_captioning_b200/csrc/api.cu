@@ -339,7 +339,7 @@ int64_t uic_att_step_workspace_bytes(int n_img, int beams, int L, int A, int H) 
 
 int uic_lstm_maxout_fwd(const float* sums, int64_t ld_sums, const float* a2c, int64_t ld_a2c, const float* c_prev, float* c_out,
                         float* h_f32, void* h_a, int64_t ld_ha, void* h_b, int64_t ld_hb, int rows, int H, void* stream) {
-  REQUIRE(sums && a2c && c_out, UIC_ERR_ARG, "uic_lstm_maxout_fwd: null pointer");
+  REQUIRE(sums && c_out, UIC_ERR_ARG, "uic_lstm_maxout_fwd: null pointer");
   if (rows == 0) return 0;
   return lstm_maxout_fwd(sums, ld_sums, a2c, ld_a2c, c_prev, c_out, h_f32, h_a, ld_ha, h_b, ld_hb, rows, H, ST(stream));
 }
@@ -490,7 +490,8 @@ int uic_lstm_cell_bwd(const float* gates, int64_t ld_gates, const float* c_prev,
 int uic_lstm_maxout_bwd(const float* sums, int64_t ld_sums, const float* a2c, int64_t ld_a2c, const float* c_prev, const float* c,
                         const float* dh0, int64_t ld0, const float* dh1, int64_t ld1, const float* dc_next, void* dsums_bf16,
                         int64_t ld_ds, void* da2c_bf16, int64_t ld_da, float* dc_prev, int rows, int H, void* stream) {
-  REQUIRE(sums && a2c && c && dsums_bf16 && da2c_bf16 && dc_prev, UIC_ERR_ARG, "uic_lstm_maxout_bwd: null pointer");
+  REQUIRE(sums && c && dsums_bf16 && dc_prev && (a2c != nullptr) == (da2c_bf16 != nullptr), UIC_ERR_ARG,
+          "uic_lstm_maxout_bwd: null pointer (a2c and da2c are given together or not at all)");
   if (rows == 0) return 0;
   return lstm_maxout_bwd(sums, ld_sums, a2c, ld_a2c, c_prev, c, dh0, ld0, dh1, ld1, dc_next, dsums_bf16, ld_ds, da2c_bf16, ld_da,
                          dc_prev, rows, H, ST(stream));

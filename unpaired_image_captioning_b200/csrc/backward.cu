@@ -135,7 +135,7 @@ __global__ void lstm_maxout_bwd_kernel(const float* __restrict__ sums, long long
     const float* s = sums + r * ld_sums;
     const float* a = a2c + r * ld_a2c;
     const float ig = sigmoid_acc(s[j]), fg = sigmoid_acc(s[H + j]), og = sigmoid_acc(s[2 * H + j]);
-    const float p1 = s[3 * H + j] + a[j], p2 = s[4 * H + j] + a[H + j];
+    const float p1 = s[3 * H + j] + (a2c ? a[j] : 0.0f), p2 = s[4 * H + j] + (a2c ? a[H + j] : 0.0f);
     const float g = fmaxf(p1, p2);
     const float tc = tanhf(c[idx]);
     const float dhv = add3(dh, r, j);
@@ -151,8 +151,10 @@ __global__ void lstm_maxout_bwd_kernel(const float* __restrict__ sums, long long
     d[2 * H + j] = __float2bfloat16_rn(dhv * tc * og * (1.0f - og));
     d[3 * H + j] = __float2bfloat16_rn(d1);
     d[4 * H + j] = __float2bfloat16_rn(d2);
-    da2c[r * ld_da + j] = __float2bfloat16_rn(d1);
-    da2c[r * ld_da + H + j] = __float2bfloat16_rn(d2);
+    if (da2c) {
+      da2c[r * ld_da + j] = __float2bfloat16_rn(d1);
+      da2c[r * ld_da + H + j] = __float2bfloat16_rn(d2);
+    }
     dc_prev[idx] = dc * fg;
   }
 }

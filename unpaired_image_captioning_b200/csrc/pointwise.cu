@@ -161,8 +161,12 @@ __global__ void lstm_maxout_fwd_kernel(const float* __restrict__ sums, long long
     ldv<VEC>(s + 2 * H + j, so);
     ldv<VEC>(s + 3 * H + j, s3);
     ldv<VEC>(s + 4 * H + j, s4);
-    ldv<VEC>(a + j, a0);
-    ldv<VEC>(a + H + j, a1);
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) a0[v] = a1[v] = 0.0f;
+    if (a2c) {  // att2all2 (:618-654): the context term was accumulated into all five gate sums by its GEMM
+      ldv<VEC>(a + j, a0);
+      ldv<VEC>(a + H + j, a1);
+    }
 #pragma unroll
     for (int v = 0; v < VEC; ++v) cp[v] = 0.0f;
     if (c_prev) ldv<VEC>(c_prev + static_cast<long long>(r) * H + j, cp);

@@ -42,6 +42,7 @@ class PackedWeights:
 
     def __init__(self, model):
         self.kind = model.kind
+        self.all_gates = bool(getattr(model, "all_gates", False))   # att2all2: the context feeds all five gate sums
         sd = {k: v.detach() for k, v in model.state_dict().items()}
         self.signature = PackedWeights.signature_of(model)
         H, E, A = model.rnn_size, model.input_encoding_size, model.att_hid_size
@@ -61,8 +62,12 @@ class PackedWeights:
             w1[:5 * H, E:] = f32("core.h2h.weight")
             w1[5 * H:, E:] = w_h2att
             self.w1 = _bf16(w1)
-            self.b1 = torch.cat([f32("core.i2h.bias") + f32("core.h2h.bias"), b_h2att]).contiguous()
-            self.w_a2c, self.b_a2c = _bf16(sd["core.a2c.weight"]), f32("core.a2c.bias")
+            if self.all_gates:   # Att2all2Core (models/AttModel.py:618-654): a2h (5H, H); its bias joins the gate bias
+                self.b1 = torch.cat([f32("core.i2h.bias") + f32("core.h2h.bias") + f32("core.a2h.bias"), b_h2att]).contiguous()
+                self.w_a2c, self.b_a2c = _bf16(sd["core.a2h.weight"]), None
+            else:
+                self.b1 = torch.cat([f32("core.i2h.bias") + f32("core.h2h.bias"), b_h2att]).contiguous()
+                self.w_a2c, self.b_a2c = _bf16(sd["core.a2c.weight"]), f32("core.a2c.bias")
         elif self.kind == "topdown":
             self.Kx = E + 5 * H
             self.w_fc, self.b_fc = _bf16(sd["fc_embed.0.weight"]), f32("fc_embed.0.bias")
@@ -252,9 +257,14 @@ class DecoderEngine:
             gemm(X, w.w1, w.b1, out_f32=S, exp_col0=5 * H, exp_scale=_lib.ATT_F_SCALE)   # S[:, 5H:] = F = 16 exp(2 att_h)
             _lib.att_step(S[:, 5 * H:], S.stride(0), feats.p_att, feats.att, w.w_alpha, feats.masks, ws["ctx"], H, None, 0, alpha,
                           feats.B, beams, feats.L, A, H)
-            gemm(ws["ctx"], w.w_a2c, w.b_a2c, out_f32=ws["a2c"])
+            if w.all_gates:   # S[:, :5H] += a2h(ctx): the saved sums already hold everything the cell (and its backward) needs
+                gemm(ws["ctx"], w.w_a2c, None, out_f32=S[:, :5 * H], accumulate=True)
+                a2c = None
+            else:
+                a2c = ws["a2c"]
+                gemm(ws["ctx"], w.w_a2c, w.b_a2c, out_f32=a2c)
             h_dst = cols(Xn, sl.h_out)
-            check(lib.uic_lstm_maxout_fwd(ptr(S), S.stride(0), ptr(ws["a2c"]), 2 * H, ptr(c[0]), ptr(c_out[0]), None,
+            check(lib.uic_lstm_maxout_fwd(ptr(S), S.stride(0), ptr(a2c), 2 * H, ptr(c[0]), ptr(c_out[0]), None,
                                           ptr(h_dst), Xn.stride(0), ptr(h_all), h_all.stride(0) if h_all is not None else 0,
                                           R, H, st))
         else:

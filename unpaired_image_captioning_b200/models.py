@@ -21,7 +21,7 @@ from . import _lib
 from ._lib import check, ptr, stream
 from .engine import BF16, DecoderEngine, Features, Slots
 
-HOT_PATH_MODELS = ("att2in2", "topdown")
+HOT_PATH_MODELS = ("att2in2", "att2all2", "topdown")
 
 
 class CaptionModel(nn.Module):
@@ -79,6 +79,19 @@ class Att2in2Core(_CoreBase):
         super().__init__()
         self.rnn_size = opt.rnn_size
         self.a2c = nn.Linear(opt.rnn_size, 2 * opt.rnn_size)
+        self.i2h = nn.Linear(opt.input_encoding_size, 5 * opt.rnn_size)
+        self.h2h = nn.Linear(opt.rnn_size, 5 * opt.rnn_size)
+        self.dropout = nn.Dropout(opt.drop_prob_lm)
+        self.attention = Attention(opt)
+
+
+class Att2all2Core(_CoreBase):
+    """models/AttModel.py:618-654 (parameters a2h, i2h, h2h, attention.*): the attended context feeds all five gate sums."""
+
+    def __init__(self, opt):
+        super().__init__()
+        self.rnn_size = opt.rnn_size
+        self.a2h = nn.Linear(opt.rnn_size, 5 * opt.rnn_size)
         self.i2h = nn.Linear(opt.input_encoding_size, 5 * opt.rnn_size)
         self.h2h = nn.Linear(opt.rnn_size, 5 * opt.rnn_size)
         self.dropout = nn.Dropout(opt.drop_prob_lm)
@@ -390,6 +403,19 @@ class Att2in2Model(AttModel):
         self._bind_core()
 
 
+class Att2all2Model(AttModel):
+    """models/AttModel.py:678-683.  Same step plan as att2in2 (`kind`); `all_gates` selects the a2h accumulation."""
+    kind = "att2in2"
+    all_gates = True
+
+    def __init__(self, opt):
+        super().__init__(opt)
+        self.core = Att2all2Core(opt)
+        delattr(self, "fc_embed")
+        self.fc_embed = lambda x: x
+        self._bind_core()
+
+
 class TopDownModel(AttModel):
     """models/AttModel.py:686-690."""
     kind = "topdown"
@@ -405,6 +431,8 @@ def setup(opt):
     """models/__init__.py:22-59 for the models on the hot path."""
     if opt.caption_model == "att2in2":
         return Att2in2Model(opt)
+    if opt.caption_model == "att2all2":
+        return Att2all2Model(opt)
     if opt.caption_model == "topdown":
         return TopDownModel(opt)
     raise Exception("Caption model not supported: {}".format(opt.caption_model))

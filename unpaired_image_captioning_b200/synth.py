@@ -33,6 +33,9 @@ CONFIGS = {
     "tiny_att2in2": dict(caption_model="att2in2", rnn_size=32, input_encoding_size=32, att_hid_size=32,
                          att_size=7, vocab_size=51, seq_length=6, batch=5, beam_size=3,
                          fc_feat_size=64, att_feat_size=64),
+    "tiny_att2all2": dict(caption_model="att2all2", rnn_size=32, input_encoding_size=32, att_hid_size=32,
+                          att_size=7, vocab_size=51, seq_length=6, batch=5, beam_size=3,
+                          fc_feat_size=64, att_feat_size=64),
     "tiny_topdown": dict(caption_model="topdown", rnn_size=32, input_encoding_size=32, att_hid_size=32,
                          att_size=7, vocab_size=51, seq_length=6, batch=5, beam_size=3,
                          fc_feat_size=64, att_feat_size=64),
@@ -115,8 +118,11 @@ def init_state_dict(opt, seed=1234, peaked=0.0, eos_bias=0.0):
     sd["att_embed.0.weight"], sd["att_embed.0.bias"] = lin(H, D)
     sd["logit.weight"], sd["logit.bias"] = lin(V, H)
     sd["ctx2att.weight"], sd["ctx2att.bias"] = lin(A, H)
-    if opt.caption_model == "att2in2":
-        sd["core.a2c.weight"], sd["core.a2c.bias"] = lin(2 * H, H)
+    if opt.caption_model in ("att2in2", "att2all2"):
+        if opt.caption_model == "att2all2":
+            sd["core.a2h.weight"], sd["core.a2h.bias"] = lin(5 * H, H)
+        else:
+            sd["core.a2c.weight"], sd["core.a2c.bias"] = lin(2 * H, H)
         sd["core.i2h.weight"], sd["core.i2h.bias"] = lin(5 * H, E)
         sd["core.h2h.weight"], sd["core.h2h.bias"] = lin(5 * H, H)
     elif opt.caption_model == "topdown":
