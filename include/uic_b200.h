@@ -264,6 +264,11 @@ int uic_lse_xent_bwd(const float* logits, int64_t ld, const float* lse, const in
 /* d logits = d lp - exp(lp) * rowsum(d lp): backward of uic_log_softmax_rows for the dense API path. */
 int uic_log_softmax_bwd(const float* dlp, int64_t ld_dlp, const float* lp, int64_t ld_lp, void* dlogits_bf16, int64_t ld_d,
                         int rows, int V, void* stream);
+/* Batch statistics of nn.BatchNorm1d(att_feat_size) in att_embed (use_bn, models/AttModel.py:79-84) over the PACKED
+ * regions that pack_wrapper (:44-53) feeds it: sum[c] += sum x[r,c], sumsq[c] += sum x[r,c]^2 over the rows
+ * (image i, region l < lens[i]) of x (n_img * L rows, pitch ld; bf16 or fp32).  lens == NULL: every row.  fp64 sums. */
+int uic_col_moments(const void* x, int is_bf16, int64_t ld, const int32_t* lens, int n_img, int L, int cols, double* sum,
+                    double* sumsq, void* stream);
 /* out[c] += sum_r x[r,c] (bias gradients); x is bf16 (is_bf16 != 0) or fp32. */
 int uic_col_sum(const void* x, int is_bf16, int64_t ld, float* out, int rows, int cols, void* stream);
 /* dEmb[tok[r], :] += dxt[r, :] where ReLU(Emb) was active (backward of uic_embed_rows). */

@@ -59,6 +59,32 @@ def dropout_mask(drop, site, row_ids, cols):
     return torch.from_numpy((u >= np.float32(p)).astype(np.float32) / np.float32(1.0 - p))
 
 
+_BN_TRAIN = False
+
+
+class bn_training:
+    """`with bn_training():` -- the BatchNorm1d of att_embed (use_bn = 1) normalises with the statistics of the batch
+    (module in train() mode) instead of its running statistics."""
+
+    def __enter__(self):
+        global _BN_TRAIN
+        self._old, _BN_TRAIN = _BN_TRAIN, True
+
+    def __exit__(self, *exc):
+        global _BN_TRAIN
+        _BN_TRAIN = self._old
+
+
+def bn_batch_stats(att_feats, att_masks):
+    """Mean / biased variance over the packed valid regions (pack_wrapper, models/AttModel.py:44-53): the first
+    sum(mask) regions of every image, after clip_att."""
+    keep = int(att_masks.long().sum(1).max())
+    n_valid = att_masks[:, :keep].long().sum(1)
+    valid = torch.arange(keep)[None, :] < n_valid[:, None]
+    xv = att_feats[:, :keep][valid]
+    return xv.mean(0), xv.var(0, unbiased=False), int(valid.sum())
+
+
 def prepare_features(sd, kind, fc_feats, att_feats, att_masks=None, drop=None):
     if att_masks is not None:  # clip_att (:99-105)
         keep = int(att_masks.long().sum(1).max())
@@ -72,7 +98,19 @@ def prepare_features(sd, kind, fc_feats, att_feats, att_masks=None, drop=None):
         fc = fc_feats
     # att_embed = Linear+ReLU (:79-84, use_bn=0, dropout off).  With masks the reference packs the
     # valid regions, embeds them and pads the rest with ZEROS (pad_packed_sequence, :50-51).
-    att = torch.relu(_linear(sd, "att_embed.0", att_feats))
+    if "att_embed.1.weight" in sd:
+        # use_bn = 1 (:79-80): BatchNorm1d(att_feat_size) in front of the Linear.  It only runs on the packed 2-D rows, i.e.
+        # with att_masks (a 3-D unmasked batch makes nn.BatchNorm1d read the region axis as channels and raise).
+        if att_masks is None:
+            raise RuntimeError("running_mean should contain %d elements not %d" % (att_feats.size(1), att_feats.size(2)))
+        if _BN_TRAIN:
+            mean, var, _ = bn_batch_stats(att_feats, att_masks)
+        else:
+            mean, var = sd["att_embed.0.running_mean"], sd["att_embed.0.running_var"]
+        xn = (att_feats - mean) / torch.sqrt(var + 1e-5) * sd["att_embed.0.weight"] + sd["att_embed.0.bias"]
+        att = torch.relu(_linear(sd, "att_embed.1", xn))
+    else:
+        att = torch.relu(_linear(sd, "att_embed.0", att_feats))
     if att_masks is not None:
         n_valid = att_masks.long().sum(1)
         valid = (torch.arange(att.size(1))[None, :] < n_valid[:, None]).to(att.dtype)
@@ -233,7 +271,7 @@ def train_loss(sd, kind, fc_feats, att_feats, labels, masks, att_masks=None, ss_
 
 
 def loss_and_grads(sd, kind, fc_feats, att_feats, labels, masks, att_masks=None, ss_prob=0.0, ss_seed=0, inputs=None, drop=None):
-    leaf = {k: v.detach().clone().requires_grad_(True) for k, v in sd.items()}
+    leaf = {k: v.detach().clone().requires_grad_(v.is_floating_point()) for k, v in sd.items()}
     loss = train_loss(leaf, kind, fc_feats, att_feats, labels, masks, att_masks, ss_prob, ss_seed, inputs, drop)
     loss.backward()
     grads = {k: (v.grad if v.grad is not None else torch.zeros_like(v)) for k, v in leaf.items()}

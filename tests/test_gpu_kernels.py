@@ -466,3 +466,22 @@ def test_diverse_select(B, b, group, V):
     assert torch.equal(ti.cpu().long(), ix[:, :b])
     torch.testing.assert_close(tv.cpu(), ys[:, :b], rtol=1e-5, atol=1e-5)
     torch.testing.assert_close(tu.cpu(), torch.gather(lp, 1, ix[:, :b]), rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("B,L,D,bf16", [(5, 7, 64, True), (37, 50, 2048, True), (9, 13, 200, False)])
+def test_col_moments(B, L, D, bf16):
+    """Column sums / sums of squares over the packed valid regions (BatchNorm1d statistics of att_embed, AttModel.py:44-53,80)."""
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(B + L)
+    x = torch.randn(B, L, D, generator=g).clamp_(min=0).cuda()
+    x = x.bfloat16() if bf16 else x
+    lens = torch.randint(1, L + 1, (B,), generator=g, dtype=torch.int32).cuda()
+    mom = torch.zeros(2, D, dtype=torch.float64, device=DEV)
+    check(lib.uic_col_moments(ptr(x), int(bf16), D, ptr(lens), B, L, D, ptr(mom[0]), ptr(mom[1]), stream()))
+    valid = (torch.arange(L, device=DEV)[None, :] < lens[:, None])
+    xv = x[valid].double()
+    torch.testing.assert_close(mom[0], xv.sum(0), rtol=1e-6, atol=1e-6)
+    torch.testing.assert_close(mom[1], (xv * xv).sum(0), rtol=1e-6, atol=1e-6)
+    mom.zero_()
+    check(lib.uic_col_moments(ptr(x), int(bf16), D, None, B, L, D, ptr(mom[0]), ptr(mom[1]), stream()))
+    torch.testing.assert_close(mom[0], x.double().sum((0, 1)), rtol=1e-6, atol=1e-6)

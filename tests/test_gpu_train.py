@@ -96,3 +96,60 @@ def test_loss_matches_dense_criterion_and_uses_global_normaliser():
     twice = masks[:, 1:].sum() * 2
     half = model(fc, None, att, labels, masks, None, mode="forward_loss", global_mask_sum=twice)
     torch.testing.assert_close(half.detach() * 2, fused.detach(), rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("kind", ["att2in2", "topdown"])
+def test_use_bn_batchnorm_folded_into_att_embed(kind):
+    """use_bn = 1 (the reference's default, opts.py:52; models/AttModel.py:79-84): eval() normalises with the running
+    statistics, train() with the statistics of the packed valid regions; gradients reach the BN affine and the Linear
+    behind it; the running statistics are updated like torch does; no att_masks -> the reference's RuntimeError."""
+    opt = synth.make_opt(caption_model=kind, vocab_size=999, rnn_size=128, input_encoding_size=64, att_hid_size=64, seq_length=10,
+                         fc_feat_size=256, att_feat_size=256, use_bn=1)
+    sd = synth.init_state_dict(opt, seed=41)
+    B, L = 12, 20
+    fc, att = synth.make_features(B, L, 256, seed=41)
+    labels, masks = synth.make_captions(B, 10, 999, seed=41, min_len=3)
+    am = synth.make_att_masks(B, L, seed=41)
+    model = uic.setup(opt)
+    model.load_state_dict(sd)
+    model = model.cuda()
+    cu = lambda t: t.cuda()
+
+    model.eval()
+    ref = O.teacher_forced(sd, kind, fc, att, labels, am)
+    with torch.no_grad():
+        out = model(cu(fc), None, cu(att), cu(labels), cu(am))
+    sel = masks[:, 1:].bool()
+    rel = ((out.cpu() - ref).abs() / ref.abs().clamp_min(1.0))[sel]
+    assert float(rel.max()) < 2e-3, float(rel.max())
+    with pytest.raises(RuntimeError):
+        model(cu(fc), None, cu(att), cu(labels), None)
+    assert int(model.att_embed[0].num_batches_tracked) == 3          # eval() leaves the statistics alone
+
+    model.train()
+    with O.bn_training():
+        ref_loss, ref_grads = O.loss_and_grads(sd, kind, fc, att, labels, masks, am)
+        mean, var, n = O.bn_batch_stats(att, am)
+    loss = model(cu(fc), None, cu(att), cu(labels), cu(masks), cu(am), mode="forward_loss")
+    loss.backward()
+    assert abs(float(loss) - float(ref_loss)) < 2e-3 * float(ref_loss)
+    errs = _grad_errors(model, ref_grads)
+    # d gamma_j = sum over rows and units of d z W (x_j - mean_j) / sigma_j: a sum of cancelling terms over only B * L = 240
+    # rows here, so the bf16 operand rounding shows more than in the other gradients (measured 4.8e-2 / 5.4e-2)
+    bad = {k: v for k, v in errs.items() if v > (8e-2 if k == "att_embed.0.weight" else 5e-2)}
+    assert not bad, bad
+    bn = model.att_embed[0]
+    assert int(bn.num_batches_tracked) == 4
+    torch.testing.assert_close(bn.running_mean.cpu(), 0.9 * sd["att_embed.0.running_mean"] + 0.1 * mean, rtol=2e-3, atol=2e-4)
+    torch.testing.assert_close(bn.running_var.cpu(), 0.9 * sd["att_embed.0.running_var"] + 0.1 * var * n / (n - 1), rtol=2e-3, atol=2e-4)
+    # sampling in eval mode with the updated statistics equals the oracle run on the model's own state_dict (wide-margin
+    # weights, so that token ids are comparable under bf16 operands)
+    peaked = synth.init_state_dict(opt, seed=41, peaked=30.0, eos_bias=0.5)
+    peaked.update({k: v.detach().cpu() for k, v in model.state_dict().items() if k.startswith("att_embed.0.")})
+    model.load_state_dict(peaked)
+    model.eval()
+    sd2 = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    ref_seq, ref_lp, _ = O.sample_beam(sd2, kind, fc, att, 10, 3, am)
+    seq, lp = model(cu(fc), None, cu(att), cu(am), opt={"beam_size": 3}, mode="sample")
+    rows = (seq == ref_seq).all(1)
+    assert float(rows.float().mean()) >= 0.75, (seq, ref_seq)

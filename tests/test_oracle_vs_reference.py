@@ -71,3 +71,48 @@ def test_diverse_beam_search(ref, kind, o):
         for a, b in zip(ref_done, done[k]):
             assert torch.equal(a["seq"], b["seq"])
             assert abs(a["p"] - b["p"]) < 1e-4 * max(1.0, abs(a["p"]))
+
+
+@pytest.mark.parametrize("kind", ["att2in2", "topdown"])
+def test_use_bn_batchnorm_in_att_embed(ref, kind):
+    """use_bn = 1 (opts.py:52 default; models/AttModel.py:79-84): BatchNorm1d over the packed valid regions.  eval(): running
+    statistics; train(): batch statistics (+ gradients of the BN affine and the Linear behind it); without att_masks the
+    reference raises."""
+    models, criterion = ref
+    opt = synth.make_opt(caption_model=kind, vocab_size=299, rnn_size=64, input_encoding_size=48, att_hid_size=40, seq_length=9,
+                         fc_feat_size=96, att_feat_size=96, use_bn=1)
+    sd = synth.init_state_dict(opt, seed=31, peaked=30.0, eos_bias=0.5)
+    model = models.setup(opt)
+    model.load_state_dict(sd)
+    B, L = 6, 11
+    fc, att = synth.make_features(B, L, 96, seed=31)
+    labels, masks = synth.make_captions(B, 9, 299, seed=31, min_len=3)
+    am = synth.make_att_masks(B, L, seed=31)
+    crit = criterion.LanguageModelCriterion(opt)
+
+    model.eval()
+    ref_out = model(fc, None, att, labels, am)
+    torch.testing.assert_close(O.teacher_forced(sd, kind, fc, att, labels, am), ref_out.detach(), rtol=1e-5, atol=3e-6)
+    with torch.no_grad():
+        rs, rlp = model(fc, None, att, am, opt={"beam_size": 3}, mode="sample")
+    s, lp = O.sample(sd, kind, fc, att, 9, am, {"beam_size": 3})
+    assert torch.equal(s, rs)
+    with pytest.raises(RuntimeError):
+        model(fc, None, att, labels, None)
+    with pytest.raises(RuntimeError):
+        O.teacher_forced(sd, kind, fc, att, labels, None)
+
+    model.load_state_dict(sd)          # the failed call above already touched num_batches_tracked
+    model.train()
+    model.zero_grad()
+    loss = crit(model(fc, None, att, labels, am), labels[:, 1:], masks[:, 1:])
+    loss.backward()
+    with O.bn_training():
+        o_loss, o_grads = O.loss_and_grads(sd, kind, fc, att, labels, masks, am)
+        mean, var, n = O.bn_batch_stats(att, am)
+    torch.testing.assert_close(o_loss, loss.detach(), rtol=1e-5, atol=1e-6)
+    for k, p in model.named_parameters():
+        torch.testing.assert_close(o_grads[k], p.grad, rtol=2e-4, atol=2e-6, msg=k)
+    bn = model.att_embed[0]
+    torch.testing.assert_close(bn.running_mean, 0.9 * sd["att_embed.0.running_mean"] + 0.1 * mean, rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(bn.running_var, 0.9 * sd["att_embed.0.running_var"] + 0.1 * var * n / (n - 1), rtol=1e-5, atol=1e-6)

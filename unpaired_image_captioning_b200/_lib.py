@@ -48,6 +48,7 @@ SIGNATURES = {
     "uic_dropout": (_i, [_p, _i, _i64, _i64, _i, _f, _p, _i, _i64, _i64, _p]),
     "uic_ss_advance": (_i, [_p, _i, _p, _i64, _f, _p, _i, _p, _i, _p, _i64, _p, _i64, _i, _i, _p]),
     "uic_beam_step": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p]),
+    "uic_col_moments": (_i, [_p, _i, _i64, _p, _i, _i, _i, _p, _p, _p]),
     "uic_diverse_select": (_i, [_p, _p, _i, _p, _i, _i, _i, _i, _i, _f, _p, _p, _p, _p]),
     "uic_beam_gather": (_i, [_p, _p, _p, _i64, _i, _i, _i, _i, _p, _p, _i, _i, _i, _p]),
     "uic_lstm_cell_bwd": (_i, [_p, _i64, _p, _p, _p, _i64, _p, _i64, _p, _i64, _p, _p, _i64, _p, _i, _i, _p]),

@@ -284,7 +284,17 @@ def bptt(r, dh_all):
     gemm(d_pre, feats.x_in, out_f32=dWe, a_mn=True, b_mn=True)
     dbe = torch.zeros(H, **f32)
     check(lib.uic_col_sum(ptr(datt), 0, H, ptr(dbe), B * L, H, st))       # fp32 masked copy left by relu_bwd_cast
-    g["att_embed.0.weight"], g["att_embed.0.bias"] = dWe, dbe
+    if w.use_bn:
+        # the Linear ran on the folded operand W' = W diag(s), b' = b + W t (engine._fold_bn); the statistics depend on the
+        # (constant) features only, so the chain rule back to W, b, gamma, beta is column-wise arithmetic on (H, D) matrices
+        bn, W = feats.bn, w.w_att_f32
+        v = torch.mv(W.t(), dbe)                                          # d beta = W^T d b'
+        g["att_embed.0.bias"] = v
+        g["att_embed.0.weight"] = ((dWe * W).sum(0) - v * bn["mean"]) * bn["inv"]
+        g["att_embed.1.weight"] = dWe * bn["s"][None, :] + dbe[:, None] * bn["t"][None, :]
+        g["att_embed.1.bias"] = dbe
+    else:
+        g["att_embed.0.weight"], g["att_embed.0.bias"] = dWe, dbe
     return g
 
 

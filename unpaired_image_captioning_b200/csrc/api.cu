@@ -539,6 +539,14 @@ int uic_col_sum(const void* x, int is_bf16, int64_t ld, float* out, int rows, in
   return col_sum(x, is_bf16, ld, out, rows, cols, ST(stream));
 }
 
+int uic_col_moments(const void* x, int is_bf16, int64_t ld, const int32_t* lens, int n_img, int L, int cols, double* sum, double* sumsq,
+                    void* stream) {
+  REQUIRE(x && sum && sumsq, UIC_ERR_ARG, "uic_col_moments: null pointer");
+  REQUIRE(ld >= cols, UIC_ERR_SHAPE, "uic_col_moments: pitch %lld < cols %d", static_cast<long long>(ld), cols);
+  if (n_img <= 0 || L <= 0 || cols <= 0) return 0;
+  return col_moments(x, is_bf16, ld, lens, n_img, L, cols, sum, sumsq, ST(stream));
+}
+
 int uic_embed_bwd(const float* dxt, int64_t ld, const int64_t* tok, const void* table_relu_bf16, float* demb, int64_t rows, int E,
                   int V, void* stream) {
   REQUIRE(dxt && tok && table_relu_bf16 && demb, UIC_ERR_ARG, "uic_embed_bwd: null pointer");

@@ -582,6 +582,63 @@ int col_sum(const void* x, int is_bf16, long long ld, float* out, int rows, int 
   return 0;
 }
 
+// ---- BatchNorm1d statistics over the packed (valid) regions (models/AttModel.py:80 with pack_wrapper :44-53) ----------
+// sum[c] += sum_r x[r, c], sumsq[c] += sum_r x[r, c]^2 over the rows (image i, region l < lens[i]) of x (n_img * L, cols).
+// One thread per column (a warp reads 128 contiguous bytes of a row), 8 rows in flight per thread, fp64 accumulation
+// so that var = E[x^2] - mean^2 keeps fp32 accuracy.
+template <typename T>
+__global__ void __launch_bounds__(256) col_moments_kernel(const T* __restrict__ x, long long ld, const int32_t* __restrict__ lens,
+                                                          int n_img, int L, int cols, double* __restrict__ sum,
+                                                          double* __restrict__ sumsq) {
+  const int c = blockIdx.x * 256 + threadIdx.x;
+  const int rows = n_img * L;
+  const int rows_per_cta = (rows + gridDim.y - 1) / gridDim.y;
+  const int r_begin = blockIdx.y * rows_per_cta, r_end = min(rows, r_begin + rows_per_cta);
+  if (c >= cols) return;
+  double s1 = 0.0, s2 = 0.0;
+  for (int r0 = r_begin; r0 < r_end; r0 += 8) {
+    float v[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int r = r0 + k;
+      v[k] = 0.0f;
+      if (r < r_end) {
+        const int img = r / L;
+        if (lens == nullptr || r - img * L < lens[img]) v[k] = static_cast<float>(x[static_cast<long long>(r) * ld + c]);
+      }
+    }
+    float p1 = 0.0f, p2 = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      p1 += v[k];
+      p2 = fmaf(v[k], v[k], p2);
+    }
+    s1 += static_cast<double>(p1);
+    s2 += static_cast<double>(p2);
+  }
+  atomicAdd(sum + c, s1);
+  atomicAdd(sumsq + c, s2);
+}
+
+int col_moments(const void* x, int is_bf16, long long ld, const int32_t* lens, int n_img, int L, int cols, double* sum, double* sumsq,
+                cudaStream_t stream) {
+  const int gx = (cols + 255) / 256;
+  const int rows = n_img * L;
+  int gy = (4 * 148 + gx - 1) / gx;
+  const int max_gy = (rows + 63) / 64;
+  gy = gy > max_gy ? max_gy : gy;
+  gy = gy < 1 ? 1 : gy;
+  dim3 grid(gx, gy);
+  launch_begin("col_moments", stream);
+  if (is_bf16)
+    col_moments_kernel<__nv_bfloat16><<<grid, 256, 0, stream>>>(static_cast<const __nv_bfloat16*>(x), ld, lens, n_img, L, cols, sum, sumsq);
+  else
+    col_moments_kernel<float><<<grid, 256, 0, stream>>>(static_cast<const float*>(x), ld, lens, n_img, L, cols, sum, sumsq);
+  UIC_CUDA_OK(cudaGetLastError());
+  launch_end(stream);
+  return 0;
+}
+
 // ---- embedding backward: dEmb[tok[r], e] += dxt[r, e] where relu(emb) was active -----------------------------
 __global__ void embed_bwd_kernel(const float* __restrict__ dxt, long long ld, const int64_t* __restrict__ tok,
                                  const __nv_bfloat16* __restrict__ table_relu, float* __restrict__ demb, long long rows, int E,

@@ -133,6 +133,8 @@ int lse_xent_bwd(const float* logits, long long ld, const float* lse, const int6
                  const float* inv_norm, float grad_scale, void* dlogits, long long ld_d, int rows, int V, cudaStream_t stream);
 int log_softmax_bwd(const float* dlp, long long ld_dlp, const float* lp, long long ld_lp, void* dlogits, long long ld_d, int rows,
                     int V, cudaStream_t stream);
+int col_moments(const void* x, int is_bf16, long long ld, const int32_t* lens, int n_img, int L, int cols, double* sum, double* sumsq,
+                cudaStream_t stream);
 int col_sum(const void* x, int is_bf16, long long ld, float* out, int rows, int cols, cudaStream_t stream);
 int embed_bwd(const float* dxt, long long ld, const int64_t* tok, const void* table_relu, float* demb, long long rows, int E, int V,
               cudaStream_t stream);

@@ -50,7 +50,12 @@ class PackedWeights:
         f32 = lambda k: sd[k].float().contiguous()
         # Embedding + ReLU folded into the table copy (models/AttModel.py:73-75)
         self.emb_relu = _lib.cast_bf16(f32("embed.0.weight"), relu=True)
-        self.w_att_embed, self.b_att_embed = _bf16(sd["att_embed.0.weight"]), f32("att_embed.0.bias")
+        self.use_bn = int(getattr(model, "use_bn", 0))
+        if self.use_bn:   # BatchNorm1d in front of the Linear: folded into the operand per batch (DecoderEngine._fold_bn)
+            self.w_att_f32, self.b_att_f32 = f32("att_embed.1.weight"), f32("att_embed.1.bias")
+            self.w_att_embed = self.b_att_embed = None
+        else:
+            self.w_att_embed, self.b_att_embed = _bf16(sd["att_embed.0.weight"]), f32("att_embed.0.bias")
         self.w_ctx2att, self.b_ctx2att = _bf16(sd["ctx2att.weight"]), f32("ctx2att.bias")
         self.w_logit, self.b_logit = _bf16(sd["logit.weight"]), f32("logit.bias")
         self.w_alpha = f32("core.attention.alpha_net.weight").reshape(-1).contiguous()
@@ -188,7 +193,10 @@ class DecoderEngine:
         else:
             x = _lib.cast_bf16(att_feats.reshape(B * L, D).float() if att_feats.dtype != torch.float32 else att_feats.reshape(B * L, D))
         att = torch.empty(B * L, H, dtype=BF16, device=x.device) if out is None else out.att.view(B * L, H)
-        gemm(x, w.w_att_embed, w.b_att_embed, out_bf16=att, relu=True)
+        w_ae, b_ae, bn = w.w_att_embed, w.b_att_embed, None
+        if w.use_bn:
+            w_ae, b_ae, bn = self._fold_bn(x, att_masks, B, L)
+        gemm(x, w_ae, b_ae, out_bf16=att, relu=True)
         if att_masks is not None:
             check(self.lib.uic_zero_padded_rows(ptr(att), ptr(att_masks), B, L, H, stream()))
         if drop is not None:   # att_embed's nn.Dropout (training mode, AttModel.py:79-84): ctx2att sees the dropped tile
@@ -211,7 +219,41 @@ class DecoderEngine:
         feats = Features(att.view(B, L, H), p_att.view(B, L, A), fc, att_masks, B, L)
         if keep_inputs:  # bf16 operand copies of the raw features, needed by the prologue wgrads
             feats.x_in, feats.fc_in = x, (fc_in if self.kind == "topdown" else None)
+            feats.bn = bn
         return feats
+
+    def _fold_bn(self, x, att_masks, B, L):
+        """nn.BatchNorm1d(att_feat_size) in front of att_embed's Linear (use_bn = 1, models/AttModel.py:79-80), applied by
+        pack_wrapper (:44-53) to the packed valid regions.  y = (x - mean) s + beta with s = gamma / sqrt(var + eps) is
+        affine per column, so it folds into the GEMM operand: W' = W diag(s), b' = b + W (beta - mean s).  train(): batch
+        statistics from one uic_col_moments pass over the bf16 operand (and the running statistics are updated like
+        torch does); eval(): running statistics.  No host synchronisation."""
+        w, bn = self.w, self.model.att_embed[0]
+        D = x.shape[1]
+        if att_masks is None:   # the reference hands the 3-D batch to BatchNorm1d, which reads the region axis as channels
+            raise RuntimeError(f"running_mean should contain {L} elements not {D}")
+        gamma, beta = bn.weight.detach().float(), bn.bias.detach().float()
+        if bn.training or bn.running_mean is None:
+            lens = att_masks.sum(1).to(torch.int32)
+            mom = torch.zeros(2, D, dtype=torch.float64, device=x.device)
+            check(self.lib.uic_col_moments(ptr(x), 1, x.stride(0), ptr(lens), B, L, D, ptr(mom[0]), ptr(mom[1]), stream()))
+            n = lens.sum().double()
+            mean64 = mom[0] / n
+            var64 = (mom[1] / n - mean64 * mean64).clamp_min_(0.0)
+            mean, var = mean64.float(), var64.float()
+            if bn.training and bn.running_mean is not None:
+                with torch.no_grad():
+                    bn.num_batches_tracked += 1
+                    m = bn.momentum if bn.momentum is not None else 1.0 / bn.num_batches_tracked.double()
+                    bn.running_mean.mul_(1.0 - m).add_((mean64 * m).to(bn.running_mean.dtype))
+                    bn.running_var.mul_(1.0 - m).add_((var64 * (n / (n - 1.0)) * m).to(bn.running_var.dtype))
+        else:
+            mean, var = bn.running_mean.float(), bn.running_var.float()
+        inv = torch.rsqrt(var + bn.eps)
+        s = gamma * inv
+        t = beta - mean * s
+        b_f = torch.addmv(w.b_att_f32, w.w_att_f32, t).contiguous()
+        return _bf16(w.w_att_f32 * s[None, :]), b_f, {"s": s, "t": t, "inv": inv, "mean": mean}
 
     def _feature_buffers(self, feats):
         """Static per-graph copies of the feature tiles (shapes of `feats`, a Features or a LazyFeatures)."""

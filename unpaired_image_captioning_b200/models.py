@@ -126,8 +126,8 @@ class AttModel(CaptionModel):
         self.att_feat_size = opt.att_feat_size
         self.att_hid_size = opt.att_hid_size
         self.use_bn = getattr(opt, "use_bn", 0)
-        if self.use_bn:
-            raise NotImplementedError("use_bn != 0 (BatchNorm around att_embed) is not on the B200 hot path yet")
+        if self.use_bn not in (0, 1):
+            raise NotImplementedError("use_bn = 2 (a second BatchNorm behind att_embed) is not on the B200 hot path yet")
         if getattr(opt, "logit_layers", 1) != 1:
             raise NotImplementedError("logit_layers > 1 is not on the B200 hot path")
         for name, v in (("rnn_size", self.rnn_size), ("input_encoding_size", self.input_encoding_size),
@@ -140,7 +140,9 @@ class AttModel(CaptionModel):
         self.embed = nn.Sequential(nn.Embedding(self.vocab_size + 1, self.input_encoding_size), nn.ReLU(),
                                    nn.Dropout(self.drop_prob_lm))
         self.fc_embed = nn.Sequential(nn.Linear(self.fc_feat_size, self.rnn_size), nn.ReLU(), nn.Dropout(self.drop_prob_lm))
-        self.att_embed = nn.Sequential(nn.Linear(self.att_feat_size, self.rnn_size), nn.ReLU(), nn.Dropout(self.drop_prob_lm))
+        # use_bn = 1 (opts.py:52): BatchNorm1d over the packed valid regions first; the engine folds it into the Linear
+        self.att_embed = nn.Sequential(*(((nn.BatchNorm1d(self.att_feat_size),) if self.use_bn else ()) +
+                                         (nn.Linear(self.att_feat_size, self.rnn_size), nn.ReLU(), nn.Dropout(self.drop_prob_lm))))
         self.logit = nn.Linear(self.rnn_size, self.vocab_size + 1)
         self.ctx2att = nn.Linear(self.rnn_size, self.att_hid_size)
         self.done_beams = []

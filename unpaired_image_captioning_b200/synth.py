@@ -115,7 +115,15 @@ def init_state_dict(opt, seed=1234, peaked=0.0, eos_bias=0.0):
     sd["embed.0.weight"] = torch.randn(V, E, generator=g)
     if opt.caption_model == "topdown":
         sd["fc_embed.0.weight"], sd["fc_embed.0.bias"] = lin(H, F_)
-    sd["att_embed.0.weight"], sd["att_embed.0.bias"] = lin(H, D)
+    if getattr(opt, "use_bn", 0):   # BatchNorm1d(att_feat_size) first (models/AttModel.py:79-80): non-trivial affine + running stats
+        sd["att_embed.0.weight"] = 0.5 + torch.rand(D, generator=g)
+        sd["att_embed.0.bias"] = 0.2 * torch.randn(D, generator=g)
+        sd["att_embed.0.running_mean"] = 0.4 + 0.1 * torch.randn(D, generator=g)
+        sd["att_embed.0.running_var"] = 0.25 + 0.2 * torch.rand(D, generator=g)
+        sd["att_embed.0.num_batches_tracked"] = torch.tensor(3, dtype=torch.int64)
+        sd["att_embed.1.weight"], sd["att_embed.1.bias"] = lin(H, D)
+    else:
+        sd["att_embed.0.weight"], sd["att_embed.0.bias"] = lin(H, D)
     sd["logit.weight"], sd["logit.bias"] = lin(V, H)
     sd["ctx2att.weight"], sd["ctx2att.bias"] = lin(A, H)
     if opt.caption_model in ("att2in2", "att2all2"):
