@@ -26,6 +26,9 @@ CONFIGS = {
     # cfg 3: TopDown, 36 regions, XE training, global batch 512
     "cfg3": dict(caption_model="topdown", rnn_size=512, input_encoding_size=512, att_hid_size=512,
                  att_size=36, vocab_size=9999, seq_length=16, batch=512, beam_size=3),
+    # cfg 4: the decoder step of the pivot path (the onmt translator stays in PyTorch): TopDown, batch 256 per GPU
+    "cfg4": dict(caption_model="topdown", rnn_size=512, input_encoding_size=512, att_hid_size=512,
+                 att_size=36, vocab_size=9999, seq_length=16, batch=256, beam_size=3),
     # cfg 5: large-vocab stress, rnn 1024, vocab 30k, seq 20, beam 5
     "cfg5": dict(caption_model="att2in2", rnn_size=1024, input_encoding_size=512, att_hid_size=512,
                  att_size=196, vocab_size=29999, seq_length=20, batch=500, beam_size=5),
