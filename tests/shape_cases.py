@@ -85,3 +85,94 @@ def run_case(case, c, strict_sampling=True):
     if worst[1] > 0.2:    # a handful of rows: one ReLU / maxout unit within bf16 rounding of its kink moves a whole gradient row
         msg.append(f"grad {worst[0]} rel {worst[1]:.3f}")
     return msg, f"tf {rel:.1e} grad {worst[1]:.3f}"
+
+
+VARIANTS = ("dropout", "scheduled_sampling", "self_critical", "use_bn", "diverse_beam")
+
+
+def _grad_worst(model, ref_grads):
+    worst = ("", 0.0)
+    for name, p in model.named_parameters():
+        r = ref_grads[name]
+        if float(r.abs().max()) < 1e-7:
+            continue
+        g = p.grad if p.grad is not None else torch.zeros_like(p)
+        e = float((g.cpu() - r).norm() / r.norm())
+        if e > worst[1]:
+            worst = (name, e)
+    return worst
+
+
+def run_variant(case, c, variant):
+    """One of the optional paths (VARIANTS) at the drawn shape, against the oracle; returns (failure messages, summary)."""
+    kind, H, E, A, D, V, L, B, T, beam, use_masks = (c[k] for k in ("kind", "H", "E", "A", "D", "V", "L", "B", "T", "beam", "use_masks"))
+    use_masks = use_masks or variant == "use_bn"          # BatchNorm1d only runs on the packed (masked) form
+    kw = dict(caption_model=kind, vocab_size=V, rnn_size=H, input_encoding_size=E, att_hid_size=A, seq_length=T, fc_feat_size=D,
+              att_feat_size=D)
+    if variant == "dropout":
+        kw["drop_prob_lm"] = 0.5
+    if variant == "use_bn":
+        kw["use_bn"] = 1
+    if variant == "use_bn" and B * L == 1:
+        return [], "skipped (one value per channel: torch's BatchNorm1d raises in train mode, and so does this path)"
+    opt = synth.make_opt(**kw)
+    sd = synth.init_state_dict(opt, seed=300 + case, eos_bias=2.0 if variant == "self_critical" else 0.0,
+                               peaked=40.0 if variant == "diverse_beam" else 0.0)
+    fc, att = synth.make_features(B, L, D, seed=300 + case)
+    labels, masks = synth.make_captions(B, T, V, seed=300 + case, min_len=1)
+    am = synth.make_att_masks(B, L, seed=300 + case) if use_masks else None
+    model = uic.setup(opt)
+    model.load_state_dict(sd)
+    model = model.cuda().train()
+    cu = lambda t: None if t is None else t.cuda()
+    msg, worst = [], ("", 0.0)
+    if variant == "diverse_beam":
+        model.eval()
+        groups = [g for g in (2, 3, 4, 5) if beam % g == 0 and beam <= V]
+        if not groups:
+            return [], "skipped (beam width has no group divisor)"
+        G = groups[case % len(groups)]
+        o = {"beam_size": beam, "group_size": G, "diversity_lambda": 0.5}
+        seq, lp = model(cu(fc), None, cu(att), cu(am), opt=o, mode="sample")
+        ref_seq, ref_lp, ref_done = O.sample_beam(sd, kind, fc, att, T, beam, am, group_size=G, diversity_lambda=0.5)
+        assert seq.shape == (B, T)
+        for k in range(B):
+            assert len(model.done_beams[k]) == len(ref_done[k])
+        first = (seq[:, 0] == ref_seq[:, 0]).float().mean()
+        if float(first) < 0.5:
+            msg.append(f"diverse beam: first tokens equal {float(first):.2f}")
+        return msg, f"G={G} rows equal {float((seq == ref_seq).all(1).float().mean()):.2f}"
+    if variant == "self_critical":
+        gen, sample_lp = model(cu(fc), None, cu(att), cu(am), opt={"sample_max": 0, "seed": 5 + case}, mode="sample")
+        g = torch.Generator().manual_seed(case)
+        reward = torch.randn(B, 1, generator=g).expand(B, T).contiguous()
+        loss = uic.RewardCriterion()(sample_lp, gen, reward.cuda())
+        loss.backward()
+        ref_loss, ref_grads, ref_lp = O.rl_loss_and_grads(sd, kind, fc, att, gen.cpu(), reward, am)
+        written = sample_lp.detach().cpu() != 0
+        d = float((sample_lp.detach().cpu()[written] - ref_lp[written]).abs().max()) if written.any() else 0.0
+        if d > 2e-2:
+            msg.append(f"sample log-prob diff {d:.3e}")
+    else:
+        ref_kw = {}
+        if variant == "dropout":
+            model.dropout_seed = 4242 + case
+            ref_kw["drop"] = (0.5, 4242 + case)
+        if variant == "scheduled_sampling":
+            model.ss_prob, model.ss_seed = 0.5, 909 + case
+            from unpaired_image_captioning_b200 import autograd as AG
+            r = AG.teacher_forced_run(model, cu(fc), cu(att), cu(labels), cu(am), all_steps=True, ss=model._scheduled_sampling(torch.device("cuda")))
+            ref_kw["inputs"] = r.tokens.t().cpu()        # the oracle is fed the draws the product path made
+        loss = model(cu(fc), None, cu(att), cu(labels), cu(masks), cu(am), mode="forward_loss")
+        loss.backward()
+        if variant == "use_bn":
+            with O.bn_training():
+                ref_loss, ref_grads = O.loss_and_grads(sd, kind, fc, att, labels, masks, am)
+        else:
+            ref_loss, ref_grads = O.loss_and_grads(sd, kind, fc, att, labels, masks, am, **ref_kw)
+    if abs(float(loss.detach()) - float(ref_loss)) > 5e-3 * max(1.0, abs(float(ref_loss))):
+        msg.append(f"{variant}: loss {float(loss.detach()):.5f} vs {float(ref_loss):.5f}")
+    worst = _grad_worst(model, ref_grads)
+    if worst[1] > 0.25:
+        msg.append(f"{variant}: grad {worst[0]} rel {worst[1]:.3f}")
+    return msg, f"loss {float(loss.detach()):.4f}/{float(ref_loss):.4f} grad {worst[1]:.3f} ({worst[0]})"

@@ -13,3 +13,11 @@ CASES = shape_cases.cases(24, 7)
 def test_random_shape(case):
     msg, _ = shape_cases.run_case(case, CASES[case], strict_sampling=False)
     assert not msg, (CASES[case], msg)
+
+
+@pytest.mark.parametrize("case", range(20))
+def test_random_shape_optional_paths(case):
+    """dropout training, scheduled sampling, self-critical step, use_bn, diverse beam search -- one of them per drawn shape."""
+    c = shape_cases.cases(20, 12)[case]
+    msg, _ = shape_cases.run_variant(case, c, shape_cases.VARIANTS[case % len(shape_cases.VARIANTS)])
+    assert not msg, (c, msg)

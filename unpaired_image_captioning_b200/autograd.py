@@ -57,7 +57,9 @@ def teacher_forced_run(model, fc_feats, att_feats, seq, att_masks, save=True, al
     r.c = torch.zeros(T + 1, sl.n_state, B, H, dtype=torch.float32, device=dev)
     r.alpha = torch.empty(T, B, L, dtype=torch.float32, device=dev)
     r.h_all = torch.zeros(B, T_total, H, dtype=BF16, device=dev)
-    r.tokens = seq[:, :T].t().contiguous().long()                      # (T, B): step-major like X
+    # (T, B) step-major like X.  An explicit copy: for B == 1 the transposed view already counts as contiguous, and the
+    # scheduled-sampling draws written into r.tokens would land in the caller's label tensor
+    r.tokens = seq[:, :T].t().long().clone(memory_format=torch.contiguous_format)
     X2d = r.X.view((T + 1) * B, w.Kx)
     check(lib.uic_embed_rows(ptr(w.emb_relu), E, ptr(r.tokens), ptr(X2d[:, sl.xt[0]:]), w.Kx, T * B, E, w.V, st))
     if drop is not None:   # self.embed's nn.Dropout; rows are t * B + b
@@ -288,10 +290,14 @@ def bptt(r, dh_all):
         # the Linear ran on the folded operand W' = W diag(s), b' = b + W t (engine._fold_bn); the statistics depend on the
         # (constant) features only, so the chain rule back to W, b, gamma, beta is column-wise arithmetic on (H, D) matrices
         bn, W = feats.bn, w.w_att_f32
-        v = torch.mv(W.t(), dbe)                                          # d beta = W^T d b'
-        g["att_embed.0.bias"] = v
-        g["att_embed.0.weight"] = ((dWe * W).sum(0) - v * bn["mean"]) * bn["inv"]
-        g["att_embed.1.weight"] = dWe * bn["s"][None, :] + dbe[:, None] * bn["t"][None, :]
+        # z = W' (x - mean) + b + W beta: the (x - mean) terms take their column sums from the same bf16 d_pre that the wgrad
+        # GEMM read, so that d_pre's rounding cancels between d W' and mean * colsum even for low-variance columns (large s)
+        dbe_r = torch.zeros(H, **f32)
+        check(lib.uic_col_sum(ptr(d_pre), 1, H, ptr(dbe_r), B * L, H, st))
+        dWc = dWe - dbe_r[:, None] * bn["mean"][None, :]                  # sum_rows d_pre (x - mean)^T
+        g["att_embed.0.bias"] = torch.mv(W.t(), dbe)                      # d beta = W^T d b
+        g["att_embed.0.weight"] = (dWc * W).sum(0) * bn["inv"]
+        g["att_embed.1.weight"] = dWc * bn["s"][None, :] + dbe[:, None] * bn["beta"][None, :]
         g["att_embed.1.bias"] = dbe
     else:
         g["att_embed.0.weight"], g["att_embed.0.bias"] = dWe, dbe

@@ -233,6 +233,8 @@ class DecoderEngine:
         if att_masks is None:   # the reference hands the 3-D batch to BatchNorm1d, which reads the region axis as channels
             raise RuntimeError(f"running_mean should contain {L} elements not {D}")
         gamma, beta = bn.weight.detach().float(), bn.bias.detach().float()
+        if bn.training and B * L == 1:
+            raise ValueError(f"Expected more than 1 value per channel when training, got input size {[1, D]}")   # as torch does
         if bn.training or bn.running_mean is None:
             lens = att_masks.sum(1).to(torch.int32)
             mom = torch.zeros(2, D, dtype=torch.float64, device=x.device)
@@ -251,9 +253,11 @@ class DecoderEngine:
             mean, var = bn.running_mean.float(), bn.running_var.float()
         inv = torch.rsqrt(var + bn.eps)
         s = gamma * inv
-        t = beta - mean * s
-        b_f = torch.addmv(w.b_att_f32, w.w_att_f32, t).contiguous()
-        return _bf16(w.w_att_f32 * s[None, :]), b_f, {"s": s, "t": t, "inv": inv, "mean": mean}
+        w_bf = _bf16(w.w_att_f32 * s[None, :])
+        # b' = b + W beta - W' mean with the ROUNDED operand W': the GEMM then computes W' (x - mean) + ... and the rounding of
+        # W' cancels between the two terms even for low-variance columns (large s)
+        b_f = (torch.addmv(w.b_att_f32, w.w_att_f32, beta) - torch.mv(w_bf.float(), mean)).contiguous()
+        return w_bf, b_f, {"s": s, "inv": inv, "mean": mean, "beta": beta}
 
     def _feature_buffers(self, feats):
         """Static per-graph copies of the feature tiles (shapes of `feats`, a Features or a LazyFeatures)."""
