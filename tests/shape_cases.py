@@ -18,9 +18,16 @@ def draw(rng):
                 use_masks=rng.random() < 0.5)
 
 
-def cases(n, seed):
+def draw_big(rng):
+    """Benchmark-sized shapes: several logit chunks in training, whole-job and segmented attention plans, big GEMM grids."""
+    return dict(kind=rng.choice(["att2in2", "att2all2", "topdown"]), H=rng.choice([512, 1024]), E=512, A=512, D=2048,
+                V=rng.choice([9999, 9486]), L=rng.choice([36, 196]), B=rng.choice([64, 150, 256, 300]), T=16,
+                beam=rng.choice([3, 5]), use_masks=rng.random() < 0.5)
+
+
+def cases(n, seed, big=False):
     rng = random.Random(seed)
-    return [draw(rng) for _ in range(n)]
+    return [(draw_big if big else draw)(rng) for _ in range(n)]
 
 
 def run_case(case, c, strict_sampling=True):
