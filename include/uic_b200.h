@@ -180,13 +180,16 @@ int uic_greedy_merge(const float* stats, int parts, int64_t* seq, float* seq_log
 
 /* The whole tail of a beam-search step in one launch: uic_beam_topk_merge + uic_beam_step and, when move_state != 0,
  * uic_beam_gather + uic_embed_rows for the next step (x_dst[r, xt_col0 : xt_col0 + E] = emb_table[next_tok[r]]).
- * Same results as the four separate calls; the candidate tables stay in shared memory.  beams <= kslots. */
+ * Same results as the four separate calls; the candidate tables stay in shared memory.  beams <= kslots.
+ * src_beams: beams per image in the SOURCE buffers (stats, x_src, c_src).  Normally == beams.  At the first step only
+ * beam 0 of every image is read (rows = 1, models/CaptionModel.py:56), so the caller may run that step on ONE row per
+ * image and pass src_beams = 1 with t = 0: stats / x_src / c_src then have n_img rows and every beam forks from it. */
 int uic_beam_advance(const float* stats, int parts, int kslots, int32_t* beam_seq, float* beam_lp, float* beam_sum,
                      int32_t* done_seq, float* done_lp, double* done_p, float* done_unaug, int32_t* done_cnt,
                      int32_t* parent_row, int64_t* next_tok, int t, int seq_length, int n_img, int beams, int flags,
                      int move_state, const void* x_src, void* x_dst, int64_t ld_x, int col0_a, int ncol_a, int col0_b,
                      int ncol_b, const float* c_src, float* c_dst, int n_state, int H, const void* emb_table_bf16,
-                     int64_t ld_table, int xt_col0, int E, int V, void* stream);
+                     int64_t ld_table, int xt_col0, int E, int V, int src_beams, void* stream);
 /* Greedy analogue: uic_greedy_merge and, when x_xt_bf16 != NULL, the next step's embedding rows
  * x_xt_bf16[r, 0:E] = emb_table[token r] (pitch ld_x), in one launch.  With temperature > 0 (same temperature and
  * seed as the uic_logit_stats call of step t) the winner's key is converted back to its unperturbed log-prob. */

@@ -362,9 +362,11 @@ def test_greedy_merge_equals_greedy_step():
     torch.testing.assert_close(a[1], b[1], rtol=1e-4, atol=2e-4)
 
 
+@pytest.mark.parametrize("compact_first", [False, True])
 @pytest.mark.parametrize("B,b,kslots", [(5, 3, 3), (9, 2, 3), (4, 5, 5), (3, 8, 8), (7, 1, 1)])
-def test_beam_advance_equals_the_four_step_chain(B, b, kslots):
-    """uic_beam_advance == uic_beam_topk_merge + uic_beam_step + uic_beam_gather + uic_embed_rows, step by step."""
+def test_beam_advance_equals_the_four_step_chain(B, b, kslots, compact_first):
+    """uic_beam_advance == uic_beam_topk_merge + uic_beam_step + uic_beam_gather + uic_embed_rows, step by step.
+    compact_first: the first step's source buffers hold ONE row per image (src_beams = 1): only beam 0 is read at t = 0."""
     lib = _lib.load()
     V, Hh, E, T = 300, 64, 32, 6
     R = B * b
@@ -403,10 +405,13 @@ def test_beam_advance_equals_the_four_step_chain(B, b, kslots):
                                       ptr(u["c"][dst]), 2, R, Hh, stream()))
             check(lib.uic_embed_rows(ptr(table), E, ptr(u["tok"]), ptr(u["X"][dst]), ld_x, R, E, V, stream()))
         # fused
-        check(lib.uic_beam_advance(ptr(stats), parts, kslots, ptr(f["beam_seq"]), ptr(f["beam_lp"]), ptr(f["beam_sum"]),
+        st_f, x_f, c_f, sb = stats, f["X"][src], f["c"][src], b
+        if compact_first and t == 0:
+            st_f, x_f, c_f, sb = stats[::b].contiguous(), f["X"][src][::b].contiguous(), f["c"][src][:, ::b].contiguous(), 1
+        check(lib.uic_beam_advance(ptr(st_f), parts, kslots, ptr(f["beam_seq"]), ptr(f["beam_lp"]), ptr(f["beam_sum"]),
                                    ptr(f["done_seq"]), ptr(f["done_lp"]), ptr(f["done_p"]), ptr(f["done_unaug"]), ptr(f["done_cnt"]),
-                                   ptr(f["parent"]), ptr(f["tok"]), t, T, B, b, 0, move, ptr(f["X"][src]), ptr(f["X"][dst]), ld_x,
-                                   ga, na, gb, nb_, ptr(f["c"][src]), ptr(f["c"][dst]), 2, Hh, ptr(table), E, 0, E, V, stream()))
+                                   ptr(f["parent"]), ptr(f["tok"]), t, T, B, b, 0, move, ptr(x_f), ptr(f["X"][dst]), ld_x,
+                                   ga, na, gb, nb_, ptr(c_f), ptr(f["c"][dst]), 2, Hh, ptr(table), E, 0, E, V, sb, stream()))
         for k in ("beam_seq", "beam_lp", "beam_sum", "done_seq", "done_lp", "done_p", "done_unaug", "done_cnt", "parent", "tok"):
             assert torch.equal(u[k], f[k]), (k, t)
         if move:

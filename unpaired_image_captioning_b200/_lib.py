@@ -43,7 +43,7 @@ SIGNATURES = {
     "uic_beam_topk_merge": (_i, [_p, _i, _i, _p, _p, _i, _i, _p]),
     "uic_greedy_merge": (_i, [_p, _i, _p, _p, _p, _p, _p, _i, _i, _i, _p]),
     "uic_beam_advance": (_i, [_p, _i, _i, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p, _p, _i64, _i, _i, _i, _i, _p, _p,
-                              _i, _i, _p, _i64, _i, _i, _i, _p]),
+                              _i, _i, _p, _i64, _i, _i, _i, _i, _p]),
     "uic_greedy_advance": (_i, [_p, _i, _p, _p, _p, _p, _p, _i, _i, _i, _p, _i64, _p, _i64, _i, _i, _f, _p, _p]),
     "uic_dropout": (_i, [_p, _i, _i64, _i64, _i, _f, _p, _i, _i64, _i64, _p]),
     "uic_ss_advance": (_i, [_p, _i, _p, _i64, _f, _p, _i, _p, _i, _p, _i64, _p, _i64, _i, _i, _p]),

@@ -388,7 +388,7 @@ int uic_beam_advance(const float* stats, int parts, int kslots, int32_t* beam_se
                      int32_t* parent_row, int64_t* next_tok, int t, int seq_length, int n_img, int beams, int flags,
                      int move_state, const void* x_src, void* x_dst, int64_t ld_x, int col0_a, int ncol_a, int col0_b,
                      int ncol_b, const float* c_src, float* c_dst, int n_state, int H, const void* emb_table_bf16,
-                     int64_t ld_table, int xt_col0, int E, int V, void* stream) {
+                     int64_t ld_table, int xt_col0, int E, int V, int src_beams, void* stream) {
   REQUIRE(stats && beam_seq && beam_lp && beam_sum && done_seq && done_lp && done_p && done_unaug && done_cnt && parent_row && next_tok,
           UIC_ERR_ARG, "uic_beam_advance: null pointer");
   REQUIRE(parts > 0 && beams > 0 && seq_length > 0 && t >= 0 && t < seq_length, UIC_ERR_SHAPE,
@@ -402,7 +402,7 @@ int uic_beam_advance(const float* stats, int parts, int kslots, int32_t* beam_se
   if (n_img == 0) return 0;
   return beam_advance(stats, parts, kslots, beam_seq, beam_lp, beam_sum, done_seq, done_lp, done_p, done_unaug, done_cnt, parent_row,
                       next_tok, t, seq_length, n_img, beams, flags, move_state, x_src, x_dst, ld_x, col0_a, ncol_a, col0_b, ncol_b,
-                      c_src, c_dst, n_state, H, emb_table_bf16, ld_table, xt_col0, E, V, ST(stream));
+                      c_src, c_dst, n_state, H, emb_table_bf16, ld_table, xt_col0, E, V, src_beams, ST(stream));
 }
 
 int uic_greedy_advance(const float* stats, int parts, int64_t* seq, float* seq_logprobs, uint8_t* unfinished, int64_t* next_tok,

@@ -255,6 +255,9 @@ struct AdvanceIO {
   const float* c_src;
   float* c_dst;
   int n_state, rows, H;
+  // beams per image in the SOURCE buffers (stats, x_src, c_src).  Equal to the beam width, except at the first step when
+  // the caller ran the step on one row per image: only beam 0 is read at t = 0 (rows = 1, models/CaptionModel.py:56).
+  int src_beams;
   // next input (uic_embed_rows): x_dst[r, xt_col0 : xt_col0 + E] = table[tok[r]]
   const __nv_bfloat16* table;
   long long ld_table;
@@ -304,10 +307,11 @@ __global__ void __launch_bounds__(ADV_THREADS) beam_advance_kernel(const float* 
   const int img = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long row0 = static_cast<long long>(img) * b;
   // 1. candidates of every beam row: ys[q, c] = log-prob of the c-th best column after the beam-search edits
-  for (int q = warp; q < b; q += ADV_THREADS / 32) {
+  const long long src_row0 = static_cast<long long>(img) * io.src_beams;
+  for (int q = warp; q < io.src_beams; q += ADV_THREADS / 32) {
     float kv[KS];
     int ki[KS];
-    const RowStats rs = merge_row_stats<KS>(stats + (row0 + q) * parts * ES, parts, kv, ki);
+    const RowStats rs = merge_row_stats<KS>(stats + (src_row0 + q) * parts * ES, parts, kv, ki);
     for (int c = 0; c < b; ++c) {
       const Best best = warp_pop_best<KS>(kv, ki);
       if (lane == 0) {
@@ -330,15 +334,15 @@ __global__ void __launch_bounds__(ADV_THREADS) beam_advance_kernel(const float* 
   const int lane3 = threadIdx.x & 31;
   for (int v = warp; v < b; v += ADV_THREADS / 32) {
     const long long r = row0 + v;
-    const long long q = parent_row[r];
+    const long long q = src_row0 + (parent_row[r] - row0);   // the parent's row in the source buffers
     long long tk = next_tok[r];
     tk = tk < 0 ? 0 : (tk >= io.V ? io.V - 1 : tk);
     copy_row_bf16(io.x_dst + r * io.ld_x + io.col0_a, io.x_src + q * io.ld_x + io.col0_a, io.ncol_a, lane3, 32);
     copy_row_bf16(io.x_dst + r * io.ld_x + io.col0_b, io.x_src + q * io.ld_x + io.col0_b, io.ncol_b, lane3, 32);
     copy_row_bf16(io.x_dst + r * io.ld_x + io.xt_col0, io.table + tk * io.ld_table, io.E, lane3, 32);
     for (int s = 0; s < io.n_state; ++s)
-      copy_row_f32(io.c_dst + (static_cast<long long>(s) * io.rows + r) * io.H, io.c_src + (static_cast<long long>(s) * io.rows + q) * io.H,
-                   io.H, lane3, 32);
+      copy_row_f32(io.c_dst + (static_cast<long long>(s) * io.rows + r) * io.H,
+                   io.c_src + (static_cast<long long>(s) * gridDim.x * io.src_beams + q) * io.H, io.H, lane3, 32);
   }
   __syncthreads();
   ADV_TRACE(113);
@@ -348,11 +352,13 @@ int beam_advance(const float* stats, int parts, int kslots, int32_t* beam_seq, f
                  float* done_lp, double* done_p, float* done_unaug, int32_t* done_cnt, int32_t* parent_row, int64_t* next_tok, int t,
                  int seq_length, int n_img, int beams, int flags, int move_state, const void* x_src, void* x_dst, long long ld_x,
                  int col0_a, int ncol_a, int col0_b, int ncol_b, const float* c_src, float* c_dst, int n_state, int H,
-                 const void* table, long long ld_table, int xt_col0, int E, int V, cudaStream_t stream) {
+                 const void* table, long long ld_table, int xt_col0, int E, int V, int src_beams, cudaStream_t stream) {
+  if (src_beams != beams && !(src_beams == 1 && t == 0))
+    return set_error(UIC_ERR_ARG, "beam_advance: src_beams=%d must be beams=%d, or 1 at the first step (t=%d)", src_beams, beams, t);
   if (beams > kslots || seq_length > BEAM_T_MAX)
     return set_error(UIC_ERR_SHAPE, "beam_advance: beams=%d (kslots %d), seq_length=%d (max %d)", beams, kslots, seq_length, BEAM_T_MAX);
   AdvanceIO io{static_cast<const __nv_bfloat16*>(x_src), static_cast<__nv_bfloat16*>(x_dst), ld_x, col0_a, ncol_a, col0_b, ncol_b,
-               c_src, c_dst, n_state, n_img * beams, H, static_cast<const __nv_bfloat16*>(table), ld_table, xt_col0, E, V,
+               c_src, c_dst, n_state, n_img * beams, H, src_beams, static_cast<const __nv_bfloat16*>(table), ld_table, xt_col0, E, V,
                gemm_trace_buffer()};
   launch_begin("beam_advance", stream);
 #define UIC_ADV(KS_)                                                                                                         \

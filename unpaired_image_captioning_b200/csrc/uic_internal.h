@@ -101,7 +101,7 @@ int beam_advance(const float* stats, int parts, int kslots, int32_t* beam_seq, f
                  float* done_lp, double* done_p, float* done_unaug, int32_t* done_cnt, int32_t* parent_row, int64_t* next_tok, int t,
                  int seq_length, int n_img, int beams, int flags, int move_state, const void* x_src, void* x_dst, long long ld_x,
                  int col0_a, int ncol_a, int col0_b, int ncol_b, const float* c_src, float* c_dst, int n_state, int H,
-                 const void* table, long long ld_table, int xt_col0, int E, int V, cudaStream_t stream);
+                 const void* table, long long ld_table, int xt_col0, int E, int V, int src_beams, cudaStream_t stream);
 int greedy_advance(const float* stats, int parts, int64_t* seq, float* seq_lp, uint8_t* unfinished, int64_t* next_tok,
                    int32_t* n_unfinished, int t, int seq_length, int rows, const void* table, long long ld_table, void* x_xt,
                    long long ld_x, int E, int V, float temperature, const unsigned long long* seed, cudaStream_t stream);

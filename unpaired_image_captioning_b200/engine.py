@@ -161,6 +161,7 @@ class DecoderEngine:
         self.max_graphs = 6     # each entry owns static tile buffers (~200 MB at B=256, L=196): keep a handful of shapes
         self.use_graphs = True
         self.fused_vocab = True   # sampling: logit GEMM with fused LSE/top-k statistics (False: write logits + row kernels)
+        self.compact_first_step = True   # beam search: step 0 on one row per image (every beam forks from beam 0 there)
         self._capture_launches = 0
         self._replayed_launches = 0
         self.lib = _lib.load()
@@ -434,7 +435,7 @@ class DecoderEngine:
         R = B * b
         tk_flags = _lib.SAMPLE_DECODING_CONSTRAINT if decoding_constraint else 0
         bs_flags = _lib.BEAM_MAX_PPL if max_ppl else 0
-        key = ("beam", B, b, feats.L, T, tk_flags, bs_flags, feats.masks is not None, self.fused_vocab)
+        key = ("beam", B, b, feats.L, T, tk_flags, bs_flags, feats.masks is not None, self.fused_vocab, self.compact_first_step)
 
         def alloc():
             s = {**self._feature_buffers(feats),
@@ -452,6 +453,13 @@ class DecoderEngine:
             s["X"], s["c"], s["sl"] = self._new_state(R, dev, s["feats"], b)
             s["X2"], s["c2"] = torch.zeros_like(s["X"]), torch.zeros_like(s["c"])
             s["img_idx"] = torch.arange(R, device=dev, dtype=torch.int64) // b
+            if self.fused_vocab and 1 < b <= 8 and self.compact_first_step:
+                # the first step reads beam 0 of every image only (rows = 1, CaptionModel.py:56): run it on B rows
+                s["X0"], s["c0"], _ = self._new_state(B, dev, s["feats"], 1)
+                s["ws0"] = self._workspace(B, dev)
+                s["stats0"] = torch.empty(B, s["parts"], s["stats"].shape[2], dtype=torch.float32, device=dev)
+                s["tok0"] = torch.zeros(B, dtype=torch.int64, device=dev)
+                s["img_idx0"] = torch.arange(B, device=dev, dtype=torch.int64)
             return s
 
         def run(s):
@@ -463,9 +471,27 @@ class DecoderEngine:
             if self.kind == "topdown":
                 for X, _ in bufs:
                     check(lib.uic_embed_rows(ptr(f.fc), w.H, ptr(s["img_idx"]), ptr(X[:, sl.fc[0]:]), X.stride(0), R, w.H, B, stream()))
-            self._embed(s["tok"], bufs[0][0], sl)  # BOS for every beam row (AttModel.py:186-190)
             (ga, na), (gb, nb) = sl.gather
-            for t in range(T):
+            t_first = 0
+            if "X0" in s:
+                X0, c0 = s["X0"], s["c0"]
+                X0.zero_(); c0.zero_()
+                if self.kind == "topdown":
+                    check(lib.uic_embed_rows(ptr(f.fc), w.H, ptr(s["img_idx0"]), ptr(X0[:, sl.fc[0]:]), X0.stride(0), B, w.H, B, stream()))
+                self._embed(s["tok0"], X0, sl)   # BOS (AttModel.py:186-190)
+                h = self.core_step(X0, c0, f, s["ws0"], beams=1)
+                check(lib.uic_logit_stats(ptr(h), h.stride(0), ptr(w.w_logit), w.H, ptr(w.b_logit), None, 1,
+                                          ptr(s["stats0"]), B, w.V, w.H, s["kslots"], 1, 0.0, None, 0, stream()))
+                Xn, cn = bufs[1]
+                check(lib.uic_beam_advance(ptr(s["stats0"]), s["parts"], s["kslots"], ptr(s["beam_seq"]), ptr(s["beam_lp"]),
+                                           ptr(s["beam_sum"]), ptr(s["done_seq"]), ptr(s["done_lp"]), ptr(s["done_p"]),
+                                           ptr(s["done_unaug"]), ptr(s["done_cnt"]), ptr(s["parent"]), ptr(s["tok"]), 0, T, B, b,
+                                           bs_flags, int(1 < T), ptr(X0), ptr(Xn), Xn.stride(0), ga, na, gb, nb, ptr(c0), ptr(cn),
+                                           sl.n_state, w.H, ptr(w.emb_relu), w.E, sl.xt[0], w.E, w.V, 1, stream()))
+                t_first = 1
+            else:
+                self._embed(s["tok"], bufs[0][0], sl)  # BOS for every beam row (AttModel.py:186-190)
+            for t in range(t_first, T):
                 X, c = bufs[t % 2]
                 Xn, cn = bufs[(t + 1) % 2]
                 h = self.core_step(X, c, f, ws, beams=b)
@@ -478,7 +504,7 @@ class DecoderEngine:
                                                ptr(s["beam_sum"]), ptr(s["done_seq"]), ptr(s["done_lp"]), ptr(s["done_p"]),
                                                ptr(s["done_unaug"]), ptr(s["done_cnt"]), ptr(s["parent"]), ptr(s["tok"]), t, T, B, b,
                                                bs_flags, int(t + 1 < T), ptr(X), ptr(Xn), X.stride(0), ga, na, gb, nb, ptr(c), ptr(cn),
-                                               sl.n_state, w.H, ptr(w.emb_relu), w.E, sl.xt[0], w.E, w.V, stream()))
+                                               sl.n_state, w.H, ptr(w.emb_relu), w.E, sl.xt[0], w.E, w.V, b, stream()))
                     continue
                 else:
                     self.logits_of(h, ws["logits"])
