@@ -7,6 +7,7 @@ mkdir -p gpurun_out
 cap() {  # name regex mode skip
   timeout 600 ncu --profile-from-start off --set full --clock-control none --import-source on -k "regex:$2" -s $4 -c 1 -o gpurun_out/ncu_$1 -f python scripts/profile_step.py $3 > gpurun_out/ncu_$1.log 2>&1; echo "ncu $1 exit $?"
   ncu -i gpurun_out/ncu_$1.ncu-rep --page raw --csv > gpurun_out/ncu_$1_raw.csv 2>/dev/null
+  rm -f gpurun_out/ncu_$1.ncu-rep     # ~40 MB each: over the 64 MiB return limit; the raw page is what gets committed
   python - "$1" <<'PY'
 import csv, sys
 name = sys.argv[1]
