@@ -126,12 +126,13 @@ def _timed_wall(fn, steps, warmup, world):
 
 
 # ----------------------------------------------------------------------------------------------------
-def cpu_baseline(cfg, opt, sd, sample_images, repeats, threads):
-    """Oracle port of the reference's CPU beam search on a bounded sample of the same workload."""
+def cpu_baseline(cfg, opt, sd, fc, att, repeats, threads, gpu_seq=None):
+    """Oracle port of the reference's CPU beam search on a bounded sample of the same workload: `fc`, `att` are the first
+    images of the very batch the GPU leg decoded, and `gpu_seq` its captions for them -- they must equal the oracle's
+    (except at decision margins inside the north-star tolerance), so the timed GPU result is tied to the oracle."""
     from oracle import decoder_oracle as O
-    from unpaired_image_captioning_b200 import synth
+    from oracle.compare import compare_beam
     torch.set_num_threads(threads)
-    fc, att = synth.make_features(sample_images, cfg["att_size"], opt.att_feat_size, seed=99)
     best = float("inf")
     with torch.no_grad():
         for i in range(repeats + 1):
@@ -140,7 +141,14 @@ def cpu_baseline(cfg, opt, sd, sample_images, repeats, threads):
             dt = time.perf_counter() - t0
             if i > 0:                      # first pass is warm-up
                 best = min(best, dt)
-    return sample_images / best
+        check = None
+        if gpu_seq is not None:            # (untimed pass that also records the decision margins)
+            ref_seq, _, _, margins = O.sample_beam(sd, opt.caption_model, fc, att, opt.seq_length, cfg["beam_size"], return_margins=True)
+            exact, exempt, failures = compare_beam(gpu_seq, ref_seq, margins, tol=1e-3)
+            if failures:
+                raise AssertionError(f"bench: the timed GPU captions differ from the oracle away from near-ties: {failures}")
+            check = {"rows": int(ref_seq.size(0)), "exact": exact, "exempt_near_ties": exempt, "tol_rel": 1e-3}
+    return fc.size(0) / best, check
 
 
 def run_reference(args, world, rank):
@@ -251,6 +259,8 @@ def run_b200(args, world, rank, local):
     l0 = eng.launches()
     beam_step()                                   # one more (untimed) step just to count its kernels
     launches = eng.launches() - l0
+    # the captions of the timed plan (same graph, same inputs), kept for the oracle check beside cpu_baseline
+    timed_seq = eng.beam(eng.prepare(fc_d, att_d, lazy=True), T, beam)[0][:, 0].long().cpu()
     ms_greedy = _timed(greedy_step, args.steps, args.warmup, world)
 
     # ---- end-to-end leg through the public API, host buffers -------------------------------------
@@ -337,9 +347,11 @@ def run_b200(args, world, rank, local):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
         sample = 8
-        v = cpu_baseline(cfg, opt, sd, sample, repeats=2, threads=threads)
+        v, check = cpu_baseline(cfg, opt, sd, fc_h[:sample].clone(), att_h[:sample].clone(), repeats=2, threads=threads,
+                                gpu_seq=timed_seq[:sample])
         cpu = {"value": v, "unit": "captions/s", "cores": threads, "kind": "port",
-               "sample": f"beam-{beam} over {sample} images of the same shapes, best of 2 after warm-up, torch CPU fp32"}
+               "sample": f"beam-{beam} over the first {sample} images of the GPU leg's own batch, best of 2 after warm-up, torch CPU fp32",
+               "parity_check": check}
 
     if rank == 0:
         line = {"metric": "beam3_captions_per_s", "value": world * B / (ms_beam * 1e-3), "unit": "captions/s",

@@ -283,7 +283,9 @@ def loss_and_grads(sd, kind, fc_feats, att_feats, labels, masks, att_masks=None,
 # ------------------------------------------------------------------------------------------------
 @torch.no_grad()
 def sample_greedy(sd, kind, fc_feats, att_feats, seq_length, att_masks=None,
-                  decoding_constraint=0, return_margins=False):
+                  decoding_constraint=0, return_margins=False, relative_margins=False):
+    """return_margins: also the oracle's top-2 log-prob margin per (row, step) (test harness, for the north-star exemption
+    of near-ties); relative_margins divides it by logprob_scale of the row."""
     B = fc_feats.size(0)
     state = init_hidden(sd, kind, B)
     fc, att, p_att, masks = prepare_features(sd, kind, fc_feats, att_feats, att_masks)
@@ -301,7 +303,7 @@ def sample_greedy(sd, kind, fc_feats, att_feats, seq_length, att_masks=None,
             break
         best, it = lp.max(1)                                            # :229
         top2 = lp.topk(2, dim=1).values
-        margins[:, t] = top2[:, 0] - top2[:, 1]
+        margins[:, t] = (top2[:, 0] - top2[:, 1]) / (logprob_scale(lp) if relative_margins else 1.0)
         unfinished = (it > 0) if t == 0 else unfinished & (it > 0)      # :242-245
         it = it * unfinished.to(it.dtype)                               # :246
         seq[:, t] = it
@@ -420,8 +422,36 @@ def rl_loss_and_grads(sd, kind, fc_feats, att_feats, seq, reward, att_masks=None
 # cost structure the CPU baseline is meant to show.
 # ------------------------------------------------------------------------------------------------
 @torch.no_grad()
+def logprob_scale(lp):
+    """Per-row magnitude that a relative tolerance on a row of log-probs refers to: |log-prob| of the best entry, or half
+    the spread of the row (~ the largest |logit|) when that is bigger -- a peaked row has a best log-prob near 0 while its
+    rounding error is that of logits of magnitude spread / 2."""
+    fin = torch.where(torch.isfinite(lp), lp, lp.new_full((), float("nan")))
+    hi = torch.nan_to_num(fin, nan=-float("inf")).max(1).values
+    lo = torch.nan_to_num(fin, nan=float("inf")).min(1).values
+    return torch.maximum(hi.abs(), 0.5 * (hi - lo))
+
+
+def _rel_gaps(vals):
+    """Smallest gap between neighbours of a descending score list, relative to the scores' magnitude.
+    The -1000 offsets (finished beams, CaptionModel.py:167; UNK, :133) are bookkeeping, not log-probability mass: the
+    rounding error of a cumulative score is proportional to the sum of its per-token log-probs, i.e. to the score with
+    those offsets removed."""
+    v = vals.double()
+    v = v[torch.isfinite(v)]
+    if v.numel() < 2:
+        return float("inf")
+    eff = (v + 1000.0 * torch.round(-v / 1000.0)).abs()
+    scale = torch.maximum(eff[:-1], eff[1:]).clamp_min(1e-6)
+    return float(((v[:-1] - v[1:]) / scale).min())
+
+
 def _beam_search_one(sd, kind, state, logprobs, fc, att, p_att, masks, seq_length, beam_size,
-                     decoding_constraint, max_ppl):
+                     decoding_constraint, max_ppl, margin_out=None):
+    """margin_out (test harness only, not part of the reference): a list that receives this image's decision margins --
+    per step the smallest relative gap among the b + 1 best entries of the full (rows x V) score matrix (a perturbed
+    evaluation whose scores move by less than half of it selects the same beams in the same order), and last the gap
+    between the two best finished hypotheses.  "Relative" = divided by the magnitude of the cumulative scores compared."""
     b, T = beam_size, seq_length
     beam_seq = torch.zeros(T, b, dtype=torch.int64)                      # CaptionModel.py:109-111
     beam_lp = torch.zeros(T, b)
@@ -435,6 +465,11 @@ def _beam_search_one(sd, kind, state, logprobs, fc, att, p_att, masks, seq_lengt
         ys, ix = torch.sort(lpf, 1, True)                               # :61
         cands = []
         rows = 1 if t == 0 else b                                       # :64-66
+        if margin_out is not None:
+            full = (beam_sum[:rows, None] + lpf[:rows]).flatten()
+            top = full.topk(min(b + 1, full.numel())).values
+            if float(top[0]) > -900.0:                                  # (every beam already finished: nothing left to decide)
+                margin_out.append(_rel_gaps(top))
         for c in range(min(b, ys.size(1))):                             # c-major, q-minor :67-73
             for q in range(rows):
                 cands.append((beam_sum[q] + ys[q, c].item(), int(ix[q, c]), q, lpf[q, ix[q, c]]))
@@ -462,12 +497,14 @@ def _beam_search_one(sd, kind, state, logprobs, fc, att, p_att, masks, seq_lengt
                 beam_sum[vix] = -1000
         logprobs, state = logprobs_state(sd, kind, beam_seq[t], fc, att, p_att, masks, state)  # :171-172
     done.sort(key=lambda d: -d["p"])                                    # :175
+    if margin_out is not None and len(done) > 1:
+        margin_out.append(_rel_gaps(torch.tensor([done[0]["p"], done[1]["p"]])))
     return done[:b]
 
 
 @torch.no_grad()
 def _diverse_beam_search_one(sd, kind, state, logprobs, fc, att, p_att, masks, seq_length, beam_size, group_size,
-                             diversity_lambda, decoding_constraint, max_ppl):
+                             diversity_lambda, decoding_constraint, max_ppl, margin_out=None):
     """models/CaptionModel.py:33-177 with group_size > 1 (diverse beam search): `group_size` groups of
     bdash = beam_size // group_size beams advance staggered by one step each; group divm ranks its candidates with
     diversity_lambda subtracted once per occurrence of a token among the tokens the groups before it hold at the same
@@ -496,6 +533,11 @@ def _diverse_beam_search_one(sd, kind, state, logprobs, fc, att, p_att, masks, s
                     lpf[:, tok] -= diversity_lambda
             ys, ix = torch.sort(lpf, 1, True)                                     # :61
             rows = 1 if lt == 0 else bdash
+            if margin_out is not None:                                            # (test harness, see _beam_search_one)
+                full = (sum_t[divm][:rows, None] + lpf[:rows]).flatten()
+                top = full.topk(min(bdash + 1, full.numel())).values
+                if float(top[0]) > -900.0:
+                    margin_out.append(_rel_gaps(top))
             cands = []
             for c in range(min(bdash, ys.size(1))):
                 for q in range(rows):
@@ -527,15 +569,20 @@ def _diverse_beam_search_one(sd, kind, state, logprobs, fc, att, p_att, masks, s
             logprobs_t[divm], state_t[divm] = logprobs_state(sd, kind, seq_t[divm][lt], f[0], f[1], f[2], f[3], state_t[divm])  # :171-172
     out = []
     for g in range(G):                                                            # :175-176
-        out += sorted(done_t[g], key=lambda d: -d["p"])[:bdash]
+        ranked = sorted(done_t[g], key=lambda d: -d["p"])
+        if margin_out is not None and g == 0 and len(ranked) > 1:                 # the returned caption is group 0's best
+            margin_out.append(_rel_gaps(torch.tensor([ranked[0]["p"], ranked[1]["p"]])))
+        out += ranked[:bdash]
     return out
 
 
 @torch.no_grad()
 def sample_beam(sd, kind, fc_feats, att_feats, seq_length, beam_size=10, att_masks=None,
-                decoding_constraint=0, max_ppl=0, group_size=1, diversity_lambda=0.5):
-    """Returns (seq (B,T) int64, seqLogprobs (B,T) fp32, done_beams list-of-lists)."""
+                decoding_constraint=0, max_ppl=0, group_size=1, diversity_lambda=0.5, return_margins=False):
+    """Returns (seq (B,T) int64, seqLogprobs (B,T) fp32, done_beams list-of-lists) and, with return_margins,
+    a (B,) tensor: the smallest relative decision margin along each image's search (see _beam_search_one)."""
     B = fc_feats.size(0)
+    margins = torch.full((B,), float("inf"), dtype=torch.float64)
     fc, att, p_att, masks = prepare_features(sd, kind, fc_feats, att_feats, att_masks)
     V = sd["logit.weight"].size(0)
     assert beam_size <= V                                               # AttModel.py:173
@@ -550,15 +597,20 @@ def sample_beam(sd, kind, fc_feats, att_feats, seq_length, beam_size=10, att_mas
         m_k = masks[k:k + 1].expand(beam_size, masks.size(1)).contiguous() if masks is not None else None
         it = torch.zeros(beam_size, dtype=torch.int64)
         lp, state = logprobs_state(sd, kind, it, fc_k, att_k, p_att_k, m_k, state)   # :186-190
+        m_k_list = [] if return_margins else None
         if group_size > 1:
             done = _diverse_beam_search_one(sd, kind, state, lp, fc_k, att_k, p_att_k, m_k, seq_length, beam_size, group_size,
-                                            diversity_lambda, decoding_constraint, max_ppl)
+                                            diversity_lambda, decoding_constraint, max_ppl, m_k_list)
         else:
             done = _beam_search_one(sd, kind, state, lp, fc_k, att_k, p_att_k, m_k, seq_length,
-                                    beam_size, decoding_constraint, max_ppl)
+                                    beam_size, decoding_constraint, max_ppl, m_k_list)
+        if m_k_list:
+            margins[k] = min(m_k_list)
         done_beams.append(done)
         seq[:, k] = done[0]["seq"]                                      # :193-194
         seq_lp[:, k] = done[0]["logps"]
+    if return_margins:
+        return seq.t(), seq_lp.t(), done_beams, margins
     return seq.t(), seq_lp.t(), done_beams
 
 

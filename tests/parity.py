@@ -1,26 +1,7 @@
-"""Helpers for comparing token sequences under the north-star tolerance: ids must be identical
-except where the oracle's top-2 log-prob margin at the first differing step is inside the tolerance
-(bf16 operands flip near-ties).  After an exempted flip the rest of that
-row is not comparable (the two decoders follow different prefixes) and is skipped."""
-import torch
+"""Helpers shared by the GPU parity tests (the comparison rules themselves live in oracle/compare.py)."""
+import torch  # noqa: F401
 
-
-def compare_greedy(seq, ref_seq, ref_margins, tol):
-    """Returns (n_exact_rows, n_exempt_rows, failures[list of (row, step, margin)])."""
-    exact = exempt = 0
-    failures = []
-    for r in range(ref_seq.size(0)):
-        diff = (seq[r] != ref_seq[r]).nonzero()
-        if diff.numel() == 0:
-            exact += 1
-            continue
-        t = int(diff[0])
-        m = float(ref_margins[r, t])
-        if m < tol:
-            exempt += 1
-        else:
-            failures.append((r, t, m))
-    return exact, exempt, failures
+from oracle.compare import compare_beam, compare_greedy  # noqa: F401
 
 
 def load_model(uic, synth, sd, kind, opt_kwargs, device="cuda"):

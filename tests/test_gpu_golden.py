@@ -9,7 +9,8 @@ pytestmark = pytest.mark.gpu
 
 import unpaired_image_captioning_b200 as uic  # noqa: E402
 from unpaired_image_captioning_b200 import synth  # noqa: E402
-from parity import load_model, opt_kwargs_from_sd  # noqa: E402
+from oracle import decoder_oracle as O  # noqa: E402
+from parity import compare_beam, compare_greedy, load_model, opt_kwargs_from_sd  # noqa: E402
 
 REL = 1e-3  # north_star: log-probs and losses within 1e-3 relative
 
@@ -53,9 +54,14 @@ def test_greedy_tokens(golden, tag, o):
     if "peaked" in golden["name"] or "masked" in golden["name"]:
         assert torch.equal(seq.cpu(), ref_seq), (seq.cpu(), ref_seq)
         torch.testing.assert_close(lp.cpu(), ref_lp, rtol=5e-2, atol=5e-2)
-    else:  # flat random-init logits: near-ties may flip under bf16; prefix must agree
-        agree = (seq.cpu() == ref_seq).float().mean()
-        assert float(agree) > 0.5
+    else:  # flat random-init logits: near-ties may flip under bf16 -- only where the oracle's top-2 margin at
+        # the first differing step is inside the north-star tolerance (1e-3 relative)
+        i = golden["in"]
+        o_seq, _, margins = O.sample_greedy(golden["sd"], golden["kind"], i["fc"], i["att"], ref_seq.shape[1], i.get("att_masks"),
+                                            o.get("decoding_constraint", 0), return_margins=True, relative_margins=True)
+        assert torch.equal(o_seq, ref_seq)                       # the oracle reproduces the reference's fixture
+        exact, exempt, failures = compare_greedy(seq.cpu(), ref_seq, margins, tol=REL)
+        assert not failures, failures
 
 
 @pytest.mark.parametrize("tag,o", [("beam3", dict(beam_size=3)), ("beam3_dc", dict(beam_size=3, decoding_constraint=1)),
@@ -66,9 +72,14 @@ def test_beam_tokens(golden, tag, o):
     seq, lp = model(fc, None, att, am, opt=dict(o), mode="sample")
     assert seq.device.type == "cpu" and seq.dtype == torch.int64          # reference returns CPU tensors
     ref_seq, ref_lp = golden[tag]["seq"], golden[tag]["lp"]
+    i = golden["in"]
+    o_seq, _, _, margins = O.sample_beam(golden["sd"], golden["kind"], i["fc"], i["att"], ref_seq.shape[1], o["beam_size"],
+                                         i.get("att_masks"), o.get("decoding_constraint", 0), o.get("max_ppl", 0), return_margins=True)
+    assert torch.equal(o_seq, ref_seq)                           # the oracle reproduces the reference's fixture
+    exact, exempt, failures = compare_beam(seq, ref_seq, margins, tol=REL)
+    assert not failures, (failures, seq, ref_seq)
+    rows_equal = (seq == ref_seq).all(1)
     if "peaked" in golden["name"] or "masked" in golden["name"]:
-        rows_equal = (seq == ref_seq).all(1)
-        assert float(rows_equal.float().mean()) >= 0.8, (seq, ref_seq)
         torch.testing.assert_close(lp[rows_equal], ref_lp[rows_equal], rtol=5e-2, atol=5e-2)
         # done_beams: scores of the kept hypotheses
         b = o["beam_size"]
@@ -80,4 +91,4 @@ def test_beam_tokens(golden, tag, o):
             assert abs(beams[0]["p"] - float(golden[tag]["done_p"][k, 0])) < 5e-2 * max(1.0, abs(float(golden[tag]["done_p"][k, 0])))
             assert torch.equal(beams[0]["seq"], golden[tag]["done_seq"][k, 0])
     else:
-        assert seq.shape == ref_seq.shape
+        torch.testing.assert_close(lp[rows_equal], ref_lp[rows_equal], rtol=REL, atol=10 * REL)

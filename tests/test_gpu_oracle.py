@@ -8,7 +8,7 @@ pytestmark = pytest.mark.gpu
 import unpaired_image_captioning_b200 as uic  # noqa: E402
 from oracle import decoder_oracle as O  # noqa: E402
 from unpaired_image_captioning_b200 import synth  # noqa: E402
-from parity import compare_greedy  # noqa: E402
+from parity import compare_beam, compare_greedy  # noqa: E402
 
 REL = 1e-3
 
@@ -43,9 +43,9 @@ def test_teacher_forced_and_loss(kind, L, masks):
 @pytest.mark.parametrize("kind,L", [("att2in2", 196), ("att2all2", 64), ("topdown", 36)])
 def test_greedy_with_margin_exemption(kind, L):
     opt, sd, model, fc, att, *_ = _case(kind, 16, L, seed=77)
-    ref_seq, ref_lp, margins = O.sample_greedy(sd, kind, fc, att, 16, return_margins=True)
+    ref_seq, ref_lp, margins = O.sample_greedy(sd, kind, fc, att, 16, return_margins=True, relative_margins=True)
     seq, lp = model(fc.cuda(), None, att.cuda(), None, opt={"beam_size": 1}, mode="sample")
-    exact, exempt, failures = compare_greedy(seq.cpu(), ref_seq, margins, tol=2e-2)
+    exact, exempt, failures = compare_greedy(seq.cpu(), ref_seq, margins, tol=REL)
     assert not failures, failures
     assert exact >= 1
     first = (seq.cpu() == ref_seq).all(1)
@@ -54,12 +54,14 @@ def test_greedy_with_margin_exemption(kind, L):
 
 @pytest.mark.parametrize("kind,L,beam", [("att2in2", 196, 3), ("topdown", 36, 3), ("att2in2", 49, 5), ("att2all2", 49, 3)])
 def test_beam_peaked_exact(kind, L, beam):
-    """Wide-margin variant (scaled logit weights, raised EOS bias): ids must be identical."""
+    """Wide-margin variant (scaled logit weights, raised EOS bias): ids must be identical -- a differing row must sit at an
+    oracle decision margin inside the north-star tolerance."""
     opt, sd, model, fc, att, *_ = _case(kind, 6, L, seed=5, peaked=40.0, eos_bias=2.0)
-    ref_seq, ref_lp, ref_done = O.sample_beam(sd, kind, fc, att, 16, beam)
+    ref_seq, ref_lp, ref_done, margins = O.sample_beam(sd, kind, fc, att, 16, beam, return_margins=True)
     seq, lp = model(fc.cuda(), None, att.cuda(), None, opt={"beam_size": beam}, mode="sample")
+    exact, exempt, failures = compare_beam(seq, ref_seq, margins, tol=REL)
+    assert not failures, (failures, seq, ref_seq)
     rows = (seq == ref_seq).all(1)
-    assert float(rows.float().mean()) >= 0.8, (seq, ref_seq)
     torch.testing.assert_close(lp[rows], ref_lp[rows], rtol=2e-2, atol=2e-2)
 
 
@@ -73,14 +75,15 @@ def test_config5_layer_sizes_beam5_and_greedy():
     model = uic.setup(opt)
     model.load_state_dict(sd)
     model = model.cuda().eval()
-    ref_seq, ref_lp, _ = O.sample_beam(sd, "att2in2", fc, att, 20, 5)
+    ref_seq, ref_lp, _, bmargins = O.sample_beam(sd, "att2in2", fc, att, 20, 5, return_margins=True)
     seq, lp = model(fc.cuda(), None, att.cuda(), None, opt={"beam_size": 5}, mode="sample")
+    exact, exempt, failures = compare_beam(seq, ref_seq, bmargins, tol=REL)
+    assert not failures, (failures, seq, ref_seq)
     rows = (seq == ref_seq).all(1)
-    assert float(rows.float().mean()) >= 0.66, (seq, ref_seq)
     torch.testing.assert_close(lp[rows], ref_lp[rows], rtol=2e-2, atol=2e-2)
-    g_ref, g_lp, margins = O.sample_greedy(sd, "att2in2", fc, att, 20, return_margins=True)
+    g_ref, g_lp, margins = O.sample_greedy(sd, "att2in2", fc, att, 20, return_margins=True, relative_margins=True)
     g_seq, g_lpc = model(fc.cuda(), None, att.cuda(), None, opt={"beam_size": 1}, mode="sample")
-    exact, exempt, failures = compare_greedy(g_seq.cpu(), g_ref, margins, tol=2e-2)
+    exact, exempt, failures = compare_greedy(g_seq.cpu(), g_ref, margins, tol=REL)
     assert not failures, failures
     assert exact >= 1
 
@@ -101,10 +104,11 @@ def test_beam10_default_and_unfused_paths():
     (the fused statistics keep at most 8 candidates per part); the same kernels must also reproduce the fused path's
     beam-3 and greedy results when the fusion is switched off."""
     opt, sd, model, fc, att, *_ = _case("att2in2", 5, 49, seed=5, peaked=40.0, eos_bias=2.0)
-    ref_seq, ref_lp, _ = O.sample_beam(sd, "att2in2", fc, att, 16, 10)
+    ref_seq, ref_lp, _, margins = O.sample_beam(sd, "att2in2", fc, att, 16, 10, return_margins=True)
     seq, lp = model(fc.cuda(), None, att.cuda(), None, opt={"beam_size": 10}, mode="sample")
+    exact, exempt, failures = compare_beam(seq, ref_seq, margins, tol=REL)
+    assert not failures, (failures, seq, ref_seq)
     rows = (seq == ref_seq).all(1)
-    assert float(rows.float().mean()) >= 0.8, (seq, ref_seq)
     torch.testing.assert_close(lp[rows], ref_lp[rows], rtol=2e-2, atol=2e-2)
     assert len(model.done_beams[0]) <= 10
     fused = [model(fc.cuda(), None, att.cuda(), None, opt={"beam_size": b}, mode="sample") for b in (3, 1)]
@@ -124,22 +128,23 @@ def test_diverse_beam_search(kind, beam, groups, lam, dc, ppl):
     """group_size > 1 (models/CaptionModel.py:36-45,100-177): groups run staggered, later groups are penalised for
     repeating the earlier groups' tokens; done_beams is the groups' lists one after the other."""
     opt, sd, model, fc, att, *_ = _case(kind, 5, 36, seed=7, peaked=40.0, eos_bias=2.0)
-    ref_seq, ref_lp, ref_done = O.sample_beam(sd, kind, fc, att, 16, beam, decoding_constraint=dc, max_ppl=ppl, group_size=groups,
-                                              diversity_lambda=lam)
+    ref_seq, ref_lp, ref_done, bmargins = O.sample_beam(sd, kind, fc, att, 16, beam, decoding_constraint=dc, max_ppl=ppl,
+                                                        group_size=groups, diversity_lambda=lam, return_margins=True)
     o = {"beam_size": beam, "group_size": groups, "diversity_lambda": lam, "decoding_constraint": dc, "max_ppl": ppl}
     seq, lp = model(fc.cuda(), None, att.cuda(), None, opt=o, mode="sample")
     rows = (seq == ref_seq).all(1)
     if beam == groups:
         # one beam per group: the first group IS greedy decoding, which cannot recover from a flipped near-tie the way a wider
         # beam does -- exempt near-ties like the greedy test, and require identity with the device's own greedy path
-        g_ref, _, margins = O.sample_greedy(sd, kind, fc, att, 16, return_margins=True)
+        g_ref, _, margins = O.sample_greedy(sd, kind, fc, att, 16, return_margins=True, relative_margins=True)
         assert torch.equal(g_ref, ref_seq)
-        exact, exempt, failures = compare_greedy(seq.cpu(), ref_seq, margins, tol=2e-2)
+        exact, exempt, failures = compare_greedy(seq.cpu(), ref_seq, margins, tol=REL)
         assert not failures, failures
         g_seq, _ = model(fc.cuda(), None, att.cuda(), None, opt={"beam_size": 1}, mode="sample")
         assert torch.equal(g_seq.cpu(), seq.cpu())
     else:
-        assert float(rows.float().mean()) >= 0.8, (seq, ref_seq)
+        exact, exempt, failures = compare_beam(seq, ref_seq, bmargins, tol=REL)
+        assert not failures, (failures, seq, ref_seq)
     torch.testing.assert_close(lp[rows], ref_lp[rows], rtol=2e-2, atol=2e-2)
     same = total = 0
     for k in range(5):
@@ -151,7 +156,8 @@ def test_diverse_beam_search(kind, beam, groups, lam, dc, ppl):
                 same += 1
                 assert abs(a["p"] - float(b["p"])) <= 2e-2 * max(1.0, abs(float(b["p"])))
                 assert abs(a["unaug_p"] - float(b["unaug_p"])) <= 2e-2 * max(1.0, abs(float(b["unaug_p"])))
-    assert same >= (0.5 if beam == groups else 0.7) * total, (same, total)
+    # (hypotheses of an image whose search took a different branch at an exempted near-tie differ as a whole list)
+    assert same >= int(rows.sum()) * len(ref_done[0]) * 0.5, (same, total)
     # a replay of the captured loop gives the same tables
     seq2, lp2 = model(fc.cuda(), None, att.cuda(), None, opt=o, mode="sample")
     assert torch.equal(seq, seq2) and torch.equal(lp, lp2)

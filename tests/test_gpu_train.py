@@ -149,7 +149,8 @@ def test_use_bn_batchnorm_folded_into_att_embed(kind):
     model.load_state_dict(peaked)
     model.eval()
     sd2 = {k: v.detach().cpu() for k, v in model.state_dict().items()}
-    ref_seq, ref_lp, _ = O.sample_beam(sd2, kind, fc, att, 10, 3, am)
+    ref_seq, ref_lp, _, margins = O.sample_beam(sd2, kind, fc, att, 10, 3, am, return_margins=True)
     seq, lp = model(cu(fc), None, cu(att), cu(am), opt={"beam_size": 3}, mode="sample")
-    rows = (seq == ref_seq).all(1)
-    assert float(rows.float().mean()) >= 0.75, (seq, ref_seq)
+    from parity import compare_beam
+    exact, exempt, failures = compare_beam(seq, ref_seq, margins, tol=1e-3)
+    assert not failures, (failures, seq, ref_seq)
