@@ -36,7 +36,9 @@ extern "C" {
 #define UIC_GEMM_ACCUMULATE 2   /* c_f32 += result (used for gradient accumulation) */
 #define UIC_GEMM_A_MN_MAJOR 4   /* A is stored [K, M] row-major instead of [M, K] */
 #define UIC_GEMM_B_MN_MAJOR 8   /* B is stored [K, N] row-major instead of [N, K] */
-#define UIC_GEMM_OUT_F16 16     /* the 16-bit output buffer receives IEEE fp16 instead of bf16 (p_att tiles) */
+#define UIC_GEMM_OUT_F16 16     /* the 16-bit output buffer receives IEEE fp16 instead of bf16 */
+#define UIC_GEMM_A_STREAM 32    /* A is read once (raw features): load it with the L2 evict-first hint */
+#define UIC_GEMM_B_STREAM 64    /* B is read once: evict-first (default: K-major B up to 32 MB is a weight, kept evict-last) */
 
 /* sampling flags (uic_greedy_step / uic_row_topk) */
 #define UIC_SAMPLE_DECODING_CONSTRAINT 1 /* -inf on the previous token (AttModel.py:220-223, CaptionModel.py:130-131) */
@@ -76,9 +78,10 @@ int uic_gemm_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, float*
 
 /* Same, with the attention-operand epilogue: when exp_scale != 0, output columns >= exp_col0 become
  * exp_scale * exp(2 x).  The additive attention needs tanh(p_att + att_h) for every (region, unit,
- * beam, step); with E = exp(2 p_att)/16 stored once per image (ctx2att, fp16) and
- * F = 16 exp(2 att_h) produced by the h2att projection each step, tanh(p + a) = 1 - 2 / (E F + 1)
- * costs one FMA and (a share of) one reciprocal instead of one MUFU.TANH (a quarter-rate op). */
+ * beam, step); with E = exp(2 p_att) stored once per image (ctx2att, a bf16 tile: fp32's exponent
+ * range, so no p_att saturates it) and F = exp(2 att_h) produced by the h2att projection each step,
+ * tanh(p + a) = 1 - 2 / (E F + 1) costs one FMA and (a share of) one reciprocal instead of one
+ * MUFU.TANH (a quarter-rate op).  The exponentials are capped at 2^60 (|x| <= 20.8). */
 int uic_gemm_bf16_ex(const void* A, int64_t lda, const void* B, int64_t ldb, float* c_f32, int64_t ldc, void* c_16, int64_t ldc16,
                      const float* bias, int M, int N, int K, int flags, int exp_col0, float exp_scale, void* stream);
 

@@ -58,7 +58,7 @@ def run_case(case, c, strict_sampling=True):
     g_ref, g_lp, margins = O.sample_greedy(sd_peaked, kind, fc, att, T, am, return_margins=True, relative_margins=True)
     g_seq, g_lpc = model(cu(fc), None, cu(att), cu(am), opt={"beam_size": 1}, mode="sample")
     assert g_seq.shape == (B, T) and g_seq.dtype == torch.int64 and g_lpc.shape == (B, T)
-    exact, exempt, failures = compare_greedy(g_seq.cpu(), g_ref, margins, tol=1e-3)
+    exact, exempt, failures = compare_greedy(g_seq.cpu(), g_ref, margins, tol=3e-3)   # (the tolerance of the log-probs above: widths down to 32 average the bf16 rounding over few terms)
     if failures:
         msg.append(f"greedy mismatches {failures[:2]}")
     if 1 < beam <= V:
@@ -70,7 +70,7 @@ def run_case(case, c, strict_sampling=True):
         if strict_sampling:
             b_ref, b_lp, _, b_margins = O.sample_beam(sd_peaked, kind, fc, att, T, beam, am, return_margins=True)
             rows = (b_seq == b_ref).all(1)
-            _, _, b_fail = compare_beam(b_seq, b_ref, b_margins, tol=1e-3)
+            _, _, b_fail = compare_beam(b_seq, b_ref, b_margins, tol=3e-3)
             if b_fail:
                 msg.append(f"beam mismatches not at a near-tie {b_fail[:2]}")
             elif rows.any() and float((b_lpc[rows] - b_lp[rows]).abs().max()) > 5e-2:

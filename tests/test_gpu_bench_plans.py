@@ -144,7 +144,7 @@ def test_att_step_fwd_launch_plans(n_img, beams, L):
     than slots (several jobs per CTA, att_h buffer rotation), and the segmented plan for comparison."""
     A = H = 512
     R = n_img * beams
-    p_att = _rand_bf16(n_img, L, A, seed=21).to(torch.float16)
+    p_att = _rand_bf16(n_img, L, A, seed=21)
     att = _rand_bf16(n_img, L, H, seed=22).abs()
     att_h = torch.randn(R, A, device=DEV)
     w = torch.randn(A, device=DEV) * 0.2
@@ -155,7 +155,7 @@ def test_att_step_fwd_launch_plans(n_img, beams, L):
     for _ in range(2):
         ctx_f.zero_()
         _lib.att_step(f, A, e_tile, att, w, None, None, 0, ctx_f, H, alpha, n_img, beams, L, A, H)
-    p_eff = 0.5 * torch.log(e_tile.float() * 16.0)
+    p_eff = _lib.tile_value(e_tile)
     for r0 in range(0, n_img, 64):                                  # reference in slabs (the tanh tensor is R x L x A fp32)
         r1 = min(n_img, r0 + 64)
         ref_ctx, ref_alpha = _att_reference(att_h[r0 * beams:r1 * beams], p_eff[r0:r1], att[r0:r1], w, None, beams)

@@ -84,7 +84,7 @@ def test_gemm_mn_major_operands(a_mn, b_mn, M, N, K):
 
 
 def test_gemm_exponential_attention_epilogue():
-    """Columns >= exp_col0 come out as scale * exp(2x); fp16 output is clamped to the fp16 range."""
+    """Columns >= exp_col0 come out as scale * exp(2x), capped at 2^60 (65504 for an fp16 output buffer)."""
     M, N, K = 70, 96, 64
     a, b = _rand_bf16(M, K, seed=31, scale=0.3), _rand_bf16(N, K, seed=32, scale=0.3)
     bias = torch.randn(N, device=DEV) * 0.1
@@ -98,6 +98,13 @@ def test_gemm_exponential_attention_epilogue():
     want = (torch.exp(2 * (ref + 6.0)) / 16).clamp(max=65504.0)
     torch.testing.assert_close(out16.float(), want, rtol=3e-3, atol=1e-3)
     assert torch.isfinite(out16.float()).all()
+    # the attention operand tile: bf16, E = exp(2 p) for |p| far outside the old fp16 window, capped at 2^60
+    tile = torch.empty(M, N, device=DEV, dtype=torch.bfloat16)
+    for shift in (-15.0, 12.0, 30.0):
+        _lib.gemm(a, b, bias + shift, out_bf16=tile, exp_col0=0, exp_scale=_lib.ATT_E_SCALE)
+        want = torch.exp(2 * (ref.double() + shift)).clamp(max=2.0 ** 60).float()
+        torch.testing.assert_close(tile.float(), want, rtol=6e-3, atol=0)
+        assert torch.isfinite(tile.float()).all() and bool((tile.float() > 0).all())
 
 
 def test_gemm_rejects_bad_arguments():
@@ -131,7 +138,7 @@ def _att_reference(att_h, p_att, att, w, masks, beams):
 def test_att_step_fwd(B, beams, L, A, H, use_masks):
     lib = _lib.load()
     R = B * beams
-    p_att, att = _rand_bf16(B, L, A, seed=11).to(torch.float16), _rand_bf16(B, L, H, seed=12).abs()
+    p_att, att = _rand_bf16(B, L, A, seed=11), _rand_bf16(B, L, H, seed=12).abs()
     att_h_full = torch.randn(R, A + 24, device=DEV)   # pitch larger than A, like the fused gate GEMM output
     att_h = att_h_full[:, 8:8 + A]
     w = torch.randn(A, device=DEV) * 0.2
@@ -142,18 +149,40 @@ def test_att_step_fwd(B, beams, L, A, H, use_masks):
     ctx_b = torch.empty(R, H, device=DEV, dtype=torch.bfloat16)
     ctx_f = torch.empty(R, H, device=DEV)
     alpha = torch.empty(R, L, device=DEV)
-    # operands in the exponential form the GEMM epilogues produce: E = exp(2 p)/16 (fp16), F = 16 exp(2 att_h)
+    # operands in the exponential form the GEMM epilogues produce: E = exp(2 p) (bf16 tile), F = exp(2 att_h)
     e_tile = _lib.exp_tile(p_att)
     f_full = (torch.exp(2.0 * att_h_full) * _lib.ATT_F_SCALE).contiguous()
     f_view = f_full[:, 8:8 + A]
     for _ in range(2):   # twice: the split-merge arrival counters must be left at zero by the kernel
         ctx_f.zero_()
         _lib.att_step(f_view, f_full.stride(0), e_tile, att, w, masks, ctx_b, H, ctx_f, H, alpha, B, beams, L, A, H)
-    p_eff = 0.5 * torch.log(e_tile.float() * 16.0)          # the value the fp16 tile actually encodes
+    p_eff = _lib.tile_value(e_tile)                         # the value the bf16 tile actually encodes
     ref_ctx, ref_alpha = _att_reference(att_h, p_eff, att, w, masks, beams)
     torch.testing.assert_close(alpha, ref_alpha, rtol=5e-3, atol=2e-5)     # tanh.approx.f32 inside the score
     torch.testing.assert_close(ctx_f, ref_ctx, rtol=5e-3, atol=5e-4)
     torch.testing.assert_close(ctx_b.float(), ref_ctx, rtol=1e-2, atol=1e-2)
+
+
+@pytest.mark.parametrize("scale_p,scale_h", [(4.0, 4.0), (8.0, 8.0), (12.0, 3.0)])
+def test_att_step_fwd_wide_operand_range(scale_p, scale_h):
+    """|p_att| and |att_h| up to ~3 sigma x scale, including pairs of opposite sign: the bf16 tile and fp32 F keep fp32's
+    exponent range, a saturated unit contributes its limit and products that overflow contribute 0, never NaN."""
+    B, beams, L, A, H = 3, 3, 50, 512, 512
+    R = B * beams
+    p_att = (_rand_bf16(B, L, A, seed=41).float() * scale_p).to(torch.bfloat16)
+    att = _rand_bf16(B, L, H, seed=42).abs()
+    att_h = torch.randn(R, A, device=DEV) * scale_h
+    att_h[:, :64] = -p_att.float()[:, 0, :64].repeat_interleave(beams, 0)       # exact cancellation against region 0
+    w = torch.randn(A, device=DEV) * 0.2
+    e_tile = _lib.exp_tile(p_att)
+    f = (torch.exp(2.0 * att_h) * _lib.ATT_F_SCALE).clamp_(max=_lib.ATT_EXP_CAP).contiguous()
+    ctx_f, alpha = torch.empty(R, H, device=DEV), torch.empty(R, L, device=DEV)
+    _lib.att_step(f, A, e_tile, att, w, None, None, 0, ctx_f, H, alpha, B, beams, L, A, H)
+    assert torch.isfinite(ctx_f).all() and torch.isfinite(alpha).all()
+    # (the reference sees what the operands encode: both are capped at 2^60, i.e. |p_att|, |att_h| <= 20.8)
+    ref_ctx, ref_alpha = _att_reference(0.5 * torch.log(f), _lib.tile_value(e_tile), att, w, None, beams)
+    torch.testing.assert_close(alpha, ref_alpha, rtol=5e-3, atol=2e-5)
+    torch.testing.assert_close(ctx_f, ref_ctx, rtol=5e-3, atol=5e-4)
 
 
 # ---------------------------------------------------------------------------------------------------

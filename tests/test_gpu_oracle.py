@@ -40,6 +40,34 @@ def test_teacher_forced_and_loss(kind, L, masks):
     assert abs(float(loss) - float(ref_loss)) < REL * float(ref_loss)
 
 
+@pytest.mark.parametrize("kind,shift", [("att2in2", 8.0), ("topdown", 8.0), ("att2in2", -9.0), ("topdown", 15.0)])
+def test_attention_operand_range(kind, shift):
+    """p_att far from zero that att_h cancels (ctx2att.bias + shift, h2att.bias - shift on half of the units): the sum
+    p_att + att_h is unchanged, so the log-probs must still match the oracle at the north-star tolerance.  The first
+    (fp16) operand tile saturated for p_att > 6.9 and flushed below -8.3; the bf16 tile covers |p_att| < 20.8."""
+    opt, sd, model, fc, att, labels, lmasks, am = _case(kind, 6, 36, seed=11)
+    sd = {k: v.clone() for k, v in sd.items()}
+    half = sd["ctx2att.bias"].numel() // 2
+    sd["ctx2att.bias"][:half] += shift
+    sd["core.attention.h2att.bias"][:half] -= shift
+    model.load_state_dict(sd)
+    ref = O.teacher_forced(sd, kind, fc, att, labels)
+    with torch.no_grad():
+        out = model(fc.cuda(), None, att.cuda(), labels.cuda())
+    sel = lmasks[:, 1:].bool()
+    rel = ((out.cpu() - ref).abs() / ref.abs().clamp_min(1.0))[sel]
+    assert float(rel.max()) < REL, float(rel.max())
+    # and the gradients flow through the same tile (BPTT recomputes tanh from it)
+    model.train()
+    ref_loss, ref_grads = O.loss_and_grads(sd, kind, fc, att, labels, lmasks)
+    loss = model(fc.cuda(), None, att.cuda(), labels.cuda(), lmasks.cuda(), None, mode="forward_loss")
+    loss.backward()
+    assert abs(float(loss.detach()) - float(ref_loss)) < REL * float(ref_loss)
+    for name in ("ctx2att.weight", "core.attention.h2att.weight", "core.attention.alpha_net.weight"):
+        g, r = dict(model.named_parameters())[name].grad.cpu(), ref_grads[name]
+        assert float((g - r).norm() / r.norm()) < 5e-2, name
+
+
 @pytest.mark.parametrize("kind,L", [("att2in2", 196), ("att2all2", 64), ("topdown", 36)])
 def test_greedy_with_margin_exemption(kind, L):
     opt, sd, model, fc, att, *_ = _case(kind, 16, L, seed=77)

@@ -38,7 +38,7 @@ def test_get_logprobs_state_steps(kind, B, L, masks):
     p_fc, p_att, p_patt, p_m = model._prepare_feature(cu(fc), cu(att), cu(am))
     assert p_att.shape == o_att.shape and p_patt.shape == o_patt.shape
     _close(p_att, o_att, 1e-2)                                               # bf16 tile
-    _close(torch.log(p_patt.float() * 16.0) / 2.0, o_patt, 2e-2)             # fp16 tile holds exp(2 p_att) / 16
+    _close(p_patt, o_patt, 2e-2)                                             # decoded from the bf16 tile exp(2 p_att)
     state, o_state = model.init_hidden(B), O.init_hidden(sd, kind, B)
     assert state[0].shape == o_state[0].shape and state[1].shape == o_state[1].shape
     it = torch.zeros(B, dtype=torch.int64)

@@ -63,7 +63,7 @@ SIGNATURES = {
     "uic_reduce_time": (_i, [_p, _i64, _i64, _i, _p, _i, _i, _i, _p]),
 }
 
-GEMM_RELU, GEMM_ACCUMULATE, GEMM_A_MN, GEMM_B_MN, GEMM_OUT_F16 = 1, 2, 4, 8, 16
+GEMM_RELU, GEMM_ACCUMULATE, GEMM_A_MN, GEMM_B_MN, GEMM_OUT_F16, GEMM_A_STREAM, GEMM_B_STREAM = 1, 2, 4, 8, 16, 32, 64
 SAMPLE_DECODING_CONSTRAINT, BEAM_MAX_PPL = 1, 2
 
 _lib = None
@@ -136,19 +136,31 @@ def _is_bf16(t):
     return t.dtype == torch.bfloat16 and t.is_cuda and t.stride(-1) == 1
 
 
-ATT_E_SCALE, ATT_F_SCALE = 1.0 / 16.0, 16.0   # E = exp(2 p_att)/16 (fp16 tile), F = 16 exp(2 att_h): E*F = exp(2(p+a))
+# Exponential operand form of the additive attention: E = exp(2 p_att) is stored once per image as a bf16 tile and
+# F = exp(2 att_h) is produced per step in fp32; tanh(p + a) = 1 - 2 / (E F + 1).  bf16 keeps fp32's exponent range, so any
+# |p_att| < 20.8 (the 2^60 cap of the GEMM epilogues) is represented with the same relative precision (2^-9 on E, i.e.
+# 2^-10 absolute on p_att) -- a first version used an fp16 tile, which saturated for p_att > 6.9 and went subnormal below -3.5.
+ATT_E_SCALE, ATT_F_SCALE = 1.0, 1.0
+ATT_EXP_CAP = float(2 ** 60)
+TILE_DTYPE = torch.bfloat16
 
 
 def exp_tile(p_att):
-    """Raw ctx2att output -> the fp16 operand tile E = exp(2 p)/16 (API-compat path only; the engine gets
-    it straight from the ctx2att GEMM epilogue)."""
-    return (torch.exp(2.0 * p_att.float()) * ATT_E_SCALE).clamp_(max=65504.0).to(torch.float16)
+    """Raw ctx2att output -> the bf16 operand tile E = exp(2 p) (API-compat path only; the engine gets it straight from
+    the ctx2att GEMM epilogue)."""
+    return (torch.exp(2.0 * p_att.float()) * ATT_E_SCALE).clamp_(max=ATT_EXP_CAP).to(TILE_DTYPE)
+
+
+def tile_value(e_tile):
+    """The p_att values an operand tile encodes."""
+    return 0.5 * torch.log(e_tile.float() / ATT_E_SCALE)
 
 
 def gemm(a, b, bias=None, out_f32=None, out_bf16=None, relu=False, accumulate=False, a_mn=False, b_mn=False,
-         exp_col0=0, exp_scale=0.0):
+         exp_col0=0, exp_scale=0.0, a_stream=False, b_stream=False):
     """D[M,N] = act(A @ B^T + bias).  `a` is (M,K) [or (K,M) if a_mn], `b` is (N,K) [or (K,N) if b_mn];
-    both 2-D bf16 views whose last stride is 1 (row pitch arbitrary)."""
+    both 2-D bf16 views whose last stride is 1 (row pitch arbitrary).  a_stream / b_stream: the operand is read once
+    (L2 evict-first hint), e.g. the raw feature matrix of the prologue."""
     if not (_is_bf16(a) and _is_bf16(b) and a.dim() == 2 and b.dim() == 2):
         raise ValueError("gemm: operands must be 2-D CUDA bfloat16 tensors with unit inner stride")
     M, K = (a.shape[1], a.shape[0]) if a_mn else a.shape
@@ -162,7 +174,8 @@ def gemm(a, b, bias=None, out_f32=None, out_bf16=None, relu=False, accumulate=Fa
     if bias is not None and (bias.dtype != torch.float32 or bias.numel() != N or not bias.is_contiguous()):
         raise ValueError("gemm: bias must be contiguous fp32 of length N")
     flags = ((GEMM_RELU if relu else 0) | (GEMM_ACCUMULATE if accumulate else 0) | (GEMM_A_MN if a_mn else 0) |
-             (GEMM_B_MN if b_mn else 0) | (GEMM_OUT_F16 if out_f16 else 0))
+             (GEMM_B_MN if b_mn else 0) | (GEMM_OUT_F16 if out_f16 else 0) | (GEMM_A_STREAM if a_stream else 0) |
+             (GEMM_B_STREAM if b_stream else 0))
     check(load().uic_gemm_bf16_ex(ptr(a), a.stride(0), ptr(b), b.stride(0), ptr(out_f32), out_f32.stride(0) if out_f32 is not None else 0,
                                   ptr(out_bf16), out_bf16.stride(0) if out_bf16 is not None else 0, ptr(bias), M, N, K, flags,
                                   int(exp_col0), float(exp_scale), stream()))
@@ -186,9 +199,9 @@ def att_workspace(n_img, beams, L, A, H, device):
 
 def att_step(att_h, ld_att_h, p_att, att, w_alpha, masks, ctx_bf16, ld_ctx_bf16, ctx_f32, ld_ctx_f32, alpha, n_img, beams, L, A, H):
     """uic_att_step_fwd with dtype checks and the cached workspace.  att_h / ctx_* may be views
-    (pass their row pitch); p_att is fp16 (n_img, L, A), att is bf16 (n_img, L, H), both contiguous."""
-    if p_att.dtype != torch.float16 or att.dtype != torch.bfloat16 or not p_att.is_contiguous() or not att.is_contiguous():
-        raise ValueError("att_step: p_att must be contiguous fp16 and att contiguous bf16")
+    (pass their row pitch); p_att is the bf16 operand tile E (n_img, L, A), att is bf16 (n_img, L, H), both contiguous."""
+    if p_att.dtype != TILE_DTYPE or att.dtype != torch.bfloat16 or not p_att.is_contiguous() or not att.is_contiguous():
+        raise ValueError("att_step: p_att (operand tile) and att must be contiguous bf16")
     ws = att_workspace(n_img, beams, L, A, H, att.device)
     check(load().uic_att_step_fwd(ptr(att_h), ld_att_h, ptr(p_att), ptr(att), ptr(w_alpha), ptr(masks), ptr(ctx_bf16), ld_ctx_bf16,
                                   ptr(ctx_f32), ld_ctx_f32, ptr(alpha), ptr(ws), ws.numel(), n_img, beams, L, A, H, stream()))

@@ -340,6 +340,7 @@ class _DecoderLossFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, grad_out):
         r, o = ctx.run, ctx.logit
+        ctx.run = ctx.logit = None   # the saved step operands die with this backward
         names, params = _param_list(r.model)
         # every gradient is linear in (d h, d W_logit, d b_logit): scaling these three by the incoming gradient
         # replaces one strided multiply per parameter (24 launches) by three
@@ -357,12 +358,14 @@ class _DecoderLogprobsFn(torch.autograd.Function):
         _logit_stage(r, None, None, None, logprobs_out=out.view(B * T_total, V), want_grad=False)
         if r.T < T_total:
             out[:, r.T:] = 0.0   # steps after the all-zero-column break stay zero (AttModel.py:123,148-151)
-        ctx.run, ctx.out = r, out
-        return out
+        ctx.run = r
+        ctx.save_for_backward(out)   # (an output kept as a plain ctx attribute would form the cycle out -> grad_fn -> ctx -> out:
+        return out                   #  330 MB at 512 x 17 x 10k freed only when the cyclic GC happens to run)
 
     @staticmethod
     def backward(ctx, dlp):
-        r, out = ctx.run, ctx.out
+        r, (out,) = ctx.run, ctx.saved_tensors
+        ctx.run = None               # the saved step operands die with this backward
         B, T_total, V = out.shape
         dlp = dlp.contiguous().float()
         if r.T < T_total:
@@ -394,6 +397,7 @@ class _DecoderTokenLogprobsFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dlp):
         r = ctx.run
+        ctx.run = None
         # d loss / d logits = (softmax - onehot) * (-d loss / d logprob): the fused XE backward with per-token weights
         weights = (-dlp).contiguous().float().view(-1)
         o = _logit_stage(r, ctx.target, weights, ctx.one, want_grad=True)

@@ -2,7 +2,7 @@
 // tiles (reference: Attention.forward, models/AttModel.py:538-558, eight separate ATen kernels and a
 // materialised (rows, L, A) tanh tensor).
 //
-// HBM-bound by design: per image and step the kernel reads p_att[i] (L x A fp16) and att[i]
+// HBM-bound by design: per image and step the kernel reads p_att[i] (L x A bf16) and att[i]
 // (L x H bf16) exactly once, no matter how many beams share the image.
 //
 // Structure (sixth iteration, see profiles/ for the ncu captures and timelines that drove it):
@@ -31,8 +31,7 @@
 //      With at least half as many jobs as CTA slots a CTA owns whole jobs and nothing is merged; smaller
 //      batches cut every job into equal segments, one CTA each, and the last warp to arrive at the job's
 //      workspace counter finishes it (threadfence reduction), column set by column set.
-#include <cuda_fp16.h>
-
+#include <cstdlib>
 #include <type_traits>
 
 #include "uic_internal.h"
@@ -49,7 +48,7 @@ constexpr int ATT_SLAB_BYTES = ATT_BATCH * 128;  // one TMA box: 16 regions x 64
 struct AttParams {
   const float* att_h;
   long long ld_att_h;
-  const __half* p_att;
+  const __nv_bfloat16* p_att;
   const __nv_bfloat16* att;
   const float* w_alpha;
   const float* masks;
@@ -58,18 +57,23 @@ struct AttParams {
   float* ctx_f32;
   long long ld_ctx_f32;
   float* alpha;
-  float* ws_partial;   // [job][segment][warp][lane][4 + 4 MT]
+  float* ws_partial;   // [cta][head | tail piece][warp][lane][4 + 4 MT]
   int* ws_counter;     // [job][ATT_WARPS], zero between launches
   int beams, L, A, H;
   int n_grp;           // beam groups per image (job = img * n_grp + grp)
   int nbpi;            // batches per image
-  int segs;            // segments per job (1: CTAs own whole jobs, no merging; > 1: one CTA per segment)
-  int items;           // jobs * segs
+  int n_batches;       // jobs * nbpi: the flat batch list the CTAs share out evenly
   int f_bufs;          // att_h buffers in shared memory (2, or 3 when every image is a single batch)
   int slab_map;        // the tensor map is the 3-D slab view: one TMA instruction stages a batch's att rows
   long long* trace;    // debug (uic_gemm_set_trace buffer): CTA 0 records globaltimer at its pipeline events
+  unsigned long long tile_policy;  // L2 eviction hint of the feature-tile loads (uic_ptx.cuh)
 };
 
+__device__ __forceinline__ void bulk_g2s_hint(uint32_t smem_dst, const void* gsrc, uint32_t bytes, uint32_t bar, uint64_t policy) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(smem_dst),
+               "l"(gsrc), "r"(bytes), "r"(bar), "l"(policy)
+               : "memory");
+}
 __device__ __forceinline__ void bulk_g2s(uint32_t smem_dst, const void* gsrc, uint32_t bytes, uint32_t bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_dst), "l"(gsrc),
                "r"(bytes), "r"(bar)
@@ -120,11 +124,10 @@ __host__ __device__ inline AttSmem att_smem_layout(int A, int H, int NB, int f_b
   return s;
 }
 
-// First batch of work item `it` (item = segment `it % segs` of job `it / segs`; a job's nbpi batches are cut into
-// `segs` nearly equal runs).
-__device__ __forceinline__ int att_item_begin(int it, int segs, int nbpi) {
-  const int job = it / segs, sg = it - job * segs;
-  return job * nbpi + (sg * nbpi) / segs;
+// CTA c owns the batches [c * n / ctas, (c + 1) * n / ctas) of the flat list (n batches): equal shares whatever the
+// number of jobs, so a job may be cut into pieces at the CTA boundaries.  The CTA that holds batch b:
+__device__ __forceinline__ int att_cta_of_batch(int b, int n_batches, int ctas) {
+  return static_cast<int>(((static_cast<long long>(b) + 1) * ctas - 1) / n_batches);
 }
 
 // Position of a batch in the job list (every warp keeps identical copies and advances them in step).
@@ -158,11 +161,10 @@ att_step_fwd_kernel(const __grid_constant__ CUtensorMap tmap_att, AttParams p) {
   pdl_launch_dependents();
   const int L = p.L, A = p.A, H = p.H;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // CTA c owns the work items [c * items / ctas, (c + 1) * items / ctas): a contiguous run of batches
-  const int item0 = static_cast<int>(static_cast<long long>(blockIdx.x) * p.items / gridDim.x);
-  const int item1 = static_cast<int>(static_cast<long long>(blockIdx.x + 1) * p.items / gridDim.x);
-  const int b_start = att_item_begin(item0, p.segs, p.nbpi);
-  const int nloc = att_item_begin(item1, p.segs, p.nbpi) - b_start;
+  // CTA c owns a contiguous, equal share of the flat batch list
+  const int b_start = static_cast<int>(static_cast<long long>(blockIdx.x) * p.n_batches / gridDim.x);
+  const int b_end = static_cast<int>(static_cast<long long>(blockIdx.x + 1) * p.n_batches / gridDim.x);
+  const int nloc = b_end - b_start;
   if (nloc <= 0) return;
 
   const AttSmem sm = att_smem_layout(A, H, NB, p.f_bufs);
@@ -213,16 +215,18 @@ att_step_fwd_kernel(const __grid_constant__ CUtensorMap tmap_att, AttParams p) {
     const uint32_t st = s_base + pr.stage * sm.stage_bytes;
     const long long l = static_cast<long long>(pr.img) * L + l0;
     mbar_expect_tx_addr(bar, n_slabs * ATT_SLAB_BYTES + nrows * A * 2 + (first ? NB * A * 4 : 0));
-    bulk_g2s(st + sm.p_off, p.p_att + l * A, nrows * A * 2, bar);
+    // the tiles are streamed once per launch: p.tile_policy marks them evict-first when they are too big to stay in L2
+    // from step to step anyway, so that they do not push the decoder weights (re-read by every step's GEMMs) out
+    bulk_g2s_hint(st + sm.p_off, p.p_att + l * A, nrows * A * 2, bar, p.tile_policy);
     if (p.slab_map) {
-      asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(st),
-                   "l"(reinterpret_cast<uint64_t>(&tmap_att)), "r"(bar), "r"(0), "r"(static_cast<int>(l)), "r"(0)
+      asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4, %5}], [%2], %6;" ::"r"(st),
+                   "l"(reinterpret_cast<uint64_t>(&tmap_att)), "r"(bar), "r"(0), "r"(static_cast<int>(l)), "r"(0), "l"(p.tile_policy)
                    : "memory");
     } else {
       for (int sl = 0; sl < n_slabs; ++sl)
-        asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+        asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(
                          st + sl * ATT_SLAB_BYTES),
-                     "l"(reinterpret_cast<uint64_t>(&tmap_att)), "r"(bar), "r"(sl * 64), "r"(static_cast<int>(l))
+                     "l"(reinterpret_cast<uint64_t>(&tmap_att)), "r"(bar), "r"(sl * 64), "r"(static_cast<int>(l)), "l"(p.tile_policy)
                      : "memory");
     }
     if (first) {
@@ -244,9 +248,10 @@ att_step_fwd_kernel(const __grid_constant__ CUtensorMap tmap_att, AttParams p) {
   ++pr_index;
 
   // ---- per-lane constants ---------------------------------------------------------------------------------
-  // tanh(p + a) = 1 - 2 / (E F + 1) with E = exp(2 p)/16 (fp16 tile) and F = 16 exp(2 att_h); the constant
-  // sum(w) drops out of the softmax, so the score is e = sum_a (-2 w_a) / (E_a F_a + 1).  One reciprocal
-  // serves a PAIR of units: w1/d1 + w2/d2 = (w1 d2 + w2 d1) / (d1 d2)   (no fp32 overflow for |att_h| < 30).
+  // tanh(p + a) = 1 - 2 / (E F + 1) with E = exp(2 p) (bf16 tile) and F = exp(2 att_h), both capped at 2^60 by their
+  // GEMM epilogues; the constant sum(w) drops out of the softmax, so the score is e = sum_a (-2 w_a) / (E_a F_a + 1).
+  // One reciprocal serves a PAIR of units: w1/d1 + w2/d2 = (w1 d2 + w2 d1) / (d1 d2).  d <= 2^120 + 1 and the numerator
+  // stay finite; when d1 d2 overflows the reciprocal is 0 and so is the term -- its limit (both tanh saturated at 1).
   float w[CA * 8];
 #pragma unroll
   for (int c = 0; c < CA; ++c)
@@ -288,10 +293,9 @@ att_step_fwd_kernel(const __grid_constant__ CUtensorMap tmap_att, AttParams p) {
           if (EXA || u0 < A)
             asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(u[0]), "=r"(u[1]) : "r"(prow + x * ATT_WARPS * A * 2 + u0 * 2));
 #pragma unroll
-          for (int k = 0; k < 2; ++k) {
-            const float2 t2 = __half22float2(*reinterpret_cast<const __half2*>(&u[k]));
-            Ef[x][c * 8 + h * 4 + 2 * k] = t2.x;
-            Ef[x][c * 8 + h * 4 + 2 * k + 1] = t2.y;
+          for (int k = 0; k < 2; ++k) {  // bf16 -> fp32 is a shift / a mask (ALU pipe; an fp16 tile cost one XU conversion per element)
+            Ef[x][c * 8 + h * 4 + 2 * k] = __uint_as_float(u[k] << 16);
+            Ef[x][c * 8 + h * 4 + 2 * k + 1] = __uint_as_float(u[k] & 0xffff0000u);
           }
         }
     float e[NR][NB];
@@ -440,17 +444,26 @@ att_step_fwd_kernel(const __grid_constant__ CUtensorMap tmap_att, AttParams p) {
 
     // ---- image finished (or the range ends inside it) -----------------------------------------------------
     if (cx.kb == p.nbpi - 1 || range_end) {
-      const int nseg = p.segs, seg = item0 - cx.job * p.segs;  // (segs > 1: this CTA owns exactly one item)
+      // A job that lies inside this CTA's share is finished here.  Otherwise it is cut into nseg pieces held by the CTAs
+      // c_first .. c_last; this one is piece `seg`, and the last piece to arrive at the job's counter merges them.
+      const int job_b0 = cx.job * p.nbpi;
+      int nseg = 1, seg = 0;
+      if (job_b0 < b_start || job_b0 + p.nbpi > b_end) {
+        const int c_first = att_cta_of_batch(job_b0, p.n_batches, gridDim.x);
+        nseg = att_cta_of_batch(job_b0 + p.nbpi - 1, p.n_batches, gridDim.x) - c_first + 1;
+        seg = static_cast<int>(blockIdx.x) - c_first;
+      }
       // statistics of the accumulator columns' beams
       float Mn[2] = {__shfl_sync(0xffffffffu, m_run, 8 * t), __shfl_sync(0xffffffffu, m_run, 8 * t + 4)};
       float Sn[2] = {__shfl_sync(0xffffffffu, s_run, 8 * t), __shfl_sync(0xffffffffu, s_run, 8 * t + 4)};
       const int n0 = 2 * t;
       bool finish = true;
       if (nseg > 1) {
-        // Every lane owns a private record of 1 + MT float4: (M0, M1, S0, S1) and its accumulators.
+        // Every lane owns a private record of 1 + MT float4: (M0, M1, S0, S1) and its accumulators.  A CTA holds at most
+        // two pieces: slot 1 = the head of a job that continues in the next CTA (piece 0), slot 0 = a later piece.
         constexpr int REC = 4 + 4 * MT;
         float4* rec = reinterpret_cast<float4*>(p.ws_partial) +
-                      (((static_cast<long long>(cx.job) * p.segs + seg) * ATT_WARPS + warp) * 32 + lane) * (REC / 4);
+                      (((static_cast<long long>(blockIdx.x) * 2 + (seg == 0 ? 1 : 0)) * ATT_WARPS + warp) * 32 + lane) * (REC / 4);
         if (n0 < NB) {
           rec[0] = make_float4(Mn[0], Mn[1], Sn[0], Sn[1]);
 #pragma unroll
@@ -468,12 +481,15 @@ att_step_fwd_kernel(const __grid_constant__ CUtensorMap tmap_att, AttParams p) {
         finish = last != 0;
         if (finish && n0 < NB) {
           __threadfence();
-          const float4* base = reinterpret_cast<const float4*>(p.ws_partial) +
-                               ((static_cast<long long>(cx.job) * p.segs * ATT_WARPS + warp) * 32 + lane) * (REC / 4);
-          const long long seg_stride = static_cast<long long>(ATT_WARPS) * 32 * (REC / 4);
+          // piece sgm lives in CTA c_first + sgm: slot 1 for the first piece, slot 0 for the others
+          const long long c_first = static_cast<long long>(blockIdx.x) - seg;
+          auto piece = [&](int sgm) {
+            return reinterpret_cast<const float4*>(p.ws_partial) +
+                   ((((c_first + sgm) * 2 + (sgm == 0 ? 1 : 0)) * ATT_WARPS + warp) * 32 + lane) * (REC / 4);
+          };
           float mx0 = -INFINITY, mx1 = -INFINITY;
           for (int sgm = 0; sgm < nseg; ++sgm) {
-            const float4 st = __ldcg(base + sgm * seg_stride);
+            const float4 st = __ldcg(piece(sgm));
             mx0 = fmaxf(mx0, st.x);
             mx1 = fmaxf(mx1, st.y);
           }
@@ -481,7 +497,7 @@ att_step_fwd_kernel(const __grid_constant__ CUtensorMap tmap_att, AttParams p) {
 #pragma unroll
           for (int q = 0; q < MT; ++q) acc[q][0] = acc[q][1] = acc[q][2] = acc[q][3] = 0.0f;
           for (int sgm = 0; sgm < nseg; ++sgm) {
-            const float4* r4 = base + sgm * seg_stride;
+            const float4* r4 = piece(sgm);
             const float4 st = __ldcg(r4);
             float4 v[MT];
 #pragma unroll
@@ -587,6 +603,17 @@ att_step_fwd_kernel(const __grid_constant__ CUtensorMap tmap_att, AttParams p) {
 }
 
 // ---- host side -------------------------------------------------------------------------------------------
+static unsigned long long att_tile_policy(long long tile_bytes) {
+  static int mode = -1;  // UIC_ATT_L2: 0 = no hint, 1 = evict-first always, default = by size
+  if (mode < 0) {
+    const char* e = getenv("UIC_ATT_L2");
+    mode = e ? atoi(e) : 2;
+  }
+  if (mode == 0) return L2_EVICT_NORMAL;
+  if (mode == 1) return L2_EVICT_FIRST;
+  return tile_bytes > (56LL << 20) ? L2_EVICT_FIRST : L2_EVICT_NORMAL;
+}
+
 static int beams_per_group(int beams) {
   if (beams <= 3) return beams;
   const int groups = (beams + 2) / 3;
@@ -594,7 +621,7 @@ static int beams_per_group(int beams) {
 }
 
 struct AttPlan {
-  int nb, groups, nbpi, ctas, segs, items, mt, f_bufs;
+  int nb, groups, nbpi, ctas, n_batches, mt, f_bufs;
 };
 
 static AttPlan make_plan(int n_img, int beams, int L, int A, int H) {
@@ -605,14 +632,11 @@ static AttPlan make_plan(int n_img, int beams, int L, int A, int H) {
   const long long jobs = static_cast<long long>(n_img) * pl.groups;
   const int per_sm = ((A + 255) / 256 <= 2 && H <= 512) ? 2 : 1;  // matches the kernel's launch bounds
   const long long slots = 148LL * per_sm;
-  // Whole jobs per CTA (no merging) unless that would leave more than half of the slots empty: then every job
-  // is cut into `segs` segments of whole batches, one CTA each.
-  long long segs = slots / (jobs > 0 ? jobs : 1);
-  segs = segs < 1 ? 1 : (segs > pl.nbpi ? pl.nbpi : segs);
-  pl.segs = static_cast<int>(segs);
-  const long long items = jobs * segs;
-  pl.items = static_cast<int>(items);
-  pl.ctas = static_cast<int>(items < slots ? items : slots);
+  // Every CTA slot gets an equal share of the flat batch list (a first version handed out whole jobs: 256 jobs on 296
+  // slots left 40 SMs with one CTA and 108 with two, and the doubly-loaded ones set the makespan).
+  const long long n_batches = jobs * pl.nbpi;
+  pl.n_batches = static_cast<int>(n_batches);
+  pl.ctas = static_cast<int>(n_batches < slots ? n_batches : slots);
   pl.mt = H <= 512 ? 4 : 8;
   pl.f_bufs = pl.nbpi == 1 ? 3 : 2;
   return pl;
@@ -622,7 +646,7 @@ long long att_step_workspace_bytes(int n_img, int beams, int L, int A, int H) {
   const AttPlan pl = make_plan(n_img, beams, L, A, H);
   const long long jobs = static_cast<long long>(n_img) * pl.groups;
   const long long counters = ((jobs * ATT_WARPS * 4 + 255) / 256) * 256;
-  return counters + (pl.segs > 1 ? jobs * pl.segs * ATT_WARPS * 32 * (4 + 4 * pl.mt) * 4 : 0);
+  return counters + static_cast<long long>(pl.ctas) * 2 * ATT_WARPS * 32 * (4 + 4 * pl.mt) * 4;
 }
 
 template <int NB, int CA, int MT, bool EXA>
@@ -678,7 +702,7 @@ int att_step_fwd(const float* att_h, long long ld_att_h, const void* p_att, cons
   AttParams p{};
   p.att_h = att_h;
   p.ld_att_h = ld_att_h;
-  p.p_att = static_cast<const __half*>(p_att);
+  p.p_att = static_cast<const __nv_bfloat16*>(p_att);
   p.att = static_cast<const __nv_bfloat16*>(att);
   p.w_alpha = w_alpha;
   p.masks = masks;
@@ -696,10 +720,13 @@ int att_step_fwd(const float* att_h, long long ld_att_h, const void* p_att, cons
   p.H = H;
   p.n_grp = pl.groups;
   p.nbpi = pl.nbpi;
-  p.segs = pl.segs;
-  p.items = pl.items;
+  p.n_batches = pl.n_batches;
   p.f_bufs = pl.f_bufs;
   p.trace = gemm_trace_buffer();
+  // Tiles that cannot stay L2-resident from one step to the next (> ~half of the 126 MB L2) are streamed evict-first;
+  // smaller tile sets (36-region features) are worth keeping, they are re-read by the next step.
+  const long long tile_bytes = static_cast<long long>(n_img) * L * (A + H) * 2;
+  p.tile_policy = att_tile_policy(tile_bytes);
   const int ca = (A + 255) / 256;
   if (H <= 512) {
     if (ca <= 1) return dispatch_nb<1, 4>(p, pl, n_img, stream);

@@ -5,7 +5,6 @@
 //   * weight gradients: one wgrad GEMM per weight over all T steps (K = T*B), MN-major operands;
 //   * the gradients w.r.t. the feature tiles (att, p_att) are NOT read-modify-written every step:
 //     each step only stores de (B, L); one pass at the end rebuilds sum_t(...) per tile element.
-#include <cuda_fp16.h>
 
 #include "uic_internal.h"
 #include "uic_ptx.cuh"
@@ -184,7 +183,7 @@ constexpr int ATTB_GROUP = 2;  // regions whose loads a warp issues before it co
 template <int C>
 __global__ void __launch_bounds__(ATTB_THREADS, C <= 2 ? 4 : 2) att_step_bwd_kernel(const float* __restrict__ dctx, long long ld_dctx,
                                                                                    const float* __restrict__ alpha,
-                                                                                   const __half* __restrict__ p_att,
+                                                                                   const __nv_bfloat16* __restrict__ p_att,
                                                                                    const __nv_bfloat16* __restrict__ att,
                                                                                    const float* __restrict__ att_h, long long ld_att_h,
                                                                                    const float* __restrict__ w_alpha, float* __restrict__ de,
@@ -197,7 +196,7 @@ __global__ void __launch_bounds__(ATTB_THREADS, C <= 2 ? 4 : 2) att_step_bwd_ker
   const int r = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const __nv_bfloat16* a_img = att + static_cast<long long>(r) * L * H;
-  const __half* p_img = p_att + static_cast<long long>(r) * L * A;
+  const __nv_bfloat16* p_img = p_att + static_cast<long long>(r) * L * A;
   const float* al = alpha + static_cast<long long>(r) * L;
 
   // phase 1: d alpha_l = <dctx, att_l>
@@ -289,8 +288,8 @@ __global__ void __launch_bounds__(ATTB_THREADS, C <= 2 ? 4 : 2) att_step_bwd_ker
         const uint32_t u[4] = {q[gi][c].x, q[gi][c].y, q[gi][c].z, q[gi][c].w};
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&u[k]));
-          // operands are E = exp(2 p)/16 and F = 16 exp(2 att_h): tanh = 1 - 2r, 1 - tanh^2 = 4 r (1 - r), r = 1/(E F + 1)
+          const float2 f = bf16x2_to_f2(u[k]);
+          // operands are E = exp(2 p) (bf16 tile) and F = exp(2 att_h): tanh = 1 - 2r, 1 - tanh^2 = 4 r (1 - r), r = 1/(E F + 1)
           const float r0 = rcp_approx(fmaf(f.x, ah[c * 8 + 2 * k], 1.0f)), r1 = rcp_approx(fmaf(f.y, ah[c * 8 + 2 * k + 1], 1.0f));
           acc[c * 8 + 2 * k] = fmaf(del, r0 * (1.0f - r0), acc[c * 8 + 2 * k]);
           acc[c * 8 + 2 * k + 1] = fmaf(del, r1 * (1.0f - r1), acc[c * 8 + 2 * k + 1]);
@@ -327,7 +326,7 @@ int att_step_bwd(const float* dctx, long long ld_dctx, const float* alpha, const
   const int chunks = ((A > H ? A : H) + 255) / 256;
   launch_begin("att_step_bwd", stream);
 #define UIC_ATTB(C_)                                                                                                          \
-  att_step_bwd_kernel<C_><<<rows, ATTB_THREADS, smem, stream>>>(dctx, ld_dctx, alpha, static_cast<const __half*>(p_att),          \
+  att_step_bwd_kernel<C_><<<rows, ATTB_THREADS, smem, stream>>>(dctx, ld_dctx, alpha, static_cast<const __nv_bfloat16*>(p_att),          \
                                                                 static_cast<const __nv_bfloat16*>(att), att_h, ld_att_h, w_alpha, \
                                                                 de, static_cast<__nv_bfloat16*>(datt_h), ld_dah, L, A, H)
   if (chunks <= 1)
@@ -352,7 +351,7 @@ constexpr int TILE_THREADS = 256;
 __global__ void __launch_bounds__(TILE_THREADS) att_tiles_bwd_kernel(
     const float* __restrict__ de_all, const float* __restrict__ alpha_all, const float* __restrict__ dctx_all,
     long long dctx_stride_t, long long ld_dctx, const float* __restrict__ att_h_all, long long ah_stride_t, long long ld_ah,
-    const __half* __restrict__ p_att, const float* __restrict__ w_alpha, float* __restrict__ datt,
+    const __nv_bfloat16* __restrict__ p_att, const float* __restrict__ w_alpha, float* __restrict__ datt,
     __nv_bfloat16* __restrict__ dp_att, float* __restrict__ dw_alpha, int T, int B, int L, int A, int H, int l_chunk) {
   extern __shared__ float sm[];
   float* s_ah = sm;                       // [T][A]
@@ -389,7 +388,7 @@ __global__ void __launch_bounds__(TILE_THREADS) att_tiles_bwd_kernel(
 #pragma unroll
       for (int u = 0; u < QU; ++u) {
         const int q = min(q0 + u, nl - 1);
-        p[u] = __half2float(p_att[(static_cast<long long>(b) * L + l0 + q) * A + a]);
+        p[u] = __bfloat162float(p_att[(static_cast<long long>(b) * L + l0 + q) * A + a]);
         acc[u] = 0.0f;
       }
       for (int t = 0; t < T; ++t) {
@@ -442,7 +441,7 @@ int att_tiles_bwd(const float* de_all, const float* alpha_all, const float* dctx
   dim3 grid(B, (L + l_chunk - 1) / l_chunk);
   launch_begin("att_tiles_bwd", stream);
   att_tiles_bwd_kernel<<<grid, TILE_THREADS, smem, stream>>>(de_all, alpha_all, dctx_all, dctx_stride_t, ld_dctx, att_h_all,
-                                                             ah_stride_t, ld_ah, static_cast<const __half*>(p_att), w_alpha,
+                                                             ah_stride_t, ld_ah, static_cast<const __nv_bfloat16*>(p_att), w_alpha,
                                                              datt, static_cast<__nv_bfloat16*>(dp_att), dw_alpha, T, B, L, A, H,
                                                              l_chunk);
   UIC_CUDA_OK(cudaGetLastError());

@@ -39,6 +39,7 @@ constexpr int BM = 128;
 constexpr int BK = 64;
 constexpr int GEMM_THREADS = 384;  // 4 control warps + 8 epilogue warps
 constexpr int EPI_WARPS = 8;
+constexpr float EXP_CAP = 1152921504606846976.0f;  // 2^60: cap of the exponential-form attention operands (attention.cu)
 constexpr int EPI_PITCH = 36;  // floats per staged row: 32 + 4 keeps every 16-byte access conflict-free
 
 struct GemmEpilogue {
@@ -69,6 +70,9 @@ struct GemmEpilogue {
   // the big operand (feature prologue: 50176 x 2048 against 512 x 2048) the m-fastest walk re-reads every A tile from HBM
   // once per column of tiles; n-fastest reads it once and finds it in L2 for the others.
   int n_fastest;
+  // L2 eviction hints of the operand loads (uic_ptx.cuh): weights re-read by every decode step are kept (evict-last),
+  // operands streamed once (raw features of the prologue) are marked evict-first
+  unsigned long long policy_a, policy_b;
 };
 
 #define UIC_TRACE(slot)                                                              \
@@ -92,7 +96,7 @@ __device__ __forceinline__ __nv_bfloat16 store16(float a, int f16) {
 }
 __device__ __forceinline__ float epi_act(float v, int col, const GemmEpilogue& ep) {
   if (ep.relu) v = fmaxf(v, 0.0f);
-  if (ep.exp_scale != 0.0f && col >= ep.exp_col0) v = fminf(ep.exp_scale * __expf(2.0f * v), ep.out_f16 ? 65504.0f : 1.0e30f);
+  if (ep.exp_scale != 0.0f && col >= ep.exp_col0) v = fminf(ep.exp_scale * __expf(2.0f * v), ep.out_f16 ? 65504.0f : EXP_CAP);
   return v;
 }
 
@@ -208,16 +212,16 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           uint8_t* sa = smem + s * L::STAGE_BYTES;
           uint8_t* sb = sa + L::A_BYTES;
           if (!A_MN) {
-            tma_load_2d(sa, &tmap_a, &full_bar[s], kb * BK, m0);
+            tma_load_2d_hint(sa, &tmap_a, &full_bar[s], kb * BK, m0, ep.policy_a);
           } else {  // A stored [K, M]: two boxes of 64 m-columns x 64 k-rows
 #pragma unroll
-            for (int i = 0; i < BM / 64; ++i) tma_load_2d(sa + i * (BK * 128), &tmap_a, &full_bar[s], m0 + 64 * i, kb * BK);
+            for (int i = 0; i < BM / 64; ++i) tma_load_2d_hint(sa + i * (BK * 128), &tmap_a, &full_bar[s], m0 + 64 * i, kb * BK, ep.policy_a);
           }
           if (!B_MN) {
-            tma_load_2d(sb, &tmap_b, &full_bar[s], kb * BK, n0);
+            tma_load_2d_hint(sb, &tmap_b, &full_bar[s], kb * BK, n0, ep.policy_b);
           } else {
 #pragma unroll
-            for (int i = 0; i < BN / 64; ++i) tma_load_2d(sb + i * (BK * 128), &tmap_b, &full_bar[s], n0 + 64 * i, kb * BK);
+            for (int i = 0; i < BN / 64; ++i) tma_load_2d_hint(sb + i * (BK * 128), &tmap_b, &full_bar[s], n0 + 64 * i, kb * BK, ep.policy_b);
           }
         }
       }
@@ -435,7 +439,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                 }
                 if (MODE == 1) { f.x = fmaxf(f.x, 0.0f); f.y = fmaxf(f.y, 0.0f); f.z = fmaxf(f.z, 0.0f); f.w = fmaxf(f.w, 0.0f); }
                 if (MODE == 2) {
-                  const float cap = ep.out_f16 ? 65504.0f : 1.0e30f;
+                  const float cap = ep.out_f16 ? 65504.0f : EXP_CAP;
                   f.x = fminf(ep.exp_scale * __expf(2.0f * f.x), cap); f.y = fminf(ep.exp_scale * __expf(2.0f * f.y), cap);
                   f.z = fminf(ep.exp_scale * __expf(2.0f * f.z), cap); f.w = fminf(ep.exp_scale * __expf(2.0f * f.w), cap);
                 }
@@ -443,7 +447,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
               } else {
                 if (MODE == 1) { f.x = fmaxf(f.x, 0.0f); f.y = fmaxf(f.y, 0.0f); f.z = fmaxf(f.z, 0.0f); f.w = fmaxf(f.w, 0.0f); }
                 if (MODE == 2) {
-                  const float cap = ep.out_f16 ? 65504.0f : 1.0e30f;
+                  const float cap = ep.out_f16 ? 65504.0f : EXP_CAP;
                   f.x = fminf(ep.exp_scale * __expf(2.0f * f.x), cap); f.y = fminf(ep.exp_scale * __expf(2.0f * f.y), cap);
                   f.z = fminf(ep.exp_scale * __expf(2.0f * f.z), cap); f.w = fminf(ep.exp_scale * __expf(2.0f * f.w), cap);
                 }
@@ -569,6 +573,26 @@ static int gemm_debug_flags() {
   return v;
 }
 
+// Operand L2 hints.  B is a weight matrix in every forward contraction of the decoder (K-major): up to 32 MB it is kept
+// evict-last, the decode loop re-reads it every step while 100 MB of feature tiles stream through L2 in between.
+// UIC_GEMM_A_STREAM / UIC_GEMM_B_STREAM mark an operand that is read once (the raw feature matrix of the prologue).
+static void gemm_l2_policies(GemmEpilogue& ep, int M, int N, int K, int flags) {
+  static int mode = -1;  // UIC_GEMM_L2=0 switches the hints off (A/B experiments)
+  if (mode < 0) {
+    const char* e = getenv("UIC_GEMM_L2");
+    mode = e ? atoi(e) : 1;
+  }
+  ep.policy_a = ep.policy_b = L2_EVICT_NORMAL;
+  if (mode == 0) return;
+  const bool b_weight = !(flags & UIC_GEMM_B_MN_MAJOR) && !(flags & UIC_GEMM_A_MN_MAJOR);
+  if (flags & UIC_GEMM_A_STREAM) ep.policy_a = L2_EVICT_FIRST;
+  if (flags & UIC_GEMM_B_STREAM)
+    ep.policy_b = L2_EVICT_FIRST;
+  else if (b_weight && static_cast<long long>(N) * K * 2 <= (32LL << 20))
+    ep.policy_b = L2_EVICT_LAST;
+  (void)M;
+}
+
 static int sm_count() {
   static int n = 0;
   if (n == 0) {
@@ -618,6 +642,7 @@ int gemm_bf16(const void* A, long long lda, const void* B, long long ldb, float*
                   (flags & UIC_GEMM_ACCUMULATE) ? 1 : 0, (flags & UIC_GEMM_OUT_F16) ? 1 : 0, exp_col0, exp_scale, gemm_trace_buffer(), gemm_debug_flags(), nullptr, nullptr, 0, 0, -1};
   // tile walk: keep the bigger operand's tile hot (see GemmEpilogue::n_fastest); the smaller one must fit L2 comfortably
   ep.n_fastest = (M > N && static_cast<long long>(N) * K * 2 <= (32LL << 20)) ? 1 : 0;
+  gemm_l2_policies(ep, M, N, K, flags);
   if (gemm_impl() == GEMM_IMPL_SIMT) {
     dim3 grid((N + 15) / 16, (M + 15) / 16), block(16, 16);
     launch_begin("gemm_bf16_simt", stream);
@@ -680,6 +705,7 @@ int logit_stats(const void* A, long long lda, const void* B, long long ldb, cons
     return set_error(UIC_ERR_ALIGN, "logit_stats: operands and stats must be 16-byte aligned with pitches that are multiples of 8 elements");
   GemmEpilogue ep{nullptr, 0, nullptr, 0, bias, 0, 0, 0, 0, 0.0f, nullptr, 0, stats, banned, banned_stride, logit_stats_parts(N), unk_suppress ? N - 1 : -1,
                   temperature > 0.0f ? 1 : 0, temperature > 0.0f ? 1.0f / temperature : 1.0f, seed, step};
+  gemm_l2_policies(ep, M, N, K, 0);
   CUtensorMap ta, tb;
   int rc = get_tensor_map_bf16(&ta, A, M, K, lda, BM, 64);
   if (rc) return rc;

@@ -167,6 +167,13 @@ class DecoderEngine:
         self.lib = _lib.load()
 
     # ---- weights ---------------------------------------------------------------------------------
+    def invalidate(self):
+        """Drop the packed bf16 operand copies and the decode graphs built from them.  Staleness is normally detected through
+        the parameters' (data_ptr, version) signature, which a CUDA-graph replay that updates parameters in place does NOT
+        bump: whoever replays such a graph (train_bench.GraphedTrainStep) calls this."""
+        self._packed = None
+        self._graphs.clear()
+
     @property
     def w(self):
         if self._packed is None or self._packed.signature != PackedWeights.signature_of(self.model):
@@ -197,14 +204,14 @@ class DecoderEngine:
         w_ae, b_ae, bn = w.w_att_embed, w.b_att_embed, None
         if w.use_bn:
             w_ae, b_ae, bn = self._fold_bn(x, att_masks, B, L)
-        gemm(x, w_ae, b_ae, out_bf16=att, relu=True)
+        gemm(x, w_ae, b_ae, out_bf16=att, relu=True, a_stream=True)   # the raw features are read once
         if att_masks is not None:
             check(self.lib.uic_zero_padded_rows(ptr(att), ptr(att_masks), B, L, H, stream()))
         if drop is not None:   # att_embed's nn.Dropout (training mode, AttModel.py:79-84): ctx2att sees the dropped tile
             _lib.dropout(att, drop, _lib.DROP_ATT)
-        # p_att is stored in the exponential operand form E = exp(2 p_att)/16 (fp16): the step kernel then
+        # p_att is stored in the exponential operand form E = exp(2 p_att) (bf16, see _lib.ATT_E_SCALE): the step kernel then
         # gets tanh(p_att + att_h) = 1 - 2/(E F + 1) from an FMA and a shared reciprocal (MUFU.TANH is quarter rate)
-        p_att = torch.empty(B * L, A, dtype=torch.float16, device=x.device) if out is None else out.p_att.view(B * L, A)
+        p_att = torch.empty(B * L, A, dtype=_lib.TILE_DTYPE, device=x.device) if out is None else out.p_att.view(B * L, A)
         gemm(att, w.w_ctx2att, w.b_ctx2att, out_bf16=p_att, exp_col0=0, exp_scale=_lib.ATT_E_SCALE)
         fc = None
         if self.kind == "topdown":
@@ -263,7 +270,7 @@ class DecoderEngine:
     def _feature_buffers(self, feats):
         """Static per-graph copies of the feature tiles (shapes of `feats`, a Features or a LazyFeatures)."""
         w, dev, B, L = self.w, feats.device, feats.B, feats.L
-        return {"att": torch.empty(B, L, w.H, dtype=BF16, device=dev), "p_att": torch.empty(B, L, w.A, dtype=torch.float16, device=dev),
+        return {"att": torch.empty(B, L, w.H, dtype=BF16, device=dev), "p_att": torch.empty(B, L, w.A, dtype=_lib.TILE_DTYPE, device=dev),
                 "fc": torch.empty(B, w.H, dtype=BF16, device=dev) if self.kind == "topdown" else None,
                 "masks": None if feats.masks is None else torch.empty(B, L, dtype=torch.float32, device=dev)}
 
@@ -301,7 +308,7 @@ class DecoderEngine:
 
         if self.kind == "att2in2":
             S = ws["S"]
-            gemm(X, w.w1, w.b1, out_f32=S, exp_col0=5 * H, exp_scale=_lib.ATT_F_SCALE)   # S[:, 5H:] = F = 16 exp(2 att_h)
+            gemm(X, w.w1, w.b1, out_f32=S, exp_col0=5 * H, exp_scale=_lib.ATT_F_SCALE)   # S[:, 5H:] = F = exp(2 att_h)
             _lib.att_step(S[:, 5 * H:], S.stride(0), feats.p_att, feats.att, w.w_alpha, feats.masks, ws["ctx"], H, None, 0, alpha,
                           feats.B, beams, feats.L, A, H)
             if w.all_gates:   # S[:, :5H] += a2h(ctx): the saved sums already hold everything the cell (and its backward) needs

@@ -51,10 +51,9 @@ class Attention(nn.Module):
         if R % n_img:
             raise ValueError(f"Attention: {R} rows do not divide over {n_img} images")
         att_b = att if att.dtype == BF16 else _lib.cast_bf16(att.reshape(-1, H).float())
-        # operand tiles: fp16 tensors are already in the engine's exponential form E = exp(2 p_att)/16
-        # (what _prepare_feature returns); anything else is a raw ctx2att output and is converted here
+        # p_att_feats is the ctx2att output like in the reference; the kernel takes it in the exponential operand form
         p3 = p_att_feats.reshape(n_img, L, A)
-        p_b = (p3 if p3.dtype == torch.float16 else _lib.exp_tile(p3)).contiguous()
+        p_b = _lib.exp_tile(p3).contiguous()
         att_h = torch.empty(R, A, device=h.device)   # F = 16 exp(2 (h2att(h) + b))
         _lib.gemm(_lib.cast_bf16(h.float().contiguous()), _lib.cast_bf16(self.h2att.weight.detach()),
                   self.h2att.bias.detach().float().contiguous(), out_f32=att_h, exp_col0=0, exp_scale=_lib.ATT_F_SCALE)
@@ -185,12 +184,12 @@ class AttModel(CaptionModel):
         return (float(self.drop_prob_lm), seed)
 
     def _prepare_feature(self, fc_feats, att_feats, att_masks):
-        """Returns (fc, att, p_att, masks) like the reference.  att is the bf16 operand tile; p_att is the
-        fp16 tile in the engine's exponential form exp(2 * ctx2att(att)) / 16 (see engine.prepare) and is
-        accepted as such by get_logprobs_state / core / core.attention."""
+        """Returns (fc, att, p_att, masks) like the reference.  att is the bf16 operand tile; p_att is ctx2att(att) in fp32,
+        decoded from the engine's exponential operand tile (engine.prepare), so the single-step API below
+        (get_logprobs_state / core / core.attention) takes exactly the reference's tensors."""
         f = self.engine.prepare(fc_feats, att_feats, att_masks)
         fc = fc_feats if self.kind == "att2in2" else f.fc
-        return fc, f.att, f.p_att, f.masks
+        return fc, f.att, _lib.tile_value(f.p_att), f.masks
 
     # ---- teacher-forced forward -----------------------------------------------------------------------
     def _scheduled_sampling(self, device):
@@ -252,7 +251,7 @@ class AttModel(CaptionModel):
         # the reference's beam path hands in per-beam expanded copies (AttModel.py:181-184): rows == n_img
         att_b = att3 if att3.dtype == BF16 else _lib.cast_bf16(att3.reshape(-1, H).float()).view(n_img, L, H)
         p3 = p_att.reshape(n_img, L, A)
-        p_b = p3 if p3.dtype == torch.float16 else _lib.exp_tile(p3)   # fp16 = already E = exp(2 p_att)/16
+        p_b = _lib.exp_tile(p3)                                        # ctx2att output -> operand tile E = exp(2 p_att)
         masks = None if att_masks is None else att_masks.reshape(n_img, L).float().contiguous()
         fc_b = None
         if self.kind == "topdown":

@@ -64,6 +64,10 @@ class GraphedTrainStep:
 
     def __call__(self):
         self.graph.replay()
+        # The replay updated the parameters in place without bumping their version counters, and the operand copies the
+        # captured step packs for itself are one update behind afterwards: eval / sampling calls on this model must not
+        # reuse them (or decode graphs built from them).
+        self.st["model"].engine.invalidate()
         return self.loss
 
 
