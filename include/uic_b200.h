@@ -135,6 +135,22 @@ int uic_lstm_maxout_fwd(const float* sums, int64_t ld_sums, const float* a2c, in
 /* torch.nn.LSTMCell pointwise, gate order i,f,g,o (models/AttModel.py:434,441): gates (rows x 4H). */
 int uic_lstm_cell_fwd(const float* gates, int64_t ld_gates, const float* c_prev, float* c_out, float* h_f32,
                       void* h_bf16_a, int64_t ld_ha, void* h_bf16_b, int64_t ld_hb, int rows, int H, void* stream);
+/* The same two cells with per-row ADDENDS to the gate pre-activations, for the decode loops:
+ *   add_tok (V x n_gates*H fp32, pitch ld_add_tok) is gathered by tok[row] -- the input-word term
+ *     i2h(relu(embed(it))) (models/AttModel.py:160,584) resp. the xt columns of att_lstm.weight_ih (:432-434) is a
+ *     function of the token alone, so it is tabulated once per weight version and the per-step gate GEMM contracts
+ *     over the recurrent columns only;
+ *   add_grp (rows/group x n_gates*H fp32) is indexed by row / group -- a term that is constant per image (the fc
+ *     columns of att_lstm.weight_ih) and shared by the `group` beams of the image.
+ * Either table may be NULL.  Out-of-range tokens are clamped to [0, V). */
+int uic_lstm_maxout_fwd_add(const float* sums, int64_t ld_sums, const float* a2c, int64_t ld_a2c, const float* c_prev,
+                            float* c_out, float* h_f32, void* h_bf16_a, int64_t ld_ha, void* h_bf16_b, int64_t ld_hb, int rows,
+                            int H, const float* add_tok, int64_t ld_add_tok, const int64_t* tok, int V, const float* add_grp,
+                            int64_t ld_add_grp, int group, void* stream);
+int uic_lstm_cell_fwd_add(const float* gates, int64_t ld_gates, const float* c_prev, float* c_out, float* h_f32,
+                          void* h_bf16_a, int64_t ld_ha, void* h_bf16_b, int64_t ld_hb, int rows, int H, const float* add_tok,
+                          int64_t ld_add_tok, const int64_t* tok, int V, const float* add_grp, int64_t ld_add_grp, int group,
+                          void* stream);
 
 /* ---- vocabulary softmax family --------------------------------------------------------------- */
 /* out[r, :] = log_softmax(logits[r, :]) (F.log_softmax, models/AttModel.py:163). */

@@ -53,6 +53,24 @@ for M, N, K in [(768, 3072, 1024), (768, 1024, 512), (768, 10000, 512), (256, 25
     ref = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
     t_cublas = time_graph(lambda: torch.matmul(a, b.t(), out=ref))
     print(f"gemm {M}x{N}x{K}: in-graph warm {t_warm:.1f} us, after eviction {t_cold:.1f} us, cuBLAS(bf16 out, warm) {t_cublas:.1f} us")
+# the fused-statistics variant of the logit GEMM (what the decode loops launch)
+M, N, K = 768, 10000, 512
+a = torch.randn(M, K, device="cuda").to(torch.bfloat16)
+b = (torch.randn(N, K, device="cuda") * 0.05).to(torch.bfloat16)
+bias = torch.randn(N, device="cuda")
+parts = int(lib.uic_logit_stats_parts(N))
+for ks in (1, 3):
+    stats = torch.empty(M, parts, int(lib.uic_logit_stats_entry_floats(ks)), device="cuda")
+
+    def st():
+        _lib.check(lib.uic_logit_stats(a.data_ptr(), K, b.data_ptr(), K, bias.data_ptr(), None, 1, stats.data_ptr(), M, N, K, ks, 1, 0.0, None, 0,
+                                       torch.cuda.current_stream().cuda_stream))
+
+    def st_cold():
+        evict.zero_()
+        st()
+
+    print(f"logit_stats {M}x{N}x{K} kslots={ks}: in-graph warm {time_graph(st):.1f} us, after eviction {time_graph(st_cold) - t_evict:.1f} us")
 if len(sys.argv) > 1:
     sys.exit(0)
 B, beams, L, A, H = 256, 3, 196, 512, 512

@@ -116,6 +116,22 @@ def test_config5_layer_sizes_beam5_and_greedy():
     assert exact >= 1
 
 
+@pytest.mark.parametrize("kind", ["att2in2", "att2all2"])
+def test_gate_table_decode_equals_the_full_gemm(kind):
+    """Decode loops take the input-word gate term from the (V, 5H) table (engine.use_gate_table): same captions and
+    log-probs as contracting the E embedding columns in every step's GEMM (two fp32 sums of the same bf16 products)."""
+    opt, sd, model, fc, att, *_ = _case(kind, 7, 49, seed=5, peaked=40.0, eos_bias=2.0)
+    outs = {}
+    for use in (True, False):
+        model.engine.use_gate_table = use
+        outs[use] = [model(fc.cuda(), None, att.cuda(), None, opt=o, mode="sample")
+                     for o in ({"beam_size": 3}, {"beam_size": 1}, {"beam_size": 4, "group_size": 2})]
+    model.engine.use_gate_table = True
+    for (s_a, lp_a), (s_b, lp_b) in zip(outs[True], outs[False]):
+        assert torch.equal(s_a.cpu(), s_b.cpu())
+        torch.testing.assert_close(lp_a.cpu(), lp_b.cpu(), rtol=1e-4, atol=2e-4)
+
+
 def test_bf16_feature_cache_is_consumed_directly():
     """Features handed over as bf16 (a host/device feature cache in the operand precision) give the same captions as the
     fp32 tensors they were rounded from, up to that rounding."""

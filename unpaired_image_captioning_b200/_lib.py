@@ -33,6 +33,8 @@ SIGNATURES = {
     "uic_att_step_workspace_bytes": (_i64, [_i, _i, _i, _i, _i]),
     "uic_lstm_maxout_fwd": (_i, [_p, _i64, _p, _i64, _p, _p, _p, _p, _i64, _p, _i64, _i, _i, _p]),
     "uic_lstm_cell_fwd": (_i, [_p, _i64, _p, _p, _p, _p, _i64, _p, _i64, _i, _i, _p]),
+    "uic_lstm_maxout_fwd_add": (_i, [_p, _i64, _p, _i64, _p, _p, _p, _p, _i64, _p, _i64, _i, _i, _p, _i64, _p, _i, _p, _i64, _i, _p]),
+    "uic_lstm_cell_fwd_add": (_i, [_p, _i64, _p, _p, _p, _p, _i64, _p, _i64, _i, _i, _p, _i64, _p, _i, _p, _i64, _i, _p]),
     "uic_log_softmax_rows": (_i, [_p, _i64, _p, _i64, _i, _i, _p]),
     "uic_lse_xent_fwd": (_i, [_p, _i64, _p, _p, _p, _p, _i, _i, _p]),
     "uic_greedy_step": (_i, [_p, _i64, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p]),

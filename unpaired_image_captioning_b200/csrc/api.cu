@@ -351,6 +351,25 @@ int uic_lstm_cell_fwd(const float* gates, int64_t ld_gates, const float* c_prev,
   return lstm_cell_fwd(gates, ld_gates, c_prev, c_out, h_f32, h_a, ld_ha, h_b, ld_hb, rows, H, ST(stream));
 }
 
+int uic_lstm_maxout_fwd_add(const float* sums, int64_t ld_sums, const float* a2c, int64_t ld_a2c, const float* c_prev, float* c_out,
+                            float* h_f32, void* h_a, int64_t ld_ha, void* h_b, int64_t ld_hb, int rows, int H, const float* add_tok,
+                            int64_t ld_add_tok, const int64_t* tok, int V, const float* add_grp, int64_t ld_add_grp, int group,
+                            void* stream) {
+  REQUIRE(sums && c_out, UIC_ERR_ARG, "uic_lstm_maxout_fwd_add: null pointer");
+  if (rows == 0) return 0;
+  return lstm_maxout_fwd(sums, ld_sums, a2c, ld_a2c, c_prev, c_out, h_f32, h_a, ld_ha, h_b, ld_hb, rows, H, ST(stream), add_tok, ld_add_tok,
+                         reinterpret_cast<const long long*>(tok), V, add_grp, ld_add_grp, group);
+}
+
+int uic_lstm_cell_fwd_add(const float* gates, int64_t ld_gates, const float* c_prev, float* c_out, float* h_f32, void* h_a,
+                          int64_t ld_ha, void* h_b, int64_t ld_hb, int rows, int H, const float* add_tok, int64_t ld_add_tok,
+                          const int64_t* tok, int V, const float* add_grp, int64_t ld_add_grp, int group, void* stream) {
+  REQUIRE(gates && c_out, UIC_ERR_ARG, "uic_lstm_cell_fwd_add: null pointer");
+  if (rows == 0) return 0;
+  return lstm_cell_fwd(gates, ld_gates, c_prev, c_out, h_f32, h_a, ld_ha, h_b, ld_hb, rows, H, ST(stream), add_tok, ld_add_tok,
+                       reinterpret_cast<const long long*>(tok), V, add_grp, ld_add_grp, group);
+}
+
 int uic_log_softmax_rows(const float* logits, int64_t ld, float* out, int64_t ld_out, int rows, int V, void* stream) {
   REQUIRE(logits && out, UIC_ERR_ARG, "uic_log_softmax_rows: null pointer");
   if (rows == 0) return 0;
@@ -397,7 +416,8 @@ int uic_beam_advance(const float* stats, int parts, int kslots, int32_t* beam_se
   if (move_state) {
     REQUIRE(x_src && x_dst && emb_table_bf16 && (n_state == 0 || (c_src && c_dst)), UIC_ERR_ARG, "uic_beam_advance: null state buffer");
     REQUIRE(x_src != x_dst && c_src != c_dst, UIC_ERR_ARG, "uic_beam_advance: the state must move between two different buffers");
-    REQUIRE(E > 0 && V > 0 && H > 0 && ncol_a >= 0 && ncol_b >= 0, UIC_ERR_SHAPE, "uic_beam_advance: bad state shape");
+    // (E == 0: no embedding rows are written -- the caller gathers the input-word term from a gate table by next_tok)
+    REQUIRE(E >= 0 && V > 0 && H > 0 && ncol_a >= 0 && ncol_b >= 0, UIC_ERR_SHAPE, "uic_beam_advance: bad state shape");
   }
   if (n_img == 0) return 0;
   return beam_advance(stats, parts, kslots, beam_seq, beam_lp, beam_sum, done_seq, done_lp, done_p, done_unaug, done_cnt, parent_row,

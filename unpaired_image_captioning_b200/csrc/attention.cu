@@ -57,12 +57,13 @@ struct AttParams {
   float* ctx_f32;
   long long ld_ctx_f32;
   float* alpha;
-  float* ws_partial;   // [cta][head | tail piece][warp][lane][4 + 4 MT]
+  float* ws_partial;   // [job][segment][warp][lane][4 + 4 MT]
   int* ws_counter;     // [job][ATT_WARPS], zero between launches
   int beams, L, A, H;
   int n_grp;           // beam groups per image (job = img * n_grp + grp)
   int nbpi;            // batches per image
-  int n_batches;       // jobs * nbpi: the flat batch list the CTAs share out evenly
+  int segs;            // segments per job (1: CTAs own whole jobs, no merging; > 1: one CTA per segment)
+  int items;           // jobs * segs
   int f_bufs;          // att_h buffers in shared memory (2, or 3 when every image is a single batch)
   int slab_map;        // the tensor map is the 3-D slab view: one TMA instruction stages a batch's att rows
   long long* trace;    // debug (uic_gemm_set_trace buffer): CTA 0 records globaltimer at its pipeline events
@@ -124,10 +125,11 @@ __host__ __device__ inline AttSmem att_smem_layout(int A, int H, int NB, int f_b
   return s;
 }
 
-// CTA c owns the batches [c * n / ctas, (c + 1) * n / ctas) of the flat list (n batches): equal shares whatever the
-// number of jobs, so a job may be cut into pieces at the CTA boundaries.  The CTA that holds batch b:
-__device__ __forceinline__ int att_cta_of_batch(int b, int n_batches, int ctas) {
-  return static_cast<int>(((static_cast<long long>(b) + 1) * ctas - 1) / n_batches);
+// First batch of work item `it` (item = segment `it % segs` of job `it / segs`; a job's nbpi batches are cut into
+// `segs` nearly equal runs).
+__device__ __forceinline__ int att_item_begin(int it, int segs, int nbpi) {
+  const int job = it / segs, sg = it - job * segs;
+  return job * nbpi + (sg * nbpi) / segs;
 }
 
 // Position of a batch in the job list (every warp keeps identical copies and advances them in step).
@@ -161,10 +163,11 @@ att_step_fwd_kernel(const __grid_constant__ CUtensorMap tmap_att, AttParams p) {
   pdl_launch_dependents();
   const int L = p.L, A = p.A, H = p.H;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // CTA c owns a contiguous, equal share of the flat batch list
-  const int b_start = static_cast<int>(static_cast<long long>(blockIdx.x) * p.n_batches / gridDim.x);
-  const int b_end = static_cast<int>(static_cast<long long>(blockIdx.x + 1) * p.n_batches / gridDim.x);
-  const int nloc = b_end - b_start;
+  // CTA c owns the work items [c * items / ctas, (c + 1) * items / ctas): a contiguous run of batches
+  const int item0 = static_cast<int>(static_cast<long long>(blockIdx.x) * p.items / gridDim.x);
+  const int item1 = static_cast<int>(static_cast<long long>(blockIdx.x + 1) * p.items / gridDim.x);
+  const int b_start = att_item_begin(item0, p.segs, p.nbpi);
+  const int nloc = att_item_begin(item1, p.segs, p.nbpi) - b_start;
   if (nloc <= 0) return;
 
   const AttSmem sm = att_smem_layout(A, H, NB, p.f_bufs);
@@ -293,7 +296,7 @@ att_step_fwd_kernel(const __grid_constant__ CUtensorMap tmap_att, AttParams p) {
           if (EXA || u0 < A)
             asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(u[0]), "=r"(u[1]) : "r"(prow + x * ATT_WARPS * A * 2 + u0 * 2));
 #pragma unroll
-          for (int k = 0; k < 2; ++k) {  // bf16 -> fp32 is a shift / a mask (ALU pipe; an fp16 tile cost one XU conversion per element)
+          for (int k = 0; k < 2; ++k) {  // bf16 -> fp32 is a shift / a mask
             Ef[x][c * 8 + h * 4 + 2 * k] = __uint_as_float(u[k] << 16);
             Ef[x][c * 8 + h * 4 + 2 * k + 1] = __uint_as_float(u[k] & 0xffff0000u);
           }
@@ -444,26 +447,17 @@ att_step_fwd_kernel(const __grid_constant__ CUtensorMap tmap_att, AttParams p) {
 
     // ---- image finished (or the range ends inside it) -----------------------------------------------------
     if (cx.kb == p.nbpi - 1 || range_end) {
-      // A job that lies inside this CTA's share is finished here.  Otherwise it is cut into nseg pieces held by the CTAs
-      // c_first .. c_last; this one is piece `seg`, and the last piece to arrive at the job's counter merges them.
-      const int job_b0 = cx.job * p.nbpi;
-      int nseg = 1, seg = 0;
-      if (job_b0 < b_start || job_b0 + p.nbpi > b_end) {
-        const int c_first = att_cta_of_batch(job_b0, p.n_batches, gridDim.x);
-        nseg = att_cta_of_batch(job_b0 + p.nbpi - 1, p.n_batches, gridDim.x) - c_first + 1;
-        seg = static_cast<int>(blockIdx.x) - c_first;
-      }
+      const int nseg = p.segs, seg = item0 - cx.job * p.segs;  // (segs > 1: this CTA owns exactly one item)
       // statistics of the accumulator columns' beams
       float Mn[2] = {__shfl_sync(0xffffffffu, m_run, 8 * t), __shfl_sync(0xffffffffu, m_run, 8 * t + 4)};
       float Sn[2] = {__shfl_sync(0xffffffffu, s_run, 8 * t), __shfl_sync(0xffffffffu, s_run, 8 * t + 4)};
       const int n0 = 2 * t;
       bool finish = true;
       if (nseg > 1) {
-        // Every lane owns a private record of 1 + MT float4: (M0, M1, S0, S1) and its accumulators.  A CTA holds at most
-        // two pieces: slot 1 = the head of a job that continues in the next CTA (piece 0), slot 0 = a later piece.
+        // Every lane owns a private record of 1 + MT float4: (M0, M1, S0, S1) and its accumulators.
         constexpr int REC = 4 + 4 * MT;
         float4* rec = reinterpret_cast<float4*>(p.ws_partial) +
-                      (((static_cast<long long>(blockIdx.x) * 2 + (seg == 0 ? 1 : 0)) * ATT_WARPS + warp) * 32 + lane) * (REC / 4);
+                      (((static_cast<long long>(cx.job) * p.segs + seg) * ATT_WARPS + warp) * 32 + lane) * (REC / 4);
         if (n0 < NB) {
           rec[0] = make_float4(Mn[0], Mn[1], Sn[0], Sn[1]);
 #pragma unroll
@@ -481,15 +475,12 @@ att_step_fwd_kernel(const __grid_constant__ CUtensorMap tmap_att, AttParams p) {
         finish = last != 0;
         if (finish && n0 < NB) {
           __threadfence();
-          // piece sgm lives in CTA c_first + sgm: slot 1 for the first piece, slot 0 for the others
-          const long long c_first = static_cast<long long>(blockIdx.x) - seg;
-          auto piece = [&](int sgm) {
-            return reinterpret_cast<const float4*>(p.ws_partial) +
-                   ((((c_first + sgm) * 2 + (sgm == 0 ? 1 : 0)) * ATT_WARPS + warp) * 32 + lane) * (REC / 4);
-          };
+          const float4* base = reinterpret_cast<const float4*>(p.ws_partial) +
+                               ((static_cast<long long>(cx.job) * p.segs * ATT_WARPS + warp) * 32 + lane) * (REC / 4);
+          const long long seg_stride = static_cast<long long>(ATT_WARPS) * 32 * (REC / 4);
           float mx0 = -INFINITY, mx1 = -INFINITY;
           for (int sgm = 0; sgm < nseg; ++sgm) {
-            const float4 st = __ldcg(piece(sgm));
+            const float4 st = __ldcg(base + sgm * seg_stride);
             mx0 = fmaxf(mx0, st.x);
             mx1 = fmaxf(mx1, st.y);
           }
@@ -497,7 +488,7 @@ att_step_fwd_kernel(const __grid_constant__ CUtensorMap tmap_att, AttParams p) {
 #pragma unroll
           for (int q = 0; q < MT; ++q) acc[q][0] = acc[q][1] = acc[q][2] = acc[q][3] = 0.0f;
           for (int sgm = 0; sgm < nseg; ++sgm) {
-            const float4* r4 = piece(sgm);
+            const float4* r4 = base + sgm * seg_stride;
             const float4 st = __ldcg(r4);
             float4 v[MT];
 #pragma unroll
@@ -621,7 +612,7 @@ static int beams_per_group(int beams) {
 }
 
 struct AttPlan {
-  int nb, groups, nbpi, ctas, n_batches, mt, f_bufs;
+  int nb, groups, nbpi, ctas, segs, items, mt, f_bufs;
 };
 
 static AttPlan make_plan(int n_img, int beams, int L, int A, int H) {
@@ -632,11 +623,14 @@ static AttPlan make_plan(int n_img, int beams, int L, int A, int H) {
   const long long jobs = static_cast<long long>(n_img) * pl.groups;
   const int per_sm = ((A + 255) / 256 <= 2 && H <= 512) ? 2 : 1;  // matches the kernel's launch bounds
   const long long slots = 148LL * per_sm;
-  // Every CTA slot gets an equal share of the flat batch list (a first version handed out whole jobs: 256 jobs on 296
-  // slots left 40 SMs with one CTA and 108 with two, and the doubly-loaded ones set the makespan).
-  const long long n_batches = jobs * pl.nbpi;
-  pl.n_batches = static_cast<int>(n_batches);
-  pl.ctas = static_cast<int>(n_batches < slots ? n_batches : slots);
+  // Whole jobs per CTA (no merging) unless that would leave more than half of the slots empty: then every job
+  // is cut into `segs` segments of whole batches, one CTA each.
+  long long segs = slots / (jobs > 0 ? jobs : 1);
+  segs = segs < 1 ? 1 : (segs > pl.nbpi ? pl.nbpi : segs);
+  pl.segs = static_cast<int>(segs);
+  const long long items = jobs * segs;
+  pl.items = static_cast<int>(items);
+  pl.ctas = static_cast<int>(items < slots ? items : slots);
   pl.mt = H <= 512 ? 4 : 8;
   pl.f_bufs = pl.nbpi == 1 ? 3 : 2;
   return pl;
@@ -646,7 +640,7 @@ long long att_step_workspace_bytes(int n_img, int beams, int L, int A, int H) {
   const AttPlan pl = make_plan(n_img, beams, L, A, H);
   const long long jobs = static_cast<long long>(n_img) * pl.groups;
   const long long counters = ((jobs * ATT_WARPS * 4 + 255) / 256) * 256;
-  return counters + static_cast<long long>(pl.ctas) * 2 * ATT_WARPS * 32 * (4 + 4 * pl.mt) * 4;
+  return counters + (pl.segs > 1 ? jobs * pl.segs * ATT_WARPS * 32 * (4 + 4 * pl.mt) * 4 : 0);
 }
 
 template <int NB, int CA, int MT, bool EXA>
@@ -720,7 +714,8 @@ int att_step_fwd(const float* att_h, long long ld_att_h, const void* p_att, cons
   p.H = H;
   p.n_grp = pl.groups;
   p.nbpi = pl.nbpi;
-  p.n_batches = pl.n_batches;
+  p.segs = pl.segs;
+  p.items = pl.items;
   p.f_bufs = pl.f_bufs;
   p.trace = gemm_trace_buffer();
   // Tiles that cannot stay L2-resident from one step to the next (> ~half of the 126 MB L2) are streamed evict-first;

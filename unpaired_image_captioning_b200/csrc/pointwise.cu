@@ -95,6 +95,8 @@ int embed_rows(const void* table, long long ld_table, const int64_t* tok, void* 
 }
 
 // ---- LSTM pointwise ---------------------------------------------------------------------------------
+static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+static bool aligned8(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 7) == 0; }
 struct HOut {
   float* h_f32;
   __nv_bfloat16* h_a;
@@ -135,17 +137,49 @@ __device__ __forceinline__ void store_h(const HOut& o, int r, int j, int H, cons
   if (o.h_a) stv_bf16<VEC>(o.h_a + static_cast<long long>(r) * o.ld_ha + j, h);
   if (o.h_b) stv_bf16<VEC>(o.h_b + static_cast<long long>(r) * o.ld_hb + j, h);
 }
-static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
-static bool aligned8(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 7) == 0; }
 static bool hout_vec_ok(const HOut& o, int H) {
   return H % 4 == 0 && aligned16(o.h_f32) && aligned8(o.h_a) && aligned8(o.h_b) && o.ld_ha % 4 == 0 && o.ld_hb % 4 == 0;
+}
+
+// Optional addends to the gate pre-activations, looked up per row (decode loops): the input-word term W_x relu(Emb[tok])
+// is a function of the token alone, so it is precomputed as a (V, n_gates H) fp32 table per weight version and gathered
+// here instead of being re-multiplied every step (the gate GEMM then contracts over the recurrent columns only); the
+// image-constant term W_fc fc of the TopDown attention LSTM is one row per image, shared by its beams.
+struct GateAdd {
+  const float* tok_table;  // [V][n_gates H] or nullptr
+  long long ld_tok;
+  const long long* tok;    // [rows] token ids
+  int V;
+  const float* grp_table;  // [rows / group][n_gates H] or nullptr
+  long long ld_grp;
+  int group;
+};
+template <int VEC>
+__device__ __forceinline__ void gate_add(const GateAdd& ga, int r, int col, float (&v)[VEC]) {
+  if (ga.tok_table != nullptr) {
+    long long t = ga.tok[r];
+    t = t < 0 ? 0 : (t >= ga.V ? ga.V - 1 : t);
+    float a[VEC];
+    ldv<VEC>(ga.tok_table + t * ga.ld_tok + col, a);
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) v[k] += a[k];
+  }
+  if (ga.grp_table != nullptr) {
+    float a[VEC];
+    ldv<VEC>(ga.grp_table + static_cast<long long>(r / ga.group) * ga.ld_grp + col, a);
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) v[k] += a[k];
+  }
+}
+static bool gate_add_vec_ok(const GateAdd& ga) {
+  return aligned16(ga.tok_table) && aligned16(ga.grp_table) && ga.ld_tok % 4 == 0 && ga.ld_grp % 4 == 0;
 }
 
 // Att2in2Core.forward pointwise part, models/AttModel.py:585-597.
 template <int VEC>
 __global__ void lstm_maxout_fwd_kernel(const float* __restrict__ sums, long long ld_sums, const float* __restrict__ a2c,
                                        long long ld_a2c, const float* __restrict__ c_prev, float* __restrict__ c_out, HOut o,
-                                       int rows, int H) {
+                                       int rows, int H, GateAdd ga) {
   pdl_launch_dependents();
   pdl_wait();
   const int per_row = H / VEC;
@@ -161,6 +195,13 @@ __global__ void lstm_maxout_fwd_kernel(const float* __restrict__ sums, long long
     ldv<VEC>(s + 2 * H + j, so);
     ldv<VEC>(s + 3 * H + j, s3);
     ldv<VEC>(s + 4 * H + j, s4);
+    if (ga.tok_table != nullptr || ga.grp_table != nullptr) {
+      gate_add<VEC>(ga, r, j, si);
+      gate_add<VEC>(ga, r, H + j, sf);
+      gate_add<VEC>(ga, r, 2 * H + j, so);
+      gate_add<VEC>(ga, r, 3 * H + j, s3);
+      gate_add<VEC>(ga, r, 4 * H + j, s4);
+    }
 #pragma unroll
     for (int v = 0; v < VEC; ++v) a0[v] = a1[v] = 0.0f;
     if (a2c) {  // att2all2 (:618-654): the context term was accumulated into all five gate sums by its GEMM
@@ -185,7 +226,7 @@ __global__ void lstm_maxout_fwd_kernel(const float* __restrict__ sums, long long
 // torch.nn.LSTMCell pointwise part (gate order i, f, g, o), used at models/AttModel.py:434,441.
 template <int VEC>
 __global__ void lstm_cell_fwd_kernel(const float* __restrict__ gates, long long ld_gates, const float* __restrict__ c_prev,
-                                     float* __restrict__ c_out, HOut o, int rows, int H) {
+                                     float* __restrict__ c_out, HOut o, int rows, int H, GateAdd ga) {
   pdl_launch_dependents();
   pdl_wait();
   const int per_row = H / VEC;
@@ -199,6 +240,12 @@ __global__ void lstm_cell_fwd_kernel(const float* __restrict__ gates, long long 
     ldv<VEC>(g4 + H + j, gf);
     ldv<VEC>(g4 + 2 * H + j, gg);
     ldv<VEC>(g4 + 3 * H + j, go);
+    if (ga.tok_table != nullptr || ga.grp_table != nullptr) {
+      gate_add<VEC>(ga, r, j, gi);
+      gate_add<VEC>(ga, r, H + j, gf);
+      gate_add<VEC>(ga, r, 2 * H + j, gg);
+      gate_add<VEC>(ga, r, 3 * H + j, go);
+    }
 #pragma unroll
     for (int v = 0; v < VEC; ++v) cp[v] = 0.0f;
     if (c_prev) ldv<VEC>(c_prev + static_cast<long long>(r) * H + j, cp);
@@ -212,34 +259,47 @@ __global__ void lstm_cell_fwd_kernel(const float* __restrict__ gates, long long 
   }
 }
 
+static int gate_add_check(const char* who, const float* add_tok, const long long* tok, int V, const float* add_grp, int group) {
+  if (add_tok != nullptr && (tok == nullptr || V <= 0)) return set_error(UIC_ERR_ARG, "%s: the token table needs token ids and V > 0", who);
+  if (add_grp != nullptr && group <= 0) return set_error(UIC_ERR_ARG, "%s: rows per group must be positive (got %d)", who, group);
+  return 0;
+}
+
 int lstm_maxout_fwd(const float* sums, long long ld_sums, const float* a2c, long long ld_a2c, const float* c_prev, float* c_out,
-                    float* h_f32, void* h_a, long long ld_ha, void* h_b, long long ld_hb, int rows, int H, cudaStream_t stream) {
+                    float* h_f32, void* h_a, long long ld_ha, void* h_b, long long ld_hb, int rows, int H, cudaStream_t stream,
+                    const float* add_tok, long long ld_add_tok, const long long* tok, int V, const float* add_grp, long long ld_add_grp,
+                    int group) {
+  if (int rc = gate_add_check("lstm_maxout_fwd", add_tok, tok, V, add_grp, group)) return rc;
   HOut o{h_f32, static_cast<__nv_bfloat16*>(h_a), ld_ha, static_cast<__nv_bfloat16*>(h_b), ld_hb};
+  GateAdd ga{add_tok, ld_add_tok, tok, V, add_grp, ld_add_grp, group > 0 ? group : 1};
   const bool vec = hout_vec_ok(o, H) && aligned16(sums) && aligned16(a2c) && aligned16(c_prev) && aligned16(c_out) && ld_sums % 4 == 0 &&
-                   ld_a2c % 4 == 0;
+                   ld_a2c % 4 == 0 && gate_add_vec_ok(ga);
   launch_begin("lstm_maxout_fwd", stream);
   if (vec)
     UIC_CUDA_OK(launch_pdl(lstm_maxout_fwd_kernel<4>, dim3(blocks_for(static_cast<long long>(rows) * H / 4, 256)), dim3(256), 0, stream, sums,
-                           ld_sums, a2c, ld_a2c, c_prev, c_out, o, rows, H));
+                           ld_sums, a2c, ld_a2c, c_prev, c_out, o, rows, H, ga));
   else
     UIC_CUDA_OK(launch_pdl(lstm_maxout_fwd_kernel<1>, dim3(blocks_for(static_cast<long long>(rows) * H, 256)), dim3(256), 0, stream, sums,
-                           ld_sums, a2c, ld_a2c, c_prev, c_out, o, rows, H));
+                           ld_sums, a2c, ld_a2c, c_prev, c_out, o, rows, H, ga));
   UIC_CUDA_OK(cudaGetLastError());
   launch_end(stream);
   return 0;
 }
 
 int lstm_cell_fwd(const float* gates, long long ld_gates, const float* c_prev, float* c_out, float* h_f32, void* h_a,
-                  long long ld_ha, void* h_b, long long ld_hb, int rows, int H, cudaStream_t stream) {
+                  long long ld_ha, void* h_b, long long ld_hb, int rows, int H, cudaStream_t stream, const float* add_tok,
+                  long long ld_add_tok, const long long* tok, int V, const float* add_grp, long long ld_add_grp, int group) {
+  if (int rc = gate_add_check("lstm_cell_fwd", add_tok, tok, V, add_grp, group)) return rc;
   HOut o{h_f32, static_cast<__nv_bfloat16*>(h_a), ld_ha, static_cast<__nv_bfloat16*>(h_b), ld_hb};
-  const bool vec = hout_vec_ok(o, H) && aligned16(gates) && aligned16(c_prev) && aligned16(c_out) && ld_gates % 4 == 0;
+  GateAdd ga{add_tok, ld_add_tok, tok, V, add_grp, ld_add_grp, group > 0 ? group : 1};
+  const bool vec = hout_vec_ok(o, H) && aligned16(gates) && aligned16(c_prev) && aligned16(c_out) && ld_gates % 4 == 0 && gate_add_vec_ok(ga);
   launch_begin("lstm_cell_fwd", stream);
   if (vec)
     UIC_CUDA_OK(launch_pdl(lstm_cell_fwd_kernel<4>, dim3(blocks_for(static_cast<long long>(rows) * H / 4, 256)), dim3(256), 0, stream, gates,
-                           ld_gates, c_prev, c_out, o, rows, H));
+                           ld_gates, c_prev, c_out, o, rows, H, ga));
   else
     UIC_CUDA_OK(launch_pdl(lstm_cell_fwd_kernel<1>, dim3(blocks_for(static_cast<long long>(rows) * H, 256)), dim3(256), 0, stream, gates,
-                           ld_gates, c_prev, c_out, o, rows, H));
+                           ld_gates, c_prev, c_out, o, rows, H, ga));
   UIC_CUDA_OK(cudaGetLastError());
   launch_end(stream);
   return 0;

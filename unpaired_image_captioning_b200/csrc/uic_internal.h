@@ -82,9 +82,13 @@ int att_step_fwd(const float* att_h, long long ld_att_h, const void* p_att, cons
                  void* workspace, long long workspace_bytes, int n_img, int beams, int L, int A, int H, cudaStream_t stream);
 long long att_step_workspace_bytes(int n_img, int beams, int L, int A, int H);
 int lstm_maxout_fwd(const float* sums, long long ld_sums, const float* a2c, long long ld_a2c, const float* c_prev, float* c_out,
-                    float* h_f32, void* h_a, long long ld_ha, void* h_b, long long ld_hb, int rows, int H, cudaStream_t stream);
+                    float* h_f32, void* h_a, long long ld_ha, void* h_b, long long ld_hb, int rows, int H, cudaStream_t stream,
+                    const float* add_tok = nullptr, long long ld_add_tok = 0, const long long* tok = nullptr, int V = 0,
+                    const float* add_grp = nullptr, long long ld_add_grp = 0, int group = 1);
 int lstm_cell_fwd(const float* gates, long long ld_gates, const float* c_prev, float* c_out, float* h_f32, void* h_a,
-                  long long ld_ha, void* h_b, long long ld_hb, int rows, int H, cudaStream_t stream);
+                  long long ld_ha, void* h_b, long long ld_hb, int rows, int H, cudaStream_t stream, const float* add_tok = nullptr,
+                  long long ld_add_tok = 0, const long long* tok = nullptr, int V = 0, const float* add_grp = nullptr,
+                  long long ld_add_grp = 0, int group = 1);
 int log_softmax_rows(const float* logits, long long ld, float* out, long long ld_out, int rows, int V, cudaStream_t stream);
 int lse_xent_fwd(const float* logits, long long ld, const int64_t* target, const float* mask, float* lse, float* nll, int rows,
                  int V, cudaStream_t stream);

@@ -67,6 +67,10 @@ class PackedWeights:
             w1[:5 * H, E:] = f32("core.h2h.weight")
             w1[5 * H:, E:] = w_h2att
             self.w1 = _bf16(w1)
+            # decode loops without dropout: the input-word term i2h(relu(embed(it))) comes from a (V, 5H) table (built on
+            # first use, gate_table()), so the step GEMM contracts over the recurrent columns only: X[:, E:] @ w1h^T
+            self.w1h = self.w1[:, E:]
+            self._gate_table = None
             if self.all_gates:   # Att2all2Core (models/AttModel.py:618-654): a2h (5H, H); its bias joins the gate bias
                 self.b1 = torch.cat([f32("core.i2h.bias") + f32("core.h2h.bias") + f32("core.a2h.bias"), b_h2att]).contiguous()
                 self.w_a2c, self.b_a2c = _bf16(sd["core.a2h.weight"]), None
@@ -87,6 +91,17 @@ class PackedWeights:
             self.w_h2att, self.b_h2att = _bf16(w_h2att), b_h2att
         else:
             raise ValueError(self.kind)
+
+    def gate_table(self):
+        """att2in2 / att2all2: T[v] = W_i2h relu(Emb[v]) + b_i2h + b_h2h (+ b_a2h), fp32 (V, 5H) -- the whole contribution of
+        the input word to the gate sums (models/AttModel.py:160,584).  One 26 GF GEMM per weight version; the decode
+        step then adds row it[r] in the cell kernel and its GEMM drops the E input columns (K = E + H -> H)."""
+        if self._gate_table is None:
+            H, E = self.H, self.E
+            self._gate_table = torch.empty(self.V, 5 * H, dtype=torch.float32, device=self.w1.device)
+            gemm(self.emb_relu, self.w1[:5 * H, :E], self.b1[:5 * H].contiguous(), out_f32=self._gate_table)
+            self.b1h = torch.cat([torch.zeros(5 * H, device=self.b1.device), self.b1[5 * H:]]).contiguous()
+        return self._gate_table
 
     @staticmethod
     def signature_of(model):
@@ -162,6 +177,7 @@ class DecoderEngine:
         self.use_graphs = True
         self.fused_vocab = True   # sampling: logit GEMM with fused LSE/top-k statistics (False: write logits + row kernels)
         self.compact_first_step = True   # beam search: step 0 on one row per image (every beam forks from beam 0 there)
+        self.use_gate_table = True       # decode loops: input-word gate term from a (V, 5H) table instead of the E columns of the step GEMM
         self._capture_launches = 0
         self._replayed_launches = 0
         self.lib = _lib.load()
@@ -292,10 +308,12 @@ class DecoderEngine:
         ws["logits"] = torch.empty(R, w.V, dtype=torch.float32, device=dev)
         return ws
 
-    def core_step(self, X, c, feats, ws, beams=1, X_next=None, c_out=None, h_all=None, alpha=None):
+    def core_step(self, X, c, feats, ws, beams=1, X_next=None, c_out=None, h_all=None, alpha=None, tok=None):
         """Runs the recurrent core for one step, in place on X / c unless X_next / c_out are given
         (teacher-forced runs keep every step's operands for backward).  h_all: optional extra bf16
-        destination (rows, H) for the step output (time-batched logit operand)."""
+        destination (rows, H) for the step output (time-batched logit operand).  tok: (rows,) int64 input tokens --
+        when given (decode loops, no dropout) the input-word term is gathered from PackedWeights.gate_table() and the
+        xt columns of X are not read."""
         w, lib, st = self.w, self.lib, stream()
         H, E, A, R = w.H, w.E, w.A, X.shape[0]
         sl = Slots(self.kind, E, H)
@@ -308,7 +326,11 @@ class DecoderEngine:
 
         if self.kind == "att2in2":
             S = ws["S"]
-            gemm(X, w.w1, w.b1, out_f32=S, exp_col0=5 * H, exp_scale=_lib.ATT_F_SCALE)   # S[:, 5H:] = F = exp(2 att_h)
+            table = w.gate_table() if (tok is not None and self.use_gate_table) else None
+            if table is not None:
+                gemm(X[:, E:], w.w1h, w.b1h, out_f32=S, exp_col0=5 * H, exp_scale=_lib.ATT_F_SCALE)
+            else:
+                gemm(X, w.w1, w.b1, out_f32=S, exp_col0=5 * H, exp_scale=_lib.ATT_F_SCALE)   # S[:, 5H:] = F = exp(2 att_h)
             _lib.att_step(S[:, 5 * H:], S.stride(0), feats.p_att, feats.att, w.w_alpha, feats.masks, ws["ctx"], H, None, 0, alpha,
                           feats.B, beams, feats.L, A, H)
             if w.all_gates:   # S[:, :5H] += a2h(ctx): the saved sums already hold everything the cell (and its backward) needs
@@ -318,9 +340,14 @@ class DecoderEngine:
                 a2c = ws["a2c"]
                 gemm(ws["ctx"], w.w_a2c, w.b_a2c, out_f32=a2c)
             h_dst = cols(Xn, sl.h_out)
-            check(lib.uic_lstm_maxout_fwd(ptr(S), S.stride(0), ptr(a2c), 2 * H, ptr(c[0]), ptr(c_out[0]), None,
-                                          ptr(h_dst), Xn.stride(0), ptr(h_all), h_all.stride(0) if h_all is not None else 0,
-                                          R, H, st))
+            if table is not None:
+                check(lib.uic_lstm_maxout_fwd_add(ptr(S), S.stride(0), ptr(a2c), 2 * H, ptr(c[0]), ptr(c_out[0]), None,
+                                                  ptr(h_dst), Xn.stride(0), ptr(h_all), h_all.stride(0) if h_all is not None else 0,
+                                                  R, H, ptr(table), table.stride(0), ptr(tok), w.V, None, 0, 1, st))
+            else:
+                check(lib.uic_lstm_maxout_fwd(ptr(S), S.stride(0), ptr(a2c), 2 * H, ptr(c[0]), ptr(c_out[0]), None,
+                                              ptr(h_dst), Xn.stride(0), ptr(h_all), h_all.stride(0) if h_all is not None else 0,
+                                              R, H, st))
         else:
             G = ws["G"]
             gemm(X[:, :E + 3 * H], w.w1, w.b1, out_f32=G)
@@ -371,7 +398,7 @@ class DecoderEngine:
             raise NotImplementedError("multinomial sampling runs in the fused statistics epilogue (engine.fused_vocab)")
         if drop is not None and not self.fused_vocab:
             raise NotImplementedError("roll-outs with dropout run in the fused statistics path (engine.fused_vocab)")
-        key = ("greedy", B, feats.L, T, flags, feats.masks is not None, self.fused_vocab, temperature,
+        key = ("greedy", B, feats.L, T, flags, feats.masks is not None, self.fused_vocab, self.use_gate_table, temperature,
                None if drop is None else (float(drop[0]), drop[1].data_ptr()))
 
         def alloc():
@@ -399,7 +426,7 @@ class DecoderEngine:
             if drop is not None:
                 _lib.dropout(xt_view, drop, _lib.DROP_XT, row0=0)
             for t in range(T):
-                h = self.core_step(X, c, f, ws)
+                h = self.core_step(X, c, f, ws, tok=s["tok"] if drop is None else None)
                 if drop is not None:   # the logit layer sees the dropped output; the recurrent state does not (AttModel.py:431,599)
                     s["h_drop"].copy_(h)
                     h = s["h_drop"]
@@ -442,7 +469,8 @@ class DecoderEngine:
         R = B * b
         tk_flags = _lib.SAMPLE_DECODING_CONSTRAINT if decoding_constraint else 0
         bs_flags = _lib.BEAM_MAX_PPL if max_ppl else 0
-        key = ("beam", B, b, feats.L, T, tk_flags, bs_flags, feats.masks is not None, self.fused_vocab, self.compact_first_step)
+        key = ("beam", B, b, feats.L, T, tk_flags, bs_flags, feats.masks is not None, self.fused_vocab, self.compact_first_step,
+               self.use_gate_table)
 
         def alloc():
             s = {**self._feature_buffers(feats),
@@ -486,7 +514,7 @@ class DecoderEngine:
                 if self.kind == "topdown":
                     check(lib.uic_embed_rows(ptr(f.fc), w.H, ptr(s["img_idx0"]), ptr(X0[:, sl.fc[0]:]), X0.stride(0), B, w.H, B, stream()))
                 self._embed(s["tok0"], X0, sl)   # BOS (AttModel.py:186-190)
-                h = self.core_step(X0, c0, f, s["ws0"], beams=1)
+                h = self.core_step(X0, c0, f, s["ws0"], beams=1, tok=s["tok0"])
                 check(lib.uic_logit_stats(ptr(h), h.stride(0), ptr(w.w_logit), w.H, ptr(w.b_logit), None, 1,
                                           ptr(s["stats0"]), B, w.V, w.H, s["kslots"], 1, 0.0, None, 0, stream()))
                 Xn, cn = bufs[1]
@@ -501,7 +529,7 @@ class DecoderEngine:
             for t in range(t_first, T):
                 X, c = bufs[t % 2]
                 Xn, cn = bufs[(t + 1) % 2]
-                h = self.core_step(X, c, f, ws, beams=b)
+                h = self.core_step(X, c, f, ws, beams=b, tok=s["tok"])
                 if self.fused_vocab and b <= 8:
                     banned = s["tok"] if (tk_flags and t > 0) else None
                     check(lib.uic_logit_stats(ptr(h), h.stride(0), ptr(w.w_logit), w.H, ptr(w.b_logit), ptr(banned), 1,
@@ -542,7 +570,8 @@ class DecoderEngine:
         R = B * b
         tk_flags = _lib.SAMPLE_DECODING_CONSTRAINT if decoding_constraint else 0
         bs_flags = _lib.BEAM_MAX_PPL if max_ppl else 0
-        key = ("beam_diverse", B, b, G, float(diversity_lambda), feats.L, T, tk_flags, bs_flags, feats.masks is not None)
+        key = ("beam_diverse", B, b, G, float(diversity_lambda), feats.L, T, tk_flags, bs_flags, feats.masks is not None,
+               self.use_gate_table)
 
         def alloc():
             s = {**self._feature_buffers(feats),
@@ -585,7 +614,7 @@ class DecoderEngine:
                     X, c = s["state"][g][lt % 2]
                     Xn, cn = s["state"][g][(lt + 1) % 2]
                     tok = s["tok"][g]
-                    h = self.core_step(X, c, f, ws, beams=b)
+                    h = self.core_step(X, c, f, ws, beams=b, tok=tok)
                     self.logits_of(h, ws["logits"])
                     kp = b * (g + 1)                                # enough to survive the penalties on <= g * b tokens
                     check(lib.uic_row_topk(ptr(ws["logits"]), w.V, ptr(tok) if (tk_flags and lt > 0) else None, ptr(s["cand_val"]),
