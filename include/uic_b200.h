@@ -175,7 +175,8 @@ int uic_row_topk(const float* logits, int64_t ld_logits, const int64_t* prev_tok
 /* Fused vocabulary projection + statistics for sampling: logits = h W^T + b are reduced inside the GEMM
  * epilogue and NEVER written to memory (replaces self.logit + F.log_softmax + torch.max / torch.sort of
  * models/AttModel.py:163,229 and models/CaptionModel.py:61,128-133 for inference).  For every row and
- * each of uic_logit_stats_parts(V) column parts it stores one entry of uic_logit_stats_entry_floats(kslots)
+ * each of uic_logit_stats_parts(rows, V) column parts (two per GEMM tile; the tile width, 128 or 224 columns, is chosen from
+ * the problem shape) it stores one entry of uic_logit_stats_entry_floats(kslots)
  * floats (2 + 2*kslots rounded up to a multiple of 4): max, sum exp(x - max), the kslots best keys (logit,
  * with -1000 on the UNK column V-1 when unk_suppress != 0 and -inf on the banned token) and their columns
  * (int bits, 0x7fffffff = empty slot), padding.  `stats` is (rows, parts, entry) fp32, 16-byte aligned.
@@ -185,7 +186,7 @@ int uic_row_topk(const float* logits, int64_t ld_logits, const int64_t* prev_tok
  * g = -log(-log(u)), u a counter-based hash of (seed, step, row, column) (csrc/uic_vocab.cuh; restated in
  * oracle/decoder_oracle.py).  `seed` points to DEVICE memory (so a captured CUDA graph can be replayed with a new
  * seed).  temperature = 0: deterministic (seed may be NULL, step is ignored). */
-int uic_logit_stats_parts(int V);
+int uic_logit_stats_parts(int rows, int V);
 int uic_logit_stats_entry_floats(int kslots);
 int uic_logit_stats(const void* h_bf16, int64_t ld_h, const void* w_logit_bf16, int64_t ld_w, const float* bias,
                     const int64_t* banned_tok, int64_t banned_stride, float* stats, int rows, int V, int H, int kslots, int unk_suppress,

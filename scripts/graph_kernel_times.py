@@ -58,7 +58,7 @@ M, N, K = 768, 10000, 512
 a = torch.randn(M, K, device="cuda").to(torch.bfloat16)
 b = (torch.randn(N, K, device="cuda") * 0.05).to(torch.bfloat16)
 bias = torch.randn(N, device="cuda")
-parts = int(lib.uic_logit_stats_parts(N))
+parts = int(lib.uic_logit_stats_parts(M, N))
 for ks in (1, 3):
     stats = torch.empty(M, parts, int(lib.uic_logit_stats_entry_floats(ks)), device="cuda")
 

@@ -324,7 +324,7 @@ def test_logit_stats_topk_equals_reference_order(R, V, H, k, kslots):
     bias[V - 1] += 30.0                                   # UNK would win without the -1000 edit
     prev = torch.randint(0, V - 1, (R,), device=DEV)
     logits = h.float() @ w.float().t() + bias
-    parts = lib.uic_logit_stats_parts(V)
+    parts = lib.uic_logit_stats_parts(R, V)
     stats = torch.empty(R, parts, lib.uic_logit_stats_entry_floats(kslots), device=DEV)
     val, idx = torch.empty(R, k, device=DEV), torch.empty(R, k, device=DEV, dtype=torch.int32)
     for constrained in (False, True):
@@ -353,7 +353,7 @@ def test_logit_stats_without_unk_suppression_keeps_unk():
     h, w, bias, _ = _stats_inputs(R, V, H, seed=5)
     bias[V - 1] += 50.0
     logits = h.float() @ w.float().t() + bias
-    parts = lib.uic_logit_stats_parts(V)
+    parts = lib.uic_logit_stats_parts(R, V)
     stats = torch.empty(R, parts, 4, device=DEV)
     val, idx = torch.empty(R, 1, device=DEV), torch.empty(R, 1, device=DEV, dtype=torch.int32)
     check(lib.uic_logit_stats(ptr(h), H, ptr(w), H, ptr(bias), None, 0, ptr(stats), R, V, H, 1, 0, 0.0, None, 0, stream()))
@@ -366,7 +366,7 @@ def test_greedy_merge_equals_greedy_step():
     """The fused greedy path writes the same tokens / log-probs / counters as logits + uic_greedy_step."""
     lib = _lib.load()
     R, V, H, T = 70, 10000, 512, 4
-    parts = lib.uic_logit_stats_parts(V)
+    parts = lib.uic_logit_stats_parts(R, V)
     stats = torch.empty(R, parts, 4, device=DEV)
 
     def state():
@@ -399,7 +399,7 @@ def test_beam_advance_equals_the_four_step_chain(B, b, kslots, compact_first):
     lib = _lib.load()
     V, Hh, E, T = 300, 64, 32, 6
     R = B * b
-    parts = lib.uic_logit_stats_parts(V)
+    parts = lib.uic_logit_stats_parts(R, V)
     es = lib.uic_logit_stats_entry_floats(kslots)
     table = _rand_bf16(V, E, seed=3)
     ld_x = E + 2 * Hh + 8
@@ -451,7 +451,7 @@ def test_beam_advance_equals_the_four_step_chain(B, b, kslots, compact_first):
 def test_greedy_advance_equals_merge_plus_embed():
     lib = _lib.load()
     R, V, H, T, E = 70, 1000, 128, 4, 48
-    parts = lib.uic_logit_stats_parts(V)
+    parts = lib.uic_logit_stats_parts(R, V)
     stats = torch.empty(R, parts, 4, device=DEV)
     table = _rand_bf16(V, E, seed=9)
 

@@ -25,7 +25,7 @@ def test_sampling_epilogue_matches_the_oracle_noise():
     w = (torch.randn(V, H, generator=g) * 0.05).to(DEV).to(torch.bfloat16)
     bias = (torch.randn(V, generator=g) * 0.1).to(DEV)
     logits = h.float() @ w.float().t() + bias
-    parts = lib.uic_logit_stats_parts(V)
+    parts = lib.uic_logit_stats_parts(R, V)
     stats = torch.empty(R, parts, 4, device=DEV)
     seed_t = torch.tensor([seed], dtype=torch.int64, device=DEV)
     seq, lp = torch.zeros(R, T, dtype=torch.int64, device=DEV), torch.zeros(R, T, device=DEV)
@@ -56,7 +56,7 @@ def test_sampling_frequencies_follow_softmax():
     w = (torch.randn(V, H, generator=g) * 0.3).to(DEV).to(torch.bfloat16)
     bias = torch.zeros(V, device=DEV)
     logits = (h[:1].float() @ w.float().t()).cpu()[0]
-    parts = lib.uic_logit_stats_parts(V)
+    parts = lib.uic_logit_stats_parts(R, V)
     stats = torch.empty(R, parts, 4, device=DEV)
     seed_t = torch.tensor([77], dtype=torch.int64, device=DEV)
     T = 2

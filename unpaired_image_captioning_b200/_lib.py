@@ -39,7 +39,7 @@ SIGNATURES = {
     "uic_lse_xent_fwd": (_i, [_p, _i64, _p, _p, _p, _p, _i, _i, _p]),
     "uic_greedy_step": (_i, [_p, _i64, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p]),
     "uic_row_topk": (_i, [_p, _i64, _p, _p, _p, _i, _i, _i, _i, _p]),
-    "uic_logit_stats_parts": (_i, [_i]),
+    "uic_logit_stats_parts": (_i, [_i, _i]),
     "uic_logit_stats_entry_floats": (_i, [_i]),
     "uic_logit_stats": (_i, [_p, _i64, _p, _i64, _p, _p, _i64, _p, _i, _i, _i, _i, _i, _f, _p, _i, _p]),
     "uic_beam_topk_merge": (_i, [_p, _i, _i, _p, _p, _i, _i, _p]),

@@ -75,7 +75,7 @@ def teacher_forced_run(model, fc_feats, att_feats, seq, att_masks, save=True, al
         r.X[:T, :, sl.fc[0]:sl.fc[1]] = feats.fc                       # fc is re-fed at every step (:432)
     if ss is not None:
         ss_prob, ss_seed = float(ss[0]), ss[1]
-        parts = int(lib.uic_logit_stats_parts(w.V))
+        parts = int(lib.uic_logit_stats_parts(B, w.V))
         ss_stats = torch.empty(B, parts, 4, dtype=torch.float32, device=dev)
         seq_l = seq.long().contiguous()
     for t in range(T):

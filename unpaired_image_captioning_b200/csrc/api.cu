@@ -273,7 +273,7 @@ int uic_gemm_bf16_ex(const void* A, int64_t lda, const void* B, int64_t ldb, flo
   return gemm_bf16(A, lda, B, ldb, c_f32, ldc, c_16, ldc16, bias, M, N, K, flags, ST(stream), exp_col0, exp_scale);
 }
 
-int uic_logit_stats_parts(int V) { return V > 0 ? logit_stats_parts(V) : 0; }
+int uic_logit_stats_parts(int rows, int V) { return V > 0 ? logit_stats_parts(rows, V) : 0; }
 int uic_logit_stats_entry_floats(int kslots) { return kslots > 0 ? logit_stats_entry_floats(kslots) : 0; }
 
 int uic_logit_stats(const void* h_bf16, int64_t ld_h, const void* w_logit_bf16, int64_t ld_w, const float* bias,

@@ -135,22 +135,25 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
-template <int BN, int STAGES>
+template <int BN, int STAGES, int STATS = 0>
 struct GemmSmem {
   static constexpr int A_BYTES = BM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int EPI_OFFSET = STAGES * STAGE_BYTES;
-  static constexpr int EPI_BYTES = EPI_WARPS * 32 * EPI_PITCH * 4;  // one 32 x 32 fp32 staging tile per epilogue warp
-  static constexpr int BAR_OFFSET = EPI_OFFSET + EPI_BYTES;
+  // storing kernels: one 32 x 32 fp32 staging tile per epilogue warp; statistics kernels: the double-buffered bias copy
+  static constexpr int EPI_BYTES = STATS > 0 ? 2 * BN * 4 : EPI_WARPS * 32 * EPI_PITCH * 4;
+  static constexpr int BAR_OFFSET = (EPI_OFFSET + EPI_BYTES + 15) / 16 * 16;
   static constexpr int TOTAL = BAR_OFFSET + 256 + 1024;  // barriers + alignment slack
+  // TMEM columns per accumulator buffer (allocations are powers of two; 224-wide tiles get 256-column buffers)
+  static constexpr int ACC_COLS = BN <= 64 ? 64 : (BN <= 128 ? 128 : 256);
 };
 
 template <int BN, int STAGES, bool A_MN, bool B_MN, int STATS>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                          GemmEpilogue ep, int M, int N, int K) {
-  using L = GemmSmem<BN, STAGES>;
+  using L = GemmSmem<BN, STAGES, STATS>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::BAR_OFFSET);
@@ -188,7 +191,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     fence_barrier_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_slot, 2 * BN);
+    tmem_alloc(tmem_slot, 2 * L::ACC_COLS);
     tmem_relinquish();
   }
   tcgen05_fence_before();
@@ -230,33 +233,47 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     // ===== MMA issuer (single thread) =====
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc_bf16(BM, BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
-      int g = 0;
+      // Shared-memory descriptors: everything but the start address is a compile-time constant, and a 16-element K step
+      // only adds to the address field.  The four descriptor pairs of a k-block are ready before its first MMA, so the
+      // four tcgen05.mma issue back to back (a first version rebuilt both 64-bit descriptors between two MMAs: 565 cycles
+      // per 128 x 128 x 64 block; now 520 = 4 x 130, the rate of the 1-CTA SS instruction at N <= 128 on this part --
+      // wider tiles amortise it: 128 x 256 x 64 takes 750).
+      //   K-major : 8-row groups 1024 B apart (SBO), LBO 16 B; a 16-element K step is 32 B inside the swizzle row.
+      //   MN-major: 64-element MN chunks BK*128 B apart (LBO), 8-k-row groups 1024 B apart (SBO); a K step is 2048 B.
+      constexpr uint64_t DESC_A = (static_cast<uint64_t>(1) << 46) | (static_cast<uint64_t>(2) << 61) |
+                                  (static_cast<uint64_t>(((A_MN ? BK * 128 : 16) >> 4) & 0x3FFF) << 16) |
+                                  (static_cast<uint64_t>((1024 >> 4) & 0x3FFF) << 32);
+      constexpr uint64_t DESC_B = (static_cast<uint64_t>(1) << 46) | (static_cast<uint64_t>(2) << 61) |
+                                  (static_cast<uint64_t>(((B_MN ? BK * 128 : 16) >> 4) & 0x3FFF) << 16) |
+                                  (static_cast<uint64_t>((1024 >> 4) & 0x3FFF) << 32);
+      constexpr uint32_t KSTEP_A = (A_MN ? 2048 : 32) >> 4, KSTEP_B = (B_MN ? 2048 : 32) >> 4;  // in 16-byte units
+      const uint32_t ring0 = smem_u32(smem) >> 4;
+      uint32_t s = 0, ph = 0;  // ring position: carries over from tile to tile
       for (int tile = blockIdx.x, it = 0; tile < num_tiles; tile += gridDim.x, ++it) {
         const int acc = it & 1;
         mbar_wait(&tmem_empty_bar[acc], ((it >> 1) & 1) ^ 1);  // epilogue has drained this accumulator
         tcgen05_fence_after();
-        const uint32_t tmem_d = tmem_base + acc * BN;
+        const uint32_t tmem_d = tmem_base + acc * L::ACC_COLS;
         UIC_TRACE(0);
-        for (int kb = 0; kb < num_kb; ++kb, ++g) {
-          const int s = g % STAGES;
-          const uint32_t ph = (g / STAGES) & 1;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          const uint32_t a_lo = ring0 + s * (L::STAGE_BYTES >> 4), b_lo = a_lo + (L::A_BYTES >> 4);
+          uint64_t da[BK / 16], db[BK / 16];
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            da[k] = DESC_A | static_cast<uint64_t>(a_lo + k * KSTEP_A);
+            db[k] = DESC_B | static_cast<uint64_t>(b_lo + k * KSTEP_B);
+          }
           mbar_wait(&full_bar[s], ph);
           if (kb < 32) UIC_TRACE(1 + kb);
           tcgen05_fence_after();
-          const uint32_t a_base = smem_u32(smem + s * L::STAGE_BYTES);
-          const uint32_t b_base = a_base + L::A_BYTES;
+          umma_bf16_ss(tmem_d, da[0], db[0], idesc, kb != 0 ? 1u : 0u);
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            // K-major : 8-row groups 1024 B apart (SBO); a 16-element K step is 32 B inside the swizzle row.
-            // MN-major: 64-element MN chunks BK*128 B apart (LBO), 8-k-row groups 1024 B apart (SBO);
-            //           a 16-row K step is 2048 B.
-            const uint64_t da = A_MN ? make_smem_desc_sw128(a_base + k * 2048, BK * 128, 1024)
-                                     : make_smem_desc_sw128(a_base + k * 32, 16, 1024);
-            const uint64_t db = B_MN ? make_smem_desc_sw128(b_base + k * 2048, BK * 128, 1024)
-                                     : make_smem_desc_sw128(b_base + k * 32, 16, 1024);
-            umma_bf16_ss(tmem_d, da, db, idesc, (kb | k) != 0 ? 1u : 0u);
-          }
+          for (int k = 1; k < BK / 16; ++k) umma_bf16_acc(tmem_d, da[k], db[k], idesc);
           umma_commit(&empty_bar[s]);  // frees the smem slot once these MMAs have read it
+          if (++s == STAGES) {
+            s = 0;
+            ph ^= 1;
+          }
         }
         umma_commit(&tmem_full_bar[acc]);  // accumulator complete
         UIC_TRACE(40);
@@ -266,7 +283,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     // ===== epilogue: TMEM -> registers -> smem transpose -> coalesced global stores =====
     const int ew = warp & 3;            // the TMEM lane quarter this warp may access (hardware rule: warp % 4)
     const int ehalf = (warp - 4) >> 2;  // warps 4-7 take the first half of the tile's column chunks, warps 8-11 the second
-    constexpr int CHUNKS = BN / 32 / 2;
+    constexpr int NCH = BN / 32;          // 32-column chunks of a tile (7 for the 224-wide statistics tiles)
+    constexpr int CHUNKS = (NCH + 1) / 2; // chunks of the first half; the second half has NCH - CHUNKS
     const uint32_t stage_s = smem_u32(smem + L::EPI_OFFSET) + (warp - 4) * 32 * EPI_PITCH * 4;  // this warp's 32 x 32 fp32 staging tile
     const int q = lane & 7, rsub = lane >> 3;  // this lane stores columns 4q..4q+3 of rows rsub, rsub+4, ...
     const bool vec_f32 = ep.c_f32 != nullptr && (ep.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(ep.c_f32) & 15) == 0);
@@ -302,10 +320,11 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
 #pragma unroll
         for (int cc = 0; cc < CHUNKS; ++cc) {
           const int c = ehalf * CHUNKS + cc;
+          if (c >= NCH) continue;  // (odd chunk count: the second half is one chunk shorter; warp-uniform)
           const int col0 = n0 + c * 32;
           uint32_t v[32];
           __syncwarp();
-          tmem_ld_32x32(tmem_base + acc * BN + (static_cast<uint32_t>(ew * 32) << 16) + c * 32, v);
+          tmem_ld_32x32(tmem_base + acc * L::ACC_COLS + (static_cast<uint32_t>(ew * 32) << 16) + c * 32, v);
           tmem_ld_wait();
           if (col0 >= N) continue;  // warp-uniform
           float x[32];
@@ -400,7 +419,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         const int col0 = n0 + c * 32;
         uint32_t v[32];
         __syncwarp();
-        if (!(ep.debug & 2)) tmem_ld_32x32(tmem_base + acc * BN + (static_cast<uint32_t>(ew * 32) << 16) + c * 32, v);
+        if (!(ep.debug & 2)) tmem_ld_32x32(tmem_base + acc * L::ACC_COLS + (static_cast<uint32_t>(ew * 32) << 16) + c * 32, v);
         const float4 b4 = bias4[cc];
         const int cq = col0 + 4 * q;
         tmem_ld_wait();
@@ -496,7 +515,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
 
   tcgen05_fence_before();
   __syncthreads();
-  if (warp == 2) tmem_dealloc(tmem_base, 2 * BN);
+  if (warp == 2) tmem_dealloc(tmem_base, 2 * L::ACC_COLS);
   if (ep.trace != nullptr && threadIdx.x == 0 && blockIdx.x < 448) {  // CTA exit time
     long long tnow;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tnow));
@@ -607,7 +626,8 @@ template <int BN, int STAGES, bool A_MN, bool B_MN, int STATS = 0>
 static int launch_tc(const CUtensorMap& ta, const CUtensorMap& tb, const GemmEpilogue& ep, int M, int N, int K,
                      cudaStream_t stream) {
   auto kern = gemm_bf16_tcgen05_kernel<BN, STAGES, A_MN, B_MN, STATS>;
-  constexpr int smem = GemmSmem<BN, STAGES>::TOTAL;
+  constexpr int smem = GemmSmem<BN, STAGES, STATS>::TOTAL;
+  static_assert(smem <= 227 * 1024, "shared memory budget");
   static bool configured = false;  // benign race: attribute set is idempotent
   if (!configured) {
     UIC_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -663,7 +683,7 @@ int gemm_bf16(const void* A, long long lda, const void* B, long long ldb, float*
   const int sms = sm_count();
   int bn = 64;
   long long best = -1;
-  const int widths[3] = {64, 128, 256}, cycles[3] = {430, 571, 750};
+  const int widths[3] = {64, 128, 256}, cycles[3] = {520, 521, 750};
   for (int i = 0; i < 3; ++i) {
     if (widths[i] > 64 && N <= widths[i] / 2) continue;  // mostly padding
     const long long tiles = tiles_m * ((N + widths[i] - 1) / widths[i]);
@@ -689,7 +709,26 @@ int gemm_bf16(const void* A, long long lda, const void* B, long long ldb, float*
   return dispatch_major<128, 5>(a_mn, b_mn, ta, tb, ep, M, N, K, stream);
 }
 
-int logit_stats_parts(int N) { return 2 * ((N + 127) / 128); }
+// Tile width of the statistics GEMM: 224 columns where that shortens the makespan (rounds of tiles over the SMs x measured
+// cycles per k-block: 520 for 128 x 128 x 64, ~700 for 128 x 224 x 64) -- 768 x 10000 is 270 tiles = 2 rounds instead of
+// 474 = 4, and the step tail merges 90 parts per row instead of 158.  A function of the problem shape only: the stats
+// layout (two parts per tile) follows it.
+static int stats_tile_width(int M, int N) {
+  static int forced = -1;  // UIC_STATS_BN=128|224 pins it (A/B experiments)
+  if (forced < 0) {
+    const char* e = getenv("UIC_STATS_BN");
+    forced = e ? atoi(e) : 0;
+  }
+  if (forced == 128 || forced == 224) return forced;
+  const long long tiles_m = (M + BM - 1) / BM, sms = sm_count();
+  const long long r128 = (tiles_m * ((N + 127) / 128) + sms - 1) / sms * 520;
+  const long long r224 = (tiles_m * ((N + 223) / 224) + sms - 1) / sms * 700;
+  return r224 < r128 ? 224 : 128;
+}
+int logit_stats_parts(int M, int N) {
+  const int bn = stats_tile_width(M, N);
+  return 2 * ((N + bn - 1) / bn);
+}
 int logit_stats_entry_floats(int kslots) { return (2 + 2 * kslots + 3) / 4 * 4; }
 
 // Logit projection with the fused statistics epilogue: stats[row][part][logit_stats_entry_floats(kslots)].
@@ -703,14 +742,23 @@ int logit_stats(const void* A, long long lda, const void* B, long long ldb, cons
   if ((reinterpret_cast<uintptr_t>(A) & 15) || (reinterpret_cast<uintptr_t>(B) & 15) || (lda % 8) || (ldb % 8) ||
       (reinterpret_cast<uintptr_t>(stats) & 15))
     return set_error(UIC_ERR_ALIGN, "logit_stats: operands and stats must be 16-byte aligned with pitches that are multiples of 8 elements");
-  GemmEpilogue ep{nullptr, 0, nullptr, 0, bias, 0, 0, 0, 0, 0.0f, nullptr, 0, stats, banned, banned_stride, logit_stats_parts(N), unk_suppress ? N - 1 : -1,
+  GemmEpilogue ep{nullptr, 0, nullptr, 0, bias, 0, 0, 0, 0, 0.0f, nullptr, 0, stats, banned, banned_stride, logit_stats_parts(M, N), unk_suppress ? N - 1 : -1,
                   temperature > 0.0f ? 1 : 0, temperature > 0.0f ? 1.0f / temperature : 1.0f, seed, step};
   gemm_l2_policies(ep, M, N, K, 0);
   CUtensorMap ta, tb;
   int rc = get_tensor_map_bf16(&ta, A, M, K, lda, BM, 64);
   if (rc) return rc;
-  rc = get_tensor_map_bf16(&tb, B, N, K, ldb, 128, 64);
+  const int bn = stats_tile_width(M, N);
+  rc = get_tensor_map_bf16(&tb, B, N, K, ldb, bn, 64);
   if (rc) return rc;
+  ep.debug = gemm_debug_flags();
+  ep.trace = gemm_trace_buffer();
+  if (bn == 224) {
+    if (kslots == 1) return launch_tc<224, 4, false, false, 1>(ta, tb, ep, M, N, K, stream);
+    if (kslots == 3) return launch_tc<224, 4, false, false, 3>(ta, tb, ep, M, N, K, stream);
+    if (kslots == 5) return launch_tc<224, 4, false, false, 5>(ta, tb, ep, M, N, K, stream);
+    return launch_tc<224, 4, false, false, 8>(ta, tb, ep, M, N, K, stream);
+  }
   if (kslots == 1) return launch_tc<128, 5, false, false, 1>(ta, tb, ep, M, N, K, stream);
   if (kslots == 3) return launch_tc<128, 5, false, false, 3>(ta, tb, ep, M, N, K, stream);
   if (kslots == 5) return launch_tc<128, 5, false, false, 5>(ta, tb, ep, M, N, K, stream);

@@ -63,7 +63,7 @@ __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepc
 int gemm_bf16(const void* A, long long lda, const void* B, long long ldb, float* c_f32, long long ldc, void* c_bf16,
               long long ldcb, const float* bias, int M, int N, int K, int flags, cudaStream_t stream, int exp_col0 = 0,
               float exp_scale = 0.0f);
-int logit_stats_parts(int N);
+int logit_stats_parts(int M, int N);
 int logit_stats_entry_floats(int kslots);
 int logit_stats(const void* A, long long lda, const void* B, long long ldb, const float* bias, const long long* banned,
                 long long banned_stride, float* stats, int M, int N, int K, int kslots, int unk_suppress, float temperature,

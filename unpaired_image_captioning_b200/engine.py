@@ -407,7 +407,7 @@ class DecoderEngine:
                  "seq": torch.zeros(B, T, dtype=torch.int64, device=dev), "lp": torch.zeros(B, T, device=dev),
                  "unf": torch.zeros(B, dtype=torch.uint8, device=dev), "tok": torch.zeros(B, dtype=torch.int64, device=dev),
                  "nunf": torch.zeros(T, dtype=torch.int32, device=dev), "seed": torch.zeros(1, dtype=torch.int64, device=dev),
-                 "parts": int(lib.uic_logit_stats_parts(w.V))}
+                 "parts": int(lib.uic_logit_stats_parts(B, w.V))}
             s["stats"] = torch.empty(B, s["parts"], 4, dtype=torch.float32, device=dev)
             s["feats"] = Features(s["att"], s["p_att"], s["fc"], s["masks"], B, feats.L)
             s["X"], s["c"], s["sl"] = self._new_state(B, dev, s["feats"], 1)
@@ -482,7 +482,8 @@ class DecoderEngine:
                  "done_p": torch.zeros(B, b, dtype=torch.float64, device=dev), "done_unaug": torch.zeros(B, b, device=dev),
                  "done_cnt": torch.zeros(B, dtype=torch.int32, device=dev),
                  "parent": torch.zeros(R, dtype=torch.int32, device=dev), "tok": torch.zeros(R, dtype=torch.int64, device=dev),
-                 "parts": int(lib.uic_logit_stats_parts(w.V)), "kslots": 1 if b == 1 else 3 if b <= 3 else 5 if b <= 5 else 8}
+                 "parts": int(lib.uic_logit_stats_parts(R, w.V)), "parts0": int(lib.uic_logit_stats_parts(B, w.V)),
+                 "kslots": 1 if b == 1 else 3 if b <= 3 else 5 if b <= 5 else 8}
             s["stats"] = torch.empty(R, s["parts"], int(lib.uic_logit_stats_entry_floats(s["kslots"])), dtype=torch.float32, device=dev)
             s["feats"] = Features(s["att"], s["p_att"], s["fc"], s["masks"], B, feats.L)
             s["X"], s["c"], s["sl"] = self._new_state(R, dev, s["feats"], b)
@@ -492,7 +493,7 @@ class DecoderEngine:
                 # the first step reads beam 0 of every image only (rows = 1, CaptionModel.py:56): run it on B rows
                 s["X0"], s["c0"], _ = self._new_state(B, dev, s["feats"], 1)
                 s["ws0"] = self._workspace(B, dev)
-                s["stats0"] = torch.empty(B, s["parts"], s["stats"].shape[2], dtype=torch.float32, device=dev)
+                s["stats0"] = torch.empty(B, s["parts0"], s["stats"].shape[2], dtype=torch.float32, device=dev)
                 s["tok0"] = torch.zeros(B, dtype=torch.int64, device=dev)
                 s["img_idx0"] = torch.arange(B, device=dev, dtype=torch.int64)
             return s
@@ -518,7 +519,7 @@ class DecoderEngine:
                 check(lib.uic_logit_stats(ptr(h), h.stride(0), ptr(w.w_logit), w.H, ptr(w.b_logit), None, 1,
                                           ptr(s["stats0"]), B, w.V, w.H, s["kslots"], 1, 0.0, None, 0, stream()))
                 Xn, cn = bufs[1]
-                check(lib.uic_beam_advance(ptr(s["stats0"]), s["parts"], s["kslots"], ptr(s["beam_seq"]), ptr(s["beam_lp"]),
+                check(lib.uic_beam_advance(ptr(s["stats0"]), s["parts0"], s["kslots"], ptr(s["beam_seq"]), ptr(s["beam_lp"]),
                                            ptr(s["beam_sum"]), ptr(s["done_seq"]), ptr(s["done_lp"]), ptr(s["done_p"]),
                                            ptr(s["done_unaug"]), ptr(s["done_cnt"]), ptr(s["parent"]), ptr(s["tok"]), 0, T, B, b,
                                            bs_flags, int(1 < T), ptr(X0), ptr(Xn), Xn.stride(0), ga, na, gb, nb, ptr(c0), ptr(cn),
