@@ -1,17 +1,23 @@
 #!/usr/bin/env python
-"""Benchmark of the decoder hot path (BASELINE.json metric: beam-3 captions/s + train samples/s).
+"""Benchmark of the decoder hot path (BASELINE.json metric: train samples/s + beam-3 captions/s; % roofline).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload cfg2|cfg3|cfg5] [--strong]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-One "step" = one pass of the hot path over one batch of synthetic input: beam-3 sampling of a
-256-image batch with the att2in2 decoder (BASELINE.json configs[1]: rnn 512, 14x14x2048 features,
-vocab 10k, seq 16), prologue GEMMs included.  Rank 0 prints ONE JSON line.
+One "step" = one pass of the hot path over one batch of synthetic input.  Rank 0 prints ONE JSON line.
 
-  value    : captions/s with the fp32 features already resident in HBM (device-timed, CUDA events)
-  e2e      : captions/s through the reference-facing API `model(fc, attri, att, masks, opt, mode='sample')`
-             from pinned HOST buffers: H2D of the features and D2H of the sequences inside the timing
-  roofline : the fused attention-step kernel (HBM-bound), timed live with CUDA events per launch
+  --workload cfg2 (default, BASELINE.json configs[1]): beam-3 sampling of a 256-image batch with the att2in2 decoder
+      (rnn 512, 14x14x2048 features, vocab 10k, seq 16), prologue GEMMs included.
+        value    : captions/s with the fp32 features already resident in HBM (device-timed, CUDA events)
+        e2e      : captions/s through `model(fc, attri, att, masks, opt, mode='sample')` fed by the package's FeatureStream
+                   from a pinned HOST FeatureCache (bf16, the operand precision): H2D of the features and D2H of the
+                   sequences inside the timing; `e2e.fp32_host_features` is the same loop with the reference's fp32 arrays
+        roofline : the fused attention-step kernel (HBM-bound), timed live with CUDA events per launch; `roofline.gemms`
+                   lists the tcgen05 GEMMs of the step against the measured bf16 peak
+        config.legs : greedy, the TopDown training step (configs[2], weak and -- N > 1 -- strong scaling), configs[4]
+                   (beam-5, vocab 30k, rnn 1024) and the stock-PyTorch eager decoder on the same GPU
+  --workload cfg3: the TopDown XE training step is the headline (`--strong`: global batch 512 split over the ranks)
+  --workload cfg5: beam-5 sampling of 500-image chunks of configs[4]
   cpu_baseline / --impl reference : the oracle port of the reference's CPU path on this box's cores
 """
 from __future__ import annotations
@@ -30,16 +36,15 @@ sys.path.insert(0, ROOT)
 
 import torch  # noqa: E402
 
-WORKLOAD = "cfg2"
-
 
 def _peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
             p = json.load(f)
-        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        return {"hbm_gbs": float(p["hbm_gbs"]), "bf16_tflops": float(p.get("bf16_tflops_sustained", p["bf16_tflops"])),
+                "source": "measured (MEASURED_PEAKS.json; bf16 = sustained cuBLAS figure)"}
     except Exception:
-        return 6650.0, "fallback (B200_PROFILING.md)"
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1500.0, "source": "fallback (B200_PROFILING.md)"}
 
 
 class ClockSampler:
@@ -77,10 +82,7 @@ class ClockSampler:
 
 
 def _dist():
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    return world, rank, local
+    return int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0"))
 
 
 def _barrier(world):
@@ -113,6 +115,8 @@ def _timed(fn, steps, warmup, world):
 
 
 def _timed_wall(fn, steps, warmup, world):
+    """Same bracket with the host clock: for legs whose step ends with a device-to-host read (the result is on the host
+    when the step returns), so the wall clock between two synchronisation points is the device + copy time."""
     for _ in range(warmup):
         fn()
     _barrier(world)
@@ -125,8 +129,47 @@ def _timed_wall(fn, steps, warmup, world):
     return _max_over_ranks(ms, world) / steps
 
 
+def _bind_near_gpu(local):
+    """N > 1: pin this rank's threads to the CPUs of the NUMA node its GPU hangs off, BEFORE the pinned host cache is
+    allocated (first touch).  Returns the node (or None when the topology is not exposed, e.g. a single-node VM)."""
+    try:
+        p = torch.cuda.get_device_properties(local)
+        bdf = "%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
+        with open("/sys/bus/pci/devices/%s/numa_node" % bdf) as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        with open("/sys/devices/system/node/node%d/cpulist" % node) as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
+
+
+def _workload_config(name, cfg, opt, world, extra=None):
+    label = {"cfg2": "configs[1]: att2in2 decoder beam-%d sampling" % cfg["beam_size"],
+             "cfg3": "configs[2]: TopDown XE training step (fwd + loss + bwd + gradient all-reduce + clip + Adam)",
+             "cfg5": "configs[4]: att2in2 rnn 1024 / vocab 30k beam-%d sampling, one 500-image chunk per step" % cfg["beam_size"]}[name]
+    c = {"workload": label, "caption_model": opt.caption_model, "rows_per_gpu": cfg["batch"], "beam_size": cfg["beam_size"],
+         "att_regions": cfg["att_size"], "att_feat_size": opt.att_feat_size, "rnn_size": opt.rnn_size,
+         "vocab": opt.vocab_size + 1, "seq_length": opt.seq_length, "parallelism": f"dp{world}",
+         "l2": "inputs larger than L2 (%d MB of fp32 features per step, 126 MB L2); no flush needed"
+               % (cfg["batch"] * cfg["att_size"] * opt.att_feat_size * 4 // 2 ** 20)}
+    c.update(extra or {})
+    return c
+
+
 # ----------------------------------------------------------------------------------------------------
-def cpu_baseline(cfg, opt, sd, fc, att, repeats, threads, gpu_seq=None):
+# CPU baselines (the oracle port of the reference's CPU path; bounded samples)
+# ----------------------------------------------------------------------------------------------------
+def cpu_beam_baseline(cfg, opt, sd, fc, att, repeats, threads, gpu_seq=None):
     """Oracle port of the reference's CPU beam search on a bounded sample of the same workload: `fc`, `att` are the first
     images of the very batch the GPU leg decoded, and `gpu_seq` its captions for them -- they must equal the oracle's
     (except at decision margins inside the north-star tolerance), so the timed GPU result is tied to the oracle."""
@@ -151,24 +194,52 @@ def cpu_baseline(cfg, opt, sd, fc, att, repeats, threads, gpu_seq=None):
     return fc.size(0) / best, check
 
 
+def cpu_train_baseline(cfg_name, rows, repeats, threads):
+    """Oracle port of the reference's CPU training computation (teacher-forced forward + masked XE + backward, fp32) on
+    `rows` rows of the named workload; samples/s."""
+    from oracle import decoder_oracle as O
+    from unpaired_image_captioning_b200 import synth
+    torch.set_num_threads(threads)
+    opt, cfg = synth.opt_for(cfg_name)
+    sd = synth.init_state_dict(opt, seed=1234)
+    fc, att = synth.make_features(rows, cfg["att_size"], opt.att_feat_size, seed=4321)
+    labels, masks = synth.make_captions(rows, opt.seq_length, opt.vocab_size, seed=4321)
+    best = float("inf")
+    for i in range(repeats + 1):
+        t0 = time.perf_counter()
+        O.loss_and_grads(sd, opt.caption_model, fc, att, labels, masks)
+        dt = time.perf_counter() - t0
+        if i > 0:
+            best = min(best, dt)
+    return {"value": rows / best, "unit": "samples/s", "cores": threads, "kind": "port",
+            "sample": f"{cfg_name} shapes, {rows} rows: oracle teacher-forced forward + XE + backward, best of {repeats} after warm-up, torch CPU fp32"}
+
+
 def run_reference(args, world, rank):
-    """`--impl reference`: the reference's own CPU implementation of the path (oracle port: the
-    reference is Python and /root/reference does not exist on the GPU box), all host threads."""
+    """`--impl reference`: the reference's own CPU implementation of the path (oracle port: the reference is Python and
+    /root/reference does not exist on the GPU box), all host threads, same metric / unit as the b200 arm's workload."""
     if rank != 0:
         return
     from oracle import decoder_oracle as O
     from unpaired_image_captioning_b200 import synth
-    opt, cfg = synth.opt_for(WORKLOAD)
+    opt, cfg = synth.opt_for(args.workload)
     sd = synth.init_state_dict(opt, seed=1234)
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
-    sample = 8
-    fc, att = synth.make_features(sample, cfg["att_size"], opt.att_feat_size, seed=99)
+    if args.workload == "cfg3":
+        sample = 16
+        fc, att = synth.make_features(sample, cfg["att_size"], opt.att_feat_size, seed=4321)
+        labels, masks = synth.make_captions(sample, opt.seq_length, opt.vocab_size, seed=4321)
+        step = lambda: O.loss_and_grads(sd, opt.caption_model, fc, att, labels, masks)
+        metric, unit, what = "train_samples_per_s", "samples/s", "teacher-forced forward + XE + backward"
+    else:
+        sample = 8 if args.workload == "cfg2" else 2
+        fc, att = synth.make_features(sample, cfg["att_size"], opt.att_feat_size, seed=1234)
 
-    def step():
-        with torch.no_grad():
-            O.sample_beam(sd, opt.caption_model, fc, att, opt.seq_length, cfg["beam_size"])
-
+        def step():
+            with torch.no_grad():
+                O.sample_beam(sd, opt.caption_model, fc, att, opt.seq_length, cfg["beam_size"])
+        metric, unit, what = "beam%d_captions_per_s" % cfg["beam_size"], "captions/s", "beam-%d sampling" % cfg["beam_size"]
     for _ in range(args.warmup):
         step()
     t0 = time.perf_counter()
@@ -176,64 +247,24 @@ def run_reference(args, world, rank):
         step()
     dt = time.perf_counter() - t0
     value = sample * args.steps / dt
-    line = {"impl": "reference", "metric": "beam3_captions_per_s", "value": value, "unit": "captions/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": _config(cfg, opt, sample_note=f"each step = beam-{cfg['beam_size']} over a bounded sample of {sample} images"),
-            "cpu_baseline": {"value": value, "unit": "captions/s", "cores": threads, "kind": "port",
-                             "sample": f"{sample} images x {args.steps} steps, oracle/decoder_oracle.py sample_beam, torch CPU fp32"},
-            "e2e": {"value": value, "unit": "captions/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0}
-    _emit(line)
-
-
-def _config(cfg, opt, sample_note=None):
-    c = {"workload": "configs[1]: att2in2 decoder beam-%d sampling (greedy reported beside it)" % cfg["beam_size"],
-         "caption_model": opt.caption_model, "images_per_gpu": cfg["batch"], "beam_size": cfg["beam_size"],
-         "att_regions": cfg["att_size"], "att_feat_size": opt.att_feat_size, "rnn_size": opt.rnn_size,
-         "vocab": opt.vocab_size + 1, "seq_length": opt.seq_length,
-         "l2": "inputs larger than L2 (411 MB of fp32 features per step, 126 MB L2); no flush needed"}
-    if sample_note:
-        c["sample"] = sample_note
-    return c
-
-
-def _bind_near_gpu(local):
-    """N > 1: pin this rank's threads to the CPUs of the NUMA node its GPU hangs off, BEFORE the pinned staging buffers are
-    allocated (first touch), so that eight ranks do not stream their 413 MB per step through one socket's memory
-    controllers and the inter-socket link.  Returns the node (or None when the topology is not exposed)."""
-    try:
-        p = torch.cuda.get_device_properties(local)
-        bdf = "%04x:%02x:%02x.0" % (p.pci_domain_id, p.pci_bus_id, p.pci_device_id)
-        with open("/sys/bus/pci/devices/%s/numa_node" % bdf) as f:
-            node = int(f.read().strip())
-        if node < 0:
-            return None
-        with open("/sys/devices/system/node/node%d/cpulist" % node) as f:
-            cpus = set()
-            for part in f.read().strip().split(","):
-                lo, _, hi = part.partition("-")
-                cpus.update(range(int(lo), int(hi or lo) + 1))
-        cpus &= os.sched_getaffinity(0)
-        if not cpus:
-            return None
-        os.sched_setaffinity(0, cpus)
-        return node
-    except Exception:
-        return None
+    note = f"each step = {what} over a bounded sample of {sample} rows of the workload"
+    _emit({"impl": "reference", "metric": metric, "value": value, "unit": unit, "n_gpus": args.gpus, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": _workload_config(args.workload, cfg, opt, world, {"sample": note}),
+           "cpu_baseline": {"value": value, "unit": unit, "cores": threads, "kind": "port",
+                            "sample": f"{sample} rows x {args.steps} steps, oracle/decoder_oracle.py ({what}), torch CPU fp32"},
+           "e2e": {"value": value, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0})
 
 
 # ----------------------------------------------------------------------------------------------------
-def run_b200(args, world, rank, local):
+# legs
+# ----------------------------------------------------------------------------------------------------
+def _decode_legs(args, world, rank, local, cfg_name, steps, with_roofline):
+    """Beam (and greedy) decode of one workload: device-resident, end to end from the host cache, kernel profile."""
     import unpaired_image_captioning_b200 as uic
     from unpaired_image_captioning_b200 import _lib, synth
-
-    torch.cuda.set_device(local)
-    if world > 1:
-        torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local))
-    _lib.require_device()
-    numa_node = _bind_near_gpu(local) if world > 1 else None
-    opt, cfg = synth.opt_for(WORKLOAD)
+    opt, cfg = synth.opt_for(cfg_name)
     B, beam, T = cfg["batch"], cfg["beam_size"], opt.seq_length
     sd = synth.init_state_dict(opt, seed=1234)                     # identical weights on every rank
     model = uic.setup(opt)
@@ -241,84 +272,45 @@ def run_b200(args, world, rank, local):
     model = model.cuda().eval()
     eng = model.engine
     fc_h, att_h = synth.make_features(B, cfg["att_size"], opt.att_feat_size, seed=1234 + rank)   # per-rank images
-    fc_h, att_h = fc_h.pin_memory(), att_h.pin_memory()
     fc_d, att_d = fc_h.cuda(), att_h.cuda()
-    sampler = ClockSampler(local)
-    sampler.start()
+    out = {"opt": opt, "cfg": cfg, "sd": sd, "fc_h": fc_h, "att_h": att_h}
 
-    # ---- device-resident legs ------------------------------------------------------------------
     def beam_step():
-        feats = eng.prepare(fc_d, att_d, lazy=True)
-        eng.beam(feats, T, beam)
+        eng.beam(eng.prepare(fc_d, att_d, lazy=True), T, beam)
 
     def greedy_step():
-        feats = eng.prepare(fc_d, att_d, lazy=True)
-        eng.greedy(feats, T)
+        eng.greedy(eng.prepare(fc_d, att_d, lazy=True), T)
 
-    ms_beam = _timed(beam_step, args.steps, args.warmup, world)
+    out["ms_beam"] = _timed(beam_step, steps, args.warmup, world)
     l0 = eng.launches()
     beam_step()                                   # one more (untimed) step just to count its kernels
-    launches = eng.launches() - l0
+    out["launches"] = eng.launches() - l0
     # the captions of the timed plan (same graph, same inputs), kept for the oracle check beside cpu_baseline
-    timed_seq = eng.beam(eng.prepare(fc_d, att_d, lazy=True), T, beam)[0][:, 0].long().cpu()
-    ms_greedy = _timed(greedy_step, args.steps, args.warmup, world)
+    out["timed_seq"] = eng.beam(eng.prepare(fc_d, att_d, lazy=True), T, beam)[0][:, 0].long().cpu()
+    out["ms_greedy"] = _timed(greedy_step, steps, args.warmup, world)
 
-    # ---- end-to-end leg through the public API, host buffers -------------------------------------
+    # ---- end to end through the public API: host FeatureCache -> FeatureStream -> model(..., mode='sample') -> host ----
     sample_opt = {"beam_size": beam}
-    # Input pipeline of the e2e leg: every step copies its own batch host->device (pinned memory) and reads
-    # its sequences back; the copy of step i+1 is issued on a side stream while step i decodes (two device
-    # buffer sets), as a loader would.  Each timed step still contains exactly one H2D and one D2H.
-    copy_stream = torch.cuda.Stream()
+    d2h = B * beam * T * (8 + 4) + B * beam * (8 + 4) + B * 4      # done tables: seq (int64 after cast) + logps, p, unaug, cnt
 
-    def make_e2e(att_host):
-        dev_bufs = [(torch.empty_like(fc_d), torch.empty(att_host.shape, dtype=att_host.dtype, device=fc_d.device)) for _ in range(2)]
-        pipe = {"i": 0, "ready": None}
+    def e2e_leg(dtype):
+        cache = uic.FeatureCache(fc_h, att_h, dtype=dtype)
+        it = iter(uic.FeatureStream(cache, B, torch.device("cuda", local), loop=True))
 
-        def _prefetch(slot):
-            with torch.cuda.stream(copy_stream):
-                dev_bufs[slot][0].copy_(fc_h, non_blocking=True)
-                dev_bufs[slot][1].copy_(att_host, non_blocking=True)
-                ev = torch.cuda.Event()
-                ev.record(copy_stream)
-            return ev
-
-        def e2e_step():
-            slot = pipe["i"] % 2
-            ev = pipe["ready"] if pipe["ready"] is not None else _prefetch(slot)
-            torch.cuda.current_stream().wait_event(ev)
-            pipe["ready"] = _prefetch(1 - slot)      # next step's batch, overlapped with this step's decode
-            pipe["i"] += 1
-            fc, att = dev_bufs[slot]
-            seq, lp = model(fc, None, att, None, opt=sample_opt, mode="sample")   # returns CPU tensors (D2H inside)
+        def step():
+            fc, att, masks, _ = next(it)
+            seq, lp = model(fc, None, att, masks, opt=sample_opt, mode="sample")   # returns CPU tensors (D2H inside)
             return seq
 
-        return e2e_step
+        ms = _timed_wall(step, steps, args.warmup, world)
+        return {"value": world * B / (ms * 1e-3), "unit": "captions/s", "ms_per_step": ms, "h2d_bytes_per_step": cache.nbytes(B),
+                "d2h_bytes_per_step": d2h, "host_gbs_per_rank": cache.nbytes(B) / (ms * 1e-3) / 1e9}
 
-    ms_e2e = _timed_wall(make_e2e(att_h), args.steps, args.warmup, world)
-    h2d = fc_h.numel() * 4 + att_h.numel() * 4
-    d2h = B * beam * T * (8 + 4) + B * beam * (8 + 4) + B * 4      # done tables: seq(int64 after cast)+logps, p, unaug, cnt
-    # the same loop fed from a bf16 feature cache on the host: half the PCIe bytes, no staging cast.
-    # Reported beside the contract's e2e number, which keeps the reference's fp32 inputs.
-    att_h16 = att_h.to(torch.bfloat16).pin_memory()
-    ms_e2e16 = _timed_wall(make_e2e(att_h16), args.steps, args.warmup, world)
-    e2e_bf16 = {"value": world * B / (ms_e2e16 * 1e-3), "unit": "captions/s", "ms_per_step": ms_e2e16,
-                "h2d_bytes_per_step": fc_h.numel() * 4 + att_h16.numel() * 2, "d2h_bytes_per_step": d2h,
-                "note": "host features cached in bf16 (the precision the kernels consume); not the contract's e2e"}
-    del att_h16
+    out["e2e_bf16"] = e2e_leg(torch.bfloat16)
+    out["e2e_fp32"] = e2e_leg(torch.float32)
 
-    # ---- training leg (teacher-forced fwd + XE + bwd + Adam), if the autograd path is present -------
-    train = None
-    if not args.no_train:
-        try:
-            from unpaired_image_captioning_b200.train_bench import train_samples_per_s
-            train = train_samples_per_s(args, world, rank, local)
-        except ImportError:
-            train = None
-    clocks = sampler.stop()
-
-    # ---- live per-kernel timing of one eager (non-graph) step: roofline of the dominant kernel -----
-    roofline, shares = None, None
-    if rank == 0:
+    # ---- live per-kernel timing of one eager (non-graph) step ---------------------------------------------------------
+    if with_roofline and rank == 0:
         eng.use_graphs = False
         beam_step()
         torch.cuda.synchronize()
@@ -328,42 +320,174 @@ def run_b200(args, world, rank, local):
         prof = _lib.profile_dump()
         _lib.profile(False)
         eng.use_graphs = True
-        total = sum(ms for _, ms in prof.values())
-        shares = {k: {"launches": n // 3, "ms_per_step": ms / 3, "share": ms / total}
-                  for k, (n, ms) in sorted(prof.items(), key=lambda kv: -kv[1][1])[:8]}
-        n_att, ms_att = prof["att_step_fwd"]
-        peak, how = _peaks()
-        alg_bytes = B * cfg["att_size"] * (opt.att_hid_size + opt.rnn_size) * 2      # p_att + att tiles, bf16, once per image
-        achieved = alg_bytes / (ms_att / n_att * 1e-3) / 1e9
-        traffic, traffic_src = _ncu_traffic()
-        roofline = {"kernel": "att_step_fwd", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": traffic, "peak_source": how,
-                    "algorithmic_bytes_per_launch": alg_bytes, "us_per_launch": ms_att / n_att * 1e3,
-                    "traffic_source": traffic_src,
-                    "note": "duration: live CUDA-event pairs around every launch of an eager decode in this run; traffic: "
-                            "dram__bytes_read.sum + dram__bytes_write.sum of the committed ncu --set full capture of the same launch"}
+        out["profile"] = {k: (n / 3.0, ms / 3.0) for k, (n, ms) in prof.items()}     # per step: launches, ms
+    del fc_d, att_d
+    model._engine = None
+    return out
 
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        threads = os.cpu_count() or 1
-        sample = 8
-        v, check = cpu_baseline(cfg, opt, sd, fc_h[:sample].clone(), att_h[:sample].clone(), repeats=2, threads=threads,
-                                gpu_seq=timed_seq[:sample])
-        cpu = {"value": v, "unit": "captions/s", "cores": threads, "kind": "port",
-               "sample": f"beam-{beam} over the first {sample} images of the GPU leg's own batch, best of 2 after warm-up, torch CPU fp32",
-               "parity_check": check}
 
+def _gemm_rooflines(profile, peak_tflops, top=4):
+    """Tensor-pipe view of the GEMMs of the profiled step: algorithmic 2MNK flops / live event time vs the bf16 peak."""
+    rows = []
+    for name, (n, ms) in profile.items():
+        if not name.startswith("gemm_") or name == "gemm_bf16_simt":
+            continue
+        m, nn, k = (int(v) for v in name[5:].split("x"))
+        us = ms / n * 1e3
+        tf = 2.0 * m * nn * k / (us * 1e-6) / 1e12
+        rows.append({"kernel": name, "launches_per_step": n, "us_per_launch": us, "achieved": tf, "unit": "TFLOP/s", "peak": peak_tflops,
+                     "frac": tf / peak_tflops, "ms_per_step": ms})
+    rows.sort(key=lambda r: -r["ms_per_step"])
+    return rows[:top]
+
+
+def _eager_baseline():
+    """Stock torch.nn decoder on this GPU (baseline/eager_decoder.py): cfg2 greedy and cfg3 training step, fp32 and bf16
+    autocast.  Rank 0 only, a handful of steps."""
+    from baseline.eager_decoder import EagerDecoder, xe_loss
+    from unpaired_image_captioning_b200 import synth
+    res = {"what": "the reference's architecture in stock torch.nn, eager (cuBLAS / ATen, one host sync per step) on this GPU",
+           "torch": torch.__version__}
+    opt, cfg = synth.opt_for("cfg2")
+    m = EagerDecoder(opt)
+    m.load_state_dict(synth.init_state_dict(opt, seed=1234))
+    m = m.cuda().eval()
+    fc, att = synth.make_features(cfg["batch"], cfg["att_size"], opt.att_feat_size, seed=1234)
+    fc, att = fc.cuda(), att.cuda()
+    for tag, ac in (("fp32", False), ("bf16_autocast", True)):
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=ac):
+            ms = _timed(lambda: m.sample_greedy(fc, att), 5, 2, 1)
+        res[f"cfg2_greedy_{tag}"] = {"value": cfg["batch"] / (ms * 1e-3), "unit": "captions/s", "ms_per_step": ms}
+    del m, fc, att
+    opt, cfg = synth.opt_for("cfg3")
+    B = cfg["batch"]
+    fc, att = synth.make_features(B, cfg["att_size"], opt.att_feat_size, seed=4321)
+    labels, masks = synth.make_captions(B, opt.seq_length, opt.vocab_size, seed=4321)
+    fc, att, labels, masks = fc.cuda(), att.cuda(), labels.cuda(), masks.cuda()
+    for tag, ac in (("fp32", False), ("bf16_autocast", True)):
+        m = EagerDecoder(opt)
+        m.load_state_dict(synth.init_state_dict(opt, seed=1234))
+        m = m.cuda().train()
+        optim = torch.optim.Adam(m.parameters(), lr=4e-4, fused=True)
+
+        def step():
+            optim.zero_grad(set_to_none=True)
+            with torch.autocast("cuda", dtype=torch.bfloat16, enabled=ac):
+                out = m(fc, att, labels)
+            loss = xe_loss(out.float(), labels[:, 1:], masks[:, 1:])
+            loss.backward()
+            torch.nn.utils.clip_grad_norm_(m.parameters(), 5.0)
+            optim.step()
+
+        ms = _timed(step, 5, 2, 1)
+        res[f"cfg3_train_{tag}"] = {"value": B / (ms * 1e-3), "unit": "samples/s", "ms_per_step": ms}
+        del m, optim
+    return res
+
+
+# ----------------------------------------------------------------------------------------------------
+def run_b200(args, world, rank, local):
+    from unpaired_image_captioning_b200 import _lib, train_bench
+
+    torch.cuda.set_device(local)
+    if world > 1:
+        torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local))
+    _lib.require_device()
+    numa_node = _bind_near_gpu(local) if world > 1 else None
+    peaks = _peaks()
+    sampler = ClockSampler(local)
+    sampler.start()
+    threads = os.cpu_count() or 1
+    wl = args.workload
+    line = None
+
+    if wl in ("cfg2", "cfg5"):
+        d = _decode_legs(args, world, rank, local, wl, args.steps, with_roofline=True)
+        opt, cfg = d["opt"], d["cfg"]
+        B, beam = cfg["batch"], cfg["beam_size"]
+        legs = {"greedy": {"value": world * B / (d["ms_greedy"] * 1e-3), "unit": "captions/s", "ms_per_step": d["ms_greedy"]}}
+        if wl == "cfg2" and not args.no_legs:
+            legs["train_cfg3_weak"] = train_bench.train_leg(args, world, rank, local, strong=False)
+            if world > 1:
+                legs["train_cfg3_strong"] = train_bench.train_leg(args, world, rank, local, strong=True)
+            d5 = _decode_legs(args, world, rank, local, "cfg5", max(3, args.steps // 4), with_roofline=False)
+            legs["cfg5_beam5"] = {"value": world * d5["cfg"]["batch"] / (d5["ms_beam"] * 1e-3), "unit": "captions/s",
+                                  "ms_per_step": d5["ms_beam"], "images_per_gpu_per_step": d5["cfg"]["batch"],
+                                  "e2e_bf16_cache": d5["e2e_bf16"], "config": _workload_config("cfg5", d5["cfg"], d5["opt"], world)}
+            del d5
+            if rank == 0:
+                legs["eager_b200_baseline"] = _eager_baseline()
+        clocks = sampler.stop()
+        if rank == 0:
+            prof = d["profile"]
+            total = sum(ms for _, ms in prof.values())
+            shares = {k: {"launches": n, "ms_per_step": ms, "share": ms / total}
+                      for k, (n, ms) in sorted(prof.items(), key=lambda kv: -kv[1][1])[:8]}
+            n_att, ms_att = prof["att_step_fwd"]
+            gemms = _gemm_rooflines(prof, peaks["bf16_tflops"])
+            if wl == "cfg2":      # the attention step dominates: HBM roofline
+                alg_bytes = B * cfg["att_size"] * (opt.att_hid_size + opt.rnn_size) * 2      # p_att + att tiles, bf16, once per image
+                achieved = alg_bytes / (ms_att / n_att * 1e-3) / 1e9
+                traffic, traffic_src = _ncu_traffic()
+                roofline = {"kernel": "att_step_fwd", "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                            "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_source": peaks["source"],
+                            "algorithmic_bytes_per_launch": alg_bytes, "us_per_launch": ms_att / n_att * 1e3,
+                            "traffic_source": traffic_src, "gemms": gemms, "kernel_shares": shares,
+                            "note": "duration: live CUDA-event pairs around every launch of an eager decode in this run; traffic: "
+                                    "dram__bytes_read.sum + dram__bytes_write.sum of the committed ncu --set full capture of the same launch"}
+            else:                  # vocab 30k x rnn 1024: the logit statistics GEMM dominates: tensor roofline
+                g0 = gemms[0]
+                roofline = {"kernel": g0["kernel"] + " (logit statistics GEMM)", "bound": "tensor", "achieved": g0["achieved"],
+                            "peak": g0["peak"], "unit": "TFLOP/s", "frac": g0["frac"], "traffic": None, "peak_source": peaks["source"],
+                            "us_per_launch": g0["us_per_launch"], "gemms": gemms, "kernel_shares": shares,
+                            "note": "algorithmic 2 M N K flops / live CUDA-event time per launch of an eager decode in this run"}
+            cpu = None
+            if world == 1 and not args.no_cpu_baseline:
+                sample = 8 if wl == "cfg2" else 2
+                v, check = cpu_beam_baseline(cfg, opt, d["sd"], d["fc_h"][:sample].clone(), d["att_h"][:sample].clone(),
+                                             repeats=2 if wl == "cfg2" else 1, threads=threads, gpu_seq=d["timed_seq"][:sample])
+                cpu = {"value": v, "unit": "captions/s", "cores": threads, "kind": "port",
+                       "sample": f"beam-{beam} over the first {sample} images of the GPU leg's own batch, best of 2 after warm-up, torch CPU fp32",
+                       "parity_check": check}
+                if wl == "cfg2" and not args.no_legs:
+                    cpu["train"] = cpu_train_baseline("cfg1", 16, repeats=2, threads=threads)
+            e2e = dict(d["e2e_bf16"])
+            e2e.update({"host_feature_cache": "bf16 (FeatureCache default: the operand precision of the att_embed GEMM; captions identical "
+                                              "to fp32 inputs, tests/test_gpu_loader.py)", "host_numa_node_rank0": numa_node,
+                        "fp32_host_features": d["e2e_fp32"]})
+            line = {"metric": "beam%d_captions_per_s" % beam, "value": world * B / (d["ms_beam"] * 1e-3), "unit": "captions/s",
+                    "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": d["ms_beam"],
+                    "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                    "config": _workload_config(wl, cfg, opt, world, {"legs": legs}), "clocks": clocks, "e2e": e2e,
+                    "gpu_launches": int(d["launches"] * args.steps), "roofline": roofline, "cpu_baseline": cpu}
+    else:   # cfg3: the training step is the headline
+        t = train_bench.train_leg(args, world, rank, local, strong=args.strong, e2e=True, profile=(rank == 0))
+        clocks = sampler.stop()
+        if rank == 0:
+            cpu = None
+            if world == 1 and not args.no_cpu_baseline:
+                cpu = cpu_train_baseline("cfg3", 16, repeats=2, threads=threads)
+            prof = t.pop("profile")
+            dims = lambda k: [int(v) for v in k[5:].split("x")]
+            gemm_keys = [k for k in prof if k.startswith("gemm_") and k != "gemm_bf16_simt"]
+            gemm_ms = sum(prof[k][1] for k in gemm_keys)
+            gemm_flop = sum(2.0 * dims(k)[0] * dims(k)[1] * dims(k)[2] * prof[k][0] for k in gemm_keys)
+            tf = gemm_flop / (gemm_ms * 1e-3) / 1e12
+            total = sum(ms for _, ms in prof.values())
+            shares = {k: {"launches": n, "ms_per_step": ms, "share": ms / total}
+                      for k, (n, ms) in sorted(prof.items(), key=lambda kv: -kv[1][1])[:8]}
+            roofline = {"kernel": "gemm_bf16_tcgen05_kernel (all GEMM launches of the step)", "bound": "tensor", "achieved": tf,
+                        "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": tf / peaks["bf16_tflops"], "traffic": None,
+                        "peak_source": peaks["source"], "share_of_step": gemm_ms / total, "gemms": _gemm_rooflines(prof, peaks["bf16_tflops"]),
+                        "kernel_shares": shares,
+                        "note": "algorithmic 2 M N K flops of every GEMM launch / their live CUDA-event time in an eager step of this run"}
+            line = {"metric": "train_samples_per_s", "value": t["value"], "unit": "samples/s", "n_gpus": world, "steps": args.steps,
+                    "warmup": args.warmup, "ms_per_step": t["ms_per_step"], "higher_is_better": True,
+                    "scaling": "strong" if args.strong else "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+                    "config": dict(t["config"], parallelism=f"dp{world}", launch_mode=t["launch_mode"], exchange=t.get("exchange")),
+                    "clocks": clocks, "e2e": t["e2e"], "gpu_launches": int(t["launches_per_step"] * args.steps), "roofline": roofline,
+                    "cpu_baseline": cpu}
     if rank == 0:
-        line = {"metric": "beam3_captions_per_s", "value": world * B / (ms_beam * 1e-3), "unit": "captions/s",
-                "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_beam,
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
-                "data": "synthetic", "config": _config(cfg, opt), "clocks": clocks,
-                "e2e": {"value": world * B / (ms_e2e * 1e-3), "unit": "captions/s", "h2d_bytes_per_step": h2d,
-                        "d2h_bytes_per_step": d2h, "ms_per_step": ms_e2e, "host_numa_node_rank0": numa_node},
-                "e2e_bf16_feature_cache": e2e_bf16,
-                "gpu_launches": int(launches * args.steps),
-                "greedy_captions_per_s": world * B / (ms_greedy * 1e-3), "greedy_ms_per_step": ms_greedy,
-                "train": train, "roofline": roofline, "kernel_shares": shares, "cpu_baseline": cpu}
         _emit(line)
     if world > 1:
         torch.distributed.destroy_process_group()
@@ -371,23 +495,25 @@ def run_b200(args, world, rank, local):
 
 def _ncu_traffic():
     """DRAM bytes per launch of the attention kernel from the newest committed `ncu --set full` capture of this workload
-    (profiles/*att_step_fwd_ncu_raw.csv, written by scripts/gpu_round5.sh); (None, reason) when there is none."""
+    (profiles/*att_step_fwd_ncu_raw.csv, written by scripts/gpu_profiles.sh); (None, reason) when there is none."""
     import csv
     import glob
     files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*att_step_fwd_ncu_raw.csv")))
+    files.sort(key=lambda f: (not os.path.basename(f).startswith("r2"), f))   # newest round first
     if not files:
         return None, "no ncu capture under profiles/"
+    pick = files[0] if os.path.basename(files[0]).startswith("r2") else files[-1]
     try:
-        rows = list(csv.reader(open(files[-1])))
+        rows = list(csv.reader(open(pick)))
         head, units, vals = rows[0], rows[1], rows[2]
         scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
         total = 0.0
         for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
             i = head.index(key)
             total += float(vals[i].replace(",", "")) * scale[units[i]]
-        return total, os.path.relpath(files[-1], ROOT)
+        return total, os.path.relpath(pick, ROOT)
     except (ValueError, KeyError, IndexError, OSError) as exc:
-        return None, f"unreadable capture {os.path.basename(files[-1])}: {exc}"
+        return None, f"unreadable capture {os.path.basename(pick)}: {exc}"
 
 
 _RESULT_OUT = None
@@ -405,7 +531,9 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--no-train", action="store_true")
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "cfg5"])
+    ap.add_argument("--strong", action="store_true", help="cfg3: global batch 512 split over the ranks (strong scaling)")
+    ap.add_argument("--no-legs", action="store_true", help="cfg2: skip the train / cfg5 / eager-baseline legs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup

@@ -25,10 +25,15 @@ fc, att = synth.make_features(cfg["batch"], cfg["att_size"], opt.att_feat_size, 
 fc, att = fc.cuda(), att.cuda()
 
 
+train_state = None
+if mode == "train":
+    from unpaired_image_captioning_b200 import train_bench
+    train_state = train_bench.make_state(0, 0, 1, cfg_name=cfg_name)
+
+
 def step():
     if mode == "train":
-        from unpaired_image_captioning_b200.train_bench import one_train_step
-        one_train_step(model, opt, cfg, fc, att)
+        train_bench.one_train_step(st=train_state)
         return
     feats = eng.prepare(fc, att, lazy=True)
     if mode == "beam":

@@ -113,18 +113,10 @@ def test_cfg3_train_step_at_bench_batch():
 def test_cfg3_graphed_train_step_matches_eager():
     """The graph-captured step bench.py times (zero grads, fwd + loss, BPTT, clip, Adam in ONE CUDA graph) produces the
     same loss trajectory and parameters as the same step issued eagerly."""
-    from unpaired_image_captioning_b200 import dp, train_bench
+    from unpaired_image_captioning_b200 import train_bench
 
     def fresh():
-        opt, cfg, sd, model = _bench_model("cfg3")
-        model.train()
-        B = 128                                                    # (four steps each way: keep it short)
-        fc, att = synth.make_features(B, cfg["att_size"], opt.att_feat_size, seed=4321)
-        labels, masks = synth.make_captions(B, opt.seq_length, opt.vocab_size, seed=4321)
-        bucket = dp.GradBucket(model)
-        optim = torch.optim.Adam(model.parameters(), lr=4e-4, betas=(0.9, 0.999), eps=1e-8, fused=True, capturable=True)
-        return dict(model=model, opt=opt, cfg=cfg, fc=fc.cuda(), att=att.cuda(), labels=labels.cuda(), masks=masks.cuda(),
-                    bucket=bucket, optim=optim)
+        return train_bench.make_state(0, 0, 1, rows=128)          # (four steps each way: keep it short)
 
     st_e = fresh()
     eager = [float(train_bench.one_train_step(st=st_e)) for _ in range(3 + 3)]   # the graphed step warms up 3x (the capture itself executes nothing)

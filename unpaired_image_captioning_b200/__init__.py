@@ -8,8 +8,10 @@ gujiuxiang/unpaired_image_captioning (pivot_based_eccv2018/models + misc/criteri
     loss = uic.LanguageModelCriterion(opt)(logprobs, labels[:, 1:], masks[:, 1:])
 """
 from .criterion import LanguageModelCriterion, RewardCriterion  # noqa: F401
+from .loader import FeatureCache, FeatureStream, decode_split, gather_captions, shard_bounds  # noqa: F401
 from .models import (Att2in2Core, Att2in2Model, AttModel, Attention, CaptionModel, TopDownCore,  # noqa: F401
                      TopDownModel, setup)
 
 __all__ = ["setup", "LanguageModelCriterion", "RewardCriterion", "AttModel", "Att2in2Model", "TopDownModel", "Attention",
-           "Att2in2Core", "TopDownCore", "CaptionModel"]
+           "Att2in2Core", "TopDownCore", "CaptionModel", "FeatureCache", "FeatureStream", "decode_split", "gather_captions",
+           "shard_bounds"]

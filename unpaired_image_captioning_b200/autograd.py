@@ -149,9 +149,11 @@ def _logit_stage(r, target, mask, inv_norm, dlogprobs=None, logprobs_out=None, w
 # ----------------------------------------------------------------------------------------------------
 # backward through time
 # ----------------------------------------------------------------------------------------------------
-def bptt(r, dh_all):
+def bptt(r, dh_all, on_ready=None):
     """dh_all: (B*T_total, H) fp32 gradient w.r.t. the step outputs (from the logit layer).
-    Returns {reference parameter name: gradient}."""
+    Returns {reference parameter name: gradient}.  on_ready(dict): called with each group of gradients as soon as it is
+    final (recurrent core + fc_embed after the time-batched wgrads, then the embedding table; the feature-side layers
+    come last, in the returned dict) so that a data-parallel caller can start their all-reduce while the rest still runs."""
     eng = r.model.engine
     w, lib, st = eng.w, eng.lib, stream()
     kind, H, E, A, V = eng.kind, w.H, w.E, w.A, w.V
@@ -166,6 +168,10 @@ def bptt(r, dh_all):
     dc = [torch.empty(sl.n_state, B, H, **f32) for _ in range(2)]
     X2d = r.X.view((T + 1) * B, w.Kx)[:T * B]
     g = {}
+
+    def emit(names):
+        if on_ready is not None:
+            on_ready({n: g[n] for n in names})
 
     if kind == "att2in2":
         NS = 5 * H + A
@@ -200,6 +206,7 @@ def bptt(r, dh_all):
         g["core.i2h.bias"] = g["core.h2h.bias"] = db1[:5 * H]
         g["core.attention.h2att.bias"] = db1[5 * H:]
         g["core.a2h.weight" if da2c is None else "core.a2c.weight"], g["core.a2h.bias" if da2c is None else "core.a2c.bias"] = dWa, dba
+        emit([n for n in g if n.startswith("core.")])
         dxt2d, ld_dxt = dX.view(T * B, w.Kx), w.Kx
         dctx_ptr, dctx_stride, dctx_ld = dctx, B * H, H
         ah_ptr, ah_stride, ah_ld = r.S[0][:, 5 * H:], B * NS, NS
@@ -254,6 +261,7 @@ def bptt(r, dh_all):
         dbfc = torch.zeros(H, **f32)
         check(lib.uic_col_sum(ptr(dfc_pre), 1, H, ptr(dbfc), B, H, st))
         g["fc_embed.0.weight"], g["fc_embed.0.bias"] = dWfc, dbfc
+        emit([n for n in g if n.startswith("core.") or n.startswith("fc_embed.")])
         dxt2d, ld_dxt = dXa.view(T * B, K1)[:, H:], K1
         dctx_ptr, dctx_stride, dctx_ld = dXb[0][:, 2 * H:], B * 3 * H, 3 * H
         ah_ptr, ah_stride, ah_ld = r.ah, B * A, A
@@ -264,6 +272,7 @@ def bptt(r, dh_all):
     demb = torch.zeros(V, E, **f32)
     check(lib.uic_embed_bwd(ptr(dxt2d), ld_dxt, ptr(r.tokens), ptr(w.emb_relu), ptr(demb), T * B, E, V, st))
     g["embed.0.weight"] = demb
+    emit(["embed.0.weight"])
 
     # ---- feature tiles and the prologue layers -----------------------------------------------------------
     datt = torch.empty(B * L, H, **f32)
@@ -405,6 +414,28 @@ class _DecoderTokenLogprobsFn(torch.autograd.Function):
         g = bptt(r, o["dh"])
         g["logit.weight"], g["logit.bias"] = o["dW"], o["db"]
         return (None,) * 6 + tuple(_finish(r, g, None, names, params))
+
+
+def xe_sum_and_grads(model, fc_feats, att_feats, labels, masks, att_masks=None, ss=None, drop=None, on_ready=None):
+    """The training computation without the autograd plumbing, for data-parallel trainers (dp.DataParallelStep):
+    returns (sum over rows and steps of the masked NLL, sum(mask), {parameter name: gradient of that SUM}).
+    Dividing both by the mask sum of the WHOLE batch -- summed over ranks -- gives the reference's loss and gradients
+    (misc/criterion.py:149), so no collective has to run before the forward pass.  on_ready(dict) receives groups of
+    gradients the moment they are final: logit.* right after the fused logit stage (before BPTT starts), then the
+    groups bptt() announces; whatever is left comes with the returned dict."""
+    with torch.no_grad():
+        r = teacher_forced_run(model, fc_feats, att_feats, labels, att_masks, all_steps=True, ss=ss, drop=drop)
+        T_total = r.T_total
+        target = labels[:, 1:T_total + 1].contiguous().view(-1).long()
+        mask = masks[:, 1:T_total + 1].contiguous().view(-1).float()
+        one = torch.ones(1, dtype=torch.float32, device=mask.device)
+        o = _logit_stage(r, target, mask, one, want_grad=True)
+        head = {"logit.weight": o["dW"], "logit.bias": o["db"]}
+        if on_ready is not None:
+            on_ready(head)
+        g = bptt(r, o["dh"], on_ready=on_ready)
+        g.update(head)
+        return o["nll"].sum(), mask.sum(), g
 
 
 def decoder_token_logprobs(model, fc_feats, att_feats, labels, att_masks=None, drop=None):

@@ -1,5 +1,6 @@
 """Training leg of bench.py: TopDown (configs[2]: 36x2048 region features, rnn 512, vocab 10k, seq 16)
-teacher-forced forward + masked XE + BPTT + gradient all-reduce + grad-norm clip + Adam."""
+teacher-forced forward + masked XE + BPTT + bucketed gradient all-reduce + grad-norm clip + Adam, the whole step in
+one CUDA graph.  Weak scaling: 512 rows per GPU; strong scaling: a global batch of 512 rows split over the ranks."""
 from __future__ import annotations
 
 import torch
@@ -7,45 +8,42 @@ import torch
 from . import dp, synth
 
 CFG = "cfg3"
-_state = {}
+GLOBAL_ROWS_STRONG = 512
 
 
-def _setup(local, rank, cfg_name=CFG):
-    key = (local, cfg_name)
-    if key in _state:
-        return _state[key]
+def make_state(local, rank, world, strong=False, cfg_name=CFG, rows=None):
     import unpaired_image_captioning_b200 as uic
     opt, cfg = synth.opt_for(cfg_name)
     model = uic.setup(opt)
     model.load_state_dict(synth.init_state_dict(opt, seed=1234))
     model = model.cuda().train()
-    B = cfg["batch"]
-    fc, att = synth.make_features(B, cfg["att_size"], opt.att_feat_size, seed=4321 + rank)
-    labels, masks = synth.make_captions(B, opt.seq_length, opt.vocab_size, seed=4321 + rank)
-    bucket = dp.GradBucket(model)
+    if rows is None:
+        rows = cfg["batch"]
+    if strong:   # one global batch (same seed on every rank), this rank's contiguous shard of it
+        fc, att = synth.make_features(GLOBAL_ROWS_STRONG, cfg["att_size"], opt.att_feat_size, seed=4321)
+        labels, masks = synth.make_captions(GLOBAL_ROWS_STRONG, opt.seq_length, opt.vocab_size, seed=4321)
+        lo, hi = uic.shard_bounds(GLOBAL_ROWS_STRONG, rank, world)
+        fc, att, labels, masks = fc[lo:hi], att[lo:hi], labels[lo:hi], masks[lo:hi]
+    else:
+        fc, att = synth.make_features(rows, cfg["att_size"], opt.att_feat_size, seed=4321 + rank)
+        labels, masks = synth.make_captions(rows, opt.seq_length, opt.vocab_size, seed=4321 + rank)
+    step = dp.DataParallelStep(model, clip=5.0)
     optim = torch.optim.Adam(model.parameters(), lr=4e-4, betas=(0.9, 0.999), eps=1e-8, fused=True, capturable=True)
-    st = dict(model=model, opt=opt, cfg=cfg, fc=fc.cuda(), att=att.cuda(), labels=labels.cuda(), masks=masks.cuda(),
-              bucket=bucket, optim=optim)
-    _state[key] = st
-    return st
+    host = dict(fc=fc.pin_memory(), att=att.pin_memory(), labels=labels.pin_memory(), masks=masks.pin_memory())
+    return dict(model=model, opt=opt, cfg=cfg, rows=fc.size(0), fc=fc.cuda(), att=att.cuda(), labels=labels.cuda(), masks=masks.cuda(),
+                host=host, step=step, bucket=step.buckets, optim=optim)
 
 
 def one_train_step(model=None, opt=None, cfg=None, fc=None, att=None, st=None, local=0, rank=0):
-    st = st or _setup(local, rank)
-    model, bucket = st["model"], st["bucket"]
-    bucket.zero()
-    norm = dp.global_mask_sum(st["masks"][:, 1:])
-    loss = model(st["fc"], None, st["att"], st["labels"], st["masks"], None, mode="forward_loss", global_mask_sum=norm)
-    loss.backward()
-    bucket.allreduce()
-    bucket.clip_(5.0)
+    st = st or make_state(local, rank, dp.world_size())
+    loss = st["step"](st["fc"], st["att"], st["labels"], st["masks"])
     st["optim"].step()
     return loss
 
 
 class GraphedTrainStep:
-    """The whole training step (zero grads, global mask sum, fused fwd+loss, BPTT, gradient all-reduce, clip,
-    Adam) captured into ONE CUDA graph: ~330 kernel launches per step would otherwise be issued from Python."""
+    """The whole training step (fused fwd + loss, BPTT, bucketed gradient all-reduce, normalise, clip, Adam) captured into
+    ONE CUDA graph: ~330 kernel launches per step would otherwise be issued from Python."""
 
     def __init__(self, st):
         self.st = st
@@ -71,9 +69,38 @@ class GraphedTrainStep:
         return self.loss
 
 
-def train_samples_per_s(args, world, rank, local):
-    from bench import _timed
-    st = _setup(local, rank)
+def grad_parity_check(local, rank, world, strong):
+    """N > 1: the all-reduced, normalised gradient of the sharded step against rank 0's single-GPU gradient of the GATHERED
+    batch (relative Frobenius error); the multi-GPU analogue of the parity tests."""
+    st = make_state(local, rank, world, strong)
+    st["step"].clip = 0.0
+    st["step"](st["fc"], st["att"], st["labels"], st["masks"])
+    got = st["bucket"].grads.clone()
+    err = None
+    if rank == 0:
+        parts = [make_state(local, r, world, strong) for r in range(world)]       # every rank's data, regenerated from its seed
+        ref = parts[0]
+        cat = lambda k: torch.cat([p[k] for p in parts], 0)
+        ref["step"].clip = 0.0
+        world_saved = dp.world_size
+        dp.world_size = lambda: 1                                                  # the reference run must not communicate
+        try:
+            ref["step"](cat("fc"), cat("att"), cat("labels"), cat("masks"))
+        finally:
+            dp.world_size = world_saved
+        want = ref["bucket"].grads
+        err = float((got - want).norm() / want.norm())
+    return err
+
+
+def train_leg(args, world, rank, local, strong=False, e2e=False, profile=False):
+    from bench import _timed, _timed_wall
+    from . import _lib
+    parity = grad_parity_check(local, rank, world, strong) if world > 1 else None
+    st = make_state(local, rank, world, strong)
+    l0 = _lib.launch_count()
+    one_train_step(st=st)
+    launches = _lib.launch_count() - l0
     try:
         step = GraphedTrainStep(st)
         mode = "cuda_graph"
@@ -81,10 +108,38 @@ def train_samples_per_s(args, world, rank, local):
         torch.cuda.synchronize()
         step, mode = (lambda: one_train_step(st=st)), f"eager ({type(e).__name__}: {str(e)[:80]})"
     ms = _timed(step, args.steps, args.warmup, world)
-    B = st["cfg"]["batch"]
+    rows = st["rows"]
     opt = st["opt"]
-    return {"metric": "train_samples_per_s", "value": world * B / (ms * 1e-3), "unit": "samples/s", "ms_per_step": ms,
-            "config": {"workload": "configs[2]: TopDown XE training (fwd + loss + bwd + allreduce + clip + Adam)",
-                       "caption_model": opt.caption_model, "rows_per_gpu": B, "att_regions": st["cfg"]["att_size"],
-                       "rnn_size": opt.rnn_size, "vocab": opt.vocab_size + 1, "seq_length": opt.seq_length},
-            "scaling": "weak", "launch_mode": mode, "loss_rank0_share": float(step().detach() if mode != "cuda_graph" else step())}
+    total_rows = GLOBAL_ROWS_STRONG if strong else world * rows
+    out = {"metric": "train_samples_per_s", "value": total_rows / (ms * 1e-3), "unit": "samples/s", "ms_per_step": ms,
+           "config": {"workload": "configs[2]: TopDown XE training (fwd + loss + bwd + bucketed all-reduce + clip + Adam)",
+                      "caption_model": opt.caption_model, "rows_per_gpu": rows, "global_rows": total_rows,
+                      "att_regions": st["cfg"]["att_size"], "rnn_size": opt.rnn_size, "vocab": opt.vocab_size + 1,
+                      "seq_length": opt.seq_length},
+           "scaling": "strong" if strong else "weak", "launch_mode": mode, "launches_per_step": launches,
+           "exchange": {"buckets_mb": [round((hi - lo) * 4 / 2 ** 20, 1) for lo, hi in st["bucket"].bounds],
+                        "order": "logit | core + fc_embed | embed | features + normaliser", "overlapped": True,
+                        "grad_parity_rel_err_vs_single_gpu": parity},
+           "loss_rank0_share": float(step())}
+    if e2e:   # the same step fed from pinned host memory: H2D of the batch and D2H of the loss inside the timing
+        h = st["host"]
+
+        def e2e_step():
+            for k in ("fc", "att", "labels", "masks"):
+                st[k].copy_(h[k], non_blocking=True)
+            return float(step())
+
+        ms_e = _timed_wall(e2e_step, args.steps, args.warmup, world)
+        out["e2e"] = {"value": total_rows / (ms_e * 1e-3), "unit": "samples/s", "ms_per_step": ms_e,
+                      "h2d_bytes_per_step": sum(h[k].numel() * h[k].element_size() for k in ("fc", "att", "labels", "masks")),
+                      "d2h_bytes_per_step": 4}
+    if profile:   # live per-kernel timing of eager steps (rank 0)
+        one_train_step(st=st)
+        torch.cuda.synchronize()
+        _lib.profile(True)
+        for _ in range(2):
+            one_train_step(st=st)
+        prof = _lib.profile_dump()
+        _lib.profile(False)
+        out["profile"] = {k: (n / 2.0, msk / 2.0) for k, (n, msk) in prof.items()}
+    return out
