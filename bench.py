@@ -461,7 +461,7 @@ def run_b200(args, world, rank, local):
                     "config": _workload_config(wl, cfg, opt, world, {"legs": legs}), "clocks": clocks, "e2e": e2e,
                     "gpu_launches": int(d["launches"] * args.steps), "roofline": roofline, "cpu_baseline": cpu}
     else:   # cfg3: the training step is the headline
-        t = train_bench.train_leg(args, world, rank, local, strong=args.strong, e2e=True, profile=(rank == 0))
+        t = train_bench.train_leg(args, world, rank, local, strong=args.strong, e2e=True, profile=True)   # (every rank: the profiled eager steps contain the all-reduces)
         clocks = sampler.stop()
         if rank == 0:
             cpu = None
