@@ -25,12 +25,12 @@ import numpy as np
 import torch
 import torch.nn.functional as F
 
-KINDS = ("att2in2", "att2all2", "topdown")
+KINDS = ("att2in2", "att2all2", "topdown", "stackatt", "denseatt")
 
 
 def num_layers(kind):
-    # models/AttModel.py:62 (att2in2 -> opt.num_layers == 1) and :689 (topdown forces 2)
-    return 2 if kind == "topdown" else 1
+    # models/AttModel.py:62 (att2in2 -> opt.num_layers == 1), :689 (topdown forces 2), :696,703 (stackatt / denseatt: 3)
+    return {"topdown": 2, "stackatt": 3, "denseatt": 3}.get(kind, 1)
 
 
 def _linear(sd, prefix, x):
@@ -90,7 +90,7 @@ def prepare_features(sd, kind, fc_feats, att_feats, att_masks=None, drop=None):
         keep = int(att_masks.long().sum(1).max())
         att_feats = att_feats[:, :keep].contiguous()
         att_masks = att_masks[:, :keep].contiguous()
-    if kind == "topdown":  # fc_embed = Linear+ReLU(+Dropout) (:76-78); identity for att2in2 (:674-675)
+    if kind not in ("att2in2", "att2all2"):  # fc_embed = Linear+ReLU(+Dropout) (:76-78); identity for att2in2 / att2all2 (:674-675,682-683)
         fc = torch.relu(_linear(sd, "fc_embed.0", fc_feats))
         if drop is not None:
             fc = fc * dropout_mask(drop, DROP_FC, np.arange(fc.size(0)), fc.size(1))
@@ -125,11 +125,11 @@ def prepare_features(sd, kind, fc_feats, att_feats, att_masks=None, drop=None):
 # ------------------------------------------------------------------------------------------------
 # additive attention -- models/AttModel.py:538-558
 # ------------------------------------------------------------------------------------------------
-def attention(sd, h, att, p_att, att_masks=None, return_weights=False):
-    att_h = _linear(sd, "core.attention.h2att", h)                      # :543
+def attention(sd, h, att, p_att, att_masks=None, return_weights=False, prefix="core.attention"):
+    att_h = _linear(sd, prefix + ".h2att", h)                           # :543
     hidden = torch.tanh(p_att + att_h[:, None, :])                      # :544-546
-    w = sd["core.attention.alpha_net.weight"].view(-1)
-    score = hidden @ w + sd["core.attention.alpha_net.bias"]            # :548-549
+    w = sd[prefix + ".alpha_net.weight"].view(-1)
+    score = hidden @ w + sd[prefix + ".alpha_net.bias"]                 # :548-549
     weight = torch.softmax(score, dim=1)                                # :551
     if att_masks is not None:                                           # :552-554
         weight = weight * att_masks.to(weight.dtype)
@@ -191,7 +191,40 @@ def core_topdown(sd, xt, fc, att, p_att, state, att_masks=None):
     return h_lang, (torch.stack([h_att, h_lang]), torch.stack([c_att, c_lang]))   # :443-446
 
 
-CORES = {"att2in2": core_att2in2, "att2all2": core_att2all2, "topdown": core_topdown}
+def _lstm_core(sd, prefix, x, h_prev, c_prev):
+    """models/FCModel.py:14-42 (LSTMCore): the 5H maxout cell without a context term (dropout p=0)."""
+    H = h_prev.size(1)
+    sums = _linear(sd, prefix + ".i2h", x) + _linear(sd, prefix + ".h2h", h_prev)       # FCModel.py:27
+    sig = torch.sigmoid(sums[:, :3 * H])                                # :28-32
+    g = torch.maximum(sums[:, 3 * H:4 * H], sums[:, 4 * H:])            # :34-36
+    c = sig[:, H:2 * H] * c_prev + sig[:, :H] * g                       # :37
+    h = sig[:, 2 * H:] * torch.tanh(c)                                  # :38
+    return h, c
+
+
+def _stack_dense(sd, xt, fc, att, p_att, state, att_masks, dense):
+    """models/AttModel.py:476-486 (StackAttCore.forward) and :516-526 (DenseAttCore.forward): three maxout cells, two
+    attentions; the dense variant fuses h_0, h_1 into the third cell's input and all three into the output."""
+    h0, c0 = _lstm_core(sd, "core.lstm0", torch.cat([xt, fc], 1), state[0][0], state[1][0])                  # :478 / :518
+    a1 = attention(sd, h0, att, p_att, att_masks, prefix="core.att1")                                         # :479 / :519
+    h1, c1 = _lstm_core(sd, "core.lstm1", torch.cat([h0, a1], 1), state[0][1], state[1][1])                  # :480 / :520
+    a2 = attention(sd, h1 + _linear(sd, "core.emb2", a1), att, p_att, att_masks, prefix="core.att2")          # :481 / :521
+    x2 = torch.relu(_linear(sd, "core.fusion1.0", torch.cat([h0, h1], 1))) if dense else h1                  # :522
+    h2, c2 = _lstm_core(sd, "core.lstm2", torch.cat([x2, a2], 1), state[0][2], state[1][2])                  # :482 / :522
+    out = torch.relu(_linear(sd, "core.fusion2.0", torch.cat([h0, h1, h2], 1))) if dense else h2             # :484 / :524
+    return out, (torch.stack([h0, h1, h2]), torch.stack([c0, c1, c2]))
+
+
+def core_stackatt(sd, xt, fc, att, p_att, state, att_masks=None):
+    return _stack_dense(sd, xt, fc, att, p_att, state, att_masks, dense=False)
+
+
+def core_denseatt(sd, xt, fc, att, p_att, state, att_masks=None):
+    return _stack_dense(sd, xt, fc, att, p_att, state, att_masks, dense=True)
+
+
+CORES = {"att2in2": core_att2in2, "att2all2": core_att2all2, "topdown": core_topdown, "stackatt": core_stackatt,
+         "denseatt": core_denseatt}
 
 
 def init_hidden(sd, kind, rows):

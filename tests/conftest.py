@@ -11,7 +11,7 @@ if ROOT not in sys.path:
 
 GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
 GOLDEN_CASES = ["att2in2_plain", "att2in2_peaked", "att2in2_masked", "att2all2_peaked",
-                "topdown_plain", "topdown_peaked", "topdown_masked"]
+                "topdown_plain", "topdown_peaked", "topdown_masked", "stackatt_plain", "stackatt_peaked", "denseatt_peaked", "denseatt_masked"]
 
 
 def pytest_configure(config):

@@ -36,6 +36,10 @@ CASES = {
     "topdown_plain": ("tiny_topdown", 1234, dict(), False),
     "topdown_peaked": ("tiny_topdown", 1237, dict(peaked=80.0, eos_bias=0.0), False),
     "topdown_masked": ("tiny_topdown", 1237, dict(peaked=80.0, eos_bias=0.0), True),
+    "stackatt_plain": ("tiny_stackatt", 1234, dict(), False),
+    "stackatt_peaked": ("tiny_stackatt", 1256, dict(peaked=80.0, eos_bias=2.0), False),
+    "denseatt_peaked": ("tiny_denseatt", 1259, dict(peaked=80.0, eos_bias=0.5), False),
+    "denseatt_masked": ("tiny_denseatt", 1259, dict(peaked=80.0, eos_bias=0.5), True),
 }
 
 

@@ -61,3 +61,33 @@ def test_python_wrappers_validate_like_torch_would():
         _lib.gemm(a.float(), b, out_f32=torch.empty(16, 8, device=DEV))    # dtype
     with pytest.raises(ValueError):
         _lib.dropout(torch.zeros(4, 4, 4, device=DEV), (0.5, torch.zeros(1, dtype=torch.int64, device=DEV)), 0)
+
+
+def test_out_of_range_tokens_raise_like_the_reference():
+    """The kernels clamp token ids; the module surface raises IndexError first, as nn.Embedding / gather do in the reference."""
+    import unpaired_image_captioning_b200 as uic
+    from unpaired_image_captioning_b200 import synth
+    opt, cfg = synth.opt_for("tiny_att2in2")
+    model = uic.setup(opt)
+    model.load_state_dict(synth.init_state_dict(opt, seed=1))
+    model = model.cuda().eval()
+    fc, att = synth.make_features(3, cfg["att_size"], opt.att_feat_size, seed=1)
+    labels, masks = synth.make_captions(3, opt.seq_length, opt.vocab_size, seed=1)
+    bad = labels.clone()
+    bad[1, 2] = opt.vocab_size + 1
+    with pytest.raises(IndexError):
+        model(fc.cuda(), None, att.cuda(), bad.cuda())
+    with pytest.raises(IndexError):
+        model(fc.cuda(), None, att.cuda(), bad.cuda(), masks.cuda(), None, mode="forward_loss")
+    bad[1, 2] = -1
+    with pytest.raises(IndexError):
+        model(fc.cuda(), None, att.cuda(), bad.cuda())
+
+
+def test_row_topk_rejects_more_than_16_candidates():
+    from unpaired_image_captioning_b200 import _lib
+    lib = _lib.load()
+    logits = torch.randn(4, 100, device="cuda")
+    val, idx = torch.empty(4, 20, device="cuda"), torch.empty(4, 20, device="cuda", dtype=torch.int32)
+    rc = lib.uic_row_topk(logits.data_ptr(), 100, None, val.data_ptr(), idx.data_ptr(), 4, 100, 20, 0, torch.cuda.current_stream().cuda_stream)
+    assert rc != 0 and b"max 16" in lib.uic_last_error()

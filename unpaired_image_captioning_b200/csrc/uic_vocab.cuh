@@ -29,7 +29,16 @@ __host__ __device__ __forceinline__ float rng_uniform(uint32_t row_key, int col)
   const uint32_t h = rng_mix(row_key ^ (static_cast<uint32_t>(col) * 0xC2B2AE3DU));
   return (static_cast<float>(h >> 9) + 0.5f) * (1.0f / 8388608.0f);  // 23 bits + 1/2: exact in fp32, strictly inside (0, 1)
 }
-__device__ __forceinline__ float rng_gumbel(uint32_t row_key, int col) { return -__logf(-__logf(rng_uniform(row_key, col))); }
+// g = -log(-log(u)).  Close to u = 1 the inner value -log(u) ~ 1 - u is as small as 6e-8, below the ABSOLUTE error of
+// __logf (2^-21.4): it could come out 0 or negative and turn g into +inf / NaN for ~5e-7 of the draws.  There the series
+// -log(1 - t) = t + t^2/2 + t^3/3 + t^4/4 (t = 1 - u is exact in fp32, relative error < 1e-7 for t < 1/32) replaces it.
+__device__ __forceinline__ float rng_gumbel(uint32_t row_key, int col) {
+  const float u = rng_uniform(row_key, col);
+  const float t = 1.0f - u;
+  const float series = t * fmaf(t, fmaf(t, fmaf(t, 0.25f, 1.0f / 3.0f), 0.5f), 1.0f);
+  const float inner = t < 0.03125f ? series : -__logf(u);
+  return -__logf(inner);
+}
 constexpr int RNG_ROW_DRAW_COL = 0x7fffffff;  // "column" of a per-row uniform draw (scheduled-sampling coin), outside any vocabulary
 
 struct MaxSum {

@@ -290,7 +290,9 @@ __global__ void __launch_bounds__(ROW_THREADS) row_topk_kernel(const float* __re
       s_winner = w.i;
       // ys[q, c] of the reference: the edited log-probability (the UNK shift is applied to the
       // log-prob in fp32, like `logprobsf[:, V-1] - 1000`)
-      float lp = ((row[w.i] - red.m) - log_s);
+      // (no candidate left -- fewer than k finite entries in the row: -inf and column 0, never an out-of-range read)
+      float lp = w.i == 0x7fffffff ? -INFINITY : ((row[w.i] - red.m) - log_s);
+      if (w.i == 0x7fffffff) w.i = 0;
       if (w.i == V - 1) lp -= 1000.0f;
       if (w.i == banned) lp = -INFINITY;
       topk_val[static_cast<long long>(r) * k + round] = lp;
@@ -303,6 +305,9 @@ __global__ void __launch_bounds__(ROW_THREADS) row_topk_kernel(const float* __re
 
 int row_topk(const float* logits, long long ld, const int64_t* prev_tok, float* topk_val, int32_t* topk_idx, int rows, int V,
              int k, int flags, cudaStream_t stream) {
+  // every thread keeps its KMAX best entries: with k > 16 a thread that holds more than 16 of the row's top k would
+  // silently drop some (the instantiations stop at 16; 32 would not fit the static shared-memory budget)
+  if (k > 16) return set_error(UIC_ERR_SHAPE, "row_topk: k=%d candidates per row (max 16)", k);
   launch_begin("row_topk", stream);
   if (k <= 4)
     row_topk_kernel<4><<<rows, ROW_THREADS, 0, stream>>>(logits, ld, prev_tok, topk_val, topk_idx, V, k, flags);

@@ -106,6 +106,7 @@ class DataParallelStep:
             from .autograd import xe_sum_and_grads
 
             def grad_fn(model, fc, att, labels, masks, att_masks, on_ready):
+                model._check_tokens(labels)
                 return xe_sum_and_grads(model, fc, att, labels, masks, att_masks, model._scheduled_sampling(att.device),
                                         model._dropout(att.device), on_ready)
         self.grad_fn = grad_fn

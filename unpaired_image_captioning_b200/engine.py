@@ -569,6 +569,8 @@ class DecoderEngine:
             raise ValueError(f"beam_size={beam_size} must be a multiple of group_size={G}")
         b = beam_size // G
         R = B * b
+        if b * G > 16:   # group g needs its b (g + 1) best entries per row to survive the penalties; uic_row_topk keeps 16
+            raise NotImplementedError(f"diverse beam search with beam_size={beam_size} > 16 is not built (row top-k keeps 16 candidates)")
         tk_flags = _lib.SAMPLE_DECODING_CONSTRAINT if decoding_constraint else 0
         bs_flags = _lib.BEAM_MAX_PPL if max_ppl else 0
         key = ("beam_diverse", B, b, G, float(diversity_lambda), feats.L, T, tk_flags, bs_flags, feats.masks is not None,

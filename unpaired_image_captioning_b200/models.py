@@ -214,7 +214,17 @@ class AttModel(CaptionModel):
         empty = (seq[:, 1:T].sum(0) == 0).nonzero()
         return T if empty.numel() == 0 else int(empty[0]) + 1
 
+    def _check_tokens(self, seq):
+        """Token ids outside [0, vocab_size] raise like the reference's nn.Embedding / gather would (IndexError) instead of
+        being clamped by the kernels.  One tiny reduction + host read; skipped while a CUDA graph is being captured."""
+        if seq.numel() == 0 or (seq.is_cuda and torch.cuda.is_current_stream_capturing()):
+            return
+        lo, hi = int(seq.min()), int(seq.max())
+        if lo < 0 or hi > self.vocab_size:
+            raise IndexError(f"token id out of range: [{lo}, {hi}] not in [0, {self.vocab_size}]")
+
     def _forward(self, fc_feats, attri_feats, att_feats, seq, att_masks=None):
+        self._check_tokens(seq)
         if att_feats.size(0) == 0:   # empty batch: the reference's torch ops return an empty (0, T, V) tensor
             return att_feats.new_zeros((0, seq.size(1) - 1, self.vocab_size + 1), dtype=torch.float32)
         ss, drop = self._scheduled_sampling(att_feats.device), self._dropout(att_feats.device)
@@ -239,6 +249,7 @@ class AttModel(CaptionModel):
         (B, T, V) log-prob tensor.  Equals crit(model(fc, attri, att, labels, att_masks), labels[:,1:], masks[:,1:]).
         `global_mask_sum` (data parallel): the loss normaliser summed over all ranks (dp.global_mask_sum)."""
         from .autograd import decoder_loss
+        self._check_tokens(labels)
         return decoder_loss(self, fc_feats, att_feats, labels, masks, att_masks, global_mask_sum,
                             self._scheduled_sampling(att_feats.device), self._dropout(att_feats.device))
 

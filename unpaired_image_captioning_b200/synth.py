@@ -42,6 +42,12 @@ CONFIGS = {
     "tiny_topdown": dict(caption_model="topdown", rnn_size=32, input_encoding_size=32, att_hid_size=32,
                          att_size=7, vocab_size=51, seq_length=6, batch=5, beam_size=3,
                          fc_feat_size=64, att_feat_size=64),
+    "tiny_stackatt": dict(caption_model="stackatt", rnn_size=32, input_encoding_size=32, att_hid_size=32,
+                          att_size=7, vocab_size=51, seq_length=6, batch=5, beam_size=3,
+                          fc_feat_size=64, att_feat_size=64),
+    "tiny_denseatt": dict(caption_model="denseatt", rnn_size=32, input_encoding_size=32, att_hid_size=32,
+                          att_size=7, vocab_size=51, seq_length=6, batch=5, beam_size=3,
+                          fc_feat_size=64, att_feat_size=64),
 }
 
 
@@ -55,7 +61,7 @@ def make_opt(caption_model="att2in2", vocab_size=9999, rnn_size=512, input_encod
         input_encoding_size=input_encoding_size, att_hid_size=att_hid_size,
         seq_length=seq_length, fc_feat_size=fc_feat_size, att_feat_size=att_feat_size,
         drop_prob_lm=drop_prob_lm, use_bn=use_bn, logit_layers=logit_layers,
-        num_layers=2 if caption_model == "topdown" else 1)
+        num_layers={"topdown": 2, "stackatt": 3, "denseatt": 3}.get(caption_model, 1))
 
 
 def opt_for(name, **over):
@@ -116,7 +122,7 @@ def init_state_dict(opt, seed=1234, peaked=0.0, eos_bias=0.0):
 
     sd = {}
     sd["embed.0.weight"] = torch.randn(V, E, generator=g)
-    if opt.caption_model == "topdown":
+    if opt.caption_model not in ("att2in2", "att2all2"):
         sd["fc_embed.0.weight"], sd["fc_embed.0.bias"] = lin(H, F_)
     if getattr(opt, "use_bn", 0):   # BatchNorm1d(att_feat_size) first (models/AttModel.py:79-80): non-trivial affine + running stats
         sd["att_embed.0.weight"] = 0.5 + torch.rand(D, generator=g)
@@ -142,10 +148,22 @@ def init_state_dict(opt, seed=1234, peaked=0.0, eos_bias=0.0):
             w_hh, b_hh = lin(4 * H, H, bound_in=H)
             sd[f"core.{name}.weight_ih"], sd[f"core.{name}.weight_hh"] = w_ih, w_hh
             sd[f"core.{name}.bias_ih"], sd[f"core.{name}.bias_hh"] = b_ih, b_hh
+    elif opt.caption_model in ("stackatt", "denseatt"):   # models/AttModel.py:458-526: att1, att2, lstm0..2 (FCModel.LSTMCore), emb2, fusions
+        for att_name in ("att1", "att2"):
+            sd[f"core.{att_name}.h2att.weight"], sd[f"core.{att_name}.h2att.bias"] = lin(A, H)
+            sd[f"core.{att_name}.alpha_net.weight"], sd[f"core.{att_name}.alpha_net.bias"] = lin(1, A)
+        for name, in_f in (("lstm0", E + H), ("lstm1", 2 * H), ("lstm2", 2 * H)):
+            sd[f"core.{name}.i2h.weight"], sd[f"core.{name}.i2h.bias"] = lin(5 * H, in_f)
+            sd[f"core.{name}.h2h.weight"], sd[f"core.{name}.h2h.bias"] = lin(5 * H, H)
+        sd["core.emb2.weight"], sd["core.emb2.bias"] = lin(H, H)
+        if opt.caption_model == "denseatt":
+            sd["core.fusion1.0.weight"], sd["core.fusion1.0.bias"] = lin(H, 2 * H)
+            sd["core.fusion2.0.weight"], sd["core.fusion2.0.bias"] = lin(H, 3 * H)
     else:
         raise ValueError(f"caption_model {opt.caption_model!r} is outside the hot path")
-    sd["core.attention.h2att.weight"], sd["core.attention.h2att.bias"] = lin(A, H)
-    sd["core.attention.alpha_net.weight"], sd["core.attention.alpha_net.bias"] = lin(1, A)
+    if opt.caption_model not in ("stackatt", "denseatt"):
+        sd["core.attention.h2att.weight"], sd["core.attention.h2att.bias"] = lin(A, H)
+        sd["core.attention.alpha_net.weight"], sd["core.attention.alpha_net.bias"] = lin(1, A)
     if peaked:
         sd["logit.weight"] = sd["logit.weight"] * peaked
     if eos_bias:
