@@ -25,7 +25,8 @@ def _case(kind, B, L, seed, peaked=0.0, eos_bias=0.0, masks=False):
     return opt, sd, model.cuda().eval(), fc, att, labels, lmasks, am
 
 
-@pytest.mark.parametrize("kind,L,masks", [("att2in2", 196, False), ("att2all2", 100, True), ("topdown", 36, False), ("topdown", 36, True)])
+@pytest.mark.parametrize("kind,L,masks", [("att2in2", 196, False), ("att2all2", 100, True), ("topdown", 36, False), ("topdown", 36, True),
+                                          ("stackatt", 36, False), ("denseatt", 49, True)])
 def test_teacher_forced_and_loss(kind, L, masks):
     opt, sd, model, fc, att, labels, lmasks, am = _case(kind, 8, L, seed=1234, masks=masks)
     ref = O.teacher_forced(sd, kind, fc, att, labels, am)
@@ -68,7 +69,7 @@ def test_attention_operand_range(kind, shift):
         assert float((g - r).norm() / r.norm()) < 5e-2, name
 
 
-@pytest.mark.parametrize("kind,L", [("att2in2", 196), ("att2all2", 64), ("topdown", 36)])
+@pytest.mark.parametrize("kind,L", [("att2in2", 196), ("att2all2", 64), ("topdown", 36), ("stackatt", 36), ("denseatt", 36)])
 def test_greedy_with_margin_exemption(kind, L):
     opt, sd, model, fc, att, *_ = _case(kind, 16, L, seed=77)
     ref_seq, ref_lp, margins = O.sample_greedy(sd, kind, fc, att, 16, return_margins=True, relative_margins=True)
@@ -80,7 +81,8 @@ def test_greedy_with_margin_exemption(kind, L):
     torch.testing.assert_close(lp.cpu()[first], ref_lp[first], rtol=REL, atol=REL * 10)
 
 
-@pytest.mark.parametrize("kind,L,beam", [("att2in2", 196, 3), ("topdown", 36, 3), ("att2in2", 49, 5), ("att2all2", 49, 3)])
+@pytest.mark.parametrize("kind,L,beam", [("att2in2", 196, 3), ("topdown", 36, 3), ("att2in2", 49, 5), ("att2all2", 49, 3),
+                                         ("stackatt", 36, 3), ("denseatt", 49, 3), ("denseatt", 36, 5)])
 def test_beam_peaked_exact(kind, L, beam):
     """Wide-margin variant (scaled logit weights, raised EOS bias): ids must be identical -- a differing row must sit at an
     oracle decision margin inside the north-star tolerance."""

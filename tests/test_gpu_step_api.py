@@ -29,7 +29,7 @@ def _close(a, b, tol=4e-3):
     assert err < tol, err
 
 
-@pytest.mark.parametrize("kind", ["att2in2", "att2all2", "topdown"])
+@pytest.mark.parametrize("kind", ["att2in2", "att2all2", "topdown", "stackatt", "denseatt"])
 @pytest.mark.parametrize("B,L,masks", [(5, 17, False), (1, 33, True), (9, 4, True)])
 def test_get_logprobs_state_steps(kind, B, L, masks):
     opt, sd, model, fc, att, am = _setup(kind, B, L, masks)

@@ -47,6 +47,13 @@ def _setup(golden):
 @pytest.mark.parametrize("mode", ["fused", "dense"])
 def test_gradients_match_reference_autograd(golden, mode):
     model, opt, fc, att, labels, masks, am = _setup(golden)
+    if golden["kind"] in ("stackatt", "denseatt"):   # inference-only cores: training calls fail loudly, there is no fallback
+        model.train()
+        with pytest.raises(NotImplementedError):
+            model(fc, None, att, labels, masks, am, mode="forward_loss")
+        with pytest.raises(NotImplementedError):
+            model(fc, None, att, labels, am)
+        return
     if mode == "fused":
         loss = model(fc, None, att, labels, masks, am, mode="forward_loss")
     else:

@@ -58,8 +58,9 @@ class PackedWeights:
             self.w_att_embed, self.b_att_embed = _bf16(sd["att_embed.0.weight"]), f32("att_embed.0.bias")
         self.w_ctx2att, self.b_ctx2att = _bf16(sd["ctx2att.weight"]), f32("ctx2att.bias")
         self.w_logit, self.b_logit = _bf16(sd["logit.weight"]), f32("logit.bias")
-        self.w_alpha = f32("core.attention.alpha_net.weight").reshape(-1).contiguous()
-        w_h2att, b_h2att = f32("core.attention.h2att.weight"), f32("core.attention.h2att.bias")
+        if self.kind in ("att2in2", "topdown"):
+            self.w_alpha = f32("core.attention.alpha_net.weight").reshape(-1).contiguous()
+            w_h2att, b_h2att = f32("core.attention.h2att.weight"), f32("core.attention.h2att.bias")
         if self.kind == "att2in2":
             self.Kx = E + H
             w1 = torch.zeros(5 * H + A, E + H, device=w_h2att.device)
@@ -89,6 +90,24 @@ class PackedWeights:
             self.w2 = _bf16(torch.cat([w_hh2, w_ih2[:, H:], w_ih2[:, :H]], 1))
             self.b2 = (f32("core.lang_lstm.bias_ih") + f32("core.lang_lstm.bias_hh")).contiguous()
             self.w_h2att, self.b_h2att = _bf16(w_h2att), b_h2att
+        elif self.kind in ("stackatt", "denseatt"):   # models/AttModel.py:458-526
+            dense = self.kind == "denseatt"
+            self.Kx = E + (7 if dense else 6) * H
+            self.w_fc, self.b_fc = _bf16(sd["fc_embed.0.weight"]), f32("fc_embed.0.bias")
+            cell = lambda n: (_bf16(torch.cat([f32(f"core.{n}.i2h.weight"), f32(f"core.{n}.h2h.weight")], 1)),
+                              (f32(f"core.{n}.i2h.bias") + f32(f"core.{n}.h2h.bias")).contiguous())
+            # i2h columns already come in slot order: lstm0 [xt | fc], lstm1 [h0 | ctx1], lstm2 [h1 or f1 | ctx2]; h2h follows
+            (self.wl0, self.bl0), (self.wl1, self.bl1), (self.wl2, self.bl2) = cell("lstm0"), cell("lstm1"), cell("lstm2")
+            self.w_h2att, self.b_h2att = _bf16(f32("core.att1.h2att.weight")), f32("core.att1.h2att.bias")
+            self.w_alpha = f32("core.att1.alpha_net.weight").reshape(-1).contiguous()
+            self.w_alpha2 = f32("core.att2.alpha_net.weight").reshape(-1).contiguous()
+            # att2's query is h2att2(h1 + emb2(ctx1)) (:481): one GEMM over [ctx1 | h1] with [W2 We | W2], bias W2 be + b2
+            w2, we = f32("core.att2.h2att.weight"), f32("core.emb2.weight")
+            self.w_q2 = _bf16(torch.cat([w2 @ we, w2], 1))
+            self.b_q2 = (torch.mv(w2, f32("core.emb2.bias")) + f32("core.att2.h2att.bias")).contiguous()
+            if dense:
+                self.w_f1, self.b_f1 = _bf16(sd["core.fusion1.0.weight"]), f32("core.fusion1.0.bias")
+                self.w_f2, self.b_f2 = _bf16(sd["core.fusion2.0.weight"]), f32("core.fusion2.0.bias")
         else:
             raise ValueError(self.kind)
 
@@ -112,16 +131,33 @@ class Slots:
     """Column ranges of the activation matrix X."""
 
     def __init__(self, kind, E, H):
+        self.fc = None
         if kind == "att2in2":
             self.xt, self.h_out = (0, E), (E, E + H)
             self.gather = [(E, H), (0, 0)]           # recurrent columns re-ordered by beam parent
             self.n_state = 1
-        else:
+            self.h_load = self.h_read = [self.h_out]  # state layer -> slot its previous value is read from / its new value lands in
+        elif kind == "topdown":
             self.h_att_prev, self.xt, self.fc = (0, H), (H, H + E), (H + E, 2 * H + E)
             self.h_lang, self.h_att, self.ctx = (2 * H + E, 3 * H + E), (3 * H + E, 4 * H + E), (4 * H + E, 5 * H + E)
             self.h_out = self.h_lang
             self.gather = [(0, H), (2 * H + E, H)]
             self.n_state = 2
+            self.h_load, self.h_read = [self.h_att_prev, self.h_lang], [self.h_att, self.h_lang]
+        else:
+            # stackatt: [xt | fc | h0 | ctx1 | h1 | ctx2 | h2]; denseatt adds f1 = fusion1(h0, h1) in front of ctx2.  Every cell
+            # overwrites its own h slot in place (its GEMM has read the previous value by then), so each GEMM operand is one
+            # contiguous column range: lstm0 [xt|fc|h0], lstm1 [h0|ctx1|h1], att2 query [ctx1|h1], lstm2 [h1 or f1|ctx2|h2].
+            dense = kind == "denseatt"
+            self.xt, self.fc, self.h0, self.ctx1, self.h1 = (0, E), (E, E + H), (E + H, E + 2 * H), (E + 2 * H, E + 3 * H), (E + 3 * H, E + 4 * H)
+            o = E + 4 * H
+            self.f1 = (o, o + H) if dense else None
+            o += H if dense else 0
+            self.ctx2, self.h2 = (o, o + H), (o + H, o + 2 * H)
+            self.h_out = self.h2
+            self.gather = [(E + H, 3 * H), (self.h2[0], H)]      # [h0|ctx1|h1] (ctx1 rides along) and h2
+            self.n_state = 3
+            self.h_load = self.h_read = [self.h0, self.h1, self.h2]
 
 
 @contextlib.contextmanager
@@ -230,7 +266,7 @@ class DecoderEngine:
         p_att = torch.empty(B * L, A, dtype=_lib.TILE_DTYPE, device=x.device) if out is None else out.p_att.view(B * L, A)
         gemm(att, w.w_ctx2att, w.b_ctx2att, out_bf16=p_att, exp_col0=0, exp_scale=_lib.ATT_E_SCALE)
         fc = None
-        if self.kind == "topdown":
+        if self.kind != "att2in2":   # fc_embed (identity for att2in2 / att2all2, models/AttModel.py:674-675)
             fc = torch.empty(B, H, dtype=BF16, device=x.device) if out is None else out.fc
             fc_in = _lib.cast_bf16(fc_feats.float().contiguous())
             gemm(fc_in, w.w_fc, w.b_fc, out_bf16=fc, relu=True)
@@ -242,7 +278,7 @@ class DecoderEngine:
             return out
         feats = Features(att.view(B, L, H), p_att.view(B, L, A), fc, att_masks, B, L)
         if keep_inputs:  # bf16 operand copies of the raw features, needed by the prologue wgrads
-            feats.x_in, feats.fc_in = x, (fc_in if self.kind == "topdown" else None)
+            feats.x_in, feats.fc_in = x, (fc_in if self.kind != "att2in2" else None)
             feats.bn = bn
         return feats
 
@@ -287,7 +323,7 @@ class DecoderEngine:
         """Static per-graph copies of the feature tiles (shapes of `feats`, a Features or a LazyFeatures)."""
         w, dev, B, L = self.w, feats.device, feats.B, feats.L
         return {"att": torch.empty(B, L, w.H, dtype=BF16, device=dev), "p_att": torch.empty(B, L, w.A, dtype=_lib.TILE_DTYPE, device=dev),
-                "fc": torch.empty(B, w.H, dtype=BF16, device=dev) if self.kind == "topdown" else None,
+                "fc": torch.empty(B, w.H, dtype=BF16, device=dev) if self.kind != "att2in2" else None,
                 "masks": None if feats.masks is None else torch.empty(B, L, dtype=torch.float32, device=dev)}
 
     # ---- one decoder step: X, c -> logits -------------------------------------------------------------
@@ -302,6 +338,12 @@ class DecoderEngine:
             ws["S"] = torch.empty(R, 5 * w.H + w.A, dtype=torch.float32, device=dev)
             ws["ctx"] = torch.empty(R, w.H, dtype=BF16, device=dev)
             ws["a2c"] = torch.empty(R, 2 * w.H, dtype=torch.float32, device=dev)
+        elif self.kind in ("stackatt", "denseatt"):
+            ws["S"] = torch.empty(R, 5 * w.H, dtype=torch.float32, device=dev)
+            ws["att_h"] = torch.empty(R, w.A, dtype=torch.float32, device=dev)
+            if self.kind == "denseatt":
+                ws["cat"] = torch.empty(R, 3 * w.H, dtype=BF16, device=dev)      # [h0 | h1 | h2]: operand of the two fusion layers
+                ws["out"] = torch.empty(R, w.H, dtype=BF16, device=dev)
         else:
             ws["G"] = torch.empty(R, 4 * w.H, dtype=torch.float32, device=dev)
             ws["att_h"] = torch.empty(R, w.A, dtype=torch.float32, device=dev)
@@ -348,6 +390,35 @@ class DecoderEngine:
                 check(lib.uic_lstm_maxout_fwd(ptr(S), S.stride(0), ptr(a2c), 2 * H, ptr(c[0]), ptr(c_out[0]), None,
                                               ptr(h_dst), Xn.stride(0), ptr(h_all), h_all.stride(0) if h_all is not None else 0,
                                               R, H, st))
+        elif self.kind in ("stackatt", "denseatt"):
+            if X_next is not None or alpha is not None:
+                raise NotImplementedError(f"{self.kind}: only the in-place (inference) step is built")
+            dense = self.kind == "denseatt"
+            S, ah, cat = ws["S"], ws["att_h"], ws.get("cat")
+
+            def cell(k0, k1, wl, bl, layer, h_slot, extra):   # 5H maxout cell (FCModel.LSTMCore): GEMM over X[:, k0:k1], h in place
+                gemm(X[:, k0:k1], wl, bl, out_f32=S)
+                check(lib.uic_lstm_maxout_fwd(ptr(S), 5 * H, None, 0, ptr(c[layer]), ptr(c_out[layer]), None, ptr(cols(X, h_slot)), ldx,
+                                              ptr(extra), extra.stride(0) if extra is not None else 0, R, H, st))
+
+            def attend(a0, a1, wq, bq, w_alpha, ctx_slot):     # Attention (AttModel.py:538-558): query GEMM over X[:, a0:a1]
+                gemm(X[:, a0:a1], wq, bq, out_f32=ah, exp_col0=0, exp_scale=_lib.ATT_F_SCALE)
+                _lib.att_step(ah, A, feats.p_att, feats.att, w_alpha, feats.masks, cols(X, ctx_slot), ldx, None, 0, None,
+                              feats.B, beams, feats.L, A, H)
+
+            cell(0, sl.h0[1], w.wl0, w.bl0, 0, sl.h0, cat[:, :H] if dense else None)                                  # :478 / :518
+            attend(sl.h0[0], sl.h0[1], w.w_h2att, w.b_h2att, w.w_alpha, sl.ctx1)                                        # :479 / :519
+            cell(sl.h0[0], sl.h1[1], w.wl1, w.bl1, 1, sl.h1, cat[:, H:2 * H] if dense else None)                       # :480 / :520
+            attend(sl.ctx1[0], sl.h1[1], w.w_q2, w.b_q2, w.w_alpha2, sl.ctx2)                                           # :481 / :521
+            if dense:
+                gemm(cat[:, :2 * H], w.w_f1, w.b_f1, out_bf16=cols(X, sl.f1), relu=True)                                # fusion1 :522
+            last_extra = cat[:, 2 * H:] if dense else h_all
+            cell((sl.f1 if dense else sl.h1)[0], sl.h2[1], w.wl2, w.bl2, 2, sl.h2, last_extra)                          # :482 / :522
+            if dense:
+                out = ws["out"] if h_all is None else h_all
+                gemm(cat, w.w_f2, w.b_f2, out_bf16=out, relu=True)                                                       # fusion2 :524
+                return out
+            return cols(X, sl.h2)
         else:
             G = ws["G"]
             gemm(X[:, :E + 3 * H], w.w1, w.b1, out_f32=G)
@@ -373,7 +444,7 @@ class DecoderEngine:
         sl = Slots(self.kind, w.E, w.H)
         X = torch.zeros(R, w.Kx, dtype=BF16, device=dev)
         c = torch.zeros(sl.n_state, R, w.H, dtype=torch.float32, device=dev)
-        if self.kind == "topdown":  # every beam row of image i carries fc[i]
+        if sl.fc is not None:  # every beam row of image i carries fc[i]
             idx = torch.arange(R, device=dev, dtype=torch.int64) // beams
             check(self.lib.uic_embed_rows(ptr(feats.fc), w.H, ptr(idx), ptr(X[:, sl.fc[0]:]), X.stride(0), R, w.H, feats.B, stream()))
         return X, c, sl
@@ -419,7 +490,7 @@ class DecoderEngine:
             f = s["feats"]
             X, c, sl, ws = s["X"], s["c"], s["sl"], s["ws"]
             X.zero_(); c.zero_(); s["seq"].zero_(); s["lp"].zero_(); s["nunf"].zero_(); s["tok"].zero_()
-            if self.kind == "topdown":
+            if sl.fc is not None:
                 check(lib.uic_embed_rows(ptr(f.fc), w.H, ptr(s["img_idx"]), ptr(X[:, sl.fc[0]:]), X.stride(0), B, w.H, B, stream()))
             self._embed(s["tok"], X, sl)
             xt_view = X[:, sl.xt[0]:sl.xt[0] + w.E]
@@ -504,7 +575,7 @@ class DecoderEngine:
                       "done_cnt", "tok"):
                 s[k].zero_()
             bufs = [(s["X"], s["c"]), (s["X2"], s["c2"])]
-            if self.kind == "topdown":
+            if sl.fc is not None:
                 for X, _ in bufs:
                     check(lib.uic_embed_rows(ptr(f.fc), w.H, ptr(s["img_idx"]), ptr(X[:, sl.fc[0]:]), X.stride(0), R, w.H, B, stream()))
             (ga, na), (gb, nb) = sl.gather
@@ -512,7 +583,7 @@ class DecoderEngine:
             if "X0" in s:
                 X0, c0 = s["X0"], s["c0"]
                 X0.zero_(); c0.zero_()
-                if self.kind == "topdown":
+                if sl.fc is not None:
                     check(lib.uic_embed_rows(ptr(f.fc), w.H, ptr(s["img_idx0"]), ptr(X0[:, sl.fc[0]:]), X0.stride(0), B, w.H, B, stream()))
                 self._embed(s["tok0"], X0, sl)   # BOS (AttModel.py:186-190)
                 h = self.core_step(X0, c0, f, s["ws0"], beams=1, tok=s["tok0"])
@@ -605,7 +676,7 @@ class DecoderEngine:
                 for X, c in s["state"][g]:
                     X.zero_()
                     c.zero_()
-                    if self.kind == "topdown":
+                    if sl.fc is not None:
                         check(lib.uic_embed_rows(ptr(f.fc), w.H, ptr(s["img_idx"]), ptr(X[:, sl.fc[0]:]), X.stride(0), R, w.H, B, stream()))
                 self._embed(s["tok"][g], s["state"][g][0][0], sl)   # BOS (AttModel.py:186-190)
             (ga, na), (gb, nb) = sl.gather

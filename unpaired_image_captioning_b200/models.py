@@ -21,7 +21,7 @@ from . import _lib
 from ._lib import check, ptr, stream
 from .engine import BF16, DecoderEngine, Features, Slots
 
-HOT_PATH_MODELS = ("att2in2", "att2all2", "topdown")
+HOT_PATH_MODELS = ("att2in2", "att2all2", "topdown", "stackatt", "denseatt")
 
 
 class CaptionModel(nn.Module):
@@ -108,6 +108,38 @@ class TopDownCore(_CoreBase):
         self.attention = Attention(opt)
 
 
+class LSTMCore(nn.Module):
+    """models/FCModel.py:14-42: the 5H maxout cell (parameters i2h, h2h)."""
+
+    def __init__(self, input_size, rnn_size, drop_prob_lm):
+        super().__init__()
+        self.i2h = nn.Linear(input_size, 5 * rnn_size)
+        self.h2h = nn.Linear(rnn_size, 5 * rnn_size)
+        self.dropout = nn.Dropout(drop_prob_lm)
+
+
+class StackAttCore(_CoreBase):
+    """models/AttModel.py:458-486 (parameters att1.*, att2.*, lstm0..2.*, emb2.*)."""
+
+    def __init__(self, opt):
+        super().__init__()
+        E, H = opt.input_encoding_size, opt.rnn_size
+        self.att1, self.att2 = Attention(opt), Attention(opt)
+        self.lstm0 = LSTMCore(E + H, H, opt.drop_prob_lm)
+        self.lstm1, self.lstm2 = LSTMCore(2 * H, H, opt.drop_prob_lm), LSTMCore(2 * H, H, opt.drop_prob_lm)
+        self.emb2 = nn.Linear(H, H)
+
+
+class DenseAttCore(StackAttCore):
+    """models/AttModel.py:489-526: StackAttCore + fusion1 (h_0, h_1 -> third cell) and fusion2 (h_0, h_1, h_2 -> output)."""
+
+    def __init__(self, opt):
+        super().__init__(opt)
+        H = opt.rnn_size
+        self.fusion1 = nn.Sequential(nn.Linear(2 * H, H), nn.ReLU(), nn.Dropout(opt.drop_prob_lm))
+        self.fusion2 = nn.Sequential(nn.Linear(3 * H, H), nn.ReLU(), nn.Dropout(opt.drop_prob_lm))
+
+
 class AttModel(CaptionModel):
     """models/AttModel.py:55-253."""
 
@@ -188,7 +220,7 @@ class AttModel(CaptionModel):
         decoded from the engine's exponential operand tile (engine.prepare), so the single-step API below
         (get_logprobs_state / core / core.attention) takes exactly the reference's tensors."""
         f = self.engine.prepare(fc_feats, att_feats, att_masks)
-        fc = fc_feats if self.kind == "att2in2" else f.fc
+        fc = fc_feats if self.kind == "att2in2" else f.fc        # (att2in2 / att2all2: fc_embed is the identity)
         return fc, f.att, _lib.tile_value(f.p_att), f.masks
 
     # ---- teacher-forced forward -----------------------------------------------------------------------
@@ -214,6 +246,11 @@ class AttModel(CaptionModel):
         empty = (seq[:, 1:T].sum(0) == 0).nonzero()
         return T if empty.numel() == 0 else int(empty[0]) + 1
 
+    def _require_training_path(self):
+        if getattr(self, "inference_only", False):
+            raise NotImplementedError(f"{type(self).__name__}: the backward pass (and training-mode dropout) of this core is not built on "
+                                      "the B200 path; call it under torch.no_grad() in eval() mode")
+
     def _check_tokens(self, seq):
         """Token ids outside [0, vocab_size] raise like the reference's nn.Embedding / gather would (IndexError) instead of
         being clamped by the kernels.  One tiny reduction + host read; skipped while a CUDA graph is being captured."""
@@ -229,6 +266,7 @@ class AttModel(CaptionModel):
             return att_feats.new_zeros((0, seq.size(1) - 1, self.vocab_size + 1), dtype=torch.float32)
         ss, drop = self._scheduled_sampling(att_feats.device), self._dropout(att_feats.device)
         if ss is not None or drop is not None or (torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters())):
+            self._require_training_path()
             from .autograd import decoder_logprobs
             return decoder_logprobs(self, fc_feats, att_feats, seq, att_masks, ss, drop)
         eng, lib = self.engine, _lib.load()
@@ -249,6 +287,7 @@ class AttModel(CaptionModel):
         (B, T, V) log-prob tensor.  Equals crit(model(fc, attri, att, labels, att_masks), labels[:,1:], masks[:,1:]).
         `global_mask_sum` (data parallel): the loss normaliser summed over all ranks (dp.global_mask_sum)."""
         from .autograd import decoder_loss
+        self._require_training_path()
         self._check_tokens(labels)
         return decoder_loss(self, fc_feats, att_feats, labels, masks, att_masks, global_mask_sum,
                             self._scheduled_sampling(att_feats.device), self._dropout(att_feats.device))
@@ -265,7 +304,7 @@ class AttModel(CaptionModel):
         p_b = _lib.exp_tile(p3)                                        # ctx2att output -> operand tile E = exp(2 p_att)
         masks = None if att_masks is None else att_masks.reshape(n_img, L).float().contiguous()
         fc_b = None
-        if self.kind == "topdown":
+        if self.kind != "att2in2":   # every other core consumes the embedded fc vector
             fc_b = fc if fc.dtype == BF16 else _lib.cast_bf16(fc.float().contiguous())
         if rows % n_img:
             raise ValueError(f"{rows} rows do not divide over {n_img} images")
@@ -288,17 +327,11 @@ class AttModel(CaptionModel):
         else:
             _lib.cast_bf16(xt_or_it.float().contiguous(), X[:, sl.xt[0]:sl.xt[1]])
         h0, c0 = state[0].float(), state[1].float().contiguous().clone()
-        if self.kind == "att2in2":
-            _lib.cast_bf16(h0[-1].contiguous(), X[:, sl.h_out[0]:sl.h_out[1]])
-        else:
-            _lib.cast_bf16(h0[0].contiguous(), X[:, sl.h_att_prev[0]:sl.h_att_prev[1]])
-            _lib.cast_bf16(h0[1].contiguous(), X[:, sl.h_lang[0]:sl.h_lang[1]])
+        for layer, slot in enumerate(sl.h_load):                       # previous hidden states -> their bf16 operand slots
+            _lib.cast_bf16(h0[layer].contiguous(), X[:, slot[0]:slot[1]])
         ws = eng._workspace(R, dev)
         h_out = eng.core_step(X, c0, feats, ws, beams=beams)
-        if self.kind == "att2in2":
-            h_state = h_out.float().unsqueeze(0)
-        else:
-            h_state = torch.stack([X[:, sl.h_att[0]:sl.h_att[1]].float(), h_out.float()])
+        h_state = torch.stack([X[:, slot[0]:slot[1]].float() for slot in sl.h_read])
         new_state = (h_state, c0)
         if not want_logprobs:
             return h_out.float(), new_state
@@ -352,6 +385,8 @@ class AttModel(CaptionModel):
         if att_feats.size(0) == 0:   # empty batch, like the reference: empty (0, seq_length) results
             return (att_feats.new_zeros((0, self.seq_length), dtype=torch.long), att_feats.new_zeros((0, self.seq_length), dtype=torch.float32))
         drop = self._dropout(att_feats.device)   # train() mode: the reference samples with its dropout layers active
+        if drop is not None or (torch.is_grad_enabled() and not sample_max and any(p.requires_grad for p in self.parameters())):
+            self._require_training_path() if getattr(self, "inference_only", False) else None
         with torch.no_grad():
             if beam_size > 1:
                 if drop is not None:
@@ -439,6 +474,31 @@ class TopDownModel(AttModel):
         self._bind_core()
 
 
+class StackAttModel(AttModel):
+    """models/AttModel.py:693-697.  Inference (teacher-forced log-probs, greedy / multinomial / beam sampling) runs on the
+    B200 path; its backward pass is not built yet, so training calls raise."""
+    kind = "stackatt"
+    inference_only = True
+
+    def __init__(self, opt):
+        super().__init__(opt)
+        self.num_layers = 3
+        self.core = StackAttCore(opt)
+        self._bind_core()
+
+
+class DenseAttModel(AttModel):
+    """models/AttModel.py:700-704 (the reference's best model, train.sh case 0).  Inference only, like StackAttModel."""
+    kind = "denseatt"
+    inference_only = True
+
+    def __init__(self, opt):
+        super().__init__(opt)
+        self.num_layers = 3
+        self.core = DenseAttCore(opt)
+        self._bind_core()
+
+
 def setup(opt):
     """models/__init__.py:22-59 for the models on the hot path."""
     if opt.caption_model == "att2in2":
@@ -447,4 +507,8 @@ def setup(opt):
         return Att2all2Model(opt)
     if opt.caption_model == "topdown":
         return TopDownModel(opt)
+    if opt.caption_model == "stackatt":
+        return StackAttModel(opt)
+    if opt.caption_model == "denseatt":
+        return DenseAttModel(opt)
     raise Exception("Caption model not supported: {}".format(opt.caption_model))
