@@ -85,6 +85,13 @@ int uic_gemm_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, float*
 int uic_gemm_bf16_ex(const void* A, int64_t lda, const void* B, int64_t ldb, float* c_f32, int64_t ldc, void* c_16, int64_t ldc16,
                      const float* bias, int M, int N, int K, int flags, int exp_col0, float exp_scale, void* stream);
 
+/* D = act(A B^T + bias) * post_scale[n] + post_shift[n]: a per-column affine behind the activation -- the eval-mode
+ * nn.BatchNorm1d(rnn_size) that use_bn = 2 appends to att_embed (models/AttModel.py:79-84), fused into the Linear + ReLU GEMM.
+ * post_scale / post_shift: fp32 vectors of length N. */
+int uic_gemm_bf16_affine(const void* A, int64_t lda, const void* B, int64_t ldb, float* c_f32, int64_t ldc, void* c_16, int64_t ldc16,
+                         const float* bias, const float* post_scale, const float* post_shift, int M, int N, int K, int flags,
+                         void* stream);
+
 /* ---- elementwise / layout ------------------------------------------------------------------ */
 /* dst_bf16[r, c] = bf16(relu?(src[r, c])) for an (rows x cols) fp32 matrix. Used to stage fp32
  * features and weights as tensor-core operands. */

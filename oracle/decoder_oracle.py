@@ -37,6 +37,18 @@ def _linear(sd, prefix, x):
     return F.linear(x, sd[prefix + ".weight"], sd[prefix + ".bias"])
 
 
+def logit_layer(sd, x):
+    """self.logit (models/AttModel.py:86-91): one Linear, or logit_layers - 1 blocks of Linear + ReLU + Dropout(0.5)
+    (indices 0, 3, 6, ... of the nn.Sequential; dropout inactive in eval mode) in front of it."""
+    if "logit.weight" in sd:
+        return _linear(sd, "logit", x)
+    i = 0
+    while f"logit.{i + 3}.weight" in sd:
+        x = torch.relu(_linear(sd, f"logit.{i}", x))
+        i += 3
+    return _linear(sd, f"logit.{i}", x)
+
+
 # ------------------------------------------------------------------------------------------------
 # feature prologue -- models/AttModel.py:99-117 (clip_att, _prepare_feature), :30-53 (pack_wrapper)
 # ------------------------------------------------------------------------------------------------
@@ -111,6 +123,13 @@ def prepare_features(sd, kind, fc_feats, att_feats, att_masks=None, drop=None):
         att = torch.relu(_linear(sd, "att_embed.1", xn))
     else:
         att = torch.relu(_linear(sd, "att_embed.0", att_feats))
+    if "att_embed.4.weight" in sd:
+        # use_bn = 2 (:84): a second BatchNorm1d(rnn_size) behind Linear + ReLU + Dropout, on the packed valid rows
+        if _BN_TRAIN:
+            mean2, var2, _ = bn_batch_stats(att, att_masks)
+        else:
+            mean2, var2 = sd["att_embed.4.running_mean"], sd["att_embed.4.running_var"]
+        att = (att - mean2) / torch.sqrt(var2 + 1e-5) * sd["att_embed.4.weight"] + sd["att_embed.4.bias"]
     if att_masks is not None:
         n_valid = att_masks.long().sum(1)
         valid = (torch.arange(att.size(1))[None, :] < n_valid[:, None]).to(att.dtype)
@@ -229,8 +248,8 @@ CORES = {"att2in2": core_att2in2, "att2all2": core_att2all2, "topdown": core_top
 
 def init_hidden(sd, kind, rows):
     # models/AttModel.py:94-97
-    H = sd["logit.weight"].size(1)
-    z = sd["logit.weight"].new_zeros(num_layers(kind), rows, H)
+    H = sd["ctx2att.weight"].size(1)
+    z = sd["ctx2att.weight"].new_zeros(num_layers(kind), rows, H)
     return (z, z.clone())
 
 
@@ -244,7 +263,7 @@ def logprobs_state(sd, kind, it, fc, att, p_att, att_masks, state, drop=None, t=
     out, state = CORES[kind](sd, xt, fc, att, p_att, state, att_masks)  # :162
     if drop is not None:
         out = out * dropout_mask(drop, DROP_OUT, np.arange(B) * T + t, out.size(1))
-    return torch.log_softmax(_linear(sd, "logit", out), dim=1), state    # :163
+    return torch.log_softmax(logit_layer(sd, out), dim=1), state         # :163
 
 
 # ------------------------------------------------------------------------------------------------
@@ -259,7 +278,7 @@ def teacher_forced(sd, kind, fc_feats, att_feats, seq, att_masks=None, ss_prob=0
     same hash for the coin.  `inputs` (B, T): feed exactly these tokens instead (to compare losses and gradients for
     the draws another implementation made)."""
     B, T = fc_feats.size(0), seq.size(1) - 1
-    V = sd["logit.weight"].size(0)
+    V = sd["embed.0.weight"].size(0)
     state = init_hidden(sd, kind, B)
     fc, att, p_att, masks = prepare_features(sd, kind, fc_feats, att_feats, att_masks, drop)
     steps, used, margins = [], [], []
@@ -617,7 +636,7 @@ def sample_beam(sd, kind, fc_feats, att_feats, seq_length, beam_size=10, att_mas
     B = fc_feats.size(0)
     margins = torch.full((B,), float("inf"), dtype=torch.float64)
     fc, att, p_att, masks = prepare_features(sd, kind, fc_feats, att_feats, att_masks)
-    V = sd["logit.weight"].size(0)
+    V = sd["embed.0.weight"].size(0)
     assert beam_size <= V                                               # AttModel.py:173
     seq = torch.zeros(seq_length, B, dtype=torch.int64)
     seq_lp = torch.zeros(seq_length, B)

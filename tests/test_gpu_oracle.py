@@ -118,6 +118,40 @@ def test_config5_layer_sizes_beam5_and_greedy():
     assert exact >= 1
 
 
+@pytest.mark.parametrize("kind,over", [("att2in2", dict(use_bn=2)), ("topdown", dict(logit_layers=2)),
+                                       ("denseatt", dict(use_bn=2, logit_layers=3)), ("att2in2", dict(logit_layers=2))])
+def test_second_batchnorm_and_hidden_logit_layers(kind, over):
+    """use_bn = 2 (BatchNorm1d behind att_embed, models/AttModel.py:84) and logit_layers > 1 (:89-91) in eval mode, at real
+    widths: teacher-forced log-probs, greedy and beam-3 against the oracle (itself pinned against the live reference for
+    these options, tests/test_oracle_vs_reference.py).  Training calls of these configurations fail loudly."""
+    opt = synth.make_opt(caption_model=kind, vocab_size=9999, rnn_size=512, input_encoding_size=512, att_hid_size=512, seq_length=16, **over)
+    sd = synth.init_state_dict(opt, seed=21)
+    B, L = 6, 36
+    fc, att = synth.make_features(B, L, 2048, seed=21)
+    labels, lmasks = synth.make_captions(B, 16, 9999, seed=21)
+    am = synth.make_att_masks(B, L, seed=21) if opt.use_bn else None
+    model = uic.setup(opt)
+    assert set(model.state_dict().keys()) == set(sd.keys())
+    model.load_state_dict(sd)
+    model = model.cuda().eval()
+    cu = lambda t: None if t is None else t.cuda()
+    ref = O.teacher_forced(sd, kind, fc, att, labels, am)
+    with torch.no_grad():
+        out = model(cu(fc), None, cu(att), cu(labels), cu(am))
+    sel = lmasks[:, 1:].bool()
+    rel = ((out.cpu() - ref).abs() / ref.abs().clamp_min(1.0))[sel]
+    assert float(rel.max()) < REL, float(rel.max())
+    ref_seq, _, margins = O.sample_greedy(sd, kind, fc, att, 16, am, return_margins=True, relative_margins=True)
+    seq, _ = model(cu(fc), None, cu(att), cu(am), opt={"beam_size": 1}, mode="sample")
+    assert not compare_greedy(seq.cpu(), ref_seq, margins, tol=REL)[2]
+    b_ref, _, _, b_margins = O.sample_beam(sd, kind, fc, att, 16, 3, am, return_margins=True)
+    b_seq, _ = model(cu(fc), None, cu(att), cu(am), opt={"beam_size": 3}, mode="sample")
+    assert not compare_beam(b_seq, b_ref, b_margins, tol=REL)[2]
+    model.train()
+    with pytest.raises(NotImplementedError):
+        model(cu(fc), None, cu(att), cu(labels), cu(lmasks), cu(am), mode="forward_loss")
+
+
 @pytest.mark.parametrize("kind", ["att2in2", "att2all2"])
 def test_gate_table_decode_equals_the_full_gemm(kind):
     """Decode loops take the input-word gate term from the (V, 5H) table (engine.use_gate_table): same captions and

@@ -15,7 +15,31 @@ def ref():
     return reference_shim.load()
 
 
-@pytest.mark.parametrize("kind", ["att2in2", "att2all2", "topdown"])
+@pytest.mark.parametrize("kind,over", [("att2in2", dict(use_bn=2)), ("topdown", dict(logit_layers=2)), ("denseatt", dict(use_bn=2, logit_layers=3)),
+                                       ("stackatt", dict(logit_layers=2))])
+def test_second_batchnorm_and_hidden_logit_layers(ref, kind, over):
+    """use_bn = 2 (models/AttModel.py:84) and logit_layers > 1 (:89-91), eval mode: log-probs, greedy, beam."""
+    models, _ = ref
+    opt = synth.make_opt(caption_model=kind, vocab_size=299, rnn_size=64, input_encoding_size=48, att_hid_size=40, seq_length=9,
+                         fc_feat_size=96, att_feat_size=96, **over)
+    sd = synth.init_state_dict(opt, seed=7, peaked=20.0, eos_bias=0.5)
+    model = models.setup(opt)
+    model.load_state_dict(sd, strict=True)
+    model.eval()
+    B, L = 5, 11
+    fc, att = synth.make_features(B, L, 96, seed=7)
+    labels, _ = synth.make_captions(B, 9, 299, seed=7, min_len=3)
+    am = synth.make_att_masks(B, L, seed=7) if opt.use_bn else None
+    with torch.no_grad():
+        torch.testing.assert_close(O.teacher_forced(sd, kind, fc, att, labels, am), model(fc, None, att, labels, am), rtol=1e-5, atol=2e-6)
+        for o in ({"beam_size": 1}, {"beam_size": 3}):
+            rs, rlp = model(fc, None, att, am, opt=dict(o), mode="sample")
+            s, lp = O.sample(sd, kind, fc, att, 9, am, dict(o))
+            assert torch.equal(s, rs), o
+            torch.testing.assert_close(lp, rlp, rtol=1e-5, atol=2e-6)
+
+
+@pytest.mark.parametrize("kind", ["att2in2", "att2all2", "topdown", "stackatt", "denseatt"])
 @pytest.mark.parametrize("seed,use_masks", [(11, False), (12, True)])
 def test_midsize_forward_loss_sampling(ref, kind, seed, use_masks):
     models, criterion = ref

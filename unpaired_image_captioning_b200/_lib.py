@@ -26,6 +26,7 @@ SIGNATURES = {
     "uic_profile_dump": (_i64, [C.c_char_p, _i64]),
     "uic_gemm_bf16": (_i, [_p, _i64, _p, _i64, _p, _i64, _p, _i64, _p, _i, _i, _i, _i, _p]),
     "uic_gemm_bf16_ex": (_i, [_p, _i64, _p, _i64, _p, _i64, _p, _i64, _p, _i, _i, _i, _i, _i, _f, _p]),
+    "uic_gemm_bf16_affine": (_i, [_p, _i64, _p, _i64, _p, _i64, _p, _i64, _p, _p, _p, _i, _i, _i, _i, _p]),
     "uic_cast_f32_bf16": (_i, [_p, _i64, _p, _i64, _i64, _i64, _i, _p]),
     "uic_embed_rows": (_i, [_p, _i64, _p, _p, _i64, _i, _i, _i, _p]),
     "uic_zero_padded_rows": (_i, [_p, _p, _i, _i, _i, _p]),
@@ -159,7 +160,7 @@ def tile_value(e_tile):
 
 
 def gemm(a, b, bias=None, out_f32=None, out_bf16=None, relu=False, accumulate=False, a_mn=False, b_mn=False,
-         exp_col0=0, exp_scale=0.0, a_stream=False, b_stream=False):
+         exp_col0=0, exp_scale=0.0, a_stream=False, b_stream=False, post_scale=None, post_shift=None):
     """D[M,N] = act(A @ B^T + bias).  `a` is (M,K) [or (K,M) if a_mn], `b` is (N,K) [or (K,N) if b_mn];
     both 2-D bf16 views whose last stride is 1 (row pitch arbitrary).  a_stream / b_stream: the operand is read once
     (L2 evict-first hint), e.g. the raw feature matrix of the prologue."""
@@ -178,6 +179,13 @@ def gemm(a, b, bias=None, out_f32=None, out_bf16=None, relu=False, accumulate=Fa
     flags = ((GEMM_RELU if relu else 0) | (GEMM_ACCUMULATE if accumulate else 0) | (GEMM_A_MN if a_mn else 0) |
              (GEMM_B_MN if b_mn else 0) | (GEMM_OUT_F16 if out_f16 else 0) | (GEMM_A_STREAM if a_stream else 0) |
              (GEMM_B_STREAM if b_stream else 0))
+    if post_scale is not None:   # act(.) * post_scale + post_shift per column (eval-mode BatchNorm behind the layer)
+        if exp_scale or post_shift is None or post_scale.numel() != N or post_shift.numel() != N:
+            raise ValueError("gemm: post_scale / post_shift must be fp32 vectors of length N (not combinable with the exp epilogue)")
+        check(load().uic_gemm_bf16_affine(ptr(a), a.stride(0), ptr(b), b.stride(0), ptr(out_f32), out_f32.stride(0) if out_f32 is not None else 0,
+                                          ptr(out_bf16), out_bf16.stride(0) if out_bf16 is not None else 0, ptr(bias),
+                                          ptr(post_scale.float().contiguous()), ptr(post_shift.float().contiguous()), M, N, K, flags, stream()))
+        return
     check(load().uic_gemm_bf16_ex(ptr(a), a.stride(0), ptr(b), b.stride(0), ptr(out_f32), out_f32.stride(0) if out_f32 is not None else 0,
                                   ptr(out_bf16), out_bf16.stride(0) if out_bf16 is not None else 0, ptr(bias), M, N, K, flags,
                                   int(exp_col0), float(exp_scale), stream()))

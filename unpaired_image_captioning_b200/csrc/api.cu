@@ -273,6 +273,12 @@ int uic_gemm_bf16_ex(const void* A, int64_t lda, const void* B, int64_t ldb, flo
   return gemm_bf16(A, lda, B, ldb, c_f32, ldc, c_16, ldc16, bias, M, N, K, flags, ST(stream), exp_col0, exp_scale);
 }
 
+int uic_gemm_bf16_affine(const void* A, int64_t lda, const void* B, int64_t ldb, float* c_f32, int64_t ldc, void* c_16, int64_t ldc16,
+                         const float* bias, const float* post_scale, const float* post_shift, int M, int N, int K, int flags, void* stream) {
+  REQUIRE(A && B && post_scale && post_shift, UIC_ERR_ARG, "uic_gemm_bf16_affine: null pointer");
+  return gemm_bf16(A, lda, B, ldb, c_f32, ldc, c_16, ldc16, bias, M, N, K, flags, ST(stream), 0, 0.0f, post_scale, post_shift);
+}
+
 int uic_logit_stats_parts(int rows, int V) { return V > 0 ? logit_stats_parts(rows, V) : 0; }
 int uic_logit_stats_entry_floats(int kslots) { return kslots > 0 ? logit_stats_entry_floats(kslots) : 0; }
 

@@ -73,6 +73,10 @@ struct GemmEpilogue {
   // L2 eviction hints of the operand loads (uic_ptx.cuh): weights re-read by every decode step are kept (evict-last),
   // operands streamed once (raw features of the prologue) are marked evict-first
   unsigned long long policy_a, policy_b;
+  // optional per-column affine AFTER the activation: y = act(x) * post_scale[n] + post_shift[n] (an eval-mode BatchNorm1d
+  // behind Linear + ReLU, use_bn = 2 of models/AttModel.py:79-84); takes the element-wise store path
+  const float* post_scale;
+  const float* post_shift;
 };
 
 #define UIC_TRACE(slot)                                                              \
@@ -96,6 +100,7 @@ __device__ __forceinline__ __nv_bfloat16 store16(float a, int f16) {
 }
 __device__ __forceinline__ float epi_act(float v, int col, const GemmEpilogue& ep) {
   if (ep.relu) v = fmaxf(v, 0.0f);
+  if (ep.post_scale != nullptr) v = fmaf(v, __ldg(ep.post_scale + col), __ldg(ep.post_shift + col));
   if (ep.exp_scale != 0.0f && col >= ep.exp_col0) v = fminf(ep.exp_scale * __expf(2.0f * v), ep.out_f16 ? 65504.0f : EXP_CAP);
   return v;
 }
@@ -492,7 +497,8 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             }
           }
         };
-        const bool fast = chunk_vec && !exp_mixed && (ep.c_f32 == nullptr || vec_f32) && (ep.c_bf16 == nullptr || vec_16) && !(ep.debug & 1);
+        const bool fast = chunk_vec && !exp_mixed && (ep.c_f32 == nullptr || vec_f32) && (ep.c_bf16 == nullptr || vec_16) && !(ep.debug & 1) &&
+                          ep.post_scale == nullptr;
         if (ep.debug & 1) {
         } else if (!fast) {
           store_rows(std::integral_constant<int, 3>{});
@@ -653,7 +659,7 @@ static int dispatch_major(bool a_mn, bool b_mn, const CUtensorMap& ta, const CUt
 
 int gemm_bf16(const void* A, long long lda, const void* B, long long ldb, float* c_f32, long long ldc, void* c_bf16,
               long long ldcb, const float* bias, int M, int N, int K, int flags, cudaStream_t stream, int exp_col0,
-              float exp_scale) {
+              float exp_scale, const float* post_scale, const float* post_shift) {
   if (M <= 0 || N <= 0 || K <= 0) return set_error(UIC_ERR_SHAPE, "gemm_bf16: empty problem M=%d N=%d K=%d", M, N, K);
   if (c_f32 == nullptr && c_bf16 == nullptr) return set_error(UIC_ERR_ARG, "gemm_bf16: no output buffer");
   const bool a_mn = flags & UIC_GEMM_A_MN_MAJOR;
@@ -663,6 +669,9 @@ int gemm_bf16(const void* A, long long lda, const void* B, long long ldb, float*
   // tile walk: keep the bigger operand's tile hot (see GemmEpilogue::n_fastest); the smaller one must fit L2 comfortably
   ep.n_fastest = (M > N && static_cast<long long>(N) * K * 2 <= (32LL << 20)) ? 1 : 0;
   gemm_l2_policies(ep, M, N, K, flags);
+  if ((post_scale == nullptr) != (post_shift == nullptr)) return set_error(UIC_ERR_ARG, "gemm_bf16: post_scale and post_shift come together");
+  ep.post_scale = post_scale;
+  ep.post_shift = post_shift;
   if (gemm_impl() == GEMM_IMPL_SIMT) {
     dim3 grid((N + 15) / 16, (M + 15) / 16), block(16, 16);
     launch_begin("gemm_bf16_simt", stream);

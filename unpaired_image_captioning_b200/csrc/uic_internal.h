@@ -62,7 +62,7 @@ __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepc
 // kernels.  Each returns 0 or a negative UIC_ERR_* (after set_error).
 int gemm_bf16(const void* A, long long lda, const void* B, long long ldb, float* c_f32, long long ldc, void* c_bf16,
               long long ldcb, const float* bias, int M, int N, int K, int flags, cudaStream_t stream, int exp_col0 = 0,
-              float exp_scale = 0.0f);
+              float exp_scale = 0.0f, const float* post_scale = nullptr, const float* post_shift = nullptr);
 int logit_stats_parts(int M, int N);
 int logit_stats_entry_floats(int kslots);
 int logit_stats(const void* A, long long lda, const void* B, long long ldb, const float* bias, const long long* banned,

@@ -57,7 +57,16 @@ class PackedWeights:
         else:
             self.w_att_embed, self.b_att_embed = _bf16(sd["att_embed.0.weight"]), f32("att_embed.0.bias")
         self.w_ctx2att, self.b_ctx2att = _bf16(sd["ctx2att.weight"]), f32("ctx2att.bias")
-        self.w_logit, self.b_logit = _bf16(sd["logit.weight"]), f32("logit.bias")
+        # self.logit (models/AttModel.py:86-91): logit_layers - 1 hidden Linear + ReLU (+ Dropout(0.5), inactive in eval) blocks
+        n_logit = int(getattr(model, "logit_layers", 1))
+        last = "logit" if n_logit == 1 else f"logit.{3 * (n_logit - 1)}"
+        self.logit_hidden = [(_bf16(sd[f"logit.{3 * i}.weight"]), f32(f"logit.{3 * i}.bias")) for i in range(n_logit - 1)]
+        self.w_logit, self.b_logit = _bf16(sd[last + ".weight"]), f32(last + ".bias")
+        self.bn2 = None
+        if self.use_bn == 2:   # eval-mode BatchNorm1d(rnn_size) behind att_embed's Linear + ReLU: y * s + t per column
+            bn = model.att_embed[4]
+            s2 = f32("att_embed.4.weight") * torch.rsqrt(f32("att_embed.4.running_var") + bn.eps)
+            self.bn2 = (s2.contiguous(), (f32("att_embed.4.bias") - f32("att_embed.4.running_mean") * s2).contiguous())
         if self.kind in ("att2in2", "topdown"):
             self.w_alpha = f32("core.attention.alpha_net.weight").reshape(-1).contiguous()
             w_h2att, b_h2att = f32("core.attention.h2att.weight"), f32("core.attention.h2att.bias")
@@ -256,7 +265,12 @@ class DecoderEngine:
         w_ae, b_ae, bn = w.w_att_embed, w.b_att_embed, None
         if w.use_bn:
             w_ae, b_ae, bn = self._fold_bn(x, att_masks, B, L)
-        gemm(x, w_ae, b_ae, out_bf16=att, relu=True, a_stream=True)   # the raw features are read once
+        if w.bn2 is not None:
+            if self.model.training:
+                raise NotImplementedError("use_bn = 2: the second BatchNorm runs with its running statistics only (eval mode)")
+            gemm(x, w_ae, b_ae, out_bf16=att, relu=True, a_stream=True, post_scale=w.bn2[0], post_shift=w.bn2[1])
+        else:
+            gemm(x, w_ae, b_ae, out_bf16=att, relu=True, a_stream=True)   # the raw features are read once
         if att_masks is not None:
             check(self.lib.uic_zero_padded_rows(ptr(att), ptr(att_masks), B, L, H, stream()))
         if drop is not None:   # att_embed's nn.Dropout (training mode, AttModel.py:79-84): ctx2att sees the dropped tile
@@ -436,7 +450,17 @@ class DecoderEngine:
                                         ptr(h_all), h_all.stride(0) if h_all is not None else 0, R, H, st))
         return cols(Xn, sl.h_out)
 
+    def logit_input(self, h):
+        """logit_layers > 1 (models/AttModel.py:89-91): the hidden Linear + ReLU blocks in front of the vocabulary projection
+        (eval mode: their Dropout(0.5) is inactive).  h: (rows, H) bf16 view -> (rows, H) bf16."""
+        for w_i, b_i in self.w.logit_hidden:
+            nxt = torch.empty(h.shape[0], self.w.H, dtype=BF16, device=h.device)
+            gemm(h, w_i, b_i, out_bf16=nxt, relu=True)
+            h = nxt
+        return h
+
     def logits_of(self, h, out):
+        """Vocabulary projection of logit_input(core output)."""
         gemm(h, self.w.w_logit, self.w.b_logit, out_f32=out)
 
     def _new_state(self, R, dev, feats, beams):
@@ -502,6 +526,7 @@ class DecoderEngine:
                     s["h_drop"].copy_(h)
                     h = s["h_drop"]
                     _lib.dropout(h, drop, _lib.DROP_OUT, row0=t, row_stride=T + 1)
+                h = self.logit_input(h)
                 if self.fused_vocab:
                     # logit GEMM with the statistics epilogue (max / sum-exp / arg-max per column part) + merge:
                     # the (B, V) logits are never written
@@ -586,7 +611,7 @@ class DecoderEngine:
                 if sl.fc is not None:
                     check(lib.uic_embed_rows(ptr(f.fc), w.H, ptr(s["img_idx0"]), ptr(X0[:, sl.fc[0]:]), X0.stride(0), B, w.H, B, stream()))
                 self._embed(s["tok0"], X0, sl)   # BOS (AttModel.py:186-190)
-                h = self.core_step(X0, c0, f, s["ws0"], beams=1, tok=s["tok0"])
+                h = self.logit_input(self.core_step(X0, c0, f, s["ws0"], beams=1, tok=s["tok0"]))
                 check(lib.uic_logit_stats(ptr(h), h.stride(0), ptr(w.w_logit), w.H, ptr(w.b_logit), None, 1,
                                           ptr(s["stats0"]), B, w.V, w.H, s["kslots"], 1, 0.0, None, 0, stream()))
                 Xn, cn = bufs[1]
@@ -601,7 +626,7 @@ class DecoderEngine:
             for t in range(t_first, T):
                 X, c = bufs[t % 2]
                 Xn, cn = bufs[(t + 1) % 2]
-                h = self.core_step(X, c, f, ws, beams=b, tok=s["tok"])
+                h = self.logit_input(self.core_step(X, c, f, ws, beams=b, tok=s["tok"]))
                 if self.fused_vocab and b <= 8:
                     banned = s["tok"] if (tk_flags and t > 0) else None
                     check(lib.uic_logit_stats(ptr(h), h.stride(0), ptr(w.w_logit), w.H, ptr(w.b_logit), ptr(banned), 1,
@@ -688,7 +713,7 @@ class DecoderEngine:
                     X, c = s["state"][g][lt % 2]
                     Xn, cn = s["state"][g][(lt + 1) % 2]
                     tok = s["tok"][g]
-                    h = self.core_step(X, c, f, ws, beams=b, tok=tok)
+                    h = self.logit_input(self.core_step(X, c, f, ws, beams=b, tok=tok))
                     self.logits_of(h, ws["logits"])
                     kp = b * (g + 1)                                # enough to survive the penalties on <= g * b tokens
                     check(lib.uic_row_topk(ptr(ws["logits"]), w.V, ptr(tok) if (tk_flags and lt > 0) else None, ptr(s["cand_val"]),
@@ -778,7 +803,7 @@ class DecoderEngine:
             self._embed(seq[:, t].contiguous(), X, sl)
             self.core_step(X, c, feats, ws, h_all=h_all[:, t])
         logits = torch.empty(B * T_total, w.V, dtype=torch.float32, device=dev)
-        gemm(h_all.view(B * T_total, w.H), w.w_logit, w.b_logit, out_f32=logits)
+        gemm(self.logit_input(h_all.view(B * T_total, w.H)), w.w_logit, w.b_logit, out_f32=logits)
         return logits.view(B, T_total, w.V)
 
     def _workspace_tf(self, R, dev):

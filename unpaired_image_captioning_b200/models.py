@@ -157,24 +157,32 @@ class AttModel(CaptionModel):
         self.att_feat_size = opt.att_feat_size
         self.att_hid_size = opt.att_hid_size
         self.use_bn = getattr(opt, "use_bn", 0)
-        if self.use_bn not in (0, 1):
-            raise NotImplementedError("use_bn = 2 (a second BatchNorm behind att_embed) is not on the B200 hot path yet")
-        if getattr(opt, "logit_layers", 1) != 1:
-            raise NotImplementedError("logit_layers > 1 is not on the B200 hot path")
+        if self.use_bn not in (0, 1, 2):
+            raise ValueError(f"use_bn={self.use_bn}")
+        self.logit_layers = int(getattr(opt, "logit_layers", 1))
+        if self.logit_layers < 1:
+            raise ValueError(f"logit_layers={self.logit_layers}")
+        # use_bn = 2 (second BatchNorm behind att_embed) and logit_layers > 1 run in eval() mode (inference); their backward
+        # passes are not built, so training calls raise (see _require_training_path)
+        self.inference_only = bool(getattr(self, "inference_only", False) or self.use_bn == 2 or self.logit_layers > 1)
         for name, v in (("rnn_size", self.rnn_size), ("input_encoding_size", self.input_encoding_size),
                         ("att_hid_size", self.att_hid_size), ("att_feat_size", self.att_feat_size),
                         ("fc_feat_size", self.fc_feat_size)):
             if v % 8:
                 raise ValueError(f"{name}={v} must be a multiple of 8 (16-byte bf16 rows for TMA)")
         self.ss_prob = 0.0
-        self.logit_layers = 1
         self.embed = nn.Sequential(nn.Embedding(self.vocab_size + 1, self.input_encoding_size), nn.ReLU(),
                                    nn.Dropout(self.drop_prob_lm))
         self.fc_embed = nn.Sequential(nn.Linear(self.fc_feat_size, self.rnn_size), nn.ReLU(), nn.Dropout(self.drop_prob_lm))
         # use_bn = 1 (opts.py:52): BatchNorm1d over the packed valid regions first; the engine folds it into the Linear
         self.att_embed = nn.Sequential(*(((nn.BatchNorm1d(self.att_feat_size),) if self.use_bn else ()) +
-                                         (nn.Linear(self.att_feat_size, self.rnn_size), nn.ReLU(), nn.Dropout(self.drop_prob_lm))))
-        self.logit = nn.Linear(self.rnn_size, self.vocab_size + 1)
+                                         (nn.Linear(self.att_feat_size, self.rnn_size), nn.ReLU(), nn.Dropout(self.drop_prob_lm)) +
+                                         ((nn.BatchNorm1d(self.rnn_size),) if self.use_bn == 2 else ())))
+        if self.logit_layers == 1:
+            self.logit = nn.Linear(self.rnn_size, self.vocab_size + 1)
+        else:   # models/AttModel.py:89-91
+            blocks = [m for _ in range(self.logit_layers - 1) for m in (nn.Linear(self.rnn_size, self.rnn_size), nn.ReLU(), nn.Dropout(0.5))]
+            self.logit = nn.Sequential(*(blocks + [nn.Linear(self.rnn_size, self.vocab_size + 1)]))
         self.ctx2att = nn.Linear(self.rnn_size, self.att_hid_size)
         self.done_beams = []
         self._engine = None
@@ -248,8 +256,9 @@ class AttModel(CaptionModel):
 
     def _require_training_path(self):
         if getattr(self, "inference_only", False):
-            raise NotImplementedError(f"{type(self).__name__}: the backward pass (and training-mode dropout) of this core is not built on "
-                                      "the B200 path; call it under torch.no_grad() in eval() mode")
+            raise NotImplementedError(f"{type(self).__name__} (use_bn={self.use_bn}, logit_layers={self.logit_layers}): the backward pass "
+                                      "(and training-mode dropout / batch statistics) of this configuration is not built on the B200 "
+                                      "path; call it under torch.no_grad() in eval() mode")
 
     def _check_tokens(self, seq):
         """Token ids outside [0, vocab_size] raise like the reference's nn.Embedding / gather would (IndexError) instead of
@@ -335,7 +344,7 @@ class AttModel(CaptionModel):
         new_state = (h_state, c0)
         if not want_logprobs:
             return h_out.float(), new_state
-        eng.logits_of(h_out, ws["logits"])
+        eng.logits_of(eng.logit_input(h_out), ws["logits"])
         out = torch.empty(R, w.V, device=dev)
         check(lib.uic_log_softmax_rows(ptr(ws["logits"]), w.V, ptr(out), w.V, R, w.V, stream()))
         return out, new_state

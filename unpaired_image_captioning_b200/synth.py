@@ -131,9 +131,22 @@ def init_state_dict(opt, seed=1234, peaked=0.0, eos_bias=0.0):
         sd["att_embed.0.running_var"] = 0.25 + 0.2 * torch.rand(D, generator=g)
         sd["att_embed.0.num_batches_tracked"] = torch.tensor(3, dtype=torch.int64)
         sd["att_embed.1.weight"], sd["att_embed.1.bias"] = lin(H, D)
+        if opt.use_bn == 2:   # a second BatchNorm1d(rnn_size) behind Linear + ReLU + Dropout (:84)
+            sd["att_embed.4.weight"] = 0.5 + torch.rand(H, generator=g)
+            sd["att_embed.4.bias"] = 0.1 * torch.randn(H, generator=g)
+            sd["att_embed.4.running_mean"] = 0.2 + 0.05 * torch.randn(H, generator=g)
+            sd["att_embed.4.running_var"] = 0.1 + 0.1 * torch.rand(H, generator=g)
+            sd["att_embed.4.num_batches_tracked"] = torch.tensor(3, dtype=torch.int64)
     else:
         sd["att_embed.0.weight"], sd["att_embed.0.bias"] = lin(H, D)
-    sd["logit.weight"], sd["logit.bias"] = lin(V, H)
+    n_logit = getattr(opt, "logit_layers", 1)
+    if n_logit == 1:
+        sd["logit.weight"], sd["logit.bias"] = lin(V, H)
+    else:   # [Linear(H, H), ReLU, Dropout(0.5)] x (n - 1) + Linear(H, V) in one nn.Sequential (:89-91)
+        for i in range(n_logit - 1):
+            sd[f"logit.{3 * i}.weight"], sd[f"logit.{3 * i}.bias"] = lin(H, H)
+        sd[f"logit.{3 * (n_logit - 1)}.weight"], sd[f"logit.{3 * (n_logit - 1)}.bias"] = lin(V, H)
+    last = "logit" if n_logit == 1 else f"logit.{3 * (n_logit - 1)}"
     sd["ctx2att.weight"], sd["ctx2att.bias"] = lin(A, H)
     if opt.caption_model in ("att2in2", "att2all2"):
         if opt.caption_model == "att2all2":
@@ -165,8 +178,8 @@ def init_state_dict(opt, seed=1234, peaked=0.0, eos_bias=0.0):
         sd["core.attention.h2att.weight"], sd["core.attention.h2att.bias"] = lin(A, H)
         sd["core.attention.alpha_net.weight"], sd["core.attention.alpha_net.bias"] = lin(1, A)
     if peaked:
-        sd["logit.weight"] = sd["logit.weight"] * peaked
+        sd[last + ".weight"] = sd[last + ".weight"] * peaked
     if eos_bias:
-        sd["logit.bias"] = sd["logit.bias"].clone()
-        sd["logit.bias"][0] += eos_bias
+        sd[last + ".bias"] = sd[last + ".bias"].clone()
+        sd[last + ".bias"][0] += eos_bias
     return sd
