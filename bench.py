@@ -18,6 +18,8 @@ One "step" = one pass of the hot path over one batch of synthetic input.  Rank 0
                    (beam-5, vocab 30k, rnn 1024) and the stock-PyTorch eager decoder on the same GPU
   --workload cfg3: the TopDown XE training step is the headline (`--strong`: global batch 512 split over the ranks)
   --workload cfg5: beam-5 sampling of 500-image chunks of configs[4]
+  --workload cfg4: configs[3], the "unpaired" joint step: TopDown decoder step (batch 256 per GPU) + pivot-translator step
+      (PyTorch arithmetic, the whole step replayed from one CUDA graph -- pivot.py); joint samples/s
   cpu_baseline / --impl reference : the oracle port of the reference's CPU path on this box's cores
 """
 from __future__ import annotations
@@ -154,7 +156,8 @@ def _bind_near_gpu(local):
 
 
 def _workload_config(name, cfg, opt, world, extra=None):
-    label = {"cfg2": "configs[1]: att2in2 decoder beam-%d sampling" % cfg["beam_size"],
+    label = {"cfg4": "configs[3]: joint step = TopDown decoder training step + pivot-translator (NMT) training step",
+             "cfg2": "configs[1]: att2in2 decoder beam-%d sampling" % cfg["beam_size"],
              "cfg3": "configs[2]: TopDown XE training step (fwd + loss + bwd + gradient all-reduce + clip + Adam)",
              "cfg5": "configs[4]: att2in2 rnn 1024 / vocab 30k beam-%d sampling, one 500-image chunk per step" % cfg["beam_size"]}[name]
     c = {"workload": label, "caption_model": opt.caption_model, "rows_per_gpu": cfg["batch"], "beam_size": cfg["beam_size"],
@@ -226,6 +229,9 @@ def run_reference(args, world, rank):
     sd = synth.init_state_dict(opt, seed=1234)
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
+    if args.workload == "cfg4":
+        _emit(_cfg4_cpu_line(args, world, threads, impl_reference=True))
+        return
     if args.workload == "cfg3":
         sample = 16
         fc, att = synth.make_features(sample, cfg["att_size"], opt.att_feat_size, seed=4321)
@@ -385,6 +391,120 @@ def _eager_baseline():
     return res
 
 
+def _cfg4_cpu(rows, repeats, threads):
+    """CPU joint step on a bounded sample: oracle decoder training computation (TopDown, `rows` rows) + the translator's
+    forward + NLL + backward in PyTorch on the host cores (`rows` sentence pairs); samples/s."""
+    from oracle import decoder_oracle as O
+    from unpaired_image_captioning_b200 import pivot, synth
+    torch.set_num_threads(threads)
+    opt, cfg = synth.opt_for("cfg4")
+    sd = synth.init_state_dict(opt, seed=1234)
+    fc, att = synth.make_features(rows, cfg["att_size"], opt.att_feat_size, seed=4321)
+    labels, masks = synth.make_captions(rows, opt.seq_length, opt.vocab_size, seed=4321)
+    gen = torch.Generator().manual_seed(1234)
+    torch.manual_seed(1234)
+    nmt = pivot.PivotNMT().train()
+    src, n = pivot.sentences(rows, 12000, gen)
+    tgt, _ = pivot.sentences(rows, 8600, gen, bos=pivot.BOS)
+    best = float("inf")
+    for i in range(repeats + 1):
+        t0 = time.perf_counter()
+        O.loss_and_grads(sd, opt.caption_model, fc, att, labels, masks)
+        nmt.zero_grad(set_to_none=True)
+        nll, cnt = nmt(src, n, tgt)
+        (nll / cnt).backward()
+        dt = time.perf_counter() - t0
+        if i > 0:
+            best = min(best, dt)
+    return rows / best
+
+
+def _cfg4_cpu_line(args, world, threads, impl_reference=False):
+    from unpaired_image_captioning_b200 import synth
+    opt, cfg = synth.opt_for("cfg4")
+    rows = 16
+    v = _cfg4_cpu(rows, max(1, args.steps if impl_reference else 1), threads)
+    base = {"value": v, "unit": "samples/s", "cores": threads, "kind": "port",
+            "sample": f"{rows} rows: oracle TopDown forward + XE + backward and the PyTorch translator forward + NLL + backward on the host cores, fp32"}
+    if not impl_reference:
+        return base
+    return {"impl": "reference", "metric": "joint_train_samples_per_s", "value": v, "unit": "samples/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": rows / v * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": _workload_config("cfg4", cfg, opt, world, {"sample": base["sample"]}),
+            "cpu_baseline": base, "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+
+
+def _run_cfg4(args, world, rank, local, peaks, sampler, threads):
+    """configs[3]: decoder step (this library's kernels, CUDA graph) + translator step (PyTorch arithmetic, CUDA graph)."""
+    from unpaired_image_captioning_b200 import _lib, pivot, synth, train_bench
+    st = train_bench.make_state(local, rank, world, cfg_name="cfg4")
+    B = st["rows"]
+    l0 = _lib.launch_count()
+    train_bench.one_train_step(st=st)
+    launches = _lib.launch_count() - l0
+    dec = train_bench.GraphedTrainStep(st)
+    torch.manual_seed(1234)                                    # identical translator weights on every rank
+    gen = torch.Generator().manual_seed(1234 + rank)           # per-rank sentences
+    nmt = pivot.PivotNMT().cuda().train()
+    src, n = pivot.sentences(B, 12000, gen, max_len=30)
+    tgt, _ = pivot.sentences(B, 8600, gen, bos=pivot.BOS, max_len=30)
+    host = [t.pin_memory() for t in (src, n, tgt)]
+    batch = [t.cuda() for t in host]
+    eager = pivot.PivotTrainStep(nmt, src.size(0), tgt.size(0), B, graph=False, batch=batch)
+    ms_eager = _timed(eager.step, max(3, args.steps // 4), 2, world)
+    graphed = pivot.PivotTrainStep(nmt, src.size(0), tgt.size(0), B, graph=True, batch=batch)
+    ms_dec = _timed(dec, args.steps, args.warmup, world)
+    ms_nmt = _timed(graphed.step, args.steps, args.warmup, world)
+
+    def joint():
+        dec()
+        graphed.step()
+
+    ms_joint = _timed(joint, args.steps, args.warmup, world)
+    hd = st["host"]
+
+    def e2e_step():          # both halves fed from pinned host memory, both losses read back
+        for k in ("fc", "att", "labels", "masks"):
+            st[k].copy_(hd[k], non_blocking=True)
+        graphed.load(*host)
+        a = dec()
+        b = graphed.step()
+        return float(a) + float(b)
+
+    ms_e2e = _timed_wall(e2e_step, args.steps, args.warmup, world)
+    clocks = sampler.stop()
+    # decoder half: tensor roofline of its GEMMs from a profiled eager step (every rank: the step contains the all-reduces)
+    train_bench.one_train_step(st=st)
+    torch.cuda.synchronize()
+    _lib.profile(True)
+    train_bench.one_train_step(st=st)
+    prof = {k: (float(nn_), ms) for k, (nn_, ms) in _lib.profile_dump().items()}
+    _lib.profile(False)
+    if rank != 0:
+        return None
+    opt, cfg = st["opt"], st["cfg"]
+    h2d = sum(hd[k].numel() * hd[k].element_size() for k in ("fc", "att", "labels", "masks")) + sum(t.numel() * 8 for t in host)
+    gemms = _gemm_rooflines(prof, peaks["bf16_tflops"])
+    g0 = gemms[0] if gemms else None
+    cpu = None if (world > 1 or args.no_cpu_baseline) else _cfg4_cpu_line(args, world, threads)
+    return {"metric": "joint_train_samples_per_s", "value": world * B / (ms_joint * 1e-3), "unit": "samples/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_joint, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16 (decoder kernels) + fp32 (translator, PyTorch)", "data": "synthetic",
+            "config": _workload_config("cfg4", cfg, opt, world, {
+                "decoder_ms": ms_dec, "translator_graph_ms": ms_nmt, "translator_eager_ms": ms_eager,
+                "translator_share_of_joint_step": ms_nmt / (ms_nmt + ms_dec), "translator": "PyTorch restatement (pivot.py), whole step "
+                "in one CUDA graph; parity unpinned (reference translator not importable, SURVEY F2/F3)",
+                "sentence_length": "U{5..30}, padded to 30 / 32", "src_vocab": 12000, "tgt_vocab": 8600,
+                "translator_params_M": round(sum(p.numel() for p in nmt.parameters()) / 1e6, 1)}),
+            "clocks": clocks,
+            "e2e": {"value": world * B / (ms_e2e * 1e-3), "unit": "samples/s", "ms_per_step": ms_e2e, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 8},
+            "gpu_launches": int(launches * args.steps),
+            "roofline": None if g0 is None else {"kernel": g0["kernel"] + " (largest GEMM of the decoder half)", "bound": "tensor", "achieved": g0["achieved"],
+                                                 "peak": g0["peak"], "unit": "TFLOP/s", "frac": g0["frac"], "traffic": None,
+                                                 "peak_source": peaks["source"], "gemms": gemms},
+            "cpu_baseline": cpu}
+
+
 # ----------------------------------------------------------------------------------------------------
 def run_b200(args, world, rank, local):
     from unpaired_image_captioning_b200 import _lib, train_bench
@@ -401,7 +521,9 @@ def run_b200(args, world, rank, local):
     wl = args.workload
     line = None
 
-    if wl in ("cfg2", "cfg5"):
+    if wl == "cfg4":
+        line = _run_cfg4(args, world, rank, local, peaks, sampler, threads)
+    elif wl in ("cfg2", "cfg5"):
         d = _decode_legs(args, world, rank, local, wl, args.steps, with_roofline=True)
         opt, cfg = d["opt"], d["cfg"]
         B, beam = cfg["batch"], cfg["beam_size"]
@@ -531,7 +653,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "cfg5"])
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg3", "cfg4", "cfg5"])
     ap.add_argument("--strong", action="store_true", help="cfg3: global batch 512 split over the ranks (strong scaling)")
     ap.add_argument("--no-legs", action="store_true", help="cfg2: skip the train / cfg5 / eager-baseline legs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
