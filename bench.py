@@ -450,9 +450,12 @@ def _run_cfg4(args, world, rank, local, peaks, sampler, threads):
     tgt, _ = pivot.sentences(B, 8600, gen, bos=pivot.BOS, max_len=30)
     host = [t.pin_memory() for t in (src, n, tgt)]
     batch = [t.cuda() for t in host]
-    eager = pivot.PivotTrainStep(nmt, src.size(0), tgt.size(0), B, graph=False, batch=batch)
+    eager = pivot.PivotTrainStep(nmt, src.size(0), tgt.size(0), B, graph=False, batch=batch, amp=False)
     ms_eager = _timed(eager.step, max(3, args.steps // 4), 2, world)
-    graphed = pivot.PivotTrainStep(nmt, src.size(0), tgt.size(0), B, graph=True, batch=batch)
+    graphed32 = pivot.PivotTrainStep(nmt, src.size(0), tgt.size(0), B, graph=True, batch=batch, amp=False)
+    ms_graph32 = _timed(graphed32.step, max(3, args.steps // 4), 2, world)
+    del graphed32
+    graphed = pivot.PivotTrainStep(nmt, src.size(0), tgt.size(0), B, graph=True, batch=batch, amp=True)
     ms_dec = _timed(dec, args.steps, args.warmup, world)
     ms_nmt = _timed(graphed.step, args.steps, args.warmup, world)
 
@@ -491,9 +494,9 @@ def _run_cfg4(args, world, rank, local, peaks, sampler, threads):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_joint, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16 (decoder kernels) + fp32 (translator, PyTorch)", "data": "synthetic",
             "config": _workload_config("cfg4", cfg, opt, world, {
-                "decoder_ms": ms_dec, "translator_graph_ms": ms_nmt, "translator_eager_ms": ms_eager,
+                "decoder_ms": ms_dec, "translator_graph_bf16_ms": ms_nmt, "translator_graph_fp32_ms": ms_graph32, "translator_eager_fp32_ms": ms_eager,
                 "translator_share_of_joint_step": ms_nmt / (ms_nmt + ms_dec), "translator": "PyTorch restatement (pivot.py), whole step "
-                "in one CUDA graph; parity unpinned (reference translator not importable, SURVEY F2/F3)",
+                "in one CUDA graph, bf16 autocast; parity unpinned (reference translator not importable, SURVEY F2/F3)",
                 "sentence_length": "U{5..30}, padded to 30 / 32", "src_vocab": 12000, "tgt_vocab": 8600,
                 "translator_params_M": round(sum(p.numel() for p in nmt.parameters()) / 1e6, 1)}),
             "clocks": clocks,

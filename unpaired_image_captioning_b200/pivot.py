@@ -39,16 +39,16 @@ class MaskedBiLSTM(nn.Module):
     def _direction(self, x, valid, layer, reverse):
         sfx = f"_l{layer}" + ("_reverse" if reverse else "")
         w_ih, w_hh = getattr(self.rnn, "weight_ih" + sfx), getattr(self.rnn, "weight_hh" + sfx)
-        b = getattr(self.rnn, "bias_ih" + sfx) + getattr(self.rnn, "bias_hh" + sfx)
+        b_ih, b_hh = getattr(self.rnn, "bias_ih" + sfx), getattr(self.rnn, "bias_hh" + sfx)
         S, B, _ = x.shape
-        gx = F.linear(x, w_ih, b)                                         # time-batched input projection
         h = x.new_zeros(B, self.hidden_size)
         c = x.new_zeros(B, self.hidden_size)
         outs = [None] * S
         for t in (range(S - 1, -1, -1) if reverse else range(S)):
-            i, f, g, o = (gx[t] + F.linear(h, w_hh)).chunk(4, 1)
-            c_new = torch.sigmoid(f) * c + torch.sigmoid(i) * torch.tanh(g)
-            h_new = torch.sigmoid(o) * torch.tanh(c_new)
+            # torch's fused LSTM cell (two GEMMs + one pointwise kernel, forward and backward): the captured graph is bound
+            # by its NUMBER of kernels, not by their arithmetic (a first version with the gate math spelled out in elementwise
+            # ops replayed ~10 000 tiny kernels per step)
+            h_new, c_new = torch._VF.lstm_cell(x[t], (h, c), w_ih, w_hh, b_ih, b_hh)
             m = valid[t]
             h, c = torch.where(m, h_new, h), torch.where(m, c_new, c)    # rows past their end keep their state
             outs[t] = h * m
@@ -130,11 +130,11 @@ def sentences(batch, vocab, gen, lo=5, hi=30, bos=None, max_len=None):
 class PivotTrainStep:
     """One translator training step (forward + NLL / tokens + backward + gradient all-reduce + clip 5.0 + Adam) on static
     device buffers `src (S, B)`, `src_len (B,)`, `tgt (T, B)`; `graph=True` captures it into one CUDA graph (call
-    `load(src, src_len, tgt)` to refresh the buffers, then `step()`)."""
+    `load(src, src_len, tgt)` to refresh the buffers, then `step()`); `amp=True` runs the matmuls in bf16 autocast."""
 
-    def __init__(self, model, S, T, B, lr=1e-3, clip=5.0, graph=True, device="cuda", batch=None):
+    def __init__(self, model, S, T, B, lr=1e-3, clip=5.0, graph=True, device="cuda", batch=None, amp=True):
         import torch.distributed as dist
-        self.model, self.clip = model, clip
+        self.model, self.clip, self.amp = model, clip, amp
         self.src = torch.zeros(S, B, dtype=torch.int64, device=device)
         self.src_len = torch.ones(B, dtype=torch.int64, device=device)
         self.tgt = torch.zeros(T, B, dtype=torch.int64, device=device)
@@ -169,7 +169,11 @@ class PivotTrainStep:
     def _eager(self):
         import torch.distributed as dist
         self.flat.zero_()
-        nll, n = self.model(self.src, self.src_len, self.tgt)
+        # amp: bf16 operands on the tensor cores with fp32 accumulation (the precision of the decoder's own GEMMs); in fp32 the
+        # step is bound by SIMT matmuls (24 M parameters, ~600 GFLOP per 256-sentence step)
+        with torch.autocast("cuda", dtype=torch.bfloat16, enabled=self.amp):
+            nll, n = self.model(self.src, self.src_len, self.tgt)
+        nll = nll.float()
         if self.world > 1:      # normalise by the token count of the global batch
             n = n.float()
             dist.all_reduce(n)
