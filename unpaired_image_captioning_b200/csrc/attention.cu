@@ -96,9 +96,9 @@ __device__ __forceinline__ long long att_now() {
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
   return t;
 }
-#define ATT_TRACE(slot)                                                                                  \
-  do {                                                                                                  \
-    if (p.trace != nullptr && blockIdx.x == 0 && warp == 0 && lane == 0 && (slot) < 128) p.trace[slot] = att_now(); \
+#define ATT_TRACE(slot)                                       \
+  do {                                                       \
+    if (tracing && (slot) < 128) p.trace[slot] = att_now();  \
   } while (0)
 __device__ __forceinline__ void ldmatrix_x4_trans(uint32_t addr, uint32_t (&r)[4]) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
@@ -163,6 +163,9 @@ att_step_fwd_kernel(const __grid_constant__ CUtensorMap tmap_att, AttParams p) {
   pdl_launch_dependents();
   const int L = p.L, A = p.A, H = p.H;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // (one predicate for the debug timeline: evaluated per use it cost an S2R of blockIdx and three compares at six places of
+  //  the per-batch loop)
+  const bool tracing = p.trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
   // CTA c owns the work items [c * items / ctas, (c + 1) * items / ctas): a contiguous run of batches
   const int item0 = static_cast<int>(static_cast<long long>(blockIdx.x) * p.items / gridDim.x);
   const int item1 = static_cast<int>(static_cast<long long>(blockIdx.x + 1) * p.items / gridDim.x);
@@ -187,6 +190,17 @@ att_step_fwd_kernel(const __grid_constant__ CUtensorMap tmap_att, AttParams p) {
     fence_barrier_init();
     tma_prefetch_desc(&tmap_att);
   }
+  // alpha_net weights of this lane's units: a parameter, not written by the stream predecessor, so its loads (an L2 round
+  // trip every CTA used to pay after the wait below) overlap the previous kernel's tail
+  float w[CA * 8];
+#pragma unroll
+  for (int c = 0; c < CA; ++c)
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int u0 = c * 256 + h * 128 + lane * 4;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) w[c * 8 + h * 4 + k] = (u0 + k < A) ? -2.0f * __ldg(p.w_alpha + u0 + k) : 0.0f;
+    }
   __syncthreads();  // the only block-wide barrier
   pdl_wait();       // (programmatic dependent launch: the set-up above overlapped the previous kernel's tail)
   ATT_TRACE(0);
@@ -255,15 +269,6 @@ att_step_fwd_kernel(const __grid_constant__ CUtensorMap tmap_att, AttParams p) {
   // GEMM epilogues; the constant sum(w) drops out of the softmax, so the score is e = sum_a (-2 w_a) / (E_a F_a + 1).
   // One reciprocal serves a PAIR of units: w1/d1 + w2/d2 = (w1 d2 + w2 d1) / (d1 d2).  d <= 2^120 + 1 and the numerator
   // stay finite; when d1 d2 overflows the reciprocal is 0 and so is the term -- its limit (both tanh saturated at 1).
-  float w[CA * 8];
-#pragma unroll
-  for (int c = 0; c < CA; ++c)
-#pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int u0 = c * 256 + h * 128 + lane * 4;
-#pragma unroll
-      for (int k = 0; k < 4; ++k) w[c * 8 + h * 4 + k] = (u0 + k < A) ? -2.0f * __ldg(p.w_alpha + u0 + k) : 0.0f;
-    }
   const int g = lane >> 2, t = lane & 3;
   const int n_mtiles = (H + 15) >> 4;
   // Tile warp + 8 q is the (warp & 3)-th 16-column group of box 2 q + warp / 4.  ldmatrix address of this lane:
