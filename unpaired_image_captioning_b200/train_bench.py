@@ -27,7 +27,8 @@ def make_state(local, rank, world, strong=False, cfg_name=CFG, rows=None):
     else:
         fc, att = synth.make_features(rows, cfg["att_size"], opt.att_feat_size, seed=4321 + rank)
         labels, masks = synth.make_captions(rows, opt.seq_length, opt.vocab_size, seed=4321 + rank)
-    step = dp.DataParallelStep(model, clip=5.0)
+    import os
+    step = dp.DataParallelStep(model, clip=5.0, overlap=os.environ.get("UIC_DP_OVERLAP", "1") != "0")   # (0: A/B experiments)
     optim = torch.optim.Adam(model.parameters(), lr=4e-4, betas=(0.9, 0.999), eps=1e-8, fused=True, capturable=True)
     host = dict(fc=fc.pin_memory(), att=att.pin_memory(), labels=labels.pin_memory(), masks=masks.pin_memory())
     return dict(model=model, opt=opt, cfg=cfg, rows=fc.size(0), fc=fc.cuda(), att=att.cuda(), labels=labels.cuda(), masks=masks.cuda(),
@@ -118,7 +119,7 @@ def train_leg(args, world, rank, local, strong=False, e2e=False, profile=False):
                       "seq_length": opt.seq_length},
            "scaling": "strong" if strong else "weak", "launch_mode": mode, "launches_per_step": launches,
            "exchange": {"buckets_mb": [round((hi - lo) * 4 / 2 ** 20, 1) for lo, hi in st["bucket"].bounds],
-                        "order": "logit | core + fc_embed | embed | features + normaliser", "overlapped": True,
+                        "order": "logit | core + fc_embed | embed | features + normaliser", "overlapped": st["step"].overlap,
                         "grad_parity_rel_err_vs_single_gpu": parity},
            "loss_rank0_share": float(step())}
     if e2e:   # the same step fed from pinned host memory: H2D of the batch and D2H of the loss inside the timing
