@@ -15,7 +15,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(PKG_DIR, "csrc")
 OBJ_DIR = os.path.join(PKG_DIR, "build")
 LIB_PATH = os.path.join(PKG_DIR, "libuic_b200.so")
-SOURCES = ["api.cu", "gemm_tcgen05.cu", "attention.cu", "pointwise.cu", "vocab.cu", "beam.cu", "backward.cu"]
+SOURCES = ["api.cu", "gemm_tcgen05.cu", "attention.cu", "attention_v7.cu", "pointwise.cu", "vocab.cu", "beam.cu", "backward.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-Xptxas", "-v"]
 
