@@ -21,12 +21,15 @@ constexpr int V7_E_SLOTS = 4;  // score buffers: the warps of a CTA drift up to 
 __device__ __forceinline__ void mbar_wait_lean(uint32_t bar, uint32_t parity) {
   if (mbar_try_wait_addr(bar, parity)) return;
   int n = 0;
-  while (!mbar_try_wait_addr_hint(bar, parity, 1000)) {
-    if (++n > (1 << 22)) {  // a protocol bug becomes a launch failure instead of a hung GPU
+  // (a failed try_wait comes back within a few tens of cycles whatever its suspend hint says: without the explicit sleep the
+  //  warps that run ahead of their CTA issued 18 % of all instructions of the kernel polling the scored barrier)
+  do {
+    __nanosleep(96);
+    if (++n > (1 << 23)) {  // a protocol bug becomes a launch failure instead of a hung GPU
       printf("uic: att_step_fwd_v7 mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
       __trap();
     }
-  }
+  } while (!mbar_try_wait_addr(bar, parity));
 }
 __device__ __forceinline__ int ld_acquire_gpu(const int* p) {
   int v;
