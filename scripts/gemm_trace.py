@@ -55,3 +55,9 @@ for M, N, K in SHAPES:
     print(f"    setup done @{rel(0)}  tma issue kb0..: {[rel(50 + i) for i in range(min(nkb, 8))]}")
     print(f"    operands landed kb0..: {[rel(1 + i) for i in range(min(nkb, 32))]}")
     print(f"    last mma issued @{rel(40)}  acc ready @{rel(41)}  epilogue done @{rel(42)}  (persistent: first tile of CTA 0)")
+    print(f"    epilogue warp 4: chunk 0 tmem loaded @{rel(43)} staged @{rel(44)} stored @{rel(45)}; chunk 1 @{rel(46)} @{rel(47)} @{rel(48)}")
+    ent = [t[128 + 2 * c] for c in range(148) if t[128 + 2 * c]]
+    ext = [t[129 + 2 * c] for c in range(148) if t[129 + 2 * c]]
+    if ent and ext:
+        print(f"    CTA lifetimes (globaltimer ns): first entry -> last exit {max(ext) - min(ent)}; entry spread {max(ent) - min(ent)}; "
+              f"median lifetime {sorted(x - e_ for x, e_ in zip(ext, ent))[len(ent) // 2]}")

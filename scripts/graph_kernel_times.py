@@ -38,7 +38,7 @@ def time_graph(fn):
 evict = torch.empty(200 << 20, dtype=torch.uint8, device="cuda")
 t_evict = time_graph(lambda: evict.zero_())
 print(f"evict (zero 200 MB): {t_evict:.1f} us")
-for M, N, K in [(768, 3072, 1024), (768, 1024, 512), (768, 10000, 512), (256, 2560, 1024)]:
+for M, N, K in [(768, 3072, 512), (768, 3072, 1024), (768, 1024, 512), (768, 10000, 512), (256, 2560, 1024)]:
     a = torch.randn(M, K, device="cuda").to(torch.bfloat16)
     b = (torch.randn(N, K, device="cuda") * 0.05).to(torch.bfloat16)
     bias = torch.randn(N, device="cuda")
@@ -52,7 +52,14 @@ for M, N, K in [(768, 3072, 1024), (768, 1024, 512), (768, 10000, 512), (256, 25
     t_cold = time_graph(both) - t_evict
     ref = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
     t_cublas = time_graph(lambda: torch.matmul(a, b.t(), out=ref))
-    print(f"gemm {M}x{N}x{K}: in-graph warm {t_warm:.1f} us, after eviction {t_cold:.1f} us, cuBLAS(bf16 out, warm) {t_cublas:.1f} us")
+    # like for like: the library GEMM above writes bf16 (2 bytes per output) and no bias; the decode loop's GEMMs write
+    # fp32 gate sums.  Same output format for ours, and cuBLAS with the bias (addmm):
+    out16 = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    t_warm16 = time_graph(lambda: _lib.gemm(a, b, bias, out_bf16=out16))
+    bias16 = bias.to(torch.bfloat16)
+    t_cublas_bias = time_graph(lambda: torch.addmm(bias16, a, b.t(), out=ref))
+    print(f"gemm {M}x{N}x{K}: in-graph warm {t_warm:.1f} us (fp32 out), {t_warm16:.1f} us (bf16 out), after eviction {t_cold:.1f} us; "
+          f"cuBLAS warm, bf16 out {t_cublas:.1f} us, with bias {t_cublas_bias:.1f} us")
 # the fused-statistics variant of the logit GEMM (what the decode loops launch)
 M, N, K = 768, 10000, 512
 a = torch.randn(M, K, device="cuda").to(torch.bfloat16)

@@ -428,6 +428,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         const float4 b4 = bias4[cc];
         const int cq = col0 + 4 * q;
         tmem_ld_wait();
+        if (threadIdx.x == 128 && cc < 2) UIC_TRACE(43 + 3 * cc);
         if (col0 >= N || row_base >= M) continue;  // warp-uniform
         if (ep.debug & 4) continue;
         // lane = row: stage the 32 accumulators of this row (explicit shared-space stores: the staging
@@ -438,14 +439,62 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
                        "r"(v[j + 2]), "r"(v[j + 3])
                        : "memory");
         __syncwarp();
+        if (threadIdx.x == 128 && cc < 2) UIC_TRACE(44 + 3 * cc);
         // The activation mode is uniform per 32-column chunk: decide it ONCE and run a specialised store
         // loop (the first version evaluated the epilogue flags per element: ~40 instructions per value,
         // which made the epilogue 3x longer than the k-loop).
         const bool chunk_vec = (col0 + 32 <= N);
         const bool exp_all = ep.exp_scale != 0.0f && col0 >= ep.exp_col0;
         const bool exp_mixed = ep.exp_scale != 0.0f && !exp_all && col0 + 32 > ep.exp_col0;
+        // Vector path: the eight 16-byte row pieces of this lane are loaded from the staging tile first, then stored through
+        // ONE base pointer per output advanced by a constant pitch; output set, activation and accumulate are template
+        // constants.  (The first version evaluated the epilogue flags per element; the second re-derived the 64-bit row
+        // address, re-read the epilogue struct from the constant bank and branched on the output pointers in every one of
+        // the eight row iterations -- ~70 dependent instructions each: the pipeline trace showed 3 600 cycles per 32 x 32
+        // chunk, i.e. an epilogue longer than the k-loop of the 768-row GEMMs whatever the output width.)
+        const int rows_valid = M - row_base;  // > 0 (checked above)
+        const bool has32 = ep.c_f32 != nullptr, has16 = ep.c_bf16 != nullptr, accum = has32 && ep.accumulate != 0;
+        auto store_fast = [&](auto mode_c) {
+          constexpr int MODE = decltype(mode_c)::value;  // 0 plain, 1 relu, 2 exp on the whole chunk
+          float* d32 = ep.c_f32 + static_cast<long long>(row_base + rsub) * ep.ldc + cq;             // (only dereferenced if has32)
+          __nv_bfloat16* d16 = ep.c_bf16 + static_cast<long long>(row_base + rsub) * ep.ldcb + cq;  // (only if has16)
+          const long long p32 = 4 * ep.ldc, p16 = 4 * ep.ldcb;
+          const int f16 = ep.out_f16;
+          const float cap = f16 ? 65504.0f : EXP_CAP, es = ep.exp_scale;
+#pragma unroll
+          for (int half = 0; half < 2; ++half) {  // two groups of four rows: 16 + 16 live registers instead of 64
+            float4 f[4], o[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int r4 = half * 4 + i;
+              asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];"
+                           : "=f"(f[i].x), "=f"(f[i].y), "=f"(f[i].z), "=f"(f[i].w)
+                           : "r"(stage_s + ((r4 * 4 + rsub) * EPI_PITCH + 4 * q) * 4));
+              o[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+              if (accum && r4 * 4 + rsub < rows_valid) o[i] = *reinterpret_cast<const float4*>(d32 + r4 * p32);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int r4 = half * 4 + i;
+              float4 v4 = f[i];
+              v4.x += b4.x + o[i].x; v4.y += b4.y + o[i].y; v4.z += b4.z + o[i].z; v4.w += b4.w + o[i].w;
+              if constexpr (MODE == 1) { v4.x = fmaxf(v4.x, 0.0f); v4.y = fmaxf(v4.y, 0.0f); v4.z = fmaxf(v4.z, 0.0f); v4.w = fmaxf(v4.w, 0.0f); }
+              if constexpr (MODE == 2) {
+                v4.x = fminf(es * __expf(2.0f * v4.x), cap); v4.y = fminf(es * __expf(2.0f * v4.y), cap);
+                v4.z = fminf(es * __expf(2.0f * v4.z), cap); v4.w = fminf(es * __expf(2.0f * v4.w), cap);
+              }
+              if (r4 * 4 + rsub < rows_valid) {
+                if (has32) *reinterpret_cast<float4*>(d32 + r4 * p32) = v4;
+                if (has16) *reinterpret_cast<uint2*>(d16 + r4 * p16) = make_uint2(pack16(v4.x, v4.y, f16), pack16(v4.z, v4.w, f16));
+              }
+            }
+          }
+        };
         auto store_rows = [&](auto mode_c) {
           constexpr int MODE = decltype(mode_c)::value;  // 0 plain, 1 relu, 2 exp on the whole chunk, 3 generic
+          if constexpr (MODE != 3) {
+            store_fast(mode_c);
+          } else {
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const int r = i * 4 + rsub;
@@ -454,32 +503,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
             asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(f.x), "=f"(f.y), "=f"(f.z), "=f"(f.w) : "r"(stage_s + (r * EPI_PITCH + 4 * q) * 4));
             if (row >= M) continue;
             f.x += b4.x; f.y += b4.y; f.z += b4.z; f.w += b4.w;
-            if (MODE != 3) {
-              if (ep.c_f32 != nullptr) {
-                float4* dst = reinterpret_cast<float4*>(ep.c_f32 + static_cast<long long>(row) * ep.ldc + cq);
-                if (ep.accumulate) {
-                  const float4 o = *dst;
-                  f.x += o.x; f.y += o.y; f.z += o.z; f.w += o.w;
-                }
-                if (MODE == 1) { f.x = fmaxf(f.x, 0.0f); f.y = fmaxf(f.y, 0.0f); f.z = fmaxf(f.z, 0.0f); f.w = fmaxf(f.w, 0.0f); }
-                if (MODE == 2) {
-                  const float cap = ep.out_f16 ? 65504.0f : EXP_CAP;
-                  f.x = fminf(ep.exp_scale * __expf(2.0f * f.x), cap); f.y = fminf(ep.exp_scale * __expf(2.0f * f.y), cap);
-                  f.z = fminf(ep.exp_scale * __expf(2.0f * f.z), cap); f.w = fminf(ep.exp_scale * __expf(2.0f * f.w), cap);
-                }
-                *dst = f;
-              } else {
-                if (MODE == 1) { f.x = fmaxf(f.x, 0.0f); f.y = fmaxf(f.y, 0.0f); f.z = fmaxf(f.z, 0.0f); f.w = fmaxf(f.w, 0.0f); }
-                if (MODE == 2) {
-                  const float cap = ep.out_f16 ? 65504.0f : EXP_CAP;
-                  f.x = fminf(ep.exp_scale * __expf(2.0f * f.x), cap); f.y = fminf(ep.exp_scale * __expf(2.0f * f.y), cap);
-                  f.z = fminf(ep.exp_scale * __expf(2.0f * f.z), cap); f.w = fminf(ep.exp_scale * __expf(2.0f * f.w), cap);
-                }
-              }
-              if (ep.c_bf16 != nullptr)
-                *reinterpret_cast<uint2*>(ep.c_bf16 + static_cast<long long>(row) * ep.ldcb + cq) =
-                    make_uint2(pack16(f.x, f.y, ep.out_f16), pack16(f.z, f.w, ep.out_f16));
-            } else {  // tails, unaligned outputs, chunk straddling exp_col0: element-wise with all the flags
+            {  // tails, unaligned outputs, chunk straddling exp_col0: element-wise with all the flags
               float e4[4] = {f.x, f.y, f.z, f.w};
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
@@ -496,6 +520,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
               }
             }
           }
+          }
         };
         const bool fast = chunk_vec && !exp_mixed && (ep.c_f32 == nullptr || vec_f32) && (ep.c_bf16 == nullptr || vec_16) && !(ep.debug & 1) &&
                           ep.post_scale == nullptr;
@@ -509,6 +534,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         } else {
           store_rows(std::integral_constant<int, 0>{});
         }
+        if (threadIdx.x == 128 && cc < 2) UIC_TRACE(45 + 3 * cc);
       }
       }  // STATS == 0
       // all four epilogue warps have read this accumulator: hand it back to the MMA issuer
