@@ -153,3 +153,33 @@ def test_att_step_fwd_launch_plans(n_img, beams, L):
         ref_ctx, ref_alpha = _att_reference(att_h[r0 * beams:r1 * beams], p_eff[r0:r1], att[r0:r1], w, None, beams)
         torch.testing.assert_close(alpha[r0 * beams:r1 * beams], ref_alpha, rtol=5e-3, atol=2e-5)
         torch.testing.assert_close(ctx_f[r0 * beams:r1 * beams], ref_ctx, rtol=5e-3, atol=5e-4)
+
+
+@pytest.mark.parametrize("n_img,beams,L,H", [(150, 5, 52, 1024), (150, 4, 36, 1024), (500, 5, 196, 1024), (80, 5, 100, 768), (150, 7, 36, 1024),
+                                             (60, 5, 36, 1024)])
+def test_att_step_fwd_wide_beam_groups(n_img, beams, L, H):
+    """configs[4] shapes (rnn 1024, beam 5): four or five beams of an image share ONE pass over its tiles in the v7 kernel
+    (att_v7_beam_cap); 7 beams -> groups of 4 + 3; 60 images -> below the v7 threshold, v6 with groups of <= 3."""
+    A = 512
+    R = n_img * beams
+    p_att = _rand_bf16(n_img, L, A, seed=31)
+    att = _rand_bf16(n_img, L, H, seed=32).abs()
+    att_h = torch.randn(R, A, device=DEV)
+    w = torch.randn(A, device=DEV) * 0.2
+    ctx_f = torch.empty(R, H, device=DEV)
+    ctx_b = torch.empty(R, H, device=DEV, dtype=torch.bfloat16)
+    alpha = torch.empty(R, L, device=DEV)
+    e_tile = _lib.exp_tile(p_att)
+    f = (torch.exp(2.0 * att_h) * _lib.ATT_F_SCALE).contiguous()
+    for _ in range(2):
+        ctx_f.zero_()
+        _lib.att_step(f, A, e_tile, att, w, None, None, 0, ctx_f, H, alpha, n_img, beams, L, A, H)
+        _lib.att_step(f, A, e_tile, att, w, None, ctx_b, H, None, 0, None, n_img, beams, L, A, H)
+    p_eff = _lib.tile_value(e_tile)
+    for r0 in range(0, n_img, 32):
+        r1 = min(n_img, r0 + 32)
+        ref_ctx, ref_alpha = _att_reference(att_h[r0 * beams:r1 * beams], p_eff[r0:r1], att[r0:r1], w, None, beams)
+        torch.testing.assert_close(alpha[r0 * beams:r1 * beams], ref_alpha, rtol=5e-3, atol=2e-5)
+        torch.testing.assert_close(ctx_f[r0 * beams:r1 * beams], ref_ctx, rtol=5e-3, atol=5e-4)
+        torch.testing.assert_close(ctx_b[r0 * beams:r1 * beams].float(), ref_ctx, rtol=2e-2, atol=5e-3)
+

@@ -520,15 +520,17 @@ static unsigned long long att_tile_policy(long long tile_bytes) {
   return tile_bytes > (56LL << 20) ? L2_EVICT_FIRST : L2_EVICT_NORMAL;
 }
 
-static int beams_per_group(int beams) {
-  if (beams <= 3) return beams;
-  const int groups = (beams + 2) / 3;
+static int beams_per_group(int beams, int cap) {
+  if (beams <= cap) return beams;
+  const int groups = (beams + cap - 1) / cap;
   return (beams + groups - 1) / groups;
 }
 
 static AttPlan make_plan(int n_img, int beams, int L, int A, int H) {
   AttPlan pl;
-  pl.nb = beams_per_group(beams);
+  // Beams of an image that share one pass over its tiles: up to 3 in general (registers of the 2-CTA-per-SM kernels, the
+  // v6 instantiations), up to 5 where the v7 kernel runs one CTA per SM anyway (att_v7_beam_cap)
+  pl.nb = beams_per_group(beams, att_v7_beam_cap(n_img, beams, L, A, H));
   pl.groups = (beams + pl.nb - 1) / pl.nb;
   pl.nbpi = (L + ATT_BATCH - 1) / ATT_BATCH;
   const long long jobs = static_cast<long long>(n_img) * pl.groups;
@@ -645,6 +647,7 @@ int att_step_fwd(const float* att_h, long long ld_att_h, const void* p_att, cons
     const int rc7 = att_step_fwd_v7(p, pl, n_img, v7_ctas, stream);
     if (rc7 <= 0) return rc7;  // 1: not launched, fall through
   }
+  if (pl.nb > 3) return set_error(UIC_ERR_SHAPE, "att_step_fwd: %d beams per pass are planned for the v7 kernel, which did not launch", pl.nb);
   const int ca = (A + 255) / 256;
   if (H <= 512) {
     if (ca <= 1) return dispatch_nb<1, 4>(p, pl, n_img, stream);

@@ -545,8 +545,14 @@ static int dispatch_v7(AttParams& p, const AttPlan& pl, int n_img, int ctas, cud
   switch (pl.nb) {
     case 1: return aux ? launch_v7<1, CA, MT, true>(p, pl, n_img, ctas, stream, q, per_sm) : launch_v7<1, CA, MT, false>(p, pl, n_img, ctas, stream, q, per_sm);
     case 2: return aux ? launch_v7<2, CA, MT, true>(p, pl, n_img, ctas, stream, q, per_sm) : launch_v7<2, CA, MT, false>(p, pl, n_img, ctas, stream, q, per_sm);
-    default: return aux ? launch_v7<3, CA, MT, true>(p, pl, n_img, ctas, stream, q, per_sm) : launch_v7<3, CA, MT, false>(p, pl, n_img, ctas, stream, q, per_sm);
+    case 3: return aux ? launch_v7<3, CA, MT, true>(p, pl, n_img, ctas, stream, q, per_sm) : launch_v7<3, CA, MT, false>(p, pl, n_img, ctas, stream, q, per_sm);
+    default: break;
   }
+  if constexpr (CA == 2 && MT == 8) {  // the one-CTA-per-SM shape with room for 4 or 5 beams per pass (att_v7_beam_cap)
+    if (pl.nb == 4) return aux ? launch_v7<4, CA, MT, true>(p, pl, n_img, ctas, stream, q, per_sm) : launch_v7<4, CA, MT, false>(p, pl, n_img, ctas, stream, q, per_sm);
+    if (pl.nb == 5) return aux ? launch_v7<5, CA, MT, true>(p, pl, n_img, ctas, stream, q, per_sm) : launch_v7<5, CA, MT, false>(p, pl, n_img, ctas, stream, q, per_sm);
+  }
+  return 1;
 }
 
 static int dispatch_shape_v7(AttParams& p, const AttPlan& pl, int n_img, int ctas, cudaStream_t stream, bool q, int* per_sm) {
@@ -562,16 +568,35 @@ static int dispatch_shape_v7(AttParams& p, const AttPlan& pl, int n_img, int cta
 
 static bool v7_shape_ok(int A, int H) { return A % 256 == 0 && (A == 256 || A == 512 || A == 1024) && H % 64 == 0 && H >= 64 && H <= 1024; }
 
-// Grid of the v7 kernel for this problem, 0 when v6 should run it: v7 covers the shapes it is instantiated for and
-// the regime where jobs are plentiful (>= half of the CTA slots); below that v6 cuts every job into equal segments,
-// whose partials are merged in parallel rather than by one owner.
-int att_v7_ctas(int n_img, int beams, int L, int A, int H, const AttPlan& pl) {
+static bool v7_enabled() {
   static int mode = -1;  // UIC_ATT_V7=0 keeps v6 everywhere
   if (mode < 0) {
     const char* e = getenv("UIC_ATT_V7");
     mode = e ? atoi(e) : 1;
   }
-  if (!mode || !v7_shape_ok(A, H)) return 0;
+  return mode != 0;
+}
+
+// With more than three beams per image the 3-beam kernels read the image's tiles once per GROUP of beams.  The shape
+// A = 512, 512 < H <= 1024 (configs[4]: rnn 1024, beam 5) runs one CTA per SM whatever the beam count, and its registers
+// and shared memory hold five beams: one pass instead of two there (UIC_ATT_NB5=0 turns it off).
+int att_v7_beam_cap(int n_img, int beams, int L, int A, int H) {
+  (void)L;
+  static int on = -1;
+  if (on < 0) {
+    const char* e = getenv("UIC_ATT_NB5");
+    on = e ? atoi(e) : 1;
+  }
+  if (!on || !v7_enabled() || beams <= 3 || A != 512 || H <= 512 || H > 1024 || H % 64) return 3;
+  if (static_cast<long long>(n_img) * 2 < 148) return 3;  // below that v6's segmented plan runs (att_v7_ctas)
+  return 5;
+}
+
+// Grid of the v7 kernel for this problem, 0 when v6 should run it: v7 covers the shapes it is instantiated for and
+// the regime where jobs are plentiful (>= half of the CTA slots); below that v6 cuts every job into equal segments,
+// whose partials are merged in parallel rather than by one owner.
+int att_v7_ctas(int n_img, int beams, int L, int A, int H, const AttPlan& pl) {
+  if (!v7_enabled() || !v7_shape_ok(A, H)) return 0;
   const long long jobs = static_cast<long long>(n_img) * pl.groups;
   const int per_sm_nominal = (A / 256 <= 2 && H <= 512) ? 2 : 1;
   if (jobs * 2 < 148LL * per_sm_nominal) return 0;

@@ -51,6 +51,8 @@ struct AttPlan {
 int att_step_fwd_v7(AttParams& p, const AttPlan& pl, int n_img, int ctas, cudaStream_t stream);
 int att_v7_ctas(int n_img, int beams, int L, int A, int H, const AttPlan& pl);  // 0: shape not covered by v7
 long long att_v7_workspace_bytes(int ctas, int mt);
+// Largest number of beams of an image the v7 kernel scores in one pass for this problem (3: the general limit).
+int att_v7_beam_cap(int n_img, int beams, int L, int A, int H);
 
 __device__ __forceinline__ void bulk_g2s_hint(uint32_t smem_dst, const void* gsrc, uint32_t bytes, uint32_t bar, uint64_t policy) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(smem_dst),
