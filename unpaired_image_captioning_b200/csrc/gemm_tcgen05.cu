@@ -315,6 +315,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
         float run_m = -INFINITY, run_s = 0.0f;
         // Two candidate lists (even / odd columns) so that consecutive insertions are independent instruction chains;
         // ids are column offsets inside this warp's half tile (compile-time constants in the unrolled loops).
+        // (From kslots = 3 on the kernel is bound by these insertions -- scripts/stats_times.py: configs[4] 124 us with
+        // kslots 1, 223 us with kslots 5.  FOUR lists were measured too: slower, 245 us -- the two extra list merges cost
+        // more than the added instruction-level parallelism returns, i.e. the epilogue is issue-bound, not latency-bound.)
         float va[STATS], vb[STATS];
         int ia[STATS], ib[STATS];
 #pragma unroll
