@@ -1,10 +1,11 @@
 """misc/criterion.py:138-159 -- LanguageModelCriterion (masked cross-entropy over log-probs), and
 misc/criterion.py:104-124 -- RewardCriterion (the self-critical policy-gradient loss).
 
-Drop-in signature `LanguageModelCriterion(opt)(input, target, mask)`.  The gather/mask/sum runs on
-whatever device `input` lives on with the library's row kernels when it is a CUDA tensor that does
-not require grad; the differentiable path goes through `unpaired_image_captioning_b200.autograd`
-(the fused loss never materialises (B, T, V)).
+Drop-in signature `LanguageModelCriterion(opt)(input, target, mask)`.  On the (B, T, V) log-prob tensor the unmodified call
+pattern `crit(model(...), labels[:, 1:], masks[:, 1:])` produces, the three-line gather / mask / sum below is plain torch
+(it is the reference's formula on a tensor that already exists; its backward is the hand-written BPTT of
+`autograd._DecoderLogprobsFn`).  The path that never materialises (B, T, V) is `mode='forward_loss'`: the model returns a
+handle whose `_uic_fused(target, mask)` runs the library's fused logit-stage / LSE / NLL kernels.
 """
 from __future__ import annotations
 
