@@ -56,6 +56,7 @@ for M, N, K in SHAPES:
     print(f"    operands landed kb0..: {[rel(1 + i) for i in range(min(nkb, 32))]}")
     print(f"    last mma issued @{rel(40)}  acc ready @{rel(41)}  epilogue done @{rel(42)}  (persistent: first tile of CTA 0)")
     print(f"    epilogue warp 4: chunk 0 tmem loaded @{rel(43)} staged @{rel(44)} stored @{rel(45)}; chunk 1 @{rel(46)} @{rel(47)} @{rel(48)}")
+    print(f"    CTA 0: entry @{rel(120)}  set-up done (barriers, TMEM allocation) @{rel(121)}  dependency wait passed @{rel(122)}  first TMA issue @0")
     ent = [t[128 + 2 * c] for c in range(148) if t[128 + 2 * c]]
     ext = [t[129 + 2 * c] for c in range(148) if t[129 + 2 * c]]
     if ent and ext:

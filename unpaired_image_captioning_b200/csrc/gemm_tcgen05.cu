@@ -174,6 +174,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     long long tnow;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(tnow));
     ep.trace[128 + 2 * blockIdx.x] = tnow;
+    if (blockIdx.x == 0) ep.trace[120] = clock64();  // CTA 0 entry on the cycle counter the pipeline events use
   }
   const int num_kb = (K + BK - 1) / BK;
   const int tiles_m = (M + BM - 1) / BM;
@@ -203,7 +204,9 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  pdl_wait();  // everything above overlapped the previous kernel's tail; operands and outputs are touched below
+  if (ep.trace != nullptr && threadIdx.x == 0 && blockIdx.x == 0) ep.trace[121] = clock64();  // set-up done (barriers, TMEM)
+  pdl_wait();
+  if (ep.trace != nullptr && threadIdx.x == 0 && blockIdx.x == 0) ep.trace[122] = clock64();  // dependency wait passed  // everything above overlapped the previous kernel's tail; operands and outputs are touched below
 
   if (warp == 0) {
     // ===== TMA producer =====
