@@ -205,8 +205,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   if (ep.trace != nullptr && threadIdx.x == 0 && blockIdx.x == 0) ep.trace[121] = clock64();  // set-up done (barriers, TMEM)
-  pdl_wait();
-  if (ep.trace != nullptr && threadIdx.x == 0 && blockIdx.x == 0) ep.trace[122] = clock64();  // dependency wait passed  // everything above overlapped the previous kernel's tail; operands and outputs are touched below
+  // The dependency wait sits in front of each role's FIRST global-memory access instead of here: the roles' loop prologues
+  // (tile coordinates, descriptor constants, and above all the first fetch of their code -- the CTA timeline showed ~830
+  // cycles between a common wait and the first TMA issue, cold instruction cache of a 13 k-instruction kernel) then overlap
+  // the predecessor's tail.  The MMA issuer touches shared memory and TMEM only and does not wait at all.
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -218,6 +220,10 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
           const int s = g % STAGES;
           const uint32_t ph = (g / STAGES) & 1;
           mbar_wait(&empty_bar[s], ph ^ 1);
+          if (g == 0) {
+            pdl_wait();  // operands written by the predecessor are read from here on
+            if (ep.trace != nullptr && blockIdx.x == 0) ep.trace[122] = clock64();  // dependency wait passed
+          }
           if (kb < 32) UIC_TRACE(50 + kb);
           mbar_arrive_expect_tx(&full_bar[s], L::STAGE_BYTES);
           uint8_t* sa = smem + s * L::STAGE_BYTES;
@@ -298,6 +304,7 @@ gemm_bf16_tcgen05_kernel(const __grid_constant__ CUtensorMap tmap_a, const __gri
     const bool vec_f32 = ep.c_f32 != nullptr && (ep.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(ep.c_f32) & 15) == 0);
     const bool vec_16 = ep.c_bf16 != nullptr && (ep.ldcb % 4 == 0) && ((reinterpret_cast<uintptr_t>(ep.c_bf16) & 7) == 0);
     const bool vec_bias = ep.bias != nullptr && ((reinterpret_cast<uintptr_t>(ep.bias) & 15) == 0);
+    pdl_wait();  // bias / banned-token loads, accumulate reads and all output stores come after this
     for (int tile = blockIdx.x, it = 0; tile < num_tiles; tile += gridDim.x, ++it) {
       const int m0 = (ep.n_fastest ? tile / tiles_n : tile % tiles_m) * BM, n0 = (ep.n_fastest ? tile % tiles_n : tile / tiles_m) * BN;
       const int acc = it & 1;
