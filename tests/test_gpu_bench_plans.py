@@ -183,3 +183,31 @@ def test_att_step_fwd_wide_beam_groups(n_img, beams, L, H):
         torch.testing.assert_close(ctx_f[r0 * beams:r1 * beams], ref_ctx, rtol=5e-3, atol=5e-4)
         torch.testing.assert_close(ctx_b[r0 * beams:r1 * beams].float(), ref_ctx, rtol=2e-2, atol=5e-3)
 
+
+@pytest.mark.parametrize("n_img,beams,L,H", [(200, 2, 52, 512), (160, 3, 100, 512), (150, 5, 40, 1024), (300, 1, 36, 512)])
+def test_att_step_fwd_v7_with_region_masks(n_img, beams, L, H):
+    """The batch-balanced kernel with ragged region masks and the alpha output (its AUX instantiations): masked regions get
+    zero weight and the rest is renormalised (models/AttModel.py:552-555), also for jobs cut between two CTAs."""
+    A = 512
+    R = n_img * beams
+    g = torch.Generator().manual_seed(41)
+    lens = torch.randint(1, L + 1, (n_img,), generator=g)
+    lens[0], lens[-1] = L, 1
+    masks = (torch.arange(L)[None, :] < lens[:, None]).float().to(DEV)
+    p_att = _rand_bf16(n_img, L, A, seed=42)
+    att = _rand_bf16(n_img, L, H, seed=43).abs()
+    att_h = torch.randn(R, A, device=DEV)
+    w = torch.randn(A, device=DEV) * 0.2
+    ctx_f = torch.empty(R, H, device=DEV)
+    alpha = torch.empty(R, L, device=DEV)
+    e_tile = _lib.exp_tile(p_att)
+    f = (torch.exp(2.0 * att_h) * _lib.ATT_F_SCALE).contiguous()
+    for _ in range(2):
+        _lib.att_step(f, A, e_tile, att, w, masks, None, 0, ctx_f, H, alpha, n_img, beams, L, A, H)
+    p_eff = _lib.tile_value(e_tile)
+    for r0 in range(0, n_img, 50):
+        r1 = min(n_img, r0 + 50)
+        ref_ctx, ref_alpha = _att_reference(att_h[r0 * beams:r1 * beams], p_eff[r0:r1], att[r0:r1], w, masks[r0:r1], beams)
+        torch.testing.assert_close(alpha[r0 * beams:r1 * beams], ref_alpha, rtol=5e-3, atol=2e-5)
+        torch.testing.assert_close(ctx_f[r0 * beams:r1 * beams], ref_ctx, rtol=5e-3, atol=5e-4)
+
