@@ -11,3 +11,9 @@ for tool in memcheck racecheck; do
     python -m pytest tests/test_gpu_kernels.py -q -x -p no:cacheprovider -k "$sel" > gpurun_out/${tag}_sanitize_${tool}.txt 2>&1
   echo "$tool exit $?"; grep -E "ERROR SUMMARY|RACECHECK SUMMARY|passed|failed|error" gpurun_out/${tag}_sanitize_${tool}.txt | tail -5
 done
+# the batch-balanced attention kernel (attention_v7.cu: release / acquire flags between CTAs, shared-memory atomics): memcheck
+sel7='v7_with_region_masks and (200-2-52 or 150-5-40) or launch_plans and (148-3-196 or 300-3-100) or wide_beam_groups and 80-5-100'
+timeout 700 compute-sanitizer --tool memcheck --error-exitcode 1 --launch-timeout 120 \
+  python -m pytest tests/test_gpu_bench_plans.py -q -x -p no:cacheprovider -k "$sel7" > gpurun_out/${tag}_sanitize_memcheck_v7.txt 2>&1
+echo "memcheck v7 exit $?"; grep -E "ERROR SUMMARY|passed|failed|error" gpurun_out/${tag}_sanitize_memcheck_v7.txt | tail -5
+
