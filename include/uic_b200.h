@@ -111,18 +111,20 @@ int uic_zero_padded_rows(void* x_bf16, const float* att_masks, int n_img, int L,
  *   e[l]  = sum_a w_alpha[a] * tanh(p_att[i,l,a] + att_h[r,a])        (alpha_net bias cancels in softmax)
  *   alpha = softmax_l(e);  if att_masks: alpha = alpha*m / sum(alpha*m)
  *   ctx[r,:] = sum_l alpha[l] * att[i,l,:]
- * Operands are passed in the exponential form produced by uic_gemm_bf16_ex:
- *   att_h  -> F[r,a]   = 16 * exp(2 * (h2att(h)[r,a] + bias))   fp32, pitch ld_att_h
- *   p_att  -> E[i,l,a] = exp(2 * p_att[i,l,a]) / 16             FP16 (n_img, L, A)
+ * Operands are passed in the exponential form produced by uic_gemm_bf16_ex (exp epilogue, scale 1, capped at 2^60):
+ *   att_h  -> F[r,a]   = exp(2 * (h2att(h)[r,a] + bias))   fp32, pitch ld_att_h
+ *   p_att  -> E[i,l,a] = exp(2 * p_att[i,l,a])             bf16 (n_img, L, A)   (the parameter keeps its round-1 name)
  * so that tanh(p_att + att_h) = 1 - 2 / (E F + 1).  att is bf16 (n_img,L,H).  Both tiles are read
- * once per image and shared by the image's beams.
+ * once per image and shared by the image's beams (up to 3 per pass; up to 5 where A = 512 < H <= 1024).
  * Outputs (each optional): ctx_bf16, ctx_f32, alpha (rows x L fp32, saved for backward).
  * att_h must be 16-byte aligned with a pitch that is a multiple of 4 floats (its rows are staged by bulk copies);
  * the context weights are rounded to bf16 for the tensor-core product (fp32 accumulation, fp32 normalisation).
- * `workspace`: uic_att_step_workspace_bytes(...) bytes, 16-byte aligned, zeroed ONCE by the caller
- * (the kernel leaves its arrival counters at zero); it holds the partial results when the regions
- * of an image are split over several CTAs (small batches only: with at least 148 (image, beam group)
- * jobs a CTA owns whole images and the workspace is only the counters). */
+ * `workspace`: uic_att_step_workspace_bytes(...) bytes, 16-byte aligned, zeroed ONCE by the caller (the kernels leave
+ * their arrival counters / publication flags at zero).  Two launch plans share it: with at least half as many
+ * (image, beam group) jobs as CTA slots the flat list of 16-region batches is cut into equal contiguous ranges, one per
+ * CTA, and a job cut by a range boundary is finished by the CTA that owns its first batch from the partial records the
+ * later CTAs publish there (all CTAs of the grid are co-resident; a wait that cannot be satisfied traps after ~1 s
+ * instead of hanging); smaller batches cut every job into equal segments merged by the last CTA to arrive. */
 int uic_att_step_fwd(const float* att_h, int64_t ld_att_h, const void* p_att_f16, const void* att_bf16,
                      const float* w_alpha, const float* att_masks, void* ctx_bf16, int64_t ld_ctx_bf16, float* ctx_f32,
                      int64_t ld_ctx_f32, float* alpha, void* workspace, int64_t workspace_bytes, int n_img, int beams, int L,
