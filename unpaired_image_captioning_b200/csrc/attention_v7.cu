@@ -16,6 +16,13 @@
 
 namespace uic {
 
+#ifndef V7_SLOTS_N
+#define V7_SLOTS_N 3
+#endif
+#ifndef V7_MIN_CTAS
+#define V7_MIN_CTAS 2
+#endif
+constexpr int V7_SLOTS = V7_SLOTS_N;  // depth of the p_att-row ring and of the att-box ring
 constexpr int V7_E_SLOTS = 4;  // score buffers: the warps of a CTA drift up to two batches apart
 
 __device__ __forceinline__ void mbar_wait_lean(uint32_t bar, uint32_t parity) {
@@ -43,7 +50,7 @@ __device__ __forceinline__ void st_release_gpu(int* p, int v) {
 // CA = A / 256: lane owns units [256c + 128h + 4 lane, +4), h = 0, 1.  MT = 16-column context tiles per warp.
 // AUX: region masks and/or the alpha output are present.
 template <int NB, int CA, int MT, bool AUX>
-__global__ void __launch_bounds__(ATT_THREADS, (CA <= 2 && MT <= 4) ? 2 : 1)
+__global__ void __launch_bounds__(ATT_THREADS, (CA <= 2 && MT <= 4) ? V7_MIN_CTAS : 1)
 att_step_fwd_v7_kernel(const __grid_constant__ CUtensorMap tmap_att, const __grid_constant__ AttParams p) {
   extern __shared__ uint8_t att_smem_raw[];
   constexpr int A = 256 * CA;
@@ -67,16 +74,16 @@ att_step_fwd_v7_kernel(const __grid_constant__ CUtensorMap tmap_att, const __gri
   const uint32_t a_slot = n_slabs * ATT_SLAB_BYTES;
   constexpr uint32_t p_slot = ATT_BATCH * A * 2;
   const uint32_t s_base = (smem_u32(att_smem_raw) + 1023) & ~1023u;
-  const uint32_t s_p = s_base + ATT_STAGES * a_slot;
-  const uint32_t s_F = s_p + ATT_STAGES * p_slot;
+  const uint32_t s_p = s_base + V7_SLOTS * a_slot;
+  const uint32_t s_F = s_p + V7_SLOTS * p_slot;
   const uint32_t s_e = s_F + f_bufs * NB * A * 4;
-  const uint32_t bar_full_p = s_e + V7_E_SLOTS * NB * ATT_BATCH * 4, bar_full_a = bar_full_p + ATT_STAGES * 8,
-                 bar_scored = bar_full_a + ATT_STAGES * 8;
-  const uint32_t cnt_scored = bar_scored + ATT_STAGES * 8, cnt_consumed = cnt_scored + ATT_STAGES * 4;  // warps done with a slot
+  const uint32_t bar_full_p = s_e + V7_E_SLOTS * NB * ATT_BATCH * 4, bar_full_a = bar_full_p + V7_SLOTS * 8,
+                 bar_scored = bar_full_a + V7_SLOTS * 8;
+  const uint32_t cnt_scored = bar_scored + V7_SLOTS * 8, cnt_consumed = cnt_scored + V7_SLOTS * 4;  // warps done with a slot
 
   if (threadIdx.x == 0) {
 #pragma unroll
-    for (int s = 0; s < ATT_STAGES; ++s) {
+    for (int s = 0; s < V7_SLOTS; ++s) {
       asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_full_p + s * 8), "r"(1));
       asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_full_a + s * 8), "r"(1));
       asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar_scored + s * 8), "r"(ATT_WARPS));
@@ -102,7 +109,7 @@ att_step_fwd_v7_kernel(const __grid_constant__ CUtensorMap tmap_att, const __gri
   // prefetch is safe before the dependency wait whatever wrote the tiles (L2 is the point of coherence: a line written
   // after it was prefetched is simply updated), and the first tile loads below then start from L2 instead of from 296
   // simultaneous DRAM misses -- the start-up latency was ~2 us of a 31 us launch.
-  if (threadIdx.x < ATT_STAGES && static_cast<int>(threadIdx.x) < nloc) {
+  if (threadIdx.x < V7_SLOTS && static_cast<int>(threadIdx.x) < nloc) {
     const int b = b0 + threadIdx.x;
     const int job = b / nbpi, kb = b - job * nbpi;
     const int img = p.n_grp > 1 ? job / p.n_grp : job;
@@ -130,7 +137,7 @@ att_step_fwd_v7_kernel(const __grid_constant__ CUtensorMap tmap_att, const __gri
   auto produce_p = [&](int j) {
     int job, kb, img, grp;
     coords(j, job, kb, img, grp);
-    const int slot = j % ATT_STAGES;
+    const int slot = j % V7_SLOTS;
     const int l0 = kb * ATT_BATCH;
     const int nrows = min(ATT_BATCH, L - l0);
     const bool first = (kb == 0) || (j == 0);
@@ -151,7 +158,7 @@ att_step_fwd_v7_kernel(const __grid_constant__ CUtensorMap tmap_att, const __gri
   auto produce_a = [&](int j) {
     int job, kb, img, grp;
     coords(j, job, kb, img, grp);
-    const int slot = j % ATT_STAGES;
+    const int slot = j % V7_SLOTS;
     const uint32_t bar = bar_full_a + slot * 8;
     const long long l = static_cast<long long>(img) * L + kb * ATT_BATCH;
     mbar_expect_tx_addr(bar, n_slabs * ATT_SLAB_BYTES);
@@ -276,8 +283,7 @@ att_step_fwd_v7_kernel(const __grid_constant__ CUtensorMap tmap_att, const __gri
       const int nrows = min(ATT_BATCH, L - kb * ATT_BATCH);
       mbar_wait_lean(bar_full_p + stage * 8, par);
       if (i == 0 && threadIdx.x == 0) {
-        if (nloc > 1) produce_p(1), produce_a(1);
-        if (nloc > 2) produce_p(2), produce_a(2);
+        for (int k = 1; k < V7_SLOTS && k < nloc; ++k) produce_p(k), produce_a(k);
       }
       const uint32_t st_e = s_e + (i & (V7_E_SLOTS - 1)) * (NB * ATT_BATCH * 4);
       const uint32_t prow = s_p + stage * p_slot + (warp * A + lane * 4) * 2;
@@ -293,12 +299,12 @@ att_step_fwd_v7_kernel(const __grid_constant__ CUtensorMap tmap_att, const __gri
       __syncwarp();
       if (lane == 0) {
         mbar_arrive_addr(bar_scored + stage * 8);
-        if (i + ATT_STAGES < nloc) {  // the last warp to finish with the rows requests those of batch i + 3 into their slot
+        if (i + V7_SLOTS < nloc) {  // the last warp to finish with the rows requests those of batch i + 3 into their slot
           uint32_t prev;
           asm volatile("atom.acq_rel.cta.shared.add.u32 %0, [%1], 1;" : "=r"(prev) : "r"(cnt_scored + stage * 4) : "memory");
           if (prev == ATT_WARPS - 1) {
             asm volatile("st.relaxed.cta.shared.u32 [%0], %1;" ::"r"(cnt_scored + stage * 4), "r"(0) : "memory");
-            produce_p(i + ATT_STAGES);
+            produce_p(i + V7_SLOTS);
           }
         }
       }
@@ -382,14 +388,14 @@ att_step_fwd_v7_kernel(const __grid_constant__ CUtensorMap tmap_att, const __gri
       // hand the boxes back: the LAST warp to get here requests those of batch j + 3 into the slot.  (v6 lets the warps take turns at
       // waiting for the other seven: the waiting warp then is the slowest of the next batch and the other seven wait
       // for it at the scored barrier -- two CTA-wide rendezvous per batch, 14 % of the instruction stream was polling)
-      if (j + ATT_STAGES < nloc) {
+      if (j + V7_SLOTS < nloc) {
         __syncwarp();
         if (lane == 0) {
           uint32_t prev;
           asm volatile("atom.acq_rel.cta.shared.add.u32 %0, [%1], 1;" : "=r"(prev) : "r"(cnt_consumed + c_stage * 4) : "memory");
           if (prev == ATT_WARPS - 1) {
             asm volatile("st.relaxed.cta.shared.u32 [%0], %1;" ::"r"(cnt_consumed + c_stage * 4), "r"(0) : "memory");
-            produce_a(j + ATT_STAGES);
+            produce_a(j + V7_SLOTS);
           }
         }
       }
@@ -514,7 +520,7 @@ att_step_fwd_v7_kernel(const __grid_constant__ CUtensorMap tmap_att, const __gri
         ++job;
         if (++fb == f_bufs) fb = 0;
       }
-      if (++stage == ATT_STAGES) {
+      if (++stage == V7_SLOTS) {
         stage = 0;
         par ^= 1;
       }
@@ -525,8 +531,8 @@ att_step_fwd_v7_kernel(const __grid_constant__ CUtensorMap tmap_att, const __gri
 // ---- host side -----------------------------------------------------------------------------------------------------
 template <int NB, int CA, int MT, bool AUX>
 static int launch_v7(AttParams& p, const AttPlan& pl, int n_img, int ctas, cudaStream_t stream, bool query_only, int* per_sm) {
-  const size_t smem = static_cast<size_t>(ATT_STAGES) * ((p.H >> 6) * ATT_SLAB_BYTES + ATT_BATCH * p.A * 2) + pl.f_bufs * NB * p.A * 4 +
-                      V7_E_SLOTS * NB * ATT_BATCH * 4 + 3 * ATT_STAGES * 8 + 2 * ATT_STAGES * 4 + 1024;
+  const size_t smem = static_cast<size_t>(V7_SLOTS) * ((p.H >> 6) * ATT_SLAB_BYTES + ATT_BATCH * p.A * 2) + pl.f_bufs * NB * p.A * 4 +
+                      V7_E_SLOTS * NB * ATT_BATCH * 4 + 3 * V7_SLOTS * 8 + 2 * V7_SLOTS * 4 + 1024;
   auto kern = att_step_fwd_v7_kernel<NB, CA, MT, AUX>;
   if (smem > 226 * 1024) return 1;
   static bool attr_set = false;  // per instantiation
