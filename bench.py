@@ -550,7 +550,12 @@ def run_b200(args, world, rank, local):
 
     torch.cuda.set_device(local)
     if world > 1:
-        torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local))
+        pg_opts = None
+        if os.environ.get("UIC_NCCL_HIGH_PRIORITY", "1") != "0":
+            # the collectives' stream gets priority over the compute stream: the gradient buckets are exchanged while BPTT
+            # still runs, and their CTAs must win the SM slots that compute kernels free (dp.DataParallelStep)
+            pg_opts = torch.distributed.ProcessGroupNCCL.Options(is_high_priority_stream=True)
+        torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local), pg_options=pg_opts)
     _lib.require_device()
     numa_node = _bind_near_gpu(local) if world > 1 else None
     peaks = _peaks()
