@@ -290,8 +290,12 @@ __device__ __forceinline__ void copy_row_f32(float* dst, const float* src, int n
 
 constexpr int ADV_THREADS = 128;
 
+// (8 warps: the candidate merge of phase 1 and the state copies of phase 3 run one warp per beam row, so every row of up to
+//  8 beams is in flight at once -- with 4 warps the fifth beam of configs[4] waited for a second round)
+constexpr int BEAM_ADV_THREADS = 256;
+
 template <int KS>
-__global__ void __launch_bounds__(ADV_THREADS) beam_advance_kernel(const float* __restrict__ stats, int parts,
+__global__ void __launch_bounds__(BEAM_ADV_THREADS) beam_advance_kernel(const float* __restrict__ stats, int parts,
                                                                     int32_t* __restrict__ beam_seq, float* __restrict__ beam_lp,
                                                                     float* __restrict__ beam_sum, int32_t* __restrict__ done_seq,
                                                                     float* __restrict__ done_lp, double* __restrict__ done_p,
@@ -308,7 +312,7 @@ __global__ void __launch_bounds__(ADV_THREADS) beam_advance_kernel(const float* 
   const long long row0 = static_cast<long long>(img) * b;
   // 1. candidates of every beam row: ys[q, c] = log-prob of the c-th best column after the beam-search edits
   const long long src_row0 = static_cast<long long>(img) * io.src_beams;
-  for (int q = warp; q < io.src_beams; q += ADV_THREADS / 32) {
+  for (int q = warp; q < io.src_beams; q += BEAM_ADV_THREADS / 32) {
     float kv[KS];
     int ki[KS];
     const RowStats rs = merge_row_stats<KS>(stats + (src_row0 + q) * parts * ES, parts, kv, ki);
@@ -332,7 +336,7 @@ __global__ void __launch_bounds__(ADV_THREADS) beam_advance_kernel(const float* 
   // 3. state of the parents + next embeddings into the other buffer: one warp per beam row, so the rows' loads are
   //    all in flight together
   const int lane3 = threadIdx.x & 31;
-  for (int v = warp; v < b; v += ADV_THREADS / 32) {
+  for (int v = warp; v < b; v += BEAM_ADV_THREADS / 32) {
     const long long r = row0 + v;
     const long long q = src_row0 + (parent_row[r] - row0);   // the parent's row in the source buffers
     long long tk = next_tok[r];
@@ -362,7 +366,7 @@ int beam_advance(const float* stats, int parts, int kslots, int32_t* beam_seq, f
                gemm_trace_buffer()};
   launch_begin("beam_advance", stream);
 #define UIC_ADV(KS_)                                                                                                         \
-  UIC_CUDA_OK(launch_pdl(beam_advance_kernel<KS_>, dim3(n_img), dim3(ADV_THREADS), 0, stream, stats, parts, beam_seq, beam_lp, beam_sum, \
+  UIC_CUDA_OK(launch_pdl(beam_advance_kernel<KS_>, dim3(n_img), dim3(BEAM_ADV_THREADS), 0, stream, stats, parts, beam_seq, beam_lp, beam_sum, \
                          done_seq, done_lp, done_p, done_unaug, done_cnt, parent_row, next_tok, t, seq_length, beams, flags,       \
                          move_state, io))
   if (kslots == 1)
