@@ -211,3 +211,24 @@ def test_att_step_fwd_v7_with_region_masks(n_img, beams, L, H):
         torch.testing.assert_close(alpha[r0 * beams:r1 * beams], ref_alpha, rtol=5e-3, atol=2e-5)
         torch.testing.assert_close(ctx_f[r0 * beams:r1 * beams], ref_ctx, rtol=5e-3, atol=5e-4)
 
+
+def test_cfg5_beam5_single_pass_plan_matches_oracle():
+    """configs[4] layer sizes (rnn 1024, vocab 30k, beam 5, 20 steps) at a batch that takes the plan `bench.py --workload cfg5`
+    times: >= 74 images, so the five beams of an image share ONE pass of the batch-balanced attention kernel; the oracle
+    decodes three images of the same batch (first, middle, last)."""
+    opt = synth.make_opt(caption_model="att2in2", vocab_size=29999, rnn_size=1024, input_encoding_size=512, att_hid_size=512,
+                         seq_length=20)
+    sd = synth.init_state_dict(opt, seed=9, peaked=40.0, eos_bias=2.0)
+    B = 96
+    fc, att = synth.make_features(B, 196, 2048, seed=9)
+    model = uic.setup(opt)
+    model.load_state_dict(sd)
+    model = model.cuda().eval()
+    seq, lp = model(fc.cuda(), None, att.cuda(), None, opt={"beam_size": 5}, mode="sample")
+    idx = torch.tensor([0, B // 2, B - 1])
+    ref_seq, ref_lp, _, margins = O.sample_beam(sd, "att2in2", fc[idx], att[idx], 20, 5, return_margins=True)
+    exact, exempt, failures = compare_beam(seq[idx], ref_seq, margins, tol=REL)
+    assert not failures, (failures, seq[idx], ref_seq)
+    rows = (seq[idx] == ref_seq).all(1)
+    torch.testing.assert_close(lp[idx][rows], ref_lp[rows], rtol=2e-2, atol=2e-2)
+
