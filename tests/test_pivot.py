@@ -43,6 +43,46 @@ def test_translator_loss_ignores_padding_beyond_the_lengths():
     torch.testing.assert_close(nll, nll2, rtol=1e-5, atol=1e-5)
 
 
+def test_translator_equals_the_plain_per_token_formulation():
+    """The kernel-count restructuring of PivotNMT.forward (word half of the first layer's input projection time-batched, one
+    GEMM over [feed | h0] per step, additive score mask) computes what the reference's step-by-step formulation does:
+    input-feed stacked LSTMCells on cat([emb_t, feed]) + "general" global attention (models/NMT_Models.py:209-262)."""
+    import torch.nn.functional as F
+    torch.manual_seed(0)
+    gen = torch.Generator().manual_seed(1)
+    m = pivot.PivotNMT(src_vocab=50, tgt_vocab=40, dim=16, layers=2, dropout=0.0).eval()
+    src, n = pivot.sentences(5, 50, gen, lo=2, hi=7)
+    tgt, _ = pivot.sentences(5, 40, gen, lo=2, hi=7, bos=pivot.BOS)
+    nll, cnt = m(src, n, tgt)
+    nll.backward()
+    g = {k: p.grad.clone() for k, p in m.named_parameters()}
+    m.zero_grad()
+
+    emb = F.relu(m.src_mlp(m.src_lut(src)))
+    memory, (h, c) = m.encoder(emb, n)
+    memory = memory.transpose(0, 1)
+    fix = lambda s: torch.cat([s[0::2], s[1::2]], 2)
+    h, c = list(fix(h)), list(fix(c))
+    mask = torch.arange(memory.size(1))[None, :] >= n[:, None]
+    feed, keys, outs = memory.new_zeros(src.size(1), m.dim), m.attn_in(memory), []
+    te = m.tgt_lut(tgt[:-1])
+    for t in range(te.size(0)):
+        x = torch.cat([te[t], feed], 1)
+        for i, cell in enumerate(m.cells):
+            h[i], c[i] = cell(x, (h[i], c[i]))
+            x = h[i]
+        score = torch.bmm(keys, x.unsqueeze(2)).squeeze(2).masked_fill(mask, float("-inf"))
+        ctx = torch.bmm(F.softmax(score, 1).unsqueeze(1), memory).squeeze(1)
+        feed = torch.tanh(m.attn_out(torch.cat([ctx, x], 1)))
+        outs.append(feed)
+    logp = F.log_softmax(m.generator(torch.stack(outs)), -1)
+    ref = F.nll_loss(logp.view(-1, logp.size(-1)), tgt[1:].reshape(-1), ignore_index=pivot.PAD, reduction="sum")
+    ref.backward()
+    torch.testing.assert_close(nll, ref, rtol=1e-5, atol=1e-5)
+    for k, p in m.named_parameters():
+        torch.testing.assert_close(g[k], p.grad, rtol=1e-4, atol=1e-5, msg=k)
+
+
 @pytest.mark.gpu
 def test_graphed_translator_step_equals_eager():
     """The CUDA-graph replay of the training step follows the same loss trajectory as the step issued eagerly (dropout 0)."""

@@ -36,38 +36,62 @@ class MaskedBiLSTM(nn.Module):
         self.rnn = nn.LSTM(input_size, hidden_size, num_layers=num_layers, dropout=dropout, bidirectional=True)
         self.hidden_size, self.num_layers, self.dropout = hidden_size, num_layers, dropout
 
-    def _direction(self, x, valid, layer, reverse):
-        sfx = f"_l{layer}" + ("_reverse" if reverse else "")
-        w_ih, w_hh = getattr(self.rnn, "weight_ih" + sfx), getattr(self.rnn, "weight_hh" + sfx)
-        b_ih, b_hh = getattr(self.rnn, "bias_ih" + sfx), getattr(self.rnn, "bias_hh" + sfx)
+    def _layer(self, x, keep, layer):
+        """One bidirectional layer over padded (S, B, D) input.  The captured step is bound by its NUMBER of kernels, so
+        (i) the input projections of all time steps and BOTH directions are one GEMM, (ii) the two directions advance
+        together -- step s handles position s forward and S-1-s backward: one batched matmul with the two recurrent
+        weights and one fused cell over 2B rows -- and (iii) only the backward direction is masked per step (its state
+        must stay zero until its sentence starts); the forward direction runs unmasked past a row's end: its outputs
+        there are zeroed once afterwards and its final state is gathered at position len-1.  4 kernels per step where
+        the per-direction torch LSTM cell + freezing `where`s took 12."""
+        rnn, Hh = self.rnn, self.hidden_size
         S, B, _ = x.shape
-        h = x.new_zeros(B, self.hidden_size)
-        c = x.new_zeros(B, self.hidden_size)
-        outs = [None] * S
-        for t in (range(S - 1, -1, -1) if reverse else range(S)):
-            # torch's fused LSTM cell (two GEMMs + one pointwise kernel, forward and backward): the captured graph is bound
-            # by its NUMBER of kernels, not by their arithmetic (a first version with the gate math spelled out in elementwise
-            # ops replayed ~10 000 tiny kernels per step)
-            h_new, c_new = torch._VF.lstm_cell(x[t], (h, c), w_ih, w_hh, b_ih, b_hh)
-            m = valid[t]
-            h, c = torch.where(m, h_new, h), torch.where(m, c_new, c)    # rows past their end keep their state
-            outs[t] = h * m
-        return torch.stack(outs), h, c
+        p = lambda name, rev: getattr(rnn, f"{name}_l{layer}" + ("_reverse" if rev else ""))
+        w_ih = torch.cat([p("weight_ih", False), p("weight_ih", True)], 0)                    # (8 Hh, D)
+        bias = torch.cat([p("bias_ih", False) + p("bias_hh", False), p("bias_ih", True) + p("bias_hh", True)], 0)
+        xw = F.linear(x, w_ih, bias).view(S, B, 2, 4 * Hh)
+        ig = torch.stack([xw[:, :, 0], xw[:, :, 1].flip(0)], 1)                               # (S, 2, B, 4 Hh): backward time-flipped
+        w_hh = torch.stack([p("weight_hh", False).t(), p("weight_hh", True).t()], 0).to(ig.dtype)   # (2, Hh, 4 Hh)
+        keep = keep.to(ig.dtype)
+        h = ig.new_zeros(2, B, Hh)
+        c = ig.new_zeros(2, B, Hh)
+        hs, cs = [None] * S, [None] * S
+        for s in range(S):
+            hg = torch.bmm(h, w_hh)                                                            # (2, B, 4 Hh)
+            h_new, c_new = _lstm_from_gates(ig[s].reshape(2 * B, 4 * Hh), hg.reshape(2 * B, 4 * Hh), c.reshape(2 * B, Hh))
+            m = keep[s]                                                                        # (2, B, 1): ones | valid[S-1-s]
+            h, c = h_new.view(2, B, Hh) * m, c_new.view(2, B, Hh) * m
+            hs[s], cs[s] = h, c
+        return torch.stack(hs), torch.stack(cs)                                                # (S, 2, B, Hh) each
 
     def forward(self, x, lengths):
         """x (S, B, D); lengths (B,) on x's device.  Returns memory (S, B, 2 hidden), (h_n, c_n) each (2 layers, B, hidden)."""
-        S = x.size(0)
+        S, B = x.size(0), x.size(1)
         valid = (torch.arange(S, device=x.device)[:, None] < lengths[None, :]).unsqueeze(2)    # (S, B, 1)
-        hs, cs = [], []
+        keep = torch.stack([torch.ones_like(valid), valid.flip(0)], 1)                         # (S, 2, B, 1)
+        last = (lengths - 1).clamp_min(0).view(1, B, 1)
+        h_n, c_n = [], []
         for layer in range(self.num_layers):
-            fw, hf, cf = self._direction(x, valid, layer, False)
-            bw, hb, cb = self._direction(x, valid, layer, True)
-            x = torch.cat([fw, bw], 2)
+            hs, cs = self._layer(x, keep, layer)
+            idx = last.expand(1, B, hs.size(3))
+            # final states: forward = the state at a row's last valid position, backward = the state after the last step
+            h_n += [hs[:, 0].gather(0, idx).squeeze(0), hs[S - 1, 1]]
+            c_n += [cs[:, 0].gather(0, idx).squeeze(0), cs[S - 1, 1]]
+            x = torch.cat([hs[:, 0] * valid.to(hs.dtype), hs[:, 1].flip(0)], 2)
             if layer + 1 < self.num_layers and self.dropout > 0:
                 x = F.dropout(x, self.dropout, self.training)
-            hs += [hf, hb]
-            cs += [cf, cb]
-        return x, (torch.stack(hs), torch.stack(cs))
+        return x, (torch.stack(h_n), torch.stack(c_n))
+
+
+def _lstm_from_gates(igates, hgates, c):
+    """LSTM cell from pre-computed input / hidden gate sums (biases included): torch's fused CUDA cell (one pointwise kernel,
+    forward and backward), the gate formulas spelled out on the CPU (tests)."""
+    if igates.is_cuda:
+        h, c2, _ = torch.ops.aten._thnn_fused_lstm_cell(igates, hgates, c)
+        return h, c2
+    i, f, g, o = (igates + hgates).chunk(4, 1)
+    c2 = torch.sigmoid(f) * c + torch.sigmoid(i) * torch.tanh(g)
+    return torch.sigmoid(o) * torch.tanh(c2), c2
 
 
 class PivotNMT(nn.Module):
@@ -96,14 +120,24 @@ class PivotNMT(nn.Module):
         keys = self.attn_in(memory)                                                        # "general" score h^T W m
         outs = []
         tgt_emb = self.tgt_lut(tgt[:-1])
+        # Kernel-count savings of the per-token loop (it replays from a CUDA graph and is launch-bound): the word half of the
+        # first layer's input projection is one GEMM over all T steps; per step the input-feed half and the recurrent
+        # projection are ONE GEMM over [feed | h0]; the padding mask enters the scores as the additive term of baddbmm.
+        c0 = self.cells[0]
+        e_gates = F.linear(tgt_emb, c0.weight_ih[:, :self.dim], c0.bias_ih + c0.bias_hh)   # (T-1, B, 4 dim)
+        w_fh = torch.cat([c0.weight_ih[:, self.dim:], c0.weight_hh], 1)                    # (4 dim, 2 dim): [feed | h0]
+        neg = torch.zeros(mask.shape, dtype=keys.dtype, device=src.device).masked_fill(mask, float("-inf")).unsqueeze(2)
         for t in range(tgt_emb.size(0)):                                                   # one step per token :209-262
-            x = torch.cat([tgt_emb[t], feed], 1)
-            for i, cell in enumerate(self.cells):
-                h[i], c[i] = cell(x, (h[i], c[i]))
-                x = self.drop(h[i]) if i + 1 < self.layers else h[i]
-            score = torch.bmm(keys, x.unsqueeze(2)).squeeze(2).masked_fill(mask, float("-inf"))
-            ctx = torch.bmm(F.softmax(score, 1).unsqueeze(1), memory).squeeze(1)
-            feed = self.drop(torch.tanh(self.attn_out(torch.cat([ctx, x], 1))))
+            hg = F.linear(torch.cat([feed, h[0]], 1), w_fh)
+            h[0], c[0] = _lstm_from_gates(e_gates[t], hg.to(e_gates.dtype), c[0].to(e_gates.dtype))
+            x = h[0]
+            for i in range(1, self.layers):
+                x = self.drop(x)
+                h[i], c[i] = self.cells[i](x, (h[i], c[i]))
+                x = h[i]
+            score = torch.baddbmm(neg, keys, x.unsqueeze(2).to(keys.dtype)).squeeze(2)
+            ctx = torch.bmm(F.softmax(score, 1).unsqueeze(1).to(memory.dtype), memory).squeeze(1)
+            feed = self.drop(torch.tanh(self.attn_out(torch.cat([ctx, x.to(ctx.dtype)], 1))))
             outs.append(feed)
         logp = F.log_softmax(self.generator(torch.stack(outs)), -1)
         gold = tgt[1:]
