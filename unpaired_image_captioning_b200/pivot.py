@@ -129,6 +129,8 @@ class PivotNMT(nn.Module):
         c0 = self.cells[0]
         e_gates = F.linear(tgt_emb, c0.weight_ih[:, :self.dim], c0.bias_ih + c0.bias_hh)   # (T-1, B, 4 dim)
         w_fh = torch.cat([c0.weight_ih[:, self.dim:], c0.weight_hh], 1)                    # (4 dim, 2 dim): [feed | h0]
+        if torch.is_autocast_enabled():   # a non-leaf operand is re-cast by autocast at EVERY use (30 x 8 MB per step): cast once
+            w_fh = w_fh.to(torch.get_autocast_dtype("cuda"))
         neg = torch.zeros(mask.shape, dtype=keys.dtype, device=src.device).masked_fill(mask, float("-inf")).unsqueeze(2)
         eg_steps = e_gates.unbind(0)
         for t in range(tgt_emb.size(0)):                                                   # one step per token :209-262
