@@ -19,7 +19,7 @@ import torch
 
 from . import _lib
 from ._lib import check, gemm, ptr, stream
-from .engine import BF16, Slots
+from .engine import BF16, Slots, _nvtx
 
 LOGIT_CHUNK_ROWS = 2048  # rows of the (B*T, V) logit matrix processed per fused fwd+bwd pass (stays L2-resident)
 
@@ -424,16 +424,19 @@ def xe_sum_and_grads(model, fc_feats, att_feats, labels, masks, att_masks=None, 
     gradients the moment they are final: logit.* right after the fused logit stage (before BPTT starts), then the
     groups bptt() announces; whatever is left comes with the returned dict."""
     with torch.no_grad():
-        r = teacher_forced_run(model, fc_feats, att_feats, labels, att_masks, all_steps=True, ss=ss, drop=drop)
+        with _nvtx("uic.train.forward"):
+            r = teacher_forced_run(model, fc_feats, att_feats, labels, att_masks, all_steps=True, ss=ss, drop=drop)
         T_total = r.T_total
         target = labels[:, 1:T_total + 1].contiguous().view(-1).long()
         mask = masks[:, 1:T_total + 1].contiguous().view(-1).float()
         one = torch.ones(1, dtype=torch.float32, device=mask.device)
-        o = _logit_stage(r, target, mask, one, want_grad=True)
+        with _nvtx("uic.train.logit_stage"):
+            o = _logit_stage(r, target, mask, one, want_grad=True)
         head = {"logit.weight": o["dW"], "logit.bias": o["db"]}
         if on_ready is not None:
             on_ready(head)
-        g = bptt(r, o["dh"], on_ready=on_ready)
+        with _nvtx("uic.train.bptt"):
+            g = bptt(r, o["dh"], on_ready=on_ready)
         g.update(head)
         return o["nll"].sum(), mask.sum(), g
 

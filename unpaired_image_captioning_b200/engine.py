@@ -18,6 +18,7 @@ from __future__ import annotations
 import collections
 import contextlib
 import gc
+import os
 import weakref
 
 import torch
@@ -167,6 +168,22 @@ class Slots:
             self.gather = [(E + H, 3 * H), (self.h2[0], H)]      # [h0|ctx1|h1] (ctx1 rides along) and h2
             self.n_state = 3
             self.h_load = self.h_read = [self.h0, self.h1, self.h2]
+
+
+_NVTX = os.environ.get("UIC_NVTX", "0") != "0"
+
+
+@contextlib.contextmanager
+def _nvtx(name):
+    """NVTX range around a phase of the path (UIC_NVTX=1; a no-op otherwise): feature prologue, decode-graph replay / first
+    eager pass, training forward / backward -- what a timeline (nsys, ncu --nvtx) needs to tell the phases apart."""
+    if _NVTX:
+        torch.cuda.nvtx.range_push(name)
+    try:
+        yield
+    finally:
+        if _NVTX:
+            torch.cuda.nvtx.range_pop()
 
 
 @contextlib.contextmanager
@@ -806,10 +823,12 @@ class DecoderEngine:
             while len(self._graphs) > self.max_graphs:   # e.g. att_masks clip every batch to a different length
                 self._graphs.popitem(last=False)
         g, s, out, n_kernels = entry
-        self._load_feats(s, feats)
+        with _nvtx("uic.prologue"):
+            self._load_feats(s, feats)
         if pre is not None:
             pre(s)      # per-call device-side inputs of the captured loop (the sampling seed)
-        g.replay()
+        with _nvtx(f"uic.decode_graph[{key[0] if isinstance(key, tuple) else key}]"):
+            g.replay()
         self._replayed_launches += n_kernels
         return out
 
