@@ -52,20 +52,7 @@ class MaskedBiLSTM(nn.Module):
         xw = F.linear(x, w_ih, bias).view(S, B, 2, 4 * Hh)
         ig = torch.stack([xw[:, :, 0], xw[:, :, 1].flip(0)], 1)                               # (S, 2, B, 4 Hh): backward time-flipped
         w_hh = torch.stack([p("weight_hh", False).t(), p("weight_hh", True).t()], 0).to(ig.dtype)   # (2, Hh, 4 Hh)
-        keep = keep.to(ig.dtype)
-        h = ig.new_zeros(2, B, Hh)
-        c = ig.new_zeros(2, B, Hh)
-        hs, cs = [None] * S, [None] * S
-        # (unbind ONCE: indexing ig[s] inside the loop makes autograd allocate and fill a full (S, 2, B, 4 Hh) zero tensor per
-        #  step in the backward pass -- 125 fills + 114 slice copies of 31 MB were 13 % of the step's device time)
-        ig_steps, keep_steps = ig.reshape(S, 2 * B, 4 * Hh).unbind(0), keep.unbind(0)
-        for s in range(S):
-            hg = torch.bmm(h, w_hh)                                                            # (2, B, 4 Hh)
-            h_new, c_new = _lstm_from_gates(ig_steps[s], hg.reshape(2 * B, 4 * Hh), c.reshape(2 * B, Hh))
-            m = keep_steps[s]                                                                  # (2, B, 1): ones | valid[S-1-s]
-            h, c = h_new.view(2, B, Hh) * m, c_new.view(2, B, Hh) * m
-            hs[s], cs[s] = h, c
-        return torch.stack(hs), torch.stack(cs)                                                # (S, 2, B, Hh) each
+        return _BiLstmLayerFn.apply(ig.reshape(S, 2 * B, 4 * Hh), w_hh, keep.to(ig.dtype))       # (S, 2, B, Hh) each
 
     def forward(self, x, lengths):
         """x (S, B, D); lengths (B,) on x's device.  Returns memory (S, B, 2 hidden), (h_n, c_n) each (2 layers, B, hidden)."""
@@ -84,6 +71,77 @@ class MaskedBiLSTM(nn.Module):
             if layer + 1 < self.num_layers and self.dropout > 0:
                 x = F.dropout(x, self.dropout, self.training)
         return x, (torch.stack(h_n), torch.stack(c_n))
+
+
+class _BiLstmLayerFn(torch.autograd.Function):
+    """The recurrence of one bidirectional layer (both directions per step, MaskedBiLSTM._layer) with a hand-written backward
+    pass: autograd's per-step bookkeeping (a weight-gradient matmul + accumulation add per step, fan-out adds, mask
+    multiplies and their gradients) was ~10 kernels per step; here the backward step is mask, fused cell backward, one batched
+    matmul for the state gradient, and the recurrent weights' gradient is ONE batched matmul over all S steps at the end.
+    ig (S, 2B, 4Hh) input gate sums (biases included), w_hh (2, Hh, 4Hh), keep (S, 2, B, 1); returns h, c (S, 2, B, Hh)."""
+
+    @staticmethod
+    def forward(ctx, ig, w_hh, keep):
+        S, B2, G = ig.shape
+        B, Hh = B2 // 2, w_hh.size(1)
+        h = ig.new_zeros(2, B, Hh)
+        c = ig.new_zeros(2, B, Hh)
+        hs, cs, h_prev, c_prev, c_new_l, work = [], [], [], [], [], []
+        fused = ig.is_cuda
+        ig_s, keep_s = ig.unbind(0), keep.unbind(0)
+        for s in range(S):
+            hg = torch.bmm(h, w_hh).view(B2, G)
+            h_prev.append(h)
+            c_prev.append(c)
+            if fused:
+                h_new, c_new, wk = torch.ops.aten._thnn_fused_lstm_cell(ig_s[s], hg, c.view(B2, Hh))
+            else:
+                i, f, g, o = (ig_s[s] + hg).chunk(4, 1)
+                i, f, g, o = torch.sigmoid(i), torch.sigmoid(f), torch.tanh(g), torch.sigmoid(o)
+                c_new = f * c.view(B2, Hh) + i * g
+                h_new = o * torch.tanh(c_new)
+                wk = torch.stack([i, f, g, o])
+            c_new_l.append(c_new)
+            work.append(wk)
+            h = h_new.view(2, B, Hh) * keep_s[s]
+            c = c_new.view(2, B, Hh) * keep_s[s]
+            hs.append(h)
+            cs.append(c)
+        ctx.fused = fused
+        ctx.save_for_backward(w_hh, keep, torch.stack(h_prev), torch.stack(c_prev), torch.stack(c_new_l), torch.stack(work))
+        return torch.stack(hs), torch.stack(cs)
+
+    @staticmethod
+    def backward(ctx, dhs, dcs):
+        w_hh, keep, h_prev, c_prev, c_new, work = ctx.saved_tensors
+        S, _, B, Hh = h_prev.shape
+        B2, G = 2 * B, 4 * Hh
+        w_t = w_hh.transpose(1, 2)
+        dh_next = dc_next = None
+        dgs = [None] * S
+        dhs_s, dcs_s, keep_s = dhs.unbind(0), dcs.unbind(0), keep.unbind(0)
+        for s in range(S - 1, -1, -1):
+            dh = dhs_s[s] if dh_next is None else dhs_s[s] + dh_next
+            dc = dcs_s[s] if dc_next is None else dcs_s[s] + dc_next
+            dh_new = (dh * keep_s[s]).reshape(B2, Hh)
+            dc_new = (dc * keep_s[s]).reshape(B2, Hh)
+            if ctx.fused:
+                dg, dc_prev, _ = torch.ops.aten._thnn_fused_lstm_cell_backward_impl(dh_new, dc_new, c_prev[s].view(B2, Hh), c_new[s], work[s], False)
+            else:
+                i, f, g, o = work[s].unbind(0)
+                tc = torch.tanh(c_new[s])
+                do = dh_new * tc
+                dcn = dc_new + dh_new * o * (1 - tc * tc)
+                dg = torch.cat([dcn * g * i * (1 - i), dcn * c_prev[s].view(B2, Hh) * f * (1 - f), dcn * i * (1 - g * g), do * o * (1 - o)], 1)
+                dc_prev = dcn * f
+            dgs[s] = dg
+            dh_next = torch.bmm(dg.view(2, B, G), w_t)
+            dc_next = dc_prev.view(2, B, Hh)
+        dig = torch.stack(dgs)                                                                 # (S, 2B, 4Hh)
+        # d w_hh[d] = sum over steps and rows of h_prev^T dgates: one batched matmul with K = S B
+        hp = h_prev.permute(1, 3, 0, 2).reshape(2, Hh, S * B)
+        dw = torch.bmm(hp, dig.view(S, 2, B, G).permute(1, 0, 2, 3).reshape(2, S * B, G))
+        return dig, dw.to(w_hh.dtype), None
 
 
 def _lstm_from_gates(igates, hgates, c):
