@@ -595,11 +595,15 @@ def run_b200(args, world, rank, local):
                 alg_bytes = B * cfg["att_size"] * (opt.att_hid_size + opt.rnn_size) * 2      # p_att + att tiles, bf16, once per image
                 us_att = _att_step_in_graph_us(B, beam, cfg["att_size"], opt.att_hid_size, opt.rnn_size)
                 achieved = alg_bytes / (us_att * 1e-6) / 1e9
+                us_att1 = _att_step_in_graph_us(B, 1, cfg["att_size"], opt.att_hid_size, opt.rnn_size)   # the greedy leg's launch: one row per image
                 traffic, traffic_src = _ncu_traffic()
                 roofline = {"kernel": "att_step_fwd", "bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                             "frac": achieved / peaks["hbm_gbs"], "traffic": traffic, "peak_source": peaks["source"],
                             "algorithmic_bytes_per_launch": alg_bytes, "us_per_launch": us_att,
                             "us_per_launch_eager_event_pairs": ms_att / n_att * 1e3,
+                            "beam1": {"us_per_launch": us_att1, "achieved": alg_bytes / (us_att1 * 1e-6) / 1e9,
+                                      "frac": alg_bytes / (us_att1 * 1e-6) / 1e9 / peaks["hbm_gbs"],
+                                      "what": "the same kernel with one row per image (greedy decode, first beam step): same bytes, a third of the arithmetic"},
                             "traffic_source": traffic_src, "gemms": gemms, "kernel_shares": shares,
                             "note": "duration: CUDA events around replays of a captured graph of 32 back-to-back launches of the kernel at "
                                     "this workload's shape (steady state, as inside the captured decode loop); us_per_launch_eager_event_pairs "
