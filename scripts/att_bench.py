@@ -71,5 +71,6 @@ for B, beams, L, A, H in cases:
     err32 = (ctx32 - ref).abs().max().item()
     erra = (alpha - al).abs().max().item()
     t = time_graph(run)
+    t_aux = time_graph(lambda: _lib.att_step(f, A, e_tile, att, w, None, None, 0, ctx32, H, alpha, B, beams, L, A, H))   # training forward: fp32 ctx + alpha
     gb = B * L * (A + H) * 2 / 1e9
-    print(f"{tag} att_step_fwd {B}x{beams}x{L} A={A} H={H}: {t:.1f} us  {gb / t * 1e6:.0f} GB/s   max|ctx-ref| bf16 {err:.4f} f32 {err32:.5f} alpha {erra:.6f}", flush=True)
+    print(f"{tag} att_step_fwd {B}x{beams}x{L} A={A} H={H}: {t:.1f} us  {gb / t * 1e6:.0f} GB/s   (with alpha output: {t_aux:.1f} us)   max|ctx-ref| bf16 {err:.4f} f32 {err32:.5f} alpha {erra:.6f}", flush=True)
