@@ -144,7 +144,11 @@ class DataParallelStep:
         for w in works:
             w.wait()
         inv = 1.0 / bk.tail                                     # 1 / global sum(mask), identical on every rank
-        bk.grads.mul_(inv)
         if self.clip:
-            bk.clip_(self.clip)
+            # normalisation and clip_grad_norm_ (misc/optimizer.py:89-93) in ONE pass over the 81 MB buffer:
+            # ||g inv|| = inv ||g||, so the clip factor of the normalised gradients is known before they are scaled
+            norm = bk.grads.norm() * inv
+            bk.grads.mul_(inv * torch.clamp(self.clip / (norm + 1e-6), max=1.0))
+        else:
+            bk.grads.mul_(inv)
         return nll_sum * inv[0]
