@@ -83,6 +83,29 @@ def test_translator_equals_the_plain_per_token_formulation():
         torch.testing.assert_close(g[k], p.grad, rtol=1e-4, atol=1e-5, msg=k)
 
 
+def test_input_feed_decoder_backward_with_dropout_gradcheck():
+    """The hand-written backward of the decoder loop (pivot._InputFeedDecoderFn) with ACTIVE dropout against numerical
+    derivatives (float64; the generator is re-seeded inside the function, so the masks are a fixed part of it)."""
+    torch.manual_seed(11)
+    T, B, d, S, L = 3, 2, 4, 3, 2
+    f64 = dict(dtype=torch.float64, requires_grad=True)
+    eg = torch.randn(T, B, 4 * d, **f64)
+    w_fh = (torch.randn(4 * d, 2 * d, dtype=torch.float64) * 0.5).requires_grad_()
+    keys, memory = torch.randn(B, S, d, **f64), torch.randn(B, S, d, **f64)
+    neg = torch.zeros(B, S, dtype=torch.float64)
+    neg[1, 2] = float("-inf")
+    w_out = (torch.randn(d, 2 * d, dtype=torch.float64) * 0.5).requires_grad_()
+    h0s, c0s = torch.randn(L, B, d, **f64), torch.randn(L, B, d, **f64)
+    w_cat = (torch.randn(4 * d, 2 * d, dtype=torch.float64) * 0.5).requires_grad_()
+    b1 = torch.randn(4 * d, **f64)
+
+    def fn(eg, w_fh, keys, memory, w_out, h0s, c0s, w_cat, b1):
+        torch.manual_seed(99)
+        return pivot._InputFeedDecoderFn.apply(0.3, True, eg, w_fh, keys, memory, neg, w_out, h0s, c0s, w_cat, b1)
+
+    assert torch.autograd.gradcheck(fn, (eg, w_fh, keys, memory, w_out, h0s, c0s, w_cat, b1), eps=1e-6, atol=1e-5, rtol=1e-4)
+
+
 @pytest.mark.gpu
 def test_graphed_translator_step_equals_eager():
     """The CUDA-graph replay of the training step follows the same loss trajectory as the step issued eagerly (dropout 0)."""

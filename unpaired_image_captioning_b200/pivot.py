@@ -144,6 +144,144 @@ class _BiLstmLayerFn(torch.autograd.Function):
         return dig, dw.to(w_hh.dtype), None
 
 
+def _cell_fwd(ig, hg, c):
+    """LSTM cell from gate sums -> (h, c_new, workspace for _cell_bwd)."""
+    if ig.is_cuda:
+        return torch.ops.aten._thnn_fused_lstm_cell(ig, hg, c)
+    i, f, g, o = (ig + hg).chunk(4, 1)
+    i, f, g, o = torch.sigmoid(i), torch.sigmoid(f), torch.tanh(g), torch.sigmoid(o)
+    c_new = f * c + i * g
+    return o * torch.tanh(c_new), c_new, torch.stack([i, f, g, o])
+
+
+def _cell_bwd(dh, dc, c_prev, c_new, wk):
+    """-> (d gate sums (B, 4H), d c_prev); dc may be None."""
+    if dh.is_cuda:
+        dg, dc_prev, _ = torch.ops.aten._thnn_fused_lstm_cell_backward_impl(dh, dc, c_prev, c_new, wk, False)
+        return dg, dc_prev
+    i, f, g, o = wk.unbind(0)
+    tc = torch.tanh(c_new)
+    dcn = dh * o * (1 - tc * tc)
+    if dc is not None:
+        dcn = dcn + dc
+    dg = torch.cat([dcn * g * i * (1 - i), dcn * c_prev * f * (1 - f), dcn * i * (1 - g * g), dh * tc * o * (1 - o)], 1)
+    return dg, dcn * f
+
+
+class _InputFeedDecoderFn(torch.autograd.Function):
+    """The per-token loop of the input-feed decoder (models/NMT_Models.py:209-262: stacked LSTM cells on [emb_t | feed_{t-1}],
+    "general" global attention, feed_t = dropout(tanh(W_out [ctx_t | h_t]))) with a hand-written backward pass.  Left to
+    autograd, every token step re-derives a weight gradient per weight use (five small GEMMs) and accumulates it (thirteen
+    adds per step with the fan-out sums); here the backward step only propagates the state gradients, and the gradients of
+    the weights, of the attention keys and of the memory bank are ONE (batched) matmul each over all T steps at the end.
+    Inputs are already in the compute dtype.  eg (T, B, 4d): word half of layer 0's gate sums (biases in); w_fh (4d, 2d) on
+    [feed | h0]; keys / memory (B, S, d); neg (B, S) additive score mask; w_out (d, 2d); h0s / c0s (L, B, d) initial
+    states; then (w_cat_i (4d, 2d) on [x | h_i], b_i (4d)) for the layers i >= 1.  Returns feeds (T, B, d)."""
+
+    @staticmethod
+    def forward(ctx, p_drop, training, eg, w_fh, keys, memory, neg, w_out, h0s, c0s, *upper):
+        T, B, _ = eg.shape
+        L = h0s.size(0)
+        drop = training and p_drop > 0
+        h, c = list(h0s.unbind(0)), list(c0s.unbind(0))
+        feed = eg.new_zeros(B, h0s.size(2))
+        zero_gates = eg.new_zeros(B, eg.size(2))
+        sv = {k: [] for k in ("cat0", "c0p", "c0n", "wk0", "a", "x", "cato", "y", "mo")}
+        sv_up = [{k: [] for k in ("cat", "cp", "cn", "wk", "m")} for _ in range(L - 1)]
+        outs = []
+        eg_s = eg.unbind(0)
+        for t in range(T):
+            cat0 = torch.cat([feed, h[0]], 1)
+            h_new, c_new, wk = _cell_fwd(eg_s[t], cat0 @ w_fh.t(), c[0])
+            sv["cat0"].append(cat0); sv["c0p"].append(c[0]); sv["c0n"].append(c_new); sv["wk0"].append(wk)
+            h[0], c[0] = h_new, c_new
+            x = h_new
+            for i in range(1, L):
+                w_cat, b = upper[2 * (i - 1)], upper[2 * (i - 1) + 1]
+                m = None
+                if drop:
+                    x, m = torch.ops.aten.native_dropout(x, p_drop, True)
+                cat_i = torch.cat([x, h[i]], 1)
+                h_new, c_new, wk = _cell_fwd(torch.addmm(b, cat_i, w_cat.t()), zero_gates, c[i])   # gate sums complete in the input half
+                u = sv_up[i - 1]
+                u["cat"].append(cat_i); u["cp"].append(c[i]); u["cn"].append(c_new); u["wk"].append(wk); u["m"].append(m)
+                h[i], c[i] = h_new, c_new
+                x = h_new
+            a = torch.softmax(torch.baddbmm(neg.unsqueeze(2), keys, x.unsqueeze(2)).squeeze(2), 1)
+            cx = torch.bmm(a.unsqueeze(1), memory).squeeze(1)
+            cato = torch.cat([cx, x], 1)
+            y = torch.tanh(cato @ w_out.t())
+            mo = None
+            feed = y
+            if drop:
+                feed, mo = torch.ops.aten.native_dropout(y, p_drop, True)
+            sv["a"].append(a); sv["x"].append(x); sv["cato"].append(cato); sv["y"].append(y); sv["mo"].append(mo)
+            outs.append(feed)
+        ctx.p_drop, ctx.drop, ctx.L = p_drop, drop, L
+        ctx.sv, ctx.sv_up = sv, sv_up
+        ctx.save_for_backward(w_fh, keys, memory, w_out, *upper)
+        return torch.stack(outs)
+
+    @staticmethod
+    def backward(ctx, d_outs):
+        w_fh, keys, memory, w_out, *upper = ctx.saved_tensors
+        sv, sv_up, L, drop = ctx.sv, ctx.sv_up, ctx.L, ctx.drop
+        scale = 1.0 / (1.0 - ctx.p_drop) if drop else 1.0
+        T = d_outs.size(0)
+        d = w_out.size(0)
+        d_feed = None
+        dh = [None] * L
+        dc = [None] * L
+        dg0_l, dy_l, ds_l, dcx_l = [None] * T, [None] * T, [None] * T, [None] * T
+        dg_up = [[None] * T for _ in range(L - 1)]
+        do_s = d_outs.unbind(0)
+        for t in range(T - 1, -1, -1):
+            df = do_s[t] if d_feed is None else do_s[t] + d_feed
+            if drop:
+                df = torch.ops.aten.native_dropout_backward(df, sv["mo"][t], scale)
+            y = sv["y"][t]
+            dy = df * (1 - y * y)
+            dy_l[t] = dy
+            dcat = dy @ w_out                                            # (B, 2d): [d ctx | d x]
+            dcx, dx = dcat[:, :d], dcat[:, d:]
+            dcx_l[t] = dcx
+            a = sv["a"][t]
+            da = torch.bmm(memory, dcx.unsqueeze(2)).squeeze(2)         # (B, S)
+            ds = torch.ops.aten._softmax_backward_data(da, a, 1, a.dtype)
+            ds_l[t] = ds
+            dx = dx + torch.bmm(ds.unsqueeze(1), keys).squeeze(1)
+            for i in range(L - 1, 0, -1):
+                u = sv_up[i - 1]
+                dhi = dx if dh[i] is None else dx + dh[i]
+                dg, dc[i] = _cell_bwd(dhi, dc[i], u["cp"][t], u["cn"][t], u["wk"][t])
+                dg_up[i - 1][t] = dg
+                dcat_i = dg @ upper[2 * (i - 1)]                         # (B, 2d): [d x | d h_i]
+                dx, dh[i] = dcat_i[:, :d], dcat_i[:, d:]
+                if drop:
+                    dx = torch.ops.aten.native_dropout_backward(dx, u["m"][t], scale)
+            dh0 = dx if dh[0] is None else dx + dh[0]
+            dg0, dc[0] = _cell_bwd(dh0, dc[0], sv["c0p"][t], sv["c0n"][t], sv["wk0"][t])
+            dg0_l[t] = dg0
+            dcat0 = dg0 @ w_fh                                           # (B, 2d): [d feed | d h0]
+            d_feed, dh[0] = dcat0[:, :d], dcat0[:, d:]
+        B = d_outs.size(1)
+        d_eg = torch.stack(dg0_l)                                        # (T, B, 4d)
+        flat = lambda lst: torch.stack(lst).reshape(T * B, -1)
+        d_w_fh = d_eg.reshape(T * B, -1).t() @ flat(sv["cat0"])
+        d_w_out = flat(dy_l).t() @ flat(sv["cato"])
+        ds_all = torch.stack(ds_l, 2)                                    # (B, S, T)
+        d_keys = torch.bmm(ds_all, torch.stack(sv["x"], 1))              # (B, S, T) x (B, T, d)
+        d_memory = torch.bmm(torch.stack(sv["a"], 2), torch.stack(dcx_l, 1))
+        zero = lambda t_: torch.zeros_like(t_)
+        d_h0s = torch.stack([dh[i] if dh[i] is not None else zero(sv["c0p"][0]) for i in range(L)])
+        d_c0s = torch.stack([dc[i] if dc[i] is not None else zero(sv["c0p"][0]) for i in range(L)])
+        d_upper = []
+        for i in range(1, L):
+            dg_all = torch.stack(dg_up[i - 1]).reshape(T * B, -1)
+            d_upper += [dg_all.t() @ flat(sv_up[i - 1]["cat"]), dg_all.sum(0)]
+        return (None, None, d_eg, d_w_fh, d_keys, d_memory, None, d_w_out, d_h0s, d_c0s, *d_upper)
+
+
 def _lstm_from_gates(igates, hgates, c):
     """LSTM cell from pre-computed input / hidden gate sums (biases included): torch's fused CUDA cell (one pointwise kernel,
     forward and backward), the gate formulas spelled out on the CPU (tests)."""
@@ -179,30 +317,24 @@ class PivotNMT(nn.Module):
         mask = torch.arange(memory.size(1), device=src.device)[None, :] >= src_len[:, None]
         feed = memory.new_zeros(src.size(1), self.dim)                                     # zero input feed :289-295
         keys = self.attn_in(memory)                                                        # "general" score h^T W m
-        outs = []
         tgt_emb = self.tgt_lut(tgt[:-1])
-        # Kernel-count savings of the per-token loop (it replays from a CUDA graph and is launch-bound): the word half of the
-        # first layer's input projection is one GEMM over all T steps; per step the input-feed half and the recurrent
-        # projection are ONE GEMM over [feed | h0]; the padding mask enters the scores as the additive term of baddbmm.
+        # The per-token loop replays from a CUDA graph and is launch-bound, so: the word half of the first layer's input
+        # projection is one GEMM over all T steps; per step the input-feed half and the recurrent projection are ONE GEMM
+        # over [feed | h0] (layers above: over [x | h_i]); the padding mask enters the scores as the additive term of
+        # baddbmm; and the loop runs under _InputFeedDecoderFn, whose backward pass keeps every weight gradient out of it.
         c0 = self.cells[0]
         e_gates = F.linear(tgt_emb, c0.weight_ih[:, :self.dim], c0.bias_ih + c0.bias_hh)   # (T-1, B, 4 dim)
-        w_fh = torch.cat([c0.weight_ih[:, self.dim:], c0.weight_hh], 1)                    # (4 dim, 2 dim): [feed | h0]
-        if torch.is_autocast_enabled():   # a non-leaf operand is re-cast by autocast at EVERY use (30 x 8 MB per step): cast once
-            w_fh = w_fh.to(torch.get_autocast_dtype("cuda"))
-        neg = torch.zeros(mask.shape, dtype=keys.dtype, device=src.device).masked_fill(mask, float("-inf")).unsqueeze(2)
-        eg_steps = e_gates.unbind(0)
-        for t in range(tgt_emb.size(0)):                                                   # one step per token :209-262
-            hg = F.linear(torch.cat([feed, h[0]], 1), w_fh)
-            h[0], c[0] = _lstm_from_gates(eg_steps[t], hg.to(e_gates.dtype), c[0].to(e_gates.dtype))
-            x = h[0]
-            for i in range(1, self.layers):
-                x = self.drop(x)
-                h[i], c[i] = self.cells[i](x, (h[i], c[i]))
-                x = h[i]
-            score = torch.baddbmm(neg, keys, x.unsqueeze(2).to(keys.dtype)).squeeze(2)
-            ctx = torch.bmm(F.softmax(score, 1).unsqueeze(1).to(memory.dtype), memory).squeeze(1)
-            feed = self.drop(torch.tanh(self.attn_out(torch.cat([ctx, x.to(ctx.dtype)], 1))))
-            outs.append(feed)
+        dt = e_gates.dtype                                                                 # compute dtype (bf16 under autocast)
+        w_fh = torch.cat([c0.weight_ih[:, self.dim:], c0.weight_hh], 1).to(dt)             # (4 dim, 2 dim): [feed | h0]
+        upper = []
+        for i in range(1, self.layers):
+            ci = self.cells[i]
+            upper += [torch.cat([ci.weight_ih, ci.weight_hh], 1).to(dt), (ci.bias_ih + ci.bias_hh).to(dt)]
+        neg = torch.zeros(mask.shape, dtype=dt, device=src.device).masked_fill(mask, float("-inf"))
+        with torch.autocast(src.device.type, enabled=False):
+            feeds = _InputFeedDecoderFn.apply(float(self.drop.p), self.training, e_gates, w_fh, keys.to(dt), memory.to(dt).contiguous(), neg,
+                                              self.attn_out.weight.to(dt), torch.stack(h).to(dt), torch.stack(c).to(dt), *upper)
+        outs = feeds.unbind(0)
         logp = F.log_softmax(self.generator(torch.stack(outs)), -1)
         gold = tgt[1:]
         nll = F.nll_loss(logp.view(-1, logp.size(-1)), gold.reshape(-1), ignore_index=PAD, reduction="sum")
