@@ -26,8 +26,9 @@ PAD, BOS, EOS = 0, 2, 3   # misc/constants.py:2-5
 
 
 class MaskedBiLSTM(nn.Module):
-    """nn.LSTM(bidirectional=True) over padded (S, B, D) input with per-row lengths, computed step by step with frozen
-    states past a row's end: same outputs (zeros at padded positions) and final states as the packed cuDNN call, but with no
+    """nn.LSTM(bidirectional=True) over padded (S, B, D) input with per-row lengths, computed step by step on sequences
+    left-aligned per direction (the states after a row's last valid step are gathered, what the extra steps compute is
+    never read): same outputs (zeros at padded positions) and final states as the packed cuDNN call, but with no
     host-side lengths -- the loop is identical for every batch of the same (S, B), so it can live in a CUDA graph.
     Holds an nn.LSTM for its parameters (state_dict compatible with the reference's encoder.rnn)."""
 
@@ -36,38 +37,42 @@ class MaskedBiLSTM(nn.Module):
         self.rnn = nn.LSTM(input_size, hidden_size, num_layers=num_layers, dropout=dropout, bidirectional=True)
         self.hidden_size, self.num_layers, self.dropout = hidden_size, num_layers, dropout
 
-    def _layer(self, x, keep, layer):
+    def _layer(self, x, rev_idx, layer):
         """One bidirectional layer over padded (S, B, D) input.  The captured step is bound by its NUMBER of kernels, so
         (i) the input projections of all time steps and BOTH directions are one GEMM, (ii) the two directions advance
-        together -- step s handles position s forward and S-1-s backward: one batched matmul with the two recurrent
-        weights and one fused cell over 2B rows -- and (iii) only the backward direction is masked per step (its state
-        must stay zero until its sentence starts); the forward direction runs unmasked past a row's end: its outputs
-        there are zeroed once afterwards and its final state is gathered at position len-1.  4 kernels per step where
-        the per-direction torch LSTM cell + freezing `where`s took 12."""
+        together -- one batched matmul with the two recurrent weights and one fused cell over 2B rows per step -- and
+        (iii) nothing is masked per step: the backward direction's inputs are gathered so that row b's sentence runs
+        len_b-1 .. 0 over the steps 0 .. len_b-1 (left-aligned like the forward one), both directions run unmasked past a
+        row's end, and the caller zeroes / re-orders the outputs once.  2 kernels per step where the per-direction torch
+        LSTM cell + freezing `where`s took 12."""
         rnn, Hh = self.rnn, self.hidden_size
         S, B, _ = x.shape
         p = lambda name, rev: getattr(rnn, f"{name}_l{layer}" + ("_reverse" if rev else ""))
         w_ih = torch.cat([p("weight_ih", False), p("weight_ih", True)], 0)                    # (8 Hh, D)
         bias = torch.cat([p("bias_ih", False) + p("bias_hh", False), p("bias_ih", True) + p("bias_hh", True)], 0)
         xw = F.linear(x, w_ih, bias).view(S, B, 2, 4 * Hh)
-        ig = torch.stack([xw[:, :, 0], xw[:, :, 1].flip(0)], 1)                               # (S, 2, B, 4 Hh): backward time-flipped
+        xw_rev = xw[:, :, 1].gather(0, rev_idx.expand(S, B, 4 * Hh))                          # step s of row b = position len_b-1-s
+        ig = torch.stack([xw[:, :, 0], xw_rev], 1)                                            # (S, 2, B, 4 Hh)
         w_hh = torch.stack([p("weight_hh", False).t(), p("weight_hh", True).t()], 0).to(ig.dtype)   # (2, Hh, 4 Hh)
-        return _BiLstmLayerFn.apply(ig.reshape(S, 2 * B, 4 * Hh), w_hh, keep.to(ig.dtype))       # (S, 2, B, Hh) each
+        return _BiLstmLayerFn.apply(ig.reshape(S, 2 * B, 4 * Hh), w_hh)                       # (S, 2, B, Hh) each
 
     def forward(self, x, lengths):
         """x (S, B, D); lengths (B,) on x's device.  Returns memory (S, B, 2 hidden), (h_n, c_n) each (2 layers, B, hidden)."""
         S, B = x.size(0), x.size(1)
-        valid = (torch.arange(S, device=x.device)[:, None] < lengths[None, :]).unsqueeze(2)    # (S, B, 1)
-        keep = torch.stack([torch.ones_like(valid), valid.flip(0)], 1)                         # (S, 2, B, 1)
+        steps = torch.arange(S, device=x.device)[:, None]
+        valid = (steps < lengths[None, :]).unsqueeze(2)                                        # (S, B, 1)
+        rev_idx = (lengths[None, :] - 1 - steps).clamp_min(0).unsqueeze(2)                     # (S, B, 1): an involution on a row's valid steps
         last = (lengths - 1).clamp_min(0).view(1, B, 1)
         h_n, c_n = [], []
         for layer in range(self.num_layers):
-            hs, cs = self._layer(x, keep, layer)
-            idx = last.expand(1, B, hs.size(3))
-            # final states: forward = the state at a row's last valid position, backward = the state after the last step
-            h_n += [hs[:, 0].gather(0, idx).squeeze(0), hs[S - 1, 1]]
-            c_n += [cs[:, 0].gather(0, idx).squeeze(0), cs[S - 1, 1]]
-            x = torch.cat([hs[:, 0] * valid.to(hs.dtype), hs[:, 1].flip(0)], 2)
+            hs, cs = self._layer(x, rev_idx, layer)
+            Hh = hs.size(3)
+            idx = last.expand(1, B, Hh)
+            # final states of both directions: the state after a row's last valid step
+            h_n += [hs[:, 0].gather(0, idx).squeeze(0), hs[:, 1].gather(0, idx).squeeze(0)]
+            c_n += [cs[:, 0].gather(0, idx).squeeze(0), cs[:, 1].gather(0, idx).squeeze(0)]
+            bw = hs[:, 1].gather(0, rev_idx.expand(S, B, Hh))                                  # back to position order
+            x = torch.cat([hs[:, 0], bw], 2) * valid.to(hs.dtype)
             if layer + 1 < self.num_layers and self.dropout > 0:
                 x = F.dropout(x, self.dropout, self.training)
         return x, (torch.stack(h_n), torch.stack(c_n))
@@ -75,73 +80,52 @@ class MaskedBiLSTM(nn.Module):
 
 class _BiLstmLayerFn(torch.autograd.Function):
     """The recurrence of one bidirectional layer (both directions per step, MaskedBiLSTM._layer) with a hand-written backward
-    pass: autograd's per-step bookkeeping (a weight-gradient matmul + accumulation add per step, fan-out adds, mask
-    multiplies and their gradients) was ~10 kernels per step; here the backward step is mask, fused cell backward, one batched
-    matmul for the state gradient, and the recurrent weights' gradient is ONE batched matmul over all S steps at the end.
-    ig (S, 2B, 4Hh) input gate sums (biases included), w_hh (2, Hh, 4Hh), keep (S, 2, B, 1); returns h, c (S, 2, B, Hh)."""
+    pass: autograd's per-step bookkeeping (a weight-gradient matmul + accumulation add per step, fan-out adds) was ~10
+    kernels per step; here the backward step is the fused cell backward and one batched matmul for the state gradient, and
+    the recurrent weights' gradient is ONE batched matmul over all S steps at the end.  No masks: both directions arrive
+    LEFT-aligned (a row's sentence occupies steps 0 .. len-1 of its direction), so the steps past a row's end compute
+    garbage that nothing reads.  ig (S, 2B, 4Hh) input gate sums (biases included), w_hh (2, Hh, 4Hh); returns the states
+    after every step, h and c (S, 2, B, Hh)."""
 
     @staticmethod
-    def forward(ctx, ig, w_hh, keep):
+    def forward(ctx, ig, w_hh):
         S, B2, G = ig.shape
         B, Hh = B2 // 2, w_hh.size(1)
         h = ig.new_zeros(2, B, Hh)
-        c = ig.new_zeros(2, B, Hh)
-        hs, cs, h_prev, c_prev, c_new_l, work = [], [], [], [], [], []
-        fused = ig.is_cuda
-        ig_s, keep_s = ig.unbind(0), keep.unbind(0)
+        c = ig.new_zeros(B2, Hh)
+        hs, cs, work = [], [], []
+        ig_s = ig.unbind(0)
         for s in range(S):
-            hg = torch.bmm(h, w_hh).view(B2, G)
-            h_prev.append(h)
-            c_prev.append(c)
-            if fused:
-                h_new, c_new, wk = torch.ops.aten._thnn_fused_lstm_cell(ig_s[s], hg, c.view(B2, Hh))
-            else:
-                i, f, g, o = (ig_s[s] + hg).chunk(4, 1)
-                i, f, g, o = torch.sigmoid(i), torch.sigmoid(f), torch.tanh(g), torch.sigmoid(o)
-                c_new = f * c.view(B2, Hh) + i * g
-                h_new = o * torch.tanh(c_new)
-                wk = torch.stack([i, f, g, o])
-            c_new_l.append(c_new)
+            h_new, c_new, wk = _cell_fwd(ig_s[s], torch.bmm(h, w_hh).view(B2, G), c)
             work.append(wk)
-            h = h_new.view(2, B, Hh) * keep_s[s]
-            c = c_new.view(2, B, Hh) * keep_s[s]
+            h, c = h_new.view(2, B, Hh), c_new
             hs.append(h)
             cs.append(c)
-        ctx.fused = fused
-        ctx.save_for_backward(w_hh, keep, torch.stack(h_prev), torch.stack(c_prev), torch.stack(c_new_l), torch.stack(work))
-        return torch.stack(hs), torch.stack(cs)
+        hs, cs = torch.stack(hs), torch.stack(cs)                                              # (S, 2, B, Hh), (S, 2B, Hh)
+        ctx.save_for_backward(w_hh, hs, cs, torch.stack(work))
+        return hs, cs.view(S, 2, B, Hh)
 
     @staticmethod
     def backward(ctx, dhs, dcs):
-        w_hh, keep, h_prev, c_prev, c_new, work = ctx.saved_tensors
-        S, _, B, Hh = h_prev.shape
+        w_hh, hs, cs, work = ctx.saved_tensors
+        S, _, B, Hh = hs.shape
         B2, G = 2 * B, 4 * Hh
         w_t = w_hh.transpose(1, 2)
         dh_next = dc_next = None
         dgs = [None] * S
-        dhs_s, dcs_s, keep_s = dhs.unbind(0), dcs.unbind(0), keep.unbind(0)
+        dhs_s, dcs_s = dhs.reshape(S, B2, Hh).unbind(0), dcs.reshape(S, B2, Hh).unbind(0)
+        c0 = cs.new_zeros(B2, Hh)
         for s in range(S - 1, -1, -1):
             dh = dhs_s[s] if dh_next is None else dhs_s[s] + dh_next
             dc = dcs_s[s] if dc_next is None else dcs_s[s] + dc_next
-            dh_new = (dh * keep_s[s]).reshape(B2, Hh)
-            dc_new = (dc * keep_s[s]).reshape(B2, Hh)
-            if ctx.fused:
-                dg, dc_prev, _ = torch.ops.aten._thnn_fused_lstm_cell_backward_impl(dh_new, dc_new, c_prev[s].view(B2, Hh), c_new[s], work[s], False)
-            else:
-                i, f, g, o = work[s].unbind(0)
-                tc = torch.tanh(c_new[s])
-                do = dh_new * tc
-                dcn = dc_new + dh_new * o * (1 - tc * tc)
-                dg = torch.cat([dcn * g * i * (1 - i), dcn * c_prev[s].view(B2, Hh) * f * (1 - f), dcn * i * (1 - g * g), do * o * (1 - o)], 1)
-                dc_prev = dcn * f
+            dg, dc_next = _cell_bwd(dh, dc, cs[s - 1] if s > 0 else c0, cs[s], work[s])
             dgs[s] = dg
-            dh_next = torch.bmm(dg.view(2, B, G), w_t)
-            dc_next = dc_prev.view(2, B, Hh)
+            dh_next = torch.bmm(dg.view(2, B, G), w_t).view(B2, Hh)
         dig = torch.stack(dgs)                                                                 # (S, 2B, 4Hh)
-        # d w_hh[d] = sum over steps and rows of h_prev^T dgates: one batched matmul with K = S B
-        hp = h_prev.permute(1, 3, 0, 2).reshape(2, Hh, S * B)
-        dw = torch.bmm(hp, dig.view(S, 2, B, G).permute(1, 0, 2, 3).reshape(2, S * B, G))
-        return dig, dw.to(w_hh.dtype), None
+        # d w_hh[d] = sum over steps and rows of h_{s-1}^T dgates_s (h_{-1} = 0): one batched matmul with K = (S-1) B
+        hp = hs[:S - 1].permute(1, 3, 0, 2).reshape(2, Hh, (S - 1) * B)
+        dw = torch.bmm(hp, dig[1:].view(S - 1, 2, B, G).permute(1, 0, 2, 3).reshape(2, (S - 1) * B, G)) if S > 1 else torch.zeros_like(w_hh)
+        return dig, dw.to(w_hh.dtype)
 
 
 def _cell_fwd(ig, hg, c):
@@ -239,8 +223,7 @@ class _InputFeedDecoderFn(torch.autograd.Function):
             df = do_s[t] if d_feed is None else do_s[t] + d_feed
             if drop:
                 df = torch.ops.aten.native_dropout_backward(df, sv["mo"][t], scale)
-            y = sv["y"][t]
-            dy = df * (1 - y * y)
+            dy = torch.ops.aten.tanh_backward(df, sv["y"][t])
             dy_l[t] = dy
             dcat = dy @ w_out                                            # (B, 2d): [d ctx | d x]
             dcx, dx = dcat[:, :d], dcat[:, d:]
@@ -249,7 +232,7 @@ class _InputFeedDecoderFn(torch.autograd.Function):
             da = torch.bmm(memory, dcx.unsqueeze(2)).squeeze(2)         # (B, S)
             ds = torch.ops.aten._softmax_backward_data(da, a, 1, a.dtype)
             ds_l[t] = ds
-            dx = dx + torch.bmm(ds.unsqueeze(1), keys).squeeze(1)
+            dx = torch.baddbmm(dx.unsqueeze(1), ds.unsqueeze(1), keys).squeeze(1)
             for i in range(L - 1, 0, -1):
                 u = sv_up[i - 1]
                 dhi = dx if dh[i] is None else dx + dh[i]
