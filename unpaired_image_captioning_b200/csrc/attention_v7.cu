@@ -16,6 +16,8 @@
 
 namespace uic {
 
+// Compile-time knobs of the occupancy experiments recorded in profiles/r2_att_v7_experiments.txt (-DV7_SLOTS_N=2: 2-slot
+// rings, +1.5 %; -DV7_MIN_CTAS=3: an 80-register build, +29 % at equal occupancy).  The defaults are what ships.
 #ifndef V7_SLOTS_N
 #define V7_SLOTS_N 3
 #endif
