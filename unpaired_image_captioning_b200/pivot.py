@@ -111,16 +111,17 @@ class _BiLstmLayerFn(torch.autograd.Function):
         S, _, B, Hh = hs.shape
         B2, G = 2 * B, 4 * Hh
         w_t = w_hh.transpose(1, 2)
-        dh_next = dc_next = None
+        dc_next = None
         dgs = [None] * S
         dhs_s, dcs_s = dhs.reshape(S, B2, Hh).unbind(0), dcs.reshape(S, B2, Hh).unbind(0)
         c0 = cs.new_zeros(B2, Hh)
+        dh = dhs_s[S - 1]
         for s in range(S - 1, -1, -1):
-            dh = dhs_s[s] if dh_next is None else dhs_s[s] + dh_next
             dc = dcs_s[s] if dc_next is None else dcs_s[s] + dc_next
             dg, dc_next = _cell_bwd(dh, dc, cs[s - 1] if s > 0 else c0, cs[s], work[s])
             dgs[s] = dg
-            dh_next = torch.bmm(dg.view(2, B, G), w_t).view(B2, Hh)
+            if s > 0:   # gradient of the previous step's state: its own output gradient + what flows back through the recurrence
+                dh = torch.baddbmm(dhs_s[s - 1].view(2, B, Hh), dg.view(2, B, G), w_t).view(B2, Hh)
         dig = torch.stack(dgs)                                                                 # (S, 2B, 4Hh)
         # d w_hh[d] = sum over steps and rows of h_{s-1}^T dgates_s (h_{-1} = 0): one batched matmul with K = (S-1) B
         hp = hs[:S - 1].permute(1, 3, 0, 2).reshape(2, Hh, (S - 1) * B)
