@@ -537,17 +537,23 @@ static int launch_v7(AttParams& p, const AttPlan& pl, int n_img, int ctas, cudaS
                       V7_E_SLOTS * NB * ATT_BATCH * 4 + 3 * V7_SLOTS * 8 + 2 * V7_SLOTS * 4 + 1024;
   auto kern = att_step_fwd_v7_kernel<NB, CA, MT, AUX>;
   if (smem > 226 * 1024) return 1;
-  static bool attr_set = false;  // per instantiation
-  static int blocks_per_sm = 0;
-  static size_t smem_set = 0;
-  if (!attr_set || smem > smem_set) {
+  // Function attributes are per device: the opt-in shared-memory size and the occupancy it yields are cached per
+  // (instantiation, device), and refreshed when a call needs more shared memory than the cached setting.
+  constexpr int MAX_DEV = 64;
+  static int blocks_per_sm[MAX_DEV] = {};
+  static size_t smem_set[MAX_DEV] = {};
+  int dev = 0;
+  UIC_CUDA_OK(cudaGetDevice(&dev));
+  const int slot = dev >= 0 && dev < MAX_DEV ? dev : 0;
+  if (blocks_per_sm[slot] == 0 || smem > smem_set[slot] || dev >= MAX_DEV) {
+    int per = 0;
     UIC_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    UIC_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm, kern, ATT_THREADS, smem));
-    attr_set = true;
-    smem_set = smem;
+    UIC_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per, kern, ATT_THREADS, smem));
+    blocks_per_sm[slot] = per;
+    smem_set[slot] = smem;
   }
   if (query_only) {
-    *per_sm = blocks_per_sm;
+    *per_sm = blocks_per_sm[slot];
     return 0;
   }
   CUtensorMap tm;
